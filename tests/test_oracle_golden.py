@@ -1,0 +1,73 @@
+"""The oracle (oracle/vae_oracle.py) against the fixtures produced by the reference
+modules themselves (tests/golden/make_golden.py).  CPU only."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import vae_oracle as vo
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+CASES = ["cfgb_full_b4", "cfgb_small_b3", "cfgb_small_eval_b2"]
+
+
+def _run(name, dtype):
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    ps, bs, B, Z, H, L, train = [int(v) for v in g["meta"]]
+    P = vo.make_params(ps, dtype=np.float64, latent=Z, hidden=H, layers=L)
+    ids, onehot, eps = vo.make_batch(bs, B, latent=Z, dtype=np.float64)
+    P = {k: v.astype(dtype) for k, v in P.items()}
+    r = vo.config_b_step(P, onehot.astype(dtype), eps.astype(dtype), max_len=120, train=bool(train), layers=L)
+    return g, r
+
+
+def _check(g, r, pre, rtol_loss, rtol_grad):
+    assert abs(r["loss"] - g[pre + "loss"]) <= rtol_loss * abs(g[pre + "loss"])
+    assert abs(r["bce"] - g[pre + "bce"]) <= rtol_loss * abs(g[pre + "bce"])
+    # the f32 fixture's kl is (loss - bce) evaluated in fp32: budget it against |loss|
+    assert abs(r["kl"] - g[pre + "kl"]) <= rtol_loss * abs(g[pre + "kl"]) + (1e-12 if pre == "f64/" else 2e-7 * abs(g[pre + "loss"]))
+    np.testing.assert_allclose(r["mu"], g[pre + "mu"], rtol=rtol_grad, atol=rtol_grad)
+    np.testing.assert_allclose(r["probs"], g[pre + "probs"], rtol=rtol_grad, atol=rtol_grad)
+    for k, gr in r["grads"].items():
+        gn = float(g[f"{pre}gnorm/{k}"])
+        assert abs(np.sqrt((gr.astype(np.float64) ** 2).sum()) - gn) <= rtol_grad * gn + 1e-12, k
+        if f"{pre}gfull/{k}" in g:
+            ref = g[f"{pre}gfull/{k}"]
+            err = np.abs(gr - ref).max()
+        else:
+            ref = g[f"{pre}gval/{k}"]
+            err = np.abs(gr.reshape(-1)[g[f"{pre}gidx/{k}"]] - ref).max()
+        # error relative to the tensor's rms-scale
+        scale = gn / np.sqrt(gr.size) + 1e-30
+        assert err <= rtol_grad * max(scale, np.abs(ref).max()), (k, err, scale)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_oracle_f64_matches_reference_f64(name):
+    g, r = _run(name, np.float64)
+    _check(g, r, "f64/", 1e-12, 1e-9)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_oracle_f32_matches_reference(name):
+    g, r = _run(name, np.float32)
+    # fp32 oracle vs fp64 reference: the 1e-5 fp32-check-mode budget of north_star
+    _check(g, r, "f64/", 1e-5, 2e-4)
+    _check(g, r, "f32/", 1e-5, 4e-4)
+
+
+def test_make_batch_layout():
+    ids, onehot, eps = vo.make_batch(5, 7)
+    assert ids.shape == (7, 120) and ids.dtype == np.uint8
+    assert onehot.shape == (7, 120, 35) and (onehot.sum(-1) == 1).all()
+    assert (onehot.argmax(-1) == ids).all()
+    lens = (ids != 0).sum(1)
+    assert lens.min() >= 10 and lens.max() <= 110
+
+
+def test_greedy_matches_step_argmax():
+    P = vo.make_params(3, latent=8, hidden=16, layers=2)
+    ids, onehot, eps = vo.make_batch(4, 3, latent=8)
+    r = vo.config_b_step(P, onehot, eps, train=False, need_grads=False, layers=2)
+    dec, _ = vo.greedy_decode(P, r["mu"], layers=2)
+    assert (dec == r["argmax"]).all()
