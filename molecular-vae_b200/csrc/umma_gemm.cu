@@ -1,0 +1,382 @@
+// tcgen05 / TMA GEMM for sm_100a:   D[M,N] (+)= A * B  (+ bias[N]),  bf16 operands, fp32 accumulate in TMEM.
+//
+// One kernel family serves every dense contraction on the ELBO path that is not inside the
+// fused recurrence (GRU input projections over all timesteps, dX of those projections, the
+// K = B*T weight-gradient reductions, the vocabulary head):
+//   * A is [M,K] "K-major" (row-major, K contiguous) or [K,M] "MN-major" (M contiguous);
+//     same for B with N.  MN-major operands are what the weight-gradient GEMMs need
+//     (dW = dG^T * X contracts over the row index of both stored matrices) and are fed to
+//     the tensor core through transposing shared-memory descriptors -- nothing is transposed
+//     in HBM.
+//   * warp-specialised, persistent: warp 0 = TMA producer, warp 1 = single-thread tcgen05.mma
+//     issuer (+ TMEM allocator), warps 2..5 = epilogue (tcgen05.ld -> registers -> global).
+//     smem ring of STAGES {A 128x64, B BNx64} SWIZZLE_128B tiles, two TMEM accumulator
+//     buffers so the epilogue of unit i overlaps the main loop of unit i+1.
+//   * split-K work units (fp32 red.add epilogue) give the skinny wgrad GEMMs a full grid.
+#include "common.cuh"
+#include "umma_gemm.h"
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle row
+constexpr int UMMA_K = 16;
+constexpr int NUM_THREADS = 192;
+constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KiB
+
+template <int BN> struct Cfg {
+  static constexpr int B_STAGE_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 192) ? 5 : (BN == 128) ? 6 : 8;
+  static constexpr int TMEM_COLS = (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+struct KernelParams {
+  int M, N, K;
+  int slabA, slabB;
+  int splits;          // split-K factor (>=1)
+  int kb_per_split;    // BK-blocks per split
+  int tiles_m, tiles_n;
+  void* out;
+  long long ldc;
+  const float* bias;   // per-N, may be null
+  int out_bf16;        // 1: bf16 output, 0: fp32
+  int accumulate;      // fp32 only: D += result (plain RMW, or red.add when splits > 1)
+  int* err_flag;
+};
+
+__device__ __forceinline__ bool wait_bar(uint64_t* bar, uint32_t parity, int* err_flag) {
+  uint32_t spins = 0;
+  unsigned long long t0 = 0;
+  while (!ptx::mbar_try_wait(bar, parity)) {
+    if ((++spins & 0x3FF) == 0) {
+      unsigned long long now;
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 2000000000ull) {  // 2 s: report instead of hanging the device
+        if (err_flag) atomicExch(err_flag, 1);
+        return false;
+      }
+    }
+  }
+  return true;
+}
+
+template <int BN, int A_MN, int B_MN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const KernelParams p) {
+  using C = Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + C::STAGES * A_STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + C::STAGES;
+  uint64_t* tfull_bar = bars + 2 * C::STAGES;
+  uint64_t* tempty_bar = bars + 2 * C::STAGES + 2;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    ptx::tma_prefetch_desc(&tmA);
+    ptx::tma_prefetch_desc(&tmB);
+    for (int s = 0; s < C::STAGES; ++s) {
+      ptx::mbar_init(&full_bar[s], 1);
+      ptx::mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      ptx::mbar_init(&tfull_bar[a], 1);
+      ptx::mbar_init(&tempty_bar[a], 128);
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_holder, C::TMEM_COLS);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  const int kb_total = (p.K + BK - 1) / BK;
+  const int n_units = p.tiles_m * p.tiles_n * p.splits;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+        const int tile = unit / p.splits, split = unit - tile * p.splits;
+        const int m_blk = tile / p.tiles_n, n_blk = tile - m_blk * p.tiles_n;
+        const int kb0 = split * p.kb_per_split;
+        const int kb1 = min(kb_total, kb0 + p.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          if (!wait_bar(&empty_bar[s], ph ^ 1, p.err_flag)) goto done;
+          ptx::mbar_arrive_expect_tx(&full_bar[s], C::STAGE_BYTES);
+          uint8_t* a_dst = sA + s * A_STAGE_BYTES;
+          uint8_t* b_dst = sB + s * C::B_STAGE_BYTES;
+          if (A_MN) {
+#pragma unroll
+            for (int c = 0; c < BM / 64; ++c)
+              ptx::tma_load_3d(a_dst + c * 8192, &tmA, &full_bar[s], m_blk * BM + c * 64, kb * BK, p.slabA);
+          } else {
+            ptx::tma_load_3d(a_dst, &tmA, &full_bar[s], kb * BK, m_blk * BM, p.slabA);
+          }
+          if (B_MN) {
+#pragma unroll
+            for (int c = 0; c < BN / 64; ++c)
+              ptx::tma_load_3d(b_dst + c * 8192, &tmB, &full_bar[s], n_blk * BN + c * 64, kb * BK, p.slabB);
+          } else {
+            ptx::tma_load_3d(b_dst, &tmB, &full_bar[s], kb * BK, n_blk * BN, p.slabB);
+          }
+          if (++s == C::STAGES) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (one thread) =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = ptx::umma_idesc_bf16(BM, BN, A_MN, B_MN);
+      int s = 0;
+      uint32_t ph = 0;
+      int acc = 0;
+      uint32_t acc_ph = 0;
+      for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+        const int tile = unit / p.splits, split = unit - tile * p.splits;
+        const int kb0 = split * p.kb_per_split;
+        const int kb1 = min(kb_total, kb0 + p.kb_per_split);
+        if (kb0 >= kb1) continue;
+        if (!wait_bar(&tempty_bar[acc], acc_ph ^ 1, p.err_flag)) goto done;
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          if (!wait_bar(&full_bar[s], ph, p.err_flag)) goto done;
+          ptx::tc_fence_after();
+          const uint32_t a_addr = ptx::smem_u32(sA + s * A_STAGE_BYTES);
+          const uint32_t b_addr = ptx::smem_u32(sB + s * C::B_STAGE_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            // K-major SW128: 8-row groups 1024 B apart, advance 32 B per K=16 inside the swizzle row.
+            // MN-major SW128: 64-wide MN chunks 8192 B apart (LBO), 8-k-row groups 1024 B apart (SBO),
+            //                 advance two k-groups (2048 B) per K=16.
+            const uint64_t adesc = A_MN ? ptx::umma_smem_desc_sw128(a_addr + k * 2048, 8192, 1024)
+                                        : ptx::umma_smem_desc_sw128(a_addr + k * 32, 16, 1024);
+            const uint64_t bdesc = B_MN ? ptx::umma_smem_desc_sw128(b_addr + k * 2048, 8192, 1024)
+                                        : ptx::umma_smem_desc_sw128(b_addr + k * 32, 16, 1024);
+            ptx::umma_bf16(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          ptx::tc_commit(&empty_bar[s]);  // frees the smem slot once these MMAs have read it
+          if (++s == C::STAGES) { s = 0; ph ^= 1; }
+        }
+        ptx::tc_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
+        if (++acc == 2) { acc = 0; acc_ph ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue: TMEM -> registers -> global =====================
+    const int q = warp & 3;  // TMEM lane quarter this warp may touch
+    int acc = 0;
+    uint32_t acc_ph = 0;
+    for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+      const int tile = unit / p.splits, split = unit - tile * p.splits;
+      const int m_blk = tile / p.tiles_n, n_blk = tile - m_blk * p.tiles_n;
+      const int kb0 = split * p.kb_per_split;
+      const int kb1 = min(kb_total, kb0 + p.kb_per_split);
+      if (kb0 >= kb1) continue;
+      if (!wait_bar(&tfull_bar[acc], acc_ph, p.err_flag)) goto done;
+      ptx::tc_fence_after();
+      const int row = m_blk * BM + q * 32 + lane;
+      const bool row_ok = row < p.M;
+      const bool add_bias = p.bias != nullptr && split == 0;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t r[32];
+        ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + c0, r);
+        ptx::tmem_ld_wait();
+        const int col0 = n_blk * BN + c0;
+        if (row_ok && col0 < p.N) {
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          if (add_bias) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.N) v[j] += __ldg(p.bias + col0 + j);
+          }
+          const bool full = (col0 + 32 <= p.N);
+          if (p.out_bf16) {
+            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + (long long)row * p.ldc + col0;
+            if (full && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                uint4 pk;
+                __nv_bfloat162 b0 = __floats2bfloat162_rn(v[j + 0], v[j + 1]);
+                __nv_bfloat162 b1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
+                __nv_bfloat162 b2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]);
+                __nv_bfloat162 b3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
+                pk.x = *reinterpret_cast<uint32_t*>(&b0);
+                pk.y = *reinterpret_cast<uint32_t*>(&b1);
+                pk.z = *reinterpret_cast<uint32_t*>(&b2);
+                pk.w = *reinterpret_cast<uint32_t*>(&b3);
+                *reinterpret_cast<uint4*>(o + j) = pk;
+              }
+            } else {
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < p.N) o[j] = __float2bfloat16_rn(v[j]);
+            }
+          } else {
+            float* o = reinterpret_cast<float*>(p.out) + (long long)row * p.ldc + col0;
+            if (p.splits > 1) {
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < p.N) atomicAdd(o + j, v[j]);
+            } else if (full && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                float4 w = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                if (p.accumulate) {
+                  float4 old = *reinterpret_cast<float4*>(o + j);
+                  w.x += old.x; w.y += old.y; w.z += old.z; w.w += old.w;
+                }
+                *reinterpret_cast<float4*>(o + j) = w;
+              }
+            } else {
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < p.N) o[j] = p.accumulate ? o[j] + v[j] : v[j];
+            }
+          }
+        }
+      }
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(&tempty_bar[acc]);
+      if (++acc == 2) { acc = 0; acc_ph ^= 1; }
+    }
+  }
+done:
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+      qres != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = reinterpret_cast<PFN_encodeTiled>(p);
+  return fn;
+}
+
+// Build the 3-D tensor map of one bf16 operand.  K-major: dims {K, rows, slabs}, box {64, box_rows, 1}.
+// MN-major: dims {rows(MN), K, slabs}, box {64, 64, 1}.
+int make_map(CUtensorMap* map, const mvae_umma_operand& op, int box_rows) {
+  PFN_encodeTiled enc = get_encode_fn();
+  if (!enc) return MVAE_ERR_DRIVER;
+  cuuint64_t dims[3];
+  cuuint64_t strides[2];
+  cuuint32_t box[3];
+  cuuint32_t estr[3] = {1, 1, 1};
+  if (op.mn_major) {
+    dims[0] = (cuuint64_t)op.mn;
+    dims[1] = (cuuint64_t)op.k;
+    box[0] = 64; box[1] = 64; box[2] = 1;
+  } else {
+    dims[0] = (cuuint64_t)op.k;
+    dims[1] = (cuuint64_t)op.mn;
+    box[0] = 64; box[1] = (cuuint32_t)box_rows; box[2] = 1;
+  }
+  dims[2] = (cuuint64_t)(op.slabs > 0 ? op.slabs : 1);
+  strides[0] = (cuuint64_t)op.ld * 2;
+  strides[1] = (cuuint64_t)(op.slabs > 1 ? op.slab_stride : (long long)op.ld * (long long)dims[1]) * 2;
+  if ((reinterpret_cast<uintptr_t>(op.ptr) & 15) || (strides[0] & 15) || (strides[1] & 15)) return MVAE_ERR_INVALID;
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(op.ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? MVAE_OK : MVAE_ERR_DRIVER;
+}
+
+template <int BN, int A_MN, int B_MN>
+int launch_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const KernelParams& kp, int grid, cudaStream_t st) {
+  auto kern = umma_gemm_kernel<BN, A_MN, B_MN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    MVAE_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM_BYTES));
+    attr_set = true;
+  }
+  kern<<<grid, NUM_THREADS, Cfg<BN>::SMEM_BYTES, st>>>(tmA, tmB, kp);
+  MVAE_CUDA_CHECK(cudaGetLastError());
+  return MVAE_OK;
+}
+
+template <int BN>
+int launch_bn(int a_mn, int b_mn, const CUtensorMap& tmA, const CUtensorMap& tmB, const KernelParams& kp, int grid,
+              cudaStream_t st) {
+  if (!a_mn && !b_mn) return launch_t<BN, 0, 0>(tmA, tmB, kp, grid, st);
+  if (!a_mn && b_mn) return launch_t<BN, 0, 1>(tmA, tmB, kp, grid, st);
+  if (a_mn && !b_mn) return launch_t<BN, 1, 0>(tmA, tmB, kp, grid, st);
+  return launch_t<BN, 1, 1>(tmA, tmB, kp, grid, st);
+}
+
+int g_num_sms = 0;
+
+}  // namespace
+
+int mvae_umma_gemm(const mvae_umma_operand* A, const mvae_umma_operand* B, const mvae_umma_out* D, int M, int N, int K,
+                   int bn, int splits, int max_ctas, int* err_flag, cudaStream_t stream) {
+  if (!A || !B || !D || M <= 0 || N <= 0 || K <= 0) return MVAE_ERR_INVALID;
+  if (g_num_sms == 0) {
+    int dev = 0;
+    MVAE_CUDA_CHECK(cudaGetDevice(&dev));
+    MVAE_CUDA_CHECK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  if (bn == 0) bn = (N > 128) ? 256 : (N > 64 ? 128 : 64);
+  if (bn != 64 && bn != 128 && bn != 192 && bn != 256) return MVAE_ERR_INVALID;
+  if (splits < 1) splits = 1;
+  if (splits > 1 && (D->bf16 || D->bias)) return MVAE_ERR_INVALID;  // split-K reduces with fp32 red.add
+  if (D->bf16 && D->accumulate) return MVAE_ERR_INVALID;
+  KernelParams kp{};
+  kp.M = M; kp.N = N; kp.K = K;
+  kp.slabA = A->slab; kp.slabB = B->slab;
+  const int kb_total = ceil_div(K, BK);
+  if (splits > kb_total) splits = kb_total;
+  kp.kb_per_split = ceil_div(kb_total, splits);
+  kp.splits = ceil_div(kb_total, kp.kb_per_split);  // no empty splits
+  kp.tiles_m = ceil_div(M, BM);
+  kp.tiles_n = ceil_div(N, bn);
+  kp.out = D->ptr; kp.ldc = D->ld; kp.bias = D->bias; kp.out_bf16 = D->bf16; kp.accumulate = D->accumulate;
+  kp.err_flag = err_flag;
+  CUtensorMap tmA, tmB;
+  int rc = make_map(&tmA, *A, BM);
+  if (rc) return rc;
+  rc = make_map(&tmB, *B, bn);
+  if (rc) return rc;
+  const long long units = (long long)kp.tiles_m * kp.tiles_n * kp.splits;
+  int cap = max_ctas > 0 ? max_ctas : g_num_sms;
+  int grid = (int)(units < cap ? units : cap);
+  const int a_mn = A->mn_major, b_mn = B->mn_major;
+  switch (bn) {
+    case 64: return launch_bn<64>(a_mn, b_mn, tmA, tmB, kp, grid, stream);
+    case 128: return launch_bn<128>(a_mn, b_mn, tmA, tmB, kp, grid, stream);
+    case 192: return launch_bn<192>(a_mn, b_mn, tmA, tmB, kp, grid, stream);
+    default: return launch_bn<256>(a_mn, b_mn, tmA, tmB, kp, grid, stream);
+  }
+}

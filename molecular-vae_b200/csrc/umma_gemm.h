@@ -1,0 +1,28 @@
+// Internal host interface of the tcgen05 GEMM (umma_gemm.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+struct mvae_umma_operand {
+  const void* ptr;        // bf16, 16-byte aligned
+  int mn_major;           // 0: stored [mn][k] (k contiguous); 1: stored [k][mn] (mn contiguous)
+  long long mn;           // extent of the M (for A) or N (for B) dimension
+  long long k;            // extent of the contraction dimension
+  long long ld;           // elements between consecutive rows of the stored matrix
+  int slabs;              // number of 2-D slabs (third TMA dimension), >= 1
+  long long slab_stride;  // elements between slabs
+  int slab;               // which slab this call uses
+};
+
+struct mvae_umma_out {
+  void* ptr;          // fp32 or bf16 [M][ld]
+  long long ld;
+  int bf16;           // output element type
+  int accumulate;     // fp32 only: D += A*B
+  const float* bias;  // optional per-column bias (fp32)
+};
+
+// bn: 0 = auto, else 64/128/192/256.  splits: split-K factor (fp32 atomics epilogue when > 1; the
+// caller zeroes D or passes an existing value to accumulate onto).  max_ctas: 0 = #SMs.
+int mvae_umma_gemm(const mvae_umma_operand* A, const mvae_umma_operand* B, const mvae_umma_out* D, int M, int N, int K,
+                   int bn, int splits, int max_ctas, int* err_flag, cudaStream_t stream);
