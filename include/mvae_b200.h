@@ -1,0 +1,128 @@
+/* C ABI of the B200-native molecular-VAE ELBO hot path (libmvae_b200.so).
+ *
+ * The reference (aclyde11/molecular-VAE) has no FFI layer: its hot path sits directly behind
+ * torch.nn.Module.  These entry points are what a binding for that path attaches to;
+ * each names the reference code it replaces.  Plain pointers and sizes only, no torch types.  All
+ * pointers are DEVICE pointers unless stated; the caller owns every buffer including the workspace;
+ * nothing here allocates device memory or synchronises (except mvae_cfgb_read_error); all work is
+ * enqueued on the given stream of the current device.  Return value: 0 or a negative MVAE_ERR_* code
+ * (mvae_strerror).  There is no CPU fallback: without a B200 the calls fail with MVAE_ERR_CUDA.
+ */
+#ifndef MVAE_B200_H_
+#define MVAE_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* mvae_stream_t; /* == cudaStream_t */
+
+#define MVAE_OK 0
+#define MVAE_ERR_INVALID (-1)
+#define MVAE_ERR_WORKSPACE (-2)
+#define MVAE_ERR_CUDA (-3)
+#define MVAE_ERR_UNSUPPORTED (-4)
+#define MVAE_ERR_DRIVER (-5)
+
+#define MVAE_PREC_FP32 0 /* check mode: fp32 storage and CUDA-core fp32 FMA everywhere            */
+#define MVAE_PREC_BF16 1 /* bf16 activations/weights into tcgen05 tensor cores, fp32 accumulation  */
+
+const char* mvae_strerror(int rc);
+const char* mvae_last_cuda_error(void);
+/* number of kernels / memsets this library has enqueued since the last reset (bench.py gpu_launches) */
+long long mvae_launch_count(void);
+void mvae_reset_launch_count(void);
+
+/* ---- "Config B": the canonical conv / latent-Z / L x H GRU model -------------------------------
+ * models2d.py:8-52 (class VAE: encode / reparametrize / decode / forward) with the latent widened
+ * to `latent`, trained with loss_function of train.py:31-38.                                       */
+typedef struct mvae_cfgb_desc {
+  int32_t batch;     /* B molecules in this call                                                   */
+  int32_t seq_len;   /* T = 120: conv1 in-channels and GRU steps (models2d.py:12,42)                */
+  int32_t charset;   /* C = 35 (<= 64)                                                             */
+  int32_t latent;    /* Z = 292                                                                    */
+  int32_t hidden;    /* H = 501                                                                    */
+  int32_t layers;    /* L = 3 (1..4)                                                               */
+  int32_t fc0;       /* 435 (models2d.py:15)                                                       */
+  int32_t precision; /* MVAE_PREC_*                                                                */
+  int32_t train;     /* 1: z = mu + eps_scale*eps*exp(logvar/2); 0: z = mu (models2d.py:32-38)      */
+  float max_len;     /* multiplier of the BCE mean (script global `max_len`, train.py:35)          */
+  float eps_scale;   /* 1.0 for models2d.py:34-35; 1e-2 for models.py Lambda (models.py:85,92)      */
+} mvae_cfgb_desc;
+
+/* Parameter / gradient tensors are passed as HOST arrays of fp32 DEVICE pointers in state_dict order
+ * (SURVEY.md A.1), unpadded, row-major, exactly the reference's shapes:
+ *   0 conv1d1.weight (9,T,9)  1 conv1d1.bias  2 conv1d2.weight (9,9,9)  3 conv1d2.bias
+ *   4 conv1d3.weight (10,9,11) 5 conv1d3.bias 6 fc0.weight (fc0,10*(C-26)) 7 fc0.bias
+ *   8 fc11.weight (Z,fc0) 9 fc11.bias 10 fc12.weight 11 fc12.bias 12 fc2.weight (Z,Z) 13 fc2.bias
+ *   14+4l gru.weight_ih_l (3H,in)  15+4l gru.weight_hh_l (3H,H)  16+4l gru.bias_ih_l  17+4l gru.bias_hh_l
+ *   14+4L fc3.weight (C,H)  15+4L fc3.bias                                                         */
+#define MVAE_CFGB_NUM_PARAMS(layers) (16 + 4 * (layers))
+
+size_t mvae_cfgb_workspace_bytes(const mvae_cfgb_desc* d);
+
+/* Fused ELBO step: forward + loss + backward of one batch (replaces train.py:98-101 =
+ * model(data); loss_function(...); loss.backward()).  ids: u8 (B,T) character ids (the argmax of the
+ * reference's one-hot input, data_loader.py:26-31); eps: fp32 (B,Z) standard-normal draws (ignored when
+ * train == 0).  grads are OVERWRITTEN.  out_scalars (device, 4 floats): loss, max_len*BCE, KL (swapped
+ * form of train.py:36-37), number of molecules whose argmax reconstruction is exact (train.py:110-112).
+ * mu_out / logvar_out: optional fp32 (B,Z).                                                        */
+int mvae_cfgb_elbo_step(const mvae_cfgb_desc* d, const float* const* params, float* const* grads,
+                        const uint8_t* ids, const float* eps, float* out_scalars, float* mu_out,
+                        float* logvar_out, void* workspace, size_t workspace_bytes, mvae_stream_t stream);
+
+/* Same work captured once into a CUDA graph (all pointers must stay valid and fixed); launch replays it. */
+typedef struct mvae_graph mvae_graph;
+int mvae_cfgb_elbo_step_graph_create(const mvae_cfgb_desc* d, const float* const* params, float* const* grads,
+                                     const uint8_t* ids, const float* eps, float* out_scalars, float* mu_out,
+                                     float* logvar_out, void* workspace, size_t workspace_bytes,
+                                     mvae_graph** out_graph);
+int mvae_graph_launch(mvae_graph* g, mvae_stream_t stream);
+long long mvae_graph_num_kernel_nodes(const mvae_graph* g);
+void mvae_graph_destroy(mvae_graph* g);
+
+/* Drop-in forward of models2d.VAE.forward (models2d.py:49-52): probs fp32 (B,T,C) = softmax over the
+ * charset, mu, logvar fp32 (B,Z).  Leaves the activations needed by mvae_cfgb_backward in `workspace`. */
+int mvae_cfgb_forward(const mvae_cfgb_desc* d, const float* const* params, const uint8_t* ids, const float* eps,
+                      float* probs, float* mu, float* logvar, void* workspace, size_t workspace_bytes,
+                      mvae_stream_t stream);
+/* Backward of that forward for arbitrary upstream gradients (autograd of the reference module):
+ * dprobs (B,T,C), dmu, dlogvar (B,Z) fp32, any of them may be NULL (= zero).  grads are OVERWRITTEN.   */
+int mvae_cfgb_backward(const mvae_cfgb_desc* d, const float* const* params, float* const* grads, const uint8_t* ids,
+                       const float* eps, const float* dprobs, const float* dmu, const float* dlogvar, void* workspace,
+                       size_t workspace_bytes, mvae_stream_t stream);
+
+/* Greedy decode of fixed latents z fp32 (B,Z) (train.py:110 / train_sample.py:31-33 applied to the Config-B
+ * decoder, models2d.py:40-47): ids_out u8 (B,T) = argmax over the charset (ties -> lowest id);
+ * probs_out optional fp32 (B,T,C).                                                                  */
+int mvae_cfgb_decode_greedy(const mvae_cfgb_desc* d, const float* const* params, const float* z, uint8_t* ids_out,
+                            float* probs_out, void* workspace, size_t workspace_bytes, mvae_stream_t stream);
+
+/* featurizer.py:8-24 / data_loader.py:26-31 one-hot (rows, C) fp32 -> u8 ids; *not_onehot (device int) is
+ * set to 1 when a row is not exactly one-hot.                                                        */
+int mvae_onehot_to_ids(const float* onehot, long long rows, int charset, uint8_t* ids, int* not_onehot,
+                       mvae_stream_t stream);
+
+/* Device-side error flag of the last call that used `workspace` (tcgen05 pipeline watchdog).  Synchronises
+ * the stream.  Writes 0/1 to *flag (host).                                                            */
+int mvae_cfgb_read_error(const mvae_cfgb_desc* d, void* workspace, size_t workspace_bytes, int* flag,
+                         mvae_stream_t stream);
+
+/* ---- building blocks, exported for the parity tests ---------------------------------------------- */
+/* D[M,N] (+)= A*B (+bias[N]); bf16 operands on the tcgen05 path.  a_mn_major: A stored [K][M];
+ * b_mn_major: B stored [K][N] (else [N][K]).  out fp32 or bf16.                                       */
+int mvae_gemm_bf16(const void* A, long long lda, int a_mn_major, const void* B, long long ldb, int b_mn_major,
+                   void* D, long long ldd, int d_is_bf16, int accumulate, const float* bias, int M, int N, int K,
+                   int tile_n, int splits, int* err_flag, mvae_stream_t stream);
+/* fp32 CUDA-core GEMM with explicit strides: A(m,k)=A[m*sam+k*sak], B(k,n)=B[k*sbk+n*sbn].            */
+int mvae_sgemm(const float* A, long long sam, long long sak, const float* B, long long sbk, long long sbn, float* C,
+               long long ldc, int M, int N, int K, const float* bias, int act, int accumulate, int splits,
+               mvae_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MVAE_B200_H_ */

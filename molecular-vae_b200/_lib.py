@@ -1,0 +1,78 @@
+"""ctypes binding of libmvae_b200.so (the C ABI in include/mvae_b200.h).
+
+There is no CPU or PyTorch fallback: if the CUDA library is missing the import fails loudly, and every
+entry point raises when the library reports an error."""
+import ctypes
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libmvae_b200.so")
+
+PREC_FP32 = 0
+PREC_BF16 = 1
+
+
+class CfgBDesc(ctypes.Structure):
+    _fields_ = [
+        ("batch", ctypes.c_int32), ("seq_len", ctypes.c_int32), ("charset", ctypes.c_int32),
+        ("latent", ctypes.c_int32), ("hidden", ctypes.c_int32), ("layers", ctypes.c_int32),
+        ("fc0", ctypes.c_int32), ("precision", ctypes.c_int32), ("train", ctypes.c_int32),
+        ("max_len", ctypes.c_float), ("eps_scale", ctypes.c_float),
+    ]
+
+
+class MvaeError(RuntimeError):
+    pass
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a). molecular-vae_b200 has no CPU fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    vp, ll, i32 = ctypes.c_void_p, ctypes.c_longlong, ctypes.c_int
+    pp = ctypes.POINTER(ctypes.c_void_p)
+    dp = ctypes.POINTER(CfgBDesc)
+    sigs = {
+        "mvae_strerror": (ctypes.c_char_p, [i32]),
+        "mvae_last_cuda_error": (ctypes.c_char_p, []),
+        "mvae_launch_count": (ll, []),
+        "mvae_reset_launch_count": (None, []),
+        "mvae_cfgb_workspace_bytes": (ctypes.c_size_t, [dp]),
+        "mvae_cfgb_elbo_step": (i32, [dp, pp, pp, vp, vp, vp, vp, vp, vp, ctypes.c_size_t, vp]),
+        "mvae_cfgb_elbo_step_graph_create": (i32, [dp, pp, pp, vp, vp, vp, vp, vp, vp, ctypes.c_size_t,
+                                                   ctypes.POINTER(vp)]),
+        "mvae_graph_launch": (i32, [vp, vp]),
+        "mvae_graph_num_kernel_nodes": (ll, [vp]),
+        "mvae_graph_destroy": (None, [vp]),
+        "mvae_cfgb_forward": (i32, [dp, pp, vp, vp, vp, vp, vp, vp, ctypes.c_size_t, vp]),
+        "mvae_cfgb_backward": (i32, [dp, pp, pp, vp, vp, vp, vp, vp, vp, ctypes.c_size_t, vp]),
+        "mvae_cfgb_decode_greedy": (i32, [dp, pp, vp, vp, vp, vp, ctypes.c_size_t, vp]),
+        "mvae_onehot_to_ids": (i32, [vp, ll, i32, vp, vp, vp]),
+        "mvae_cfgb_read_error": (i32, [dp, vp, ctypes.c_size_t, ctypes.POINTER(i32), vp]),
+        "mvae_gemm_bf16": (i32, [vp, ll, i32, vp, ll, i32, vp, ll, i32, i32, vp, i32, i32, i32, i32, i32, vp, vp]),
+        "mvae_sgemm": (i32, [vp, ll, ll, vp, ll, ll, vp, ll, i32, i32, i32, vp, i32, i32, i32, vp]),
+    }
+    for name, (res, args) in sigs.items():
+        fn = getattr(lib, name)  # AttributeError here == header and library out of sync
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+lib = _load()
+EXPORTED = [
+    "mvae_strerror", "mvae_last_cuda_error", "mvae_launch_count", "mvae_reset_launch_count",
+    "mvae_cfgb_workspace_bytes", "mvae_cfgb_elbo_step", "mvae_cfgb_elbo_step_graph_create", "mvae_graph_launch",
+    "mvae_graph_num_kernel_nodes", "mvae_graph_destroy", "mvae_cfgb_forward", "mvae_cfgb_backward",
+    "mvae_cfgb_decode_greedy", "mvae_onehot_to_ids", "mvae_cfgb_read_error", "mvae_gemm_bf16", "mvae_sgemm",
+]
+
+
+def check(rc):
+    if rc != 0:
+        msg = lib.mvae_strerror(rc).decode()
+        if rc == -3:
+            msg += ": " + lib.mvae_last_cuda_error().decode()
+        raise MvaeError(f"libmvae_b200: {msg} (rc={rc})")

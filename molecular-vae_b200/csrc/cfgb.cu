@@ -1,0 +1,670 @@
+// Orchestration + C ABI of the Config-B ELBO step (models2d.py:8-52 + train.py:31-38) on one B200.
+//
+// HBM layout (all recurrent tensors are TIME-MAJOR so that step t of a layer is one contiguous
+// [Bp][Hp] matrix = one TMA slab; Bp = B rounded up to 128 rows, Hp = H rounded up to 64 columns,
+// pad rows/columns are exact zeros and stay zero through the recurrence):
+//   hs[l]   [(T+1)][Bp][Hp]   TA   hidden states, slab 0 = h0 = 0; slabs 1..T feed the next layer / head
+//   sv[l]   [T][Bp][4Hp]      TA   saved (r, z, n, W_hn h + b_hn) for BPTT
+//   gi_all  [T][Bp][3Hp]      TA   x_t W_ih^T + b_ih of the current layer (l >= 1); layer 0's projection
+//                                  is time-invariant (the Repeat(T) of models2d.py:42 is never built)
+//   dG      [T][Bp][4Hp]      TA   [da_n | da_r | da_z | da_n*r]: columns [0,3Hp) = dgi in (n,r,z) order,
+//                                  columns [Hp,4Hp) = dgh in (r,z,n) order -> both GEMM windows contiguous
+//   dX      [T][Bp][Hp]       TA   gradient flowing into a layer's outputs (from the head or the layer above)
+// TA = float in MVAE_PREC_FP32 (CUDA-core SGEMM everywhere) and bf16 in MVAE_PREC_BF16 (tcgen05 GEMMs,
+// fp32 accumulation, fp32 master copy of h across steps).
+#include <new>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/mvae_b200.h"
+#include "common.cuh"
+#include "simt_kernels.cuh"
+#include "umma_gemm.h"
+
+namespace {
+
+long long g_launches = 0;
+inline void count(int n = 1) { g_launches += n; }
+
+struct Dims {
+  int B, Bp, T, C, CP, Z, H, Hp, L, F0, FLAT, L1, L2, L3;
+  bool bf16, train;
+  float max_len, eps_scale;
+};
+
+int make_dims(const mvae_cfgb_desc* d, Dims* o) {
+  if (!d) return MVAE_ERR_INVALID;
+  if (d->batch <= 0 || d->seq_len <= 0 || d->seq_len > 255 || d->charset < 27 || d->charset > 64 || d->latent <= 0 ||
+      d->hidden <= 0 || d->layers < 1 || d->layers > 4 || d->fc0 <= 0)
+    return MVAE_ERR_INVALID;
+  if (d->precision != MVAE_PREC_FP32 && d->precision != MVAE_PREC_BF16) return MVAE_ERR_INVALID;
+  o->B = d->batch; o->Bp = round_up(d->batch, 128);
+  o->T = d->seq_len; o->C = d->charset; o->CP = 64;
+  o->Z = d->latent; o->H = d->hidden; o->Hp = round_up(d->hidden, 64); o->L = d->layers; o->F0 = d->fc0;
+  o->L1 = o->C - 8; o->L2 = o->L1 - 8; o->L3 = o->L2 - 10;
+  if (o->L3 <= 0) return MVAE_ERR_INVALID;
+  o->FLAT = 10 * o->L3;
+  o->bf16 = d->precision == MVAE_PREC_BF16;
+  o->train = d->train != 0;
+  o->max_len = d->max_len; o->eps_scale = d->eps_scale;
+  return MVAE_OK;
+}
+
+// ---- workspace carve-up ---------------------------------------------------------------------
+struct WS {
+  // control
+  int* err_flag; int* bad_input; double* bce_sum; double* kl_sum; int* hit_count;
+  // encoder / latent (fp32)
+  float *h1, *h2, *h3, *h4, *mu, *lv, *z, *zr, *dzr, *da5, *dz, *dmu, *dlv, *dh4, *dflat;
+  float* gi0;      // [Bp][3Hp]
+  float* dgi0sum;  // [Bp][3Hp]
+  // recurrent
+  void* hs[4]; void* sv[4];
+  void* gi_all; void* dG; void* dX;
+  float* gh;        // [Bp][3Hp]
+  float* h32[2];    // [Bp][Hp] fp32 master h (bf16 mode)
+  float* dh_carry;  // [Bp][Hp]
+  // head
+  float* logits;    // [T*Bp][CP]
+  void* dlogits;    // [T*Bp][CP] TA
+  // padded weights (TA) and biases (fp32)
+  void* Whh_p[4]; void* Wih_p[4]; void* Wih_nrz[4]; void* W3_p;
+  float* bih_p[4]; float* bhh_p[4]; float* b3_p;
+  // padded gradient staging (fp32)
+  float* dW_p;   // [3Hp][Hp]
+  float* dW3_p;  // [CP][Hp]
+  float* csum;   // [4Hp]
+  size_t total;
+};
+
+struct Carver {
+  uint8_t* base; size_t off;
+  template <typename T> T* take(size_t n) {
+    off = (off + 255) & ~size_t(255);
+    T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+    off += n * sizeof(T);
+    return p;
+  }
+};
+
+void carve(const Dims& d, void* base, WS* w) {
+  Carver c{reinterpret_cast<uint8_t*>(base), 0};
+  const size_t es = d.bf16 ? 2 : 4;
+  const size_t B = d.B, Bp = d.Bp, T = d.T, Hp = d.Hp;
+  w->err_flag = c.take<int>(1);
+  w->bad_input = c.take<int>(1);
+  w->bce_sum = c.take<double>(1);
+  w->kl_sum = c.take<double>(1);
+  w->hit_count = c.take<int>(B);
+  w->h1 = c.take<float>(B * 9 * d.L1);
+  w->h2 = c.take<float>(B * 9 * d.L2);
+  w->h3 = c.take<float>(B * d.FLAT);
+  w->h4 = c.take<float>(B * d.F0);
+  w->mu = c.take<float>(B * d.Z);
+  w->lv = c.take<float>(B * d.Z);
+  w->z = c.take<float>(B * d.Z);
+  w->zr = c.take<float>(B * d.Z);
+  w->dzr = c.take<float>(B * d.Z);
+  w->da5 = c.take<float>(B * d.Z);
+  w->dz = c.take<float>(B * d.Z);
+  w->dmu = c.take<float>(B * d.Z);
+  w->dlv = c.take<float>(B * d.Z);
+  w->dh4 = c.take<float>(B * d.F0);
+  w->dflat = c.take<float>(B * d.FLAT);
+  w->gi0 = c.take<float>(Bp * 3 * Hp);
+  w->dgi0sum = c.take<float>(Bp * 3 * Hp);
+  for (int l = 0; l < d.L; ++l) {
+    w->hs[l] = c.take<uint8_t>((T + 1) * Bp * Hp * es);
+    w->sv[l] = c.take<uint8_t>(T * Bp * 4 * Hp * es);
+  }
+  w->gi_all = c.take<uint8_t>(T * Bp * 3 * Hp * es);
+  w->dG = c.take<uint8_t>(T * Bp * 4 * Hp * es);
+  w->dX = c.take<uint8_t>(T * Bp * Hp * es);
+  w->gh = c.take<float>(Bp * 3 * Hp);
+  w->h32[0] = c.take<float>(Bp * Hp);
+  w->h32[1] = c.take<float>(Bp * Hp);
+  w->dh_carry = c.take<float>(Bp * Hp);
+  w->logits = c.take<float>(T * Bp * d.CP);
+  w->dlogits = c.take<uint8_t>(T * Bp * d.CP * es);
+  for (int l = 0; l < d.L; ++l) {
+    w->Whh_p[l] = c.take<uint8_t>(3 * Hp * Hp * es);
+    w->Wih_p[l] = c.take<uint8_t>(3 * Hp * Hp * es);
+    w->Wih_nrz[l] = c.take<uint8_t>(3 * Hp * Hp * es);
+    w->bih_p[l] = c.take<float>(3 * Hp);
+    w->bhh_p[l] = c.take<float>(3 * Hp);
+  }
+  w->W3_p = c.take<uint8_t>(d.CP * Hp * es);
+  w->b3_p = c.take<float>(d.CP);
+  w->dW_p = c.take<float>(3 * Hp * Hp);
+  w->dW3_p = c.take<float>(d.CP * Hp);
+  w->csum = c.take<float>(4 * Hp);
+  w->total = (c.off + 255) & ~size_t(255);
+}
+
+// parameter indices (state_dict order)
+enum { P_C1W = 0, P_C1B, P_C2W, P_C2B, P_C3W, P_C3B, P_FC0W, P_FC0B, P_FC11W, P_FC11B, P_FC12W, P_FC12B, P_FC2W, P_FC2B, P_GRU0 };
+inline int P_WIH(int l) { return P_GRU0 + 4 * l; }
+inline int P_WHH(int l) { return P_GRU0 + 4 * l + 1; }
+inline int P_BIH(int l) { return P_GRU0 + 4 * l + 2; }
+inline int P_BHH(int l) { return P_GRU0 + 4 * l + 3; }
+inline int P_FC3W(int L) { return P_GRU0 + 4 * L; }
+inline int P_FC3B(int L) { return P_GRU0 + 4 * L + 1; }
+
+#define RC(expr) do { int _rc = (expr); if (_rc != MVAE_OK) return _rc; } while (0)
+#define KCHECK() do { count(); MVAE_CUDA_CHECK(cudaGetLastError()); } while (0)
+
+inline int grid_for(long long n, int block = 256, int cap = 148 * 16) {
+  long long g = (n + block - 1) / block;
+  return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+inline int memset_async(void* p, size_t bytes, cudaStream_t st) {
+  count();
+  MVAE_CUDA_CHECK(cudaMemsetAsync(p, 0, bytes, st));
+  return MVAE_OK;
+}
+
+// ---- the GEMM dispatcher --------------------------------------------------------------------
+// out[M][N] (+)= A * B (+bias).  a_trans: A stored [K][M] (else [M][K]); b_kmajor: B stored [N][K] (else [K][N]).
+template <typename TA>
+int gemm(const Dims& d, const WS& w, cudaStream_t st, const TA* A, long long lda, bool a_trans, const TA* B,
+         long long ldb, bool b_kmajor, void* out, long long ldc, bool out_is_ta, int M, int N, int K, const float* bias,
+         bool accumulate, int splits, int bn = 0) {
+  count();
+  if constexpr (sizeof(TA) == 4) {
+    (void)out_is_ta; (void)bn; (void)d; (void)w;
+    return simt::sgemm(st, reinterpret_cast<const float*>(A), a_trans ? 1 : lda, a_trans ? lda : 1,
+                       reinterpret_cast<const float*>(B), b_kmajor ? 1 : ldb, b_kmajor ? ldb : 1,
+                       reinterpret_cast<float*>(out), ldc, M, N, K, bias, simt::ACT_NONE, accumulate ? 1 : 0, splits);
+  } else {
+    (void)d;
+    mvae_umma_operand a{A, a_trans ? 1 : 0, M, K, lda, 1, 0, 0};
+    mvae_umma_operand b{B, b_kmajor ? 0 : 1, N, K, ldb, 1, 0, 0};
+    mvae_umma_out o{out, ldc, out_is_ta ? 1 : 0, accumulate ? 1 : 0, bias};
+    return mvae_umma_gemm(&a, &b, &o, M, N, K, bn, splits, 0, w.err_flag, st);
+  }
+}
+
+inline int sg(cudaStream_t st, const float* A, long long sam, long long sak, const float* B, long long sbk,
+              long long sbn, float* C, long long ldc, int M, int N, int K, const float* bias, int act, int accumulate,
+              int splits = 1) {
+  count();
+  return simt::sgemm(st, A, sam, sak, B, sbk, sbn, C, ldc, M, N, K, bias, act, accumulate, splits);
+}
+// dW[M][N] = A^T B with the contraction over the batch rows: zero + split-K
+inline int sg_wgrad(cudaStream_t st, const float* A, long long sam, long long sak, const float* B, long long sbk,
+                    long long sbn, float* C, long long ldc, int M, int N, int K) {
+  // C rows are contiguous blocks of N only when ldc == N; zero row by row otherwise
+  if (ldc == N) RC(memset_async(C, (size_t)M * N * 4, st));
+  else {
+    count();
+    MVAE_CUDA_CHECK(cudaMemset2DAsync(C, ldc * 4, 0, (size_t)N * 4, M, st));
+  }
+  int splits = K >= 1024 ? 16 : (K >= 256 ? 4 : 1);
+  return sg(st, A, sam, sak, B, sbk, sbn, C, ldc, M, N, K, nullptr, simt::ACT_NONE, 1, splits);
+}
+
+__global__ void gate_bias_grads_kernel(const float* __restrict__ csum, int H, int Hp, float* __restrict__ db_ih,
+                                       float* __restrict__ db_hh) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 3 * H) return;
+  const int g = i / H, j = i - g * H;
+  // csum blocks: 0 = da_n, 1 = da_r, 2 = da_z, 3 = da_n*r
+  const int blk_ih = (g == 0) ? 1 : (g == 1 ? 2 : 0);
+  const int blk_hh = (g == 0) ? 1 : (g == 1 ? 2 : 3);
+  db_ih[i] = csum[blk_ih * Hp + j];
+  db_hh[i] = csum[blk_hh * Hp + j];
+}
+__global__ void copy_prefix_kernel(const float* __restrict__ src, float* __restrict__ dst, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[i];
+}
+
+// ---- weight preparation ---------------------------------------------------------------------
+template <typename TA>
+int prep_weights(const Dims& d, const WS& w, const float* const* P, cudaStream_t st, bool need_bwd) {
+  const int H = d.H, Hp = d.Hp;
+  const int g = grid_for(3ll * Hp * Hp);
+  for (int l = 0; l < d.L; ++l) {
+    simt::pad_gate_matrix_kernel<TA><<<g, 256, 0, st>>>(P[P_WHH(l)], H, H, (TA*)w.Whh_p[l], Hp, Hp, 0, 1, 2);
+    KCHECK();
+    if (l >= 1) {
+      simt::pad_gate_matrix_kernel<TA><<<g, 256, 0, st>>>(P[P_WIH(l)], H, H, (TA*)w.Wih_p[l], Hp, Hp, 0, 1, 2);
+      KCHECK();
+      if (need_bwd) {
+        simt::pad_gate_matrix_kernel<TA><<<g, 256, 0, st>>>(P[P_WIH(l)], H, H, (TA*)w.Wih_nrz[l], Hp, Hp, 2, 0, 1);
+        KCHECK();
+      }
+      simt::pad_gate_vector_kernel<<<ceil_div(3 * Hp, 256), 256, 0, st>>>(P[P_BIH(l)], H, w.bih_p[l], Hp);
+      KCHECK();
+    }
+    simt::pad_gate_vector_kernel<<<ceil_div(3 * Hp, 256), 256, 0, st>>>(P[P_BHH(l)], H, w.bhh_p[l], Hp);
+    KCHECK();
+  }
+  simt::pad_matrix_kernel<TA><<<grid_for((long long)d.CP * Hp), 256, 0, st>>>(P[P_FC3W(d.L)], d.C, H, (TA*)w.W3_p, d.CP, Hp);
+  KCHECK();
+  simt::pad_matrix_kernel<float><<<1, 64, 0, st>>>(P[P_FC3B(d.L)], 1, d.C, w.b3_p, 1, d.CP);
+  KCHECK();
+  return MVAE_OK;
+}
+
+// ---- forward --------------------------------------------------------------------------------
+// from_z: decode-only entry (z given in w.z); save: keep BPTT state
+template <typename TA>
+int run_forward(const Dims& d, const WS& w, const float* const* P, const uint8_t* ids, const float* eps,
+                cudaStream_t st, bool decode_only, bool save) {
+  const int B = d.B, Bp = d.Bp, T = d.T, Z = d.Z, H = d.H, Hp = d.Hp;
+  const size_t slab = (size_t)Bp * Hp;
+  RC(memset_async(w.err_flag, 4, st));
+  RC(memset_async(w.bce_sum, 8, st));
+  RC(memset_async(w.kl_sum, 8, st));
+  RC(memset_async(w.hit_count, (size_t)B * 4, st));
+  RC(memset_async(w.gi0, (size_t)Bp * 3 * Hp * 4, st));
+  for (int l = 0; l < d.L; ++l) RC(memset_async(w.hs[l], slab * sizeof(TA), st));
+  if (!decode_only) {
+    simt::ConvDims cd{T, d.C, d.L1, d.L2, d.L3};
+    const size_t smem = (729 + 990 + 9 * d.L1 + 9 * d.L2) * 4 + round_up(T, 4);
+    simt::enc_conv_fwd_kernel<<<min(B, 148 * 4), 256, smem, st>>>(ids, B, cd, P[P_C1W], P[P_C1B], P[P_C2W], P[P_C2B],
+                                                                   P[P_C3W], P[P_C3B], w.h1, w.h2, w.h3);
+    KCHECK();
+    // fc0 + SELU (models2d.py:28)
+    RC(sg(st, w.h3, d.FLAT, 1, P[P_FC0W], 1, d.FLAT, w.h4, d.F0, B, d.F0, d.FLAT, P[P_FC0B], simt::ACT_SELU, 0));
+    // fc11 / fc12 (models2d.py:29)
+    RC(sg(st, w.h4, d.F0, 1, P[P_FC11W], 1, d.F0, w.mu, Z, B, Z, d.F0, P[P_FC11B], simt::ACT_NONE, 0));
+    RC(sg(st, w.h4, d.F0, 1, P[P_FC12W], 1, d.F0, w.lv, Z, B, Z, d.F0, P[P_FC12B], simt::ACT_NONE, 0));
+    simt::reparam_kl_kernel<<<grid_for((long long)B * Z, 256, 592), 256, 0, st>>>(w.mu, w.lv, eps, d.eps_scale,
+                                                                                  d.train ? 1 : 0, (long long)B * Z,
+                                                                                  w.z, w.kl_sum);
+    KCHECK();
+  }
+  // fc2 + SELU (models2d.py:41); layer-0 input projection computed once per molecule
+  RC(sg(st, w.z, Z, 1, P[P_FC2W], 1, Z, w.zr, Z, B, Z, Z, P[P_FC2B], simt::ACT_SELU, 0));
+  for (int g = 0; g < 3; ++g)
+    RC(sg(st, w.zr, Z, 1, P[P_WIH(0)] + (size_t)g * H * Z, 1, Z, w.gi0 + (size_t)g * Hp, 3 * Hp, B, H, Z,
+          P[P_BIH(0)] + (size_t)g * H, simt::ACT_NONE, 0));
+  const int gate_grid = ceil_div(Bp * Hp, 256);
+  for (int l = 0; l < d.L; ++l) {
+    TA* hs = (TA*)w.hs[l];
+    TA* sv = (TA*)w.sv[l];
+    if (l >= 1) {
+      const TA* X = (const TA*)w.hs[l - 1] + slab;
+      RC(gemm<TA>(d, w, st, X, Hp, false, (const TA*)w.Wih_p[l], Hp, true, w.gi_all, 3 * Hp, true, T * Bp, 3 * Hp, Hp,
+                  w.bih_p[l], false, 1));
+    }
+    if (d.bf16) RC(memset_async(w.h32[0], slab * 4, st));
+    for (int t = 0; t < T; ++t) {
+      RC(gemm<TA>(d, w, st, hs + t * slab, Hp, false, (const TA*)w.Whh_p[l], Hp, true, w.gh, 3 * Hp, false, Bp, 3 * Hp,
+                  Hp, w.bhh_p[l], false, 1));
+      TA* svt = save ? sv + (size_t)t * Bp * 4 * Hp : nullptr;
+      float* hp32 = d.bf16 ? w.h32[t & 1] : nullptr;
+      float* hn32 = d.bf16 ? w.h32[(t + 1) & 1] : nullptr;
+      if (l == 0)
+        simt::gru_gate_fwd_kernel<TA, float><<<gate_grid, 256, 0, st>>>(w.gi0, w.gh, hp32, hs + t * slab,
+                                                                        hs + (t + 1) * slab, hn32, svt, Bp, Hp);
+      else
+        simt::gru_gate_fwd_kernel<TA, TA><<<gate_grid, 256, 0, st>>>((const TA*)w.gi_all + (size_t)t * Bp * 3 * Hp,
+                                                                     w.gh, hp32, hs + t * slab, hs + (t + 1) * slab,
+                                                                     hn32, svt, Bp, Hp);
+      KCHECK();
+    }
+  }
+  // vocabulary head logits (models2d.py:44-45)
+  const TA* top = (const TA*)w.hs[d.L - 1] + slab;
+  RC(gemm<TA>(d, w, st, top, Hp, false, (const TA*)w.W3_p, Hp, true, w.logits, d.CP, false, T * Bp, d.CP, Hp, w.b3_p,
+              false, 1, 64));
+  return MVAE_OK;
+}
+
+// ---- backward -------------------------------------------------------------------------------
+// expects w.dlogits filled.  kl_internal: add the swapped-KL gradient; ext_dmu/ext_dlv optional.
+template <typename TA>
+int run_backward(const Dims& d, const WS& w, const float* const* P, float* const* G, const uint8_t* ids,
+                 const float* eps, cudaStream_t st, bool kl_internal, const float* ext_dmu, const float* ext_dlv) {
+  const int B = d.B, Bp = d.Bp, T = d.T, Z = d.Z, H = d.H, Hp = d.Hp, CP = d.CP, L = d.L;
+  const size_t slab = (size_t)Bp * Hp;
+  const int TB = T * Bp;
+  const int wsplits = d.bf16 ? max(1, min(64, (148 * 2) / (ceil_div(3 * Hp, 128) * ceil_div(Hp, 256)))) : 64;
+  const TA* dlog = (const TA*)w.dlogits;
+  // head: dX = dlogits * W3 ; dW3 = dlogits^T * h_top ; db3 = colsum(dlogits)
+  RC(gemm<TA>(d, w, st, dlog, CP, false, (const TA*)w.W3_p, Hp, false, w.dX, Hp, true, TB, Hp, CP, nullptr, false, 1));
+  RC(memset_async(w.dW3_p, (size_t)CP * Hp * 4, st));
+  RC(gemm<TA>(d, w, st, dlog, CP, true, (const TA*)w.hs[L - 1] + slab, Hp, false, w.dW3_p, Hp, false, CP, Hp, TB,
+              nullptr, true, d.bf16 ? 148 : 64, 256));
+  simt::unpad_matrix_kernel<<<grid_for((long long)d.C * H), 256, 0, st>>>(w.dW3_p, Hp, G[P_FC3W(L)], d.C, H);
+  KCHECK();
+  RC(memset_async(w.csum, (size_t)4 * Hp * 4, st));
+  RC(simt::colsum<TA>(st, dlog, TB, CP, CP, w.csum)); count();
+  copy_prefix_kernel<<<1, 64, 0, st>>>(w.csum, G[P_FC3B(L)], d.C);
+  KCHECK();
+
+  const int gate_grid = ceil_div(Bp * Hp, 256);
+  for (int l = L - 1; l >= 0; --l) {
+    const TA* hs = (const TA*)w.hs[l];
+    const TA* sv = (const TA*)w.sv[l];
+    TA* dG = (TA*)w.dG;
+    TA* dX = (TA*)w.dX;
+    RC(memset_async(w.dh_carry, slab * 4, st));
+    if (l == 0) RC(memset_async(w.dgi0sum, (size_t)Bp * 3 * Hp * 4, st));
+    for (int t = T - 1; t >= 0; --t) {
+      TA* dGt = dG + (size_t)t * Bp * 4 * Hp;
+      simt::gru_gate_bwd_kernel<TA><<<gate_grid, 256, 0, st>>>(sv + (size_t)t * Bp * 4 * Hp, hs + t * slab,
+                                                               dX + t * slab, w.dh_carry, dGt,
+                                                               l == 0 ? w.dgi0sum : nullptr, Bp, Hp);
+      KCHECK();
+      if (t > 0)  // dh_{t-1} += dgh_t * W_hh
+        RC(gemm<TA>(d, w, st, dGt + Hp, 4 * Hp, false, (const TA*)w.Whh_p[l], Hp, false, w.dh_carry, Hp, false, Bp, Hp,
+                    3 * Hp, nullptr, true, 1));
+    }
+    // dW_hh = dgh^T * h_{t-1}   (K = T*Bp)
+    RC(memset_async(w.dW_p, (size_t)3 * Hp * Hp * 4, st));
+    RC(gemm<TA>(d, w, st, dG + Hp, 4 * Hp, true, hs, Hp, false, w.dW_p, Hp, false, 3 * Hp, Hp, TB, nullptr, true,
+                wsplits, 256));
+    simt::unpad_gate_matrix_kernel<<<grid_for(3ll * H * H), 256, 0, st>>>(w.dW_p, Hp, Hp, G[P_WHH(l)], H, H, 0, 1, 2);
+    KCHECK();
+    // bias grads from the column sums of dG
+    RC(memset_async(w.csum, (size_t)4 * Hp * 4, st));
+    RC(simt::colsum<TA>(st, dG, TB, 4 * Hp, 4 * Hp, w.csum)); count();
+    gate_bias_grads_kernel<<<ceil_div(3 * H, 256), 256, 0, st>>>(w.csum, H, Hp, G[P_BIH(l)], G[P_BHH(l)]);
+    KCHECK();
+    if (l >= 1) {
+      const TA* X = (const TA*)w.hs[l - 1] + slab;
+      RC(memset_async(w.dW_p, (size_t)3 * Hp * Hp * 4, st));
+      RC(gemm<TA>(d, w, st, dG, 4 * Hp, true, X, Hp, false, w.dW_p, Hp, false, 3 * Hp, Hp, TB, nullptr, true, wsplits,
+                  256));
+      simt::unpad_gate_matrix_kernel<<<grid_for(3ll * H * H), 256, 0, st>>>(w.dW_p, Hp, Hp, G[P_WIH(l)], H, H, 2, 0, 1);
+      KCHECK();
+      // gradient into the layer below: dX = dgi * W_ih
+      RC(gemm<TA>(d, w, st, dG, 4 * Hp, false, (const TA*)w.Wih_nrz[l], Hp, false, w.dX, Hp, true, TB, Hp, 3 * Hp,
+                  nullptr, false, 1));
+    } else {
+      // time-invariant layer-0 input: dW_ih0 = (sum_t dgi)^T zr ; dzr = (sum_t dgi) W_ih0
+      for (int g = 0; g < 3; ++g) {
+        RC(sg_wgrad(st, w.dgi0sum + (size_t)g * Hp, 1, 3 * Hp, w.zr, Z, 1, G[P_WIH(0)] + (size_t)g * H * Z, Z, H, Z, B));
+        RC(sg(st, w.dgi0sum + (size_t)g * Hp, 3 * Hp, 1, P[P_WIH(0)] + (size_t)g * H * Z, Z, 1, w.dzr, Z, B, Z, H,
+              nullptr, simt::ACT_NONE, g > 0 ? 1 : 0));
+      }
+    }
+  }
+  // fc2 (+SELU)
+  const long long nBZ = (long long)B * Z;
+  simt::selu_bwd_kernel<<<grid_for(nBZ), 256, 0, st>>>(w.zr, w.dzr, w.da5, nBZ);
+  KCHECK();
+  RC(sg_wgrad(st, w.da5, 1, Z, w.z, Z, 1, G[P_FC2W], Z, Z, Z, B));
+  RC(memset_async(G[P_FC2B], (size_t)Z * 4, st));
+  RC(simt::colsum<float>(st, w.da5, B, Z, Z, G[P_FC2B])); count();
+  RC(sg(st, w.da5, Z, 1, P[P_FC2W], Z, 1, w.dz, Z, B, Z, Z, nullptr, simt::ACT_NONE, 0));
+  // reparametrisation + KL
+  simt::reparam_kl_bwd_kernel<<<grid_for(nBZ), 256, 0, st>>>(w.mu, w.lv, eps, d.eps_scale, d.train ? 1 : 0, w.dz,
+                                                            kl_internal ? 1.0f / (float)nBZ : 0.f, ext_dmu, ext_dlv,
+                                                            nBZ, w.dmu, w.dlv);
+  KCHECK();
+  // fc11 / fc12
+  RC(sg_wgrad(st, w.dmu, 1, Z, w.h4, d.F0, 1, G[P_FC11W], d.F0, Z, d.F0, B));
+  RC(sg_wgrad(st, w.dlv, 1, Z, w.h4, d.F0, 1, G[P_FC12W], d.F0, Z, d.F0, B));
+  RC(memset_async(G[P_FC11B], (size_t)Z * 4, st));
+  RC(simt::colsum<float>(st, w.dmu, B, Z, Z, G[P_FC11B])); count();
+  RC(memset_async(G[P_FC12B], (size_t)Z * 4, st));
+  RC(simt::colsum<float>(st, w.dlv, B, Z, Z, G[P_FC12B])); count();
+  RC(sg(st, w.dmu, Z, 1, P[P_FC11W], d.F0, 1, w.dh4, d.F0, B, d.F0, Z, nullptr, simt::ACT_NONE, 0));
+  RC(sg(st, w.dlv, Z, 1, P[P_FC12W], d.F0, 1, w.dh4, d.F0, B, d.F0, Z, nullptr, simt::ACT_NONE, 1));
+  const long long nBF = (long long)B * d.F0;
+  simt::selu_bwd_kernel<<<grid_for(nBF), 256, 0, st>>>(w.h4, w.dh4, w.dh4, nBF);
+  KCHECK();
+  // fc0
+  RC(sg_wgrad(st, w.dh4, 1, d.F0, w.h3, d.FLAT, 1, G[P_FC0W], d.FLAT, d.F0, d.FLAT, B));
+  RC(memset_async(G[P_FC0B], (size_t)d.F0 * 4, st));
+  RC(simt::colsum<float>(st, w.dh4, B, d.F0, d.F0, G[P_FC0B])); count();
+  RC(sg(st, w.dh4, d.F0, 1, P[P_FC0W], d.FLAT, 1, w.dflat, d.FLAT, B, d.FLAT, d.F0, nullptr, simt::ACT_NONE, 0));
+  // convs
+  RC(memset_async(G[P_C1W], (size_t)9 * T * 9 * 4, st));
+  RC(memset_async(G[P_C1B], 9 * 4, st));
+  RC(memset_async(G[P_C2W], 729 * 4, st));
+  RC(memset_async(G[P_C2B], 9 * 4, st));
+  RC(memset_async(G[P_C3W], 990 * 4, st));
+  RC(memset_async(G[P_C3B], 10 * 4, st));
+  {
+    simt::ConvDims cd{T, d.C, d.L1, d.L2, d.L3};
+    const size_t smem = (size_t)(9 * T * 9 + 729 + 990 + 32 + 729 + 990 + 9 * d.L1 + 9 * d.L2 + 10 * d.L3 + 9 * d.L2 +
+                                 9 * d.L1) * 4 + round_up(T, 4);
+    static bool attr = false;
+    if (!attr) {
+      MVAE_CUDA_CHECK(cudaFuncSetAttribute(simt::enc_conv_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+      attr = true;
+    }
+    if (smem > 100 * 1024) return MVAE_ERR_UNSUPPORTED;
+    simt::enc_conv_bwd_kernel<<<min(B, 148 * 2), 256, smem, st>>>(ids, B, cd, P[P_C2W], P[P_C3W], w.h1, w.h2, w.h3,
+                                                                   w.dflat, G[P_C1W], G[P_C1B], G[P_C2W], G[P_C2B],
+                                                                   G[P_C3W], G[P_C3B]);
+    KCHECK();
+  }
+  return MVAE_OK;
+}
+
+template <typename TA>
+int head_fused(const Dims& d, const WS& w, const uint8_t* ids, float* probs, bool want_dlogits, cudaStream_t st) {
+  const long long rows = (long long)d.T * d.Bp;
+  const float gscale = d.max_len / ((float)d.B * (float)d.T * (float)d.C);
+  simt::head_softmax_bce_kernel<TA><<<(unsigned)ceil_div64(rows * 32, 256), 256, 0, st>>>(
+      w.logits, d.CP, d.C, ids, d.B, d.Bp, d.T, gscale, want_dlogits ? (TA*)w.dlogits : nullptr, probs, w.bce_sum,
+      w.hit_count);
+  KCHECK();
+  return MVAE_OK;
+}
+
+int finalize(const Dims& d, const WS& w, float* out_scalars, float* mu_out, float* lv_out, cudaStream_t st) {
+  if (out_scalars) {
+    simt::finalize_scalars_kernel<<<1, 256, 0, st>>>(w.bce_sum, w.kl_sum, w.hit_count, d.B, d.T,
+                                                    (double)d.max_len / ((double)d.B * d.T * d.C),
+                                                    1.0 / ((double)d.B * d.Z), out_scalars);
+    KCHECK();
+  }
+  const size_t n = (size_t)d.B * d.Z * 4;
+  if (mu_out) { count(); MVAE_CUDA_CHECK(cudaMemcpyAsync(mu_out, w.mu, n, cudaMemcpyDeviceToDevice, st)); }
+  if (lv_out) { count(); MVAE_CUDA_CHECK(cudaMemcpyAsync(lv_out, w.lv, n, cudaMemcpyDeviceToDevice, st)); }
+  return MVAE_OK;
+}
+
+template <typename TA>
+int elbo_step_t(const Dims& d, const WS& w, const float* const* P, float* const* G, const uint8_t* ids,
+                const float* eps, float* out_scalars, float* mu_out, float* lv_out, cudaStream_t st) {
+  RC(prep_weights<TA>(d, w, P, st, true));
+  RC(run_forward<TA>(d, w, P, ids, eps, st, false, true));
+  RC(head_fused<TA>(d, w, ids, nullptr, true, st));
+  RC(run_backward<TA>(d, w, P, G, ids, eps, st, true, nullptr, nullptr));
+  RC(finalize(d, w, out_scalars, mu_out, lv_out, st));
+  return MVAE_OK;
+}
+
+int check_ws(const mvae_cfgb_desc* desc, void* ws, size_t ws_bytes, Dims* d, WS* w) {
+  RC(make_dims(desc, d));
+  if (!ws || (reinterpret_cast<uintptr_t>(ws) & 255)) return MVAE_ERR_INVALID;
+  carve(*d, ws, w);
+  if (ws_bytes < w->total) return MVAE_ERR_WORKSPACE;
+  return MVAE_OK;
+}
+
+}  // namespace
+
+struct mvae_graph {
+  cudaGraph_t graph;
+  cudaGraphExec_t exec;
+  long long kernel_nodes;
+  long long counted_launches;
+};
+
+extern "C" {
+
+long long mvae_launch_count(void) { return g_launches; }
+void mvae_reset_launch_count(void) { g_launches = 0; }
+
+size_t mvae_cfgb_workspace_bytes(const mvae_cfgb_desc* desc) {
+  Dims d; WS w;
+  if (make_dims(desc, &d) != MVAE_OK) return 0;
+  carve(d, nullptr, &w);
+  return w.total;
+}
+
+int mvae_cfgb_elbo_step(const mvae_cfgb_desc* desc, const float* const* params, float* const* grads,
+                        const uint8_t* ids, const float* eps, float* out_scalars, float* mu_out, float* logvar_out,
+                        void* workspace, size_t workspace_bytes, mvae_stream_t stream) {
+  Dims d; WS w;
+  RC(check_ws(desc, workspace, workspace_bytes, &d, &w));
+  if (!params || !grads || !ids || (d.train && !eps)) return MVAE_ERR_INVALID;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  return d.bf16 ? elbo_step_t<__nv_bfloat16>(d, w, params, grads, ids, eps, out_scalars, mu_out, logvar_out, st)
+                : elbo_step_t<float>(d, w, params, grads, ids, eps, out_scalars, mu_out, logvar_out, st);
+}
+
+int mvae_cfgb_elbo_step_graph_create(const mvae_cfgb_desc* desc, const float* const* params, float* const* grads,
+                                     const uint8_t* ids, const float* eps, float* out_scalars, float* mu_out,
+                                     float* logvar_out, void* workspace, size_t workspace_bytes,
+                                     mvae_graph** out_graph) {
+  if (!out_graph) return MVAE_ERR_INVALID;
+  cudaStream_t cs;
+  MVAE_CUDA_CHECK(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+  const long long before = g_launches;
+  MVAE_CUDA_CHECK(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+  int rc = mvae_cfgb_elbo_step(desc, params, grads, ids, eps, out_scalars, mu_out, logvar_out, workspace,
+                               workspace_bytes, reinterpret_cast<mvae_stream_t>(cs));
+  cudaGraph_t graph = nullptr;
+  cudaError_t e = cudaStreamEndCapture(cs, &graph);
+  const long long counted = g_launches - before;
+  g_launches = before;
+  cudaStreamDestroy(cs);
+  if (rc != MVAE_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+  MVAE_CUDA_CHECK(e);
+  mvae_graph* g = new (std::nothrow) mvae_graph();
+  if (!g) return MVAE_ERR_INVALID;
+  g->graph = graph;
+  g->counted_launches = counted;
+  e = cudaGraphInstantiate(&g->exec, graph, 0);
+  if (e != cudaSuccess) { cudaGraphDestroy(graph); delete g; MVAE_CUDA_CHECK(e); }
+  size_t n = 0;
+  cudaGraphGetNodes(graph, nullptr, &n);
+  g->kernel_nodes = (long long)n;
+  *out_graph = g;
+  return MVAE_OK;
+}
+
+int mvae_graph_launch(mvae_graph* g, mvae_stream_t stream) {
+  if (!g) return MVAE_ERR_INVALID;
+  MVAE_CUDA_CHECK(cudaGraphLaunch(g->exec, reinterpret_cast<cudaStream_t>(stream)));
+  g_launches += g->counted_launches;
+  return MVAE_OK;
+}
+long long mvae_graph_num_kernel_nodes(const mvae_graph* g) { return g ? g->kernel_nodes : 0; }
+void mvae_graph_destroy(mvae_graph* g) {
+  if (!g) return;
+  cudaGraphExecDestroy(g->exec);
+  cudaGraphDestroy(g->graph);
+  delete g;
+}
+
+int mvae_cfgb_forward(const mvae_cfgb_desc* desc, const float* const* params, const uint8_t* ids, const float* eps,
+                      float* probs, float* mu, float* logvar, void* workspace, size_t workspace_bytes,
+                      mvae_stream_t stream) {
+  Dims d; WS w;
+  RC(check_ws(desc, workspace, workspace_bytes, &d, &w));
+  if (!params || !ids || (d.train && !eps)) return MVAE_ERR_INVALID;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (d.bf16) {
+    RC(prep_weights<__nv_bfloat16>(d, w, params, st, true));
+    RC(run_forward<__nv_bfloat16>(d, w, params, ids, eps, st, false, true));
+    RC(head_fused<__nv_bfloat16>(d, w, ids, probs, false, st));
+  } else {
+    RC(prep_weights<float>(d, w, params, st, true));
+    RC(run_forward<float>(d, w, params, ids, eps, st, false, true));
+    RC(head_fused<float>(d, w, ids, probs, false, st));
+  }
+  return finalize(d, w, nullptr, mu, logvar, st);
+}
+
+int mvae_cfgb_backward(const mvae_cfgb_desc* desc, const float* const* params, float* const* grads,
+                       const uint8_t* ids, const float* eps, const float* dprobs, const float* dmu,
+                       const float* dlogvar, void* workspace, size_t workspace_bytes, mvae_stream_t stream) {
+  Dims d; WS w;
+  RC(check_ws(desc, workspace, workspace_bytes, &d, &w));
+  if (!params || !grads || !ids || (d.train && !eps)) return MVAE_ERR_INVALID;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const long long rows = (long long)d.T * d.Bp;
+  const size_t es = d.bf16 ? 2 : 4;
+  if (!dprobs) {
+    RC(memset_async(w.dlogits, (size_t)rows * d.CP * es, st));
+  } else if (d.bf16) {
+    simt::head_softmax_bwd_kernel<__nv_bfloat16><<<(unsigned)ceil_div64(rows * 32, 256), 256, 0, st>>>(
+        w.logits, d.CP, d.C, dprobs, d.B, d.Bp, d.T, (__nv_bfloat16*)w.dlogits);
+    KCHECK();
+  } else {
+    simt::head_softmax_bwd_kernel<float><<<(unsigned)ceil_div64(rows * 32, 256), 256, 0, st>>>(
+        w.logits, d.CP, d.C, dprobs, d.B, d.Bp, d.T, (float*)w.dlogits);
+    KCHECK();
+  }
+  return d.bf16 ? run_backward<__nv_bfloat16>(d, w, params, grads, ids, eps, st, false, dmu, dlogvar)
+                : run_backward<float>(d, w, params, grads, ids, eps, st, false, dmu, dlogvar);
+}
+
+int mvae_cfgb_decode_greedy(const mvae_cfgb_desc* desc, const float* const* params, const float* z, uint8_t* ids_out,
+                            float* probs_out, void* workspace, size_t workspace_bytes, mvae_stream_t stream) {
+  Dims d; WS w;
+  RC(check_ws(desc, workspace, workspace_bytes, &d, &w));
+  if (!params || !z || !ids_out) return MVAE_ERR_INVALID;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  count();
+  MVAE_CUDA_CHECK(cudaMemcpyAsync(w.z, z, (size_t)d.B * d.Z * 4, cudaMemcpyDeviceToDevice, st));
+  if (d.bf16) {
+    RC(prep_weights<__nv_bfloat16>(d, w, params, st, false));
+    RC(run_forward<__nv_bfloat16>(d, w, params, nullptr, nullptr, st, true, false));
+  } else {
+    RC(prep_weights<float>(d, w, params, st, false));
+    RC(run_forward<float>(d, w, params, nullptr, nullptr, st, true, false));
+  }
+  const long long rows = (long long)d.T * d.Bp;
+  simt::head_argmax_kernel<<<(unsigned)ceil_div64(rows * 32, 256), 256, 0, st>>>(w.logits, d.CP, d.C, d.B, d.Bp, d.T,
+                                                                                 ids_out);
+  KCHECK();
+  if (probs_out) {
+    // reuse the fused head in probs-only mode (ids only select the BCE target, which is discarded here)
+    if (d.bf16) RC(head_fused<__nv_bfloat16>(d, w, ids_out, probs_out, false, st));
+    else RC(head_fused<float>(d, w, ids_out, probs_out, false, st));
+  }
+  return MVAE_OK;
+}
+
+int mvae_onehot_to_ids(const float* onehot, long long rows, int charset, uint8_t* ids, int* not_onehot,
+                       mvae_stream_t stream) {
+  if (!onehot || !ids || !not_onehot || rows <= 0 || charset <= 0 || charset > 255) return MVAE_ERR_INVALID;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  simt::onehot_to_ids_kernel<<<(unsigned)ceil_div64(rows, 256), 256, 0, st>>>(onehot, (int)rows, charset, ids, not_onehot);
+  KCHECK();
+  return MVAE_OK;
+}
+
+int mvae_cfgb_read_error(const mvae_cfgb_desc* desc, void* workspace, size_t workspace_bytes, int* flag,
+                         mvae_stream_t stream) {
+  Dims d; WS w;
+  RC(check_ws(desc, workspace, workspace_bytes, &d, &w));
+  if (!flag) return MVAE_ERR_INVALID;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  MVAE_CUDA_CHECK(cudaMemcpyAsync(flag, w.err_flag, 4, cudaMemcpyDeviceToHost, st));
+  MVAE_CUDA_CHECK(cudaStreamSynchronize(st));
+  return MVAE_OK;
+}
+
+int mvae_gemm_bf16(const void* A, long long lda, int a_mn_major, const void* B, long long ldb, int b_mn_major, void* D,
+                   long long ldd, int d_is_bf16, int accumulate, const float* bias, int M, int N, int K, int tile_n,
+                   int splits, int* err_flag, mvae_stream_t stream) {
+  mvae_umma_operand a{A, a_mn_major ? 1 : 0, M, K, lda, 1, 0, 0};
+  mvae_umma_operand b{B, b_mn_major ? 1 : 0, N, K, ldb, 1, 0, 0};
+  mvae_umma_out o{D, ldd, d_is_bf16, accumulate, bias};
+  count();
+  return mvae_umma_gemm(&a, &b, &o, M, N, K, tile_n, splits, 0, err_flag, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int mvae_sgemm(const float* A, long long sam, long long sak, const float* B, long long sbk, long long sbn, float* C,
+               long long ldc, int M, int N, int K, const float* bias, int act, int accumulate, int splits,
+               mvae_stream_t stream) {
+  count();
+  return simt::sgemm(reinterpret_cast<cudaStream_t>(stream), A, sam, sak, B, sbk, sbn, C, ldc, M, N, K, bias, act,
+                     accumulate, splits);
+}
+
+}  // extern "C"

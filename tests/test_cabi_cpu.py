@@ -1,0 +1,61 @@
+"""CPU-side checks: the C-ABI library loads, exports every symbol include/mvae_b200.h declares, and validates
+arguments without a GPU (no compute calls)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _lib():
+    import molecular_vae_b200 as m
+    return m._lib
+
+
+def test_header_symbols_exported():
+    hdr = open(os.path.join(ROOT, "include", "mvae_b200.h")).read()
+    names = set(re.findall(r"\b(mvae_[a-z0-9_]+)\s*\(", hdr))
+    names -= {"mvae_stream_t"}
+    L = _lib()
+    missing = [n for n in sorted(names) if not hasattr(L.lib, n)]
+    assert not missing, missing
+    assert set(L.EXPORTED) <= names
+
+
+def test_workspace_size_and_argument_validation():
+    L = _lib()
+    d = L.CfgBDesc(4096, 120, 35, 292, 501, 3, 435, L.PREC_BF16, 1, 120.0, 1.0)
+    n16 = L.lib.mvae_cfgb_workspace_bytes(ctypes.byref(d))
+    d32 = L.CfgBDesc(4096, 120, 35, 292, 501, 3, 435, L.PREC_FP32, 1, 120.0, 1.0)
+    n32 = L.lib.mvae_cfgb_workspace_bytes(ctypes.byref(d32))
+    assert 8e9 < n16 < 20e9 and n32 > 1.7 * n16
+    bad = L.CfgBDesc(0, 120, 35, 292, 501, 3, 435, L.PREC_BF16, 1, 120.0, 1.0)
+    assert L.lib.mvae_cfgb_workspace_bytes(ctypes.byref(bad)) == 0
+    bad2 = L.CfgBDesc(8, 120, 35, 292, 501, 9, 435, L.PREC_BF16, 1, 120.0, 1.0)
+    assert L.lib.mvae_cfgb_workspace_bytes(ctypes.byref(bad2)) == 0
+    assert L.lib.mvae_strerror(-2).decode() == "workspace too small"
+    with pytest.raises(L.MvaeError):
+        L.check(-1)
+
+
+def test_param_order_matches_reference_state_dict():
+    import molecular_vae_b200 as m
+    from oracle import vae_oracle as vo
+    keys = m.param_order(3)
+    assert keys == list(vo.config_b_shapes().keys())
+    model = m.VAE(latent=292)
+    sd = model.state_dict()
+    assert list(sd.keys()) == [k for k in sd.keys()] and set(sd.keys()) == set(keys)
+    for k, shp in vo.config_b_shapes().items():
+        assert tuple(sd[k].shape) == shp, k
+
+
+def test_no_cpu_fallback():
+    import torch
+    import molecular_vae_b200 as m
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(m._lib.MvaeError):
+        m.CfgBEngine(4)

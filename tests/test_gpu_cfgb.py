@@ -1,0 +1,178 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the float64 oracle and the golden fixtures.
+
+Tolerances (BASELINE.json north_star): loss / KL / reconstruction within 1e-3 relative and parameter gradients
+within 1e-2 relative in bf16 mode; 1e-5 in fp32 check mode; greedy decodes bit-exact in fp32 mode."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from tests.util_gpu import build_model, grads_of, load_pkg, make_case, oracle_step, rel_l2
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+FP32_LOSS_RTOL = 1e-5
+FP32_GRAD_RTOL = 1e-5   # relative L2 error per parameter tensor
+BF16_LOSS_RTOL = 1e-3
+BF16_GRAD_RTOL = 1e-2
+
+
+def _fused(model, ids, eps, max_len=120):
+    out = model.elbo_step(torch.from_numpy(ids).cuda(), torch.from_numpy(eps).cuda(), max_len=max_len)
+    torch.cuda.synchronize()
+    model.engine(ids.shape[0]).check_device_error()
+    return out.cpu().numpy()
+
+
+def _compare(model, sc, ref, loss_rtol, grad_rtol, tag):
+    assert abs(sc[0] - ref["loss"]) <= loss_rtol * abs(ref["loss"]), (tag, sc, ref["loss"])
+    assert abs(sc[1] - ref["bce"]) <= loss_rtol * abs(ref["bce"]), (tag, sc, ref["bce"])
+    assert abs(sc[2] - ref["kl"]) <= loss_rtol * abs(ref["kl"]) + 1e-7, (tag, sc, ref["kl"])
+    bad = {}
+    for k, g in grads_of(model).items():
+        e = rel_l2(g, ref["grads"][k])
+        if not (e <= grad_rtol):
+            bad[k] = e
+    assert not bad, (tag, bad)
+
+
+@pytest.mark.parametrize("B,Z,H,L", [(5, 16, 24, 3), (3, 8, 16, 1), (130, 12, 70, 2)])
+def test_fused_step_fp32_small(B, Z, H, L):
+    m = load_pkg()
+    P, ids, onehot, eps = make_case(11 + B, 21 + B, B, Z, H, L)
+    ref = oracle_step(P, onehot, eps, L)
+    model = build_model(m, P, Z, H, L, "fp32")
+    sc = _fused(model, ids, eps)
+    _compare(model, sc, ref, FP32_LOSS_RTOL, FP32_GRAD_RTOL, "fp32-small")
+    assert int(sc[3]) == int((ref["argmax"] == ids).all(1).sum())
+
+
+def test_fused_step_fp32_full_config_matches_golden():
+    """Full Config B (Z=292, H=501, L=3, T=120, C=35), B=4: against the reference-generated fixture."""
+    m = load_pkg()
+    g = np.load(os.path.join(GOLD, "cfgb_full_b4.npz"))
+    ps, bs, B, Z, H, L, train = [int(v) for v in g["meta"]]
+    P, ids, onehot, eps = make_case(ps, bs, B, Z, H, L)
+    model = build_model(m, P, Z, H, L, "fp32")
+    sc = _fused(model, ids, eps)
+    assert abs(sc[0] - g["f64/loss"]) <= FP32_LOSS_RTOL * abs(g["f64/loss"])
+    assert abs(sc[1] - g["f64/bce"]) <= FP32_LOSS_RTOL * abs(g["f64/bce"])
+    assert abs(sc[2] - g["f64/kl"]) <= FP32_LOSS_RTOL * abs(g["f64/kl"]) + 1e-7
+    for k, gr in grads_of(model).items():
+        gn = float(g[f"f64/gnorm/{k}"])
+        assert abs(np.sqrt((gr.astype(np.float64) ** 2).sum()) - gn) <= 1e-5 * gn, k
+        if f"f64/gfull/{k}" in g:
+            assert rel_l2(gr, g[f"f64/gfull/{k}"]) <= FP32_GRAD_RTOL, k
+        else:
+            idx = g[f"f64/gidx/{k}"]
+            scale = gn / np.sqrt(gr.size)
+            assert np.abs(gr.reshape(-1)[idx] - g[f"f64/gval/{k}"]).max() <= 2e-4 * scale, k
+
+
+def test_dropin_forward_backward_fp32_matches_reference_contract():
+    """model(x) -> (probs, mu, logvar); loss_function; loss.backward()  (train.py:98-101) with float one-hot input."""
+    m = load_pkg()
+    B, Z, H, L = 6, 16, 24, 2
+    P, ids, onehot, eps = make_case(5, 6, B, Z, H, L)
+    ref = oracle_step(P, onehot, eps, L)
+    model = build_model(m, P, Z, H, L, "fp32")
+    model.train()
+    model.eps_override = torch.from_numpy(eps)
+    x = torch.from_numpy(onehot).cuda()
+    probs, mu, logvar = model(x)
+    assert probs.shape == (B, 120, 35) and mu.shape == (B, Z)
+    np.testing.assert_allclose(probs.detach().cpu().numpy(), ref["probs"], rtol=2e-5, atol=1e-7)
+    np.testing.assert_allclose(mu.detach().cpu().numpy(), ref["mu"], rtol=1e-5, atol=1e-6)
+    loss = m.loss_function(probs, x, mu, logvar)
+    loss.backward()
+    torch.cuda.synchronize()
+    assert abs(float(loss) - ref["loss"]) <= 1e-5 * abs(ref["loss"])
+    bad = {k: rel_l2(g, ref["grads"][k]) for k, g in grads_of(model).items() if rel_l2(g, ref["grads"][k]) > FP32_GRAD_RTOL}
+    assert not bad, bad
+
+
+def test_eval_mode_uses_mu_and_rejects_non_onehot():
+    m = load_pkg()
+    B, Z, H, L = 4, 8, 16, 2
+    P, ids, onehot, eps = make_case(7, 8, B, Z, H, L)
+    ref = oracle_step(P, onehot, eps, L, train=False, need_grads=False)
+    model = build_model(m, P, Z, H, L, "fp32").eval()
+    with torch.no_grad():
+        probs, mu, logvar = model(torch.from_numpy(ids).cuda())
+    np.testing.assert_allclose(probs.cpu().numpy(), ref["probs"], rtol=2e-5, atol=1e-7)
+    bad = onehot.copy()
+    bad[0, 0, :] = 0.5
+    with pytest.raises(ValueError):
+        model(torch.from_numpy(bad).cuda())
+
+
+def test_greedy_decode_bit_exact_fp32():
+    m = load_pkg()
+    from oracle import vae_oracle as vo
+    B, Z, H, L = 16, 292, 501, 3
+    P, ids, onehot, eps = make_case(31, 32, B, Z, H, L)
+    z = np.random.Generator(np.random.PCG64(9)).standard_normal((B, Z)).astype(np.float32)
+    P64 = {k: v.astype(np.float64) for k, v in P.items()}
+    want, logits = vo.greedy_decode(P64, z.astype(np.float64), layers=L)
+    model = build_model(m, P, Z, H, L, "fp32").eval()
+    got = model.decode_greedy(torch.from_numpy(z).cuda()).cpu().numpy()
+    # exclude positions where the oracle's own top-2 margin is below fp32 resolution
+    srt = np.sort(logits, -1)
+    safe = (srt[..., -1] - srt[..., -2]) > 1e-4
+    assert (got[safe] == want[safe]).all()
+    assert safe.mean() > 0.99
+
+
+@pytest.mark.parametrize("B", [64, 200])
+def test_fused_step_bf16_full_config(B):
+    m = load_pkg()
+    Z, H, L = 292, 501, 3
+    P, ids, onehot, eps = make_case(41, 42 + B, B, Z, H, L)
+    ref = oracle_step(P, onehot, eps, L)
+    model = build_model(m, P, Z, H, L, "bf16")
+    sc = _fused(model, ids, eps)
+    _compare(model, sc, ref, BF16_LOSS_RTOL, BF16_GRAD_RTOL, "bf16-full")
+
+
+def test_graph_replay_matches_direct_launch():
+    m = load_pkg()
+    B, Z, H, L = 128, 292, 501, 3
+    P, ids, onehot, eps = make_case(51, 52, B, Z, H, L)
+    model = build_model(m, P, Z, H, L, "bf16")
+    sc = _fused(model, ids, eps).copy()
+    g_direct = {k: v.copy() for k, v in grads_of(model).items()}
+    eng = model.engine(B)
+    params = model.ordered_params()
+    ids_d, eps_d = torch.from_numpy(ids).cuda(), torch.from_numpy(eps).cuda()
+    for p in params:
+        p.grad.zero_()
+    n_nodes = eng.capture_elbo_step([p.data for p in params], [p.grad for p in params], ids_d, eps_d)
+    assert n_nodes > 100
+    out = eng.launch_graph()
+    torch.cuda.synchronize()
+    eng.check_device_error()
+    np.testing.assert_allclose(out.cpu().numpy()[:3], sc[:3], rtol=1e-5)
+    for k, g in grads_of(model).items():
+        assert rel_l2(g, g_direct[k]) <= 1e-4, k
+    eng.destroy_graph()
+
+
+def test_gemm_bf16_c_abi():
+    m = load_pkg()
+    import ctypes
+    lib = m._lib.lib
+    M, N, K = 300, 200, 520
+    a = torch.randn(M, K, device="cuda").bfloat16()
+    b = torch.randn(N, K, device="cuda").bfloat16()
+    d = torch.empty(M, N, device="cuda", dtype=torch.float32)
+    err = torch.zeros(1, dtype=torch.int32, device="cuda")
+    vp = ctypes.c_void_p
+    rc = lib.mvae_gemm_bf16(vp(a.data_ptr()), K, 0, vp(b.data_ptr()), K, 0, vp(d.data_ptr()), N, 0, 0, vp(0), M, N, K,
+                            0, 1, vp(err.data_ptr()), vp(torch.cuda.current_stream().cuda_stream))
+    assert rc == 0
+    torch.cuda.synchronize()
+    assert int(err.item()) == 0
+    ref = a.double() @ b.double().t()
+    assert (d.double() - ref).abs().max().item() < 1e-2
