@@ -1,0 +1,288 @@
+#!/usr/bin/env python
+"""Headline benchmark: train molecules/sec of one fused fwd+bwd ELBO step (BASELINE.json metric) on the
+canonical Config-B model (Conv1d encoder over one-hot 120x35, latent 292, 3x501 GRU decoder), bf16 tensor-core
+mode, batch 4096 per GPU, synthetic ZINC-like ids (ZINC-250k is not in the image).
+
+    python bench.py --gpus N --steps K --warmup W            # this framework (one rank per GPU under torchrun)
+    python bench.py --impl reference --steps K --warmup W    # CPU arm: the oracle port of the reference path
+
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for how each field is obtained.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+GFLOP_PER_MOLECULE = 2.7301  # fwd+bwd, 2*MACs, layer-0 projection counted once
+METRIC = "train molecules/sec (fwd+bwd ELBO)"
+WORKLOAD = "Config B: models2d-stack MolecularVAE (conv enc, latent 292, 3x501 GRU, 120x35), batch 4096/GPU, bf16"
+CFG = dict(latent=292, hidden=501, layers=3, seq_len=120, charset=35)
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return d, "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], threading.Event()
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
+                self.rows.append([c.strip() for c in out.strip().split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def cpu_oracle_rate(sample_b, steps, warmup):
+    """molecules/sec of the numpy oracle port (fp32, BLAS threads = all host cores) on `sample_b` molecules."""
+    import numpy as np
+    from oracle import vae_oracle as vo
+    P = vo.make_params(42, dtype=np.float32, **CFG)
+    ids, onehot, eps = vo.make_batch(43, sample_b, dtype=np.float32)
+    for _ in range(warmup):
+        vo.config_b_step(P, onehot, eps)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        vo.config_b_step(P, onehot, eps)
+    dt = time.perf_counter() - t0
+    return sample_b * steps / dt, dt / steps
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    total = args.steps + args.warmup
+    sample_b = int(max(8, min(250, 6000 // max(total, 1))))
+    rate, sec = cpu_oracle_rate(sample_b, args.steps, args.warmup)
+    sample = f"{sample_b} molecules/step (BASELINE config[0] shape, fp32 numpy port of models2d.py+train.py:31-38)"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": "molecules/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample_batch": sample_b},
+        "cpu_baseline": {"value": rate, "unit": "molecules/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": rate, "unit": "molecules/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def time_kernel(fn, iters=5):
+    import torch
+    st = torch.cuda.current_stream()
+    fn()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record(st)
+    for _ in range(iters):
+        fn()
+    e1.record(st)
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters * 1e-3
+
+
+def kernel_rooflines(B, peaks):
+    """Live CUDA-event timings of the three GEMM shapes that carry >99 % of the step's FLOPs."""
+    import ctypes
+    import torch
+    import molecular_vae_b200 as m
+    lib, vp = m._lib.lib, ctypes.c_void_p
+    T, Hp = 120, 512
+    st = vp(torch.cuda.current_stream().cuda_stream)
+    err = torch.zeros(1, dtype=torch.int32, device="cuda")
+    out = {}
+
+    def gemm(a, lda, amn, b, ldb, bmn, d, ldd, dbf, acc, M, N, K, bn, splits):
+        m._lib.check(lib.mvae_gemm_bf16(vp(a.data_ptr()), lda, amn, vp(b.data_ptr()), ldb, bmn, vp(d.data_ptr()), ldd,
+                                        dbf, acc, vp(0), M, N, K, bn, splits, vp(err.data_ptr()), st))
+    x = torch.randn(T * B, Hp, device="cuda").bfloat16()
+    w = (torch.randn(3 * Hp, Hp, device="cuda") * 0.04).bfloat16()
+    gi = torch.empty(T * B, 3 * Hp, device="cuda", dtype=torch.bfloat16)
+    t = time_kernel(lambda: gemm(x, Hp, 0, w, Hp, 0, gi, 3 * Hp, 1, 0, T * B, 3 * Hp, Hp, 256, 1))
+    fl = 2.0 * T * B * 3 * Hp * Hp
+    out["input_projection_gemm"] = {"ms": t * 1e3, "tflops": fl / t * 1e-12, "frac": fl / t * 1e-12 / peaks["bf16_tflops"]}
+    gh = torch.empty(B, 3 * Hp, device="cuda", dtype=torch.float32)
+    t = time_kernel(lambda: gemm(x, Hp, 0, w, Hp, 0, gh, 3 * Hp, 0, 0, B, 3 * Hp, Hp, 256, 1), iters=50)
+    fl = 2.0 * B * 3 * Hp * Hp
+    out["recurrent_step_gemm"] = {"ms": t * 1e3, "tflops": fl / t * 1e-12, "frac": fl / t * 1e-12 / peaks["bf16_tflops"]}
+    dw = torch.zeros(3 * Hp, Hp, device="cuda", dtype=torch.float32)
+    t = time_kernel(lambda: gemm(gi, 3 * Hp, 1, x, Hp, 1, dw, Hp, 0, 1, 3 * Hp, Hp, T * B, 256, 12))
+    fl = 2.0 * T * B * 3 * Hp * Hp
+    out["wgrad_gemm"] = {"ms": t * 1e3, "tflops": fl / t * 1e-12, "frac": fl / t * 1e-12 / peaks["bf16_tflops"]}
+    torch.cuda.synchronize()
+    assert int(err.item()) == 0
+    return out
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    torch.cuda.set_device(local)
+    import molecular_vae_b200 as m
+    from oracle import vae_oracle as vo  # synthetic-batch generator + cpu_baseline only
+    peaks, peak_src = load_peaks()
+    B = args.batch
+    torch.manual_seed(42)
+    model = m.VAE(precision=args.precision, **CFG).cuda()
+    params = model.ordered_params()
+    # one flat gradient buffer -> a single NCCL all-reduce per step in data-parallel runs
+    flat = torch.zeros(sum(p.numel() for p in params), dtype=torch.float32, device="cuda")
+    off = 0
+    for p in params:
+        p.grad = flat[off:off + p.numel()].view_as(p)
+        off += p.numel()
+    ids_np, _, eps_np = vo.make_batch(1000 + rank, B)
+    ids_host = torch.from_numpy(ids_np).pin_memory()
+    ids_dev = torch.from_numpy(ids_np).cuda()
+    eps_dev = torch.from_numpy(eps_np).cuda()
+    eng = model.engine(B, max_len=120)
+    eng.set_train(True)
+    nodes = eng.capture_elbo_step([p.data for p in params], [p.grad for p in params], ids_dev, eps_dev)
+
+    def step_resident():
+        eng.launch_graph()
+        if world > 1:
+            dist.all_reduce(flat)
+            flat.div_(world)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    barrier()
+    eng.check_device_error()
+    sampler = ClockSampler(local)
+    sampler.start()
+    m._lib.lib.mvae_reset_launch_count()
+    st = torch.cuda.current_stream()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(st)
+    for _ in range(args.steps):
+        step_resident()
+    e1.record(st)
+    barrier()
+    launches = int(m._lib.lib.mvae_launch_count())
+    sec = e0.elapsed_time(e1) * 1e-3
+    scal = eng.scalars.cpu().numpy().tolist()
+
+    # end to end through the public API: pinned host ids -> H2D, device-side eps draw, fused step, loss D2H
+    def step_e2e():
+        x = ids_host.to("cuda", non_blocking=True)
+        out = model.elbo_step(x)
+        if world > 1:
+            dist.all_reduce(flat)
+            flat.div_(world)
+        return out.cpu()
+
+    eng.destroy_graph()
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(2, min(args.steps, 10))
+    for _ in range(e2e_steps):
+        res = step_e2e()
+    barrier()
+    sec_e2e = time.perf_counter() - t0
+    sampler.stop_flag.set()
+    sampler.join(timeout=2)
+
+    tmax = torch.tensor([sec, sec_e2e], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    sec, sec_e2e = tmax.tolist()
+    value = world * B * args.steps / sec
+    e2e_value = world * B * e2e_steps / sec_e2e
+    if rank == 0:
+        peak = peaks["bf16_tflops_sustained"]
+        achieved = (value / world) * GFLOP_PER_MOLECULE * 1e-3  # TFLOP/s per GPU
+        line = {
+            "metric": METRIC, "value": value, "unit": "molecules/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": sec / args.steps * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32",
+            "data": "synthetic",
+            "config": {"workload": WORKLOAD, "batch_per_gpu": B, "global_batch": B * world,
+                       "parallelism": f"dp{world}", "cache": "per-step working set ~12 GB of activations >> 126 MB L2",
+                       "graph_nodes": int(nodes), "loss": scal[0]},
+            "e2e": {"value": e2e_value, "unit": "molecules/s", "h2d_bytes_per_step": int(ids_host.numel()),
+                    "d2h_bytes_per_step": 16, "steps": e2e_steps},
+            "gpu_launches": launches,
+            "clocks": sampler.summary(),
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src + " bf16_tflops_sustained",
+                         "scope": "whole fused step (algorithmic 2.7301 GFLOP/molecule x batch / step time)"},
+        }
+        if world == 1:
+            try:
+                line["roofline"]["kernels"] = kernel_rooflines(B, peaks)
+            except Exception as ex:  # never lose the headline over the side measurement
+                line["roofline"]["kernels_error"] = repr(ex)
+            cores = os.cpu_count() or 1
+            rate, _ = cpu_oracle_rate(250, 2, 1)
+            line["cpu_baseline"] = {"value": rate, "unit": "molecules/s", "cores": cores, "kind": "port",
+                                    "sample": "2 timed steps of 250 molecules (BASELINE config[0] batch) after 1 "
+                                              "warm-up, fp32 numpy port oracle/vae_oracle.py, BLAS on all cores"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=4096)
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -103,19 +103,37 @@ class VAE(nn.Module):
         return ids
 
     # -- fused fast path ----------------------------------------------------------------------------
-    def elbo_step(self, x, eps=None, max_len=None):
+    def elbo_step(self, x, eps=None, max_len=None, use_graph=True):
         """Fused forward + loss_function (train.py:31-38) + backward.  Fills p.grad of every parameter and
-        returns the device tensor [loss, max_len*BCE, KL, n_exact_reconstructions]."""
+        returns the device tensor [loss, max_len*BCE, KL, n_exact_reconstructions].
+
+        With use_graph the ~1.5k kernel launches of a step are captured once into a CUDA graph over static
+        input buffers and replayed; the capture is redone if a parameter or gradient tensor moves."""
         eng = self.engine(x.shape[0], max_len)
-        if max_len is not None:
+        if max_len is not None and float(max_len) != eng.desc.max_len:
             eng.desc.max_len = float(max_len)
+            eng.destroy_graph()
         ids = eng.to_ids(x)
-        eps = self._eps(x.shape[0], ids.device) if eps is None else eps.to(ids.device, torch.float32).contiguous()
+        if eps is None:
+            eps = self._eps(x.shape[0], ids.device)
+        else:
+            eps = eps.to(ids.device, torch.float32).contiguous()
         params = self.ordered_params()
         for p in params:
             if p.grad is None:
                 p.grad = torch.empty_like(p)
-        return eng.elbo_step([p.data for p in params], [p.grad for p in params], ids, eps)
+        if not use_graph:
+            return eng.elbo_step([p.data for p in params], [p.grad for p in params], ids, eps)
+        key = (tuple(p.data_ptr() for p in params), tuple(p.grad.data_ptr() for p in params), eng.desc.train)
+        if eng._graph is None or getattr(eng, "_graph_key", None) != key:
+            eng._ids_static = torch.empty_like(ids)
+            eng._eps_static = torch.empty_like(eps)
+            eng.capture_elbo_step([p.data for p in params], [p.grad for p in params], eng._ids_static,
+                                  eng._eps_static)
+            eng._graph_key = key
+        eng._ids_static.copy_(ids, non_blocking=True)
+        eng._eps_static.copy_(eps, non_blocking=True)
+        return eng.launch_graph()
 
 
 max_len = 120  # script-level global read by loss_function, as in train.py:43 / train_distributed.py:61
