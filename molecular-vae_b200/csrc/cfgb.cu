@@ -20,6 +20,8 @@
 #include "common.cuh"
 #include "simt_kernels.cuh"
 #include "umma_gemm.h"
+#include "gru_rec.h"
+#include <stdlib.h>
 
 namespace {
 
@@ -69,6 +71,9 @@ struct WS {
   void* dlogits;    // [T*Bp][CP] TA
   // padded weights (TA) and biases (fp32)
   void* Whh_p[4]; void* Wih_p[4]; void* Wih_nrz[4]; void* W3_p;
+  void* WhhT_p[4];          // bf16 [Hp][3Hp] (fused BPTT kernel operand)
+  void* gi0_bf;             // bf16 [Bp][3Hp] copy of the layer-0 projection (fused forward kernel)
+  unsigned int* counters;   // [Bp/128] inter-CTA step counters of the fused recurrence
   float* bih_p[4]; float* bhh_p[4]; float* b3_p;
   // padded gradient staging (fp32)
   float* dW_p;   // [3Hp][Hp]
@@ -130,6 +135,7 @@ void carve(const Dims& d, void* base, WS* w) {
     w->Whh_p[l] = c.take<uint8_t>(3 * Hp * Hp * es);
     w->Wih_p[l] = c.take<uint8_t>(3 * Hp * Hp * es);
     w->Wih_nrz[l] = c.take<uint8_t>(3 * Hp * Hp * es);
+    w->WhhT_p[l] = c.take<uint8_t>(3 * Hp * Hp * es);
     w->bih_p[l] = c.take<float>(3 * Hp);
     w->bhh_p[l] = c.take<float>(3 * Hp);
   }
@@ -138,6 +144,8 @@ void carve(const Dims& d, void* base, WS* w) {
   w->dW_p = c.take<float>(3 * Hp * Hp);
   w->dW3_p = c.take<float>(d.CP * Hp);
   w->csum = c.take<float>(4 * Hp);
+  w->gi0_bf = c.take<uint8_t>(Bp * 3 * Hp * 2);
+  w->counters = c.take<unsigned int>(Bp / 128 + 1);
   w->total = (c.off + 255) & ~size_t(255);
 }
 
@@ -219,6 +227,54 @@ __global__ void copy_prefix_kernel(const float* __restrict__ src, float* __restr
   if (i < n) dst[i] = src[i];
 }
 
+
+// W_hh^T padded: dst[j][g*Hp + i] = W_hh[g*H + i][j]   (K-major operand of the fused BPTT kernel)
+__global__ void pad_gate_matrix_T_kernel(const float* __restrict__ src, int H, __nv_bfloat16* __restrict__ dst, int Hp) {
+  const long long total = 3ll * Hp * Hp;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(idx % (3 * Hp));
+    const int j = (int)(idx / (3 * Hp));
+    const int g = k / Hp, i = k - g * Hp;
+    float v = 0.f;
+    if (i < H && j < H) v = src[((long long)g * H + i) * H + j];
+    dst[idx] = __float2bfloat16_rn(v);
+  }
+}
+__global__ void f32_to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    dst[i] = __float2bfloat16_rn(src[i]);
+}
+// layer 0: sum over time of the dgi window of dG ([T][Bp][4Hp], blocks n,r,z) -> fp32 [Bp][3Hp] in (r,z,n) order
+__global__ void dgi_time_sum_kernel(const __nv_bfloat16* __restrict__ dG, int T, int Bp, int Hp,
+                                    float* __restrict__ out) {
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= (long long)Bp * 3 * Hp) return;
+  const int c = (int)(idx % (3 * Hp));
+  const int b = (int)(idx / (3 * Hp));
+  const int g = c / Hp, j = c - g * Hp;
+  const int blk = (g == 0) ? 1 : (g == 1 ? 2 : 0);
+  const __nv_bfloat16* p = dG + (long long)b * 4 * Hp + blk * Hp + j;
+  float s = 0.f;
+  for (int t = 0; t < T; ++t) s += __bfloat162float(p[(long long)t * Bp * 4 * Hp]);
+  out[idx] = s;
+}
+
+int g_sm_count = 0;
+// 0: per-step GEMM + gate kernels; 1/2: persistent fused recurrence variants (gru_rec.cu)
+int rec_variant(const Dims& d) {
+  if (!d.bf16) return 0;
+  const char* e = getenv("MVAE_REC");
+  int v = e ? atoi(e) : 1;
+  if (v <= 0) return 0;
+  if (g_sm_count == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    if (cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+  }
+  if (d.Bp > mvae_gru_rec_max_rows(d.Hp, v, g_sm_count)) return 0;
+  return v;
+}
+
 // ---- weight preparation ---------------------------------------------------------------------
 template <typename TA>
 int prep_weights(const Dims& d, const WS& w, const float* const* P, cudaStream_t st, bool need_bwd) {
@@ -227,6 +283,10 @@ int prep_weights(const Dims& d, const WS& w, const float* const* P, cudaStream_t
   for (int l = 0; l < d.L; ++l) {
     simt::pad_gate_matrix_kernel<TA><<<g, 256, 0, st>>>(P[P_WHH(l)], H, H, (TA*)w.Whh_p[l], Hp, Hp, 0, 1, 2);
     KCHECK();
+    if (need_bwd && rec_variant(d) > 0) {
+      pad_gate_matrix_T_kernel<<<g, 256, 0, st>>>(P[P_WHH(l)], H, (__nv_bfloat16*)w.WhhT_p[l], Hp);
+      KCHECK();
+    }
     if (l >= 1) {
       simt::pad_gate_matrix_kernel<TA><<<g, 256, 0, st>>>(P[P_WIH(l)], H, H, (TA*)w.Wih_p[l], Hp, Hp, 0, 1, 2);
       KCHECK();
@@ -290,6 +350,28 @@ int run_forward(const Dims& d, const WS& w, const float* const* P, const uint8_t
       RC(gemm<TA>(d, w, st, X, Hp, false, (const TA*)w.Wih_p[l], Hp, true, w.gi_all, 3 * Hp, true, T * Bp, 3 * Hp, Hp,
                   w.bih_p[l], false, 1));
     }
+    const int rv = rec_variant(d);
+    if (rv > 0) {
+      if constexpr (sizeof(TA) == 2) {
+        const __nv_bfloat16* gi = (const __nv_bfloat16*)w.gi_all;
+        long long gstride = (long long)Bp * 3 * Hp;
+        if (l == 0) {
+          f32_to_bf16_kernel<<<grid_for((long long)Bp * 3 * Hp), 256, 0, st>>>(w.gi0, (__nv_bfloat16*)w.gi0_bf,
+                                                                               (long long)Bp * 3 * Hp);
+          KCHECK();
+          gi = (const __nv_bfloat16*)w.gi0_bf;
+          gstride = 0;
+        }
+        mvae_gru_rec_args ra{};
+        ra.backward = 0; ra.variant = rv; ra.Bp = Bp; ra.Hp = Hp; ra.T = T;
+        ra.W = (const __nv_bfloat16*)w.Whh_p[l]; ra.gi = gi; ra.gi_tstride = gstride; ra.bhh = w.bhh_p[l];
+        ra.hs = (__nv_bfloat16*)hs; ra.sv = save ? (__nv_bfloat16*)sv : nullptr; ra.counters = w.counters;
+        ra.err_flag = w.err_flag;
+        count(2);
+        RC(mvae_gru_rec_launch(&ra, st));
+      }
+      continue;
+    }
     if (d.bf16) RC(memset_async(w.h32[0], slab * 4, st));
     for (int t = 0; t < T; ++t) {
       RC(gemm<TA>(d, w, st, hs + t * slab, Hp, false, (const TA*)w.Whh_p[l], Hp, true, w.gh, 3 * Hp, false, Bp, 3 * Hp,
@@ -342,6 +424,23 @@ int run_backward(const Dims& d, const WS& w, const float* const* P, float* const
     const TA* sv = (const TA*)w.sv[l];
     TA* dG = (TA*)w.dG;
     TA* dX = (TA*)w.dX;
+    const int rv = rec_variant(d);
+    if (rv > 0) {
+      if constexpr (sizeof(TA) == 2) {
+        mvae_gru_rec_args ra{};
+        ra.backward = 1; ra.variant = rv; ra.Bp = Bp; ra.Hp = Hp; ra.T = T;
+        ra.W = (const __nv_bfloat16*)w.WhhT_p[l]; ra.hs = (__nv_bfloat16*)w.hs[l]; ra.sv = (__nv_bfloat16*)w.sv[l];
+        ra.dX = (const __nv_bfloat16*)dX; ra.dG = (__nv_bfloat16*)dG; ra.counters = w.counters;
+        ra.err_flag = w.err_flag;
+        count(2);
+        RC(mvae_gru_rec_launch(&ra, st));
+        if (l == 0) {
+          dgi_time_sum_kernel<<<(unsigned)ceil_div64((long long)Bp * 3 * Hp, 256), 256, 0, st>>>(
+              (const __nv_bfloat16*)dG, T, Bp, Hp, w.dgi0sum);
+          KCHECK();
+        }
+      }
+    } else {
     RC(memset_async(w.dh_carry, slab * 4, st));
     if (l == 0) RC(memset_async(w.dgi0sum, (size_t)Bp * 3 * Hp * 4, st));
     for (int t = T - 1; t >= 0; --t) {
@@ -353,6 +452,7 @@ int run_backward(const Dims& d, const WS& w, const float* const* P, float* const
       if (t > 0)  // dh_{t-1} += dgh_t * W_hh
         RC(gemm<TA>(d, w, st, dGt + Hp, 4 * Hp, false, (const TA*)w.Whh_p[l], Hp, false, w.dh_carry, Hp, false, Bp, Hp,
                     3 * Hp, nullptr, true, 1));
+    }
     }
     // dW_hh = dgh^T * h_{t-1}   (K = T*Bp)
     RC(memset_async(w.dW_p, (size_t)3 * Hp * Hp * 4, st));

@@ -1,0 +1,25 @@
+// Internal host interface of the persistent fused GRU recurrence (gru_rec.cu).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+struct mvae_gru_rec_args {
+  int backward;              // 0: forward sweep, 1: BPTT sweep
+  int variant;               // 1: 64 units x 2 tiles x 2 stages per CTA; 2: 32 units x 4 tiles x 8 stages
+  int Bp, Hp, T;             // Bp % 128 == 0, Hp % 64 == 0, Hp <= 512
+  const __nv_bfloat16* W;    // fwd: padded W_hh [3Hp][Hp]; bwd: padded W_hh^T [Hp][3Hp]
+  const __nv_bfloat16* gi;   // fwd: input projections incl. b_ih, [T][Bp][3Hp] (or [Bp][3Hp] with gi_tstride 0)
+  long long gi_tstride;
+  const float* bhh;          // fwd: padded b_hh [3Hp]
+  __nv_bfloat16* hs;         // [(T+1)][Bp][Hp]; slab 0 = h0 (fwd writes slabs 1..T, bwd reads slabs 0..T-1)
+  __nv_bfloat16* sv;         // [T][Bp][4Hp]
+  const __nv_bfloat16* dX;   // bwd: [T][Bp][Hp]
+  __nv_bfloat16* dG;         // bwd: [T][Bp][4Hp]
+  unsigned int* counters;    // [Bp/128]
+  int* err_flag;
+  unsigned long long* trace; // optional debug timestamps [T][tiles per CTA][8] of CTA (0,0), may be null
+};
+
+// rows (molecules) one cooperative launch can cover on a device with num_sms SMs (0: shape unsupported)
+int mvae_gru_rec_max_rows(int Hp, int variant, int num_sms);
+int mvae_gru_rec_launch(const mvae_gru_rec_args* a, cudaStream_t stream);
