@@ -40,7 +40,7 @@ int make_dims(const mvae_cfgb_desc* d, Dims* o) {
       d->hidden <= 0 || d->layers < 1 || d->layers > 4 || d->fc0 <= 0)
     return MVAE_ERR_INVALID;
   if (d->precision != MVAE_PREC_FP32 && d->precision != MVAE_PREC_BF16) return MVAE_ERR_INVALID;
-  o->B = d->batch; o->Bp = round_up(d->batch, 128);
+  o->B = d->batch; o->Bp = round_up(d->batch, 256);
   o->T = d->seq_len; o->C = d->charset; o->CP = 64;
   o->Z = d->latent; o->H = d->hidden; o->Hp = round_up(d->hidden, 64); o->L = d->layers; o->F0 = d->fc0;
   o->L1 = o->C - 8; o->L2 = o->L1 - 8; o->L3 = o->L2 - 10;
@@ -75,6 +75,7 @@ struct WS {
   void* gi0_bf;             // bf16 [Bp][3Hp] copy of the layer-0 projection (fused forward kernel)
   unsigned int* counters;   // [Bp/128] inter-CTA step counters of the fused recurrence
   float* bih_p[4]; float* bhh_p[4]; float* b3_p;
+  float* bcomb_p[4];        // b_ih + (b_hr, b_hz, 0): projection bias when the fused kernel only adds b_hn
   // padded gradient staging (fp32)
   float* dW_p;   // [3Hp][Hp]
   float* dW3_p;  // [CP][Hp]
@@ -138,6 +139,7 @@ void carve(const Dims& d, void* base, WS* w) {
     w->WhhT_p[l] = c.take<uint8_t>(3 * Hp * Hp * es);
     w->bih_p[l] = c.take<float>(3 * Hp);
     w->bhh_p[l] = c.take<float>(3 * Hp);
+    w->bcomb_p[l] = c.take<float>(3 * Hp);
   }
   w->W3_p = c.take<uint8_t>(d.CP * Hp * es);
   w->b3_p = c.take<float>(d.CP);
@@ -264,15 +266,36 @@ int g_sm_count = 0;
 int rec_variant(const Dims& d) {
   if (!d.bf16) return 0;
   const char* e = getenv("MVAE_REC");
-  int v = e ? atoi(e) : 1;
+  int v = e ? atoi(e) : 3;
   if (v <= 0) return 0;
   if (g_sm_count == 0) {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return 0;
     if (cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
   }
+  if (v == 3) {
+    if (d.Hp == 256 || d.Hp == 512) return 3;
+    v = 1;
+  }
   if (d.Bp > mvae_gru_rec_max_rows(d.Hp, v, g_sm_count)) return 0;
   return v;
+}
+int fast_gates() {
+  const char* e = getenv("MVAE_FAST_GATES");
+  return e ? atoi(e) : 0;
+}
+__global__ void combine_bias_kernel(const float* __restrict__ bih, const float* __restrict__ bhh, float* __restrict__ out,
+                                    int Hp) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < 3 * Hp) out[i] = bih[i] + (i < 2 * Hp ? bhh[i] : 0.f);
+}
+// layer-0 projection -> bf16, optionally adding the recurrent r/z biases (fused kernel variant 3)
+__global__ void gi0_to_bf16_kernel(const float* __restrict__ src, const float* __restrict__ bhh_rz, int Hp,
+                                   __nv_bfloat16* __restrict__ dst, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % (3 * Hp));
+    dst[i] = __float2bfloat16_rn(src[i] + ((bhh_rz && c < 2 * Hp) ? bhh_rz[c] : 0.f));
+  }
 }
 
 // ---- weight preparation ---------------------------------------------------------------------
@@ -299,6 +322,10 @@ int prep_weights(const Dims& d, const WS& w, const float* const* P, cudaStream_t
     }
     simt::pad_gate_vector_kernel<<<ceil_div(3 * Hp, 256), 256, 0, st>>>(P[P_BHH(l)], H, w.bhh_p[l], Hp);
     KCHECK();
+    if (l >= 1 && rec_variant(d) == 3) {
+      combine_bias_kernel<<<ceil_div(3 * Hp, 256), 256, 0, st>>>(w.bih_p[l], w.bhh_p[l], w.bcomb_p[l], Hp);
+      KCHECK();
+    }
   }
   simt::pad_matrix_kernel<TA><<<grid_for((long long)d.CP * Hp), 256, 0, st>>>(P[P_FC3W(d.L)], d.C, H, (TA*)w.W3_p, d.CP, Hp);
   KCHECK();
@@ -348,7 +375,7 @@ int run_forward(const Dims& d, const WS& w, const float* const* P, const uint8_t
     if (l >= 1) {
       const TA* X = (const TA*)w.hs[l - 1] + slab;
       RC(gemm<TA>(d, w, st, X, Hp, false, (const TA*)w.Wih_p[l], Hp, true, w.gi_all, 3 * Hp, true, T * Bp, 3 * Hp, Hp,
-                  w.bih_p[l], false, 1));
+                  rec_variant(d) == 3 ? w.bcomb_p[l] : w.bih_p[l], false, 1));
     }
     const int rv = rec_variant(d);
     if (rv > 0) {
@@ -356,8 +383,8 @@ int run_forward(const Dims& d, const WS& w, const float* const* P, const uint8_t
         const __nv_bfloat16* gi = (const __nv_bfloat16*)w.gi_all;
         long long gstride = (long long)Bp * 3 * Hp;
         if (l == 0) {
-          f32_to_bf16_kernel<<<grid_for((long long)Bp * 3 * Hp), 256, 0, st>>>(w.gi0, (__nv_bfloat16*)w.gi0_bf,
-                                                                               (long long)Bp * 3 * Hp);
+          gi0_to_bf16_kernel<<<grid_for((long long)Bp * 3 * Hp), 256, 0, st>>>(
+              w.gi0, rv == 3 ? w.bhh_p[0] : nullptr, Hp, (__nv_bfloat16*)w.gi0_bf, (long long)Bp * 3 * Hp);
           KCHECK();
           gi = (const __nv_bfloat16*)w.gi0_bf;
           gstride = 0;
@@ -368,7 +395,12 @@ int run_forward(const Dims& d, const WS& w, const float* const* P, const uint8_t
         ra.hs = (__nv_bfloat16*)hs; ra.sv = save ? (__nv_bfloat16*)sv : nullptr; ra.counters = w.counters;
         ra.err_flag = w.err_flag;
         count(2);
-        RC(mvae_gru_rec_launch(&ra, st));
+        if (rv == 3) {
+          ra.bhh = w.bhh_p[l] + 2 * Hp;
+          RC(mvae_gru_rec2_launch(&ra, fast_gates(), st));
+        } else {
+          RC(mvae_gru_rec_launch(&ra, st));
+        }
       }
       continue;
     }
@@ -433,7 +465,8 @@ int run_backward(const Dims& d, const WS& w, const float* const* P, float* const
         ra.dX = (const __nv_bfloat16*)dX; ra.dG = (__nv_bfloat16*)dG; ra.counters = w.counters;
         ra.err_flag = w.err_flag;
         count(2);
-        RC(mvae_gru_rec_launch(&ra, st));
+        if (rv == 3) RC(mvae_gru_rec2_launch(&ra, 0, st));
+        else RC(mvae_gru_rec_launch(&ra, st));
         if (l == 0) {
           dgi_time_sum_kernel<<<(unsigned)ceil_div64((long long)Bp * 3 * Hp, 256), 256, 0, st>>>(
               (const __nv_bfloat16*)dG, T, Bp, Hp, w.dgi0sum);

@@ -14,6 +14,7 @@
 // All waits are bounded (2 s) and report through err_flag instead of hanging the device.
 #include "common.cuh"
 #include "gru_rec.h"
+#include "rec_common.cuh"
 
 namespace {
 
@@ -36,101 +37,7 @@ struct RecParams {
   unsigned long long* trace; // optional [T][NTILES][8] timestamps of CTA (0,0) (debug)
 };
 
-__device__ __forceinline__ unsigned long long gtime() {
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-  return t;
-}
-__device__ __forceinline__ bool wait_bar(uint64_t* bar, uint32_t parity, int* err_flag) {
-  if (ptx::mbar_try_wait(bar, parity)) return true;
-  if (*(volatile int*)err_flag) return false;
-  uint32_t spins = 0;
-  unsigned long long t0 = 0;
-  while (!ptx::mbar_try_wait(bar, parity)) {
-    if ((++spins & 0x3FF) == 0) {
-      const unsigned long long now = gtime();
-      if (t0 == 0) t0 = now;
-      else if (now - t0 > 2000000000ull) { atomicExch(err_flag, 2); return false; }
-      if (*(volatile int*)err_flag) return false;
-    }
-  }
-  return true;
-}
-__device__ __forceinline__ unsigned int ld_acquire(const unsigned int* p) {
-  unsigned int v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void red_release_add(unsigned int* p, unsigned int v) {
-  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ bool wait_counter(const unsigned int* ctr, unsigned int target, int* err_flag) {
-  uint32_t spins = 0;
-  unsigned long long t0 = 0;
-  while (ld_acquire(ctr) < target) {
-    if ((++spins & 0xFF) == 0) {
-      const unsigned long long now = gtime();
-      if (t0 == 0) t0 = now;
-      else if (now - t0 > 2000000000ull) { atomicExch(err_flag, 3); return false; }
-      if (*(volatile int*)err_flag) return false;
-    }
-  }
-  return true;
-}
-__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n" ::"r"(
-          ptx::smem_u32(smem_dst)),
-      "l"(reinterpret_cast<uint64_t>(m)), "r"(ptx::smem_u32(bar)), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const float (&v)[16]) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
-      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};\n" ::"r"(taddr),
-      "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
-      "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
-      "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
-      "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
-      : "memory");
-}
-__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory"); }
-
-__device__ __forceinline__ float bf_lo(uint32_t u) { return __uint_as_float(u << 16); }
-__device__ __forceinline__ float bf_hi(uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); }
-__device__ __forceinline__ uint32_t pack_bf2(float a, float b) {
-  __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&t);
-}
-__device__ __forceinline__ void st16(__nv_bfloat16* dst, const float (&v)[16]) {
-  uint4 a, b;
-  a.x = pack_bf2(v[0], v[1]); a.y = pack_bf2(v[2], v[3]); a.z = pack_bf2(v[4], v[5]); a.w = pack_bf2(v[6], v[7]);
-  b.x = pack_bf2(v[8], v[9]); b.y = pack_bf2(v[10], v[11]); b.z = pack_bf2(v[12], v[13]); b.w = pack_bf2(v[14], v[15]);
-  reinterpret_cast<uint4*>(dst)[0] = a;
-  reinterpret_cast<uint4*>(dst)[1] = b;
-}
-__device__ __forceinline__ void unpack16(const uint4& a, const uint4& b, float (&v)[16]) {
-  v[0] = bf_lo(a.x); v[1] = bf_hi(a.x); v[2] = bf_lo(a.y); v[3] = bf_hi(a.y);
-  v[4] = bf_lo(a.z); v[5] = bf_hi(a.z); v[6] = bf_lo(a.w); v[7] = bf_hi(a.w);
-  v[8] = bf_lo(b.x); v[9] = bf_hi(b.x); v[10] = bf_lo(b.y); v[11] = bf_hi(b.y);
-  v[12] = bf_lo(b.z); v[13] = bf_hi(b.z); v[14] = bf_lo(b.w); v[15] = bf_hi(b.w);
-}
-
-#ifdef MVAE_FAST_GATES
-__device__ __forceinline__ float tanh_fast(float x) {
-  float y;
-  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-__device__ __forceinline__ float gate_sigmoid(float x) { return fmaf(0.5f, tanh_fast(0.5f * x), 0.5f); }
-__device__ __forceinline__ float gate_tanh(float x) { return tanh_fast(x); }
-#else
-__device__ __forceinline__ float gate_sigmoid(float x) { return 1.0f / (1.0f + __expf(-x)); }
-__device__ __forceinline__ float gate_tanh(float x) {
-  // tanh(x) = 1 - 2/(exp(2x)+1): two MUFU ops, ~1e-7 absolute error
-  return 1.0f - 2.0f / (__expf(2.0f * x) + 1.0f);
-}
-#endif
+using namespace rec;
 
 template <int RU, int NTILES, int STAGES, bool BWD> struct Cfg {
   static constexpr int NB = BWD ? RU : 3 * RU;           // MMA N = resident B rows

@@ -17,9 +17,14 @@ struct mvae_gru_rec_args {
   __nv_bfloat16* dG;         // bwd: [T][Bp][4Hp]
   unsigned int* counters;    // [Bp/128]
   int* err_flag;
+  int debug;                 // timing experiments only (gru_rec2): bit0 skip counter waits, bit1 de-share operand rows
   unsigned long long* trace; // optional debug timestamps [T][tiles per CTA][8] of CTA (0,0), may be null
 };
 
 // rows (molecules) one cooperative launch can cover on a device with num_sms SMs (0: shape unsupported)
 int mvae_gru_rec_max_rows(int Hp, int variant, int num_sms);
 int mvae_gru_rec_launch(const mvae_gru_rec_args* a, cudaStream_t stream);
+// 2-CTA / cluster-multicast version (gru_rec2.cu): Bp % 256 == 0, Hp in {256, 512}; a->bhh = n-gate slice of the
+// padded b_hh, b_hr / b_hz already folded into gi.
+int mvae_gru_rec2_launch(const mvae_gru_rec_args* a, int fast_gates, cudaStream_t stream);
+int mvae_gru_rec2_max_clusters(int backward, int cluster);

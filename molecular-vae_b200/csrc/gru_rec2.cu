@@ -1,0 +1,520 @@
+// Persistent fused GRU recurrence, 2-CTA tensor-core version (tcgen05 cta_group::2 + TMA multicast in clusters of 8).
+//
+// Why this shape (measured on B200, profiles/r01_rec_trace_v1.txt): with one CTA holding the whole W_hh slice
+// of 64 hidden units (192 KB) only 32 KB of shared memory is left for the streamed operand, and the 8 CTAs that
+// share a batch tile each pull the same h_{t-1} / dgh_{t+1} rows out of L2 -- the sweep ran at the L2 -> SM
+// bandwidth / latency limit (~32 us per step), not at the tensor pipe.  Here
+//   * a CTA PAIR owns 64 hidden units and issues M=256 MMAs (tcgen05.mma.cta_group::2): the resident weight
+//     slice is split over the pair (96 KB per CTA), leaving 8 x 16 KB operand stages per CTA;
+//   * 4 pairs form a cluster; the operand rows a CTA needs are also needed by the 3 same-parity CTAs of the
+//     cluster, so each loads a quarter of every stage and TMA-multicasts it (L2 reads / 4);
+//   * each CTA runs the gate epilogue for its own 128 rows x 64 units out of its own TMEM (16 epilogue warps),
+//     fp32 master copy of h (forward) / of the dh carry (backward) stays in TMEM columns.
+// Cross-pair dependencies (all 8 pairs of a row group must have published step t before step t+1 loads) go
+// through per-(tile, parity) global counters with release/acquire; everything inside a cluster uses mbarriers.
+// Every wait is bounded (2 s) and reports through err_flag.
+#include "common.cuh"
+#include "gru_rec.h"
+#include "rec_common.cuh"
+
+namespace {
+using namespace rec;
+
+constexpr int STAGES = 8;
+constexpr int NTILES = 2;                 // pair-tiles (256 rows) per pair
+constexpr int RU = 64;                    // hidden units per pair
+constexpr int A_STAGE = 128 * 64 * 2;     // this CTA's 128 rows x 64 k, bf16
+constexpr int EPI_WARPS = 16;
+constexpr int THREADS = (2 + EPI_WARPS) * 32;
+constexpr int EPI_BAR = 1;
+
+struct Params2 {
+  int Bp, Hp, T, pair_tiles, npairs;
+  const __nv_bfloat16* gi; long long gi_tstride;
+  const float* bhn;          // fwd: b_hh of the n gate, padded [Hp]  (b_hr, b_hz are folded into gi)
+  __nv_bfloat16* hs; __nv_bfloat16* sv;
+  const __nv_bfloat16* dX; __nv_bfloat16* dG;
+  unsigned int* counters;    // [pair_tiles][2]
+  int* err_flag;
+  unsigned long long* trace; // optional debug timestamps [T][NTILES][12] of CTA (0,0)
+  int debug;                 // timing experiments only: bit0 skip counter waits, bit1 de-share operand rows
+};
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release;\n" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire;\n" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa(uint32_t local_smem_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void remote_arrive(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_mc(void* smem_dst, const CUtensorMap* m, uint64_t* bar, uint16_t mask,
+                                               int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%4, %5, %6}], [%2], %3;\n" ::"r"(ptx::smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(ptx::smem_u32(bar)), "h"(mask), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+// 2-CTA TMA loads: data lands in the executing CTA's smem, the transaction bytes are reported to an mbarrier that
+// may live in the peer CTA (the pair leader) -- address given in the shared::cluster window.
+__device__ __forceinline__ void tma_load_3d_2sm(void* smem_dst, const CUtensorMap* m, uint32_t bar_cluster_addr, int c0,
+                                                int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5}], [%2];\n" ::"r"(ptx::smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* m, uint32_t bar_cluster_addr, int c0,
+                                                int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];\n" ::"r"(ptx::smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void remote_arrive_relaxed(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t* holder, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(ptx::smem_u32(holder)),
+               "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;\n" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;\n" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma2_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                           uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void commit2_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n" ::"r"(
+          ptx::smem_u32(bar)),
+      "h"(mask)
+      : "memory");
+}
+
+template <bool BWD, bool FAST, int CL>
+__global__ void __launch_bounds__(THREADS, 1)
+gru_rec2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmA, const Params2 p) {
+  constexpr int NB = BWD ? RU : 3 * RU;        // MMA N of the pair
+  constexpr int NBH = NB / 2;                  // resident rows per CTA
+  constexpr int CHUNK = NBH * 128;             // bytes of one 64-wide K chunk of the resident half
+  constexpr int MASTER0 = NTILES * NB;
+  constexpr int TMEM_COLS = BWD ? 256 : 512;
+  constexpr int NSAME = CL / 2;                // same-parity CTAs (= pairs) per cluster
+  constexpr int A_PART = A_STAGE / NSAME;      // bytes of a stage this CTA loads and multicasts
+  constexpr int A_PART_ROWS = 128 / NSAME;
+  static_assert(NTILES * (NB + RU) <= TMEM_COLS, "TMEM");
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int KC = (BWD ? 3 * p.Hp : p.Hp) / 64;
+  uint8_t* sW = smem;
+  uint8_t* sA = smem + (size_t)KC * CHUNK;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sA + STAGES * A_STAGE);
+  uint64_t* full_bar = bars;                         // [STAGES] own operand stage landed (tx)
+  uint64_t* empty_bar = bars + STAGES;               // [STAGES] all 4 pairs of the cluster consumed the stage
+  uint64_t* pfull_bar = bars + 2 * STAGES;           // [STAGES] leader: peer's stage landed (relayed)
+  uint64_t* tfull_bar = bars + 3 * STAGES;           // [NTILES] accumulator ready (both CTAs)
+  uint64_t* tempty_bar = tfull_bar + NTILES;         // [NTILES] leader: both CTAs drained the accumulator
+  uint64_t* wfull_bar = tempty_bar + NTILES;         // resident weights landed
+  uint64_t* pwfull_bar = wfull_bar + 1;              // leader: peer's weights landed
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(pwfull_bar + 1);
+  float* sBias = reinterpret_cast<float*>(tmem_holder + 2);  // fwd: b_hn for the pair's 64 units
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int parity = rank & 1;
+  const bool leader = parity == 0;
+  const int pair = blockIdx.x >> 1;                   // global pair index along the hidden dimension
+  const int u0 = pair * RU;
+  const int tile0 = blockIdx.y * NTILES;
+  const int ntiles = min(NTILES, p.pair_tiles - tile0);
+  const uint16_t mask_par = (uint16_t)((CL == 8 ? 0x55 : CL == 4 ? 0x5 : 0x1) << parity);  // same-parity CTAs
+  const uint16_t mask_pair = (uint16_t)(3u << (rank & ~1u));
+  const int qd = rank >> 1;                           // which 32-row quarter of the operand tile this CTA loads
+
+  if (threadIdx.x == 0) {
+    ptx::tma_prefetch_desc(&tmW);
+    ptx::tma_prefetch_desc(&tmA);
+    for (int s = 0; s < STAGES; ++s) {
+      ptx::mbar_init(&full_bar[s], 1);
+      ptx::mbar_init(&empty_bar[s], NSAME);
+      ptx::mbar_init(&pfull_bar[s], 1);
+    }
+    for (int i = 0; i < NTILES; ++i) { ptx::mbar_init(&tfull_bar[i], 1); ptx::mbar_init(&tempty_bar[i], 2); }
+    ptx::mbar_init(wfull_bar, 1);
+    ptx::mbar_init(pwfull_bar, 1);
+    ptx::fence_mbar_init();
+  }
+  if (!BWD) for (int i = threadIdx.x; i < RU; i += THREADS) sBias[i] = p.bhn[u0 + i];
+  if (warp == 1) tmem_alloc2(tmem_holder, TMEM_COLS);
+  ptx::tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  if (warp == 0) {
+    // ===================== TMA producer (every CTA) =====================
+    if (lane == 0) {
+      constexpr bool DIRECT = (CL == 2);   // pair-only clusters: both CTAs' TMA report straight to the leader's barriers
+      const uint32_t lrank = rank & ~1u;
+      const uint32_t wbar_addr = DIRECT ? mapa(ptx::smem_u32(wfull_bar), lrank) : ptx::smem_u32(wfull_bar);
+      if (DIRECT) { if (leader) ptx::mbar_arrive_expect_tx(wfull_bar, (uint32_t)(2 * KC * CHUNK)); }
+      else ptx::mbar_arrive_expect_tx(wfull_bar, (uint32_t)(KC * CHUNK));
+      for (int kc = 0; kc < KC; ++kc) {
+        uint8_t* dst = sW + (size_t)kc * CHUNK;
+        if (BWD) {
+          if (DIRECT) tma_load_2d_2sm(dst, &tmW, wbar_addr, kc * 64, u0 + 32 * parity);
+          else tma_load_2d(dst, &tmW, wfull_bar, kc * 64, u0 + 32 * parity);     // 32 rows of W_hh^T
+        } else {
+#pragma unroll
+          for (int b = 0; b < 3; ++b) {                                     // 3 boxes of 32 gate rows
+            const int n = 96 * parity + 32 * b;                             // row inside the pair's [r|z|n] x 64 block
+            if (DIRECT) tma_load_2d_2sm(dst + b * 4096, &tmW, wbar_addr, kc * 64, (n >> 6) * p.Hp + u0 + (n & 63));
+            else tma_load_2d(dst + b * 4096, &tmW, wfull_bar, kc * 64, (n >> 6) * p.Hp + u0 + (n & 63));
+          }
+        }
+      }
+      int s = 0; uint32_t ph = 0;
+      for (int step = 1; step < p.T; ++step) {
+        int slab = BWD ? (p.T - step) : step;
+        if (p.debug & 2) slab = (slab + pair * 5) % p.T;
+        for (int i = 0; i < ntiles; ++i) {
+          const int tile = tile0 + i;
+          if (!(p.debug & 1) && !wait_counter(p.counters + tile * 2 + parity, (unsigned)(p.npairs * step), p.err_flag)) goto done;
+          ptx::fence_proxy_async_all();
+          if (p.trace && blockIdx.x == 0 && blockIdx.y == 0) p.trace[((size_t)step * NTILES + i) * 12 + 0] = gtime();
+          const int row0 = tile * 256 + parity * 128 + qd * A_PART_ROWS;
+          for (int kc = 0; kc < KC; ++kc) {
+            if (!wait_bar(&empty_bar[s], ph ^ 1, p.err_flag)) goto done;
+            if (DIRECT) {
+              if (leader) ptx::mbar_arrive_expect_tx(&full_bar[s], 2 * A_STAGE);
+              tma_load_3d_2sm(sA + s * A_STAGE, &tmA, mapa(ptx::smem_u32(&full_bar[s]), lrank), kc * 64, row0, slab);
+            } else {
+              ptx::mbar_arrive_expect_tx(&full_bar[s], A_STAGE);
+              tma_load_3d_mc(sA + s * A_STAGE + qd * A_PART, &tmA, &full_bar[s], mask_par, kc * 64, row0, slab);
+            }
+            if (++s == STAGES) { s = 0; ph ^= 1; }
+          }
+          if (p.trace && blockIdx.x == 0 && blockIdx.y == 0) p.trace[((size_t)step * NTILES + i) * 12 + 1] = gtime();
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      if (!leader && CL == 2) {
+        // pair-only clusters need no relay: the peer's TMA reports directly to the leader's barriers
+      } else if (!leader) {
+        // ===================== relay (odd CTA): forward "my stage landed" to the pair leader =====================
+        const uint32_t lrank = rank & ~1u;
+        if (!wait_bar(wfull_bar, 0, p.err_flag)) goto done;
+        remote_arrive_relaxed(mapa(ptx::smem_u32(pwfull_bar), lrank));
+        int s = 0; uint32_t ph = 0;
+        for (int step = 1; step < p.T; ++step)
+          for (int i = 0; i < ntiles; ++i)
+            for (int kc = 0; kc < KC; ++kc) {
+              if (!wait_bar(&full_bar[s], ph, p.err_flag)) goto done;
+              remote_arrive_relaxed(mapa(ptx::smem_u32(&pfull_bar[s]), lrank));
+              if (++s == STAGES) { s = 0; ph ^= 1; }
+            }
+      } else {
+        // ===================== MMA issuer (even CTA, one thread for the pair) =====================
+        constexpr uint32_t idesc = ptx::umma_idesc_bf16(256, NB, 0, 0);
+        if (!wait_bar(wfull_bar, 0, p.err_flag)) goto done;
+        if (CL != 2 && !wait_bar(pwfull_bar, 0, p.err_flag)) goto done;
+        int s = 0; uint32_t ph = 0;
+        for (int step = 0; step < p.T; ++step) {
+          for (int i = 0; i < ntiles; ++i) {
+            if (step > 0) {
+              if (!wait_bar(&tempty_bar[i], (uint32_t)((step - 1) & 1), p.err_flag)) goto done;
+              ptx::tc_fence_after();
+              const uint32_t d_tmem = tmem_base + i * NB;
+              for (int kc = 0; kc < KC; ++kc) {
+                const bool trm = p.trace && blockIdx.x == 0 && blockIdx.y == 0;
+                if (!wait_bar(&full_bar[s], ph, p.err_flag)) goto done;
+                if (trm && kc == 0) p.trace[((size_t)step * NTILES + i) * 12 + 2] = gtime();
+                if (trm && kc == KC - 1) p.trace[((size_t)step * NTILES + i) * 12 + 9] = gtime();
+                if (CL != 2 && !wait_bar(&pfull_bar[s], ph, p.err_flag)) goto done;
+                if (trm && kc == 0) p.trace[((size_t)step * NTILES + i) * 12 + 8] = gtime();
+                if (trm && kc == KC - 1) p.trace[((size_t)step * NTILES + i) * 12 + 10] = gtime();
+                ptx::tc_fence_after();
+                const uint32_t a_addr = ptx::smem_u32(sA + s * A_STAGE);
+                const uint32_t b_addr = ptx::smem_u32(sW + (size_t)kc * CHUNK);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  const uint64_t adesc = ptx::umma_smem_desc_sw128(a_addr + k * 32, 16, 1024);
+                  const uint64_t bdesc = ptx::umma_smem_desc_sw128(b_addr + k * 32, 16, 1024);
+                  umma2_bf16(d_tmem, adesc, bdesc, idesc, (kc > 0 || k > 0) ? 1u : 0u);
+                }
+                commit2_mc(&empty_bar[s], (uint16_t)((1u << CL) - 1));      // stage s is free in every CTA of the cluster (for this pair)
+                if (++s == STAGES) { s = 0; ph ^= 1; }
+              }
+            }
+            commit2_mc(&tfull_bar[i], mask_pair);     // accumulator i complete -> both epilogues
+            if (p.trace && blockIdx.x == 0 && blockIdx.y == 0) p.trace[((size_t)step * NTILES + i) * 12 + 3] = gtime();
+          }
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue warps (every CTA: own 128 rows x 64 units) =====================
+    const int q = warp & 3;
+    const int part = (warp - 2) >> 2;          // 0..3 -> 16 units each
+    const int uc = part * 16;
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    const uint32_t tempty_remote = mapa(ptx::smem_u32(&tempty_bar[0]), rank & ~1u);
+    uint32_t fph = 0;
+    for (int step = 0; step < p.T; ++step) {
+      const int t = BWD ? (p.T - 1 - step) : step;
+      for (int i = 0; i < ntiles; ++i) {
+        const int tile = tile0 + i;
+        const long long row = (long long)tile * 256 + parity * 128 + q * 32 + lane;
+        // saved activations use a per-thread "fragment" layout (consumed only by the BPTT epilogue with the same
+        // thread mapping): block (t, tile, pair, parity, part, array) of 4 KB, thread (q, lane) owns 32 B -> every
+        // warp-wide 256-bit access is 1 KB contiguous.
+        const size_t sv_blk = ((((size_t)t * p.pair_tiles + tile) * p.npairs + pair) * 2 + parity) * 4 + part;
+        __nv_bfloat16* svp = p.sv ? p.sv + sv_blk * 4 * 2048 + (size_t)(q * 32 + lane) * 16 : nullptr;
+        u32x8 pre[BWD ? 6 : 3];
+        if (!BWD) {
+          const __nv_bfloat16* g = p.gi + (long long)t * p.gi_tstride + row * 3 * p.Hp + u0 + uc;
+#pragma unroll
+          for (int gate = 0; gate < 3; ++gate) pre[gate] = ldg256(g + (long long)gate * p.Hp);
+        } else {
+#pragma unroll
+          for (int blk = 0; blk < 4; ++blk) pre[blk] = ldg256(svp + blk * 2048);
+          pre[4] = ldg256(p.hs + ((long long)t * p.Bp + row) * p.Hp + u0 + uc);
+          pre[5] = ldg256(p.dX + ((long long)t * p.Bp + row) * p.Hp + u0 + uc);
+        }
+        (void)wait_bar(&tfull_bar[i], fph, p.err_flag);   // on failure keep walking: barriers below must be reached
+        ptx::tc_fence_after();
+        const bool tr = p.trace && blockIdx.x == 0 && blockIdx.y == 0 && warp == 2 && lane == 0;
+        if (tr) p.trace[((size_t)step * NTILES + i) * 12 + 4] = gtime();
+        const uint32_t master_addr = tmem_base + lane_off + MASTER0 + i * RU + uc;
+        if (!BWD) {
+          uint32_t ar[16], az[16], an[16], hm[16];
+          if (step > 0) {
+            const uint32_t acc = tmem_base + lane_off + i * NB + uc;
+            ptx::tmem_ld_32x16(acc, ar);
+            ptx::tmem_ld_32x16(acc + RU, az);
+            ptx::tmem_ld_32x16(acc + 2 * RU, an);
+            ptx::tmem_ld_32x16(master_addr, hm);
+            ptx::tmem_ld_wait();
+          } else {
+#pragma unroll
+            for (int k = 0; k < 16; ++k) { ar[k] = 0u; az[k] = 0u; an[k] = 0u; hm[k] = 0u; }
+          }
+          float gr[16], gz[16], gn[16];
+          unpack16(pre[0], gr);
+          unpack16(pre[1], gz);
+          unpack16(pre[2], gn);
+          float h[16];
+#pragma unroll
+          for (int k = 0; k < 16; ++k) {
+            const float ghn = __uint_as_float(an[k]) + sBias[uc + k];
+            const float r = gate_sigmoid_t<FAST>(gr[k] + __uint_as_float(ar[k]));   // b_hr folded into gi
+            const float z = gate_sigmoid_t<FAST>(gz[k] + __uint_as_float(az[k]));   // b_hz folded into gi
+            const float n = gate_tanh_t<FAST>(fmaf(r, ghn, gn[k]));
+            h[k] = fmaf(z, __uint_as_float(hm[k]) - n, n);
+            gr[k] = r; gz[k] = z; gn[k] = n;
+            an[k] = __float_as_uint(ghn);
+          }
+          tmem_st_32x16(master_addr, h);
+          stg256(p.hs + ((long long)(t + 1) * p.Bp + row) * p.Hp + u0 + uc, h);
+          if (svp) {
+            stg256(svp, gr);
+            stg256(svp + 2048, gz);
+            stg256(svp + 2 * 2048, gn);
+#pragma unroll
+            for (int k = 0; k < 16; ++k) h[k] = __uint_as_float(an[k]);
+            stg256(svp + 3 * 2048, h);
+          }
+        } else {
+          uint32_t acc[16], cm[16];
+          if (step > 0) {
+            ptx::tmem_ld_32x16(tmem_base + lane_off + i * NB + uc, acc);
+            ptx::tmem_ld_32x16(master_addr, cm);
+            ptx::tmem_ld_wait();
+          } else {
+#pragma unroll
+            for (int k = 0; k < 16; ++k) { acc[k] = 0u; cm[k] = 0u; }
+          }
+          float r[16], z[16], n[16], ghn[16], hp[16], dx[16];
+          unpack16(pre[0], r);
+          unpack16(pre[1], z);
+          unpack16(pre[2], n);
+          unpack16(pre[3], ghn);
+          unpack16(pre[4], hp);
+          unpack16(pre[5], dx);
+          float carry[16];
+#pragma unroll
+          for (int k = 0; k < 16; ++k) {
+            const float dh = __uint_as_float(acc[k]) + __uint_as_float(cm[k]) + dx[k];
+            const float dan = dh * (1.f - z[k]) * (1.f - n[k] * n[k]);
+            const float daz = dh * (hp[k] - n[k]) * z[k] * (1.f - z[k]);
+            const float dar = dan * ghn[k] * r[k] * (1.f - r[k]);
+            carry[k] = dh * z[k];
+            hp[k] = dan * r[k];   // da_n * r
+            n[k] = dan; ghn[k] = dar; dx[k] = daz;
+          }
+          tmem_st_32x16(master_addr, carry);
+          __nv_bfloat16* g4 = p.dG + ((long long)t * p.Bp + row) * 4 * p.Hp + u0 + uc;
+          stg256(g4, n);
+          stg256(g4 + p.Hp, ghn);
+          stg256(g4 + 2 * p.Hp, dx);
+          stg256(g4 + 3 * p.Hp, hp);
+        }
+        tmem_st_wait();
+        ptx::tc_fence_before();
+        if (tr) p.trace[((size_t)step * NTILES + i) * 12 + 5] = gtime();
+        asm volatile("bar.sync %0, %1;" ::"n"(EPI_BAR), "n"(EPI_WARPS * 32) : "memory");
+        if (warp == 2 && lane == 0) {
+          remote_arrive(tempty_remote + (uint32_t)(i * 8));    // accumulator i drained in this CTA -> pair leader
+          if (tr) p.trace[((size_t)step * NTILES + i) * 12 + 6] = gtime();
+          __threadfence();                                     // cumulative over the CTA's stores (ordered by bar.sync)
+          ptx::fence_proxy_async_all();
+          red_release_add(p.counters + tile * 2 + parity, 1u);
+          if (tr) p.trace[((size_t)step * NTILES + i) * 12 + 7] = gtime();
+        }
+      }
+      fph ^= 1;
+    }
+  }
+done:
+  ptx::tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();   // nobody leaves while cluster peers may still signal its barriers / multicast into its smem
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    tmem_dealloc2(tmem_base, TMEM_COLS);
+  }
+}
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+      qres != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = reinterpret_cast<PFN_encodeTiled>(p);
+  return fn;
+}
+int encode(CUtensorMap* map, const void* ptr, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+           const cuuint32_t* box) {
+  PFN_encodeTiled enc = get_encode_fn();
+  if (!enc) return MVAE_ERR_DRIVER;
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(ptr), dims, strides_bytes, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? MVAE_OK : MVAE_ERR_DRIVER;
+}
+
+template <bool BWD, bool FAST, int CL>
+int launch2(const mvae_gru_rec_args& a, cudaStream_t st) {
+  const int Hp = a.Hp, Bp = a.Bp, T = a.T;
+  constexpr int NBH = (BWD ? RU : 3 * RU) / 2;
+  const int KC = (BWD ? 3 * Hp : Hp) / 64;
+  const size_t smem = (size_t)KC * NBH * 128 + (size_t)STAGES * A_STAGE + 1024 + 1024;
+  if (smem > 232448) return MVAE_ERR_UNSUPPORTED;
+  CUtensorMap tmW, tmA;
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)(BWD ? 3 * Hp : Hp), (cuuint64_t)(BWD ? Hp : 3 * Hp)};
+    cuuint64_t str[1] = {(cuuint64_t)(BWD ? 3 * Hp : Hp) * 2};
+    cuuint32_t box[2] = {64, 32};
+    int rc = encode(&tmW, a.W, 2, dims, str, box);
+    if (rc) return rc;
+  }
+  {
+    cuuint32_t box[3] = {64, (cuuint32_t)(128 / (CL / 2)), 1};
+    if (BWD) {
+      cuuint64_t dims[3] = {(cuuint64_t)3 * Hp, (cuuint64_t)Bp, (cuuint64_t)T};
+      cuuint64_t str[2] = {(cuuint64_t)4 * Hp * 2, (cuuint64_t)Bp * 4 * Hp * 2};
+      int rc = encode(&tmA, a.dG + Hp, 3, dims, str, box);
+      if (rc) return rc;
+    } else {
+      cuuint64_t dims[3] = {(cuuint64_t)Hp, (cuuint64_t)Bp, (cuuint64_t)(T + 1)};
+      cuuint64_t str[2] = {(cuuint64_t)Hp * 2, (cuuint64_t)Bp * Hp * 2};
+      int rc = encode(&tmA, a.hs, 3, dims, str, box);
+      if (rc) return rc;
+    }
+  }
+  Params2 p{};
+  p.Bp = Bp; p.Hp = Hp; p.T = T; p.pair_tiles = Bp / 256; p.npairs = Hp / RU;
+  p.gi = a.gi; p.gi_tstride = a.gi_tstride; p.bhn = a.bhh; p.hs = a.hs; p.sv = a.sv; p.dX = a.dX; p.dG = a.dG;
+  p.counters = a.counters; p.err_flag = a.err_flag; p.trace = a.trace; p.debug = a.debug;
+  auto kern = gru_rec2_kernel<BWD, FAST, CL>;
+  static bool attr = false;
+  if (!attr) {
+    MVAE_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = true;
+  }
+  MVAE_CUDA_CHECK(cudaMemsetAsync(a.counters, 0, sizeof(unsigned int) * 2 * (Bp / 256), st));
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(Hp / 32, ceil_div(Bp / 256, NTILES), 1);
+  cfg.blockDim = dim3(THREADS, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  MVAE_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, tmW, tmA, p));
+  return MVAE_OK;
+}
+
+template <int CL> int max_clusters_t(int backward) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(16, 8, 1); cfg.blockDim = dim3(THREADS, 1, 1); cfg.dynamicSmemBytes = 231424;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  int n = -1;
+  if (backward) { cudaFuncSetAttribute(gru_rec2_kernel<true, false, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 231424); cudaOccupancyMaxActiveClusters(&n, gru_rec2_kernel<true, false, CL>, &cfg); }
+  else { cudaFuncSetAttribute(gru_rec2_kernel<false, false, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 231424); cudaOccupancyMaxActiveClusters(&n, gru_rec2_kernel<false, false, CL>, &cfg); }
+  return n;
+}
+}  // namespace
+
+int mvae_gru_rec2_max_clusters(int backward, int cluster) {
+  return cluster == 8 ? max_clusters_t<8>(backward) : cluster == 4 ? max_clusters_t<4>(backward) : max_clusters_t<2>(backward);
+}
+
+// variant 3.  Requires Bp % 256 == 0 and Hp in {256, 512}.  a->bhh must point at the n-gate slice of the padded
+// b_hh (b_hr / b_hz are expected to be folded into gi by the caller).  a->variant: 3 -> clusters of 2 (pair only),
+// 34 -> clusters of 4, 38 -> clusters of 8 (operand multicast across the pairs of a cluster).
+int mvae_gru_rec2_launch(const mvae_gru_rec_args* a, int fast_gates, cudaStream_t stream) {
+  if (!a || a->Bp % 256 || (a->Hp != 256 && a->Hp != 512) || a->T < 1) return MVAE_ERR_INVALID;
+  const int cl = a->variant == 38 ? 8 : a->variant == 34 ? 4 : 2;
+#define MVAE_DISPATCH(CLV)                                                                     \
+  if (a->backward) return launch2<true, false, CLV>(*a, stream);                                \
+  return fast_gates ? launch2<false, true, CLV>(*a, stream) : launch2<false, false, CLV>(*a, stream);
+  if (cl == 8) { MVAE_DISPATCH(8) }
+  if (cl == 4) { MVAE_DISPATCH(4) }
+  MVAE_DISPATCH(2)
+#undef MVAE_DISPATCH
+}

@@ -11,13 +11,15 @@ int main(int argc, char** argv) {
   const int variant = argc > 1 ? atoi(argv[1]) : 1;
   const int B = argc > 2 ? atoi(argv[2]) : 4096;
   const int T = argc > 3 ? atoi(argv[3]) : 120;
+  const int fast = argc > 4 ? atoi(argv[4]) : 0;
+  const int debug = argc > 5 ? atoi(argv[5]) : 0;
   const int Hp = 512;
   const size_t slab = (size_t)B * Hp;
   __nv_bfloat16 *W, *WT, *gi, *hs, *sv, *dX, *dG; float* bhh; unsigned* ctr; int* err; unsigned long long* trace;
   cudaMalloc(&W, 3 * Hp * Hp * 2); cudaMalloc(&WT, 3 * Hp * Hp * 2);
   cudaMalloc(&gi, (size_t)T * B * 3 * Hp * 2); cudaMalloc(&hs, (T + 1) * slab * 2); cudaMalloc(&sv, T * slab * 4 * 2);
   cudaMalloc(&dX, T * slab * 2); cudaMalloc(&dG, T * slab * 4 * 2); cudaMalloc(&bhh, 3 * Hp * 4);
-  cudaMalloc(&ctr, 4096); cudaMalloc(&err, 4); cudaMalloc(&trace, (size_t)T * 4 * 8 * 8);
+  cudaMalloc(&ctr, 4096); cudaMalloc(&err, 4); cudaMalloc(&trace, (size_t)T * 4 * 12 * 8);
   // small random-ish contents
   std::vector<__nv_bfloat16> h(3 * Hp * Hp);
   unsigned s = 1;
@@ -26,17 +28,19 @@ int main(int argc, char** argv) {
   cudaMemcpy(WT, h.data(), h.size() * 2, cudaMemcpyHostToDevice);
   cudaMemset(gi, 0x3c, (size_t)T * B * 3 * Hp * 2); cudaMemset(hs, 0, (T + 1) * slab * 2);
   cudaMemset(dX, 0x30, T * slab * 2); cudaMemset(bhh, 0, 3 * Hp * 4); cudaMemset(err, 0, 4);
-  cudaMemset(trace, 0, (size_t)T * 4 * 8 * 8);
+  cudaMemset(trace, 0, (size_t)T * 4 * 12 * 8);
   for (int bwd = 0; bwd < 2; ++bwd) {
     mvae_gru_rec_args a{};
     a.backward = bwd; a.variant = variant; a.Bp = B; a.Hp = Hp; a.T = T;
     a.W = bwd ? WT : W; a.gi = gi; a.gi_tstride = (long long)B * 3 * Hp; a.bhh = bhh; a.hs = hs; a.sv = sv; a.dX = dX; a.dG = dG;
-    a.counters = ctr; a.err_flag = err; a.trace = nullptr;
+    a.counters = ctr; a.err_flag = err; a.trace = nullptr; a.debug = debug;
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-    int rc = mvae_gru_rec_launch(&a, 0);
+    auto launch = [&](const mvae_gru_rec_args* aa) { return variant >= 3 ? mvae_gru_rec2_launch(aa, fast, 0) : mvae_gru_rec_launch(aa, 0); };
+    if (variant >= 3) printf("max active clusters (%s): cl2=%d cl4=%d cl8=%d\n", bwd ? "bwd" : "fwd", mvae_gru_rec2_max_clusters(bwd, 2), mvae_gru_rec2_max_clusters(bwd, 4), mvae_gru_rec2_max_clusters(bwd, 8));
+    int rc = launch(&a);
     cudaDeviceSynchronize();
     cudaEventRecord(e0);
-    for (int i = 0; i < 3; ++i) rc |= mvae_gru_rec_launch(&a, 0);
+    for (int i = 0; i < 3; ++i) rc |= launch(&a);
     cudaEventRecord(e1);
     cudaError_t e = cudaDeviceSynchronize();
     float ms; cudaEventElapsedTime(&ms, e0, e1); ms /= 3;
@@ -46,18 +50,19 @@ int main(int argc, char** argv) {
     if (rc) printf("  %s\n", mvae_last_cuda_error());
     // traced run
     a.trace = trace;
-    mvae_gru_rec_launch(&a, 0);
+    launch(&a);
     cudaDeviceSynchronize();
     const int NT = variant == 2 ? 4 : 2;
-    std::vector<unsigned long long> tr((size_t)T * NT * 8);
+    const int NS = variant >= 3 ? 12 : 8;
+    std::vector<unsigned long long> tr((size_t)T * NT * NS);
     cudaMemcpy(tr.data(), trace, tr.size() * 8, cudaMemcpyDeviceToHost);
     printf("  trace CTA(0,0), ns relative to counter-ok of (step, tile 0): [ctr_ok, tma_issued, first_full, mma_issued, tfull_seen, epi_done, fenced, red_done]\n");
     for (int step : {1, 2, 60, 61}) {
       if (step >= T) continue;
-      unsigned long long base = tr[((size_t)step * NT + 0) * 8 + 0];
+      unsigned long long base = tr[((size_t)step * NT + 0) * NS + 0];
       for (int i = 0; i < NT; ++i) {
         printf("  step %3d tile %d:", step, i);
-        for (int k = 0; k < 8; ++k) printf(" %7lld", (long long)(tr[((size_t)step * NT + i) * 8 + k] - base));
+        for (int k = 0; k < NS; ++k) printf(" %7lld", (long long)(tr[((size_t)step * NT + i) * NS + k] - base));
         printf("\n");
       }
     }
