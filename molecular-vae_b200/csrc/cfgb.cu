@@ -273,8 +273,8 @@ int rec_variant(const Dims& d) {
     if (cudaGetDevice(&dev) != cudaSuccess) return 0;
     if (cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
   }
-  if (v == 3) {
-    if (d.Hp == 256 || d.Hp == 512) return 3;
+  if (v >= 3) {  // 3: pair clusters, 34 / 38: clusters of 4 / 8 with operand multicast
+    if (d.Hp == 256 || d.Hp == 512) return v;
     v = 1;
   }
   if (d.Bp > mvae_gru_rec_max_rows(d.Hp, v, g_sm_count)) return 0;
@@ -322,7 +322,7 @@ int prep_weights(const Dims& d, const WS& w, const float* const* P, cudaStream_t
     }
     simt::pad_gate_vector_kernel<<<ceil_div(3 * Hp, 256), 256, 0, st>>>(P[P_BHH(l)], H, w.bhh_p[l], Hp);
     KCHECK();
-    if (l >= 1 && rec_variant(d) == 3) {
+    if (l >= 1 && rec_variant(d) >= 3) {
       combine_bias_kernel<<<ceil_div(3 * Hp, 256), 256, 0, st>>>(w.bih_p[l], w.bhh_p[l], w.bcomb_p[l], Hp);
       KCHECK();
     }
@@ -375,7 +375,7 @@ int run_forward(const Dims& d, const WS& w, const float* const* P, const uint8_t
     if (l >= 1) {
       const TA* X = (const TA*)w.hs[l - 1] + slab;
       RC(gemm<TA>(d, w, st, X, Hp, false, (const TA*)w.Wih_p[l], Hp, true, w.gi_all, 3 * Hp, true, T * Bp, 3 * Hp, Hp,
-                  rec_variant(d) == 3 ? w.bcomb_p[l] : w.bih_p[l], false, 1));
+                  rec_variant(d) >= 3 ? w.bcomb_p[l] : w.bih_p[l], false, 1));
     }
     const int rv = rec_variant(d);
     if (rv > 0) {
@@ -384,7 +384,7 @@ int run_forward(const Dims& d, const WS& w, const float* const* P, const uint8_t
         long long gstride = (long long)Bp * 3 * Hp;
         if (l == 0) {
           gi0_to_bf16_kernel<<<grid_for((long long)Bp * 3 * Hp), 256, 0, st>>>(
-              w.gi0, rv == 3 ? w.bhh_p[0] : nullptr, Hp, (__nv_bfloat16*)w.gi0_bf, (long long)Bp * 3 * Hp);
+              w.gi0, rv >= 3 ? w.bhh_p[0] : nullptr, Hp, (__nv_bfloat16*)w.gi0_bf, (long long)Bp * 3 * Hp);
           KCHECK();
           gi = (const __nv_bfloat16*)w.gi0_bf;
           gstride = 0;
@@ -395,7 +395,7 @@ int run_forward(const Dims& d, const WS& w, const float* const* P, const uint8_t
         ra.hs = (__nv_bfloat16*)hs; ra.sv = save ? (__nv_bfloat16*)sv : nullptr; ra.counters = w.counters;
         ra.err_flag = w.err_flag;
         count(2);
-        if (rv == 3) {
+        if (rv >= 3) {
           ra.bhh = w.bhh_p[l] + 2 * Hp;
           RC(mvae_gru_rec2_launch(&ra, fast_gates(), st));
         } else {
@@ -465,7 +465,7 @@ int run_backward(const Dims& d, const WS& w, const float* const* P, float* const
         ra.dX = (const __nv_bfloat16*)dX; ra.dG = (__nv_bfloat16*)dG; ra.counters = w.counters;
         ra.err_flag = w.err_flag;
         count(2);
-        if (rv == 3) RC(mvae_gru_rec2_launch(&ra, 0, st));
+        if (rv >= 3) RC(mvae_gru_rec2_launch(&ra, 0, st));
         else RC(mvae_gru_rec_launch(&ra, st));
         if (l == 0) {
           dgi_time_sum_kernel<<<(unsigned)ceil_div64((long long)Bp * 3 * Hp, 256), 256, 0, st>>>(

@@ -25,7 +25,8 @@ constexpr int NTILES = 2;                 // pair-tiles (256 rows) per pair
 constexpr int RU = 64;                    // hidden units per pair
 constexpr int A_STAGE = 128 * 64 * 2;     // this CTA's 128 rows x 64 k, bf16
 constexpr int EPI_WARPS = 16;
-constexpr int THREADS = (2 + EPI_WARPS) * 32;
+constexpr int THREADS = (3 + EPI_WARPS) * 32;   // + producer, MMA issuer, publisher
+constexpr int PUB_WARP = 2 + EPI_WARPS;
 constexpr int EPI_BAR = 1;
 
 struct Params2 {
@@ -83,6 +84,17 @@ __device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMa
       "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
       : "memory");
 }
+// 2-CTA multicast load: the box is written at the same smem offset of every CTA in `mask`; the transaction bytes are
+// reported, for each destination, to the mbarrier at `bar` offset in that destination's PAIR LEADER (peer bit cleared).
+__device__ __forceinline__ void tma_load_3d_2sm_mc(void* smem_dst, const CUtensorMap* m, uint64_t* bar, uint16_t mask,
+                                                   int c0, int c1, int c2) {
+  const uint32_t bar_addr = ptx::smem_u32(bar) & 0xFEFFFFFFu;
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%4, %5, %6}], [%2], %3;\n" ::"r"(ptx::smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_addr), "h"(mask), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
 __device__ __forceinline__ void remote_arrive_relaxed(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
@@ -137,7 +149,8 @@ gru_rec2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
   uint64_t* tempty_bar = tfull_bar + NTILES;         // [NTILES] leader: both CTAs drained the accumulator
   uint64_t* wfull_bar = tempty_bar + NTILES;         // resident weights landed
   uint64_t* pwfull_bar = wfull_bar + 1;              // leader: peer's weights landed
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(pwfull_bar + 1);
+  uint64_t* epi_bar = pwfull_bar + 1;                // [NTILES] all epilogue threads finished the tile
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(epi_bar + NTILES);
   float* sBias = reinterpret_cast<float*>(tmem_holder + 2);  // fwd: b_hn for the pair's 64 units
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -160,7 +173,11 @@ gru_rec2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
       ptx::mbar_init(&empty_bar[s], NSAME);
       ptx::mbar_init(&pfull_bar[s], 1);
     }
-    for (int i = 0; i < NTILES; ++i) { ptx::mbar_init(&tfull_bar[i], 1); ptx::mbar_init(&tempty_bar[i], 2); }
+    for (int i = 0; i < NTILES; ++i) {
+      ptx::mbar_init(&tfull_bar[i], 1);
+      ptx::mbar_init(&tempty_bar[i], 2);
+      ptx::mbar_init(&epi_bar[i], EPI_WARPS * 32);
+    }
     ptx::mbar_init(wfull_bar, 1);
     ptx::mbar_init(pwfull_bar, 1);
     ptx::fence_mbar_init();
@@ -176,7 +193,7 @@ gru_rec2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
   if (warp == 0) {
     // ===================== TMA producer (every CTA) =====================
     if (lane == 0) {
-      constexpr bool DIRECT = (CL == 2);   // pair-only clusters: both CTAs' TMA report straight to the leader's barriers
+      constexpr bool DIRECT = true;        // both CTAs' TMA report straight to the pair leader's barriers (no relay)
       const uint32_t lrank = rank & ~1u;
       const uint32_t wbar_addr = DIRECT ? mapa(ptx::smem_u32(wfull_bar), lrank) : ptx::smem_u32(wfull_bar);
       if (DIRECT) { if (leader) ptx::mbar_arrive_expect_tx(wfull_bar, (uint32_t)(2 * KC * CHUNK)); }
@@ -199,6 +216,7 @@ gru_rec2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
       for (int step = 1; step < p.T; ++step) {
         int slab = BWD ? (p.T - step) : step;
         if (p.debug & 2) slab = (slab + pair * 5) % p.T;
+        if (p.debug & 16) slab = 0;   // timing experiment: operand that nobody writes during the sweep
         for (int i = 0; i < ntiles; ++i) {
           const int tile = tile0 + i;
           if (!(p.debug & 1) && !wait_counter(p.counters + tile * 2 + parity, (unsigned)(p.npairs * step), p.err_flag)) goto done;
@@ -207,9 +225,14 @@ gru_rec2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
           const int row0 = tile * 256 + parity * 128 + qd * A_PART_ROWS;
           for (int kc = 0; kc < KC; ++kc) {
             if (!wait_bar(&empty_bar[s], ph ^ 1, p.err_flag)) goto done;
-            if (DIRECT) {
+            if (p.debug & 4) {
+              if (leader) ptx::mbar_arrive(&full_bar[s]);   // timing experiment: no operand traffic
+            } else if (DIRECT) {
               if (leader) ptx::mbar_arrive_expect_tx(&full_bar[s], 2 * A_STAGE);
-              tma_load_3d_2sm(sA + s * A_STAGE, &tmA, mapa(ptx::smem_u32(&full_bar[s]), lrank), kc * 64, row0, slab);
+              if (CL == 2)
+                tma_load_3d_2sm(sA + s * A_STAGE, &tmA, mapa(ptx::smem_u32(&full_bar[s]), lrank), kc * 64, row0, slab);
+              else
+                tma_load_3d_2sm_mc(sA + s * A_STAGE + qd * A_PART, &tmA, &full_bar[s], mask_par, kc * 64, row0, slab);
             } else {
               ptx::mbar_arrive_expect_tx(&full_bar[s], A_STAGE);
               tma_load_3d_mc(sA + s * A_STAGE + qd * A_PART, &tmA, &full_bar[s], mask_par, kc * 64, row0, slab);
@@ -222,7 +245,9 @@ gru_rec2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      if (!leader && CL == 2) {
+      if (!leader) {
+        // no relay needed
+      } else if (false) {
         // pair-only clusters need no relay: the peer's TMA reports directly to the leader's barriers
       } else if (!leader) {
         // ===================== relay (odd CTA): forward "my stage landed" to the pair leader =====================
@@ -241,7 +266,7 @@ gru_rec2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
         // ===================== MMA issuer (even CTA, one thread for the pair) =====================
         constexpr uint32_t idesc = ptx::umma_idesc_bf16(256, NB, 0, 0);
         if (!wait_bar(wfull_bar, 0, p.err_flag)) goto done;
-        if (CL != 2 && !wait_bar(pwfull_bar, 0, p.err_flag)) goto done;
+
         int s = 0; uint32_t ph = 0;
         for (int step = 0; step < p.T; ++step) {
           for (int i = 0; i < ntiles; ++i) {
@@ -254,7 +279,6 @@ gru_rec2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
                 if (!wait_bar(&full_bar[s], ph, p.err_flag)) goto done;
                 if (trm && kc == 0) p.trace[((size_t)step * NTILES + i) * 12 + 2] = gtime();
                 if (trm && kc == KC - 1) p.trace[((size_t)step * NTILES + i) * 12 + 9] = gtime();
-                if (CL != 2 && !wait_bar(&pfull_bar[s], ph, p.err_flag)) goto done;
                 if (trm && kc == 0) p.trace[((size_t)step * NTILES + i) * 12 + 8] = gtime();
                 if (trm && kc == KC - 1) p.trace[((size_t)step * NTILES + i) * 12 + 10] = gtime();
                 ptx::tc_fence_after();
@@ -270,11 +294,35 @@ gru_rec2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
                 if (++s == STAGES) { s = 0; ph ^= 1; }
               }
             }
+            const unsigned long long t_issue = (p.debug & 8) ? gtime() : 0ull;
             commit2_mc(&tfull_bar[i], mask_pair);     // accumulator i complete -> both epilogues
+            if ((p.debug & 8) && p.trace && blockIdx.x == 0 && blockIdx.y == 0) {
+              // timing experiment: how long until the tensor pipe has really finished this tile's MMAs
+              wait_bar(&tfull_bar[i], (uint32_t)(step & 1), p.err_flag);
+              p.trace[((size_t)step * NTILES + i) * 12 + 9] = t_issue;
+              p.trace[((size_t)step * NTILES + i) * 12 + 10] = gtime();
+            }
             if (p.trace && blockIdx.x == 0 && blockIdx.y == 0) p.trace[((size_t)step * NTILES + i) * 12 + 3] = gtime();
           }
         }
       }
+    }
+  } else if (warp == PUB_WARP) {
+    // ===================== publisher: frees the accumulator and publishes the tile's step to the other pairs =====================
+    if (lane == 0) {
+      const uint32_t tempty_remote = mapa(ptx::smem_u32(&tempty_bar[0]), rank & ~1u);
+      for (int step = 0; step < p.T; ++step)
+        for (int i = 0; i < ntiles; ++i) {
+          const int tile = tile0 + i;
+          if (!wait_bar(&epi_bar[i], (uint32_t)(step & 1), p.err_flag)) goto done;
+          remote_arrive(tempty_remote + (uint32_t)(i * 8));    // accumulator i drained in this CTA -> pair leader
+          const bool tr = p.trace && blockIdx.x == 0 && blockIdx.y == 0;
+          if (tr) p.trace[((size_t)step * NTILES + i) * 12 + 6] = gtime();
+          __threadfence();                                     // cumulative over the epilogue threads' stores
+          ptx::fence_proxy_async_all();
+          red_release_add(p.counters + tile * 2 + parity, 1u);
+          if (tr) p.trace[((size_t)step * NTILES + i) * 12 + 7] = gtime();
+        }
     }
   } else {
     // ===================== epilogue warps (every CTA: own 128 rows x 64 units) =====================
@@ -282,7 +330,6 @@ gru_rec2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
     const int part = (warp - 2) >> 2;          // 0..3 -> 16 units each
     const int uc = part * 16;
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
-    const uint32_t tempty_remote = mapa(ptx::smem_u32(&tempty_bar[0]), rank & ~1u);
     uint32_t fph = 0;
     for (int step = 0; step < p.T; ++step) {
       const int t = BWD ? (p.T - 1 - step) : step;
@@ -295,7 +342,13 @@ gru_rec2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
         const size_t sv_blk = ((((size_t)t * p.pair_tiles + tile) * p.npairs + pair) * 2 + parity) * 4 + part;
         __nv_bfloat16* svp = p.sv ? p.sv + sv_blk * 4 * 2048 + (size_t)(q * 32 + lane) * 16 : nullptr;
         u32x8 pre[BWD ? 6 : 3];
-        if (!BWD) {
+        const bool nomem = (p.debug & 32) != 0;   // timing experiment: epilogue without global traffic
+        if (nomem) {
+#pragma unroll
+          for (int a = 0; a < (BWD ? 6 : 3); ++a)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) pre[a].v[k] = 0x3c003c00u;
+        } else if (!BWD) {
           const __nv_bfloat16* g = p.gi + (long long)t * p.gi_tstride + row * 3 * p.Hp + u0 + uc;
 #pragma unroll
           for (int gate = 0; gate < 3; ++gate) pre[gate] = ldg256(g + (long long)gate * p.Hp);
@@ -339,8 +392,8 @@ gru_rec2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
             an[k] = __float_as_uint(ghn);
           }
           tmem_st_32x16(master_addr, h);
-          stg256(p.hs + ((long long)(t + 1) * p.Bp + row) * p.Hp + u0 + uc, h);
-          if (svp) {
+          if (!nomem) stg256(p.hs + ((long long)(t + 1) * p.Bp + row) * p.Hp + u0 + uc, h);
+          if (svp && !nomem) {
             stg256(svp, gr);
             stg256(svp + 2048, gz);
             stg256(svp + 2 * 2048, gn);
@@ -378,23 +431,17 @@ gru_rec2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
           }
           tmem_st_32x16(master_addr, carry);
           __nv_bfloat16* g4 = p.dG + ((long long)t * p.Bp + row) * 4 * p.Hp + u0 + uc;
-          stg256(g4, n);
-          stg256(g4 + p.Hp, ghn);
-          stg256(g4 + 2 * p.Hp, dx);
-          stg256(g4 + 3 * p.Hp, hp);
+          if (!nomem) {
+            stg256(g4, n);
+            stg256(g4 + p.Hp, ghn);
+            stg256(g4 + 2 * p.Hp, dx);
+            stg256(g4 + 3 * p.Hp, hp);
+          }
         }
         tmem_st_wait();
         ptx::tc_fence_before();
         if (tr) p.trace[((size_t)step * NTILES + i) * 12 + 5] = gtime();
-        asm volatile("bar.sync %0, %1;" ::"n"(EPI_BAR), "n"(EPI_WARPS * 32) : "memory");
-        if (warp == 2 && lane == 0) {
-          remote_arrive(tempty_remote + (uint32_t)(i * 8));    // accumulator i drained in this CTA -> pair leader
-          if (tr) p.trace[((size_t)step * NTILES + i) * 12 + 6] = gtime();
-          __threadfence();                                     // cumulative over the CTA's stores (ordered by bar.sync)
-          ptx::fence_proxy_async_all();
-          red_release_add(p.counters + tile * 2 + parity, 1u);
-          if (tr) p.trace[((size_t)step * NTILES + i) * 12 + 7] = gtime();
-        }
+        ptx::mbar_arrive(&epi_bar[i]);
       }
       fph ^= 1;
     }
