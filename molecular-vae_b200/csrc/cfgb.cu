@@ -121,7 +121,7 @@ void carve(const Dims& d, void* base, WS* w) {
   w->dgi0sum = c.take<float>(Bp * 3 * Hp);
   for (int l = 0; l < d.L; ++l) {
     w->hs[l] = c.take<uint8_t>((T + 1) * Bp * Hp * es);
-    w->sv[l] = c.take<uint8_t>(T * Bp * 4 * Hp * es);
+    w->sv[l] = c.take<uint8_t>(T * Bp * 5 * Hp * es);   // 5th block: h_{t-1} copy (fused kernel, fragment layout)
   }
   w->gi_all = c.take<uint8_t>(T * Bp * 3 * Hp * es);
   w->dG = c.take<uint8_t>(T * Bp * 4 * Hp * es);
@@ -178,18 +178,18 @@ inline int memset_async(void* p, size_t bytes, cudaStream_t st) {
 template <typename TA>
 int gemm(const Dims& d, const WS& w, cudaStream_t st, const TA* A, long long lda, bool a_trans, const TA* B,
          long long ldb, bool b_kmajor, void* out, long long ldc, bool out_is_ta, int M, int N, int K, const float* bias,
-         bool accumulate, int splits, int bn = 0) {
+         bool accumulate, int splits, int bn = 0, bool out_rb = false) {
   count();
   if constexpr (sizeof(TA) == 4) {
-    (void)out_is_ta; (void)bn; (void)d; (void)w;
+    (void)out_is_ta; (void)bn; (void)d; (void)w; (void)out_rb;
     return simt::sgemm(st, reinterpret_cast<const float*>(A), a_trans ? 1 : lda, a_trans ? lda : 1,
                        reinterpret_cast<const float*>(B), b_kmajor ? 1 : ldb, b_kmajor ? ldb : 1,
                        reinterpret_cast<float*>(out), ldc, M, N, K, bias, simt::ACT_NONE, accumulate ? 1 : 0, splits);
   } else {
     (void)d;
-    mvae_umma_operand a{A, a_trans ? 1 : 0, M, K, lda, 1, 0, 0};
-    mvae_umma_operand b{B, b_kmajor ? 0 : 1, N, K, ldb, 1, 0, 0};
-    mvae_umma_out o{out, ldc, out_is_ta ? 1 : 0, accumulate ? 1 : 0, bias};
+    mvae_umma_operand a{A, a_trans ? 1 : 0, M, K, lda, 1, 0, 0, 0};
+    mvae_umma_operand b{B, b_kmajor ? 0 : 1, N, K, ldb, 1, 0, 0, 0};
+    mvae_umma_out o{out, ldc, out_is_ta ? 1 : 0, accumulate ? 1 : 0, bias, out_rb ? 1 : 0};
     return mvae_umma_gemm(&a, &b, &o, M, N, K, bn, splits, 0, w.err_flag, st);
   }
 }
@@ -249,16 +249,52 @@ __global__ void f32_to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16*
 // layer 0: sum over time of the dgi window of dG ([T][Bp][4Hp], blocks n,r,z) -> fp32 [Bp][3Hp] in (r,z,n) order
 __global__ void dgi_time_sum_kernel(const __nv_bfloat16* __restrict__ dG, int T, int Bp, int Hp,
                                     float* __restrict__ out) {
+  // one thread per (row b, 8 consecutive columns of the dgi window): 16-byte loads, fp32 accumulation over t
   const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (idx >= (long long)Bp * 3 * Hp) return;
-  const int c = (int)(idx % (3 * Hp));
-  const int b = (int)(idx / (3 * Hp));
-  const int g = c / Hp, j = c - g * Hp;
-  const int blk = (g == 0) ? 1 : (g == 1 ? 2 : 0);
-  const __nv_bfloat16* p = dG + (long long)b * 4 * Hp + blk * Hp + j;
-  float s = 0.f;
-  for (int t = 0; t < T; ++t) s += __bfloat162float(p[(long long)t * Bp * 4 * Hp]);
-  out[idx] = s;
+  const int cpr = 3 * Hp / 8;
+  if (idx >= (long long)Bp * cpr) return;
+  const int c8 = (int)(idx % cpr) * 8;          // column inside the (n,r,z) dgi window of dG
+  const int b = (int)(idx / cpr);
+  const int blk = c8 / Hp, j = c8 - blk * Hp;   // blk: 0 = n, 1 = r, 2 = z
+  const int g = (blk == 0) ? 2 : (blk - 1);     // -> (r,z,n) order of the output
+  const uint4* p = reinterpret_cast<const uint4*>(dG + (long long)b * 4 * Hp + c8);
+  const long long tstride = (long long)Bp * 4 * Hp / 8;
+  float s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int t = 0; t < T; ++t) {
+    const uint4 v = __ldg(p + (long long)t * tstride);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      s[2 * k] += __uint_as_float(w[k] << 16);
+      s[2 * k + 1] += __uint_as_float(w[k] & 0xFFFF0000u);
+    }
+  }
+  float* o = out + (long long)b * 3 * Hp + g * Hp + j;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) o[k] = s[k];
+}
+
+// ones-column helpers (fused path): column Hp-1 of every hidden-state slab is the constant 1
+__global__ void set_column_kernel(__nv_bfloat16* __restrict__ x, long long rows, int ld, int col, float v) {
+  const long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (r < rows) x[r * ld + col] = __float2bfloat16_rn(v);
+}
+// bias grads read from the ones column of the padded weight gradients: src [3Hp][Hp] blocks named by (g0,g1,g2)
+__global__ void gate_bias_from_dw_kernel(const float* __restrict__ dW_p, int H, int Hp, int g0, int g1, int g2,
+                                         float* __restrict__ db) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 3 * H) return;
+  const int g = i / H, j = i - g * H;
+  const int blk = (g == g0) ? 0 : ((g == g1) ? 1 : 2);
+  db[i] = dW_p[((long long)blk * Hp + j) * Hp + (Hp - 1)];
+}
+__global__ void unpad_gate_vector_kernel(const float* __restrict__ src, int Hp, float* __restrict__ dst, int H) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < 3 * H) dst[i] = src[(i / H) * Hp + (i % H)];
+}
+__global__ void strided_copy_kernel(const float* __restrict__ src, long long stride, float* __restrict__ dst, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[(long long)i * stride];
 }
 
 int g_sm_count = 0;
@@ -280,6 +316,8 @@ int rec_variant(const Dims& d) {
   if (d.Bp > mvae_gru_rec_max_rows(d.Hp, v, g_sm_count)) return 0;
   return v;
 }
+// the fused path keeps a constant-1 pad column in every hidden-state slab (needs H < Hp)
+bool ones_column(const Dims& d) { return rec_variant(d) >= 3 && d.H < d.Hp; }
 int fast_gates() {
   const char* e = getenv("MVAE_FAST_GATES");
   return e ? atoi(e) : 0;
@@ -290,11 +328,14 @@ __global__ void combine_bias_kernel(const float* __restrict__ bih, const float* 
   if (i < 3 * Hp) out[i] = bih[i] + (i < 2 * Hp ? bhh[i] : 0.f);
 }
 // layer-0 projection -> bf16, optionally adding the recurrent r/z biases (fused kernel variant 3)
+// rb: write the row-blocked layout [row/32][3Hp/16][32][16] the fused kernel's epilogue reads
 __global__ void gi0_to_bf16_kernel(const float* __restrict__ src, const float* __restrict__ bhh_rz, int Hp,
-                                   __nv_bfloat16* __restrict__ dst, long long n) {
+                                   __nv_bfloat16* __restrict__ dst, long long n, int rb) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const int c = (int)(i % (3 * Hp));
-    dst[i] = __float2bfloat16_rn(src[i] + ((bhh_rz && c < 2 * Hp) ? bhh_rz[c] : 0.f));
+    const long long r = i / (3 * Hp);
+    const long long o = rb ? ((r >> 5) * (3 * Hp / 16) + (c >> 4)) * 512 + (r & 31) * 16 + (c & 15) : i;
+    dst[o] = __float2bfloat16_rn(src[i] + ((bhh_rz && c < 2 * Hp) ? bhh_rz[c] : 0.f));
   }
 }
 
@@ -346,7 +387,15 @@ int run_forward(const Dims& d, const WS& w, const float* const* P, const uint8_t
   RC(memset_async(w.kl_sum, 8, st));
   RC(memset_async(w.hit_count, (size_t)B * 4, st));
   RC(memset_async(w.gi0, (size_t)Bp * 3 * Hp * 4, st));
-  for (int l = 0; l < d.L; ++l) RC(memset_async(w.hs[l], slab * sizeof(TA), st));
+  for (int l = 0; l < d.L; ++l) {
+    RC(memset_async(w.hs[l], slab * sizeof(TA), st));
+    if constexpr (sizeof(TA) == 2) {
+      if (ones_column(d)) {
+        set_column_kernel<<<ceil_div(Bp, 256), 256, 0, st>>>((__nv_bfloat16*)w.hs[l], Bp, Hp, Hp - 1, 1.0f);
+        KCHECK();
+      }
+    }
+  }
   if (!decode_only) {
     simt::ConvDims cd{T, d.C, d.L1, d.L2, d.L3};
     const size_t smem = (729 + 990 + 9 * d.L1 + 9 * d.L2) * 4 + round_up(T, 4);
@@ -375,7 +424,7 @@ int run_forward(const Dims& d, const WS& w, const float* const* P, const uint8_t
     if (l >= 1) {
       const TA* X = (const TA*)w.hs[l - 1] + slab;
       RC(gemm<TA>(d, w, st, X, Hp, false, (const TA*)w.Wih_p[l], Hp, true, w.gi_all, 3 * Hp, true, T * Bp, 3 * Hp, Hp,
-                  rec_variant(d) >= 3 ? w.bcomb_p[l] : w.bih_p[l], false, 1));
+                  rec_variant(d) >= 3 ? w.bcomb_p[l] : w.bih_p[l], false, 1, 0, rec_variant(d) >= 3));
     }
     const int rv = rec_variant(d);
     if (rv > 0) {
@@ -384,7 +433,7 @@ int run_forward(const Dims& d, const WS& w, const float* const* P, const uint8_t
         long long gstride = (long long)Bp * 3 * Hp;
         if (l == 0) {
           gi0_to_bf16_kernel<<<grid_for((long long)Bp * 3 * Hp), 256, 0, st>>>(
-              w.gi0, rv >= 3 ? w.bhh_p[0] : nullptr, Hp, (__nv_bfloat16*)w.gi0_bf, (long long)Bp * 3 * Hp);
+              w.gi0, rv >= 3 ? w.bhh_p[0] : nullptr, Hp, (__nv_bfloat16*)w.gi0_bf, (long long)Bp * 3 * Hp, rv >= 3 ? 1 : 0);
           KCHECK();
           gi = (const __nv_bfloat16*)w.gi0_bf;
           gstride = 0;
@@ -394,6 +443,7 @@ int run_forward(const Dims& d, const WS& w, const float* const* P, const uint8_t
         ra.W = (const __nv_bfloat16*)w.Whh_p[l]; ra.gi = gi; ra.gi_tstride = gstride; ra.bhh = w.bhh_p[l];
         ra.hs = (__nv_bfloat16*)hs; ra.sv = save ? (__nv_bfloat16*)sv : nullptr; ra.counters = w.counters;
         ra.err_flag = w.err_flag;
+        ra.ones_col = ones_column(d) ? Hp - 1 : -1;
         count(2);
         if (rv >= 3) {
           ra.bhh = w.bhh_p[l] + 2 * Hp;
@@ -439,16 +489,23 @@ int run_backward(const Dims& d, const WS& w, const float* const* P, float* const
   const int wsplits = d.bf16 ? max(1, min(64, (148 * 2) / (ceil_div(3 * Hp, 128) * ceil_div(Hp, 256)))) : 64;
   const TA* dlog = (const TA*)w.dlogits;
   // head: dX = dlogits * W3 ; dW3 = dlogits^T * h_top ; db3 = colsum(dlogits)
-  RC(gemm<TA>(d, w, st, dlog, CP, false, (const TA*)w.W3_p, Hp, false, w.dX, Hp, true, TB, Hp, CP, nullptr, false, 1));
+  RC(gemm<TA>(d, w, st, dlog, CP, false, (const TA*)w.W3_p, Hp, false, w.dX, Hp, true, TB, Hp, CP, nullptr, false, 1, 0,
+              rec_variant(d) >= 3));
   RC(memset_async(w.dW3_p, (size_t)CP * Hp * 4, st));
   RC(gemm<TA>(d, w, st, dlog, CP, true, (const TA*)w.hs[L - 1] + slab, Hp, false, w.dW3_p, Hp, false, CP, Hp, TB,
               nullptr, true, d.bf16 ? 148 : 64, 256));
   simt::unpad_matrix_kernel<<<grid_for((long long)d.C * H), 256, 0, st>>>(w.dW3_p, Hp, G[P_FC3W(L)], d.C, H);
   KCHECK();
-  RC(memset_async(w.csum, (size_t)4 * Hp * 4, st));
-  RC(simt::colsum<TA>(st, dlog, TB, CP, CP, w.csum)); count();
-  copy_prefix_kernel<<<1, 64, 0, st>>>(w.csum, G[P_FC3B(L)], d.C);
-  KCHECK();
+  const bool ones = ones_column(d);
+  if (ones) {  // db3 = ones column of dW3
+    strided_copy_kernel<<<1, 64, 0, st>>>(w.dW3_p + (Hp - 1), Hp, G[P_FC3B(L)], d.C);
+    KCHECK();
+  } else {
+    RC(memset_async(w.csum, (size_t)4 * Hp * 4, st));
+    RC(simt::colsum<TA>(st, dlog, TB, CP, CP, w.csum)); count();
+    copy_prefix_kernel<<<1, 64, 0, st>>>(w.csum, G[P_FC3B(L)], d.C);
+    KCHECK();
+  }
 
   const int gate_grid = ceil_div(Bp * Hp, 256);
   for (int l = L - 1; l >= 0; --l) {
@@ -468,7 +525,7 @@ int run_backward(const Dims& d, const WS& w, const float* const* P, float* const
         if (rv >= 3) RC(mvae_gru_rec2_launch(&ra, 0, st));
         else RC(mvae_gru_rec_launch(&ra, st));
         if (l == 0) {
-          dgi_time_sum_kernel<<<(unsigned)ceil_div64((long long)Bp * 3 * Hp, 256), 256, 0, st>>>(
+          dgi_time_sum_kernel<<<(unsigned)ceil_div64((long long)Bp * 3 * Hp / 8, 256), 256, 0, st>>>(
               (const __nv_bfloat16*)dG, T, Bp, Hp, w.dgi0sum);
           KCHECK();
         }
@@ -493,11 +550,23 @@ int run_backward(const Dims& d, const WS& w, const float* const* P, float* const
                 wsplits, 256));
     simt::unpad_gate_matrix_kernel<<<grid_for(3ll * H * H), 256, 0, st>>>(w.dW_p, Hp, Hp, G[P_WHH(l)], H, H, 0, 1, 2);
     KCHECK();
-    // bias grads from the column sums of dG
-    RC(memset_async(w.csum, (size_t)4 * Hp * 4, st));
-    RC(simt::colsum<TA>(st, dG, TB, 4 * Hp, 4 * Hp, w.csum)); count();
-    gate_bias_grads_kernel<<<ceil_div(3 * H, 256), 256, 0, st>>>(w.csum, H, Hp, G[P_BIH(l)], G[P_BHH(l)]);
-    KCHECK();
+    if (ones) {
+      // bias grads = ones column of the padded weight gradients (h pad column Hp-1 is the constant 1)
+      gate_bias_from_dw_kernel<<<ceil_div(3 * H, 256), 256, 0, st>>>(w.dW_p, H, Hp, 0, 1, 2, G[P_BHH(l)]);
+      KCHECK();
+      if (l == 0) {
+        RC(memset_async(w.csum, (size_t)4 * Hp * 4, st));
+        RC(simt::colsum<float>(st, w.dgi0sum, Bp, 3 * Hp, 3 * Hp, w.csum)); count();
+        unpad_gate_vector_kernel<<<ceil_div(3 * H, 256), 256, 0, st>>>(w.csum, Hp, G[P_BIH(0)], H);
+        KCHECK();
+      }
+    } else {
+      // bias grads from the column sums of dG
+      RC(memset_async(w.csum, (size_t)4 * Hp * 4, st));
+      RC(simt::colsum<TA>(st, dG, TB, 4 * Hp, 4 * Hp, w.csum)); count();
+      gate_bias_grads_kernel<<<ceil_div(3 * H, 256), 256, 0, st>>>(w.csum, H, Hp, G[P_BIH(l)], G[P_BHH(l)]);
+      KCHECK();
+    }
     if (l >= 1) {
       const TA* X = (const TA*)w.hs[l - 1] + slab;
       RC(memset_async(w.dW_p, (size_t)3 * Hp * Hp * 4, st));
@@ -505,9 +574,13 @@ int run_backward(const Dims& d, const WS& w, const float* const* P, float* const
                   256));
       simt::unpad_gate_matrix_kernel<<<grid_for(3ll * H * H), 256, 0, st>>>(w.dW_p, Hp, Hp, G[P_WIH(l)], H, H, 2, 0, 1);
       KCHECK();
+      if (ones) {
+        gate_bias_from_dw_kernel<<<ceil_div(3 * H, 256), 256, 0, st>>>(w.dW_p, H, Hp, 2, 0, 1, G[P_BIH(l)]);
+        KCHECK();
+      }
       // gradient into the layer below: dX = dgi * W_ih
       RC(gemm<TA>(d, w, st, dG, 4 * Hp, false, (const TA*)w.Wih_nrz[l], Hp, false, w.dX, Hp, true, TB, Hp, 3 * Hp,
-                  nullptr, false, 1));
+                  nullptr, false, 1, 0, rec_variant(d) >= 3));
     } else {
       // time-invariant layer-0 input: dW_ih0 = (sum_t dgi)^T zr ; dzr = (sum_t dgi) W_ih0
       for (int g = 0; g < 3; ++g) {
@@ -785,9 +858,9 @@ int mvae_cfgb_read_error(const mvae_cfgb_desc* desc, void* workspace, size_t wor
 int mvae_gemm_bf16(const void* A, long long lda, int a_mn_major, const void* B, long long ldb, int b_mn_major, void* D,
                    long long ldd, int d_is_bf16, int accumulate, const float* bias, int M, int N, int K, int tile_n,
                    int splits, int* err_flag, mvae_stream_t stream) {
-  mvae_umma_operand a{A, a_mn_major ? 1 : 0, M, K, lda, 1, 0, 0};
-  mvae_umma_operand b{B, b_mn_major ? 1 : 0, N, K, ldb, 1, 0, 0};
-  mvae_umma_out o{D, ldd, d_is_bf16, accumulate, bias};
+  mvae_umma_operand a{A, a_mn_major ? 1 : 0, M, K, lda, 1, 0, 0, 0};
+  mvae_umma_operand b{B, b_mn_major ? 1 : 0, N, K, ldb, 1, 0, 0, 0};
+  mvae_umma_out o{D, ldd, d_is_bf16, accumulate, bias, 0};
   count();
   return mvae_umma_gemm(&a, &b, &o, M, N, K, tile_n, splits, 0, err_flag, reinterpret_cast<cudaStream_t>(stream));
 }

@@ -38,6 +38,7 @@ struct Params2 {
   unsigned int* counters;    // [pair_tiles][2]
   int* err_flag;
   unsigned long long* trace; // optional debug timestamps [T][NTILES][12] of CTA (0,0)
+  int ones_col;              // fwd: hidden-unit index forced to 1.0 (bias-gradient trick) or -1
   int debug;                 // timing experiments only: bit0 skip counter waits, bit1 de-share operand rows
 };
 
@@ -340,7 +341,10 @@ gru_rec2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
         // thread mapping): block (t, tile, pair, parity, part, array) of 4 KB, thread (q, lane) owns 32 B -> every
         // warp-wide 256-bit access is 1 KB contiguous.
         const size_t sv_blk = ((((size_t)t * p.pair_tiles + tile) * p.npairs + pair) * 2 + parity) * 4 + part;
-        __nv_bfloat16* svp = p.sv ? p.sv + sv_blk * 4 * 2048 + (size_t)(q * 32 + lane) * 16 : nullptr;
+        __nv_bfloat16* svp = p.sv ? p.sv + sv_blk * 5 * 2048 + (size_t)(q * 32 + lane) * 16 : nullptr;
+        // gi / dX are produced by the GEMM epilogues in the row-blocked layout [row/32][width/16][32][16]:
+        // this thread's 16 units of its row are 32 contiguous bytes and the warp's 32 rows 1 KB contiguous.
+        const long long rblk = row >> 5;   // = tile*8 + parity*4 + q ; row & 31 == lane
         u32x8 pre[BWD ? 6 : 3];
         const bool nomem = (p.debug & 32) != 0;   // timing experiment: epilogue without global traffic
         if (nomem) {
@@ -349,14 +353,15 @@ gru_rec2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
 #pragma unroll
             for (int k = 0; k < 8; ++k) pre[a].v[k] = 0x3c003c00u;
         } else if (!BWD) {
-          const __nv_bfloat16* g = p.gi + (long long)t * p.gi_tstride + row * 3 * p.Hp + u0 + uc;
+          const __nv_bfloat16* g = p.gi + (long long)t * p.gi_tstride +
+                                   (rblk * (3 * p.Hp / 16) + ((u0 + uc) >> 4)) * 512 + lane * 16;
 #pragma unroll
-          for (int gate = 0; gate < 3; ++gate) pre[gate] = ldg256(g + (long long)gate * p.Hp);
+          for (int gate = 0; gate < 3; ++gate) pre[gate] = ldg256(g + (long long)gate * (p.Hp / 16) * 512);
         } else {
 #pragma unroll
           for (int blk = 0; blk < 4; ++blk) pre[blk] = ldg256(svp + blk * 2048);
-          pre[4] = ldg256(p.hs + ((long long)t * p.Bp + row) * p.Hp + u0 + uc);
-          pre[5] = ldg256(p.dX + ((long long)t * p.Bp + row) * p.Hp + u0 + uc);
+          pre[4] = ldg256(svp + 4 * 2048);   // h_{t-1} (saved by the forward sweep next to the gates)
+          pre[5] = ldg256(p.dX + (long long)t * p.Bp * p.Hp + (rblk * (p.Hp / 16) + ((u0 + uc) >> 4)) * 512 + lane * 16);
         }
         (void)wait_bar(&tfull_bar[i], fph, p.err_flag);   // on failure keep walking: barriers below must be reached
         ptx::tc_fence_after();
@@ -388,6 +393,9 @@ gru_rec2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
             const float z = gate_sigmoid_t<FAST>(gz[k] + __uint_as_float(az[k]));   // b_hz folded into gi
             const float n = gate_tanh_t<FAST>(fmaf(r, ghn, gn[k]));
             h[k] = fmaf(z, __uint_as_float(hm[k]) - n, n);
+            // "ones column": the last pad unit carries the constant 1 so that the K = T*B weight-gradient GEMMs
+            // also produce the bias gradients (its weights are zero padding, so it never feeds the recurrence)
+            if (p.ones_col >= 0 && u0 + uc + k == p.ones_col) h[k] = 1.0f;
             gr[k] = r; gz[k] = z; gn[k] = n;
             an[k] = __float_as_uint(ghn);
           }
@@ -400,6 +408,9 @@ gru_rec2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
 #pragma unroll
             for (int k = 0; k < 16; ++k) h[k] = __uint_as_float(an[k]);
             stg256(svp + 3 * 2048, h);
+#pragma unroll
+            for (int k = 0; k < 16; ++k) h[k] = __uint_as_float(hm[k]);
+            stg256(svp + 4 * 2048, h);   // h_{t-1}: lets the BPTT epilogue skip the row-major hs read
           }
         } else {
           uint32_t acc[16], cm[16];
@@ -513,7 +524,7 @@ int launch2(const mvae_gru_rec_args& a, cudaStream_t st) {
   Params2 p{};
   p.Bp = Bp; p.Hp = Hp; p.T = T; p.pair_tiles = Bp / 256; p.npairs = Hp / RU;
   p.gi = a.gi; p.gi_tstride = a.gi_tstride; p.bhn = a.bhh; p.hs = a.hs; p.sv = a.sv; p.dX = a.dX; p.dG = a.dG;
-  p.counters = a.counters; p.err_flag = a.err_flag; p.trace = a.trace; p.debug = a.debug;
+  p.counters = a.counters; p.err_flag = a.err_flag; p.trace = a.trace; p.debug = a.debug; p.ones_col = a.ones_col;
   auto kern = gru_rec2_kernel<BWD, FAST, CL>;
   static bool attr = false;
   if (!attr) {

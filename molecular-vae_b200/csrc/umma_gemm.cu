@@ -41,6 +41,8 @@ struct KernelParams {
   void* out;
   long long ldc;
   const float* bias;   // per-N, may be null
+  int rbA, rbB;        // operand stored in the row-blocked layout (5-D tensor map)
+  int out_rb;          // bf16 output in the row-blocked layout
   int out_bf16;        // 1: bf16 output, 0: fp32
   int accumulate;      // fp32 only: D += result (plain RMW, or red.add when splits > 1)
   int* err_flag;
@@ -122,19 +124,26 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           ptx::mbar_arrive_expect_tx(&full_bar[s], C::STAGE_BYTES);
           uint8_t* a_dst = sA + s * A_STAGE_BYTES;
           uint8_t* b_dst = sB + s * C::B_STAGE_BYTES;
+          // plain layout: 3-D map {inner, rows, slab}; row-blocked layout: 5-D map {16, cols/16, 32, rows/32, slab}
           if (A_MN) {
 #pragma unroll
-            for (int c = 0; c < BM / 64; ++c)
-              ptx::tma_load_3d(a_dst + c * 8192, &tmA, &full_bar[s], m_blk * BM + c * 64, kb * BK, p.slabA);
+            for (int c = 0; c < BM / 64; ++c) {
+              if (p.rbA) ptx::tma_load_5d(a_dst + c * 8192, &tmA, &full_bar[s], 0, (m_blk * BM + c * 64) >> 4, 0, (kb * BK) >> 5, p.slabA);
+              else ptx::tma_load_3d(a_dst + c * 8192, &tmA, &full_bar[s], m_blk * BM + c * 64, kb * BK, p.slabA);
+            }
           } else {
-            ptx::tma_load_3d(a_dst, &tmA, &full_bar[s], kb * BK, m_blk * BM, p.slabA);
+            if (p.rbA) ptx::tma_load_5d(a_dst, &tmA, &full_bar[s], 0, (kb * BK) >> 4, 0, (m_blk * BM) >> 5, p.slabA);
+            else ptx::tma_load_3d(a_dst, &tmA, &full_bar[s], kb * BK, m_blk * BM, p.slabA);
           }
           if (B_MN) {
 #pragma unroll
-            for (int c = 0; c < BN / 64; ++c)
-              ptx::tma_load_3d(b_dst + c * 8192, &tmB, &full_bar[s], n_blk * BN + c * 64, kb * BK, p.slabB);
+            for (int c = 0; c < BN / 64; ++c) {
+              if (p.rbB) ptx::tma_load_5d(b_dst + c * 8192, &tmB, &full_bar[s], 0, (n_blk * BN + c * 64) >> 4, 0, (kb * BK) >> 5, p.slabB);
+              else ptx::tma_load_3d(b_dst + c * 8192, &tmB, &full_bar[s], n_blk * BN + c * 64, kb * BK, p.slabB);
+            }
           } else {
-            ptx::tma_load_3d(b_dst, &tmB, &full_bar[s], kb * BK, n_blk * BN, p.slabB);
+            if (p.rbB) ptx::tma_load_5d(b_dst, &tmB, &full_bar[s], 0, (kb * BK) >> 4, 0, (n_blk * BN) >> 5, p.slabB);
+            else ptx::tma_load_3d(b_dst, &tmB, &full_bar[s], kb * BK, n_blk * BN, p.slabB);
           }
           if (++s == C::STAGES) { s = 0; ph ^= 1; }
         }
@@ -211,7 +220,26 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               if (col0 + j < p.N) v[j] += __ldg(p.bias + col0 + j);
           }
           const bool full = (col0 + 32 <= p.N);
-          if (p.out_bf16) {
+          if (p.out_bf16 && p.out_rb) {
+            // row-blocked output: [row/32][ldc/16][row%32][16] -> a warp's 32 rows x 16 cols are 1 KB contiguous
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const int col = col0 + h * 16;
+              if (col < p.N) {
+                __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) +
+                                   ((long long)(row >> 5) * (p.ldc >> 4) + (col >> 4)) * 512 + (row & 31) * 16;
+                uint32_t w[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  __nv_bfloat162 b2 = __floats2bfloat162_rn(v[h * 16 + 2 * j], v[h * 16 + 2 * j + 1]);
+                  w[j] = *reinterpret_cast<uint32_t*>(&b2);
+                }
+                asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(o), "r"(w[0]), "r"(w[1]), "r"(w[2]),
+                             "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
+                             : "memory");
+              }
+            }
+          } else if (p.out_bf16) {
             __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + (long long)row * p.ldc + col0;
             if (full && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
 #pragma unroll
@@ -291,26 +319,32 @@ PFN_encodeTiled get_encode_fn() {
 int make_map(CUtensorMap* map, const mvae_umma_operand& op, int box_rows) {
   PFN_encodeTiled enc = get_encode_fn();
   if (!enc) return MVAE_ERR_DRIVER;
-  cuuint64_t dims[3];
-  cuuint64_t strides[2];
-  cuuint32_t box[3];
-  cuuint32_t estr[3] = {1, 1, 1};
-  if (op.mn_major) {
-    dims[0] = (cuuint64_t)op.mn;
-    dims[1] = (cuuint64_t)op.k;
-    box[0] = 64; box[1] = 64; box[2] = 1;
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  const long long slabs = op.slabs > 0 ? op.slabs : 1;
+  // stored matrix: rows x cols with `cols` contiguous in the plain layout
+  const long long rows = op.mn_major ? op.k : op.mn;
+  const long long cols = op.mn_major ? op.mn : op.k;
+  const int brow = op.mn_major ? 64 : box_rows;   // box extent along the stored rows
+  if (reinterpret_cast<uintptr_t>(op.ptr) & 15) return MVAE_ERR_INVALID;
+  CUresult r;
+  if (op.rb) {
+    if ((rows & 31) || (cols & 15) || (op.ld & 15) || (brow & 31)) return MVAE_ERR_INVALID;
+    cuuint64_t dims[5] = {16, (cuuint64_t)(cols / 16), 32, (cuuint64_t)(rows / 32), (cuuint64_t)slabs};
+    cuuint64_t strides[4] = {1024, 32, (cuuint64_t)(op.ld / 16) * 1024,
+                             (cuuint64_t)(slabs > 1 ? op.slab_stride : op.ld * rows) * 2};
+    cuuint32_t box[5] = {16, 4, 32, (cuuint32_t)(brow / 32), 1};
+    r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(op.ptr), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   } else {
-    dims[0] = (cuuint64_t)op.k;
-    dims[1] = (cuuint64_t)op.mn;
-    box[0] = 64; box[1] = (cuuint32_t)box_rows; box[2] = 1;
+    cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)slabs};
+    cuuint64_t strides[2] = {(cuuint64_t)op.ld * 2, (cuuint64_t)(slabs > 1 ? op.slab_stride : op.ld * rows) * 2};
+    cuuint32_t box[3] = {64, (cuuint32_t)brow, 1};
+    if ((strides[0] & 15) || (strides[1] & 15)) return MVAE_ERR_INVALID;
+    r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(op.ptr), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   }
-  dims[2] = (cuuint64_t)(op.slabs > 0 ? op.slabs : 1);
-  strides[0] = (cuuint64_t)op.ld * 2;
-  strides[1] = (cuuint64_t)(op.slabs > 1 ? op.slab_stride : (long long)op.ld * (long long)dims[1]) * 2;
-  if ((reinterpret_cast<uintptr_t>(op.ptr) & 15) || (strides[0] & 15) || (strides[1] & 15)) return MVAE_ERR_INVALID;
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(op.ptr), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? MVAE_OK : MVAE_ERR_DRIVER;
 }
 
@@ -364,6 +398,8 @@ int mvae_umma_gemm(const mvae_umma_operand* A, const mvae_umma_operand* B, const
   kp.tiles_n = ceil_div(N, bn);
   kp.out = D->ptr; kp.ldc = D->ld; kp.bias = D->bias; kp.out_bf16 = D->bf16; kp.accumulate = D->accumulate;
   kp.err_flag = err_flag;
+  kp.rbA = A->rb; kp.rbB = B->rb; kp.out_rb = D->rb;
+  if (D->rb && (!D->bf16 || (D->ld & 15) || (N & 15))) return MVAE_ERR_INVALID;
   CUtensorMap tmA, tmB;
   int rc = make_map(&tmA, *A, BM);
   if (rc) return rc;

@@ -17,7 +17,7 @@ int main(int argc, char** argv) {
   const size_t slab = (size_t)B * Hp;
   __nv_bfloat16 *W, *WT, *gi, *hs, *sv, *dX, *dG; float* bhh; unsigned* ctr; int* err; unsigned long long* trace;
   cudaMalloc(&W, 3 * Hp * Hp * 2); cudaMalloc(&WT, 3 * Hp * Hp * 2);
-  cudaMalloc(&gi, (size_t)T * B * 3 * Hp * 2); cudaMalloc(&hs, (T + 1) * slab * 2); cudaMalloc(&sv, T * slab * 4 * 2);
+  cudaMalloc(&gi, (size_t)T * B * 3 * Hp * 2); cudaMalloc(&hs, (T + 1) * slab * 2); cudaMalloc(&sv, T * slab * 5 * 2);
   cudaMalloc(&dX, T * slab * 2); cudaMalloc(&dG, T * slab * 4 * 2); cudaMalloc(&bhh, 3 * Hp * 4);
   cudaMalloc(&ctr, 4096); cudaMalloc(&err, 4); cudaMalloc(&trace, (size_t)T * 4 * 12 * 8);
   // small random-ish contents
@@ -33,7 +33,7 @@ int main(int argc, char** argv) {
     mvae_gru_rec_args a{};
     a.backward = bwd; a.variant = variant; a.Bp = B; a.Hp = Hp; a.T = T;
     a.W = bwd ? WT : W; a.gi = gi; a.gi_tstride = (long long)B * 3 * Hp; a.bhh = bhh; a.hs = hs; a.sv = sv; a.dX = dX; a.dG = dG;
-    a.counters = ctr; a.err_flag = err; a.trace = nullptr; a.debug = debug;
+    a.counters = ctr; a.err_flag = err; a.trace = nullptr; a.debug = debug; a.ones_col = -1;
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     auto launch = [&](const mvae_gru_rec_args* aa) { return variant >= 3 ? mvae_gru_rec2_launch(aa, fast, 0) : mvae_gru_rec_launch(aa, 0); };
     if (variant >= 3) printf("max active clusters (%s): cl2=%d cl4=%d cl8=%d\n", bwd ? "bwd" : "fwd", mvae_gru_rec2_max_clusters(bwd, 2), mvae_gru_rec2_max_clusters(bwd, 4), mvae_gru_rec2_max_clusters(bwd, 8));

@@ -19,7 +19,11 @@ static float frand() {
 }
 static float bf16_round(float f) { return __bfloat162float(__float2bfloat16_rn(f)); }
 
-struct Case { int M, N, K, a_mn, b_mn, bn, splits, out_bf16, accumulate, bias, slabs; };
+struct Case { int M, N, K, a_mn, b_mn, bn, splits, out_bf16, accumulate, bias, slabs, rb_a, rb_b, rb_out; };
+// element (r, c) of a stored [rows][ld] matrix: plain row-major or the row-blocked layout [r/32][ld/16][32][16]
+static inline long long IDX(int rb, long long r, long long c, long long ld) {
+  return rb ? ((r >> 5) * (ld >> 4) + (c >> 4)) * 512 + (r & 31) * 16 + (c & 15) : r * ld + c;
+}
 
 static int run_case(const Case& c, int verbose) {
   const int slabs = c.slabs > 0 ? c.slabs : 1;
@@ -27,41 +31,43 @@ static int run_case(const Case& c, int verbose) {
   // stored shapes
   const long long a_rows = c.a_mn ? c.K : c.M, a_cols = c.a_mn ? c.M : c.K;
   const long long b_rows = c.b_mn ? c.K : c.N, b_cols = c.b_mn ? c.N : c.K;
-  const long long lda = (a_cols + 7) / 8 * 8 + 8, ldb = (b_cols + 7) / 8 * 8 + 16;  // padded leading dims
-  const long long a_slab = a_rows * lda, b_slab = b_rows * ldb;
+  const long long lda = c.rb_a ? (a_cols + 15) / 16 * 16 + 16 : (a_cols + 7) / 8 * 8 + 8;
+  const long long ldb = c.rb_b ? (b_cols + 15) / 16 * 16 + 32 : (b_cols + 7) / 8 * 8 + 16;  // padded leading dims
+  const long long a_slab = (c.rb_a ? (a_rows + 31) / 32 * 32 : a_rows) * lda, b_slab = (c.rb_b ? (b_rows + 31) / 32 * 32 : b_rows) * ldb;
   std::vector<__nv_bfloat16> hA(a_slab * slabs), hB(b_slab * slabs);
   std::vector<float> fA(a_slab * slabs), fB(b_slab * slabs);
   for (size_t i = 0; i < hA.size(); ++i) { float v = bf16_round(frand()); fA[i] = v; hA[i] = __float2bfloat16_rn(v); }
   for (size_t i = 0; i < hB.size(); ++i) { float v = bf16_round(frand()); fB[i] = v; hB[i] = __float2bfloat16_rn(v); }
-  const long long ldc = (c.N + 7) / 8 * 8;
-  std::vector<float> hC0((size_t)c.M * ldc), hBias(c.N);
+  const long long ldc = c.rb_out ? (c.N + 15) / 16 * 16 : (c.N + 7) / 8 * 8;
+  const long long Mp = c.rb_out ? (c.M + 31) / 32 * 32 : c.M;
+  std::vector<float> hC0((size_t)Mp * ldc), hBias(c.N);
   for (auto& v : hC0) v = (c.accumulate || c.splits > 1) ? frand() : 777.0f;
   for (auto& v : hBias) v = frand();
   __nv_bfloat16 *dA, *dB; void* dC; float* dBias; int* dErr;
   cudaMalloc(&dA, hA.size() * 2); cudaMalloc(&dB, hB.size() * 2);
-  cudaMalloc(&dC, (size_t)c.M * ldc * 4); cudaMalloc(&dBias, c.N * 4); cudaMalloc(&dErr, 4);
+  cudaMalloc(&dC, (size_t)Mp * ldc * 4); cudaMalloc(&dBias, c.N * 4); cudaMalloc(&dErr, 4);
   cudaMemcpy(dA, hA.data(), hA.size() * 2, cudaMemcpyHostToDevice);
   cudaMemcpy(dB, hB.data(), hB.size() * 2, cudaMemcpyHostToDevice);
   cudaMemcpy(dBias, hBias.data(), c.N * 4, cudaMemcpyHostToDevice);
   cudaMemset(dErr, 0, 4);
-  if (c.out_bf16) cudaMemset(dC, 0x7f, (size_t)c.M * ldc * 4);
+  if (c.out_bf16) cudaMemset(dC, 0x7f, (size_t)Mp * ldc * 4);
   else cudaMemcpy(dC, hC0.data(), hC0.size() * 4, cudaMemcpyHostToDevice);
-  mvae_umma_operand A{dA, c.a_mn, c.M, c.K, lda, slabs, a_slab, slab};
-  mvae_umma_operand B{dB, c.b_mn, c.N, c.K, ldb, slabs, b_slab, slab};
-  mvae_umma_out D{dC, ldc, c.out_bf16, c.accumulate, c.bias ? dBias : nullptr};
+  mvae_umma_operand A{dA, c.a_mn, c.M, c.K, lda, slabs, a_slab, slab, c.rb_a};
+  mvae_umma_operand B{dB, c.b_mn, c.N, c.K, ldb, slabs, b_slab, slab, c.rb_b};
+  mvae_umma_out D{dC, ldc, c.out_bf16, c.accumulate, c.bias ? dBias : nullptr, c.rb_out};
   int rc = mvae_umma_gemm(&A, &B, &D, c.M, c.N, c.K, c.bn, c.splits, 0, dErr, 0);
   cudaError_t e = cudaDeviceSynchronize();
   int herr = 0;
   cudaMemcpy(&herr, dErr, 4, cudaMemcpyDeviceToHost);
-  printf("case M=%d N=%d K=%d a_mn=%d b_mn=%d bn=%d splits=%d obf16=%d acc=%d bias=%d slabs=%d : rc=%d cuda=%s errflag=%d",
-         c.M, c.N, c.K, c.a_mn, c.b_mn, c.bn, c.splits, c.out_bf16, c.accumulate, c.bias, slabs, rc,
+  printf("case M=%d N=%d K=%d a_mn=%d b_mn=%d bn=%d splits=%d obf16=%d acc=%d bias=%d slabs=%d rb=%d%d%d : rc=%d cuda=%s errflag=%d",
+         c.M, c.N, c.K, c.a_mn, c.b_mn, c.bn, c.splits, c.out_bf16, c.accumulate, c.bias, slabs, c.rb_a, c.rb_b, c.rb_out, rc,
          cudaGetErrorString(e), herr);
   int bad = (rc != 0 || e != cudaSuccess || herr != 0);
   if (rc != 0) printf(" [%s]", mvae_last_cuda_error());
   if (!bad) {
-    std::vector<float> out((size_t)c.M * ldc);
+    std::vector<float> out((size_t)Mp * ldc);
     if (c.out_bf16) {
-      std::vector<__nv_bfloat16> ob((size_t)c.M * ldc);
+      std::vector<__nv_bfloat16> ob((size_t)Mp * ldc);
       cudaMemcpy(ob.data(), dC, ob.size() * 2, cudaMemcpyDeviceToHost);
       for (size_t i = 0; i < ob.size(); ++i) out[i] = __bfloat162float(ob[i]);
     } else {
@@ -76,13 +82,13 @@ static int run_case(const Case& c, int verbose) {
       for (int n = 0; n < c.N; n += cstep) {
         double acc = 0;
         for (int k = 0; k < c.K; ++k) {
-          float a = c.a_mn ? pa[(long long)k * lda + m] : pa[(long long)m * lda + k];
-          float b = c.b_mn ? pb[(long long)k * ldb + n] : pb[(long long)n * ldb + k];
+          float a = c.a_mn ? pa[IDX(c.rb_a, k, m, lda)] : pa[IDX(c.rb_a, m, k, lda)];
+          float b = c.b_mn ? pb[IDX(c.rb_b, k, n, ldb)] : pb[IDX(c.rb_b, n, k, ldb)];
           acc += (double)a * b;
         }
         if (c.bias) acc += hBias[n];
         if (c.accumulate || c.splits > 1) acc += hC0[(size_t)m * ldc + n];
-        double got = out[(size_t)m * ldc + n];
+        double got = out[IDX(c.rb_out, m, n, ldc)];
         double tol = 2e-3 * sqrt((double)c.K) * 0.1 + (c.out_bf16 ? 0.01 * fabs(acc) + 1e-2 : 1e-4 * fabs(acc));
         double err = fabs(got - acc);
         if (err > maxerr) maxerr = err;
@@ -105,13 +111,13 @@ static int run_case(const Case& c, int verbose) {
               if (m >= c.M || n >= c.N || (m % rstep) || (n % cstep)) continue;
               double acc = 0;
               for (int k = 0; k < c.K; ++k) {
-                float a = c.a_mn ? pa[(long long)k * lda + m] : pa[(long long)m * lda + k];
-                float b = c.b_mn ? pb[(long long)k * ldb + n] : pb[(long long)n * ldb + k];
+                float a = c.a_mn ? pa[IDX(c.rb_a, k, m, lda)] : pa[IDX(c.rb_a, m, k, lda)];
+                float b = c.b_mn ? pb[IDX(c.rb_b, k, n, ldb)] : pb[IDX(c.rb_b, n, k, ldb)];
                 acc += (double)a * b;
               }
               if (c.bias) acc += hBias[n];
               if (c.accumulate || c.splits > 1) acc += hC0[(size_t)m * ldc + n];
-              if (fabs(out[(size_t)m * ldc + n] - acc) > 0.05 + 0.02 * fabs(acc)) anybad = 1;
+              if (fabs(out[IDX(c.rb_out, m, n, ldc)] - acc) > 0.05 + 0.02 * fabs(acc)) anybad = 1;
             }
             putchar(anybad ? 'X' : '.');
           }
@@ -127,16 +133,16 @@ static int run_case(const Case& c, int verbose) {
   return bad;
 }
 
-static void bench_case(int M, int N, int K, int a_mn, int b_mn, int bn, int splits, int out_bf16) {
+static void bench_case(int M, int N, int K, int a_mn, int b_mn, int bn, int splits, int out_bf16, int rb = 0) {
   const long long a_rows = a_mn ? K : M, a_cols = a_mn ? M : K, b_rows = b_mn ? K : N, b_cols = b_mn ? N : K;
   __nv_bfloat16 *dA, *dB; void* dC; int* dErr;
   cudaMalloc(&dA, a_rows * a_cols * 2); cudaMalloc(&dB, b_rows * b_cols * 2);
   cudaMalloc(&dC, (size_t)M * N * 4); cudaMalloc(&dErr, 4);
   cudaMemset(dA, 0x11, a_rows * a_cols * 2); cudaMemset(dB, 0x11, b_rows * b_cols * 2); cudaMemset(dC, 0, (size_t)M * N * 4);
   cudaMemset(dErr, 0, 4);
-  mvae_umma_operand A{dA, a_mn, M, K, a_cols, 1, 0, 0};
-  mvae_umma_operand B{dB, b_mn, N, K, b_cols, 1, 0, 0};
-  mvae_umma_out D{dC, N, out_bf16, 0, nullptr};
+  mvae_umma_operand A{dA, a_mn, M, K, a_cols, 1, 0, 0, rb & 1};
+  mvae_umma_operand B{dB, b_mn, N, K, b_cols, 1, 0, 0, (rb >> 1) & 1};
+  mvae_umma_out D{dC, N, out_bf16, 0, nullptr, (rb >> 2) & 1};
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
   for (int i = 0; i < 3; ++i) mvae_umma_gemm(&A, &B, &D, M, N, K, bn, splits, 0, dErr, 0);
   cudaEventRecord(e0);
@@ -146,7 +152,7 @@ static void bench_case(int M, int N, int K, int a_mn, int b_mn, int bn, int spli
   cudaError_t e = cudaDeviceSynchronize();
   float ms = 0; cudaEventElapsedTime(&ms, e0, e1); ms /= iters;
   int herr = 0; cudaMemcpy(&herr, dErr, 4, cudaMemcpyDeviceToHost);
-  printf("bench M=%d N=%d K=%d a_mn=%d b_mn=%d bn=%d splits=%d obf16=%d : %.3f ms  %.1f TFLOP/s  (cuda=%s err=%d)\n", M, N, K,
+  printf("bench rb=%d M=%d N=%d K=%d a_mn=%d b_mn=%d bn=%d splits=%d obf16=%d : %.3f ms  %.1f TFLOP/s  (cuda=%s err=%d)\n", rb, M, N, K,
          a_mn, b_mn, bn, splits, out_bf16, ms, 2.0 * M * N * K / ms * 1e-9, cudaGetErrorString(e), herr);
   fflush(stdout);
   cudaFree(dA); cudaFree(dB); cudaFree(dC); cudaFree(dErr);
@@ -186,8 +192,33 @@ int main(int argc, char** argv) {
     };
     cases.insert(cases.end(), more.begin(), more.end());
   }
+  if (stage == 3) {
+    cases = {
+        {128, 64, 64, 0, 0, 64, 1, 0, 0, 0, 1, 1, 0, 0},
+        {128, 64, 64, 0, 0, 64, 1, 0, 0, 0, 1, 0, 1, 0},
+        {128, 64, 64, 1, 0, 64, 1, 0, 0, 0, 1, 1, 0, 0},
+        {128, 64, 64, 0, 1, 64, 1, 0, 0, 0, 1, 0, 1, 0},
+        {128, 64, 64, 0, 0, 64, 1, 1, 0, 0, 1, 0, 0, 1},
+        {384, 512, 512, 0, 0, 256, 1, 1, 0, 1, 2, 1, 0, 1},
+        {256, 1536, 512, 0, 0, 256, 1, 1, 0, 1, 3, 1, 0, 1},
+        {256, 512, 1536, 0, 1, 256, 1, 1, 0, 0, 1, 1, 0, 1},
+        {1536, 512, 4096, 1, 1, 256, 8, 0, 0, 0, 1, 1, 1, 0},
+        {1536, 512, 4096, 1, 1, 128, 3, 0, 0, 0, 2, 1, 1, 0},
+        {64, 512, 4096, 1, 1, 256, 4, 0, 0, 0, 1, 0, 1, 0},
+        {4096, 64, 512, 0, 0, 64, 1, 0, 0, 1, 1, 1, 0, 0},
+        {4096, 512, 64, 0, 1, 256, 1, 1, 0, 0, 1, 0, 0, 1},
+        {40000 / 32 * 32, 1536, 512, 0, 0, 256, 1, 1, 0, 1, 1, 1, 0, 1},
+    };
+  }
   for (auto& c : cases) fails += run_case(c, 1);
   printf("SUMMARY: %d failing of %zu\n", fails, cases.size());
+  if (stage == 3 && fails == 0) {
+    bench_case(491520, 1536, 512, 0, 0, 256, 1, 1, 0);
+    bench_case(491520, 1536, 512, 0, 0, 256, 1, 1, 5);   // A and output row-blocked
+    bench_case(491520, 512, 1536, 0, 0, 256, 1, 1, 5);
+    bench_case(1536, 512, 491520, 1, 1, 256, 12, 0, 3);
+    return 0;
+  }
   if (stage >= 2 && fails == 0) {
     bench_case(8192, 8192, 8192, 0, 0, 256, 1, 1);
     bench_case(8192, 8192, 8192, 0, 0, 128, 1, 1);
