@@ -164,11 +164,8 @@ def run_ours(args):
     model = m.VAE(precision=args.precision, **CFG).cuda()
     params = model.ordered_params()
     # one flat gradient buffer -> a single NCCL all-reduce per step in data-parallel runs
-    flat = torch.zeros(sum(p.numel() for p in params), dtype=torch.float32, device="cuda")
-    off = 0
-    for p in params:
-        p.grad = flat[off:off + p.numel()].view_as(p)
-        off += p.numel()
+    gbuf = m.ddp.FlatGradBuffer(params)
+    flat = gbuf.flat
     ids_np, _, eps_np = vo.make_batch(1000 + rank, B)
     ids_host = torch.from_numpy(ids_np).pin_memory()
     ids_dev = torch.from_numpy(ids_np).cuda()

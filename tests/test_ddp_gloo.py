@@ -1,0 +1,66 @@
+"""world_size-2 gloo test (CPU) of the data-parallel host logic: per-rank gradients of equal shards, averaged through
+FlatGradBuffer.allreduce_mean, equal the full-batch gradients (DataParallel semantics, train_distributed.py:87-89).
+The per-rank gradients come from the numpy oracle, so no GPU is needed."""
+import os
+import socket
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import vae_oracle as vo
+
+Z, H, L, B = 8, 16, 2, 6
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import molecular_vae_b200 as m
+    from molecular_vae_b200.ddp import FlatGradBuffer, shard_rows
+    P = vo.make_params(3, dtype=np.float64, latent=Z, hidden=H, layers=L)
+    ids, onehot, eps = vo.make_batch(4, B, latent=Z, dtype=np.float64)
+    lo, hi = shard_rows(B, rank, world)
+    r = vo.config_b_step(P, onehot[lo:hi], eps[lo:hi], layers=L)
+    keys = m.param_order(L)
+    params = [torch.nn.Parameter(torch.from_numpy(P[k]).clone()) for k in keys]
+    buf = FlatGradBuffer(params)
+    for p, k in zip(params, keys):
+        p.grad.copy_(torch.from_numpy(r["grads"][k]))
+    buf.allreduce_mean()
+    loss = torch.tensor([r["loss"]], dtype=torch.float64)
+    dist.all_reduce(loss)
+    if rank == 0:
+        np.savez(os.path.join(out_dir, "ddp.npz"), loss=loss.numpy() / world,
+                 **{k: p.grad.numpy() for k, p in zip(keys, params)})
+    dist.destroy_process_group()
+
+
+def test_allreduce_mean_matches_full_batch(tmp_path):
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    got = np.load(os.path.join(str(tmp_path), "ddp.npz"))
+    P = vo.make_params(3, dtype=np.float64, latent=Z, hidden=H, layers=L)
+    ids, onehot, eps = vo.make_batch(4, B, latent=Z, dtype=np.float64)
+    full = vo.config_b_step(P, onehot, eps, layers=L)
+    assert abs(float(got["loss"][0]) - full["loss"]) < 1e-10
+    for k, g in full["grads"].items():
+        np.testing.assert_allclose(got[k], g, rtol=1e-9, atol=1e-12)
+
+
+def test_shard_rows_cover_batch():
+    from molecular_vae_b200.ddp import shard_rows
+    for n, w in [(4096, 8), (250, 4), (7, 3)]:
+        spans = [shard_rows(n, r, w) for r in range(w)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
