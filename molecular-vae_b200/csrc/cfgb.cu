@@ -328,13 +328,13 @@ __global__ void combine_bias_kernel(const float* __restrict__ bih, const float* 
   if (i < 3 * Hp) out[i] = bih[i] + (i < 2 * Hp ? bhh[i] : 0.f);
 }
 // layer-0 projection -> bf16, optionally adding the recurrent r/z biases (fused kernel variant 3)
-// rb: write the row-blocked layout [row/32][3Hp/16][32][16] the fused kernel's epilogue reads
+// rb: write the row-blocked layout [row/32][3Hp/8][32][8] the fused kernel's epilogue reads
 __global__ void gi0_to_bf16_kernel(const float* __restrict__ src, const float* __restrict__ bhh_rz, int Hp,
                                    __nv_bfloat16* __restrict__ dst, long long n, int rb) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const int c = (int)(i % (3 * Hp));
     const long long r = i / (3 * Hp);
-    const long long o = rb ? ((r >> 5) * (3 * Hp / 16) + (c >> 4)) * 512 + (r & 31) * 16 + (c & 15) : i;
+    const long long o = rb ? ((r >> 5) * (3 * Hp / 8) + (c >> 3)) * 256 + (r & 31) * 8 + (c & 7) : i;
     dst[o] = __float2bfloat16_rn(src[i] + ((bhh_rz && c < 2 * Hp) ? bhh_rz[c] : 0.f));
   }
 }

@@ -17,6 +17,7 @@ struct mvae_gru_rec_args {
   __nv_bfloat16* dG;         // bwd: [T][Bp][4Hp]
   unsigned int* counters;    // [Bp/128]
   int* err_flag;
+  int a_box_rows;            // gru_rec2: rows per operand TMA box (0/128, 64, 32)
   int ones_col;              // gru_rec2 fwd: hidden-unit index whose h is forced to 1.0 (-1: none)
   int debug;                 // timing experiments only (gru_rec2): bit0 skip counter waits, bit1 de-share operand rows
   unsigned long long* trace; // optional debug timestamps [T][tiles per CTA][8] of CTA (0,0), may be null

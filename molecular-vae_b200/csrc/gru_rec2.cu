@@ -38,6 +38,7 @@ struct Params2 {
   unsigned int* counters;    // [pair_tiles][2]
   int* err_flag;
   unsigned long long* trace; // optional debug timestamps [T][NTILES][12] of CTA (0,0)
+  int a_box_rows;            // rows per operand TMA box (128, 64 or 32): a stage is loaded as 128/a_box_rows boxes
   int ones_col;              // fwd: hidden-unit index forced to 1.0 (bias-gradient trick) or -1
   int debug;                 // timing experiments only: bit0 skip counter waits, bit1 de-share operand rows
 };
@@ -231,7 +232,11 @@ gru_rec2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
             } else if (DIRECT) {
               if (leader) ptx::mbar_arrive_expect_tx(&full_bar[s], 2 * A_STAGE);
               if (CL == 2)
-                tma_load_3d_2sm(sA + s * A_STAGE, &tmA, mapa(ptx::smem_u32(&full_bar[s]), lrank), kc * 64, row0, slab);
+              {
+                const uint32_t fb = mapa(ptx::smem_u32(&full_bar[s]), lrank);
+                for (int r0 = 0; r0 < 128; r0 += p.a_box_rows)
+                  tma_load_3d_2sm(sA + s * A_STAGE + r0 * 128, &tmA, fb, kc * 64, row0 + r0, slab);
+              }
               else
                 tma_load_3d_2sm_mc(sA + s * A_STAGE + qd * A_PART, &tmA, &full_bar[s], mask_par, kc * 64, row0, slab);
             } else {
@@ -341,9 +346,10 @@ gru_rec2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
         // thread mapping): block (t, tile, pair, parity, part, array) of 4 KB, thread (q, lane) owns 32 B -> every
         // warp-wide 256-bit access is 1 KB contiguous.
         const size_t sv_blk = ((((size_t)t * p.pair_tiles + tile) * p.npairs + pair) * 2 + parity) * 4 + part;
-        __nv_bfloat16* svp = p.sv ? p.sv + sv_blk * 5 * 2048 + (size_t)(q * 32 + lane) * 16 : nullptr;
-        // gi / dX are produced by the GEMM epilogues in the row-blocked layout [row/32][width/16][32][16]:
-        // this thread's 16 units of its row are 32 contiguous bytes and the warp's 32 rows 1 KB contiguous.
+        // inside a 4 KB block: [q][half][lane][8 units] -> this thread's two 16-byte halves are 512 B apart
+        __nv_bfloat16* svp = p.sv ? p.sv + sv_blk * 5 * 2048 + (size_t)q * 512 + lane * 8 : nullptr;
+        // gi / dX are produced by the GEMM epilogues in the row-blocked layout [row/32][width/8][32][8]:
+        // this thread's 16 units of its row are two 16-byte pieces 512 B apart; a warp access is 512 B contiguous.
         const long long rblk = row >> 5;   // = tile*8 + parity*4 + q ; row & 31 == lane
         u32x8 pre[BWD ? 6 : 3];
         const bool nomem = (p.debug & 32) != 0;   // timing experiment: epilogue without global traffic
@@ -354,14 +360,14 @@ gru_rec2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
             for (int k = 0; k < 8; ++k) pre[a].v[k] = 0x3c003c00u;
         } else if (!BWD) {
           const __nv_bfloat16* g = p.gi + (long long)t * p.gi_tstride +
-                                   (rblk * (3 * p.Hp / 16) + ((u0 + uc) >> 4)) * 512 + lane * 16;
+                                   (rblk * (3 * p.Hp / 8) + ((u0 + uc) >> 3)) * 256 + lane * 8;
 #pragma unroll
-          for (int gate = 0; gate < 3; ++gate) pre[gate] = ldg256(g + (long long)gate * (p.Hp / 16) * 512);
+          for (int gate = 0; gate < 3; ++gate) pre[gate] = ldg2x128(g + (long long)gate * (p.Hp / 8) * 256);
         } else {
 #pragma unroll
-          for (int blk = 0; blk < 4; ++blk) pre[blk] = ldg256(svp + blk * 2048);
-          pre[4] = ldg256(svp + 4 * 2048);   // h_{t-1} (saved by the forward sweep next to the gates)
-          pre[5] = ldg256(p.dX + (long long)t * p.Bp * p.Hp + (rblk * (p.Hp / 16) + ((u0 + uc) >> 4)) * 512 + lane * 16);
+          for (int blk = 0; blk < 4; ++blk) pre[blk] = ldg2x128(svp + blk * 2048);
+          pre[4] = ldg2x128(svp + 4 * 2048);   // h_{t-1} (saved by the forward sweep next to the gates)
+          pre[5] = ldg2x128(p.dX + (long long)t * p.Bp * p.Hp + (rblk * (p.Hp / 8) + ((u0 + uc) >> 3)) * 256 + lane * 8);
         }
         (void)wait_bar(&tfull_bar[i], fph, p.err_flag);   // on failure keep walking: barriers below must be reached
         ptx::tc_fence_after();
@@ -381,6 +387,8 @@ gru_rec2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
 #pragma unroll
             for (int k = 0; k < 16; ++k) { ar[k] = 0u; az[k] = 0u; an[k] = 0u; hm[k] = 0u; }
           }
+          const bool tr2 = tr && (p.debug & 64);
+          if (tr2) p.trace[((size_t)step * NTILES + i) * 12 + 8] = gtime();
           float gr[16], gz[16], gn[16];
           unpack16(pre[0], gr);
           unpack16(pre[1], gz);
@@ -399,18 +407,24 @@ gru_rec2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
             gr[k] = r; gz[k] = z; gn[k] = n;
             an[k] = __float_as_uint(ghn);
           }
+          if (tr2) p.trace[((size_t)step * NTILES + i) * 12 + 9] = gtime();
           tmem_st_32x16(master_addr, h);
           if (!nomem) stg256(p.hs + ((long long)(t + 1) * p.Bp + row) * p.Hp + u0 + uc, h);
+          // everything other CTAs / the MMA wait for is issued: let the publisher go before the saved-gate stores
+          tmem_st_wait();
+          ptx::tc_fence_before();
+          ptx::mbar_arrive(&epi_bar[i]);
+          if (tr2) p.trace[((size_t)step * NTILES + i) * 12 + 10] = gtime();
           if (svp && !nomem) {
-            stg256(svp, gr);
-            stg256(svp + 2048, gz);
-            stg256(svp + 2 * 2048, gn);
+            stg2x128(svp, gr);
+            stg2x128(svp + 2048, gz);
+            stg2x128(svp + 2 * 2048, gn);
 #pragma unroll
             for (int k = 0; k < 16; ++k) h[k] = __uint_as_float(an[k]);
-            stg256(svp + 3 * 2048, h);
+            stg2x128(svp + 3 * 2048, h);
 #pragma unroll
             for (int k = 0; k < 16; ++k) h[k] = __uint_as_float(hm[k]);
-            stg256(svp + 4 * 2048, h);   // h_{t-1}: lets the BPTT epilogue skip the row-major hs read
+            stg2x128(svp + 4 * 2048, h);   // h_{t-1}: lets the BPTT epilogue skip the row-major hs read
           }
         } else {
           uint32_t acc[16], cm[16];
@@ -449,10 +463,13 @@ gru_rec2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
             stg256(g4 + 3 * p.Hp, hp);
           }
         }
-        tmem_st_wait();
-        ptx::tc_fence_before();
+        if (tr && (p.debug & 64)) p.trace[((size_t)step * NTILES + i) * 12 + 11] = gtime();
+        if (BWD) {
+          tmem_st_wait();
+          ptx::tc_fence_before();
+        }
         if (tr) p.trace[((size_t)step * NTILES + i) * 12 + 5] = gtime();
-        ptx::mbar_arrive(&epi_bar[i]);
+        if (BWD) ptx::mbar_arrive(&epi_bar[i]);
       }
       fph ^= 1;
     }
@@ -508,7 +525,8 @@ int launch2(const mvae_gru_rec_args& a, cudaStream_t st) {
     if (rc) return rc;
   }
   {
-    cuuint32_t box[3] = {64, (cuuint32_t)(128 / (CL / 2)), 1};
+    const int box_rows = (CL == 2) ? (a.a_box_rows > 0 ? a.a_box_rows : 128) : 128 / (CL / 2);
+    cuuint32_t box[3] = {64, (cuuint32_t)box_rows, 1};
     if (BWD) {
       cuuint64_t dims[3] = {(cuuint64_t)3 * Hp, (cuuint64_t)Bp, (cuuint64_t)T};
       cuuint64_t str[2] = {(cuuint64_t)4 * Hp * 2, (cuuint64_t)Bp * 4 * Hp * 2};
@@ -525,6 +543,7 @@ int launch2(const mvae_gru_rec_args& a, cudaStream_t st) {
   p.Bp = Bp; p.Hp = Hp; p.T = T; p.pair_tiles = Bp / 256; p.npairs = Hp / RU;
   p.gi = a.gi; p.gi_tstride = a.gi_tstride; p.bhn = a.bhh; p.hs = a.hs; p.sv = a.sv; p.dX = a.dX; p.dG = a.dG;
   p.counters = a.counters; p.err_flag = a.err_flag; p.trace = a.trace; p.debug = a.debug; p.ones_col = a.ones_col;
+  p.a_box_rows = a.a_box_rows > 0 ? a.a_box_rows : 128;
   auto kern = gru_rec2_kernel<BWD, FAST, CL>;
   static bool attr = false;
   if (!attr) {

@@ -117,6 +117,23 @@ __device__ __forceinline__ void stg256(void* p, const float (&v)[16]) {
                "r"(pack_bf2(v[10], v[11])), "r"(pack_bf2(v[12], v[13])), "r"(pack_bf2(v[14], v[15]))
                : "memory");
 }
+// 32 bytes per thread as two 16-byte halves 512 B apart: with lane l at +16*l each warp instruction covers 512
+// contiguous bytes in full 32-byte sectors (a 256-bit access costs two partial sector transactions per sector in L2).
+__device__ __forceinline__ u32x8 ldg2x128(const __nv_bfloat16* p) {
+  u32x8 r;
+  const uint4 a = __ldg(reinterpret_cast<const uint4*>(p));
+  const uint4 b = __ldg(reinterpret_cast<const uint4*>(p + 256));
+  r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
+  r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+  return r;
+}
+__device__ __forceinline__ void stg2x128(__nv_bfloat16* p, const float (&v)[16]) {
+  uint4 a, b;
+  a.x = pack_bf2(v[0], v[1]); a.y = pack_bf2(v[2], v[3]); a.z = pack_bf2(v[4], v[5]); a.w = pack_bf2(v[6], v[7]);
+  b.x = pack_bf2(v[8], v[9]); b.y = pack_bf2(v[10], v[11]); b.z = pack_bf2(v[12], v[13]); b.w = pack_bf2(v[14], v[15]);
+  *reinterpret_cast<uint4*>(p) = a;
+  *reinterpret_cast<uint4*>(p + 256) = b;
+}
 __device__ __forceinline__ void unpack16(const u32x8& a, float (&v)[16]) {
 #pragma unroll
   for (int i = 0; i < 8; ++i) { v[2 * i] = bf_lo(a.v[i]); v[2 * i + 1] = bf_hi(a.v[i]); }

@@ -41,7 +41,6 @@ struct KernelParams {
   void* out;
   long long ldc;
   const float* bias;   // per-N, may be null
-  int rbA, rbB;        // operand stored in the row-blocked layout (5-D tensor map)
   int out_rb;          // bf16 output in the row-blocked layout
   int out_bf16;        // 1: bf16 output, 0: fp32
   int accumulate;      // fp32 only: D += result (plain RMW, or red.add when splits > 1)
@@ -124,26 +123,19 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           ptx::mbar_arrive_expect_tx(&full_bar[s], C::STAGE_BYTES);
           uint8_t* a_dst = sA + s * A_STAGE_BYTES;
           uint8_t* b_dst = sB + s * C::B_STAGE_BYTES;
-          // plain layout: 3-D map {inner, rows, slab}; row-blocked layout: 5-D map {16, cols/16, 32, rows/32, slab}
           if (A_MN) {
 #pragma unroll
-            for (int c = 0; c < BM / 64; ++c) {
-              if (p.rbA) ptx::tma_load_5d(a_dst + c * 8192, &tmA, &full_bar[s], 0, (m_blk * BM + c * 64) >> 4, 0, (kb * BK) >> 5, p.slabA);
-              else ptx::tma_load_3d(a_dst + c * 8192, &tmA, &full_bar[s], m_blk * BM + c * 64, kb * BK, p.slabA);
-            }
+            for (int c = 0; c < BM / 64; ++c)
+              ptx::tma_load_3d(a_dst + c * 8192, &tmA, &full_bar[s], m_blk * BM + c * 64, kb * BK, p.slabA);
           } else {
-            if (p.rbA) ptx::tma_load_5d(a_dst, &tmA, &full_bar[s], 0, (kb * BK) >> 4, 0, (m_blk * BM) >> 5, p.slabA);
-            else ptx::tma_load_3d(a_dst, &tmA, &full_bar[s], kb * BK, m_blk * BM, p.slabA);
+            ptx::tma_load_3d(a_dst, &tmA, &full_bar[s], kb * BK, m_blk * BM, p.slabA);
           }
           if (B_MN) {
 #pragma unroll
-            for (int c = 0; c < BN / 64; ++c) {
-              if (p.rbB) ptx::tma_load_5d(b_dst + c * 8192, &tmB, &full_bar[s], 0, (n_blk * BN + c * 64) >> 4, 0, (kb * BK) >> 5, p.slabB);
-              else ptx::tma_load_3d(b_dst + c * 8192, &tmB, &full_bar[s], n_blk * BN + c * 64, kb * BK, p.slabB);
-            }
+            for (int c = 0; c < BN / 64; ++c)
+              ptx::tma_load_3d(b_dst + c * 8192, &tmB, &full_bar[s], n_blk * BN + c * 64, kb * BK, p.slabB);
           } else {
-            if (p.rbB) ptx::tma_load_5d(b_dst, &tmB, &full_bar[s], 0, (kb * BK) >> 4, 0, (n_blk * BN) >> 5, p.slabB);
-            else ptx::tma_load_3d(b_dst, &tmB, &full_bar[s], kb * BK, n_blk * BN, p.slabB);
+            ptx::tma_load_3d(b_dst, &tmB, &full_bar[s], kb * BK, n_blk * BN, p.slabB);
           }
           if (++s == C::STAGES) { s = 0; ph ^= 1; }
         }
@@ -221,22 +213,23 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
           const bool full = (col0 + 32 <= p.N);
           if (p.out_bf16 && p.out_rb) {
-            // row-blocked output: [row/32][ldc/16][row%32][16] -> a warp's 32 rows x 16 cols are 1 KB contiguous
+            // row-blocked output [row/32][ldc/8][row%32][8]: a warp's 32 rows x 8 cols are 512 B contiguous (full sectors)
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              const int col = col0 + h * 16;
+            for (int h = 0; h < 4; ++h) {
+              const int col = col0 + h * 8;
               if (col < p.N) {
                 __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) +
-                                   ((long long)(row >> 5) * (p.ldc >> 4) + (col >> 4)) * 512 + (row & 31) * 16;
-                uint32_t w[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                  __nv_bfloat162 b2 = __floats2bfloat162_rn(v[h * 16 + 2 * j], v[h * 16 + 2 * j + 1]);
-                  w[j] = *reinterpret_cast<uint32_t*>(&b2);
-                }
-                asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(o), "r"(w[0]), "r"(w[1]), "r"(w[2]),
-                             "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
-                             : "memory");
+                                   ((long long)(row >> 5) * (p.ldc >> 3) + (col >> 3)) * 256 + (row & 31) * 8;
+                uint4 pk;
+                __nv_bfloat162 b0 = __floats2bfloat162_rn(v[h * 8 + 0], v[h * 8 + 1]);
+                __nv_bfloat162 b1 = __floats2bfloat162_rn(v[h * 8 + 2], v[h * 8 + 3]);
+                __nv_bfloat162 b2 = __floats2bfloat162_rn(v[h * 8 + 4], v[h * 8 + 5]);
+                __nv_bfloat162 b3 = __floats2bfloat162_rn(v[h * 8 + 6], v[h * 8 + 7]);
+                pk.x = *reinterpret_cast<uint32_t*>(&b0);
+                pk.y = *reinterpret_cast<uint32_t*>(&b1);
+                pk.z = *reinterpret_cast<uint32_t*>(&b2);
+                pk.w = *reinterpret_cast<uint32_t*>(&b3);
+                *reinterpret_cast<uint4*>(o) = pk;
               }
             }
           } else if (p.out_bf16) {
@@ -328,14 +321,8 @@ int make_map(CUtensorMap* map, const mvae_umma_operand& op, int box_rows) {
   if (reinterpret_cast<uintptr_t>(op.ptr) & 15) return MVAE_ERR_INVALID;
   CUresult r;
   if (op.rb) {
-    if ((rows & 31) || (cols & 15) || (op.ld & 15) || (brow & 31)) return MVAE_ERR_INVALID;
-    cuuint64_t dims[5] = {16, (cuuint64_t)(cols / 16), 32, (cuuint64_t)(rows / 32), (cuuint64_t)slabs};
-    cuuint64_t strides[4] = {1024, 32, (cuuint64_t)(op.ld / 16) * 1024,
-                             (cuuint64_t)(slabs > 1 ? op.slab_stride : op.ld * rows) * 2};
-    cuuint32_t box[5] = {16, 4, 32, (cuuint32_t)(brow / 32), 1};
-    r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(op.ptr), dims, strides, box, estr,
-            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    // a 5-D tensor map over the row-blocked layout needs non-monotonic strides, which the TMA unit does not honour
+    return MVAE_ERR_UNSUPPORTED;
   } else {
     cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)slabs};
     cuuint64_t strides[2] = {(cuuint64_t)op.ld * 2, (cuuint64_t)(slabs > 1 ? op.slab_stride : op.ld * rows) * 2};
@@ -398,8 +385,8 @@ int mvae_umma_gemm(const mvae_umma_operand* A, const mvae_umma_operand* B, const
   kp.tiles_n = ceil_div(N, bn);
   kp.out = D->ptr; kp.ldc = D->ld; kp.bias = D->bias; kp.out_bf16 = D->bf16; kp.accumulate = D->accumulate;
   kp.err_flag = err_flag;
-  kp.rbA = A->rb; kp.rbB = B->rb; kp.out_rb = D->rb;
-  if (D->rb && (!D->bf16 || (D->ld & 15) || (N & 15))) return MVAE_ERR_INVALID;
+  kp.out_rb = D->rb;
+  if (D->rb && (!D->bf16 || (D->ld & 7) || (N & 7))) return MVAE_ERR_INVALID;
   CUtensorMap tmA, tmB;
   int rc = make_map(&tmA, *A, BM);
   if (rc) return rc;

@@ -12,7 +12,7 @@ struct mvae_umma_operand {
   int slabs;              // number of 2-D slabs (third TMA dimension), >= 1
   long long slab_stride;  // elements between slabs
   int slab;               // which slab this call uses
-  int rb;                 // 1: row-blocked layout [rows/32][ld/16][32][16] of the stored matrix (rows%32==0, ld%16==0)
+  int rb;                 // reserved (row-blocked operands are not supported by the TMA path); must be 0
 };
 
 struct mvae_umma_out {
@@ -21,7 +21,7 @@ struct mvae_umma_out {
   int bf16;           // output element type
   int accumulate;     // fp32 only: D += A*B
   const float* bias;  // optional per-column bias (fp32)
-  int rb;             // bf16 output only: row-blocked layout [M/32][ld/16][32][16]
+  int rb;             // bf16 output only: row-blocked layout [M/32][ld/8][32][8] (consumed by the recurrence epilogues)
 };
 
 // bn: 0 = auto, else 64/128/192/256.  splits: split-K factor (fp32 atomics epilogue when > 1; the

@@ -13,6 +13,7 @@ int main(int argc, char** argv) {
   const int T = argc > 3 ? atoi(argv[3]) : 120;
   const int fast = argc > 4 ? atoi(argv[4]) : 0;
   const int debug = argc > 5 ? atoi(argv[5]) : 0;
+  const int boxr = argc > 6 ? atoi(argv[6]) : 0;
   const int Hp = 512;
   const size_t slab = (size_t)B * Hp;
   __nv_bfloat16 *W, *WT, *gi, *hs, *sv, *dX, *dG; float* bhh; unsigned* ctr; int* err; unsigned long long* trace;
@@ -33,7 +34,7 @@ int main(int argc, char** argv) {
     mvae_gru_rec_args a{};
     a.backward = bwd; a.variant = variant; a.Bp = B; a.Hp = Hp; a.T = T;
     a.W = bwd ? WT : W; a.gi = gi; a.gi_tstride = (long long)B * 3 * Hp; a.bhh = bhh; a.hs = hs; a.sv = sv; a.dX = dX; a.dG = dG;
-    a.counters = ctr; a.err_flag = err; a.trace = nullptr; a.debug = debug; a.ones_col = -1;
+    a.counters = ctr; a.err_flag = err; a.trace = nullptr; a.debug = debug; a.ones_col = -1; a.a_box_rows = boxr;
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     auto launch = [&](const mvae_gru_rec_args* aa) { return variant >= 3 ? mvae_gru_rec2_launch(aa, fast, 0) : mvae_gru_rec_launch(aa, 0); };
     if (variant >= 3) printf("max active clusters (%s): cl2=%d cl4=%d cl8=%d\n", bwd ? "bwd" : "fwd", mvae_gru_rec2_max_clusters(bwd, 2), mvae_gru_rec2_max_clusters(bwd, 4), mvae_gru_rec2_max_clusters(bwd, 8));
