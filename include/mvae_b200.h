@@ -111,6 +111,21 @@ int mvae_onehot_to_ids(const float* onehot, long long rows, int charset, uint8_t
 int mvae_cfgb_read_error(const mvae_cfgb_desc* d, void* workspace, size_t workspace_bytes, int* flag,
                          mvae_stream_t stream);
 
+/* ---- optimiser step on flat fp32 buffers (train.py:102-104, train_distributed.py:91-94) ------------------
+ * Global-norm clipping = torch.nn.utils.clip_grad_norm(params, max_norm) over ONE flat gradient buffer (the layout
+ * molecular-vae_b200/ddp.py uses); the clip coefficient min(1, max_norm/(norm+1e-6)) stays on the device at
+ * (float*)((char*)scratch16 + 8) so no host sync is needed; apply_scale=0 leaves the gradients untouched and lets the
+ * optimiser kernels fold the coefficient in.  Adam = torch.optim.Adam (train.py:81), SGD = torch.optim.SGD with
+ * momentum (train_distributed.py:73).                                                                      */
+int mvae_clip_grad_norm(float* grads, long long n, float max_norm, void* scratch16, float* norm_out, int apply_scale,
+                        mvae_stream_t stream);
+int mvae_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n, float lr,
+                   float beta1, float beta2, float eps, float weight_decay, int step, const float* clip_coef,
+                   mvae_stream_t stream);
+int mvae_sgd_momentum_step(float* params, const float* grads, float* momentum_buf, long long n, float lr,
+                           float momentum, float weight_decay, int first_step, const float* clip_coef,
+                           mvae_stream_t stream);
+
 /* ---- building blocks, exported for the parity tests ---------------------------------------------- */
 /* D[M,N] (+)= A*B (+bias[N]); bf16 operands on the tcgen05 path.  a_mn_major: A stored [K][M];
  * b_mn_major: B stored [K][N] (else [N][K]).  out fp32 or bf16.                                       */

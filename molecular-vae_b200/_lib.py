@@ -51,6 +51,9 @@ def _load():
         "mvae_cfgb_decode_greedy": (i32, [dp, pp, vp, vp, vp, vp, ctypes.c_size_t, vp]),
         "mvae_onehot_to_ids": (i32, [vp, ll, i32, vp, vp, vp]),
         "mvae_cfgb_read_error": (i32, [dp, vp, ctypes.c_size_t, ctypes.POINTER(i32), vp]),
+        "mvae_clip_grad_norm": (i32, [vp, ll, ctypes.c_float, vp, vp, i32, vp]),
+        "mvae_adam_step": (i32, [vp, vp, vp, vp, ll] + [ctypes.c_float] * 5 + [i32, vp, vp]),
+        "mvae_sgd_momentum_step": (i32, [vp, vp, vp, ll] + [ctypes.c_float] * 3 + [i32, vp, vp]),
         "mvae_gemm_bf16": (i32, [vp, ll, i32, vp, ll, i32, vp, ll, i32, i32, vp, i32, i32, i32, i32, i32, vp, vp]),
         "mvae_sgemm": (i32, [vp, ll, ll, vp, ll, ll, vp, ll, i32, i32, i32, vp, i32, i32, i32, vp]),
     }
@@ -67,6 +70,7 @@ EXPORTED = [
     "mvae_cfgb_workspace_bytes", "mvae_cfgb_elbo_step", "mvae_cfgb_elbo_step_graph_create", "mvae_graph_launch",
     "mvae_graph_num_kernel_nodes", "mvae_graph_destroy", "mvae_cfgb_forward", "mvae_cfgb_backward",
     "mvae_cfgb_decode_greedy", "mvae_onehot_to_ids", "mvae_cfgb_read_error", "mvae_gemm_bf16", "mvae_sgemm",
+    "mvae_clip_grad_norm", "mvae_adam_step", "mvae_sgd_momentum_step",
 ]
 
 

@@ -9,7 +9,7 @@
 //     the tensor core through transposing shared-memory descriptors -- nothing is transposed
 //     in HBM.
 //   * warp-specialised, persistent: warp 0 = TMA producer, warp 1 = single-thread tcgen05.mma
-//     issuer (+ TMEM allocator), warps 2..5 = epilogue (tcgen05.ld -> registers -> global).
+//     issuer (+ TMEM allocator), warps 2..9 = epilogue (tcgen05.ld -> registers -> global).
 //     smem ring of STAGES {A 128x64, B BNx64} SWIZZLE_128B tiles, two TMEM accumulator
 //     buffers so the epilogue of unit i overlaps the main loop of unit i+1.
 //   * split-K work units (fp32 red.add epilogue) give the skinny wgrad GEMMs a full grid.
@@ -21,7 +21,8 @@ namespace {
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle row
 constexpr int UMMA_K = 16;
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_EPI_WARPS = 8;   // two warps per TMEM lane quarter, each takes half of the tile's columns
+constexpr int NUM_THREADS = (2 + NUM_EPI_WARPS) * 32;
 constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KiB
 
 template <int BN> struct Cfg {
@@ -92,7 +93,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(&tfull_bar[a], 1);
-      ptx::mbar_init(&tempty_bar[a], 128);
+      ptx::mbar_init(&tempty_bar[a], NUM_EPI_WARPS * 32);
     }
     ptx::fence_mbar_init();
   }
@@ -183,6 +184,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   } else {
     // ===================== epilogue: TMEM -> registers -> global =====================
     const int q = warp & 3;  // TMEM lane quarter this warp may touch
+    const int chalf = (warp - 2) >> 2;   // which half of the tile's columns this warp drains
+    constexpr int CH = BN / 2;
     int acc = 0;
     uint32_t acc_ph = 0;
     for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
@@ -197,7 +200,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const bool row_ok = row < p.M;
       const bool add_bias = p.bias != nullptr && split == 0;
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
+      for (int c0 = chalf * CH; c0 < (chalf + 1) * CH; c0 += 32) {
         uint32_t r[32];
         ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + c0, r);
         ptx::tmem_ld_wait();

@@ -179,3 +179,32 @@ def test_gemm_bf16_c_abi():
     assert int(err.item()) == 0
     ref = a.double() @ b.double().t()
     assert (d.double() - ref).abs().max().item() < 1e-2
+
+
+@pytest.mark.parametrize("kind", ["adam", "sgd"])
+def test_fused_clip_and_optimizer_match_torch(kind):
+    """clip_grad_norm + Adam (train.py:81,102-104) / SGD momentum (train_distributed.py:73,91-94) on flat buffers."""
+    m = load_pkg()
+    torch.manual_seed(0)
+    shapes = [(37, 11), (501,), (64, 3, 5), (1,)]
+    ps_ref = [torch.nn.Parameter(torch.randn(*s, device="cuda")) for s in shapes]
+    ps_new = [torch.nn.Parameter(p.detach().clone()) for p in ps_ref]
+    fp = m.optim.FlatParams(ps_new)
+    if kind == "adam":
+        ref = torch.optim.Adam(ps_ref, lr=8e-4)
+        opt = m.optim.FusedOptimizer(fp, "adam", lr=8e-4, max_norm=3.0)
+    else:
+        ref = torch.optim.SGD(ps_ref, lr=1.2e-3, momentum=0.85)
+        opt = m.optim.FusedOptimizer(fp, "sgd", lr=1.2e-3, momentum=0.85, max_norm=3.0)
+    for it in range(4):
+        gs = [torch.randn(*s, device="cuda") * (5.0 if it % 2 == 0 else 0.01) for s in shapes]
+        for p, q, g in zip(ps_ref, ps_new, gs):
+            p.grad = g.clone()
+            q.grad.copy_(g)
+        norm = torch.nn.utils.clip_grad_norm_(ps_ref, 3.0)
+        ref.step()
+        opt.step()
+        torch.cuda.synchronize()
+        assert abs(float(opt.norm) - float(norm)) <= 1e-5 * float(norm)
+        for p, q in zip(ps_ref, ps_new):
+            np.testing.assert_allclose(q.detach().cpu().numpy(), p.detach().cpu().numpy(), rtol=2e-5, atol=2e-6)
