@@ -71,3 +71,28 @@ def test_greedy_matches_step_argmax():
     r = vo.config_b_step(P, onehot, eps, train=False, need_grads=False, layers=2)
     dec, _ = vo.greedy_decode(P, r["mu"], layers=2)
     assert (dec == r["argmax"]).all()
+
+
+# ---- MOSES VAE oracle (oracle/moses_oracle.py) against fixtures from the reference's mosesvae.py ----
+@pytest.mark.parametrize("name", ["moses_b6", "moses_b3_kl1"])
+def test_moses_oracle_matches_reference(name):
+    from oracle import moses_oracle as mo
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    ps, bs, B = [int(v) for v in g["meta"]]
+    klw = float(g["kl_weight"][0])
+    P = mo.make_moses_params(ps, dtype=np.float64)
+    seqs, eps, pad = mo.make_moses_batch(bs, B, dtype=np.float64)
+    r = mo.moses_step(P, seqs, eps, pad, kl_weight=klw)
+    assert abs(r["kl"] - g["f64/kl"]) <= 1e-11 * abs(g["f64/kl"])
+    assert abs(r["recon"] - g["f64/recon"]) <= 1e-11 * abs(g["f64/recon"])
+    np.testing.assert_allclose(r["z"], g["f64/z"], rtol=1e-10, atol=1e-12)
+    # padded outputs: the reference applies decoder_fc to zero rows, i.e. the bias
+    np.testing.assert_allclose(r["y"], g["f64/y"], rtol=1e-9, atol=1e-11)
+    for k, gr in r["grads"].items():
+        gn = float(g[f"f64/gnorm/{k}"])
+        assert abs(np.sqrt((gr ** 2).sum()) - gn) <= 1e-9 * gn + 1e-14, k
+        if f"f64/gfull/{k}" in g:
+            np.testing.assert_allclose(gr, g[f"f64/gfull/{k}"], rtol=1e-8, atol=1e-12 + 1e-9 * gn)
+        else:
+            np.testing.assert_allclose(gr.reshape(-1)[g[f"f64/gidx/{k}"]], g[f"f64/gval/{k}"], rtol=1e-8,
+                                       atol=1e-12 + 1e-9 * gn)
