@@ -111,6 +111,39 @@ int mvae_onehot_to_ids(const float* onehot, long long rows, int charset, uint8_t
 int mvae_cfgb_read_error(const mvae_cfgb_desc* d, void* workspace, size_t workspace_bytes, int* flag,
                          mvae_stream_t stream);
 
+/* ---- MOSES-style character VAE ------------------------------------------------------------------------------
+ * mosesvae.py:27-199 (class VAE: forward :126-140, forward_encoder :142-164, forward_decoder :166-199).       */
+typedef struct mvae_moses_desc {
+  int32_t batch;      /* B sequences, sorted by length descending as the reference's collate does             */
+  int32_t max_len;    /* T: padded length of `ids` in this call (= longest sequence incl. bos/eos)             */
+  int32_t vocab;      /* V = len(vocab) <= 64 (chars + bos,eos,pad,unk; vocab.py:24); embedding is V x V       */
+  int32_t d_z;        /* 160 (mosesvae.py:39)                                                                 */
+  int32_t q_hidden;   /* 256 encoder GRU (mosesvae.py:33), multiple of 64                                     */
+  int32_t d_hidden;   /* 512 decoder GRU (mosesvae.py:40), multiple of 64                                     */
+  int32_t d_layers;   /* 3                                                                                    */
+  int32_t mlp_hidden; /* 256: hidden width of the q_mu / q_logvar MLPs (mosesvae.py:68-69)                     */
+  int32_t pad_id;     /* vocab.pad: ignore_index of the CE and padding_idx of the embedding                   */
+  int32_t precision;  /* MVAE_PREC_*                                                                          */
+  float kl_weight;    /* the scalar differentiated is kl_weight*kl + recon_weight*recon                        */
+  float recon_weight; /* (moses_train_distrib_logp.py:302-306 uses kl_weight*kl + recon, :335 recon only)      */
+} mvae_moses_desc;
+/* parameters / gradients: host arrays of fp32 device pointers in this order (reference shapes, row-major):
+ *   0 x_emb.weight (V,V) | 1-4 encoder_rnn.{weight_ih_l0 (3Hq,V), weight_hh_l0, bias_ih_l0, bias_hh_l0}
+ *   5-8 q_mu.{0.weight (mlp,Hq), 0.bias, 2.weight (d_z,mlp), 2.bias} | 9-12 q_logvar.{...}
+ *   13+4l.. decoder_rnn.{weight_ih_l (3Hd, V+d_z | Hd), weight_hh_l, bias_ih_l, bias_hh_l}
+ *   13+4L decoder_lat.weight (Hd,d_z), +1 decoder_lat.bias, +2 decoder_fc.weight (V,Hd), +3 decoder_fc.bias     */
+#define MVAE_MOSES_NUM_PARAMS(layers) (17 + 4 * (layers))
+size_t mvae_moses_workspace_bytes(const mvae_moses_desc* d);
+/* One step of VAE.forward (+ backward when grads != NULL; dropout is the identity).  ids: u8 (B,T) right-padded
+ * with pad_id; lengths: int32 (B) (incl. bos/eos); eps: fp32 (B,d_z).  out_scalars (device, 4 floats):
+ * kl_weight*kl + recon_weight*recon, kl, recon, number of non-pad targets.  z_out, logvar_out (B,d_z) and
+ * y_out (B,T,V; the logits the reference returns, decoder_fc bias at padded positions) are optional.           */
+int mvae_moses_step(const mvae_moses_desc* d, const float* const* params, float* const* grads, const uint8_t* ids,
+                    const int32_t* lengths, const float* eps, float* out_scalars, float* z_out, float* logvar_out,
+                    float* y_out, void* workspace, size_t workspace_bytes, mvae_stream_t stream);
+int mvae_moses_read_error(const mvae_moses_desc* d, void* workspace, size_t workspace_bytes, int* flag,
+                          mvae_stream_t stream);
+
 /* ---- optimiser step on flat fp32 buffers (train.py:102-104, train_distributed.py:91-94) ------------------
  * Global-norm clipping = torch.nn.utils.clip_grad_norm(params, max_norm) over ONE flat gradient buffer (the layout
  * molecular-vae_b200/ddp.py uses); the clip coefficient min(1, max_norm/(norm+1e-6)) stays on the device at

@@ -21,6 +21,12 @@ class CfgBDesc(ctypes.Structure):
     ]
 
 
+class MosesDesc(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int32) for n in ("batch", "max_len", "vocab", "d_z", "q_hidden", "d_hidden", "d_layers",
+                                              "mlp_hidden", "pad_id", "precision")] + [("kl_weight", ctypes.c_float),
+                                                                                   ("recon_weight", ctypes.c_float)]
+
+
 class MvaeError(RuntimeError):
     pass
 
@@ -51,6 +57,9 @@ def _load():
         "mvae_cfgb_decode_greedy": (i32, [dp, pp, vp, vp, vp, vp, ctypes.c_size_t, vp]),
         "mvae_onehot_to_ids": (i32, [vp, ll, i32, vp, vp, vp]),
         "mvae_cfgb_read_error": (i32, [dp, vp, ctypes.c_size_t, ctypes.POINTER(i32), vp]),
+        "mvae_moses_workspace_bytes": (ctypes.c_size_t, [ctypes.POINTER(MosesDesc)]),
+        "mvae_moses_step": (i32, [ctypes.POINTER(MosesDesc), pp, pp, vp, vp, vp, vp, vp, vp, vp, vp, ctypes.c_size_t, vp]),
+        "mvae_moses_read_error": (i32, [ctypes.POINTER(MosesDesc), vp, ctypes.c_size_t, ctypes.POINTER(i32), vp]),
         "mvae_clip_grad_norm": (i32, [vp, ll, ctypes.c_float, vp, vp, i32, vp]),
         "mvae_adam_step": (i32, [vp, vp, vp, vp, ll] + [ctypes.c_float] * 5 + [i32, vp, vp]),
         "mvae_sgd_momentum_step": (i32, [vp, vp, vp, ll] + [ctypes.c_float] * 3 + [i32, vp, vp]),
@@ -71,6 +80,7 @@ EXPORTED = [
     "mvae_graph_num_kernel_nodes", "mvae_graph_destroy", "mvae_cfgb_forward", "mvae_cfgb_backward",
     "mvae_cfgb_decode_greedy", "mvae_onehot_to_ids", "mvae_cfgb_read_error", "mvae_gemm_bf16", "mvae_sgemm",
     "mvae_clip_grad_norm", "mvae_adam_step", "mvae_sgd_momentum_step",
+    "mvae_moses_workspace_bytes", "mvae_moses_step", "mvae_moses_read_error",
 ]
 
 

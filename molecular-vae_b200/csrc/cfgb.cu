@@ -690,6 +690,8 @@ int check_ws(const mvae_cfgb_desc* desc, void* ws, size_t ws_bytes, Dims* d, WS*
 
 }  // namespace
 
+void mvae_count_launches(int n) { g_launches += n; }   // used by the other orchestration units (moses.cu)
+
 struct mvae_graph {
   cudaGraph_t graph;
   cudaGraphExec_t exec;

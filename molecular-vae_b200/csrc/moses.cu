@@ -1,0 +1,594 @@
+// MOSES-style character VAE (mosesvae.py:27-199): fused forward + loss + backward of one batch on one B200.
+//
+//   encoder  (mosesvae.py:142-164): trainable one-hot-initialised embedding -> packed GRU(V -> Hq) -> last state ->
+//            two 2-layer MLP heads (mu, logvar) -> z = mu + exp(logvar/2) eps,  kl = 0.5 mean_b sum_d (e^lv + mu^2 - 1 - lv)
+//   decoder  (mosesvae.py:166-199): input [emb(x_t) | z], h0 = decoder_lat(z) for every layer, GRU L x Hd, fc -> V,
+//            recon = CE(y[:, :-1], x[:, 1:], ignore_index = pad)  (mean over the batch's non-pad targets)
+// Layout choices (same conventions as cfgb.cu): time-major slabs [T][Bp][H], Bp = B rounded to 256; sequences are
+// right-padded to T = max length.  Padded steps are simply computed: nothing a valid position needs depends on them
+// (a sequence's padded steps come AFTER its valid ones) and every gradient that enters them is zero (ignore_index /
+// final-state scatter), so no masking is needed inside the recurrence; the encoder's final state is captured at
+// t = L_b - 1 by the gate kernel.  The embedding makes the layer-0 input projections table look-ups:
+//   x_t W_ih^T = (E W_ih[:, :V]^T)[x_t]  (+ z W_ih[:, V:]^T + b_ih for the decoder, computed once per molecule),
+// and their gradients one skinny tensor-core GEMM  dTBL = onehot^T * dgi  (K = T*B).
+// The recurrence here is the per-step engine (tcgen05 GEMM + gate kernel per step); the persistent 2-CTA kernel of
+// gru_rec2.cu needs an h0 / dh0 port before it can serve this path (next round).
+#include <stdlib.h>
+
+#include "../../include/mvae_b200.h"
+#include "common.cuh"
+#include "simt_kernels.cuh"
+#include "umma_gemm.h"
+
+void mvae_count_launches(int n);   // cfgb.cu
+
+namespace {
+
+#define RC(expr) do { int _rc = (expr); if (_rc != MVAE_OK) return _rc; } while (0)
+#define KCHECK() do { mvae_count_launches(1); MVAE_CUDA_CHECK(cudaGetLastError()); } while (0)
+
+struct MDims {
+  int B, Bp, T, V, CP, Z, Hq, Hd, L, MLP, pad;
+  bool bf16;
+  float kl_w, rec_w;
+};
+
+int make_dims(const mvae_moses_desc* d, MDims* o) {
+  if (!d) return MVAE_ERR_INVALID;
+  if (d->batch <= 0 || d->max_len < 2 || d->max_len > 512 || d->vocab < 5 || d->vocab > 64 || d->d_z <= 0 ||
+      d->q_hidden <= 0 || d->d_hidden <= 0 || d->d_layers < 1 || d->d_layers > 4 || d->mlp_hidden <= 0)
+    return MVAE_ERR_INVALID;
+  if ((d->q_hidden & 63) || (d->d_hidden & 63)) return MVAE_ERR_UNSUPPORTED;   // hidden sizes must be multiples of 64
+  if (d->precision != MVAE_PREC_FP32 && d->precision != MVAE_PREC_BF16) return MVAE_ERR_INVALID;
+  o->B = d->batch; o->Bp = round_up(d->batch, 256); o->T = d->max_len; o->V = d->vocab; o->CP = 64;
+  o->Z = d->d_z; o->Hq = d->q_hidden; o->Hd = d->d_hidden; o->L = d->d_layers; o->MLP = d->mlp_hidden;
+  o->pad = d->pad_id; o->bf16 = d->precision == MVAE_PREC_BF16; o->kl_w = d->kl_weight; o->rec_w = d->recon_weight;
+  return MVAE_OK;
+}
+
+struct Carver {
+  uint8_t* base; size_t off;
+  template <typename T> T* take(size_t n) {
+    off = (off + 255) & ~size_t(255);
+    T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+    off += n * sizeof(T);
+    return p;
+  }
+};
+
+struct MWS {
+  int* err_flag; double* kl_sum; double* nll_sum; int* M;
+  float *TBLe, *TBLd, *hlast, *rmu, *rlv, *mu, *lv, *z, *h0, *zproj, *dh0, *dz, *dmu, *dlv, *dr, *dhenc, *dgisum;
+  float *dTBL;      // [CP][3Hd] fp32, columns in (n,r,z) order
+  float *dWT;       // [3Hd][V] staging
+  void *OH;         // [T*Bp][CP] TA one-hot of the tokens
+  void *gi;         // [T][Bp][3Hd] TA
+  void *hs_enc, *sv_enc, *hs[4], *sv[4], *dG, *dX, *dlogits;
+  float *gh, *h32[2], *dh_carry, *logits;
+  void *Whh_enc, *Whh[4], *Wih[4], *Wih_nrz[4], *Wfc;
+  float *bhh_enc, *bih[4], *bhh[4], *bfc;
+  float *dW_p, *dWfc_p, *csum;
+  size_t total;
+};
+
+void carve(const MDims& d, void* base, MWS* w) {
+  Carver c{reinterpret_cast<uint8_t*>(base), 0};
+  const size_t es = d.bf16 ? 2 : 4;
+  const size_t B = d.B, Bp = d.Bp, T = d.T, Hd = d.Hd, Hq = d.Hq;
+  w->err_flag = c.take<int>(1); w->kl_sum = c.take<double>(1); w->nll_sum = c.take<double>(1); w->M = c.take<int>(1);
+  w->TBLe = c.take<float>((size_t)d.V * 3 * Hq); w->TBLd = c.take<float>((size_t)d.V * 3 * Hd);
+  w->hlast = c.take<float>(Bp * Hq); w->rmu = c.take<float>(B * d.MLP); w->rlv = c.take<float>(B * d.MLP);
+  w->mu = c.take<float>(B * d.Z); w->lv = c.take<float>(B * d.Z); w->z = c.take<float>(B * d.Z);
+  w->h0 = c.take<float>(Bp * Hd); w->zproj = c.take<float>(B * 3 * Hd); w->dh0 = c.take<float>(Bp * Hd);
+  w->dz = c.take<float>(B * d.Z); w->dmu = c.take<float>(B * d.Z); w->dlv = c.take<float>(B * d.Z);
+  w->dr = c.take<float>(B * d.MLP); w->dhenc = c.take<float>(B * Hq); w->dgisum = c.take<float>(Bp * 3 * Hd);
+  w->dTBL = c.take<float>((size_t)d.CP * 3 * Hd); w->dWT = c.take<float>((size_t)3 * Hd * d.CP);
+  w->OH = c.take<uint8_t>(T * Bp * d.CP * es);
+  w->gi = c.take<uint8_t>(T * Bp * 3 * Hd * es);
+  w->hs_enc = c.take<uint8_t>((T + 1) * Bp * Hq * es); w->sv_enc = c.take<uint8_t>(T * Bp * 4 * Hq * es);
+  for (int l = 0; l < d.L; ++l) {
+    w->hs[l] = c.take<uint8_t>((T + 1) * Bp * Hd * es);
+    w->sv[l] = c.take<uint8_t>(T * Bp * 4 * Hd * es);
+  }
+  w->dG = c.take<uint8_t>(T * Bp * 4 * Hd * es); w->dX = c.take<uint8_t>(T * Bp * Hd * es);
+  w->dlogits = c.take<uint8_t>(T * Bp * d.CP * es);
+  w->gh = c.take<float>(Bp * 3 * Hd); w->h32[0] = c.take<float>(Bp * Hd); w->h32[1] = c.take<float>(Bp * Hd);
+  w->dh_carry = c.take<float>(Bp * Hd); w->logits = c.take<float>(T * Bp * d.CP);
+  w->Whh_enc = c.take<uint8_t>(3 * Hq * Hq * es); w->bhh_enc = c.take<float>(3 * Hq);
+  for (int l = 0; l < d.L; ++l) {
+    w->Whh[l] = c.take<uint8_t>(3 * Hd * Hd * es); w->Wih[l] = c.take<uint8_t>(3 * Hd * Hd * es);
+    w->Wih_nrz[l] = c.take<uint8_t>(3 * Hd * Hd * es);
+    w->bih[l] = c.take<float>(3 * Hd); w->bhh[l] = c.take<float>(3 * Hd);
+  }
+  w->Wfc = c.take<uint8_t>(d.CP * Hd * es); w->bfc = c.take<float>(d.CP);
+  w->dW_p = c.take<float>(3 * Hd * Hd); w->dWfc_p = c.take<float>(d.CP * Hd); w->csum = c.take<float>(4 * Hd);
+  w->total = (c.off + 255) & ~size_t(255);
+}
+
+// parameter order = oracle.moses_oracle.moses_shapes / state_dict order of mosesvae.VAE (first occurrence of each tensor)
+enum { P_EMB = 0, P_E_WIH, P_E_WHH, P_E_BIH, P_E_BHH, P_MU0W, P_MU0B, P_MU2W, P_MU2B, P_LV0W, P_LV0B, P_LV2W, P_LV2B, P_DEC0 };
+inline int P_WIH(int l) { return P_DEC0 + 4 * l; }
+inline int P_WHH(int l) { return P_DEC0 + 4 * l + 1; }
+inline int P_BIH(int l) { return P_DEC0 + 4 * l + 2; }
+inline int P_BHH(int l) { return P_DEC0 + 4 * l + 3; }
+inline int P_LATW(int L) { return P_DEC0 + 4 * L; }
+inline int P_LATB(int L) { return P_DEC0 + 4 * L + 1; }
+inline int P_FCW(int L) { return P_DEC0 + 4 * L + 2; }
+inline int P_FCB(int L) { return P_DEC0 + 4 * L + 3; }
+
+inline int grid_for(long long n, int block = 256, int cap = 148 * 16) {
+  long long g = (n + block - 1) / block;
+  return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+inline int memset_async(void* p, size_t bytes, cudaStream_t st) {
+  mvae_count_launches(1);
+  MVAE_CUDA_CHECK(cudaMemsetAsync(p, 0, bytes, st));
+  return MVAE_OK;
+}
+template <typename TA>
+int gemm(int* err_flag, cudaStream_t st, const TA* A, long long lda, bool a_trans, const TA* B, long long ldb,
+         bool b_kmajor, void* out, long long ldc, bool out_is_ta, int M, int N, int K, const float* bias,
+         bool accumulate, int splits, int bn = 0) {
+  mvae_count_launches(1);
+  if constexpr (sizeof(TA) == 4) {
+    (void)out_is_ta; (void)bn; (void)err_flag;
+    return simt::sgemm(st, reinterpret_cast<const float*>(A), a_trans ? 1 : lda, a_trans ? lda : 1,
+                       reinterpret_cast<const float*>(B), b_kmajor ? 1 : ldb, b_kmajor ? ldb : 1,
+                       reinterpret_cast<float*>(out), ldc, M, N, K, bias, simt::ACT_NONE, accumulate ? 1 : 0, splits);
+  } else {
+    mvae_umma_operand a{A, a_trans ? 1 : 0, M, K, lda, 1, 0, 0, 0};
+    mvae_umma_operand b{B, b_kmajor ? 0 : 1, N, K, ldb, 1, 0, 0, 0};
+    mvae_umma_out o{out, ldc, out_is_ta ? 1 : 0, accumulate ? 1 : 0, bias, 0};
+    return mvae_umma_gemm(&a, &b, &o, M, N, K, bn, splits, 0, err_flag, st);
+  }
+}
+inline int sg(cudaStream_t st, const float* A, long long sam, long long sak, const float* B, long long sbk,
+              long long sbn, float* C, long long ldc, int M, int N, int K, const float* bias, int act, int accumulate,
+              int splits = 1) {
+  mvae_count_launches(1);
+  return simt::sgemm(st, A, sam, sak, B, sbk, sbn, C, ldc, M, N, K, bias, act, accumulate, splits);
+}
+inline int sg_wgrad(cudaStream_t st, const float* A, long long sam, long long sak, const float* B, long long sbk,
+                    long long sbn, float* C, long long ldc, int M, int N, int K) {
+  if (ldc == N) RC(memset_async(C, (size_t)M * N * 4, st));
+  else { mvae_count_launches(1); MVAE_CUDA_CHECK(cudaMemset2DAsync(C, ldc * 4, 0, (size_t)N * 4, M, st)); }
+  const int splits = K >= 1024 ? 16 : (K >= 256 ? 4 : 1);
+  return sg(st, A, sam, sak, B, sbk, sbn, C, ldc, M, N, K, nullptr, simt::ACT_NONE, 1, splits);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// kernels specific to this path
+// ---------------------------------------------------------------------------------------------------------
+// out[t][b][c] = tbl[ids[b][t]][c] (+ add[b][c]);  rows b >= B are zero.  tbl is [V][W] fp32, out [T][Bp][W] TA.
+template <typename TA>
+__global__ void gather_rows_kernel(const float* __restrict__ tbl, int W, const uint8_t* __restrict__ ids, int ids_ld,
+                                   const float* __restrict__ add, int B, int Bp, int T, TA* __restrict__ out) {
+  const long long total = (long long)T * Bp * W;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % W);
+    const long long rb = i / W;
+    const int b = (int)(rb % Bp), t = (int)(rb / Bp);
+    float v = 0.f;
+    if (b < B) {
+      v = tbl[(long long)ids[(long long)b * ids_ld + t] * W + c];
+      if (add) v += add[(long long)b * W + c];
+    }
+    out[i] = from_f32<TA>(v);
+  }
+}
+// OH[t*Bp + b][v] = 1 iff b < B and ids[b][t] == v   (CP columns)
+template <typename TA>
+__global__ void onehot_rows_kernel(const uint8_t* __restrict__ ids, int ids_ld, int B, int Bp, int T, int CP,
+                                   TA* __restrict__ out) {
+  const long long total = (long long)T * Bp * CP;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % CP);
+    const long long rb = i / CP;
+    const int b = (int)(rb % Bp), t = (int)(rb / Bp);
+    out[i] = from_f32<TA>((b < B && ids[(long long)b * ids_ld + t] == c) ? 1.f : 0.f);
+  }
+}
+// z = mu + exp(lv/2) eps ; kl_sum += sum 0.5 (e^lv + mu^2 - 1 - lv)     (mosesvae.py:159-162)
+__global__ void reparam_kl_std_kernel(const float* __restrict__ mu, const float* __restrict__ lv,
+                                      const float* __restrict__ eps, long long n, float* __restrict__ z,
+                                      double* __restrict__ kl_sum) {
+  double local = 0.0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float m = mu[i], l = lv[i];
+    z[i] = fmaf(eps[i], expf(0.5f * l), m);
+    local += 0.5 * (double)(expf(l) + m * m - 1.0f - l);
+  }
+  for (int o = 16; o; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+  __shared__ double red[32];
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = local;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int w = 0; w < (blockDim.x >> 5); ++w) s += red[w];
+    atomicAdd(kl_sum, s);
+  }
+}
+__global__ void reparam_kl_std_bwd_kernel(const float* __restrict__ mu, const float* __restrict__ lv,
+                                          const float* __restrict__ eps, const float* __restrict__ dz, float klw_over_b,
+                                          long long n, float* __restrict__ dmu, float* __restrict__ dlv) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float m = mu[i], l = lv[i], g = dz[i];
+    dmu[i] = g + klw_over_b * m;
+    dlv[i] = g * eps[i] * 0.5f * expf(0.5f * l) + klw_over_b * 0.5f * (expf(l) - 1.0f);
+  }
+}
+__global__ void relu_bwd_kernel(const float* __restrict__ out, float* __restrict__ d, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    if (!(out[i] > 0.f)) d[i] = 0.f;
+}
+__global__ void count_targets_kernel(const int* __restrict__ lens, int B, int* __restrict__ M) {
+  int local = 0;
+  for (int b = threadIdx.x; b < B; b += blockDim.x) local += lens[b] - 1;
+  atomicAdd(M, local);
+}
+// slab-0 initialisation: hsA[b][j] = h0[b][j] (rows >= B zero), h32 copy
+template <typename TA>
+__global__ void init_h0_kernel(const float* __restrict__ h0, int B, int Bp, int H, TA* __restrict__ hsA,
+                               float* __restrict__ h32) {
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= (long long)Bp * H) return;
+  const int b = (int)(idx / H);
+  const float v = b < B ? h0[idx] : 0.f;
+  hsA[idx] = from_f32<TA>(v);
+  if (h32) h32[idx] = v;
+}
+// shifted cross entropy with ignore_index (mosesvae.py:193-197): row (t,b) is a target position iff t+1 < L_b.
+// One warp per row of logits[T*Bp][CP]; dlogits = (softmax - onehot(x[b][t+1])) / M on target rows, 0 elsewhere.
+// y (optional, [B][T][V]): the reference's returned logits (decoder_fc(0) = bias at padded positions).
+template <typename TA>
+__global__ void head_ce_kernel(const float* __restrict__ logits, int CP, int V, const uint8_t* __restrict__ ids,
+                               int ids_ld, const int* __restrict__ lens, int B, int Bp, int T,
+                               const int* __restrict__ Mcount, float rec_w, const float* __restrict__ bias,
+                               TA* __restrict__ dlogits,
+                               float* __restrict__ y, double* __restrict__ nll_sum) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  double local = 0.0;
+  if (warp < (long long)T * Bp) {
+    const int t = warp / Bp, b = warp - t * Bp;
+    const long long row = warp;
+    const int L = b < B ? lens[b] : 0;
+    const bool target = b < B && (t + 1 < L);
+    const float a0 = lane < V ? logits[row * CP + lane] : -INFINITY;
+    const float a1 = (lane + 32) < V ? logits[row * CP + lane + 32] : -INFINITY;
+    if (y && b < B) {
+      float* yr = y + ((long long)b * T + t) * V;
+      if (lane < V) yr[lane] = t < L ? a0 : bias[lane];
+      if (lane + 32 < V) yr[lane + 32] = t < L ? a1 : bias[lane + 32];
+    }
+    float d0 = 0.f, d1 = 0.f;
+    if (target) {
+      float m = fmaxf(a0, a1);
+      for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+      const float e0 = lane < V ? expf(a0 - m) : 0.f, e1 = (lane + 32) < V ? expf(a1 - m) : 0.f;
+      float s = e0 + e1;
+      for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      const int tgt = ids[(long long)b * ids_ld + t + 1];
+      const float inv = rec_w / (float)Mcount[0];
+      d0 = (e0 / s - (lane == tgt ? 1.f : 0.f)) * inv;
+      d1 = (e1 / s - (lane + 32 == tgt ? 1.f : 0.f)) * inv;
+      const float at = __shfl_sync(0xffffffffu, tgt < 32 ? a0 : a1, tgt & 31);
+      if (lane == 0) local = (double)(m + logf(s) - at);
+    }
+    if (dlogits) {
+      dlogits[row * CP + lane] = from_f32<TA>(lane < V ? d0 : 0.f);
+      dlogits[row * CP + lane + 32] = from_f32<TA>((lane + 32) < V ? d1 : 0.f);
+    }
+  }
+  __shared__ double red[32];
+  if (lane == 0) red[threadIdx.x >> 5] = local;
+  __syncthreads();
+  if (threadIdx.x == 0 && nll_sum) {
+    double s = 0.0;
+    for (int w = 0; w < (blockDim.x >> 5); ++w) s += red[w];
+    atomicAdd(nll_sum, s);
+  }
+}
+// dX_enc[L_b - 1][b][:] = dh_enc[b][:] (the only gradient entering the encoder GRU); dX zeroed beforehand
+template <typename TA>
+__global__ void scatter_final_grad_kernel(const float* __restrict__ dh, const int* __restrict__ lens, int B, int Bp,
+                                          int H, TA* __restrict__ dX) {
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= (long long)B * H) return;
+  const int b = (int)(idx / H), j = (int)(idx - (long long)b * H);
+  dX[((long long)(lens[b] - 1) * Bp + b) * H + j] = from_f32<TA>(dh[idx]);
+}
+// sum over time of the dgi window of dG ([T][Bp][4H], blocks n,r,z) -> fp32 [Bp][3H] in (r,z,n) order
+template <typename TA>
+__global__ void dgi_time_sum_t_kernel(const TA* __restrict__ dG, int T, int Bp, int H, float* __restrict__ out) {
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= (long long)Bp * 3 * H) return;
+  const int c = (int)(idx % (3 * H));
+  const int b = (int)(idx / (3 * H));
+  const int g = c / H, j = c - g * H;
+  const int blk = (g == 0) ? 1 : (g == 1 ? 2 : 0);
+  const TA* p = dG + (long long)b * 4 * H + blk * H + j;
+  float s = 0.f;
+  for (int t = 0; t < T; ++t) s += to_f32<TA>(p[(long long)t * Bp * 4 * H]);
+  out[idx] = s;
+}
+// dW[(r,z,n) row g*H+j][v] = dTBL[v][blk(g)*H + j]   : transposes the (n,r,z)-ordered table gradient into torch's order
+__global__ void tbl_grad_to_rzn_T_kernel(const float* __restrict__ dTBL, int H, int V, float* __restrict__ out /*[3H][V]*/) {
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= 3ll * H * V) return;
+  const int v = (int)(idx % V);
+  const int r = (int)(idx / V);
+  const int g = r / H, j = r - g * H;
+  const int blk = (g == 0) ? 1 : (g == 1 ? 2 : 0);
+  out[idx] = dTBL[(long long)v * 3 * H + blk * H + j];
+}
+__global__ void gate_bias_grads_kernel(const float* __restrict__ csum, int H, float* __restrict__ db_ih,
+                                       float* __restrict__ db_hh) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 3 * H) return;
+  const int g = i / H, j = i - g * H;
+  const int blk_ih = (g == 0) ? 1 : (g == 1 ? 2 : 0);
+  const int blk_hh = (g == 0) ? 1 : (g == 1 ? 2 : 3);
+  if (db_ih) db_ih[i] = csum[blk_ih * H + j];
+  db_hh[i] = csum[blk_hh * H + j];
+}
+__global__ void add_inplace_kernel(float* __restrict__ a, const float* __restrict__ b, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) a[i] += b[i];
+}
+__global__ void zero_row_kernel(float* __restrict__ a, int row, int cols) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < cols) a[(long long)row * cols + i] = 0.f;
+}
+__global__ void finalize_kernel(const double* __restrict__ kl_sum, const double* __restrict__ nll_sum,
+                                const int* __restrict__ M, int B, float klw, float recw, float* __restrict__ out) {
+  const double kl = kl_sum[0] / B, rec = nll_sum[0] / (double)M[0];
+  out[0] = (float)(klw * kl + recw * rec); out[1] = (float)kl; out[2] = (float)rec; out[3] = (float)M[0];
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// per-step GRU engine (one layer), time-major, optional h0 / final-state capture / dh0
+// ---------------------------------------------------------------------------------------------------------
+template <typename TA>
+int gru_fwd(const MDims& d, const MWS& w, cudaStream_t st, const TA* gi, const TA* Whh, const float* bhh, TA* hs, TA* sv,
+            int H, const float* h0, const int* lens, float* hlast) {
+  const int Bp = d.Bp, T = d.T;
+  const size_t slab = (size_t)Bp * H;
+  if (h0) {
+    init_h0_kernel<TA><<<ceil_div((int)slab, 256), 256, 0, st>>>(h0, d.B, Bp, H, hs, d.bf16 ? w.h32[0] : nullptr);
+    KCHECK();
+  } else {
+    RC(memset_async(hs, slab * sizeof(TA), st));
+    if (d.bf16) RC(memset_async(w.h32[0], slab * 4, st));
+  }
+  const int gate_grid = ceil_div((int)slab, 256);
+  for (int t = 0; t < T; ++t) {
+    RC(gemm<TA>(w.err_flag, st, hs + t * slab, H, false, Whh, H, true, w.gh, 3 * H, false, Bp, 3 * H, H, bhh, false, 1));
+    simt::gru_gate_fwd_kernel<TA, TA><<<gate_grid, 256, 0, st>>>(
+        gi + (size_t)t * Bp * 3 * H, w.gh, d.bf16 ? w.h32[t & 1] : nullptr, hs + t * slab, hs + (t + 1) * slab,
+        d.bf16 ? w.h32[(t + 1) & 1] : nullptr, sv + (size_t)t * Bp * 4 * H, Bp, H, lens, hlast, t, d.B);
+    KCHECK();
+  }
+  return MVAE_OK;
+}
+// after the call: dG filled for all t; if dh0_acc != null, dh0_acc += dL/dh0
+template <typename TA>
+int gru_bwd(const MDims& d, const MWS& w, cudaStream_t st, const TA* Whh, const TA* hs, const TA* sv, const TA* dX, TA* dG,
+            int H, float* dh0_acc) {
+  const int Bp = d.Bp, T = d.T;
+  const size_t slab = (size_t)Bp * H;
+  RC(memset_async(w.dh_carry, slab * 4, st));
+  const int gate_grid = ceil_div((int)slab, 256);
+  for (int t = T - 1; t >= 0; --t) {
+    TA* dGt = dG + (size_t)t * Bp * 4 * H;
+    simt::gru_gate_bwd_kernel<TA><<<gate_grid, 256, 0, st>>>(sv + (size_t)t * Bp * 4 * H, hs + t * slab, dX + t * slab,
+                                                             w.dh_carry, dGt, nullptr, Bp, H);
+    KCHECK();
+    if (t > 0 || dh0_acc)
+      RC(gemm<TA>(w.err_flag, st, dGt + H, 4 * H, false, Whh, H, false, w.dh_carry, H, false, Bp, H, 3 * H, nullptr, true, 1));
+  }
+  if (dh0_acc) {
+    add_inplace_kernel<<<grid_for((long long)slab), 256, 0, st>>>(dh0_acc, w.dh_carry, (long long)slab);
+    KCHECK();
+  }
+  return MVAE_OK;
+}
+
+template <typename TA>
+int step_t(const MDims& d, const MWS& w, const float* const* P, float* const* G, const uint8_t* ids,
+           const int* lens, const float* eps, float* out_scalars, float* z_out, float* lv_out, float* y_out,
+           bool backward, cudaStream_t st) {
+  const int B = d.B, Bp = d.Bp, T = d.T, V = d.V, CP = d.CP, Z = d.Z, Hq = d.Hq, Hd = d.Hd, L = d.L, ML = d.MLP;
+  const int TB = T * Bp;
+  const int IN0 = V + Z;   // decoder layer-0 input width
+  // ---- control + weight preparation
+  RC(memset_async(w.err_flag, 4, st)); RC(memset_async(w.kl_sum, 8, st)); RC(memset_async(w.nll_sum, 8, st));
+  RC(memset_async(w.M, 4, st));
+  count_targets_kernel<<<1, 256, 0, st>>>(lens, B, w.M); KCHECK();
+  simt::pad_gate_matrix_kernel<TA><<<grid_for(3ll * Hq * Hq), 256, 0, st>>>(P[P_E_WHH], Hq, Hq, (TA*)w.Whh_enc, Hq, Hq, 0, 1, 2); KCHECK();
+  simt::pad_gate_vector_kernel<<<ceil_div(3 * Hq, 256), 256, 0, st>>>(P[P_E_BHH], Hq, w.bhh_enc, Hq); KCHECK();
+  for (int l = 0; l < L; ++l) {
+    simt::pad_gate_matrix_kernel<TA><<<grid_for(3ll * Hd * Hd), 256, 0, st>>>(P[P_WHH(l)], Hd, Hd, (TA*)w.Whh[l], Hd, Hd, 0, 1, 2); KCHECK();
+    simt::pad_gate_vector_kernel<<<ceil_div(3 * Hd, 256), 256, 0, st>>>(P[P_BHH(l)], Hd, w.bhh[l], Hd); KCHECK();
+    if (l >= 1) {
+      simt::pad_gate_matrix_kernel<TA><<<grid_for(3ll * Hd * Hd), 256, 0, st>>>(P[P_WIH(l)], Hd, Hd, (TA*)w.Wih[l], Hd, Hd, 0, 1, 2); KCHECK();
+      simt::pad_gate_matrix_kernel<TA><<<grid_for(3ll * Hd * Hd), 256, 0, st>>>(P[P_WIH(l)], Hd, Hd, (TA*)w.Wih_nrz[l], Hd, Hd, 2, 0, 1); KCHECK();
+      simt::pad_gate_vector_kernel<<<ceil_div(3 * Hd, 256), 256, 0, st>>>(P[P_BIH(l)], Hd, w.bih[l], Hd); KCHECK();
+    }
+  }
+  simt::pad_matrix_kernel<TA><<<grid_for((long long)CP * Hd), 256, 0, st>>>(P[P_FCW(L)], V, Hd, (TA*)w.Wfc, CP, Hd); KCHECK();
+  simt::pad_matrix_kernel<float><<<1, 64, 0, st>>>(P[P_FCB(L)], 1, V, w.bfc, 1, CP); KCHECK();
+
+  // ---- encoder: table look-up projection, GRU, final state, MLP heads, reparametrise + KL
+  RC(sg(st, P[P_EMB], V, 1, P[P_E_WIH], 1, V, w.TBLe, 3 * Hq, V, 3 * Hq, V, P[P_E_BIH], simt::ACT_NONE, 0));
+  gather_rows_kernel<TA><<<grid_for((long long)TB * 3 * Hq), 256, 0, st>>>(w.TBLe, 3 * Hq, ids, T, nullptr, B, Bp, T, (TA*)w.gi); KCHECK();
+  RC(memset_async(w.hlast, (size_t)Bp * Hq * 4, st));
+  RC(gru_fwd<TA>(d, w, st, (const TA*)w.gi, (const TA*)w.Whh_enc, w.bhh_enc, (TA*)w.hs_enc, (TA*)w.sv_enc, Hq, nullptr, lens, w.hlast));
+  RC(sg(st, w.hlast, Hq, 1, P[P_MU0W], 1, Hq, w.rmu, ML, B, ML, Hq, P[P_MU0B], simt::ACT_RELU, 0));
+  RC(sg(st, w.rmu, ML, 1, P[P_MU2W], 1, ML, w.mu, Z, B, Z, ML, P[P_MU2B], simt::ACT_NONE, 0));
+  RC(sg(st, w.hlast, Hq, 1, P[P_LV0W], 1, Hq, w.rlv, ML, B, ML, Hq, P[P_LV0B], simt::ACT_RELU, 0));
+  RC(sg(st, w.rlv, ML, 1, P[P_LV2W], 1, ML, w.lv, Z, B, Z, ML, P[P_LV2B], simt::ACT_NONE, 0));
+  reparam_kl_std_kernel<<<grid_for((long long)B * Z, 256, 592), 256, 0, st>>>(w.mu, w.lv, eps, (long long)B * Z, w.z, w.kl_sum); KCHECK();
+
+  // ---- decoder: h0, layer-0 projection = table + per-molecule z part, GRU stack, head
+  RC(memset_async(w.h0, (size_t)Bp * Hd * 4, st));
+  RC(sg(st, w.z, Z, 1, P[P_LATW(L)], 1, Z, w.h0, Hd, B, Hd, Z, P[P_LATB(L)], simt::ACT_NONE, 0));
+  RC(sg(st, P[P_EMB], V, 1, P[P_WIH(0)], 1, IN0, w.TBLd, 3 * Hd, V, 3 * Hd, V, nullptr, simt::ACT_NONE, 0));
+  RC(sg(st, w.z, Z, 1, P[P_WIH(0)] + V, 1, IN0, w.zproj, 3 * Hd, B, 3 * Hd, Z, P[P_BIH(0)], simt::ACT_NONE, 0));
+  gather_rows_kernel<TA><<<grid_for((long long)TB * 3 * Hd), 256, 0, st>>>(w.TBLd, 3 * Hd, ids, T, w.zproj, B, Bp, T, (TA*)w.gi); KCHECK();
+  for (int l = 0; l < L; ++l) {
+    if (l >= 1)
+      RC(gemm<TA>(w.err_flag, st, (const TA*)w.hs[l - 1] + (size_t)Bp * Hd, Hd, false, (const TA*)w.Wih[l], Hd, true, w.gi,
+                  3 * Hd, true, TB, 3 * Hd, Hd, w.bih[l], false, 1));
+    RC(gru_fwd<TA>(d, w, st, (const TA*)w.gi, (const TA*)w.Whh[l], w.bhh[l], (TA*)w.hs[l], (TA*)w.sv[l], Hd, w.h0, nullptr, nullptr));
+  }
+  RC(gemm<TA>(w.err_flag, st, (const TA*)w.hs[L - 1] + (size_t)Bp * Hd, Hd, false, (const TA*)w.Wfc, Hd, true, w.logits, CP, false,
+              TB, CP, Hd, w.bfc, false, 1, 64));
+  head_ce_kernel<TA><<<(unsigned)ceil_div64((long long)TB * 32, 256), 256, 0, st>>>(
+      w.logits, CP, V, ids, T, lens, B, Bp, T, w.M, d.rec_w, w.bfc, backward ? (TA*)w.dlogits : nullptr, y_out, w.nll_sum);
+  KCHECK();
+  finalize_kernel<<<1, 1, 0, st>>>(w.kl_sum, w.nll_sum, w.M, B, d.kl_w, d.rec_w, out_scalars); KCHECK();
+  if (z_out) { mvae_count_launches(1); MVAE_CUDA_CHECK(cudaMemcpyAsync(z_out, w.z, (size_t)B * Z * 4, cudaMemcpyDeviceToDevice, st)); }
+  if (lv_out) { mvae_count_launches(1); MVAE_CUDA_CHECK(cudaMemcpyAsync(lv_out, w.lv, (size_t)B * Z * 4, cudaMemcpyDeviceToDevice, st)); }
+  if (!backward) return MVAE_OK;
+
+  // =================================== backward ===================================
+  const TA* dlog = (const TA*)w.dlogits;
+  const int wsplits = d.bf16 ? 12 : 64;
+  onehot_rows_kernel<TA><<<grid_for((long long)TB * CP), 256, 0, st>>>(ids, T, B, Bp, T, CP, (TA*)w.OH); KCHECK();
+  // head
+  RC(gemm<TA>(w.err_flag, st, dlog, CP, false, (const TA*)w.Wfc, Hd, false, w.dX, Hd, true, TB, Hd, CP, nullptr, false, 1));
+  RC(memset_async(w.dWfc_p, (size_t)CP * Hd * 4, st));
+  RC(gemm<TA>(w.err_flag, st, dlog, CP, true, (const TA*)w.hs[L - 1] + (size_t)Bp * Hd, Hd, false, w.dWfc_p, Hd, false, CP, Hd, TB,
+              nullptr, true, d.bf16 ? 148 : 64, 256));
+  simt::unpad_matrix_kernel<<<grid_for((long long)V * Hd), 256, 0, st>>>(w.dWfc_p, Hd, G[P_FCW(L)], V, Hd); KCHECK();
+  RC(memset_async(w.csum, (size_t)4 * Hd * 4, st));
+  RC(simt::colsum<TA>(st, dlog, TB, CP, CP, w.csum)); mvae_count_launches(1);
+  simt::pad_matrix_kernel<float><<<1, 64, 0, st>>>(w.csum, 1, V, G[P_FCB(L)], 1, V); KCHECK();
+  // decoder GRU stack
+  RC(memset_async(w.dh0, (size_t)Bp * Hd * 4, st));
+  for (int l = L - 1; l >= 0; --l) {
+    const TA* hs = (const TA*)w.hs[l];
+    TA* dG = (TA*)w.dG;
+    RC(gru_bwd<TA>(d, w, st, (const TA*)w.Whh[l], hs, (const TA*)w.sv[l], (const TA*)w.dX, dG, Hd, w.dh0));
+    RC(memset_async(w.dW_p, (size_t)3 * Hd * Hd * 4, st));
+    RC(gemm<TA>(w.err_flag, st, dG + Hd, 4 * Hd, true, hs, Hd, false, w.dW_p, Hd, false, 3 * Hd, Hd, TB, nullptr, true, wsplits, 256));
+    simt::unpad_gate_matrix_kernel<<<grid_for(3ll * Hd * Hd), 256, 0, st>>>(w.dW_p, Hd, Hd, G[P_WHH(l)], Hd, Hd, 0, 1, 2); KCHECK();
+    RC(memset_async(w.csum, (size_t)4 * Hd * 4, st));
+    RC(simt::colsum<TA>(st, dG, TB, 4 * Hd, 4 * Hd, w.csum)); mvae_count_launches(1);
+    gate_bias_grads_kernel<<<ceil_div(3 * Hd, 256), 256, 0, st>>>(w.csum, Hd, G[P_BIH(l)], G[P_BHH(l)]); KCHECK();
+    if (l >= 1) {
+      const TA* X = (const TA*)w.hs[l - 1] + (size_t)Bp * Hd;
+      RC(memset_async(w.dW_p, (size_t)3 * Hd * Hd * 4, st));
+      RC(gemm<TA>(w.err_flag, st, dG, 4 * Hd, true, X, Hd, false, w.dW_p, Hd, false, 3 * Hd, Hd, TB, nullptr, true, wsplits, 256));
+      simt::unpad_gate_matrix_kernel<<<grid_for(3ll * Hd * Hd), 256, 0, st>>>(w.dW_p, Hd, Hd, G[P_WIH(l)], Hd, Hd, 2, 0, 1); KCHECK();
+      RC(gemm<TA>(w.err_flag, st, dG, 4 * Hd, false, (const TA*)w.Wih_nrz[l], Hd, false, w.dX, Hd, true, TB, Hd, 3 * Hd, nullptr, false, 1));
+    } else {
+      // layer 0: table gradient (tensor-core GEMM onehot^T * dgi) and the per-molecule z part (time sum)
+      RC(memset_async(w.dTBL, (size_t)CP * 3 * Hd * 4, st));
+      RC(gemm<TA>(w.err_flag, st, (const TA*)w.OH, CP, true, dG, 4 * Hd, false, w.dTBL, 3 * Hd, false, CP, 3 * Hd, TB, nullptr, true,
+                  d.bf16 ? 24 : 64, 256));
+      dgi_time_sum_t_kernel<TA><<<(unsigned)ceil_div64((long long)Bp * 3 * Hd, 256), 256, 0, st>>>(dG, T, Bp, Hd, w.dgisum); KCHECK();
+    }
+  }
+  // decoder layer-0 input weights: W_ih[:, :V] through the table, W_ih[:, V:] through z
+  tbl_grad_to_rzn_T_kernel<<<(unsigned)ceil_div64(3ll * Hd * V, 256), 256, 0, st>>>(w.dTBL, Hd, V, w.dWT); KCHECK();
+  //   dW_ih[:, :V] = dTBL_rzn^T(3Hd x V) * E (V x V)
+  RC(sg(st, w.dWT, V, 1, P[P_EMB], V, 1, G[P_WIH(0)], IN0, 3 * Hd, V, V, nullptr, simt::ACT_NONE, 0));
+  //   dE = dTBL_rzn (V x 3Hd) * W_ih[:, :V] (3Hd x V)
+  RC(sg(st, w.dWT, 1, V, P[P_WIH(0)], IN0, 1, G[P_EMB], V, V, V, 3 * Hd, nullptr, simt::ACT_NONE, 0));
+  //   dW_ih[:, V:] = dgisum^T * z ; dz = dgisum * W_ih[:, V:]
+  RC(sg_wgrad(st, w.dgisum, 1, 3 * Hd, w.z, Z, 1, G[P_WIH(0)] + V, IN0, 3 * Hd, Z, B));
+  RC(sg(st, w.dgisum, 3 * Hd, 1, P[P_WIH(0)] + V, IN0, 1, w.dz, Z, B, Z, 3 * Hd, nullptr, simt::ACT_NONE, 0));
+  // decoder_lat: h0 = z W^T + b, shared by all layers (dh0 already summed over layers)
+  RC(sg_wgrad(st, w.dh0, 1, Hd, w.z, Z, 1, G[P_LATW(L)], Z, Hd, Z, B));
+  RC(memset_async(G[P_LATB(L)], (size_t)Hd * 4, st));
+  RC(simt::colsum<float>(st, w.dh0, B, Hd, Hd, G[P_LATB(L)])); mvae_count_launches(1);
+  RC(sg(st, w.dh0, Hd, 1, P[P_LATW(L)], Z, 1, w.dz, Z, B, Z, Hd, nullptr, simt::ACT_NONE, 1));
+  // reparametrisation + KL
+  const long long nBZ = (long long)B * Z;
+  reparam_kl_std_bwd_kernel<<<grid_for(nBZ), 256, 0, st>>>(w.mu, w.lv, eps, w.dz, d.kl_w / (float)B, nBZ, w.dmu, w.dlv); KCHECK();
+  // MLP heads (mu then logvar), accumulating into dh_enc
+  for (int head = 0; head < 2; ++head) {
+    const float* dout = head == 0 ? w.dmu : w.dlv;
+    const float* r = head == 0 ? w.rmu : w.rlv;
+    const int W0 = head == 0 ? P_MU0W : P_LV0W, B0 = W0 + 1, W2 = W0 + 2, B2 = W0 + 3;
+    RC(sg_wgrad(st, dout, 1, Z, r, ML, 1, G[W2], ML, Z, ML, B));
+    RC(memset_async(G[B2], (size_t)Z * 4, st));
+    RC(simt::colsum<float>(st, dout, B, Z, Z, G[B2])); mvae_count_launches(1);
+    RC(sg(st, dout, Z, 1, P[W2], ML, 1, w.dr, ML, B, ML, Z, nullptr, simt::ACT_NONE, 0));
+    relu_bwd_kernel<<<grid_for((long long)B * ML), 256, 0, st>>>(r, w.dr, (long long)B * ML); KCHECK();
+    RC(sg_wgrad(st, w.dr, 1, ML, w.hlast, Hq, 1, G[W0], Hq, ML, Hq, B));
+    RC(memset_async(G[B0], (size_t)ML * 4, st));
+    RC(simt::colsum<float>(st, w.dr, B, ML, ML, G[B0])); mvae_count_launches(1);
+    RC(sg(st, w.dr, ML, 1, P[W0], Hq, 1, w.dhenc, Hq, B, Hq, ML, nullptr, simt::ACT_NONE, head));
+  }
+  // encoder GRU: the gradient enters only at each sequence's last step
+  {
+    TA* dXe = (TA*)w.dX;
+    TA* dG = (TA*)w.dG;
+    RC(memset_async(dXe, (size_t)TB * Hq * sizeof(TA), st));
+    scatter_final_grad_kernel<TA><<<(unsigned)ceil_div64((long long)B * Hq, 256), 256, 0, st>>>(w.dhenc, lens, B, Bp, Hq, dXe); KCHECK();
+    RC(gru_bwd<TA>(d, w, st, (const TA*)w.Whh_enc, (const TA*)w.hs_enc, (const TA*)w.sv_enc, dXe, dG, Hq, nullptr));
+    RC(memset_async(w.dW_p, (size_t)3 * Hq * Hq * 4, st));
+    RC(gemm<TA>(w.err_flag, st, dG + Hq, 4 * Hq, true, (const TA*)w.hs_enc, Hq, false, w.dW_p, Hq, false, 3 * Hq, Hq, TB, nullptr, true,
+                wsplits, 256));
+    simt::unpad_gate_matrix_kernel<<<grid_for(3ll * Hq * Hq), 256, 0, st>>>(w.dW_p, Hq, Hq, G[P_E_WHH], Hq, Hq, 0, 1, 2); KCHECK();
+    RC(memset_async(w.csum, (size_t)4 * Hd * 4, st));
+    RC(simt::colsum<TA>(st, dG, TB, 4 * Hq, 4 * Hq, w.csum)); mvae_count_launches(1);
+    gate_bias_grads_kernel<<<ceil_div(3 * Hq, 256), 256, 0, st>>>(w.csum, Hq, G[P_E_BIH], G[P_E_BHH]); KCHECK();
+    RC(memset_async(w.dTBL, (size_t)CP * 3 * Hd * 4, st));
+    RC(gemm<TA>(w.err_flag, st, (const TA*)w.OH, CP, true, dG, 4 * Hq, false, w.dTBL, 3 * Hq, false, CP, 3 * Hq, TB, nullptr, true,
+                d.bf16 ? 24 : 64, 256));
+    tbl_grad_to_rzn_T_kernel<<<(unsigned)ceil_div64(3ll * Hq * V, 256), 256, 0, st>>>(w.dTBL, Hq, V, w.dWT); KCHECK();
+    RC(sg(st, w.dWT, V, 1, P[P_EMB], V, 1, G[P_E_WIH], V, 3 * Hq, V, V, nullptr, simt::ACT_NONE, 0));
+    RC(sg(st, w.dWT, 1, V, P[P_E_WIH], V, 1, G[P_EMB], V, V, V, 3 * Hq, nullptr, simt::ACT_NONE, 1));   // accumulate onto the decoder part
+  }
+  if (d.pad >= 0 && d.pad < V) {   // nn.Embedding(padding_idx = pad): the pad row receives no gradient
+    zero_row_kernel<<<1, 64, 0, st>>>(G[P_EMB], d.pad, V); KCHECK();
+  }
+  return MVAE_OK;
+}
+
+int check_ws(const mvae_moses_desc* desc, void* ws, size_t ws_bytes, MDims* d, MWS* w) {
+  RC(make_dims(desc, d));
+  if (!ws || (reinterpret_cast<uintptr_t>(ws) & 255)) return MVAE_ERR_INVALID;
+  carve(*d, ws, w);
+  if (ws_bytes < w->total) return MVAE_ERR_WORKSPACE;
+  return MVAE_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+size_t mvae_moses_workspace_bytes(const mvae_moses_desc* desc) {
+  MDims d; MWS w;
+  if (make_dims(desc, &d) != MVAE_OK) return 0;
+  carve(d, nullptr, &w);
+  return w.total;
+}
+
+int mvae_moses_step(const mvae_moses_desc* desc, const float* const* params, float* const* grads, const uint8_t* ids,
+                    const int32_t* lengths, const float* eps, float* out_scalars, float* z_out, float* logvar_out,
+                    float* y_out, void* workspace, size_t workspace_bytes, mvae_stream_t stream) {
+  MDims d; MWS w;
+  RC(check_ws(desc, workspace, workspace_bytes, &d, &w));
+  if (!params || !ids || !lengths || !eps || !out_scalars) return MVAE_ERR_INVALID;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const bool backward = grads != nullptr;
+  return d.bf16 ? step_t<__nv_bfloat16>(d, w, params, grads, ids, lengths, eps, out_scalars, z_out, logvar_out, y_out, backward, st)
+                : step_t<float>(d, w, params, grads, ids, lengths, eps, out_scalars, z_out, logvar_out, y_out, backward, st);
+}
+
+int mvae_moses_read_error(const mvae_moses_desc* desc, void* workspace, size_t workspace_bytes, int* flag,
+                          mvae_stream_t stream) {
+  MDims d; MWS w;
+  RC(check_ws(desc, workspace, workspace_bytes, &d, &w));
+  if (!flag) return MVAE_ERR_INVALID;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  MVAE_CUDA_CHECK(cudaMemcpyAsync(flag, w.err_flag, 4, cudaMemcpyDeviceToHost, st));
+  MVAE_CUDA_CHECK(cudaStreamSynchronize(st));
+  return MVAE_OK;
+}
+
+}  // extern "C"

@@ -6,6 +6,7 @@
 #include "common.cuh"
 
 namespace simt {
+namespace {   // internal linkage: this header is included by several translation units
 
 constexpr float SELU_ALPHA = 1.6732632423543772848170429916717f;
 constexpr float SELU_SCALE = 1.0507009873554804934193349852946f;
@@ -449,7 +450,8 @@ template <typename TA, typename TG>
 __global__ void gru_gate_fwd_kernel(const TG* __restrict__ gi, const float* __restrict__ gh,
                                     const float* __restrict__ hprev32, const TA* __restrict__ hprevA,
                                     TA* __restrict__ hnextA, float* __restrict__ hnext32, TA* __restrict__ sv, int Bp,
-                                    int Hp) {
+                                    int Hp, const int* __restrict__ lens = nullptr, float* __restrict__ hlast = nullptr,
+                                    int t = 0, int B = 0) {
   const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (idx >= (long long)Bp * Hp) return;
   const int b = (int)(idx / Hp), j = (int)(idx - (long long)b * Hp);
@@ -463,6 +465,8 @@ __global__ void gru_gate_fwd_kernel(const TG* __restrict__ gi, const float* __re
   const float h = fmaf(z, hp - n, n);  // (1-z) n + z h
   hnextA[idx] = from_f32<TA>(h);
   if (hnext32) hnext32[idx] = h;
+  // packed-sequence final state (mosesvae.py:153-156): sequence b ends after lens[b] steps
+  if (lens && b < B && t + 1 == lens[b]) hlast[idx] = h;
   if (sv) {
     const long long s4 = (long long)b * 4 * Hp + j;
     sv[s4] = from_f32<TA>(r);
@@ -652,4 +656,5 @@ __global__ void finalize_scalars_kernel(const double* __restrict__ bce_sum, cons
   }
 }
 
+}  // namespace
 }  // namespace simt

@@ -1,0 +1,161 @@
+"""Drop-in for the reference's mosesvae.py `VAE` (mosesvae.py:27-199) running on the B200 kernels.
+
+Same constructor (`VAE(vocab)` with the vocab duck-type of vocab.py:10-87), same submodules and ModuleList groupings
+(`encoder`, `decoder`, `vae` -> identical `state_dict()` keys incl. the aliases, and `model.encoder.parameters()` /
+`model.decoder.parameters()` feed separate optimisers as in moses_train_distrib_logp.py:267-268), same
+`forward(list[LongTensor]) -> (kl, recon, z, logvar, x_padded, y)`, `string2tensor` / `tensor2string`.
+`elbo_step()` is the fused fast path.  Not ported this round: `sample()` (mosesvae.py:214-262) and train-mode
+dropout between decoder layers (the step treats dropout as the identity, i.e. the reference in eval()).
+"""
+import ctypes
+
+import torch
+from torch import nn
+
+from . import _lib
+from ._lib import MosesDesc, check, lib
+from .engine import _p, _ptr_table, _stream
+
+
+def moses_param_order(d_layers=3):
+    keys = ["x_emb.weight", "encoder_rnn.weight_ih_l0", "encoder_rnn.weight_hh_l0", "encoder_rnn.bias_ih_l0",
+            "encoder_rnn.bias_hh_l0", "q_mu.0.weight", "q_mu.0.bias", "q_mu.2.weight", "q_mu.2.bias",
+            "q_logvar.0.weight", "q_logvar.0.bias", "q_logvar.2.weight", "q_logvar.2.bias"]
+    for l in range(d_layers):
+        keys += [f"decoder_rnn.weight_ih_l{l}", f"decoder_rnn.weight_hh_l{l}", f"decoder_rnn.bias_ih_l{l}",
+                 f"decoder_rnn.bias_hh_l{l}"]
+    return keys + ["decoder_lat.weight", "decoder_lat.bias", "decoder_fc.weight", "decoder_fc.bias"]
+
+
+class _MosesFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, model, ids, lens, eps, *params):
+        kl, recon, z, logvar, y = model._run(list(params), None, ids, lens, eps, 1.0, 1.0, want_y=True)
+        ctx.model, ctx.ids, ctx.lens, ctx.eps = model, ids, lens, eps
+        ctx.save_for_backward(*params)
+        ctx.mark_non_differentiable(z, logvar, y)
+        return kl, recon, z, logvar, y
+
+    @staticmethod
+    def backward(ctx, dkl, drecon, dz, dlv, dy):
+        params = list(ctx.saved_tensors)
+        grads = [torch.empty_like(p) for p in params]
+        klw = float(dkl) if dkl is not None else 0.0
+        rw = float(drecon) if drecon is not None else 0.0
+        ctx.model._run(params, grads, ctx.ids, ctx.lens, ctx.eps, klw, rw, want_y=False)
+        return (None, None, None, None, *grads)
+
+
+class VAE(nn.Module):
+    def __init__(self, vocab, precision="bf16"):
+        super().__init__()
+        q_d_h, q_n_layers, d_n_layers, d_dropout, d_z, d_d_h = 256, 1, 3, 0.2, 160, 512
+        self.vocabulary = vocab
+        for ss in ("bos", "eos", "unk", "pad"):
+            setattr(self, ss, getattr(vocab, ss))
+        n_vocab, d_emb = len(vocab), vocab.vectors.size(1)
+        self.x_emb = nn.Embedding(n_vocab, d_emb, self.pad)
+        self.x_emb.weight.data.copy_(vocab.vectors)
+        self.encoder_rnn = nn.GRU(d_emb, q_d_h, num_layers=q_n_layers, batch_first=True, dropout=0, bidirectional=False)
+        self.q_mu = nn.Sequential(nn.Linear(q_d_h, 256), nn.ReLU(), nn.Linear(256, d_z))
+        self.q_logvar = nn.Sequential(nn.Linear(q_d_h, 256), nn.ReLU(), nn.Linear(256, d_z))
+        self.decoder_rnn = nn.GRU(d_emb + d_z, d_d_h, num_layers=d_n_layers, batch_first=True, dropout=d_dropout)
+        self.decoder_lat = nn.Linear(d_z, d_d_h)
+        self.decoder_fc = nn.Linear(d_d_h, n_vocab)
+        self.encoder = nn.ModuleList([self.x_emb, self.encoder_rnn, self.q_mu, self.q_logvar])
+        self.decoder = nn.ModuleList([self.decoder_rnn, self.decoder_lat, self.decoder_fc])
+        self.vae = nn.ModuleList([self.x_emb, self.encoder, self.decoder])
+        self.precision = precision
+        self.cfg = dict(vocab=n_vocab, d_z=d_z, q_hidden=q_d_h, d_hidden=d_d_h, d_layers=d_n_layers, mlp_hidden=256)
+        self._keys = moses_param_order(d_n_layers)
+        self._ws = None
+        self.eps_override = None
+
+    @property
+    def device(self):
+        return next(self.parameters()).device
+
+    def string2tensor(self, string, device="model"):
+        ids = self.vocabulary.string2ids(string, add_bos=True, add_eos=True)
+        return torch.tensor(ids, dtype=torch.long, device=self.device if device == "model" else device)
+
+    def tensor2string(self, tensor):
+        return self.vocabulary.ids2string(tensor.tolist(), rem_bos=True, rem_eos=True)
+
+    def ordered_params(self):
+        named = dict(self.named_parameters())
+        return [named[k] for k in self._keys]
+
+    # -- plumbing ------------------------------------------------------------------------------------
+    def _pack(self, x):
+        """list of id tensors (sorted by length desc, as pack_sequence requires) -> u8 (B,T) padded, int32 lengths"""
+        lens = [int(t.numel()) for t in x]
+        if any(lens[i] < lens[i + 1] for i in range(len(lens) - 1)):
+            raise RuntimeError("sequences must be sorted by length in decreasing order (pack_sequence contract)")
+        padded = nn.utils.rnn.pad_sequence(x, batch_first=True, padding_value=self.pad)
+        dev = self.device
+        return (padded.to(dev), padded.to(device=dev, dtype=torch.uint8).contiguous(),
+                torch.tensor(lens, dtype=torch.int32, device=dev))
+
+    def _run(self, params, grads, ids, lens, eps, kl_weight, recon_weight, want_y):
+        if not torch.cuda.is_available():
+            raise _lib.MvaeError("molecular-vae_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        B, T = ids.shape
+        c = self.cfg
+        prec = {"fp32": _lib.PREC_FP32, "bf16": _lib.PREC_BF16}[self.precision]
+        d = MosesDesc(B, T, c["vocab"], c["d_z"], c["q_hidden"], c["d_hidden"], c["d_layers"], c["mlp_hidden"],
+                      int(self.pad), prec, float(kl_weight), float(recon_weight))
+        need = lib.mvae_moses_workspace_bytes(ctypes.byref(d))
+        if need == 0:
+            raise ValueError("invalid MOSES VAE description")
+        dev = ids.device
+        if self._ws is None or self._ws.numel() < need + 256 or self._ws.device != dev:
+            self._ws = torch.empty(need + 256, dtype=torch.uint8, device=dev)
+        wsp = ctypes.c_void_p(self._ws.data_ptr() + (-self._ws.data_ptr()) % 256)
+        out = torch.zeros(4, dtype=torch.float32, device=dev)
+        z = torch.empty(B, c["d_z"], dtype=torch.float32, device=dev)
+        lv = torch.empty_like(z)
+        y = torch.empty(B, T, c["vocab"], dtype=torch.float32, device=dev) if want_y else None
+        P = _ptr_table(params)
+        G = _ptr_table(grads) if grads is not None else None
+        with torch.cuda.device(dev):
+            check(lib.mvae_moses_step(ctypes.byref(d), P, G, _p(ids), _p(lens), _p(eps), _p(out), _p(z), _p(lv), _p(y),
+                                      wsp, need, _stream()))
+        self._last_desc = (d, wsp, need)
+        self._last_scalars = out
+        return out[1], out[2], z, lv, y
+
+    def check_device_error(self):
+        d, wsp, need = self._last_desc
+        flag = ctypes.c_int(0)
+        check(lib.mvae_moses_read_error(ctypes.byref(d), wsp, need, ctypes.byref(flag), _stream()))
+        if flag.value:
+            raise _lib.MvaeError("tcgen05 pipeline watchdog fired (device-side error flag set)")
+
+    def _eps(self, B, dev):
+        if self.eps_override is not None:
+            return self.eps_override.to(device=dev, dtype=torch.float32).contiguous()
+        return torch.randn(B, self.cfg["d_z"], device=dev, dtype=torch.float32)
+
+    # -- reference API (mosesvae.py:126-140) ------------------------------------------------------------
+    def forward(self, x):
+        x_pad, ids, lens = self._pack(x)
+        eps = self._eps(ids.shape[0], ids.device)
+        params = [p if p.is_contiguous() else p.contiguous() for p in self.ordered_params()]
+        kl, recon, z, logvar, y = _MosesFunction.apply(self, ids, lens, eps, *params)
+        return kl, recon, z, logvar, x_pad, y
+
+    def elbo_step(self, x, kl_weight=1.0, recon_weight=1.0, eps=None):
+        """Fused forward + backward of kl_weight*kl + recon_weight*recon: fills p.grad and returns the device tensor
+        [loss, kl, recon, n_targets]."""
+        _, ids, lens = self._pack(x)
+        eps = self._eps(ids.shape[0], ids.device) if eps is None else eps.to(ids.device, torch.float32).contiguous()
+        params = self.ordered_params()
+        for p in params:
+            if p.grad is None:
+                p.grad = torch.empty_like(p)
+        self._run([p.data for p in params], [p.grad for p in params], ids, lens, eps, kl_weight, recon_weight, False)
+        return self._last_scalars
+
+    def sample(self, n_batch, max_len=100, z=None, temp=1.0):
+        raise NotImplementedError("VAE.sample (mosesvae.py:214-262) is not ported to the B200 path yet")

@@ -1,0 +1,95 @@
+"""GPU parity of the MOSES VAE step (molecular-vae_b200/mosesvae.py -> mvae_moses_step) against the float64 oracle
+(oracle/moses_oracle.py, itself pinned to the reference's mosesvae.py by tests/golden/moses_*.npz)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import moses_oracle as mo
+from tests.util_gpu import load_pkg, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+class _Vocab:   # the reference's vocab duck-type (vocab.py:10-87), V = 30 chars + 4 specials
+    def __init__(self, n_chars=30):
+        self.chars = [chr(ord("A") + i) for i in range(n_chars)]
+        self.c2i = {c: i for i, c in enumerate(self.chars)}
+        self.bos, self.eos, self.pad, self.unk = n_chars, n_chars + 1, n_chars + 2, n_chars + 3
+        self.vectors = torch.eye(n_chars + 4)
+
+    def __len__(self):
+        return len(self.chars) + 4
+
+    def string2ids(self, s, add_bos=False, add_eos=False):
+        ids = [self.c2i.get(c, self.unk) for c in s]
+        return ([self.bos] if add_bos else []) + ids + ([self.eos] if add_eos else [])
+
+    def ids2string(self, ids, rem_bos=True, rem_eos=True):
+        if ids and rem_bos and ids[0] == self.bos:
+            ids = ids[1:]
+        if ids and rem_eos and ids[-1] == self.eos:
+            ids = ids[:-1]
+        return "".join(self.chars[i] if i < len(self.chars) else "?" for i in ids)
+
+
+def _setup(m, precision, pseed, bseed, B):
+    P = mo.make_moses_params(pseed, dtype=np.float32)
+    seqs, eps, pad = mo.make_moses_batch(bseed, B, dtype=np.float32)
+    model = m.mosesvae.VAE(_Vocab(), precision=precision)
+    sd = model.state_dict()
+    with torch.no_grad():
+        for k, v in P.items():
+            sd[k].copy_(torch.from_numpy(v))
+    model = model.cuda()
+    assert model.pad == pad
+    return P, seqs, eps, pad, model
+
+
+@pytest.mark.parametrize("precision,B,ltol,gtol", [("fp32", 6, 2e-5, 3e-5), ("fp32", 70, 2e-5, 3e-5),
+                                                   ("bf16", 64, 2e-3, 2e-2), ("bf16", 300, 2e-3, 2e-2)])
+def test_moses_fused_step(precision, B, ltol, gtol):
+    m = load_pkg()
+    klw = 0.1
+    P, seqs, eps, pad, model = _setup(m, precision, 311, 411 + B, B)
+    ref = mo.moses_step({k: v.astype(np.float64) for k, v in P.items()}, seqs, eps.astype(np.float64), pad, kl_weight=klw)
+    x = [torch.from_numpy(s).cuda() for s in seqs]
+    out = model.elbo_step(x, kl_weight=klw, eps=torch.from_numpy(eps).cuda())
+    torch.cuda.synchronize()
+    model.check_device_error()
+    sc = out.cpu().numpy()
+    assert abs(sc[1] - ref["kl"]) <= ltol * abs(ref["kl"]), (sc, ref["kl"])
+    assert abs(sc[2] - ref["recon"]) <= ltol * abs(ref["recon"]), (sc, ref["recon"])
+    assert int(sc[3]) == ref["M"]
+    bad = {}
+    for k, p in model.named_parameters():
+        if k not in ref["grads"]:
+            continue
+        e = rel_l2(p.grad.cpu().numpy(), ref["grads"][k])
+        if not e <= gtol:
+            bad[k] = e
+    assert not bad, bad
+
+
+def test_moses_dropin_forward_backward_and_state_dict():
+    m = load_pkg()
+    P, seqs, eps, pad, model = _setup(m, "fp32", 312, 412, 5)
+    keys = set(model.state_dict().keys())
+    for k in ("x_emb.weight", "encoder.1.weight_hh_l0", "decoder.0.weight_ih_l0", "vae.1.2.0.weight", "vae.2.2.bias"):
+        assert k in keys                                   # ModuleList aliases of mosesvae.py:90-105
+    assert len(list(model.encoder.parameters())) == 13 and len(list(model.decoder.parameters())) == 16
+    ref = mo.moses_step({k: v.astype(np.float64) for k, v in P.items()}, seqs, eps.astype(np.float64), pad, kl_weight=0.25)
+    model.eval()
+    model.eps_override = torch.from_numpy(eps)
+    kl, recon, z, logvar, x_pad, y = model([torch.from_numpy(s).cuda() for s in seqs])
+    assert y.shape == ref["y"].shape and x_pad.shape == ref["x"].shape
+    np.testing.assert_allclose(y.detach().cpu().numpy(), ref["y"], rtol=2e-4, atol=2e-5)
+    np.testing.assert_allclose(z.cpu().numpy(), ref["z"], rtol=1e-4, atol=1e-5)
+    loss = 0.25 * kl + recon
+    loss.backward()
+    torch.cuda.synchronize()
+    assert abs(float(loss.detach()) - ref["loss"]) <= 2e-5 * abs(ref["loss"])
+    bad = {k: rel_l2(p.grad.cpu().numpy(), ref["grads"][k]) for k, p in model.named_parameters()
+           if k in ref["grads"] and rel_l2(p.grad.cpu().numpy(), ref["grads"][k]) > 3e-5}
+    assert not bad, bad
+    with pytest.raises(RuntimeError):
+        model([torch.from_numpy(s).cuda() for s in seqs[::-1]])       # not length-sorted
