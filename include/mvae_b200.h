@@ -141,6 +141,14 @@ size_t mvae_moses_workspace_bytes(const mvae_moses_desc* d);
 int mvae_moses_step(const mvae_moses_desc* d, const float* const* params, float* const* grads, const uint8_t* ids,
                     const int32_t* lengths, const float* eps, float* out_scalars, float* z_out, float* logvar_out,
                     float* y_out, void* workspace, size_t workspace_bytes, mvae_stream_t stream);
+/* VAE.sample (mosesvae.py:214-262; hugesample.py:28): autoregressive decode of B latents z fp32 (B,d_z) for
+ * max_len-1 steps (desc->max_len = the sampler's max_len, 100 in the reference).  mode 0 = greedy argmax (ties ->
+ * lowest id; the bit-exact parity mode), mode 1 = multinomial over softmax(y/temp) with a counter-based generator
+ * (seed, sequence, step).  ids_out u8 (B,max_len): bos, generated ids up to and including eos, pad after;
+ * lengths_out int32 (B) = the reference's end_pads (eos index + 1, or max_len).  All rows run every step.          */
+int mvae_moses_sample(const mvae_moses_desc* d, const float* const* params, const float* z, int bos_id, int eos_id,
+                      int mode, float temp, unsigned long long seed, uint8_t* ids_out, int32_t* lengths_out,
+                      void* workspace, size_t workspace_bytes, mvae_stream_t stream);
 int mvae_moses_read_error(const mvae_moses_desc* d, void* workspace, size_t workspace_bytes, int* flag,
                           mvae_stream_t stream);
 

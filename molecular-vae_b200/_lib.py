@@ -59,6 +59,8 @@ def _load():
         "mvae_cfgb_read_error": (i32, [dp, vp, ctypes.c_size_t, ctypes.POINTER(i32), vp]),
         "mvae_moses_workspace_bytes": (ctypes.c_size_t, [ctypes.POINTER(MosesDesc)]),
         "mvae_moses_step": (i32, [ctypes.POINTER(MosesDesc), pp, pp, vp, vp, vp, vp, vp, vp, vp, vp, ctypes.c_size_t, vp]),
+        "mvae_moses_sample": (i32, [ctypes.POINTER(MosesDesc), pp, vp, i32, i32, i32, ctypes.c_float, ctypes.c_ulonglong, vp, vp,
+                                    vp, ctypes.c_size_t, vp]),
         "mvae_moses_read_error": (i32, [ctypes.POINTER(MosesDesc), vp, ctypes.c_size_t, ctypes.POINTER(i32), vp]),
         "mvae_clip_grad_norm": (i32, [vp, ll, ctypes.c_float, vp, vp, i32, vp]),
         "mvae_adam_step": (i32, [vp, vp, vp, vp, ll] + [ctypes.c_float] * 5 + [i32, vp, vp]),
@@ -80,7 +82,7 @@ EXPORTED = [
     "mvae_graph_num_kernel_nodes", "mvae_graph_destroy", "mvae_cfgb_forward", "mvae_cfgb_backward",
     "mvae_cfgb_decode_greedy", "mvae_onehot_to_ids", "mvae_cfgb_read_error", "mvae_gemm_bf16", "mvae_sgemm",
     "mvae_clip_grad_norm", "mvae_adam_step", "mvae_sgd_momentum_step",
-    "mvae_moses_workspace_bytes", "mvae_moses_step", "mvae_moses_read_error",
+    "mvae_moses_workspace_bytes", "mvae_moses_step", "mvae_moses_sample", "mvae_moses_read_error",
 ]
 
 

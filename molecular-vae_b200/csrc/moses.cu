@@ -549,6 +549,125 @@ int step_t(const MDims& d, const MWS& w, const float* const* P, float* const* G,
   return MVAE_OK;
 }
 
+// one decode step of VAE.sample (mosesvae.py:243-255): y/temp -> argmax (greedy) or inverse-CDF draw (multinomial) ->
+// masked write + EOS bookkeeping.  One warp per sequence; logits row = [CP] fp32.
+__device__ __forceinline__ float u01_hash(unsigned long long seed, unsigned int b, unsigned int i) {
+  unsigned long long x = seed + 0x9E3779B97F4A7C15ull * ((unsigned long long)b * 1000003ull + i + 1);
+  x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ull; x ^= x >> 27; x *= 0x94D049BB133111EBull; x ^= x >> 31;
+  return (float)((x >> 40) + 0.5) * (1.0f / 16777216.0f);
+}
+__global__ void sample_step_kernel(const float* __restrict__ logits, int CP, int V, int B, int step, int max_len,
+                                   int eos, int mode, float inv_temp, unsigned long long seed,
+                                   uint8_t* __restrict__ w_cur, uint8_t* __restrict__ x, int* __restrict__ end,
+                                   uint8_t* __restrict__ done) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= B) return;
+  const int b = warp;
+  const float a0 = lane < V ? logits[(long long)b * CP + lane] * inv_temp : -INFINITY;
+  const float a1 = (lane + 32) < V ? logits[(long long)b * CP + lane + 32] * inv_temp : -INFINITY;
+  float m = fmaxf(a0, a1);
+  int arg = a0 >= a1 ? lane : lane + 32;
+  for (int o = 16; o; o >>= 1) {
+    const float om = __shfl_xor_sync(0xffffffffu, m, o);
+    const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+    if (om > m || (om == m && oa < arg)) { m = om; arg = oa; }
+  }
+  int tok = arg;
+  if (mode == 1) {
+    const float e0 = lane < V ? expf(a0 - m) : 0.f, e1 = (lane + 32) < V ? expf(a1 - m) : 0.f;
+    // inclusive prefix sums over the 64 candidate ids (ids 0..31 in e0, 32..63 in e1)
+    float c0 = e0, c1 = e1;
+    for (int o = 1; o < 32; o <<= 1) {
+      const float t0 = __shfl_up_sync(0xffffffffu, c0, o), t1 = __shfl_up_sync(0xffffffffu, c1, o);
+      if (lane >= o) { c0 += t0; c1 += t1; }
+    }
+    const float tot0 = __shfl_sync(0xffffffffu, c0, 31), tot1 = __shfl_sync(0xffffffffu, c1, 31);
+    const float u = u01_hash(seed, (unsigned)b, (unsigned)step) * (tot0 + tot1);
+    // first id whose cumulative mass exceeds u
+    const unsigned m0 = __ballot_sync(0xffffffffu, c0 > u);
+    const unsigned m1 = __ballot_sync(0xffffffffu, tot0 + c1 > u);
+    tok = m0 ? (__ffs(m0) - 1) : (m1 ? 32 + __ffs(m1) - 1 : arg);
+    if (tok >= V) tok = arg;
+  }
+  if (lane == 0) {
+    w_cur[b] = (uint8_t)tok;
+    if (!done[b]) {
+      x[(long long)b * max_len + step] = (uint8_t)tok;
+      if (tok == eos) { end[b] = step + 1; done[b] = 1; }
+    }
+  }
+}
+__global__ void sample_init_kernel(int B, int max_len, int bos, int pad, uint8_t* __restrict__ w_cur,
+                                   uint8_t* __restrict__ x, int* __restrict__ end, uint8_t* __restrict__ done) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i < (long long)B * max_len) x[i] = (i % max_len == 0) ? (uint8_t)bos : (uint8_t)pad;
+  if (i < B) { w_cur[i] = (uint8_t)bos; end[i] = max_len; done[i] = 0; }
+}
+
+template <typename TA>
+int sample_t(const MDims& d, const MWS& w, const float* const* P, const float* z, int bos, int eos, int mode, float temp,
+             unsigned long long seed, uint8_t* ids_out, int* len_out, uint8_t* w_cur, uint8_t* done, cudaStream_t st) {
+  const int B = d.B, Bp = d.Bp, V = d.V, CP = d.CP, Z = d.Z, Hd = d.Hd, L = d.L, max_len = d.T;
+  const int IN0 = V + Z;
+  const size_t slab = (size_t)Bp * Hd;
+  RC(memset_async(w.err_flag, 4, st));
+  for (int l = 0; l < L; ++l) {
+    simt::pad_gate_matrix_kernel<TA><<<grid_for(3ll * Hd * Hd), 256, 0, st>>>(P[P_WHH(l)], Hd, Hd, (TA*)w.Whh[l], Hd, Hd, 0, 1, 2); KCHECK();
+    simt::pad_gate_vector_kernel<<<ceil_div(3 * Hd, 256), 256, 0, st>>>(P[P_BHH(l)], Hd, w.bhh[l], Hd); KCHECK();
+    if (l >= 1) {
+      simt::pad_gate_matrix_kernel<TA><<<grid_for(3ll * Hd * Hd), 256, 0, st>>>(P[P_WIH(l)], Hd, Hd, (TA*)w.Wih[l], Hd, Hd, 0, 1, 2); KCHECK();
+      simt::pad_gate_vector_kernel<<<ceil_div(3 * Hd, 256), 256, 0, st>>>(P[P_BIH(l)], Hd, w.bih[l], Hd); KCHECK();
+    }
+  }
+  simt::pad_matrix_kernel<TA><<<grid_for((long long)CP * Hd), 256, 0, st>>>(P[P_FCW(L)], V, Hd, (TA*)w.Wfc, CP, Hd); KCHECK();
+  simt::pad_matrix_kernel<float><<<1, 64, 0, st>>>(P[P_FCB(L)], 1, V, w.bfc, 1, CP); KCHECK();
+  // h0 (mosesvae.py:229-230), token table and the per-sequence z part of the layer-0 projection
+  RC(memset_async(w.h0, (size_t)Bp * Hd * 4, st));
+  RC(sg(st, z, Z, 1, P[P_LATW(L)], 1, Z, w.h0, Hd, B, Hd, Z, P[P_LATB(L)], simt::ACT_NONE, 0));
+  RC(sg(st, P[P_EMB], V, 1, P[P_WIH(0)], 1, IN0, w.TBLd, 3 * Hd, V, 3 * Hd, V, nullptr, simt::ACT_NONE, 0));
+  RC(sg(st, z, Z, 1, P[P_WIH(0)] + V, 1, IN0, w.zproj, 3 * Hd, B, 3 * Hd, Z, P[P_BIH(0)], simt::ACT_NONE, 0));
+  // per layer two hidden-state slabs (ping-pong by step parity): hs[l] slab (step & 1) holds h before the step
+  for (int l = 0; l < L; ++l) {
+    init_h0_kernel<TA><<<ceil_div((int)slab, 256), 256, 0, st>>>(w.h0, B, Bp, Hd, (TA*)w.hs[l] + slab, nullptr); KCHECK();
+  }
+  // fp32 master states: reuse the saved-gate buffers (not needed when sampling): sv[l] holds 2 fp32 slabs
+  float* h32[4][2];
+  for (int l = 0; l < L; ++l) {
+    h32[l][0] = reinterpret_cast<float*>(w.sv[l]);
+    h32[l][1] = h32[l][0] + slab;
+    if (d.bf16) { init_h0_kernel<float><<<ceil_div((int)slab, 256), 256, 0, st>>>(w.h0, B, Bp, Hd, h32[l][1], nullptr); KCHECK(); }
+  }
+  sample_init_kernel<<<(unsigned)ceil_div64((long long)B * max_len, 256), 256, 0, st>>>(B, max_len, bos, d.pad, w_cur, ids_out, len_out, done); KCHECK();
+  const int gate_grid = ceil_div((int)slab, 256);
+  TA* gi0 = (TA*)w.gi;                       // [Bp][3Hd]
+  TA* gi1 = gi0 + (size_t)Bp * 3 * Hd;       // projection of the lower layer's new state
+  for (int i = 1; i < max_len; ++i) {
+    const int cur = i & 1, nxt = cur ^ 1;
+    gather_rows_kernel<TA><<<grid_for((long long)Bp * 3 * Hd), 256, 0, st>>>(w.TBLd, 3 * Hd, w_cur, 1, w.zproj, B, Bp, 1, gi0); KCHECK();
+    for (int l = 0; l < L; ++l) {
+      TA* hcur = (TA*)w.hs[l] + cur * slab;
+      TA* hnxt = (TA*)w.hs[l] + nxt * slab;
+      const TA* gi = gi0;
+      if (l >= 1) {
+        RC(gemm<TA>(w.err_flag, st, (const TA*)w.hs[l - 1] + nxt * slab, Hd, false, (const TA*)w.Wih[l], Hd, true, gi1, 3 * Hd, true,
+                    Bp, 3 * Hd, Hd, w.bih[l], false, 1));
+        gi = gi1;
+      }
+      RC(gemm<TA>(w.err_flag, st, hcur, Hd, false, (const TA*)w.Whh[l], Hd, true, w.gh, 3 * Hd, false, Bp, 3 * Hd, Hd, w.bhh[l], false, 1));
+      simt::gru_gate_fwd_kernel<TA, TA><<<gate_grid, 256, 0, st>>>(gi, w.gh, d.bf16 ? h32[l][cur] : nullptr, hcur, hnxt,
+                                                                   d.bf16 ? h32[l][nxt] : nullptr, nullptr, Bp, Hd);
+      KCHECK();
+    }
+    RC(gemm<TA>(w.err_flag, st, (const TA*)w.hs[L - 1] + nxt * slab, Hd, false, (const TA*)w.Wfc, Hd, true, w.logits, CP, false, Bp, CP, Hd,
+                w.bfc, false, 1, 64));
+    sample_step_kernel<<<ceil_div(B * 32, 256), 256, 0, st>>>(w.logits, CP, V, B, i, max_len, eos, mode, 1.0f / temp, seed, w_cur,
+                                                              ids_out, len_out, done);
+    KCHECK();
+  }
+  return MVAE_OK;
+}
+
 int check_ws(const mvae_moses_desc* desc, void* ws, size_t ws_bytes, MDims* d, MWS* w) {
   RC(make_dims(desc, d));
   if (!ws || (reinterpret_cast<uintptr_t>(ws) & 255)) return MVAE_ERR_INVALID;
@@ -578,6 +697,20 @@ int mvae_moses_step(const mvae_moses_desc* desc, const float* const* params, flo
   const bool backward = grads != nullptr;
   return d.bf16 ? step_t<__nv_bfloat16>(d, w, params, grads, ids, lengths, eps, out_scalars, z_out, logvar_out, y_out, backward, st)
                 : step_t<float>(d, w, params, grads, ids, lengths, eps, out_scalars, z_out, logvar_out, y_out, backward, st);
+}
+
+int mvae_moses_sample(const mvae_moses_desc* desc, const float* const* params, const float* z, int bos_id, int eos_id,
+                      int mode, float temp, unsigned long long seed, uint8_t* ids_out, int32_t* lengths_out,
+                      void* workspace, size_t workspace_bytes, mvae_stream_t stream) {
+  MDims d; MWS w;
+  RC(check_ws(desc, workspace, workspace_bytes, &d, &w));
+  if (!params || !z || !ids_out || !lengths_out || temp <= 0.f || (mode != 0 && mode != 1)) return MVAE_ERR_INVALID;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  // small per-sequence state lives at the start of the (unused while sampling) one-hot buffer
+  uint8_t* w_cur = reinterpret_cast<uint8_t*>(w.OH);
+  uint8_t* done = w_cur + d.Bp;
+  return d.bf16 ? sample_t<__nv_bfloat16>(d, w, params, z, bos_id, eos_id, mode, temp, seed, ids_out, lengths_out, w_cur, done, st)
+                : sample_t<float>(d, w, params, z, bos_id, eos_id, mode, temp, seed, ids_out, lengths_out, w_cur, done, st);
 }
 
 int mvae_moses_read_error(const mvae_moses_desc* desc, void* workspace, size_t workspace_bytes, int* flag,

@@ -4,8 +4,8 @@ Same constructor (`VAE(vocab)` with the vocab duck-type of vocab.py:10-87), same
 (`encoder`, `decoder`, `vae` -> identical `state_dict()` keys incl. the aliases, and `model.encoder.parameters()` /
 `model.decoder.parameters()` feed separate optimisers as in moses_train_distrib_logp.py:267-268), same
 `forward(list[LongTensor]) -> (kl, recon, z, logvar, x_padded, y)`, `string2tensor` / `tensor2string`.
-`elbo_step()` is the fused fast path.  Not ported this round: `sample()` (mosesvae.py:214-262) and train-mode
-dropout between decoder layers (the step treats dropout as the identity, i.e. the reference in eval()).
+`sample(n_batch, max_len, z, temp) -> (list[str], z)`.  `elbo_step()` is the fused fast path.  Not ported this round:
+train-mode dropout between decoder layers (the step treats dropout as the identity, i.e. the reference in eval()).
 """
 import ctypes
 
@@ -157,5 +157,41 @@ class VAE(nn.Module):
         self._run([p.data for p in params], [p.grad for p in params], ids, lens, eps, kl_weight, recon_weight, False)
         return self._last_scalars
 
-    def sample(self, n_batch, max_len=100, z=None, temp=1.0):
-        raise NotImplementedError("VAE.sample (mosesvae.py:214-262) is not ported to the B200 path yet")
+    def sample_z_prior(self, n_batch):
+        """z ~ N(0, I).  The shipped mosesvae.py:201-211 returns zeros through an undefined `self.d_z`; the working
+        prior is mosesfile.py:165-166 (randn), which is what this returns."""
+        return torch.randn(n_batch, self.cfg["d_z"], device=self.device)
+
+    @torch.no_grad()
+    def sample_ids(self, n_batch, max_len=100, z=None, temp=1.0, greedy=False, seed=None):
+        """Device-side result of sample(): (ids u8 (B,max_len), lengths int32 (B), z)."""
+        if z is None:
+            z = self.sample_z_prior(n_batch)
+        z = z.to(self.device, torch.float32).contiguous()
+        B, c = z.shape[0], self.cfg
+        prec = {"fp32": _lib.PREC_FP32, "bf16": _lib.PREC_BF16}[self.precision]
+        d = MosesDesc(B, int(max_len), c["vocab"], c["d_z"], c["q_hidden"], c["d_hidden"], c["d_layers"], c["mlp_hidden"],
+                      int(self.pad), prec, 1.0, 1.0)
+        need = lib.mvae_moses_workspace_bytes(ctypes.byref(d))
+        dev = z.device
+        if self._ws is None or self._ws.numel() < need + 256 or self._ws.device != dev:
+            self._ws = torch.empty(need + 256, dtype=torch.uint8, device=dev)
+        wsp = ctypes.c_void_p(self._ws.data_ptr() + (-self._ws.data_ptr()) % 256)
+        ids = torch.empty(B, int(max_len), dtype=torch.uint8, device=dev)
+        lens = torch.empty(B, dtype=torch.int32, device=dev)
+        if seed is None:
+            seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+        params = [p.detach() for p in self.ordered_params()]
+        with torch.cuda.device(dev):
+            check(lib.mvae_moses_sample(ctypes.byref(d), _ptr_table(params), _p(z), int(self.bos), int(self.eos),
+                                        0 if greedy else 1, float(temp), ctypes.c_ulonglong(seed), _p(ids), _p(lens), wsp,
+                                        need, _stream()))
+        self._last_desc = (d, wsp, need)
+        return ids, lens, z
+
+    def sample(self, n_batch, max_len=100, z=None, temp=1.0, greedy=False, seed=None):
+        """mosesvae.py:214-262: returns (list[str], z).  Multinomial draws by default (the reference behaviour),
+        greedy=True selects argmax decoding (the bit-exact parity mode)."""
+        ids, lens, z = self.sample_ids(n_batch, max_len, z, temp, greedy, seed)
+        ids_h, lens_h = ids.cpu(), lens.cpu().tolist()
+        return [self.tensor2string(ids_h[i, :lens_h[i]]) for i in range(ids_h.shape[0])], z

@@ -214,3 +214,38 @@ def moses_step(P, seqs, eps, pad, kl_weight=1.0, need_grads=True, d_layers=3):
     G["x_emb.weight"] = dE
     res["grads"] = G
     return res
+
+
+def moses_sample_greedy(P, z, bos, eos, pad, max_len=100, d_layers=3):
+    """Greedy restatement of VAE.sample (mosesvae.py:214-262; the shipped uint8 eos_mask / undefined d_z are fixed as
+    SURVEY.md 8c prescribes: bool mask, argmax instead of torch.multinomial, ties -> lowest id).  All rows run all
+    max_len-1 steps; tokens after EOS are not written; returns ids (B,max_len) filled with pad, lengths end_pads."""
+    B = z.shape[0]
+    E = P["x_emb.weight"]
+    V = E.shape[0]
+    d_h = P["decoder_lat.weight"].shape[0]
+    h0 = z @ P["decoder_lat.weight"].T + P["decoder_lat.bias"]
+    h = [h0.copy() for _ in range(d_layers)]
+    w = np.full(B, bos, dtype=np.int64)
+    x = np.full((B, max_len), pad, dtype=np.int64)
+    x[:, 0] = bos
+    end = np.full(B, max_len, dtype=np.int64)
+    done = np.zeros(B, dtype=bool)
+    for i in range(1, max_len):
+        inp = np.concatenate([E[w], z], 1)
+        for l in range(d_layers):
+            H = d_h
+            gi = inp @ P[f"decoder_rnn.weight_ih_l{l}"].T + P[f"decoder_rnn.bias_ih_l{l}"]
+            gh = h[l] @ P[f"decoder_rnn.weight_hh_l{l}"].T + P[f"decoder_rnn.bias_hh_l{l}"]
+            r = sigmoid(gi[:, :H] + gh[:, :H])
+            zz = sigmoid(gi[:, H:2 * H] + gh[:, H:2 * H])
+            n = np.tanh(gi[:, 2 * H:] + r * gh[:, 2 * H:])
+            h[l] = (1 - zz) * n + zz * h[l]
+            inp = h[l]
+        y = inp @ P["decoder_fc.weight"].T + P["decoder_fc.bias"]
+        w = y.argmax(-1)
+        x[~done, i] = w[~done]
+        new_eos = ~done & (w == eos)
+        end[new_eos] = i + 1
+        done |= new_eos
+    return x, end, y
