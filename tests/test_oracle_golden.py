@@ -96,3 +96,25 @@ def test_moses_oracle_matches_reference(name):
         else:
             np.testing.assert_allclose(gr.reshape(-1)[g[f"f64/gidx/{k}"]], g[f"f64/gval/{k}"], rtol=1e-8,
                                        atol=1e-12 + 1e-9 * gn)
+
+
+# ---- Config A oracle (oracle/cfga_oracle.py) against fixtures from the reference's models.py ----
+@pytest.mark.parametrize("name", ["cfga_small_b3", "cfga_full_b2"])
+def test_cfga_oracle_matches_reference(name):
+    from oracle import cfga_oracle as ca
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    ps, bs, B = [int(v) for v in g["meta"]]
+    eh, el, dh, dl, Z = [int(v) for v in g["cfg"]]
+    P = ca.make_cfga_params(ps, dtype=np.float64, eh=eh, el=el, dh=dh, dl=dl, Z=Z)
+    ids, onehot, eps = vo.make_batch(bs, B, latent=Z, dtype=np.float64)
+    r = ca.cfga_step(P, ids.astype(np.int64), eps, el=el, dl=dl)
+    assert abs(r["loss"] - float(g["loss"])) <= 1e-11 * abs(float(g["loss"]))
+    np.testing.assert_allclose(r["probs"], g["probs"], rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(r["mu"], g["mu"], rtol=1e-9, atol=1e-12)
+    for k, gr in r["grads"].items():
+        gn = float(g[f"gnorm/{k}"])
+        assert abs(np.sqrt((gr ** 2).sum()) - gn) <= 1e-8 * gn + 1e-14, k
+        if f"gfull/{k}" in g:
+            np.testing.assert_allclose(gr, g[f"gfull/{k}"], rtol=1e-7, atol=1e-12 + 1e-9 * gn)
+        else:
+            np.testing.assert_allclose(gr.reshape(-1)[g[f"gidx/{k}"]], g[f"gval/{k}"], rtol=1e-7, atol=1e-12 + 1e-9 * gn)
