@@ -19,13 +19,9 @@
 #include "common.cuh"
 #include "simt_kernels.cuh"
 #include "umma_gemm.h"
-
-void mvae_count_launches(int n);   // cfgb.cu
+#include "host_common.cuh"
 
 namespace {
-
-#define RC(expr) do { int _rc = (expr); if (_rc != MVAE_OK) return _rc; } while (0)
-#define KCHECK() do { mvae_count_launches(1); MVAE_CUDA_CHECK(cudaGetLastError()); } while (0)
 
 struct MDims {
   int B, Bp, T, V, CP, Z, Hq, Hd, L, MLP, pad;
@@ -45,16 +41,6 @@ int make_dims(const mvae_moses_desc* d, MDims* o) {
   o->pad = d->pad_id; o->bf16 = d->precision == MVAE_PREC_BF16; o->kl_w = d->kl_weight; o->rec_w = d->recon_weight;
   return MVAE_OK;
 }
-
-struct Carver {
-  uint8_t* base; size_t off;
-  template <typename T> T* take(size_t n) {
-    off = (off + 255) & ~size_t(255);
-    T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
-    off += n * sizeof(T);
-    return p;
-  }
-};
 
 struct MWS {
   int* err_flag; double* kl_sum; double* nll_sum; int* M;
@@ -116,78 +102,9 @@ inline int P_LATB(int L) { return P_DEC0 + 4 * L + 1; }
 inline int P_FCW(int L) { return P_DEC0 + 4 * L + 2; }
 inline int P_FCB(int L) { return P_DEC0 + 4 * L + 3; }
 
-inline int grid_for(long long n, int block = 256, int cap = 148 * 16) {
-  long long g = (n + block - 1) / block;
-  return (int)(g < 1 ? 1 : (g > cap ? cap : g));
-}
-inline int memset_async(void* p, size_t bytes, cudaStream_t st) {
-  mvae_count_launches(1);
-  MVAE_CUDA_CHECK(cudaMemsetAsync(p, 0, bytes, st));
-  return MVAE_OK;
-}
-template <typename TA>
-int gemm(int* err_flag, cudaStream_t st, const TA* A, long long lda, bool a_trans, const TA* B, long long ldb,
-         bool b_kmajor, void* out, long long ldc, bool out_is_ta, int M, int N, int K, const float* bias,
-         bool accumulate, int splits, int bn = 0) {
-  mvae_count_launches(1);
-  if constexpr (sizeof(TA) == 4) {
-    (void)out_is_ta; (void)bn; (void)err_flag;
-    return simt::sgemm(st, reinterpret_cast<const float*>(A), a_trans ? 1 : lda, a_trans ? lda : 1,
-                       reinterpret_cast<const float*>(B), b_kmajor ? 1 : ldb, b_kmajor ? ldb : 1,
-                       reinterpret_cast<float*>(out), ldc, M, N, K, bias, simt::ACT_NONE, accumulate ? 1 : 0, splits);
-  } else {
-    mvae_umma_operand a{A, a_trans ? 1 : 0, M, K, lda, 1, 0, 0, 0};
-    mvae_umma_operand b{B, b_kmajor ? 0 : 1, N, K, ldb, 1, 0, 0, 0};
-    mvae_umma_out o{out, ldc, out_is_ta ? 1 : 0, accumulate ? 1 : 0, bias, 0};
-    return mvae_umma_gemm(&a, &b, &o, M, N, K, bn, splits, 0, err_flag, st);
-  }
-}
-inline int sg(cudaStream_t st, const float* A, long long sam, long long sak, const float* B, long long sbk,
-              long long sbn, float* C, long long ldc, int M, int N, int K, const float* bias, int act, int accumulate,
-              int splits = 1) {
-  mvae_count_launches(1);
-  return simt::sgemm(st, A, sam, sak, B, sbk, sbn, C, ldc, M, N, K, bias, act, accumulate, splits);
-}
-inline int sg_wgrad(cudaStream_t st, const float* A, long long sam, long long sak, const float* B, long long sbk,
-                    long long sbn, float* C, long long ldc, int M, int N, int K) {
-  if (ldc == N) RC(memset_async(C, (size_t)M * N * 4, st));
-  else { mvae_count_launches(1); MVAE_CUDA_CHECK(cudaMemset2DAsync(C, ldc * 4, 0, (size_t)N * 4, M, st)); }
-  const int splits = K >= 1024 ? 16 : (K >= 256 ? 4 : 1);
-  return sg(st, A, sam, sak, B, sbk, sbn, C, ldc, M, N, K, nullptr, simt::ACT_NONE, 1, splits);
-}
-
 // ---------------------------------------------------------------------------------------------------------
 // kernels specific to this path
 // ---------------------------------------------------------------------------------------------------------
-// out[t][b][c] = tbl[ids[b][t]][c] (+ add[b][c]);  rows b >= B are zero.  tbl is [V][W] fp32, out [T][Bp][W] TA.
-template <typename TA>
-__global__ void gather_rows_kernel(const float* __restrict__ tbl, int W, const uint8_t* __restrict__ ids, int ids_ld,
-                                   const float* __restrict__ add, int B, int Bp, int T, TA* __restrict__ out) {
-  const long long total = (long long)T * Bp * W;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(i % W);
-    const long long rb = i / W;
-    const int b = (int)(rb % Bp), t = (int)(rb / Bp);
-    float v = 0.f;
-    if (b < B) {
-      v = tbl[(long long)ids[(long long)b * ids_ld + t] * W + c];
-      if (add) v += add[(long long)b * W + c];
-    }
-    out[i] = from_f32<TA>(v);
-  }
-}
-// OH[t*Bp + b][v] = 1 iff b < B and ids[b][t] == v   (CP columns)
-template <typename TA>
-__global__ void onehot_rows_kernel(const uint8_t* __restrict__ ids, int ids_ld, int B, int Bp, int T, int CP,
-                                   TA* __restrict__ out) {
-  const long long total = (long long)T * Bp * CP;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(i % CP);
-    const long long rb = i / CP;
-    const int b = (int)(rb % Bp), t = (int)(rb / Bp);
-    out[i] = from_f32<TA>((b < B && ids[(long long)b * ids_ld + t] == c) ? 1.f : 0.f);
-  }
-}
 // z = mu + exp(lv/2) eps ; kl_sum += sum 0.5 (e^lv + mu^2 - 1 - lv)     (mosesvae.py:159-162)
 __global__ void reparam_kl_std_kernel(const float* __restrict__ mu, const float* __restrict__ lv,
                                       const float* __restrict__ eps, long long n, float* __restrict__ z,

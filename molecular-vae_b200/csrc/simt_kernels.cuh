@@ -507,6 +507,91 @@ __global__ void gru_gate_bwd_kernel(const TA* __restrict__ sv, const TA* __restr
   }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// LSTM cell (torch.nn.LSTM, gate rows i,f,g,o; models.py:128,164 name these modules "gru" but they are nn.LSTM):
+//   a = gi + gh ; i,f,o = sigmoid, g = tanh ; c' = f c + i g ; h' = o tanh(c')
+// One thread per (row b, unit j) of a [Bp][Hp] slab; gi (incl. both biases) is per-step [Bp][4Hp] (TG) or the
+// time-invariant layer-0 projection; gh fp32 [Bp][4Hp]; c: fp32 state, updated in place.
+// Saves (i,f,g,o,c_prev,tanh c') into sv[Bp][6Hp] for BPTT.
+// ------------------------------------------------------------------------------------------
+template <typename TA, typename TG>
+__global__ void lstm_gate_fwd_kernel(const TG* __restrict__ gi, const float* __restrict__ gh, float* __restrict__ c,
+                                     TA* __restrict__ hnextA, TA* __restrict__ sv, int Bp, int Hp) {
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= (long long)Bp * Hp) return;
+  const int b = (int)(idx / Hp), j = (int)(idx - (long long)b * Hp);
+  const long long g4 = (long long)b * 4 * Hp + j;
+  const float ai = to_f32<TG>(gi[g4]) + gh[g4], af = to_f32<TG>(gi[g4 + Hp]) + gh[g4 + Hp];
+  const float ag = to_f32<TG>(gi[g4 + 2 * Hp]) + gh[g4 + 2 * Hp], ao = to_f32<TG>(gi[g4 + 3 * Hp]) + gh[g4 + 3 * Hp];
+  const float i = sigmoid_acc(ai), f = sigmoid_acc(af), g = tanhf(ag), o = sigmoid_acc(ao);
+  const float cp = c[idx];
+  const float cn = fmaf(f, cp, i * g);
+  const float tc = tanhf(cn);
+  c[idx] = cn;
+  hnextA[idx] = from_f32<TA>(o * tc);
+  if (sv) {
+    const long long s6 = (long long)b * 6 * Hp + j;
+    sv[s6] = from_f32<TA>(i); sv[s6 + Hp] = from_f32<TA>(f); sv[s6 + 2 * Hp] = from_f32<TA>(g);
+    sv[s6 + 3 * Hp] = from_f32<TA>(o); sv[s6 + 4 * Hp] = from_f32<TA>(cp); sv[s6 + 5 * Hp] = from_f32<TA>(tc);
+  }
+}
+// BPTT step: dh = dh_carry + dX[t]; writes dG[t] = [di|df|dg|do] (pre-activation grads, shared by the ih and hh paths),
+// dc_carry <- dc_total * f.  dh_carry for the previous step is then dG[t] * W_hh (GEMM, not accumulated).
+template <typename TA>
+__global__ void lstm_gate_bwd_kernel(const TA* __restrict__ sv, const TA* __restrict__ dX,
+                                     const float* __restrict__ dh_carry, float* __restrict__ dc_carry,
+                                     TA* __restrict__ dG, int Bp, int Hp) {
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= (long long)Bp * Hp) return;
+  const int b = (int)(idx / Hp), j = (int)(idx - (long long)b * Hp);
+  const long long s6 = (long long)b * 6 * Hp + j;
+  const float i = to_f32<TA>(sv[s6]), f = to_f32<TA>(sv[s6 + Hp]), g = to_f32<TA>(sv[s6 + 2 * Hp]),
+              o = to_f32<TA>(sv[s6 + 3 * Hp]), cp = to_f32<TA>(sv[s6 + 4 * Hp]), tc = to_f32<TA>(sv[s6 + 5 * Hp]);
+  const float dh = dh_carry[idx] + to_f32<TA>(dX[idx]);
+  const float dct = dc_carry[idx] + dh * o * (1.f - tc * tc);
+  const long long g4 = (long long)b * 4 * Hp + j;
+  dG[g4] = from_f32<TA>(dct * g * i * (1.f - i));
+  dG[g4 + Hp] = from_f32<TA>(dct * cp * f * (1.f - f));
+  dG[g4 + 2 * Hp] = from_f32<TA>(dct * i * (1.f - g * g));
+  dG[g4 + 3 * Hp] = from_f32<TA>(dh * tc * o * (1.f - o));
+  dc_carry[idx] = dct * f;
+}
+// 4-gate padding helpers: dst[4Hp][cols_p] <- src[4H][cols] ; inverse ; bias vectors
+template <typename T>
+__global__ void pad_gates4_kernel(const float* __restrict__ src, int H, int cols, T* __restrict__ dst, int Hp, int cols_p) {
+  const long long total = 4ll * Hp * cols_p;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cols_p);
+    const int r = (int)(i / cols_p);
+    const int g = r / Hp, j = r - g * Hp;
+    dst[i] = from_f32<T>((j < H && c < cols) ? src[((long long)g * H + j) * cols + c] : 0.f);
+  }
+}
+__global__ void unpad_gates4_kernel(const float* __restrict__ src, int Hp, int cols_p, float* __restrict__ dst, int H, int cols) {
+  const long long total = 4ll * H * cols;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cols);
+    const int r = (int)(i / cols);
+    const int g = r / H, j = r - g * H;
+    dst[i] = src[((long long)g * Hp + j) * cols_p + c];
+  }
+}
+// padded combined bias: dst[4Hp] = b_ih + b_hh
+__global__ void pad_bias4_sum_kernel(const float* __restrict__ bih, const float* __restrict__ bhh, int H, float* __restrict__ dst, int Hp) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 4 * Hp) return;
+  const int g = i / Hp, j = i - g * Hp;
+  dst[i] = j < H ? bih[g * H + j] + bhh[g * H + j] : 0.f;
+}
+// dst_a[4H] = dst_b[4H] = src[4Hp] (unpadded): the two LSTM biases receive the same gradient
+__global__ void unpad_bias4_dup_kernel(const float* __restrict__ src, int Hp, float* __restrict__ a, float* __restrict__ b, int H) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 4 * H) return;
+  const float v = src[(i / H) * Hp + (i % H)];
+  a[i] = v; b[i] = v;
+}
+
 // ------------------------------------------------------------------------------------------
 // Head: softmax over the charset + max_len * BCE(mean) (train.py:31-35) and its gradient wrt the logits
 // (SURVEY.md A.3).  One warp per (t,b) row of logits[T*Bp][CP]; lanes cover columns c, c+32.
