@@ -111,6 +111,54 @@ int mvae_onehot_to_ids(const float* onehot, long long rows, int charset, uint8_t
 int mvae_cfgb_read_error(const mvae_cfgb_desc* d, void* workspace, size_t workspace_bytes, int* flag,
                          mvae_stream_t stream);
 
+/* ---- "Config A": models.py exactly as shipped ----------------------------------------------------------------
+ * models.py:97-165 (MolecularVAE = MolEncoder :109-135 [Embedding -> LSTM -> 3 x ConvSELU(k18) -> Linear+SELU -> Lambda
+ * :80-94] + MolDecoder :148-165 [Linear+SELU -> Repeat -> LSTM -> Linear -> Softmax]), trained with loss_function of
+ * train.py:31-38.  The conv widths (120, 64, 64), kernel size 18 and dense_1 width 512 are the reference's literals.     */
+typedef struct mvae_cfga_desc {
+  int32_t batch;      /* B                                                                                            */
+  int32_t seq_len;    /* T = 120 = `i`: LSTM steps AND conv_1 in-channels (models.py:118)                              */
+  int32_t charset;    /* C = 35 (<= 64)                                                                               */
+  int32_t embed;      /* word_embedding_size = 30 (models.py:111)                                                     */
+  int32_t enc_hidden; /* h_size = 72  (>= 52 so that three k=18 convolutions fit)                                     */
+  int32_t enc_layers; /* num_lstm = 3 (1..4)                                                                          */
+  int32_t latent;     /* o = 292                                                                                      */
+  int32_t dec_hidden; /* 1024 (models.py:150), multiple of 64                                                         */
+  int32_t dec_layers; /* num_gru = 4 (1..4)                                                                           */
+  int32_t precision;  /* MVAE_PREC_*                                                                                  */
+  float max_len;      /* multiplier of the BCE mean (script global, 128 in train.py:43)                               */
+  float eps_scale;    /* Lambda.scale = 1e-2 (models.py:82,92)                                                        */
+} mvae_cfga_desc;
+/* parameters / gradients: host arrays of fp32 device pointers in state_dict order:
+ *   0 encoder.embedding.weight (C,E) | 1+4l.. encoder.gru.{weight_ih_l, weight_hh_l, bias_ih_l, bias_hh_l} (4*EH rows, i,f,g,o)
+ *   then encoder.conv_{1,2,3}.0.{weight,bias}, encoder.dense_1.0.{weight,bias}, encoder.lmbd.z_mean.{weight,bias},
+ *   encoder.lmbd.z_log_var.{weight,bias}, decoder.latent_input.0.{weight,bias}, decoder.gru.{...}_l (4 per layer),
+ *   decoder.decoded_mean.module.0.{weight,bias}                                                                       */
+#define MVAE_CFGA_NUM_PARAMS(enc_layers, dec_layers) (17 + 4 * (enc_layers) + 4 * (dec_layers))
+size_t mvae_cfga_workspace_bytes(const mvae_cfga_desc* d);
+/* Fused step = train.py:98-101 (model(data); loss_function(...); loss.backward()) for the shipped model.  ids u8 (B,T);
+ * eps fp32 (B,Z) standard-normal draws (the reference draws them on the CPU generator, models.py:92).  grads are
+ * OVERWRITTEN.  out_scalars as for mvae_cfgb_elbo_step.                                                               */
+int mvae_cfga_elbo_step(const mvae_cfga_desc* d, const float* const* params, float* const* grads, const uint8_t* ids,
+                        const float* eps, float* out_scalars, float* mu_out, float* logvar_out, void* workspace,
+                        size_t workspace_bytes, mvae_stream_t stream);
+int mvae_cfga_elbo_step_graph_create(const mvae_cfga_desc* d, const float* const* params, float* const* grads,
+                                     const uint8_t* ids, const float* eps, float* out_scalars, float* mu_out,
+                                     float* logvar_out, void* workspace, size_t workspace_bytes, mvae_graph** out_graph);
+/* MolecularVAE.forward (models.py:104-106): probs fp32 (B,T,C), mu, logvar fp32 (B,Z); and its autograd backward.        */
+int mvae_cfga_forward(const mvae_cfga_desc* d, const float* const* params, const uint8_t* ids, const float* eps,
+                      float* probs, float* mu, float* logvar, void* workspace, size_t workspace_bytes,
+                      mvae_stream_t stream);
+int mvae_cfga_backward(const mvae_cfga_desc* d, const float* const* params, float* const* grads, const uint8_t* ids,
+                       const float* eps, const float* dprobs, const float* dmu, const float* dlogvar, void* workspace,
+                       size_t workspace_bytes, mvae_stream_t stream);
+/* MolDecoder.forward on given latents (train_sample.py:31-33: model.decoder(z) -> argmax): ids_out u8 (B,T), probs_out
+ * optional fp32 (B,T,C).                                                                                              */
+int mvae_cfga_decode(const mvae_cfga_desc* d, const float* const* params, const float* z, uint8_t* ids_out,
+                     float* probs_out, void* workspace, size_t workspace_bytes, mvae_stream_t stream);
+int mvae_cfga_read_error(const mvae_cfga_desc* d, void* workspace, size_t workspace_bytes, int* flag,
+                         mvae_stream_t stream);
+
 /* ---- MOSES-style character VAE ------------------------------------------------------------------------------
  * mosesvae.py:27-199 (class VAE: forward :126-140, forward_encoder :142-164, forward_decoder :166-199).       */
 typedef struct mvae_moses_desc {

@@ -21,6 +21,12 @@ class CfgBDesc(ctypes.Structure):
     ]
 
 
+class CfgADesc(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int32) for n in ("batch", "seq_len", "charset", "embed", "enc_hidden", "enc_layers", "latent",
+                                              "dec_hidden", "dec_layers", "precision")] + [("max_len", ctypes.c_float),
+                                                                                         ("eps_scale", ctypes.c_float)]
+
+
 class MosesDesc(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int32) for n in ("batch", "max_len", "vocab", "d_z", "q_hidden", "d_hidden", "d_layers",
                                               "mlp_hidden", "pad_id", "precision")] + [("kl_weight", ctypes.c_float),
@@ -40,6 +46,7 @@ def _load():
     vp, ll, i32 = ctypes.c_void_p, ctypes.c_longlong, ctypes.c_int
     pp = ctypes.POINTER(ctypes.c_void_p)
     dp = ctypes.POINTER(CfgBDesc)
+    ap = ctypes.POINTER(CfgADesc)
     sigs = {
         "mvae_strerror": (ctypes.c_char_p, [i32]),
         "mvae_last_cuda_error": (ctypes.c_char_p, []),
@@ -57,6 +64,14 @@ def _load():
         "mvae_cfgb_decode_greedy": (i32, [dp, pp, vp, vp, vp, vp, ctypes.c_size_t, vp]),
         "mvae_onehot_to_ids": (i32, [vp, ll, i32, vp, vp, vp]),
         "mvae_cfgb_read_error": (i32, [dp, vp, ctypes.c_size_t, ctypes.POINTER(i32), vp]),
+        "mvae_cfga_workspace_bytes": (ctypes.c_size_t, [ap]),
+        "mvae_cfga_elbo_step": (i32, [ap, pp, pp, vp, vp, vp, vp, vp, vp, ctypes.c_size_t, vp]),
+        "mvae_cfga_elbo_step_graph_create": (i32, [ap, pp, pp, vp, vp, vp, vp, vp, vp, ctypes.c_size_t,
+                                                   ctypes.POINTER(vp)]),
+        "mvae_cfga_forward": (i32, [ap, pp, vp, vp, vp, vp, vp, vp, ctypes.c_size_t, vp]),
+        "mvae_cfga_backward": (i32, [ap, pp, pp, vp, vp, vp, vp, vp, vp, ctypes.c_size_t, vp]),
+        "mvae_cfga_decode": (i32, [ap, pp, vp, vp, vp, vp, ctypes.c_size_t, vp]),
+        "mvae_cfga_read_error": (i32, [ap, vp, ctypes.c_size_t, ctypes.POINTER(i32), vp]),
         "mvae_moses_workspace_bytes": (ctypes.c_size_t, [ctypes.POINTER(MosesDesc)]),
         "mvae_moses_step": (i32, [ctypes.POINTER(MosesDesc), pp, pp, vp, vp, vp, vp, vp, vp, vp, vp, ctypes.c_size_t, vp]),
         "mvae_moses_sample": (i32, [ctypes.POINTER(MosesDesc), pp, vp, i32, i32, i32, ctypes.c_float, ctypes.c_ulonglong, vp, vp,
@@ -82,6 +97,8 @@ EXPORTED = [
     "mvae_graph_num_kernel_nodes", "mvae_graph_destroy", "mvae_cfgb_forward", "mvae_cfgb_backward",
     "mvae_cfgb_decode_greedy", "mvae_onehot_to_ids", "mvae_cfgb_read_error", "mvae_gemm_bf16", "mvae_sgemm",
     "mvae_clip_grad_norm", "mvae_adam_step", "mvae_sgd_momentum_step",
+    "mvae_cfga_workspace_bytes", "mvae_cfga_elbo_step", "mvae_cfga_elbo_step_graph_create", "mvae_cfga_forward",
+    "mvae_cfga_backward", "mvae_cfga_decode", "mvae_cfga_read_error",
     "mvae_moses_workspace_bytes", "mvae_moses_step", "mvae_moses_sample", "mvae_moses_read_error",
 ]
 

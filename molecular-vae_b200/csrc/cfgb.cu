@@ -699,6 +699,34 @@ struct mvae_graph {
   long long counted_launches;
 };
 
+// Capture whatever `fn` enqueues on a fresh stream into an instantiated CUDA graph (shared by cfgb.cu / cfga.cu).
+int mvae_capture_into_graph(int (*fn)(void*, cudaStream_t), void* ctx, mvae_graph** out_graph) {
+  if (!out_graph || !fn) return MVAE_ERR_INVALID;
+  cudaStream_t cs;
+  MVAE_CUDA_CHECK(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+  const long long before = g_launches;
+  MVAE_CUDA_CHECK(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+  int rc = fn(ctx, cs);
+  cudaGraph_t graph = nullptr;
+  cudaError_t e = cudaStreamEndCapture(cs, &graph);
+  const long long counted = g_launches - before;
+  g_launches = before;
+  cudaStreamDestroy(cs);
+  if (rc != MVAE_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+  MVAE_CUDA_CHECK(e);
+  mvae_graph* g = new (std::nothrow) mvae_graph();
+  if (!g) return MVAE_ERR_INVALID;
+  g->graph = graph;
+  g->counted_launches = counted;
+  e = cudaGraphInstantiate(&g->exec, graph, 0);
+  if (e != cudaSuccess) { cudaGraphDestroy(graph); delete g; MVAE_CUDA_CHECK(e); }
+  size_t n = 0;
+  cudaGraphGetNodes(graph, nullptr, &n);
+  g->kernel_nodes = (long long)n;
+  *out_graph = g;
+  return MVAE_OK;
+}
+
 extern "C" {
 
 long long mvae_launch_count(void) { return g_launches; }
@@ -726,31 +754,17 @@ int mvae_cfgb_elbo_step_graph_create(const mvae_cfgb_desc* desc, const float* co
                                      const uint8_t* ids, const float* eps, float* out_scalars, float* mu_out,
                                      float* logvar_out, void* workspace, size_t workspace_bytes,
                                      mvae_graph** out_graph) {
-  if (!out_graph) return MVAE_ERR_INVALID;
-  cudaStream_t cs;
-  MVAE_CUDA_CHECK(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
-  const long long before = g_launches;
-  MVAE_CUDA_CHECK(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
-  int rc = mvae_cfgb_elbo_step(desc, params, grads, ids, eps, out_scalars, mu_out, logvar_out, workspace,
-                               workspace_bytes, reinterpret_cast<mvae_stream_t>(cs));
-  cudaGraph_t graph = nullptr;
-  cudaError_t e = cudaStreamEndCapture(cs, &graph);
-  const long long counted = g_launches - before;
-  g_launches = before;
-  cudaStreamDestroy(cs);
-  if (rc != MVAE_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
-  MVAE_CUDA_CHECK(e);
-  mvae_graph* g = new (std::nothrow) mvae_graph();
-  if (!g) return MVAE_ERR_INVALID;
-  g->graph = graph;
-  g->counted_launches = counted;
-  e = cudaGraphInstantiate(&g->exec, graph, 0);
-  if (e != cudaSuccess) { cudaGraphDestroy(graph); delete g; MVAE_CUDA_CHECK(e); }
-  size_t n = 0;
-  cudaGraphGetNodes(graph, nullptr, &n);
-  g->kernel_nodes = (long long)n;
-  *out_graph = g;
-  return MVAE_OK;
+  struct Ctx {
+    const mvae_cfgb_desc* desc; const float* const* params; float* const* grads; const uint8_t* ids; const float* eps;
+    float *out_scalars, *mu_out, *logvar_out; void* ws; size_t ws_bytes;
+  } c{desc, params, grads, ids, eps, out_scalars, mu_out, logvar_out, workspace, workspace_bytes};
+  return mvae_capture_into_graph(
+      [](void* p, cudaStream_t cs) {
+        Ctx* c = static_cast<Ctx*>(p);
+        return mvae_cfgb_elbo_step(c->desc, c->params, c->grads, c->ids, c->eps, c->out_scalars, c->mu_out, c->logvar_out,
+                                   c->ws, c->ws_bytes, reinterpret_cast<mvae_stream_t>(cs));
+      },
+      &c, out_graph);
 }
 
 int mvae_graph_launch(mvae_graph* g, mvae_stream_t stream) {

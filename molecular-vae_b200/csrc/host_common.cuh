@@ -6,6 +6,8 @@
 #include "umma_gemm.h"
 
 void mvae_count_launches(int n);   // cfgb.cu
+struct mvae_graph;
+int mvae_capture_into_graph(int (*fn)(void*, cudaStream_t), void* ctx, mvae_graph** out_graph);   // cfgb.cu
 
 #define RC(expr) do { int _rc = (expr); if (_rc != MVAE_OK) return _rc; } while (0)
 #define KCHECK() do { mvae_count_launches(1); MVAE_CUDA_CHECK(cudaGetLastError()); } while (0)

@@ -52,6 +52,24 @@ def test_param_order_matches_reference_state_dict():
         assert tuple(sd[k].shape) == shp, k
 
 
+def test_cfga_state_dict_matches_reference_layout():
+    """models.MolecularVAE() exposes the reference's state_dict keys / shapes in C-ABI pointer order."""
+    import molecular_vae_b200 as m
+    from oracle import cfga_oracle as ca
+    model = m.models.MolecularVAE()
+    sd = model.state_dict()
+    shapes = ca.cfga_shapes()
+    assert list(sd.keys()) == list(shapes.keys()) == m.models.cfga_param_order(3, 4)
+    for k, shp in shapes.items():
+        assert tuple(sd[k].shape) == shp, k
+    assert sum(p.numel() for p in model.parameters()) == 32285105
+    L = m._lib
+    d = L.CfgADesc(4096, 120, 35, 30, 72, 3, 292, 1024, 4, L.PREC_BF16, 120.0, 1e-2)
+    assert 30e9 < L.lib.mvae_cfga_workspace_bytes(ctypes.byref(d)) < 80e9
+    bad = L.CfgADesc(8, 120, 35, 30, 40, 3, 292, 1024, 4, L.PREC_BF16, 120.0, 1e-2)   # three k=18 convs do not fit
+    assert L.lib.mvae_cfga_workspace_bytes(ctypes.byref(bad)) == 0
+
+
 def test_no_cpu_fallback():
     import torch
     import molecular_vae_b200 as m
@@ -59,3 +77,5 @@ def test_no_cpu_fallback():
         pytest.skip("GPU present")
     with pytest.raises(m._lib.MvaeError):
         m.CfgBEngine(4)
+    with pytest.raises(m._lib.MvaeError):
+        m.models.CfgAEngine(4)
