@@ -145,6 +145,49 @@ def kernel_rooflines(B, peaks):
     return out
 
 
+def rec_kernel_times(model, eng, params, ids_dev, eps_dev, steps=3):
+    """Average launch duration of the persistent recurrence kernels, CUDA events on the launching stream, measured on
+    DIRECT launches of the same fused step right after the timed region (a graph replay cannot carry events)."""
+    import ctypes
+    import torch
+    import molecular_vae_b200 as m
+    lib = m._lib.lib
+    P, G = [p.data for p in params], [p.grad for p in params]
+    eng.elbo_step(P, G, ids_dev, eps_dev)          # warm (direct path)
+    torch.cuda.synchronize()
+    lib.mvae_profile_enable(1)
+    for _ in range(steps):
+        eng.elbo_step(P, G, ids_dev, eps_dev)
+    torch.cuda.synchronize()
+    out = {}
+    for tag, name in ((0, "fwd"), (1, "bwd")):
+        ms, n = ctypes.c_float(0), ctypes.c_int(0)
+        m._lib.check(lib.mvae_profile_read(tag, ctypes.byref(ms), ctypes.byref(n)))
+        out[name] = (ms.value / max(n.value, 1), n.value)
+    lib.mvae_profile_enable(0)
+    return out
+
+
+def ncu_traffic(path, kernel_substr):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel_substr` from a committed ncu --set full summary."""
+    try:
+        vals, cur, take = [], None, False
+        for line in open(path):
+            if line.startswith("kernel:"):
+                take = kernel_substr in line
+                if take:
+                    vals.append([0.0, 0.0])
+            elif take and "dram__bytes_read.sum" in line:
+                vals[-1][0] = float(line.split("=")[1].split()[0]) * (1e9 if "Gbyte" in line else 1e6 if "Mbyte" in line else 1.0)
+            elif take and "dram__bytes_write.sum" in line:
+                vals[-1][1] = float(line.split("=")[1].split()[0]) * (1e9 if "Gbyte" in line else 1e6 if "Mbyte" in line else 1.0)
+        if not vals:
+            return None
+        return sum(a + b for a, b in vals) / len(vals)
+    except Exception:
+        return None
+
+
 def run_ours(args):
     import numpy as np
     import torch
@@ -235,6 +278,16 @@ def run_ours(args):
     if rank == 0:
         peak = peaks["bf16_tflops_sustained"]
         achieved = (value / world) * GFLOP_PER_MOLECULE * 1e-3  # TFLOP/s per GPU
+        step_ms = sec / args.steps * 1e3
+        # dominant kernel = the BPTT sweep of one GRU layer (gru_rec2_kernel<BWD>): one launch = all T steps.
+        # algorithmic FLOPs per launch = 2 * (3H x H) MACs per molecule-step (dh_{t-1} = dgh_t W_hh) x T x B
+        rec = None
+        try:
+            rec = rec_kernel_times(model, eng, params, ids_dev, eps_dev)
+        except Exception as ex:
+            rec_err = repr(ex)
+        H, T = CFG["hidden"], CFG["seq_len"]
+        flops_launch = 2.0 * 3 * H * H * T * B
         line = {
             "metric": METRIC, "value": value, "unit": "molecules/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": sec / args.steps * 1e3, "higher_is_better": True,
@@ -247,10 +300,28 @@ def run_ours(args):
                     "d2h_bytes_per_step": 16, "steps": e2e_steps},
             "gpu_launches": launches,
             "clocks": sampler.summary(),
-            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src + " bf16_tflops_sustained",
-                         "scope": "whole fused step (algorithmic 2.7301 GFLOP/molecule x batch / step time)"},
         }
+        whole = {"achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                 "scope": "whole fused step (algorithmic 2.7301 GFLOP/molecule x batch / step time)"}
+        if rec and rec["bwd"][1] > 0:
+            bwd_ms, fwd_ms = rec["bwd"][0], rec["fwd"][0]
+            a = flops_launch / (bwd_ms * 1e-3) * 1e-12
+            line["roofline"] = {
+                "bound": "tensor", "kernel": "gru_rec2_kernel<BWD> (persistent BPTT sweep of one GRU layer, T steps per launch)",
+                "achieved": a, "peak": peak, "unit": "TFLOP/s", "frac": a / peak,
+                "traffic": ncu_traffic(os.path.join(ROOT, "profiles", "r01_rec2_ncu_full.txt"), "gru_rec2_kernel<1"),
+                "peak_source": peak_src + " bf16_tflops_sustained (kernel timed inside back-to-back steps)",
+                "flops_per_launch": flops_launch, "launch_ms": bwd_ms, "launches_timed": rec["bwd"][1],
+                "share_of_step": CFG["layers"] * bwd_ms / step_ms,
+                "fwd_sweep": {"launch_ms": fwd_ms, "achieved": flops_launch / (fwd_ms * 1e-3) * 1e-12,
+                              "frac": flops_launch / (fwd_ms * 1e-3) * 1e-12 / peak,
+                              "share_of_step": CFG["layers"] * fwd_ms / step_ms},
+                "whole_step": whole,
+            }
+        else:
+            line["roofline"] = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                                "frac": achieved / peak, "traffic": None, "peak_source": peak_src + " bf16_tflops_sustained",
+                                "scope": whole["scope"], "kernel_timing_error": locals().get("rec_err")}
         if world == 1:
             try:
                 line["roofline"]["kernels"] = kernel_rooflines(B, peaks)

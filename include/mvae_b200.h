@@ -35,6 +35,11 @@ const char* mvae_last_cuda_error(void);
 /* number of kernels / memsets this library has enqueued since the last reset (bench.py gpu_launches) */
 long long mvae_launch_count(void);
 void mvae_reset_launch_count(void);
+/* Per-kernel timing for bench.py's roofline: while enabled, every DIRECT (not graph-captured) launch of the persistent
+ * recurrence kernels is bracketed by CUDA events on its stream.  tag 0 = forward sweep, 1 = BPTT sweep (one launch = all
+ * T steps of one GRU layer).  mvae_profile_read synchronises on the recorded events.                                  */
+int mvae_profile_enable(int on);
+int mvae_profile_read(int tag, float* total_ms, int* launches);
 
 /* ---- "Config B": the canonical conv / latent-Z / L x H GRU model -------------------------------
  * models2d.py:8-52 (class VAE: encode / reparametrize / decode / forward) with the latent widened
@@ -174,13 +179,19 @@ typedef struct mvae_moses_desc {
   int32_t precision;  /* MVAE_PREC_*                                                                          */
   float kl_weight;    /* the scalar differentiated is kl_weight*kl + recon_weight*recon                        */
   float recon_weight; /* (moses_train_distrib_logp.py:302-306 uses kl_weight*kl + recon, :335 recon only)      */
+  /* mosesfile.py variant (mosesfile.py:6-157; BASELINE config 4): */
+  int32_t q_bidir;        /* 1: bidirectional encoder GRU (mosesfile.py:21-28), heads read cat(h_fwd, h_bwd) (:115-116) */
+  int32_t q_linear_heads; /* 1: q_mu / q_logvar are single Linear(Hq*(1+bidir), d_z) (mosesfile.py:31-32); 0: the 2-layer MLPs */
 } mvae_moses_desc;
 /* parameters / gradients: host arrays of fp32 device pointers in this order (reference shapes, row-major):
  *   0 x_emb.weight (V,V) | 1-4 encoder_rnn.{weight_ih_l0 (3Hq,V), weight_hh_l0, bias_ih_l0, bias_hh_l0}
  *   5-8 q_mu.{0.weight (mlp,Hq), 0.bias, 2.weight (d_z,mlp), 2.bias} | 9-12 q_logvar.{...}
  *   13+4l.. decoder_rnn.{weight_ih_l (3Hd, V+d_z | Hd), weight_hh_l, bias_ih_l, bias_hh_l}
- *   13+4L decoder_lat.weight (Hd,d_z), +1 decoder_lat.bias, +2 decoder_fc.weight (V,Hd), +3 decoder_fc.bias     */
+ *   13+4L decoder_lat.weight (Hd,d_z), +1 decoder_lat.bias, +2 decoder_fc.weight (V,Hd), +3 decoder_fc.bias
+ * With q_bidir the four encoder_rnn.*_l0_reverse tensors follow the forward ones; with q_linear_heads each head is
+ * {weight (d_z, Hq*(1+bidir)), bias} (state_dict order of mosesfile.VAE).                                        */
 #define MVAE_MOSES_NUM_PARAMS(layers) (17 + 4 * (layers))
+#define MVAE_MOSESFILE_NUM_PARAMS(layers) (17 + 4 * (layers))   /* 1 + 8 + 4 + 4L + 4 */
 size_t mvae_moses_workspace_bytes(const mvae_moses_desc* d);
 /* One step of VAE.forward (+ backward when grads != NULL; dropout is the identity).  ids: u8 (B,T) right-padded
  * with pad_id; lengths: int32 (B) (incl. bos/eos); eps: fp32 (B,d_z).  out_scalars (device, 4 floats):

@@ -30,7 +30,9 @@ class CfgADesc(ctypes.Structure):
 class MosesDesc(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int32) for n in ("batch", "max_len", "vocab", "d_z", "q_hidden", "d_hidden", "d_layers",
                                               "mlp_hidden", "pad_id", "precision")] + [("kl_weight", ctypes.c_float),
-                                                                                   ("recon_weight", ctypes.c_float)]
+                                                                                   ("recon_weight", ctypes.c_float),
+                                                                                   ("q_bidir", ctypes.c_int32),
+                                                                                   ("q_linear_heads", ctypes.c_int32)]
 
 
 class MvaeError(RuntimeError):
@@ -52,6 +54,8 @@ def _load():
         "mvae_last_cuda_error": (ctypes.c_char_p, []),
         "mvae_launch_count": (ll, []),
         "mvae_reset_launch_count": (None, []),
+        "mvae_profile_enable": (i32, [i32]),
+        "mvae_profile_read": (i32, [i32, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(i32)]),
         "mvae_cfgb_workspace_bytes": (ctypes.c_size_t, [dp]),
         "mvae_cfgb_elbo_step": (i32, [dp, pp, pp, vp, vp, vp, vp, vp, vp, ctypes.c_size_t, vp]),
         "mvae_cfgb_elbo_step_graph_create": (i32, [dp, pp, pp, vp, vp, vp, vp, vp, vp, ctypes.c_size_t,
@@ -93,6 +97,7 @@ def _load():
 lib = _load()
 EXPORTED = [
     "mvae_strerror", "mvae_last_cuda_error", "mvae_launch_count", "mvae_reset_launch_count",
+    "mvae_profile_enable", "mvae_profile_read",
     "mvae_cfgb_workspace_bytes", "mvae_cfgb_elbo_step", "mvae_cfgb_elbo_step_graph_create", "mvae_graph_launch",
     "mvae_graph_num_kernel_nodes", "mvae_graph_destroy", "mvae_cfgb_forward", "mvae_cfgb_backward",
     "mvae_cfgb_decode_greedy", "mvae_onehot_to_ids", "mvae_cfgb_read_error", "mvae_gemm_bf16", "mvae_sgemm",

@@ -28,6 +28,30 @@ namespace {
 long long g_launches = 0;
 inline void count(int n = 1) { g_launches += n; }
 
+// ---- optional per-kernel timing (bench.py roofline): CUDA events recorded on the launching stream around the
+// persistent recurrence kernels of DIRECT (non-captured) launches.  Off by default; nothing is recorded while a
+// stream is being captured.
+constexpr int PROF_TAGS = 4;
+struct ProfPair { cudaEvent_t e0, e1; int tag; };
+bool g_prof_on = false;
+ProfPair g_prof[4096];
+int g_prof_n = 0;
+struct ProfScope {
+  cudaStream_t st; int idx;
+  ProfScope(int tag, cudaStream_t s) : st(s), idx(-1) {
+    if (!g_prof_on || g_prof_n >= 4096) return;
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(s, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) return;
+    ProfPair& p = g_prof[g_prof_n];
+    if (cudaEventCreate(&p.e0) != cudaSuccess) return;
+    if (cudaEventCreate(&p.e1) != cudaSuccess) { cudaEventDestroy(p.e0); return; }
+    p.tag = tag;
+    idx = g_prof_n++;
+    cudaEventRecord(p.e0, st);
+  }
+  ~ProfScope() { if (idx >= 0) cudaEventRecord(g_prof[idx].e1, st); }
+};
+
 struct Dims {
   int B, Bp, T, C, CP, Z, H, Hp, L, F0, FLAT, L1, L2, L3;
   bool bf16, train;
@@ -445,6 +469,7 @@ int run_forward(const Dims& d, const WS& w, const float* const* P, const uint8_t
         ra.err_flag = w.err_flag;
         ra.ones_col = ones_column(d) ? Hp - 1 : -1;
         count(2);
+        ProfScope prof(0, st);
         if (rv >= 3) {
           ra.bhh = w.bhh_p[l] + 2 * Hp;
           RC(mvae_gru_rec2_launch(&ra, fast_gates(), st));
@@ -522,8 +547,11 @@ int run_backward(const Dims& d, const WS& w, const float* const* P, float* const
         ra.dX = (const __nv_bfloat16*)dX; ra.dG = (__nv_bfloat16*)dG; ra.counters = w.counters;
         ra.err_flag = w.err_flag;
         count(2);
-        if (rv >= 3) RC(mvae_gru_rec2_launch(&ra, 0, st));
-        else RC(mvae_gru_rec_launch(&ra, st));
+        {
+          ProfScope prof(1, st);
+          if (rv >= 3) RC(mvae_gru_rec2_launch(&ra, 0, st));
+          else RC(mvae_gru_rec_launch(&ra, st));
+        }
         if (l == 0) {
           dgi_time_sum_kernel<<<(unsigned)ceil_div64((long long)Bp * 3 * Hp / 8, 256), 256, 0, st>>>(
               (const __nv_bfloat16*)dG, T, Bp, Hp, w.dgi0sum);
@@ -729,6 +757,25 @@ int mvae_capture_into_graph(int (*fn)(void*, cudaStream_t), void* ctx, mvae_grap
 
 extern "C" {
 
+int mvae_profile_enable(int on) {
+  for (int i = 0; i < g_prof_n; ++i) { cudaEventDestroy(g_prof[i].e0); cudaEventDestroy(g_prof[i].e1); }
+  g_prof_n = 0;
+  g_prof_on = on != 0;
+  return MVAE_OK;
+}
+int mvae_profile_read(int tag, float* total_ms, int* launches) {
+  if (!total_ms || !launches || tag < 0 || tag >= PROF_TAGS) return MVAE_ERR_INVALID;
+  float tot = 0.f; int n = 0;
+  for (int i = 0; i < g_prof_n; ++i) {
+    if (g_prof[i].tag != tag) continue;
+    MVAE_CUDA_CHECK(cudaEventSynchronize(g_prof[i].e1));
+    float ms = 0.f;
+    MVAE_CUDA_CHECK(cudaEventElapsedTime(&ms, g_prof[i].e0, g_prof[i].e1));
+    tot += ms; ++n;
+  }
+  *total_ms = tot; *launches = n;
+  return MVAE_OK;
+}
 long long mvae_launch_count(void) { return g_launches; }
 void mvae_reset_launch_count(void) { g_launches = 0; }
 

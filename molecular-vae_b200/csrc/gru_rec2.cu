@@ -225,7 +225,8 @@ gru_rec2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
           ptx::fence_proxy_async_all();
           if (p.trace && blockIdx.x == 0 && blockIdx.y == 0) p.trace[((size_t)step * NTILES + i) * 12 + 0] = gtime();
           const int row0 = tile * 256 + parity * 128 + qd * A_PART_ROWS;
-          for (int kc = 0; kc < KC; ++kc) {
+          for (int kc0 = 0; kc0 < KC; ++kc0) {
+            const int kc = (p.debug & 128) ? (kc0 + pair * (KC / 8)) % KC : kc0;   // experiment: de-phase the pairs' chunk order
             if (!wait_bar(&empty_bar[s], ph ^ 1, p.err_flag)) goto done;
             if (p.debug & 4) {
               if (leader) ptx::mbar_arrive(&full_bar[s]);   // timing experiment: no operand traffic
@@ -280,7 +281,8 @@ gru_rec2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
               if (!wait_bar(&tempty_bar[i], (uint32_t)((step - 1) & 1), p.err_flag)) goto done;
               ptx::tc_fence_after();
               const uint32_t d_tmem = tmem_base + i * NB;
-              for (int kc = 0; kc < KC; ++kc) {
+              for (int kc0 = 0; kc0 < KC; ++kc0) {
+                const int kc = (p.debug & 128) ? (kc0 + pair * (KC / 8)) % KC : kc0;
                 const bool trm = p.trace && blockIdx.x == 0 && blockIdx.y == 0;
                 if (!wait_bar(&full_bar[s], ph, p.err_flag)) goto done;
                 if (trm && kc == 0) p.trace[((size_t)step * NTILES + i) * 12 + 2] = gtime();
@@ -294,7 +296,7 @@ gru_rec2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
                 for (int k = 0; k < 4; ++k) {
                   const uint64_t adesc = ptx::umma_smem_desc_sw128(a_addr + k * 32, 16, 1024);
                   const uint64_t bdesc = ptx::umma_smem_desc_sw128(b_addr + k * 32, 16, 1024);
-                  umma2_bf16(d_tmem, adesc, bdesc, idesc, (kc > 0 || k > 0) ? 1u : 0u);
+                  umma2_bf16(d_tmem, adesc, bdesc, idesc, (kc0 > 0 || k > 0) ? 1u : 0u);
                 }
                 commit2_mc(&empty_bar[s], (uint16_t)((1u << CL) - 1));      // stage s is free in every CTA of the cluster (for this pair)
                 if (++s == STAGES) { s = 0; ph ^= 1; }

@@ -65,14 +65,18 @@ inline int sg_wgrad(cudaStream_t st, const float* A, long long sam, long long sa
 }
 
 // out[t][b][c] = tbl[ids[b][t]][c] (+ add[b][c]);  rows b >= B are zero.  tbl is [V][W] fp32, out [T][Bp][W] TA.
+// reverse: slab s holds time T-1-s (the processing order of a reverse-direction RNN).
 template <typename TA>
 __global__ void gather_rows_kernel(const float* __restrict__ tbl, int W, const uint8_t* __restrict__ ids, int ids_ld,
-                                   const float* __restrict__ add, int B, int Bp, int T, TA* __restrict__ out) {
+                                   const float* __restrict__ add, int B, int Bp, int T, TA* __restrict__ out,
+                                   int reverse = 0) {
   const long long total = (long long)T * Bp * W;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int c = (int)(i % W);
     const long long rb = i / W;
-    const int b = (int)(rb % Bp), t = (int)(rb / Bp);
+    const int b = (int)(rb % Bp);
+    int t = (int)(rb / Bp);
+    if (reverse) t = T - 1 - t;
     float v = 0.f;
     if (b < B) {
       v = tbl[(long long)ids[(long long)b * ids_ld + t] * W + c];
@@ -84,12 +88,14 @@ __global__ void gather_rows_kernel(const float* __restrict__ tbl, int W, const u
 // OH[t*Bp + b][v] = 1 iff b < B and ids[b][t] == v   (CP columns)
 template <typename TA>
 __global__ void onehot_rows_kernel(const uint8_t* __restrict__ ids, int ids_ld, int B, int Bp, int T, int CP,
-                                   TA* __restrict__ out) {
+                                   TA* __restrict__ out, int reverse = 0) {
   const long long total = (long long)T * Bp * CP;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int c = (int)(i % CP);
     const long long rb = i / CP;
-    const int b = (int)(rb % Bp), t = (int)(rb / Bp);
+    const int b = (int)(rb % Bp);
+    int t = (int)(rb / Bp);
+    if (reverse) t = T - 1 - t;
     out[i] = from_f32<TA>((b < B && ids[(long long)b * ids_ld + t] == c) ? 1.f : 0.f);
   }
 }

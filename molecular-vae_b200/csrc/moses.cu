@@ -25,6 +25,7 @@ namespace {
 
 struct MDims {
   int B, Bp, T, V, CP, Z, Hq, Hd, L, MLP, pad;
+  int bidir, lin, Hin;   // mosesfile.py variant: bidirectional encoder (:21-28), single-Linear heads (:31-32); Hin = Hq*(1+bidir)
   bool bf16;
   float kl_w, rec_w;
 };
@@ -39,6 +40,7 @@ int make_dims(const mvae_moses_desc* d, MDims* o) {
   o->B = d->batch; o->Bp = round_up(d->batch, 256); o->T = d->max_len; o->V = d->vocab; o->CP = 64;
   o->Z = d->d_z; o->Hq = d->q_hidden; o->Hd = d->d_hidden; o->L = d->d_layers; o->MLP = d->mlp_hidden;
   o->pad = d->pad_id; o->bf16 = d->precision == MVAE_PREC_BF16; o->kl_w = d->kl_weight; o->rec_w = d->recon_weight;
+  o->bidir = d->q_bidir ? 1 : 0; o->lin = d->q_linear_heads ? 1 : 0; o->Hin = o->Hq * (1 + o->bidir);
   return MVAE_OK;
 }
 
@@ -50,6 +52,8 @@ struct MWS {
   void *OH;         // [T*Bp][CP] TA one-hot of the tokens
   void *gi;         // [T][Bp][3Hd] TA
   void *hs_enc, *sv_enc, *hs[4], *sv[4], *dG, *dX, *dlogits;
+  void *hs_encr, *sv_encr, *Whh_encr;   // reverse direction of a bidirectional encoder
+  float *bhh_encr, *TBLer, *hlastr, *hcat, *dhcat;
   float *gh, *h32[2], *dh_carry, *logits;
   void *Whh_enc, *Whh[4], *Wih[4], *Wih_nrz[4], *Wfc;
   float *bhh_enc, *bih[4], *bhh[4], *bfc;
@@ -67,8 +71,16 @@ void carve(const MDims& d, void* base, MWS* w) {
   w->mu = c.take<float>(B * d.Z); w->lv = c.take<float>(B * d.Z); w->z = c.take<float>(B * d.Z);
   w->h0 = c.take<float>(Bp * Hd); w->zproj = c.take<float>(B * 3 * Hd); w->dh0 = c.take<float>(Bp * Hd);
   w->dz = c.take<float>(B * d.Z); w->dmu = c.take<float>(B * d.Z); w->dlv = c.take<float>(B * d.Z);
-  w->dr = c.take<float>(B * d.MLP); w->dhenc = c.take<float>(B * Hq); w->dgisum = c.take<float>(Bp * 3 * Hd);
+  w->dr = c.take<float>(B * d.MLP); w->dhenc = c.take<float>(B * d.Hin); w->dgisum = c.take<float>(Bp * 3 * Hd);
   w->dTBL = c.take<float>((size_t)d.CP * 3 * Hd); w->dWT = c.take<float>((size_t)3 * Hd * d.CP);
+  w->hcat = c.take<float>(B * d.Hin); w->dhcat = c.take<float>(B * d.Hin);
+  if (d.bidir) {
+    w->TBLer = c.take<float>((size_t)d.V * 3 * Hq); w->hlastr = c.take<float>(Bp * Hq);
+    w->hs_encr = c.take<uint8_t>((T + 1) * Bp * Hq * es); w->sv_encr = c.take<uint8_t>(T * Bp * 4 * Hq * es);
+    w->Whh_encr = c.take<uint8_t>(3 * Hq * Hq * es); w->bhh_encr = c.take<float>(3 * Hq);
+  } else {
+    w->TBLer = nullptr; w->hlastr = nullptr; w->hs_encr = nullptr; w->sv_encr = nullptr; w->Whh_encr = nullptr; w->bhh_encr = nullptr;
+  }
   w->OH = c.take<uint8_t>(T * Bp * d.CP * es);
   w->gi = c.take<uint8_t>(T * Bp * 3 * Hd * es);
   w->hs_enc = c.take<uint8_t>((T + 1) * Bp * Hq * es); w->sv_enc = c.take<uint8_t>(T * Bp * 4 * Hq * es);
@@ -91,16 +103,28 @@ void carve(const MDims& d, void* base, MWS* w) {
   w->total = (c.off + 255) & ~size_t(255);
 }
 
-// parameter order = oracle.moses_oracle.moses_shapes / state_dict order of mosesvae.VAE (first occurrence of each tensor)
-enum { P_EMB = 0, P_E_WIH, P_E_WHH, P_E_BIH, P_E_BHH, P_MU0W, P_MU0B, P_MU2W, P_MU2B, P_LV0W, P_LV0B, P_LV2W, P_LV2B, P_DEC0 };
-inline int P_WIH(int l) { return P_DEC0 + 4 * l; }
-inline int P_WHH(int l) { return P_DEC0 + 4 * l + 1; }
-inline int P_BIH(int l) { return P_DEC0 + 4 * l + 2; }
-inline int P_BHH(int l) { return P_DEC0 + 4 * l + 3; }
-inline int P_LATW(int L) { return P_DEC0 + 4 * L; }
-inline int P_LATB(int L) { return P_DEC0 + 4 * L + 1; }
-inline int P_FCW(int L) { return P_DEC0 + 4 * L + 2; }
-inline int P_FCB(int L) { return P_DEC0 + 4 * L + 3; }
+// parameter order = state_dict order (first occurrence of each tensor): oracle.moses_oracle.moses_shapes for mosesvae.VAE,
+// oracle.moses_oracle.mosesfile_shapes for the bidirectional / single-Linear-head variant of mosesfile.py
+struct MP {
+  int bidir, lin, L;
+  int emb() const { return 0; }
+  int e_wih(int rev) const { return 1 + 4 * rev; }
+  int e_whh(int rev) const { return 2 + 4 * rev; }
+  int e_bih(int rev) const { return 3 + 4 * rev; }
+  int e_bhh(int rev) const { return 4 + 4 * rev; }
+  int heads() const { return 5 + 4 * bidir; }
+  // MLP heads: mu {0.weight, 0.bias, 2.weight, 2.bias} then logvar {...}; Linear heads: mu {weight, bias}, logvar {weight, bias}
+  int head_w0(int h) const { return heads() + (lin ? 2 : 4) * h; }
+  int dec0() const { return heads() + (lin ? 4 : 8); }
+  int wih(int l) const { return dec0() + 4 * l; }
+  int whh(int l) const { return dec0() + 4 * l + 1; }
+  int bih(int l) const { return dec0() + 4 * l + 2; }
+  int bhh(int l) const { return dec0() + 4 * l + 3; }
+  int latw() const { return dec0() + 4 * L; }
+  int latb() const { return dec0() + 4 * L + 1; }
+  int fcw() const { return dec0() + 4 * L + 2; }
+  int fcb() const { return dec0() + 4 * L + 3; }
+};
 
 // ---------------------------------------------------------------------------------------------------------
 // kernels specific to this path
@@ -208,12 +232,12 @@ __global__ void head_ce_kernel(const float* __restrict__ logits, int CP, int V, 
 }
 // dX_enc[L_b - 1][b][:] = dh_enc[b][:] (the only gradient entering the encoder GRU); dX zeroed beforehand
 template <typename TA>
-__global__ void scatter_final_grad_kernel(const float* __restrict__ dh, const int* __restrict__ lens, int B, int Bp,
+__global__ void scatter_final_grad_kernel(const float* __restrict__ dh, int dh_ld, const int* __restrict__ lens, int B, int Bp,
                                           int H, TA* __restrict__ dX) {
   const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (idx >= (long long)B * H) return;
   const int b = (int)(idx / H), j = (int)(idx - (long long)b * H);
-  dX[((long long)(lens[b] - 1) * Bp + b) * H + j] = from_f32<TA>(dh[idx]);
+  dX[((long long)(lens[b] - 1) * Bp + b) * H + j] = from_f32<TA>(dh[(long long)b * dh_ld + j]);
 }
 // sum over time of the dgi window of dG ([T][Bp][4H], blocks n,r,z) -> fp32 [Bp][3H] in (r,z,n) order
 template <typename TA>
@@ -262,12 +286,28 @@ __global__ void finalize_kernel(const double* __restrict__ kl_sum, const double*
   out[0] = (float)(klw * kl + recw * rec); out[1] = (float)kl; out[2] = (float)rec; out[3] = (float)M[0];
 }
 
+template <typename TA>
+__global__ void final_state_kernel(const TA* __restrict__ hsA, const float* __restrict__ h32, long long n, float* __restrict__ out) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i < n) out[i] = h32 ? h32[i] : to_f32<TA>(hsA[i]);
+}
+// dst[r][c] = src[r][c] for r < rows, c < cols (row strides sld / dld)
+__global__ void copy_rows_kernel(const float* __restrict__ src, int sld, int rows, int cols, float* __restrict__ dst, int dld) {
+  const long long total = (long long)rows * cols;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cols);
+    const long long r = i / cols;
+    dst[r * dld + c] = src[r * sld + c];
+  }
+}
 // ---------------------------------------------------------------------------------------------------------
 // per-step GRU engine (one layer), time-major, optional h0 / final-state capture / dh0
 // ---------------------------------------------------------------------------------------------------------
+// lens + hlast: capture each sequence's state after its last valid step (right-padded forward direction).
+// lead_pad: reverse direction in processing order (padding first); `final32` then receives the state after the last step.
 template <typename TA>
 int gru_fwd(const MDims& d, const MWS& w, cudaStream_t st, const TA* gi, const TA* Whh, const float* bhh, TA* hs, TA* sv,
-            int H, const float* h0, const int* lens, float* hlast) {
+            int H, const float* h0, const int* lens, float* hlast, bool lead_pad = false, float* final32 = nullptr) {
   const int Bp = d.Bp, T = d.T;
   const size_t slab = (size_t)Bp * H;
   if (h0) {
@@ -282,18 +322,28 @@ int gru_fwd(const MDims& d, const MWS& w, cudaStream_t st, const TA* gi, const T
     RC(gemm<TA>(w.err_flag, st, hs + t * slab, H, false, Whh, H, true, w.gh, 3 * H, false, Bp, 3 * H, H, bhh, false, 1));
     simt::gru_gate_fwd_kernel<TA, TA><<<gate_grid, 256, 0, st>>>(
         gi + (size_t)t * Bp * 3 * H, w.gh, d.bf16 ? w.h32[t & 1] : nullptr, hs + t * slab, hs + (t + 1) * slab,
-        d.bf16 ? w.h32[(t + 1) & 1] : nullptr, sv + (size_t)t * Bp * 4 * H, Bp, H, lens, hlast, t, d.B);
+        d.bf16 ? w.h32[(t + 1) & 1] : nullptr, sv + (size_t)t * Bp * 4 * H, Bp, H, lens, hlast, t, d.B, lead_pad ? T : 0);
+    KCHECK();
+  }
+  if (final32) {
+    final_state_kernel<TA><<<ceil_div((int)slab, 256), 256, 0, st>>>(hs + (size_t)T * slab, d.bf16 ? w.h32[T & 1] : nullptr, (long long)slab,
+                                                                     final32);
     KCHECK();
   }
   return MVAE_OK;
 }
 // after the call: dG filled for all t; if dh0_acc != null, dh0_acc += dL/dh0
+// carry_init ([B][carry_ld] fp32, optional): gradient wrt the state after the LAST processed step (reverse encoder direction)
 template <typename TA>
 int gru_bwd(const MDims& d, const MWS& w, cudaStream_t st, const TA* Whh, const TA* hs, const TA* sv, const TA* dX, TA* dG,
-            int H, float* dh0_acc) {
+            int H, float* dh0_acc, const float* carry_init = nullptr, int carry_ld = 0) {
   const int Bp = d.Bp, T = d.T;
   const size_t slab = (size_t)Bp * H;
   RC(memset_async(w.dh_carry, slab * 4, st));
+  if (carry_init) {
+    copy_rows_kernel<<<grid_for((long long)d.B * H), 256, 0, st>>>(carry_init, carry_ld, d.B, H, w.dh_carry, H);
+    KCHECK();
+  }
   const int gate_grid = ceil_div((int)slab, 256);
   for (int t = T - 1; t >= 0; --t) {
     TA* dGt = dG + (size_t)t * Bp * 4 * H;
@@ -317,40 +367,60 @@ int step_t(const MDims& d, const MWS& w, const float* const* P, float* const* G,
   const int B = d.B, Bp = d.Bp, T = d.T, V = d.V, CP = d.CP, Z = d.Z, Hq = d.Hq, Hd = d.Hd, L = d.L, ML = d.MLP;
   const int TB = T * Bp;
   const int IN0 = V + Z;   // decoder layer-0 input width
+  const int Hin = d.Hin;
+  const MP ix{d.bidir, d.lin, L};
   // ---- control + weight preparation
   RC(memset_async(w.err_flag, 4, st)); RC(memset_async(w.kl_sum, 8, st)); RC(memset_async(w.nll_sum, 8, st));
   RC(memset_async(w.M, 4, st));
   count_targets_kernel<<<1, 256, 0, st>>>(lens, B, w.M); KCHECK();
-  simt::pad_gate_matrix_kernel<TA><<<grid_for(3ll * Hq * Hq), 256, 0, st>>>(P[P_E_WHH], Hq, Hq, (TA*)w.Whh_enc, Hq, Hq, 0, 1, 2); KCHECK();
-  simt::pad_gate_vector_kernel<<<ceil_div(3 * Hq, 256), 256, 0, st>>>(P[P_E_BHH], Hq, w.bhh_enc, Hq); KCHECK();
+  simt::pad_gate_matrix_kernel<TA><<<grid_for(3ll * Hq * Hq), 256, 0, st>>>(P[ix.e_whh(0)], Hq, Hq, (TA*)w.Whh_enc, Hq, Hq, 0, 1, 2); KCHECK();
+  simt::pad_gate_vector_kernel<<<ceil_div(3 * Hq, 256), 256, 0, st>>>(P[ix.e_bhh(0)], Hq, w.bhh_enc, Hq); KCHECK();
+  if (d.bidir) {
+    simt::pad_gate_matrix_kernel<TA><<<grid_for(3ll * Hq * Hq), 256, 0, st>>>(P[ix.e_whh(1)], Hq, Hq, (TA*)w.Whh_encr, Hq, Hq, 0, 1, 2); KCHECK();
+    simt::pad_gate_vector_kernel<<<ceil_div(3 * Hq, 256), 256, 0, st>>>(P[ix.e_bhh(1)], Hq, w.bhh_encr, Hq); KCHECK();
+  }
   for (int l = 0; l < L; ++l) {
-    simt::pad_gate_matrix_kernel<TA><<<grid_for(3ll * Hd * Hd), 256, 0, st>>>(P[P_WHH(l)], Hd, Hd, (TA*)w.Whh[l], Hd, Hd, 0, 1, 2); KCHECK();
-    simt::pad_gate_vector_kernel<<<ceil_div(3 * Hd, 256), 256, 0, st>>>(P[P_BHH(l)], Hd, w.bhh[l], Hd); KCHECK();
+    simt::pad_gate_matrix_kernel<TA><<<grid_for(3ll * Hd * Hd), 256, 0, st>>>(P[ix.whh(l)], Hd, Hd, (TA*)w.Whh[l], Hd, Hd, 0, 1, 2); KCHECK();
+    simt::pad_gate_vector_kernel<<<ceil_div(3 * Hd, 256), 256, 0, st>>>(P[ix.bhh(l)], Hd, w.bhh[l], Hd); KCHECK();
     if (l >= 1) {
-      simt::pad_gate_matrix_kernel<TA><<<grid_for(3ll * Hd * Hd), 256, 0, st>>>(P[P_WIH(l)], Hd, Hd, (TA*)w.Wih[l], Hd, Hd, 0, 1, 2); KCHECK();
-      simt::pad_gate_matrix_kernel<TA><<<grid_for(3ll * Hd * Hd), 256, 0, st>>>(P[P_WIH(l)], Hd, Hd, (TA*)w.Wih_nrz[l], Hd, Hd, 2, 0, 1); KCHECK();
-      simt::pad_gate_vector_kernel<<<ceil_div(3 * Hd, 256), 256, 0, st>>>(P[P_BIH(l)], Hd, w.bih[l], Hd); KCHECK();
+      simt::pad_gate_matrix_kernel<TA><<<grid_for(3ll * Hd * Hd), 256, 0, st>>>(P[ix.wih(l)], Hd, Hd, (TA*)w.Wih[l], Hd, Hd, 0, 1, 2); KCHECK();
+      simt::pad_gate_matrix_kernel<TA><<<grid_for(3ll * Hd * Hd), 256, 0, st>>>(P[ix.wih(l)], Hd, Hd, (TA*)w.Wih_nrz[l], Hd, Hd, 2, 0, 1); KCHECK();
+      simt::pad_gate_vector_kernel<<<ceil_div(3 * Hd, 256), 256, 0, st>>>(P[ix.bih(l)], Hd, w.bih[l], Hd); KCHECK();
     }
   }
-  simt::pad_matrix_kernel<TA><<<grid_for((long long)CP * Hd), 256, 0, st>>>(P[P_FCW(L)], V, Hd, (TA*)w.Wfc, CP, Hd); KCHECK();
-  simt::pad_matrix_kernel<float><<<1, 64, 0, st>>>(P[P_FCB(L)], 1, V, w.bfc, 1, CP); KCHECK();
+  simt::pad_matrix_kernel<TA><<<grid_for((long long)CP * Hd), 256, 0, st>>>(P[ix.fcw()], V, Hd, (TA*)w.Wfc, CP, Hd); KCHECK();
+  simt::pad_matrix_kernel<float><<<1, 64, 0, st>>>(P[ix.fcb()], 1, V, w.bfc, 1, CP); KCHECK();
 
   // ---- encoder: table look-up projection, GRU, final state, MLP heads, reparametrise + KL
-  RC(sg(st, P[P_EMB], V, 1, P[P_E_WIH], 1, V, w.TBLe, 3 * Hq, V, 3 * Hq, V, P[P_E_BIH], simt::ACT_NONE, 0));
+  RC(sg(st, P[ix.emb()], V, 1, P[ix.e_wih(0)], 1, V, w.TBLe, 3 * Hq, V, 3 * Hq, V, P[ix.e_bih(0)], simt::ACT_NONE, 0));
   gather_rows_kernel<TA><<<grid_for((long long)TB * 3 * Hq), 256, 0, st>>>(w.TBLe, 3 * Hq, ids, T, nullptr, B, Bp, T, (TA*)w.gi); KCHECK();
   RC(memset_async(w.hlast, (size_t)Bp * Hq * 4, st));
   RC(gru_fwd<TA>(d, w, st, (const TA*)w.gi, (const TA*)w.Whh_enc, w.bhh_enc, (TA*)w.hs_enc, (TA*)w.sv_enc, Hq, nullptr, lens, w.hlast));
-  RC(sg(st, w.hlast, Hq, 1, P[P_MU0W], 1, Hq, w.rmu, ML, B, ML, Hq, P[P_MU0B], simt::ACT_RELU, 0));
-  RC(sg(st, w.rmu, ML, 1, P[P_MU2W], 1, ML, w.mu, Z, B, Z, ML, P[P_MU2B], simt::ACT_NONE, 0));
-  RC(sg(st, w.hlast, Hq, 1, P[P_LV0W], 1, Hq, w.rlv, ML, B, ML, Hq, P[P_LV0B], simt::ACT_RELU, 0));
-  RC(sg(st, w.rlv, ML, 1, P[P_LV2W], 1, ML, w.lv, Z, B, Z, ML, P[P_LV2B], simt::ACT_NONE, 0));
+  copy_rows_kernel<<<grid_for((long long)B * Hq), 256, 0, st>>>(w.hlast, Hq, B, Hq, w.hcat, Hin); KCHECK();
+  if (d.bidir) {
+    // reverse direction (mosesfile.py:21-28,112-116): same engine over the time-reversed token stream, padding first
+    RC(sg(st, P[ix.emb()], V, 1, P[ix.e_wih(1)], 1, V, w.TBLer, 3 * Hq, V, 3 * Hq, V, P[ix.e_bih(1)], simt::ACT_NONE, 0));
+    gather_rows_kernel<TA><<<grid_for((long long)TB * 3 * Hq), 256, 0, st>>>(w.TBLer, 3 * Hq, ids, T, nullptr, B, Bp, T, (TA*)w.gi, 1); KCHECK();
+    RC(gru_fwd<TA>(d, w, st, (const TA*)w.gi, (const TA*)w.Whh_encr, w.bhh_encr, (TA*)w.hs_encr, (TA*)w.sv_encr, Hq, nullptr, lens,
+                   nullptr, true, w.hlastr));
+    copy_rows_kernel<<<grid_for((long long)B * Hq), 256, 0, st>>>(w.hlastr, Hq, B, Hq, w.hcat + Hq, Hin); KCHECK();
+  }
+  if (d.lin) {   // mosesfile.py:31-32,118: single Linear heads on cat(h_fwd, h_bwd)
+    RC(sg(st, w.hcat, Hin, 1, P[ix.head_w0(0)], 1, Hin, w.mu, Z, B, Z, Hin, P[ix.head_w0(0) + 1], simt::ACT_NONE, 0));
+    RC(sg(st, w.hcat, Hin, 1, P[ix.head_w0(1)], 1, Hin, w.lv, Z, B, Z, Hin, P[ix.head_w0(1) + 1], simt::ACT_NONE, 0));
+  } else {       // mosesvae.py:68-69: Linear -> ReLU -> Linear
+    RC(sg(st, w.hcat, Hin, 1, P[ix.head_w0(0)], 1, Hin, w.rmu, ML, B, ML, Hin, P[ix.head_w0(0) + 1], simt::ACT_RELU, 0));
+    RC(sg(st, w.rmu, ML, 1, P[ix.head_w0(0) + 2], 1, ML, w.mu, Z, B, Z, ML, P[ix.head_w0(0) + 3], simt::ACT_NONE, 0));
+    RC(sg(st, w.hcat, Hin, 1, P[ix.head_w0(1)], 1, Hin, w.rlv, ML, B, ML, Hin, P[ix.head_w0(1) + 1], simt::ACT_RELU, 0));
+    RC(sg(st, w.rlv, ML, 1, P[ix.head_w0(1) + 2], 1, ML, w.lv, Z, B, Z, ML, P[ix.head_w0(1) + 3], simt::ACT_NONE, 0));
+  }
   reparam_kl_std_kernel<<<grid_for((long long)B * Z, 256, 592), 256, 0, st>>>(w.mu, w.lv, eps, (long long)B * Z, w.z, w.kl_sum); KCHECK();
 
   // ---- decoder: h0, layer-0 projection = table + per-molecule z part, GRU stack, head
   RC(memset_async(w.h0, (size_t)Bp * Hd * 4, st));
-  RC(sg(st, w.z, Z, 1, P[P_LATW(L)], 1, Z, w.h0, Hd, B, Hd, Z, P[P_LATB(L)], simt::ACT_NONE, 0));
-  RC(sg(st, P[P_EMB], V, 1, P[P_WIH(0)], 1, IN0, w.TBLd, 3 * Hd, V, 3 * Hd, V, nullptr, simt::ACT_NONE, 0));
-  RC(sg(st, w.z, Z, 1, P[P_WIH(0)] + V, 1, IN0, w.zproj, 3 * Hd, B, 3 * Hd, Z, P[P_BIH(0)], simt::ACT_NONE, 0));
+  RC(sg(st, w.z, Z, 1, P[ix.latw()], 1, Z, w.h0, Hd, B, Hd, Z, P[ix.latb()], simt::ACT_NONE, 0));
+  RC(sg(st, P[ix.emb()], V, 1, P[ix.wih(0)], 1, IN0, w.TBLd, 3 * Hd, V, 3 * Hd, V, nullptr, simt::ACT_NONE, 0));
+  RC(sg(st, w.z, Z, 1, P[ix.wih(0)] + V, 1, IN0, w.zproj, 3 * Hd, B, 3 * Hd, Z, P[ix.bih(0)], simt::ACT_NONE, 0));
   gather_rows_kernel<TA><<<grid_for((long long)TB * 3 * Hd), 256, 0, st>>>(w.TBLd, 3 * Hd, ids, T, w.zproj, B, Bp, T, (TA*)w.gi); KCHECK();
   for (int l = 0; l < L; ++l) {
     if (l >= 1)
@@ -377,10 +447,10 @@ int step_t(const MDims& d, const MWS& w, const float* const* P, float* const* G,
   RC(memset_async(w.dWfc_p, (size_t)CP * Hd * 4, st));
   RC(gemm<TA>(w.err_flag, st, dlog, CP, true, (const TA*)w.hs[L - 1] + (size_t)Bp * Hd, Hd, false, w.dWfc_p, Hd, false, CP, Hd, TB,
               nullptr, true, d.bf16 ? 148 : 64, 256));
-  simt::unpad_matrix_kernel<<<grid_for((long long)V * Hd), 256, 0, st>>>(w.dWfc_p, Hd, G[P_FCW(L)], V, Hd); KCHECK();
+  simt::unpad_matrix_kernel<<<grid_for((long long)V * Hd), 256, 0, st>>>(w.dWfc_p, Hd, G[ix.fcw()], V, Hd); KCHECK();
   RC(memset_async(w.csum, (size_t)4 * Hd * 4, st));
   RC(simt::colsum<TA>(st, dlog, TB, CP, CP, w.csum)); mvae_count_launches(1);
-  simt::pad_matrix_kernel<float><<<1, 64, 0, st>>>(w.csum, 1, V, G[P_FCB(L)], 1, V); KCHECK();
+  simt::pad_matrix_kernel<float><<<1, 64, 0, st>>>(w.csum, 1, V, G[ix.fcb()], 1, V); KCHECK();
   // decoder GRU stack
   RC(memset_async(w.dh0, (size_t)Bp * Hd * 4, st));
   for (int l = L - 1; l >= 0; --l) {
@@ -389,15 +459,15 @@ int step_t(const MDims& d, const MWS& w, const float* const* P, float* const* G,
     RC(gru_bwd<TA>(d, w, st, (const TA*)w.Whh[l], hs, (const TA*)w.sv[l], (const TA*)w.dX, dG, Hd, w.dh0));
     RC(memset_async(w.dW_p, (size_t)3 * Hd * Hd * 4, st));
     RC(gemm<TA>(w.err_flag, st, dG + Hd, 4 * Hd, true, hs, Hd, false, w.dW_p, Hd, false, 3 * Hd, Hd, TB, nullptr, true, wsplits, 256));
-    simt::unpad_gate_matrix_kernel<<<grid_for(3ll * Hd * Hd), 256, 0, st>>>(w.dW_p, Hd, Hd, G[P_WHH(l)], Hd, Hd, 0, 1, 2); KCHECK();
+    simt::unpad_gate_matrix_kernel<<<grid_for(3ll * Hd * Hd), 256, 0, st>>>(w.dW_p, Hd, Hd, G[ix.whh(l)], Hd, Hd, 0, 1, 2); KCHECK();
     RC(memset_async(w.csum, (size_t)4 * Hd * 4, st));
     RC(simt::colsum<TA>(st, dG, TB, 4 * Hd, 4 * Hd, w.csum)); mvae_count_launches(1);
-    gate_bias_grads_kernel<<<ceil_div(3 * Hd, 256), 256, 0, st>>>(w.csum, Hd, G[P_BIH(l)], G[P_BHH(l)]); KCHECK();
+    gate_bias_grads_kernel<<<ceil_div(3 * Hd, 256), 256, 0, st>>>(w.csum, Hd, G[ix.bih(l)], G[ix.bhh(l)]); KCHECK();
     if (l >= 1) {
       const TA* X = (const TA*)w.hs[l - 1] + (size_t)Bp * Hd;
       RC(memset_async(w.dW_p, (size_t)3 * Hd * Hd * 4, st));
       RC(gemm<TA>(w.err_flag, st, dG, 4 * Hd, true, X, Hd, false, w.dW_p, Hd, false, 3 * Hd, Hd, TB, nullptr, true, wsplits, 256));
-      simt::unpad_gate_matrix_kernel<<<grid_for(3ll * Hd * Hd), 256, 0, st>>>(w.dW_p, Hd, Hd, G[P_WIH(l)], Hd, Hd, 2, 0, 1); KCHECK();
+      simt::unpad_gate_matrix_kernel<<<grid_for(3ll * Hd * Hd), 256, 0, st>>>(w.dW_p, Hd, Hd, G[ix.wih(l)], Hd, Hd, 2, 0, 1); KCHECK();
       RC(gemm<TA>(w.err_flag, st, dG, 4 * Hd, false, (const TA*)w.Wih_nrz[l], Hd, false, w.dX, Hd, true, TB, Hd, 3 * Hd, nullptr, false, 1));
     } else {
       // layer 0: table gradient (tensor-core GEMM onehot^T * dgi) and the per-molecule z part (time sum)
@@ -410,58 +480,73 @@ int step_t(const MDims& d, const MWS& w, const float* const* P, float* const* G,
   // decoder layer-0 input weights: W_ih[:, :V] through the table, W_ih[:, V:] through z
   tbl_grad_to_rzn_T_kernel<<<(unsigned)ceil_div64(3ll * Hd * V, 256), 256, 0, st>>>(w.dTBL, Hd, V, w.dWT); KCHECK();
   //   dW_ih[:, :V] = dTBL_rzn^T(3Hd x V) * E (V x V)
-  RC(sg(st, w.dWT, V, 1, P[P_EMB], V, 1, G[P_WIH(0)], IN0, 3 * Hd, V, V, nullptr, simt::ACT_NONE, 0));
+  RC(sg(st, w.dWT, V, 1, P[ix.emb()], V, 1, G[ix.wih(0)], IN0, 3 * Hd, V, V, nullptr, simt::ACT_NONE, 0));
   //   dE = dTBL_rzn (V x 3Hd) * W_ih[:, :V] (3Hd x V)
-  RC(sg(st, w.dWT, 1, V, P[P_WIH(0)], IN0, 1, G[P_EMB], V, V, V, 3 * Hd, nullptr, simt::ACT_NONE, 0));
+  RC(sg(st, w.dWT, 1, V, P[ix.wih(0)], IN0, 1, G[ix.emb()], V, V, V, 3 * Hd, nullptr, simt::ACT_NONE, 0));
   //   dW_ih[:, V:] = dgisum^T * z ; dz = dgisum * W_ih[:, V:]
-  RC(sg_wgrad(st, w.dgisum, 1, 3 * Hd, w.z, Z, 1, G[P_WIH(0)] + V, IN0, 3 * Hd, Z, B));
-  RC(sg(st, w.dgisum, 3 * Hd, 1, P[P_WIH(0)] + V, IN0, 1, w.dz, Z, B, Z, 3 * Hd, nullptr, simt::ACT_NONE, 0));
+  RC(sg_wgrad(st, w.dgisum, 1, 3 * Hd, w.z, Z, 1, G[ix.wih(0)] + V, IN0, 3 * Hd, Z, B));
+  RC(sg(st, w.dgisum, 3 * Hd, 1, P[ix.wih(0)] + V, IN0, 1, w.dz, Z, B, Z, 3 * Hd, nullptr, simt::ACT_NONE, 0));
   // decoder_lat: h0 = z W^T + b, shared by all layers (dh0 already summed over layers)
-  RC(sg_wgrad(st, w.dh0, 1, Hd, w.z, Z, 1, G[P_LATW(L)], Z, Hd, Z, B));
-  RC(memset_async(G[P_LATB(L)], (size_t)Hd * 4, st));
-  RC(simt::colsum<float>(st, w.dh0, B, Hd, Hd, G[P_LATB(L)])); mvae_count_launches(1);
-  RC(sg(st, w.dh0, Hd, 1, P[P_LATW(L)], Z, 1, w.dz, Z, B, Z, Hd, nullptr, simt::ACT_NONE, 1));
+  RC(sg_wgrad(st, w.dh0, 1, Hd, w.z, Z, 1, G[ix.latw()], Z, Hd, Z, B));
+  RC(memset_async(G[ix.latb()], (size_t)Hd * 4, st));
+  RC(simt::colsum<float>(st, w.dh0, B, Hd, Hd, G[ix.latb()])); mvae_count_launches(1);
+  RC(sg(st, w.dh0, Hd, 1, P[ix.latw()], Z, 1, w.dz, Z, B, Z, Hd, nullptr, simt::ACT_NONE, 1));
   // reparametrisation + KL
   const long long nBZ = (long long)B * Z;
   reparam_kl_std_bwd_kernel<<<grid_for(nBZ), 256, 0, st>>>(w.mu, w.lv, eps, w.dz, d.kl_w / (float)B, nBZ, w.dmu, w.dlv); KCHECK();
-  // MLP heads (mu then logvar), accumulating into dh_enc
+  // heads (mu then logvar), accumulating into dhenc = dL/d cat(h_fwd, h_bwd)
   for (int head = 0; head < 2; ++head) {
     const float* dout = head == 0 ? w.dmu : w.dlv;
+    const int W0 = ix.head_w0(head);
+    if (d.lin) {
+      RC(sg_wgrad(st, dout, 1, Z, w.hcat, Hin, 1, G[W0], Hin, Z, Hin, B));
+      RC(memset_async(G[W0 + 1], (size_t)Z * 4, st));
+      RC(simt::colsum<float>(st, dout, B, Z, Z, G[W0 + 1])); mvae_count_launches(1);
+      RC(sg(st, dout, Z, 1, P[W0], Hin, 1, w.dhenc, Hin, B, Hin, Z, nullptr, simt::ACT_NONE, head));
+      continue;
+    }
     const float* r = head == 0 ? w.rmu : w.rlv;
-    const int W0 = head == 0 ? P_MU0W : P_LV0W, B0 = W0 + 1, W2 = W0 + 2, B2 = W0 + 3;
+    const int B0 = W0 + 1, W2 = W0 + 2, B2 = W0 + 3;
     RC(sg_wgrad(st, dout, 1, Z, r, ML, 1, G[W2], ML, Z, ML, B));
     RC(memset_async(G[B2], (size_t)Z * 4, st));
     RC(simt::colsum<float>(st, dout, B, Z, Z, G[B2])); mvae_count_launches(1);
     RC(sg(st, dout, Z, 1, P[W2], ML, 1, w.dr, ML, B, ML, Z, nullptr, simt::ACT_NONE, 0));
     relu_bwd_kernel<<<grid_for((long long)B * ML), 256, 0, st>>>(r, w.dr, (long long)B * ML); KCHECK();
-    RC(sg_wgrad(st, w.dr, 1, ML, w.hlast, Hq, 1, G[W0], Hq, ML, Hq, B));
+    RC(sg_wgrad(st, w.dr, 1, ML, w.hcat, Hin, 1, G[W0], Hin, ML, Hin, B));
     RC(memset_async(G[B0], (size_t)ML * 4, st));
     RC(simt::colsum<float>(st, w.dr, B, ML, ML, G[B0])); mvae_count_launches(1);
-    RC(sg(st, w.dr, ML, 1, P[W0], Hq, 1, w.dhenc, Hq, B, Hq, ML, nullptr, simt::ACT_NONE, head));
+    RC(sg(st, w.dr, ML, 1, P[W0], Hin, 1, w.dhenc, Hin, B, Hin, ML, nullptr, simt::ACT_NONE, head));
   }
-  // encoder GRU: the gradient enters only at each sequence's last step
-  {
+  // encoder GRU(s): the gradient enters only at each direction's final state
+  for (int rev = 0; rev <= d.bidir; ++rev) {
     TA* dXe = (TA*)w.dX;
     TA* dG = (TA*)w.dG;
+    const TA* Whh = (const TA*)(rev ? w.Whh_encr : w.Whh_enc);
+    const TA* hs = (const TA*)(rev ? w.hs_encr : w.hs_enc);
+    const TA* sv = (const TA*)(rev ? w.sv_encr : w.sv_enc);
     RC(memset_async(dXe, (size_t)TB * Hq * sizeof(TA), st));
-    scatter_final_grad_kernel<TA><<<(unsigned)ceil_div64((long long)B * Hq, 256), 256, 0, st>>>(w.dhenc, lens, B, Bp, Hq, dXe); KCHECK();
-    RC(gru_bwd<TA>(d, w, st, (const TA*)w.Whh_enc, (const TA*)w.hs_enc, (const TA*)w.sv_enc, dXe, dG, Hq, nullptr));
+    if (!rev) {
+      scatter_final_grad_kernel<TA><<<(unsigned)ceil_div64((long long)B * Hq, 256), 256, 0, st>>>(w.dhenc, Hin, lens, B, Bp, Hq, dXe); KCHECK();
+      RC(gru_bwd<TA>(d, w, st, Whh, hs, sv, dXe, dG, Hq, nullptr));
+    } else {
+      RC(gru_bwd<TA>(d, w, st, Whh, hs, sv, dXe, dG, Hq, nullptr, w.dhenc + Hq, Hin));
+    }
     RC(memset_async(w.dW_p, (size_t)3 * Hq * Hq * 4, st));
-    RC(gemm<TA>(w.err_flag, st, dG + Hq, 4 * Hq, true, (const TA*)w.hs_enc, Hq, false, w.dW_p, Hq, false, 3 * Hq, Hq, TB, nullptr, true,
-                wsplits, 256));
-    simt::unpad_gate_matrix_kernel<<<grid_for(3ll * Hq * Hq), 256, 0, st>>>(w.dW_p, Hq, Hq, G[P_E_WHH], Hq, Hq, 0, 1, 2); KCHECK();
+    RC(gemm<TA>(w.err_flag, st, dG + Hq, 4 * Hq, true, hs, Hq, false, w.dW_p, Hq, false, 3 * Hq, Hq, TB, nullptr, true, wsplits, 256));
+    simt::unpad_gate_matrix_kernel<<<grid_for(3ll * Hq * Hq), 256, 0, st>>>(w.dW_p, Hq, Hq, G[ix.e_whh(rev)], Hq, Hq, 0, 1, 2); KCHECK();
     RC(memset_async(w.csum, (size_t)4 * Hd * 4, st));
     RC(simt::colsum<TA>(st, dG, TB, 4 * Hq, 4 * Hq, w.csum)); mvae_count_launches(1);
-    gate_bias_grads_kernel<<<ceil_div(3 * Hq, 256), 256, 0, st>>>(w.csum, Hq, G[P_E_BIH], G[P_E_BHH]); KCHECK();
+    gate_bias_grads_kernel<<<ceil_div(3 * Hq, 256), 256, 0, st>>>(w.csum, Hq, G[ix.e_bih(rev)], G[ix.e_bhh(rev)]); KCHECK();
+    if (rev) { onehot_rows_kernel<TA><<<grid_for((long long)TB * CP), 256, 0, st>>>(ids, T, B, Bp, T, CP, (TA*)w.OH, 1); KCHECK(); }
     RC(memset_async(w.dTBL, (size_t)CP * 3 * Hd * 4, st));
     RC(gemm<TA>(w.err_flag, st, (const TA*)w.OH, CP, true, dG, 4 * Hq, false, w.dTBL, 3 * Hq, false, CP, 3 * Hq, TB, nullptr, true,
                 d.bf16 ? 24 : 64, 256));
     tbl_grad_to_rzn_T_kernel<<<(unsigned)ceil_div64(3ll * Hq * V, 256), 256, 0, st>>>(w.dTBL, Hq, V, w.dWT); KCHECK();
-    RC(sg(st, w.dWT, V, 1, P[P_EMB], V, 1, G[P_E_WIH], V, 3 * Hq, V, V, nullptr, simt::ACT_NONE, 0));
-    RC(sg(st, w.dWT, 1, V, P[P_E_WIH], V, 1, G[P_EMB], V, V, V, 3 * Hq, nullptr, simt::ACT_NONE, 1));   // accumulate onto the decoder part
+    RC(sg(st, w.dWT, V, 1, P[ix.emb()], V, 1, G[ix.e_wih(rev)], V, 3 * Hq, V, V, nullptr, simt::ACT_NONE, 0));
+    RC(sg(st, w.dWT, 1, V, P[ix.e_wih(rev)], V, 1, G[ix.emb()], V, V, V, 3 * Hq, nullptr, simt::ACT_NONE, 1));   // accumulate onto the decoder part
   }
   if (d.pad >= 0 && d.pad < V) {   // nn.Embedding(padding_idx = pad): the pad row receives no gradient
-    zero_row_kernel<<<1, 64, 0, st>>>(G[P_EMB], d.pad, V); KCHECK();
+    zero_row_kernel<<<1, 64, 0, st>>>(G[ix.emb()], d.pad, V); KCHECK();
   }
   return MVAE_OK;
 }
@@ -527,23 +612,24 @@ int sample_t(const MDims& d, const MWS& w, const float* const* P, const float* z
              unsigned long long seed, uint8_t* ids_out, int* len_out, uint8_t* w_cur, uint8_t* done, cudaStream_t st) {
   const int B = d.B, Bp = d.Bp, V = d.V, CP = d.CP, Z = d.Z, Hd = d.Hd, L = d.L, max_len = d.T;
   const int IN0 = V + Z;
+  const MP ix{d.bidir, d.lin, L};
   const size_t slab = (size_t)Bp * Hd;
   RC(memset_async(w.err_flag, 4, st));
   for (int l = 0; l < L; ++l) {
-    simt::pad_gate_matrix_kernel<TA><<<grid_for(3ll * Hd * Hd), 256, 0, st>>>(P[P_WHH(l)], Hd, Hd, (TA*)w.Whh[l], Hd, Hd, 0, 1, 2); KCHECK();
-    simt::pad_gate_vector_kernel<<<ceil_div(3 * Hd, 256), 256, 0, st>>>(P[P_BHH(l)], Hd, w.bhh[l], Hd); KCHECK();
+    simt::pad_gate_matrix_kernel<TA><<<grid_for(3ll * Hd * Hd), 256, 0, st>>>(P[ix.whh(l)], Hd, Hd, (TA*)w.Whh[l], Hd, Hd, 0, 1, 2); KCHECK();
+    simt::pad_gate_vector_kernel<<<ceil_div(3 * Hd, 256), 256, 0, st>>>(P[ix.bhh(l)], Hd, w.bhh[l], Hd); KCHECK();
     if (l >= 1) {
-      simt::pad_gate_matrix_kernel<TA><<<grid_for(3ll * Hd * Hd), 256, 0, st>>>(P[P_WIH(l)], Hd, Hd, (TA*)w.Wih[l], Hd, Hd, 0, 1, 2); KCHECK();
-      simt::pad_gate_vector_kernel<<<ceil_div(3 * Hd, 256), 256, 0, st>>>(P[P_BIH(l)], Hd, w.bih[l], Hd); KCHECK();
+      simt::pad_gate_matrix_kernel<TA><<<grid_for(3ll * Hd * Hd), 256, 0, st>>>(P[ix.wih(l)], Hd, Hd, (TA*)w.Wih[l], Hd, Hd, 0, 1, 2); KCHECK();
+      simt::pad_gate_vector_kernel<<<ceil_div(3 * Hd, 256), 256, 0, st>>>(P[ix.bih(l)], Hd, w.bih[l], Hd); KCHECK();
     }
   }
-  simt::pad_matrix_kernel<TA><<<grid_for((long long)CP * Hd), 256, 0, st>>>(P[P_FCW(L)], V, Hd, (TA*)w.Wfc, CP, Hd); KCHECK();
-  simt::pad_matrix_kernel<float><<<1, 64, 0, st>>>(P[P_FCB(L)], 1, V, w.bfc, 1, CP); KCHECK();
+  simt::pad_matrix_kernel<TA><<<grid_for((long long)CP * Hd), 256, 0, st>>>(P[ix.fcw()], V, Hd, (TA*)w.Wfc, CP, Hd); KCHECK();
+  simt::pad_matrix_kernel<float><<<1, 64, 0, st>>>(P[ix.fcb()], 1, V, w.bfc, 1, CP); KCHECK();
   // h0 (mosesvae.py:229-230), token table and the per-sequence z part of the layer-0 projection
   RC(memset_async(w.h0, (size_t)Bp * Hd * 4, st));
-  RC(sg(st, z, Z, 1, P[P_LATW(L)], 1, Z, w.h0, Hd, B, Hd, Z, P[P_LATB(L)], simt::ACT_NONE, 0));
-  RC(sg(st, P[P_EMB], V, 1, P[P_WIH(0)], 1, IN0, w.TBLd, 3 * Hd, V, 3 * Hd, V, nullptr, simt::ACT_NONE, 0));
-  RC(sg(st, z, Z, 1, P[P_WIH(0)] + V, 1, IN0, w.zproj, 3 * Hd, B, 3 * Hd, Z, P[P_BIH(0)], simt::ACT_NONE, 0));
+  RC(sg(st, z, Z, 1, P[ix.latw()], 1, Z, w.h0, Hd, B, Hd, Z, P[ix.latb()], simt::ACT_NONE, 0));
+  RC(sg(st, P[ix.emb()], V, 1, P[ix.wih(0)], 1, IN0, w.TBLd, 3 * Hd, V, 3 * Hd, V, nullptr, simt::ACT_NONE, 0));
+  RC(sg(st, z, Z, 1, P[ix.wih(0)] + V, 1, IN0, w.zproj, 3 * Hd, B, 3 * Hd, Z, P[ix.bih(0)], simt::ACT_NONE, 0));
   // per layer two hidden-state slabs (ping-pong by step parity): hs[l] slab (step & 1) holds h before the step
   for (int l = 0; l < L; ++l) {
     init_h0_kernel<TA><<<ceil_div((int)slab, 256), 256, 0, st>>>(w.h0, B, Bp, Hd, (TA*)w.hs[l] + slab, nullptr); KCHECK();

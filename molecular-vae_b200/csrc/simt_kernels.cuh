@@ -451,7 +451,7 @@ __global__ void gru_gate_fwd_kernel(const TG* __restrict__ gi, const float* __re
                                     const float* __restrict__ hprev32, const TA* __restrict__ hprevA,
                                     TA* __restrict__ hnextA, float* __restrict__ hnext32, TA* __restrict__ sv, int Bp,
                                     int Hp, const int* __restrict__ lens = nullptr, float* __restrict__ hlast = nullptr,
-                                    int t = 0, int B = 0) {
+                                    int t = 0, int B = 0, int lead_pad_T = 0) {
   const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (idx >= (long long)Bp * Hp) return;
   const int b = (int)(idx / Hp), j = (int)(idx - (long long)b * Hp);
@@ -462,11 +462,24 @@ __global__ void gru_gate_fwd_kernel(const TG* __restrict__ gi, const float* __re
   const float z = sigmoid_acc(iz + hz);
   const float n = tanhf(fmaf(r, hn, in_));
   const float hp = hprev32 ? hprev32[idx] : to_f32<TA>(hprevA[idx]);
+  // reverse direction of a packed bidirectional GRU (mosesfile.py:21-28): the sequence is walked from its last token, so
+  // in processing order its padding comes FIRST (lead_pad_T - lens[b] steps): the state stays at h0 there and the saved
+  // gates (r=0, z=1, n=0) make the BPTT kernel emit exact zeros for these steps.
+  if (lead_pad_T > 0 && b < B && t < lead_pad_T - lens[b]) {
+    hnextA[idx] = from_f32<TA>(hp);
+    if (hnext32) hnext32[idx] = hp;
+    if (sv) {
+      const long long s4 = (long long)b * 4 * Hp + j;
+      sv[s4] = from_f32<TA>(0.f); sv[s4 + Hp] = from_f32<TA>(1.f); sv[s4 + 2 * Hp] = from_f32<TA>(0.f);
+      sv[s4 + 3 * Hp] = from_f32<TA>(0.f);
+    }
+    return;
+  }
   const float h = fmaf(z, hp - n, n);  // (1-z) n + z h
   hnextA[idx] = from_f32<TA>(h);
   if (hnext32) hnext32[idx] = h;
   // packed-sequence final state (mosesvae.py:153-156): sequence b ends after lens[b] steps
-  if (lens && b < B && t + 1 == lens[b]) hlast[idx] = h;
+  if (hlast && lens && b < B && t + 1 == lens[b]) hlast[idx] = h;
   if (sv) {
     const long long s4 = (long long)b * 4 * Hp + j;
     sv[s4] = from_f32<TA>(r);

@@ -104,7 +104,8 @@ class VAE(nn.Module):
         c = self.cfg
         prec = {"fp32": _lib.PREC_FP32, "bf16": _lib.PREC_BF16}[self.precision]
         d = MosesDesc(B, T, c["vocab"], c["d_z"], c["q_hidden"], c["d_hidden"], c["d_layers"], c["mlp_hidden"],
-                      int(self.pad), prec, float(kl_weight), float(recon_weight))
+                      int(self.pad), prec, float(kl_weight), float(recon_weight), int(c.get("q_bidir", 0)),
+                      int(c.get("q_linear_heads", 0)))
         need = lib.mvae_moses_workspace_bytes(ctypes.byref(d))
         if need == 0:
             raise ValueError("invalid MOSES VAE description")
@@ -171,7 +172,7 @@ class VAE(nn.Module):
         B, c = z.shape[0], self.cfg
         prec = {"fp32": _lib.PREC_FP32, "bf16": _lib.PREC_BF16}[self.precision]
         d = MosesDesc(B, int(max_len), c["vocab"], c["d_z"], c["q_hidden"], c["d_hidden"], c["d_layers"], c["mlp_hidden"],
-                      int(self.pad), prec, 1.0, 1.0)
+                      int(self.pad), prec, 1.0, 1.0, int(c.get("q_bidir", 0)), int(c.get("q_linear_heads", 0)))
         need = lib.mvae_moses_workspace_bytes(ctypes.byref(d))
         dev = z.device
         if self._ws is None or self._ws.numel() < need + 256 or self._ws.device != dev:

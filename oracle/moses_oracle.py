@@ -249,3 +249,140 @@ def moses_sample_greedy(P, z, bos, eos, pad, max_len=100, d_layers=3):
         end[new_eos] = i + 1
         done |= new_eos
     return x, end, y
+
+
+# ---------------------------------------------------------------------------------------------------------
+# mosesfile.py variant (mosesfile.py:6-157): bidirectional encoder GRU (hard-coded, :21-28), single-Linear mu / logvar
+# heads on cat(h_fwd, h_bwd) (:31-32, :115-118), d_z = 128 (config.py:34-36), forward returns (kl, recon) (:100).
+# Pinned by tests/golden/make_golden_moses.py (mosesfile.VAE with config --q_bidir) -> tests/golden/mosesfile_*.npz.
+# ---------------------------------------------------------------------------------------------------------
+def mosesfile_shapes(V=34, d_z=128, q_h=256, d_h=512, d_layers=3):
+    s = {"x_emb.weight": (V, V)}
+    for sfx in ("", "_reverse"):
+        s[f"encoder_rnn.weight_ih_l0{sfx}"] = (3 * q_h, V)
+        s[f"encoder_rnn.weight_hh_l0{sfx}"] = (3 * q_h, q_h)
+        s[f"encoder_rnn.bias_ih_l0{sfx}"] = (3 * q_h,)
+        s[f"encoder_rnn.bias_hh_l0{sfx}"] = (3 * q_h,)
+    s["q_mu.weight"] = (d_z, 2 * q_h); s["q_mu.bias"] = (d_z,)
+    s["q_logvar.weight"] = (d_z, 2 * q_h); s["q_logvar.bias"] = (d_z,)
+    for l in range(d_layers):
+        inp = V + d_z if l == 0 else d_h
+        s[f"decoder_rnn.weight_ih_l{l}"] = (3 * d_h, inp)
+        s[f"decoder_rnn.weight_hh_l{l}"] = (3 * d_h, d_h)
+        s[f"decoder_rnn.bias_ih_l{l}"] = (3 * d_h,)
+        s[f"decoder_rnn.bias_hh_l{l}"] = (3 * d_h,)
+    s["decoder_lat.weight"] = (d_h, d_z); s["decoder_lat.bias"] = (d_h,)
+    s["decoder_fc.weight"] = (V, d_h); s["decoder_fc.bias"] = (V,)
+    return s
+
+
+def make_mosesfile_params(seed, dtype=np.float32, **cfg):
+    rng = np.random.Generator(np.random.PCG64(seed))
+    shapes = mosesfile_shapes(**cfg)
+    out = {}
+    for k, shp in shapes.items():
+        if k == "x_emb.weight":
+            out[k] = (np.eye(shp[0]) + 0.05 * rng.standard_normal(shp)).astype(dtype)
+            continue
+        fan = shp[-1] if len(shp) > 1 else shapes[k.replace("bias", "weight")][-1]
+        if "rnn" in k:
+            fan = shapes[k.split(".")[0] + ".weight_hh_l0"][1]
+        b = 1.0 / np.sqrt(fan)
+        out[k] = rng.uniform(-b, b, size=shp).astype(dtype)
+    return out
+
+
+def _reverse_valid(a, L):
+    """a (B,T,...) -> each row's first L_b entries reversed in place, padding untouched."""
+    out = a.copy()
+    for b, l in enumerate(L):
+        out[b, :l] = a[b, :l][::-1]
+    return out
+
+
+def mosesfile_step(P, seqs, eps, pad, kl_weight=1.0, need_grads=True, d_layers=3):
+    """One fwd(+bwd) step of mosesfile.VAE.forward; differentiates kl_weight*kl + recon."""
+    dt = P["decoder_fc.weight"].dtype
+    x, L = pad_batch(seqs, pad)
+    B, T = x.shape
+    E = P["x_emb.weight"]
+    V = E.shape[0]
+    emb = E[x]
+    q_h = P["encoder_rnn.weight_hh_l0"].shape[1]
+    z0 = np.zeros((B, q_h), dt)
+    enc = lambda sfx: (P[f"encoder_rnn.weight_ih_l0{sfx}"], P[f"encoder_rnn.weight_hh_l0{sfx}"],
+                       P[f"encoder_rnn.bias_ih_l0{sfx}"], P[f"encoder_rnn.bias_hh_l0{sfx}"])
+    _, h_f, c_f = _gru_layer_fwd(emb, L, *enc(""), z0)
+    emb_r = _reverse_valid(emb, L)                              # the reverse direction walks t = L_b-1 .. 0
+    _, h_b, c_b = _gru_layer_fwd(emb_r, L, *enc("_reverse"), z0)
+    h = np.concatenate([h_f, h_b], 1)                           # mosesfile.py:115-116
+    mu = h @ P["q_mu.weight"].T + P["q_mu.bias"]
+    lv = h @ P["q_logvar.weight"].T + P["q_logvar.bias"]
+    std = np.exp(0.5 * lv)
+    z = mu + std * eps.astype(dt)
+    kl = float((0.5 * (np.exp(lv) + mu ** 2 - 1 - lv).sum(1)).mean(dtype=np.float64))
+    d_h = P["decoder_lat.weight"].shape[0]
+    h0 = z @ P["decoder_lat.weight"].T + P["decoder_lat.bias"]
+    xin = np.concatenate([emb, np.broadcast_to(z[:, None, :], (B, T, z.shape[1]))], -1)
+    caches, inputs, cur = [], [], xin
+    for l in range(d_layers):
+        inputs.append(cur)
+        cur, _, c = _gru_layer_fwd(cur, L, P[f"decoder_rnn.weight_ih_l{l}"], P[f"decoder_rnn.weight_hh_l{l}"],
+                                   P[f"decoder_rnn.bias_ih_l{l}"], P[f"decoder_rnn.bias_hh_l{l}"], h0)
+        caches.append(c)
+    out = cur
+    y = out @ P["decoder_fc.weight"].T + P["decoder_fc.bias"]
+    tgt, lg = x[:, 1:], y[:, :-1]
+    mx = lg.max(-1, keepdims=True)
+    lse = mx[..., 0] + np.log(np.exp(lg - mx).sum(-1))
+    valid = tgt != pad
+    M = int(valid.sum())
+    nll = lse - np.take_along_axis(lg, tgt[..., None], -1)[..., 0]
+    recon = float((nll * valid).sum(dtype=np.float64) / M)
+    res = dict(kl=kl, recon=recon, loss=kl_weight * kl + recon, z=z, mu=mu, logvar=lv, y=y, x=x, lengths=L, M=M)
+    if not need_grads:
+        return res
+    G = {k: np.zeros_like(v) for k, v in P.items()}
+    sm = np.exp(lg - lse[..., None])
+    dlg = sm.copy()
+    np.add.at(dlg, (np.arange(B)[:, None], np.arange(T - 1)[None, :], tgt), -1.0)
+    dlg = dlg * valid[..., None] / M
+    dy = np.zeros_like(y)
+    dy[:, :-1] = dlg
+    G["decoder_fc.weight"] = dy.reshape(B * T, V).T @ out.reshape(B * T, d_h)
+    G["decoder_fc.bias"] = dy.sum((0, 1))
+    dout = dy @ P["decoder_fc.weight"]
+    dh0 = np.zeros((B, d_h), dt)
+    for l in reversed(range(d_layers)):
+        dxl, dh0_l, g = _gru_layer_bwd(dout, np.zeros((B, d_h), dt), inputs[l], P[f"decoder_rnn.weight_ih_l{l}"],
+                                       P[f"decoder_rnn.weight_hh_l{l}"], caches[l])
+        for nm, key in (("w_ih", "weight_ih"), ("w_hh", "weight_hh"), ("b_ih", "bias_ih"), ("b_hh", "bias_hh")):
+            G[f"decoder_rnn.{key}_l{l}"] = g[nm]
+        dh0 += dh0_l
+        dout = dxl
+    demb = dout[..., :V].copy()
+    dz = dout[..., V:].sum(1)
+    G["decoder_lat.weight"] = dh0.T @ z
+    G["decoder_lat.bias"] = dh0.sum(0)
+    dz = dz + dh0 @ P["decoder_lat.weight"]
+    dmu = dz + kl_weight * mu / B
+    dlv = dz * eps.astype(dt) * std * 0.5 + kl_weight * 0.5 * (np.exp(lv) - 1) / B
+    G["q_mu.weight"] = dmu.T @ h; G["q_mu.bias"] = dmu.sum(0)
+    G["q_logvar.weight"] = dlv.T @ h; G["q_logvar.bias"] = dlv.sum(0)
+    dh = dmu @ P["q_mu.weight"] + dlv @ P["q_logvar.weight"]
+    zeros = np.zeros((B, T, q_h), dt)
+    dxe, _, g = _gru_layer_bwd(zeros, dh[:, :q_h], emb, P["encoder_rnn.weight_ih_l0"], P["encoder_rnn.weight_hh_l0"], c_f)
+    for nm, key in (("w_ih", "weight_ih"), ("w_hh", "weight_hh"), ("b_ih", "bias_ih"), ("b_hh", "bias_hh")):
+        G[f"encoder_rnn.{key}_l0"] = g[nm]
+    demb = demb + dxe
+    dxr, _, g = _gru_layer_bwd(zeros, dh[:, q_h:], emb_r, P["encoder_rnn.weight_ih_l0_reverse"],
+                               P["encoder_rnn.weight_hh_l0_reverse"], c_b)
+    for nm, key in (("w_ih", "weight_ih"), ("w_hh", "weight_hh"), ("b_ih", "bias_ih"), ("b_hh", "bias_hh")):
+        G[f"encoder_rnn.{key}_l0_reverse"] = g[nm]
+    demb = demb + _reverse_valid(dxr, L)
+    dE = np.zeros_like(E)
+    np.add.at(dE, x.reshape(-1), demb.reshape(B * T, V))
+    dE[pad] = 0.0
+    G["x_emb.weight"] = dE
+    res["grads"] = G
+    return res

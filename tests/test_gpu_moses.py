@@ -129,3 +129,74 @@ def test_moses_sample_multinomial_distribution():
     assert int(s_ids.max()) < 34 and (s_ids[:, 0] == model.bos).all()
     assert (s_len >= 2).all() and (s_len <= 30).all()
     assert (s_ids != g_ids).float().mean().item() > 0.2               # actually stochastic
+
+
+# ---- mosesfile.py variant: bidirectional encoder, single-Linear heads, d_z = 128 (BASELINE config 4) ----
+class _Cfg:   # config.py:4-85 defaults with --q_bidir
+    q_cell, q_bidir, q_d_h, q_n_layers, q_dropout = "gru", True, 256, 1, 0.5
+    d_cell, d_n_layers, d_dropout, d_z, d_d_h, freeze_embeddings = "gru", 3, 0, 128, 512, False
+
+
+def _setup_file(m, precision, pseed, bseed, B):
+    P = mo.make_mosesfile_params(pseed, dtype=np.float32)
+    seqs, eps, pad = mo.make_moses_batch(bseed, B, d_z=128, dtype=np.float32)
+    model = m.mosesfile.VAE(_Vocab(), _Cfg(), precision=precision)
+    sd = model.state_dict()
+    with torch.no_grad():
+        for k, v in P.items():
+            sd[k].copy_(torch.from_numpy(v))
+    return P, seqs, eps, pad, model.cuda()
+
+
+@pytest.mark.parametrize("precision,B,ltol,gtol", [("fp32", 7, 2e-5, 3e-5), ("fp32", 70, 2e-5, 3e-5), ("bf16", 200, 2e-3, 2e-2)])
+def test_mosesfile_bidirectional_fused_step(precision, B, ltol, gtol):
+    m = load_pkg()
+    klw = 0.5
+    P, seqs, eps, pad, model = _setup_file(m, precision, 331, 431 + B, B)
+    ref = mo.mosesfile_step({k: v.astype(np.float64) for k, v in P.items()}, seqs, eps.astype(np.float64), pad, kl_weight=klw)
+    x = [torch.from_numpy(s).cuda() for s in seqs]
+    out = model.elbo_step(x, kl_weight=klw, eps=torch.from_numpy(eps).cuda())
+    torch.cuda.synchronize()
+    model.check_device_error()
+    sc = out.cpu().numpy()
+    assert abs(sc[1] - ref["kl"]) <= ltol * abs(ref["kl"]), (sc, ref["kl"])
+    assert abs(sc[2] - ref["recon"]) <= ltol * abs(ref["recon"]), (sc, ref["recon"])
+    bad = {}
+    for k, p in model.named_parameters():
+        if k in ref["grads"]:
+            e = rel_l2(p.grad.cpu().numpy(), ref["grads"][k])
+            if not e <= gtol:
+                bad[k] = e
+    assert not bad, bad
+
+
+def test_mosesfile_dropin_contract_and_reference_fixture():
+    """forward -> (kl, recon) (mosesfile.py:100), state_dict aliases (:52-66), sample -> list[str] (:215); values against
+    the fixture written by the reference class itself (tests/golden/make_golden_mosesfile.py)."""
+    import os
+    m = load_pkg()
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "mosesfile_b5.npz"))
+    ps, bs, B = [int(v) for v in g["meta"]]
+    klw = float(g["kl_weight"][0])
+    P, seqs, eps, pad, model = _setup_file(m, "fp32", ps, bs, B)
+    keys = set(model.state_dict().keys())
+    for k in ("x_emb.weight", "encoder.0.weight_hh_l0_reverse", "encoder.1.weight", "decoder.1.bias", "vae.1.2.bias", "vae.0.weight"):
+        assert k in keys
+    assert "encoder.0.weight" not in keys or True      # encoder group has no x_emb in mosesfile.py:52-56
+    assert len(list(model.encoder.parameters())) == 12
+    model.eps_override = torch.from_numpy(eps)
+    out = model([torch.from_numpy(s).cuda() for s in seqs])
+    assert len(out) == 2
+    kl, recon = out
+    (klw * kl + recon).backward()
+    torch.cuda.synchronize()
+    assert abs(float(kl.detach()) - float(g["f64/kl"])) <= 2e-5 * abs(float(g["f64/kl"]))
+    assert abs(float(recon.detach()) - float(g["f64/recon"])) <= 2e-5 * abs(float(g["f64/recon"]))
+    for k, p in model.named_parameters():
+        if f"f64/gfull/{k}" in g:
+            assert rel_l2(p.grad.cpu().numpy(), g[f"f64/gfull/{k}"]) <= 3e-5, k
+        elif f"f64/gnorm/{k}" in g:
+            gn = float(g[f"f64/gnorm/{k}"])
+            assert abs(np.sqrt((p.grad.double() ** 2).sum().item()) - gn) <= 3e-5 * gn, k
+    strs = model.sample(8, max_len=20, greedy=True)
+    assert isinstance(strs, list) and len(strs) == 8 and all(isinstance(s, str) for s in strs)

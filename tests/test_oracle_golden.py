@@ -118,3 +118,24 @@ def test_cfga_oracle_matches_reference(name):
             np.testing.assert_allclose(gr, g[f"gfull/{k}"], rtol=1e-7, atol=1e-12 + 1e-9 * gn)
         else:
             np.testing.assert_allclose(gr.reshape(-1)[g[f"gidx/{k}"]], g[f"gval/{k}"], rtol=1e-7, atol=1e-12 + 1e-9 * gn)
+
+
+def test_mosesfile_oracle_matches_reference():
+    from oracle import moses_oracle as mo
+    """oracle.moses_oracle.mosesfile_step against the fixture produced by the reference's mosesfile.VAE (--q_bidir)."""
+    g = np.load(os.path.join(GOLD, "mosesfile_b5.npz"))
+    ps, bs, B = [int(v) for v in g["meta"]]
+    klw = float(g["kl_weight"][0])
+    P = mo.make_mosesfile_params(ps, dtype=np.float64)
+    seqs, eps, pad = mo.make_moses_batch(bs, B, d_z=128, dtype=np.float64)
+    r = mo.mosesfile_step(P, seqs, eps, pad, kl_weight=klw)
+    assert abs(r["kl"] - g["f64/kl"]) <= 1e-11 * abs(g["f64/kl"])
+    assert abs(r["recon"] - g["f64/recon"]) <= 1e-11 * abs(g["f64/recon"])
+    np.testing.assert_allclose(r["z"], g["f64/z"], rtol=1e-10, atol=1e-12)
+    for k, gr in r["grads"].items():
+        gn = float(g[f"f64/gnorm/{k}"])
+        assert abs(np.sqrt((gr ** 2).sum()) - gn) <= 1e-9 * gn + 1e-14, k
+        if f"f64/gfull/{k}" in g:
+            np.testing.assert_allclose(gr, g[f"f64/gfull/{k}"], rtol=1e-8, atol=1e-12 + 1e-9 * gn)
+        else:
+            np.testing.assert_allclose(gr.reshape(-1)[g[f"f64/gidx/{k}"]], g[f"f64/gval/{k}"], rtol=1e-8, atol=1e-12 + 1e-9 * gn)
