@@ -211,6 +211,27 @@ int mvae_moses_sample(const mvae_moses_desc* d, const float* const* params, cons
 int mvae_moses_read_error(const mvae_moses_desc* d, void* workspace, size_t workspace_bytes, int* flag,
                           mvae_stream_t stream);
 
+/* ---- BindingModel property head (mosesvae.py:6-25; callers moses_train_distrib.py:274, trainbinding.py:216) ----------
+ * Linear(Z,256) -> BatchNorm1d(256) -> Tanh -> Linear(256,256) -> ReLU -> Linear(256,64) -> BatchNorm1d(64) -> ReLU -> Linear(64,1)
+ * on latents z fp32 (B,Z).  params / grads: host arrays of 12 fp32 device pointers in state_dict order
+ *   binding_model.{0.weight (256,Z), 0.bias, 1.weight, 1.bias, 3.weight (256,256), 3.bias, 5.weight (64,256), 5.bias,
+ *                  6.weight, 6.bias, 8.weight (1,64), 8.bias};
+ * running: 4 device pointers {1.running_mean, 1.running_var, 6.running_mean, 6.running_var}, updated in train mode
+ * (momentum bn_momentum, unbiased variance) and read in eval mode.  forward leaves the activations backward needs in
+ * `workspace`; out fp32 (B) = the module's (B,1) output; dout fp32 (B); dz optional fp32 (B,Z).  grads are OVERWRITTEN.  */
+typedef struct mvae_binding_desc {
+  int32_t batch;
+  int32_t z_size;    /* 128 (mosesvae.py:7) */
+  int32_t train;     /* BatchNorm1d mode */
+  float bn_eps;      /* 1e-5 */
+  float bn_momentum; /* 0.1 */
+} mvae_binding_desc;
+size_t mvae_binding_workspace_bytes(const mvae_binding_desc* d);
+int mvae_binding_forward(const mvae_binding_desc* d, const float* const* params, float* const* running, const float* z,
+                         float* out, void* workspace, size_t workspace_bytes, mvae_stream_t stream);
+int mvae_binding_backward(const mvae_binding_desc* d, const float* const* params, float* const* grads, const float* z,
+                          const float* dout, float* dz, void* workspace, size_t workspace_bytes, mvae_stream_t stream);
+
 /* ---- optimiser step on flat fp32 buffers (train.py:102-104, train_distributed.py:91-94) ------------------
  * Global-norm clipping = torch.nn.utils.clip_grad_norm(params, max_norm) over ONE flat gradient buffer (the layout
  * molecular-vae_b200/ddp.py uses); the clip coefficient min(1, max_norm/(norm+1e-6)) stays on the device at

@@ -35,6 +35,11 @@ class MosesDesc(ctypes.Structure):
                                                                                    ("q_linear_heads", ctypes.c_int32)]
 
 
+class BindingDesc(ctypes.Structure):
+    _fields_ = [("batch", ctypes.c_int32), ("z_size", ctypes.c_int32), ("train", ctypes.c_int32),
+                ("bn_eps", ctypes.c_float), ("bn_momentum", ctypes.c_float)]
+
+
 class MvaeError(RuntimeError):
     pass
 
@@ -81,6 +86,9 @@ def _load():
         "mvae_moses_sample": (i32, [ctypes.POINTER(MosesDesc), pp, vp, i32, i32, i32, ctypes.c_float, ctypes.c_ulonglong, vp, vp,
                                     vp, ctypes.c_size_t, vp]),
         "mvae_moses_read_error": (i32, [ctypes.POINTER(MosesDesc), vp, ctypes.c_size_t, ctypes.POINTER(i32), vp]),
+        "mvae_binding_workspace_bytes": (ctypes.c_size_t, [ctypes.POINTER(BindingDesc)]),
+        "mvae_binding_forward": (i32, [ctypes.POINTER(BindingDesc), pp, pp, vp, vp, vp, ctypes.c_size_t, vp]),
+        "mvae_binding_backward": (i32, [ctypes.POINTER(BindingDesc), pp, pp, vp, vp, vp, vp, ctypes.c_size_t, vp]),
         "mvae_clip_grad_norm": (i32, [vp, ll, ctypes.c_float, vp, vp, i32, vp]),
         "mvae_adam_step": (i32, [vp, vp, vp, vp, ll] + [ctypes.c_float] * 5 + [i32, vp, vp]),
         "mvae_sgd_momentum_step": (i32, [vp, vp, vp, ll] + [ctypes.c_float] * 3 + [i32, vp, vp]),
@@ -104,6 +112,7 @@ EXPORTED = [
     "mvae_clip_grad_norm", "mvae_adam_step", "mvae_sgd_momentum_step",
     "mvae_cfga_workspace_bytes", "mvae_cfga_elbo_step", "mvae_cfga_elbo_step_graph_create", "mvae_cfga_forward",
     "mvae_cfga_backward", "mvae_cfga_decode", "mvae_cfga_read_error",
+    "mvae_binding_workspace_bytes", "mvae_binding_forward", "mvae_binding_backward",
     "mvae_moses_workspace_bytes", "mvae_moses_step", "mvae_moses_sample", "mvae_moses_read_error",
 ]
 

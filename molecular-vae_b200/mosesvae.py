@@ -46,6 +46,78 @@ class _MosesFunction(torch.autograd.Function):
         return (None, None, None, None, *grads)
 
 
+class _BindingFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, model, z, *params):
+        out = model._forward(z, list(params))
+        ctx.model, ctx.z = model, z
+        ctx.save_for_backward(*params)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        params = list(ctx.saved_tensors)
+        grads = [torch.empty_like(p) for p in params]
+        dz = ctx.model._backward(ctx.z, params, grads, dout.contiguous().float().view(-1), ctx.needs_input_grad[1])
+        return (None, dz, *grads)
+
+
+class BindingModel(nn.Module):
+    """Drop-in for mosesvae.BindingModel (mosesvae.py:6-25): same nn.Sequential (hence state_dict keys incl. the BatchNorm
+    buffers); forward/backward run in libmvae_b200.so (binding.cu).  A forward is followed by at most one backward."""
+
+    KEYS = ["0.weight", "0.bias", "1.weight", "1.bias", "3.weight", "3.bias", "5.weight", "5.bias", "6.weight", "6.bias",
+            "8.weight", "8.bias"]
+
+    def __init__(self, z_size=128):
+        super().__init__()
+        self.binding_model = nn.Sequential(
+            nn.Linear(z_size, 256), nn.BatchNorm1d(256), nn.Tanh(),
+            nn.Linear(256, 256), nn.ReLU(),
+            nn.Linear(256, 64), nn.BatchNorm1d(64), nn.ReLU(),
+            nn.Linear(64, 1))
+        self.z_size = z_size
+        self._ws = None
+
+    def _desc(self, B):
+        bn = self.binding_model[1]
+        d = _lib.BindingDesc(B, self.z_size, int(self.training), float(bn.eps), float(bn.momentum))
+        need = lib.mvae_binding_workspace_bytes(ctypes.byref(d))
+        return d, need
+
+    def _forward(self, z, params):
+        if not torch.cuda.is_available():
+            raise _lib.MvaeError("molecular-vae_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        B = z.shape[0]
+        d, need = self._desc(B)
+        if self._ws is None or self._ws.numel() < need + 256 or self._ws.device != z.device:
+            self._ws = torch.empty(need + 256, dtype=torch.uint8, device=z.device)
+        wsp = ctypes.c_void_p(self._ws.data_ptr() + (-self._ws.data_ptr()) % 256)
+        bn1, bn2 = self.binding_model[1], self.binding_model[6]
+        running = _ptr_table([bn1.running_mean, bn1.running_var, bn2.running_mean, bn2.running_var])
+        out = torch.empty(B, dtype=torch.float32, device=z.device)
+        with torch.cuda.device(z.device):
+            check(lib.mvae_binding_forward(ctypes.byref(d), _ptr_table(params), running, _p(z), _p(out), wsp, need, _stream()))
+        if self.training:
+            bn1.num_batches_tracked += 1
+            bn2.num_batches_tracked += 1
+        self._last = (d, wsp, need)
+        return out.view(B, 1)
+
+    def _backward(self, z, params, grads, dout, want_dz):
+        d, wsp, need = self._last
+        dz = torch.empty_like(z) if want_dz else None
+        with torch.cuda.device(z.device):
+            check(lib.mvae_binding_backward(ctypes.byref(d), _ptr_table(params), _ptr_table(grads), _p(z), _p(dout), _p(dz), wsp,
+                                            need, _stream()))
+        return dz
+
+    def forward(self, x):
+        named = dict(self.binding_model.named_parameters())
+        params = [named[k] if named[k].is_contiguous() else named[k].contiguous() for k in self.KEYS]
+        return _BindingFunction.apply(self, x.float().contiguous(), *params)
+
+
 class VAE(nn.Module):
     def __init__(self, vocab, precision="bf16"):
         super().__init__()

@@ -200,3 +200,44 @@ def test_mosesfile_dropin_contract_and_reference_fixture():
             assert abs(np.sqrt((p.grad.double() ** 2).sum().item()) - gn) <= 3e-5 * gn, k
     strs = model.sample(8, max_len=20, greedy=True)
     assert isinstance(strs, list) and len(strs) == 8 and all(isinstance(s, str) for s in strs)
+
+
+# ---- BindingModel property head (mosesvae.py:6-25) ----
+@pytest.mark.parametrize("mode,B", [("train", 12), ("eval", 12), ("train", 700)])
+def test_binding_model_forward_backward(mode, B):
+    import os
+    from oracle import binding_oracle as bo
+    m = load_pkg()
+    Z = 128
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "binding_b12.npz"))
+    P, run = bo.make_binding_params(501, Z, dtype=np.float32)
+    if B == 12:
+        z, dout = g["z"].astype(np.float32), g["dout"].astype(np.float32)
+    else:
+        rng = np.random.Generator(np.random.PCG64(78))
+        z, dout = rng.standard_normal((B, Z)).astype(np.float32), rng.standard_normal(B).astype(np.float32)
+    ref = bo.binding_step({k: v.astype(np.float64) for k, v in P.items()}, {k: v.astype(np.float64) for k, v in run.items()},
+                          z.astype(np.float64), dout.astype(np.float64), train=mode == "train")
+    model = m.mosesvae.BindingModel(Z)
+    sd = model.state_dict()
+    assert set(k for k in sd if "num_batches" not in k) == {"binding_model." + k for k in list(P) + list(run)}
+    with torch.no_grad():
+        for k, v in {**P, **run}.items():
+            sd["binding_model." + k].copy_(torch.from_numpy(v))
+    model = model.cuda().train(mode == "train")
+    zt = torch.from_numpy(z).cuda().requires_grad_(True)
+    out = model(zt)
+    assert out.shape == (B, 1)
+    out.backward(torch.from_numpy(dout).cuda().view(B, 1))
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(out.detach().cpu().numpy(), ref["out"], rtol=2e-4, atol=2e-5)
+    assert rel_l2(zt.grad.cpu().numpy(), ref["dz"]) <= 5e-5
+    for k, p in model.binding_model.named_parameters():
+        got, want = p.grad.cpu().numpy().astype(np.float64), ref["grads"][k]
+        # a bias in front of a train-mode BatchNorm has an exactly-zero gradient: compare on an absolute floor there
+        assert np.sqrt(((got - want) ** 2).sum()) <= 5e-5 * np.sqrt((want ** 2).sum()) + 5e-5, (k, np.sqrt(((got - want) ** 2).sum()))
+    for k, v in ref["running"].items():
+        np.testing.assert_allclose(model.state_dict()["binding_model." + k].cpu().numpy(), v, rtol=1e-5, atol=1e-6, err_msg=k)
+    if B == 12:   # and directly against the reference-generated fixture
+        np.testing.assert_allclose(out.detach().cpu().numpy(), g[f"{mode}/out"], rtol=2e-4, atol=2e-5)
+        assert rel_l2(zt.grad.cpu().numpy(), g[f"{mode}/dz"]) <= 5e-5

@@ -139,3 +139,19 @@ def test_mosesfile_oracle_matches_reference():
             np.testing.assert_allclose(gr, g[f"f64/gfull/{k}"], rtol=1e-8, atol=1e-12 + 1e-9 * gn)
         else:
             np.testing.assert_allclose(gr.reshape(-1)[g[f"f64/gidx/{k}"]], g[f"f64/gval/{k}"], rtol=1e-8, atol=1e-12 + 1e-9 * gn)
+
+
+@pytest.mark.parametrize("mode", ["train", "eval"])
+def test_binding_oracle_matches_reference(mode):
+    """oracle.binding_oracle against the fixture produced by the reference's mosesvae.BindingModel."""
+    from oracle import binding_oracle as bo
+    g = np.load(os.path.join(GOLD, "binding_b12.npz"))
+    ps, B, Z = [int(v) for v in g["meta"]]
+    P, run = bo.make_binding_params(ps, Z, dtype=np.float64)
+    r = bo.binding_step(P, run, g["z"], g["dout"], train=mode == "train")
+    np.testing.assert_allclose(r["out"], g[f"{mode}/out"], rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(r["dz"], g[f"{mode}/dz"], rtol=1e-8, atol=1e-12)
+    for k, v in r["grads"].items():
+        np.testing.assert_allclose(v, g[f"{mode}/grad/{k}"], rtol=1e-8, atol=1e-11, err_msg=k)
+    for k, v in r["running"].items():
+        np.testing.assert_allclose(v, g[f"{mode}/{k}"], rtol=1e-10, atol=1e-12, err_msg=k)
