@@ -97,6 +97,11 @@ struct WS {
   void* Whh_p[4]; void* Wih_p[4]; void* Wih_nrz[4]; void* W3_p;
   void* WhhT_p[4];          // bf16 [Hp][3Hp] (fused BPTT kernel operand)
   void* gi0_bf;             // bf16 [Bp][3Hp] copy of the layer-0 projection (fused forward kernel)
+  // tensor-core layer-0 path (fused recurrence only): bf16 operands of gi0 = zr W_ih0^T and of its two gradient GEMMs
+  void* zr_bf;              // [Bp][Zp]
+  void* Wih0_p;             // [3Hp][Zp] gate-padded W_ih_l0
+  void* dgi0sum_bf;         // [Bp][3Hp] (r,z,n) time-summed dgi of layer 0
+  float* dWih0_p;           // [3Hp][Zp] staging
   unsigned int* counters;   // [Bp/128] inter-CTA step counters of the fused recurrence
   float* bih_p[4]; float* bhh_p[4]; float* b3_p;
   float* bcomb_p[4];        // b_ih + (b_hr, b_hz, 0): projection bias when the fused kernel only adds b_hn
@@ -171,6 +176,13 @@ void carve(const Dims& d, void* base, WS* w) {
   w->dW3_p = c.take<float>(d.CP * Hp);
   w->csum = c.take<float>(4 * Hp);
   w->gi0_bf = c.take<uint8_t>(Bp * 3 * Hp * 2);
+  {
+    const size_t Zp = (size_t)round_up(d.Z, 8);
+    w->zr_bf = c.take<uint8_t>(Bp * Zp * 2);
+    w->Wih0_p = c.take<uint8_t>(3 * Hp * Zp * 2);
+    w->dgi0sum_bf = c.take<uint8_t>(Bp * 3 * Hp * 2);
+    w->dWih0_p = c.take<float>(3 * Hp * Zp);
+  }
   w->counters = c.take<unsigned int>(Bp / 128 + 1);
   w->total = (c.off + 255) & ~size_t(255);
 }
@@ -272,7 +284,7 @@ __global__ void f32_to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16*
 }
 // layer 0: sum over time of the dgi window of dG ([T][Bp][4Hp], blocks n,r,z) -> fp32 [Bp][3Hp] in (r,z,n) order
 __global__ void dgi_time_sum_kernel(const __nv_bfloat16* __restrict__ dG, int T, int Bp, int Hp,
-                                    float* __restrict__ out) {
+                                    float* __restrict__ out, __nv_bfloat16* __restrict__ out_bf = nullptr) {
   // one thread per (row b, 8 consecutive columns of the dgi window): 16-byte loads, fp32 accumulation over t
   const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   const int cpr = 3 * Hp / 8;
@@ -296,6 +308,11 @@ __global__ void dgi_time_sum_kernel(const __nv_bfloat16* __restrict__ dG, int T,
   float* o = out + (long long)b * 3 * Hp + g * Hp + j;
 #pragma unroll
   for (int k = 0; k < 8; ++k) o[k] = s[k];
+  if (out_bf) {
+    __nv_bfloat16* ob = out_bf + (long long)b * 3 * Hp + g * Hp + j;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) ob[k] = __float2bfloat16_rn(s[k]);
+  }
 }
 
 // ones-column helpers (fused path): column Hp-1 of every hidden-state slab is the constant 1
@@ -342,9 +359,11 @@ int rec_variant(const Dims& d) {
 }
 // the fused path keeps a constant-1 pad column in every hidden-state slab (needs H < Hp)
 bool ones_column(const Dims& d) { return rec_variant(d) >= 3 && d.H < d.Hp; }
+// gate non-linearities of the fused forward sweep through tanh.approx (one MUFU op per gate, |err| ~ 5e-4, below the
+// bf16 rounding of the saved gates); MVAE_FAST_GATES=0 selects the exp/rcp forms.  fp32 check mode never uses it.
 int fast_gates() {
   const char* e = getenv("MVAE_FAST_GATES");
-  return e ? atoi(e) : 0;
+  return e ? atoi(e) : 1;
 }
 __global__ void combine_bias_kernel(const float* __restrict__ bih, const float* __restrict__ bhh, float* __restrict__ out,
                                     int Hp) {
@@ -390,6 +409,17 @@ int prep_weights(const Dims& d, const WS& w, const float* const* P, cudaStream_t
     if (l >= 1 && rec_variant(d) >= 3) {
       combine_bias_kernel<<<ceil_div(3 * Hp, 256), 256, 0, st>>>(w.bih_p[l], w.bhh_p[l], w.bcomb_p[l], Hp);
       KCHECK();
+    }
+    if constexpr (sizeof(TA) == 2) {
+      if (l == 0 && rec_variant(d) >= 3) {
+        const int Zp = round_up(d.Z, 8);
+        simt::pad_gate_matrix_kernel<TA><<<grid_for(3ll * Hp * Zp), 256, 0, st>>>(P[P_WIH(0)], H, d.Z, (TA*)w.Wih0_p, Hp, Zp, 0, 1, 2);
+        KCHECK();
+        simt::pad_gate_vector_kernel<<<ceil_div(3 * Hp, 256), 256, 0, st>>>(P[P_BIH(0)], H, w.bih_p[0], Hp);
+        KCHECK();
+        combine_bias_kernel<<<ceil_div(3 * Hp, 256), 256, 0, st>>>(w.bih_p[0], w.bhh_p[0], w.bcomb_p[0], Hp);
+        KCHECK();
+      }
     }
   }
   simt::pad_matrix_kernel<TA><<<grid_for((long long)d.CP * Hp), 256, 0, st>>>(P[P_FC3W(d.L)], d.C, H, (TA*)w.W3_p, d.CP, Hp);
@@ -438,9 +468,23 @@ int run_forward(const Dims& d, const WS& w, const float* const* P, const uint8_t
   }
   // fc2 + SELU (models2d.py:41); layer-0 input projection computed once per molecule
   RC(sg(st, w.z, Z, 1, P[P_FC2W], 1, Z, w.zr, Z, B, Z, Z, P[P_FC2B], simt::ACT_SELU, 0));
-  for (int g = 0; g < 3; ++g)
-    RC(sg(st, w.zr, Z, 1, P[P_WIH(0)] + (size_t)g * H * Z, 1, Z, w.gi0 + (size_t)g * Hp, 3 * Hp, B, H, Z,
-          P[P_BIH(0)] + (size_t)g * H, simt::ACT_NONE, 0));
+  bool gi0_tc = false;
+  if constexpr (sizeof(TA) == 2) {
+    if (rec_variant(d) >= 3) {
+      // layer-0 projection on the tensor cores straight into the row-blocked bf16 operand of the fused recurrence
+      // (bias = b_ih + (b_hr, b_hz, 0)); pad rows get the bias only, which is harmless (their gradients are zero)
+      const int Zp = round_up(Z, 8);
+      simt::pad_matrix_kernel<TA><<<grid_for((long long)Bp * Zp), 256, 0, st>>>(w.zr, B, Z, (TA*)w.zr_bf, Bp, Zp);
+      KCHECK();
+      RC(gemm<TA>(d, w, st, (const TA*)w.zr_bf, Zp, false, (const TA*)w.Wih0_p, Zp, true, w.gi0_bf, 3 * Hp, true, Bp, 3 * Hp, Zp,
+                  w.bcomb_p[0], false, 1, 0, true));
+      gi0_tc = true;
+    }
+  }
+  if (!gi0_tc)
+    for (int g = 0; g < 3; ++g)
+      RC(sg(st, w.zr, Z, 1, P[P_WIH(0)] + (size_t)g * H * Z, 1, Z, w.gi0 + (size_t)g * Hp, 3 * Hp, B, H, Z,
+            P[P_BIH(0)] + (size_t)g * H, simt::ACT_NONE, 0));
   const int gate_grid = ceil_div(Bp * Hp, 256);
   for (int l = 0; l < d.L; ++l) {
     TA* hs = (TA*)w.hs[l];
@@ -456,9 +500,11 @@ int run_forward(const Dims& d, const WS& w, const float* const* P, const uint8_t
         const __nv_bfloat16* gi = (const __nv_bfloat16*)w.gi_all;
         long long gstride = (long long)Bp * 3 * Hp;
         if (l == 0) {
-          gi0_to_bf16_kernel<<<grid_for((long long)Bp * 3 * Hp), 256, 0, st>>>(
-              w.gi0, rv >= 3 ? w.bhh_p[0] : nullptr, Hp, (__nv_bfloat16*)w.gi0_bf, (long long)Bp * 3 * Hp, rv >= 3 ? 1 : 0);
-          KCHECK();
+          if (!gi0_tc) {
+            gi0_to_bf16_kernel<<<grid_for((long long)Bp * 3 * Hp), 256, 0, st>>>(
+                w.gi0, rv >= 3 ? w.bhh_p[0] : nullptr, Hp, (__nv_bfloat16*)w.gi0_bf, (long long)Bp * 3 * Hp, rv >= 3 ? 1 : 0);
+            KCHECK();
+          }
           gi = (const __nv_bfloat16*)w.gi0_bf;
           gstride = 0;
         }
@@ -554,7 +600,7 @@ int run_backward(const Dims& d, const WS& w, const float* const* P, float* const
         }
         if (l == 0) {
           dgi_time_sum_kernel<<<(unsigned)ceil_div64((long long)Bp * 3 * Hp / 8, 256), 256, 0, st>>>(
-              (const __nv_bfloat16*)dG, T, Bp, Hp, w.dgi0sum);
+              (const __nv_bfloat16*)dG, T, Bp, Hp, w.dgi0sum, rv >= 3 ? (__nv_bfloat16*)w.dgi0sum_bf : nullptr);
           KCHECK();
         }
       }
@@ -611,7 +657,21 @@ int run_backward(const Dims& d, const WS& w, const float* const* P, float* const
                   nullptr, false, 1, 0, rec_variant(d) >= 3));
     } else {
       // time-invariant layer-0 input: dW_ih0 = (sum_t dgi)^T zr ; dzr = (sum_t dgi) W_ih0
-      for (int g = 0; g < 3; ++g) {
+      bool tc = false;
+      if constexpr (sizeof(TA) == 2) {
+        if (rec_variant(d) >= 3) {
+          const int Zp = round_up(Z, 8);
+          RC(memset_async(w.dWih0_p, (size_t)3 * Hp * Zp * 4, st));
+          RC(gemm<TA>(d, w, st, (const TA*)w.dgi0sum_bf, 3 * Hp, true, (const TA*)w.zr_bf, Zp, false, w.dWih0_p, Zp, false, 3 * Hp, Zp,
+                      Bp, nullptr, true, max(1, min(8, Bp / 512)), 256));
+          simt::unpad_gate_matrix_kernel<<<grid_for(3ll * H * Z), 256, 0, st>>>(w.dWih0_p, Hp, Zp, G[P_WIH(0)], H, Z, 0, 1, 2);
+          KCHECK();
+          RC(gemm<TA>(d, w, st, (const TA*)w.dgi0sum_bf, 3 * Hp, false, (const TA*)w.Wih0_p, Zp, false, w.dzr, Z, false, B, Z, 3 * Hp,
+                      nullptr, false, 1));
+          tc = true;
+        }
+      }
+      for (int g = 0; g < 3 && !tc; ++g) {
         RC(sg_wgrad(st, w.dgi0sum + (size_t)g * Hp, 1, 3 * Hp, w.zr, Z, 1, G[P_WIH(0)] + (size_t)g * H * Z, Z, H, Z, B));
         RC(sg(st, w.dgi0sum + (size_t)g * Hp, 3 * Hp, 1, P[P_WIH(0)] + (size_t)g * H * Z, Z, 1, w.dzr, Z, B, Z, H,
               nullptr, simt::ACT_NONE, g > 0 ? 1 : 0));

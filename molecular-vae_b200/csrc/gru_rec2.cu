@@ -141,6 +141,7 @@ gru_rec2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int KC = (BWD ? 3 * p.Hp : p.Hp) / 64;
+  const int KCS = (p.debug & 256) ? KC / 2 : KC;   // timing experiment: stream only half of K (wrong results)
   uint8_t* sW = smem;
   uint8_t* sA = smem + (size_t)KC * CHUNK;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sA + STAGES * A_STAGE);
@@ -225,7 +226,7 @@ gru_rec2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
           ptx::fence_proxy_async_all();
           if (p.trace && blockIdx.x == 0 && blockIdx.y == 0) p.trace[((size_t)step * NTILES + i) * 12 + 0] = gtime();
           const int row0 = tile * 256 + parity * 128 + qd * A_PART_ROWS;
-          for (int kc0 = 0; kc0 < KC; ++kc0) {
+          for (int kc0 = 0; kc0 < KCS; ++kc0) {
             const int kc = (p.debug & 128) ? (kc0 + pair * (KC / 8)) % KC : kc0;   // experiment: de-phase the pairs' chunk order
             if (!wait_bar(&empty_bar[s], ph ^ 1, p.err_flag)) goto done;
             if (p.debug & 4) {
@@ -281,7 +282,7 @@ gru_rec2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
               if (!wait_bar(&tempty_bar[i], (uint32_t)((step - 1) & 1), p.err_flag)) goto done;
               ptx::tc_fence_after();
               const uint32_t d_tmem = tmem_base + i * NB;
-              for (int kc0 = 0; kc0 < KC; ++kc0) {
+              for (int kc0 = 0; kc0 < KCS; ++kc0) {
                 const int kc = (p.debug & 128) ? (kc0 + pair * (KC / 8)) % KC : kc0;
                 const bool trm = p.trace && blockIdx.x == 0 && blockIdx.y == 0;
                 if (!wait_bar(&full_bar[s], ph, p.err_flag)) goto done;
@@ -326,8 +327,13 @@ gru_rec2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
           remote_arrive(tempty_remote + (uint32_t)(i * 8));    // accumulator i drained in this CTA -> pair leader
           const bool tr = p.trace && blockIdx.x == 0 && blockIdx.y == 0;
           if (tr) p.trace[((size_t)step * NTILES + i) * 12 + 6] = gtime();
-          __threadfence();                                     // cumulative over the epilogue threads' stores
-          ptx::fence_proxy_async_all();
+          // The release of the red is cumulative over the epilogue threads' stores this thread observed through the
+          // epi_bar acquire; the consumer issues the generic->async proxy fence after its acquire.  (A separate
+          // __threadfence + writer-side proxy fence here cost 0.9 us per step; debug&512 restores them.)
+          if (p.debug & 512) {
+            __threadfence();
+            ptx::fence_proxy_async_all();
+          }
           red_release_add(p.counters + tile * 2 + parity, 1u);
           if (tr) p.trace[((size_t)step * NTILES + i) * 12 + 7] = gtime();
         }
