@@ -343,7 +343,7 @@ int g_sm_count = 0;
 int rec_variant(const Dims& d) {
   if (!d.bf16) return 0;
   const char* e = getenv("MVAE_REC");
-  int v = e ? atoi(e) : 3;
+  int v = e ? atoi(e) : 32;   // 32: pair kernel forward + K-split BPTT (gru_rec2.cu); 3: pair kernel both ways
   if (v <= 0) return 0;
   if (g_sm_count == 0) {
     int dev = 0;

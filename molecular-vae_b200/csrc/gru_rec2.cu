@@ -13,6 +13,12 @@
 // Cross-pair dependencies (all 8 pairs of a row group must have published step t before step t+1 loads) go
 // through per-(tile, parity) global counters with release/acquire; everything inside a cluster uses mbarriers.
 // Every wait is bounded (2 s) and reports through err_flag.
+//
+// KS (BPTT only, "K-split"): the sweep is bound by the L2 -> SM delivery of the streamed operand (8 unit slices each
+// re-read the whole [Bp x 3Hp] dgh slab: 100 MB per step).  With KS a cluster of TWO pairs owns 128 units: each pair
+// keeps the W_hh^T rows of those 128 units for ONE HALF of K (same 96 KB per CTA), streams only that half of dgh
+// (operand traffic halves), and the two pairs exchange the fp32 partial sums of the 64 units the other one finalises
+// through distributed shared memory (32 KB per CTA per tile-step, off the L2 path).
 #include "common.cuh"
 #include "gru_rec.h"
 #include "rec_common.cuh"
@@ -97,6 +103,31 @@ __device__ __forceinline__ void tma_load_3d_2sm_mc(void* smem_dst, const CUtenso
       "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_addr), "h"(mask), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+__device__ __forceinline__ void st_cluster_f32(uint32_t cluster_addr, uint32_t v) {
+  asm volatile("st.shared::cluster.b32 [%0], %1;" ::"r"(cluster_addr), "r"(v) : "memory");
+}
+// wait on a LOCAL mbarrier whose arrivals come from another CTA of the cluster (release.cluster): acquire at cluster scope
+__device__ __forceinline__ bool wait_bar_cluster(uint64_t* bar, uint32_t parity, int* err_flag) {
+  uint32_t spins = 0;
+  unsigned long long t0 = 0;
+  for (;;) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred P;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t}\n"
+        : "=r"(ok)
+        : "r"(ptx::smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (ok) return true;
+    if ((++spins & 0x3FF) == 0) {
+      const unsigned long long now = gtime();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 2000000000ull) { atomicExch(err_flag, 4); return false; }
+      if (*(volatile int*)err_flag) return false;
+    }
+  }
+}
 __device__ __forceinline__ void remote_arrive_relaxed(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
@@ -126,34 +157,40 @@ __device__ __forceinline__ void commit2_mc(uint64_t* bar, uint16_t mask) {
       : "memory");
 }
 
-template <bool BWD, bool FAST, int CL>
+template <bool BWD, bool FAST, int CL, bool KS>
 __global__ void __launch_bounds__(THREADS, 1)
 gru_rec2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmA, const Params2 p) {
-  constexpr int NB = BWD ? RU : 3 * RU;        // MMA N of the pair
+  static_assert(!KS || (BWD && CL == 2), "K-split is a BPTT variant of the pair kernel");
+  constexpr int NST = KS ? 6 : STAGES;         // operand stages (KS gives 32 KB to the exchange buffer)
+  constexpr int XBUF = 128 * RU * 4;           // KS: one tile's incoming partial sums (128 rows x 64 units fp32)
+  constexpr int NB = BWD ? (KS ? 2 * RU : RU) : 3 * RU;        // MMA N of the pair
   constexpr int NBH = NB / 2;                  // resident rows per CTA
   constexpr int CHUNK = NBH * 128;             // bytes of one 64-wide K chunk of the resident half
   constexpr int MASTER0 = NTILES * NB;
-  constexpr int TMEM_COLS = BWD ? 256 : 512;
+  constexpr int TMEM_COLS = (BWD && !KS) ? 256 : 512;
   constexpr int NSAME = CL / 2;                // same-parity CTAs (= pairs) per cluster
   constexpr int A_PART = A_STAGE / NSAME;      // bytes of a stage this CTA loads and multicasts
   constexpr int A_PART_ROWS = 128 / NSAME;
   static_assert(NTILES * (NB + RU) <= TMEM_COLS, "TMEM");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int KC = (BWD ? 3 * p.Hp : p.Hp) / 64;
+  const int KC = (BWD ? 3 * p.Hp : p.Hp) / 64 / (KS ? 2 : 1);   // k chunks this pair contracts over
   const int KCS = (p.debug & 256) ? KC / 2 : KC;   // timing experiment: stream only half of K (wrong results)
   uint8_t* sW = smem;
   uint8_t* sA = smem + (size_t)KC * CHUNK;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sA + STAGES * A_STAGE);
-  uint64_t* full_bar = bars;                         // [STAGES] own operand stage landed (tx)
-  uint64_t* empty_bar = bars + STAGES;               // [STAGES] all 4 pairs of the cluster consumed the stage
-  uint64_t* pfull_bar = bars + 2 * STAGES;           // [STAGES] leader: peer's stage landed (relayed)
-  uint64_t* tfull_bar = bars + 3 * STAGES;           // [NTILES] accumulator ready (both CTAs)
+  float* xbuf = reinterpret_cast<float*>(sA + NST * A_STAGE);   // KS: [64 units][128 rows], reused by consecutive tile-steps
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sA + NST * A_STAGE + (KS ? XBUF : 0));
+  uint64_t* full_bar = bars;                         // [NST] own operand stage landed (tx)
+  uint64_t* empty_bar = bars + NST;                  // [NST] all pairs that share the stage consumed it
+  uint64_t* pfull_bar = bars + 2 * NST;              // [NST] leader: peer's stage landed (relayed)
+  uint64_t* tfull_bar = bars + 3 * NST;              // [NTILES] accumulator ready (both CTAs)
   uint64_t* tempty_bar = tfull_bar + NTILES;         // [NTILES] leader: both CTAs drained the accumulator
   uint64_t* wfull_bar = tempty_bar + NTILES;         // resident weights landed
   uint64_t* pwfull_bar = wfull_bar + 1;              // leader: peer's weights landed
   uint64_t* epi_bar = pwfull_bar + 1;                // [NTILES] all epilogue threads finished the tile
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(epi_bar + NTILES);
+  uint64_t* xfull_bar = epi_bar + NTILES;            // KS: the partner pair's partial sums landed in our xbuf
+  uint64_t* xfree_bar = xfull_bar + 1;               // KS: the partner consumed what we last wrote into ITS xbuf
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(xfree_bar + 1);
   float* sBias = reinterpret_cast<float*>(tmem_holder + 2);  // fwd: b_hn for the pair's 64 units
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -161,17 +198,20 @@ gru_rec2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
   const int parity = rank & 1;
   const bool leader = parity == 0;
   const int pair = blockIdx.x >> 1;                   // global pair index along the hidden dimension
-  const int u0 = pair * RU;
+  const int u0 = pair * RU;                           // first of the 64 units this pair finalises
+  const int kh = KS ? (pair & 1) : 0;                 // KS: which half of K this pair contracts over
+  const int koff = KS ? kh * (3 * p.Hp / 2) : 0;      // first dgh column (= first W_hh^T column) of that half
+  const int U0 = KS ? (pair >> 1) * 2 * RU : u0;      // KS: first of the 128 units of the two-pair cluster
   const int tile0 = blockIdx.y * NTILES;
   const int ntiles = min(NTILES, p.pair_tiles - tile0);
   const uint16_t mask_par = (uint16_t)((CL == 8 ? 0x55 : CL == 4 ? 0x5 : 0x1) << parity);  // same-parity CTAs
   const uint16_t mask_pair = (uint16_t)(3u << (rank & ~1u));
-  const int qd = rank >> 1;                           // which 32-row quarter of the operand tile this CTA loads
+  const int qd = CL == 2 ? 0 : (int)(rank >> 1);      // multicast clusters: which part of the operand tile this CTA loads
 
   if (threadIdx.x == 0) {
     ptx::tma_prefetch_desc(&tmW);
     ptx::tma_prefetch_desc(&tmA);
-    for (int s = 0; s < STAGES; ++s) {
+    for (int s = 0; s < NST; ++s) {
       ptx::mbar_init(&full_bar[s], 1);
       ptx::mbar_init(&empty_bar[s], NSAME);
       ptx::mbar_init(&pfull_bar[s], 1);
@@ -181,6 +221,8 @@ gru_rec2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
       ptx::mbar_init(&tempty_bar[i], 2);
       ptx::mbar_init(&epi_bar[i], EPI_WARPS * 32);
     }
+    ptx::mbar_init(xfull_bar, EPI_WARPS);
+    ptx::mbar_init(xfree_bar, EPI_WARPS);
     ptx::mbar_init(wfull_bar, 1);
     ptx::mbar_init(pwfull_bar, 1);
     ptx::fence_mbar_init();
@@ -203,7 +245,11 @@ gru_rec2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
       else ptx::mbar_arrive_expect_tx(wfull_bar, (uint32_t)(KC * CHUNK));
       for (int kc = 0; kc < KC; ++kc) {
         uint8_t* dst = sW + (size_t)kc * CHUNK;
-        if (BWD) {
+        if (BWD && KS) {
+#pragma unroll
+          for (int b = 0; b < 2; ++b)                                       // 64 rows (units) of W_hh^T, this pair's K half
+            tma_load_2d_2sm(dst + b * 4096, &tmW, wbar_addr, koff + kc * 64, U0 + 64 * parity + 32 * b);
+        } else if (BWD) {
           if (DIRECT) tma_load_2d_2sm(dst, &tmW, wbar_addr, kc * 64, u0 + 32 * parity);
           else tma_load_2d(dst, &tmW, wfull_bar, kc * 64, u0 + 32 * parity);     // 32 rows of W_hh^T
         } else {
@@ -237,7 +283,7 @@ gru_rec2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
               {
                 const uint32_t fb = mapa(ptx::smem_u32(&full_bar[s]), lrank);
                 for (int r0 = 0; r0 < 128; r0 += p.a_box_rows)
-                  tma_load_3d_2sm(sA + s * A_STAGE + r0 * 128, &tmA, fb, kc * 64, row0 + r0, slab);
+                  tma_load_3d_2sm(sA + s * A_STAGE + r0 * 128, &tmA, fb, koff + kc * 64, row0 + r0, slab);
               }
               else
                 tma_load_3d_2sm_mc(sA + s * A_STAGE + qd * A_PART, &tmA, &full_bar[s], mask_par, kc * 64, row0, slab);
@@ -245,7 +291,7 @@ gru_rec2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
               ptx::mbar_arrive_expect_tx(&full_bar[s], A_STAGE);
               tma_load_3d_mc(sA + s * A_STAGE + qd * A_PART, &tmA, &full_bar[s], mask_par, kc * 64, row0, slab);
             }
-            if (++s == STAGES) { s = 0; ph ^= 1; }
+            if (++s == NST) { s = 0; ph ^= 1; }
           }
           if (p.trace && blockIdx.x == 0 && blockIdx.y == 0) p.trace[((size_t)step * NTILES + i) * 12 + 1] = gtime();
         }
@@ -268,7 +314,7 @@ gru_rec2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
             for (int kc = 0; kc < KC; ++kc) {
               if (!wait_bar(&full_bar[s], ph, p.err_flag)) goto done;
               remote_arrive_relaxed(mapa(ptx::smem_u32(&pfull_bar[s]), lrank));
-              if (++s == STAGES) { s = 0; ph ^= 1; }
+              if (++s == NST) { s = 0; ph ^= 1; }
             }
       } else {
         // ===================== MMA issuer (even CTA, one thread for the pair) =====================
@@ -299,8 +345,9 @@ gru_rec2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
                   const uint64_t bdesc = ptx::umma_smem_desc_sw128(b_addr + k * 32, 16, 1024);
                   umma2_bf16(d_tmem, adesc, bdesc, idesc, (kc0 > 0 || k > 0) ? 1u : 0u);
                 }
-                commit2_mc(&empty_bar[s], (uint16_t)((1u << CL) - 1));      // stage s is free in every CTA of the cluster (for this pair)
-                if (++s == STAGES) { s = 0; ph ^= 1; }
+                // stage s is free (for this pair) in every CTA that shares it: the pair itself, or the whole multicast cluster
+                commit2_mc(&empty_bar[s], CL == 2 ? mask_pair : (uint16_t)((1u << CL) - 1));
+                if (++s == NST) { s = 0; ph ^= 1; }
               }
             }
             const unsigned long long t_issue = (p.debug & 8) ? gtime() : 0ull;
@@ -437,9 +484,36 @@ gru_rec2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
         } else {
           uint32_t acc[16], cm[16];
           if (step > 0) {
-            ptx::tmem_ld_32x16(tmem_base + lane_off + i * NB + uc, acc);
-            ptx::tmem_ld_32x16(master_addr, cm);
-            ptx::tmem_ld_wait();
+            if (KS) {
+              // this pair contracted over ONE half of K for all 128 units of the cluster: hand the partial sums of the 64
+              // units the partner pair finalises to the partner CTA (same parity -> same rows) through its shared memory,
+              // and add the partner's partial sums for our own 64 units.
+              uint32_t oth[16];
+              ptx::tmem_ld_32x16(tmem_base + lane_off + i * NB + RU * (1 - kh) + uc, oth);
+              ptx::tmem_ld_32x16(tmem_base + lane_off + i * NB + RU * kh + uc, acc);
+              ptx::tmem_ld_32x16(master_addr, cm);
+              ptx::tmem_ld_wait();
+              const uint32_t partner = rank ^ 2u;
+              const uint32_t ev = (uint32_t)((step - 1) * ntiles + i);   // exchange number (tile-steps alternate strictly)
+              // xbuf[unit][row]: a warp store covers 32 consecutive rows of one unit (128 contiguous bytes)
+              const uint32_t xloc = ptx::smem_u32(xbuf + (size_t)uc * 128 + q * 32 + lane);
+              const uint32_t xrem = mapa(xloc, partner);
+              if (ev > 0) (void)wait_bar_cluster(xfree_bar, (ev - 1) & 1u, p.err_flag);   // partner read exchange ev-1
+#pragma unroll
+              for (int k = 0; k < 16; ++k) st_cluster_f32(xrem + (uint32_t)k * 512u, oth[k]);
+              __syncwarp();
+              if (lane == 0) remote_arrive(mapa(ptx::smem_u32(xfull_bar), partner));   // release.cluster, 16 per exchange
+              (void)wait_bar_cluster(xfull_bar, ev & 1u, p.err_flag);
+              const float* xin = xbuf + (size_t)uc * 128 + q * 32 + lane;
+#pragma unroll
+              for (int k = 0; k < 16; ++k) acc[k] = __float_as_uint(__uint_as_float(acc[k]) + xin[k * 128]);
+              __syncwarp();
+              if (lane == 0) remote_arrive(mapa(ptx::smem_u32(xfree_bar), partner));
+            } else {
+              ptx::tmem_ld_32x16(tmem_base + lane_off + i * NB + uc, acc);
+              ptx::tmem_ld_32x16(master_addr, cm);
+              ptx::tmem_ld_wait();
+            }
           } else {
 #pragma unroll
             for (int k = 0; k < 16; ++k) { acc[k] = 0u; cm[k] = 0u; }
@@ -517,12 +591,12 @@ int encode(CUtensorMap* map, const void* ptr, int rank, const cuuint64_t* dims, 
   return r == CUDA_SUCCESS ? MVAE_OK : MVAE_ERR_DRIVER;
 }
 
-template <bool BWD, bool FAST, int CL>
+template <bool BWD, bool FAST, int CL, bool KS = false>
 int launch2(const mvae_gru_rec_args& a, cudaStream_t st) {
   const int Hp = a.Hp, Bp = a.Bp, T = a.T;
-  constexpr int NBH = (BWD ? RU : 3 * RU) / 2;
-  const int KC = (BWD ? 3 * Hp : Hp) / 64;
-  const size_t smem = (size_t)KC * NBH * 128 + (size_t)STAGES * A_STAGE + 1024 + 1024;
+  constexpr int NBH = (BWD ? (KS ? 2 * RU : RU) : 3 * RU) / 2;
+  const int KC = (BWD ? 3 * Hp : Hp) / 64 / (KS ? 2 : 1);
+  const size_t smem = (size_t)KC * NBH * 128 + (size_t)(KS ? 6 : STAGES) * A_STAGE + (KS ? 128 * RU * 4 : 0) + 1024 + 1024;
   if (smem > 232448) return MVAE_ERR_UNSUPPORTED;
   CUtensorMap tmW, tmA;
   {
@@ -552,7 +626,7 @@ int launch2(const mvae_gru_rec_args& a, cudaStream_t st) {
   p.gi = a.gi; p.gi_tstride = a.gi_tstride; p.bhn = a.bhh; p.hs = a.hs; p.sv = a.sv; p.dX = a.dX; p.dG = a.dG;
   p.counters = a.counters; p.err_flag = a.err_flag; p.trace = a.trace; p.debug = a.debug; p.ones_col = a.ones_col;
   p.a_box_rows = a.a_box_rows > 0 ? a.a_box_rows : 128;
-  auto kern = gru_rec2_kernel<BWD, FAST, CL>;
+  auto kern = gru_rec2_kernel<BWD, FAST, CL, KS>;
   static bool attr = false;
   if (!attr) {
     MVAE_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -566,7 +640,7 @@ int launch2(const mvae_gru_rec_args& a, cudaStream_t st) {
   cfg.stream = st;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeClusterDimension;
-  at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  at[0].val.clusterDim.x = KS ? 4 : CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at; cfg.numAttrs = 1;
   MVAE_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, tmW, tmA, p));
   return MVAE_OK;
@@ -579,8 +653,8 @@ template <int CL> int max_clusters_t(int backward) {
   at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at; cfg.numAttrs = 1;
   int n = -1;
-  if (backward) { cudaFuncSetAttribute(gru_rec2_kernel<true, false, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 231424); cudaOccupancyMaxActiveClusters(&n, gru_rec2_kernel<true, false, CL>, &cfg); }
-  else { cudaFuncSetAttribute(gru_rec2_kernel<false, false, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 231424); cudaOccupancyMaxActiveClusters(&n, gru_rec2_kernel<false, false, CL>, &cfg); }
+  if (backward) { cudaFuncSetAttribute(gru_rec2_kernel<true, false, CL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 231424); cudaOccupancyMaxActiveClusters(&n, gru_rec2_kernel<true, false, CL, false>, &cfg); }
+  else { cudaFuncSetAttribute(gru_rec2_kernel<false, false, CL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 231424); cudaOccupancyMaxActiveClusters(&n, gru_rec2_kernel<false, false, CL, false>, &cfg); }
   return n;
 }
 }  // namespace
@@ -589,12 +663,14 @@ int mvae_gru_rec2_max_clusters(int backward, int cluster) {
   return cluster == 8 ? max_clusters_t<8>(backward) : cluster == 4 ? max_clusters_t<4>(backward) : max_clusters_t<2>(backward);
 }
 
-// variant 3.  Requires Bp % 256 == 0 and Hp in {256, 512}.  a->bhh must point at the n-gate slice of the padded
+// variant 3.  Requires Bp % 256 == 0 and Hp in {256, 512}.  a->variant 32: K-split BPTT sweep (clusters of two pairs; the
+// forward sweep of that variant is the plain pair kernel).  a->bhh must point at the n-gate slice of the padded
 // b_hh (b_hr / b_hz are expected to be folded into gi by the caller).  a->variant: 3 -> clusters of 2 (pair only),
 // 34 -> clusters of 4, 38 -> clusters of 8 (operand multicast across the pairs of a cluster).
 int mvae_gru_rec2_launch(const mvae_gru_rec_args* a, int fast_gates, cudaStream_t stream) {
   if (!a || a->Bp % 256 || (a->Hp != 256 && a->Hp != 512) || a->T < 1) return MVAE_ERR_INVALID;
   const int cl = a->variant == 38 ? 8 : a->variant == 34 ? 4 : 2;
+  if (a->variant == 32 && a->backward) return launch2<true, false, 2, true>(*a, stream);
 #define MVAE_DISPATCH(CLV)                                                                     \
   if (a->backward) return launch2<true, false, CLV>(*a, stream);                                \
   return fast_gates ? launch2<false, true, CLV>(*a, stream) : launch2<false, false, CLV>(*a, stream);

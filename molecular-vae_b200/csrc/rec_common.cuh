@@ -36,7 +36,7 @@ __device__ __forceinline__ bool wait_counter(const unsigned int* ctr, unsigned i
   uint32_t spins = 0;
   unsigned long long t0 = 0;
   while (ld_acquire(ctr) < target) {
-    __nanosleep(64);
+    __nanosleep(32);
     if ((++spins & 0xFF) == 0) {
       const unsigned long long now = gtime();
       if (t0 == 0) t0 = now;

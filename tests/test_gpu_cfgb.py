@@ -125,7 +125,7 @@ def test_greedy_decode_bit_exact_fp32():
     assert safe.mean() > 0.99
 
 
-@pytest.mark.parametrize("rec", ["0", "1", "3"])
+@pytest.mark.parametrize("rec", ["0", "1", "3", "32"])
 @pytest.mark.parametrize("B", [64, 200, 640])
 def test_fused_step_bf16_full_config(B, rec, monkeypatch):
     """rec selects the recurrence engine: 0 = per-step GEMM + gate kernels, 1/2 = persistent fused kernel variants."""

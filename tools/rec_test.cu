@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <math.h>
 #include <vector>
 #include "../molecular-vae_b200/csrc/gru_rec.h"
 extern "C" const char* mvae_last_cuda_error(void);
@@ -68,6 +69,50 @@ int main(int argc, char** argv) {
       }
     }
     fflush(stdout);
+  }
+  if (variant == 32) {
+    // cross-check: BPTT of the K-split variant against the pair kernel on identical inputs
+    const size_t n = (size_t)T * B * 4 * Hp;
+    {
+      std::vector<__nv_bfloat16> hx((size_t)T * slab);
+      unsigned s2 = 7;
+      for (auto& v : hx) { s2 = s2 * 1664525u + 1013904223u; v = __float2bfloat16(((s2 >> 8) & 0xFFFF) / 65536.0f - 0.5f); }
+      cudaMemcpy(dX, hx.data(), hx.size() * 2, cudaMemcpyHostToDevice);
+    }
+    std::vector<__nv_bfloat16> ref(n), got(n);
+    mvae_gru_rec_args a{};
+    a.backward = 1; a.Bp = B; a.Hp = Hp; a.T = T; a.W = WT; a.gi = gi; a.gi_tstride = (long long)B * 3 * Hp; a.bhh = bhh;
+    a.hs = hs; a.sv = sv; a.dX = dX; a.dG = dG; a.counters = ctr; a.err_flag = err; a.ones_col = -1;
+    for (int pass = 0; pass < 2; ++pass) {
+      a.variant = pass ? 32 : 3;
+      cudaMemset(dG, 0, n * 2);
+      mvae_gru_rec2_launch(&a, 0, 0);
+      cudaDeviceSynchronize();
+      cudaMemcpy(pass ? got.data() : ref.data(), dG, n * 2, cudaMemcpyDeviceToHost);
+    }
+    size_t bad = 0; double maxd = 0, maxr = 0;
+    std::vector<size_t> by_t(T, 0), by_pair(8, 0), by_rowblk(B / 128, 0), by_blk(4, 0);
+    for (size_t i = 0; i < n; ++i) {
+      const float r = __bfloat162float(ref[i]), g = __bfloat162float(got[i]);
+      const double d = fabs((double)r - g);
+      if (fabs(r) > maxr) maxr = fabs(r);
+      if (d > maxd) maxd = d;
+      if (d > 2e-2 * fabs(r) + 2e-3) {
+        if (bad < 12) {
+          const size_t t = i / ((size_t)B * 4 * Hp), row = (i / (4 * Hp)) % B, col = i % (4 * Hp);
+          printf("  mismatch t=%zu row=%zu col=%zu (block %zu unit %zu): pair %g ksplit %g\n", t, row, col, col / Hp, col % Hp, r, g);
+        }
+        ++bad;
+        const size_t t = i / ((size_t)B * 4 * Hp), row = (i / (4 * Hp)) % B, col = i % (4 * Hp);
+        by_t[t]++; by_pair[(col % Hp) / 64]++; by_rowblk[row / 128]++; by_blk[col / Hp]++;
+      }
+    }
+    printf("  by t:"); for (auto v : by_t) printf(" %zu", v);
+    printf("\n  by pair:"); for (auto v : by_pair) printf(" %zu", v);
+    printf("\n  by row block (128):"); for (auto v : by_rowblk) printf(" %zu", v);
+    printf("\n  by dG block:"); for (auto v : by_blk) printf(" %zu", v);
+    printf("\n");
+    printf("K-split vs pair kernel dG: %zu mismatching of %zu, max |diff| %g, max |ref| %g\n", bad, n, maxd, maxr);
   }
   return 0;
 }
