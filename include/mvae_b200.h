@@ -182,6 +182,11 @@ typedef struct mvae_moses_desc {
   /* mosesfile.py variant (mosesfile.py:6-157; BASELINE config 4): */
   int32_t q_bidir;        /* 1: bidirectional encoder GRU (mosesfile.py:21-28), heads read cat(h_fwd, h_bwd) (:115-116) */
   int32_t q_linear_heads; /* 1: q_mu / q_logvar are single Linear(Hq*(1+bidir), d_z) (mosesfile.py:31-32); 0: the 2-layer MLPs */
+  /* train-mode dropout between decoder GRU layers (nn.GRU(dropout=0.2), mosesvae.py:38,78): element (l, t, b, j) of the
+   * output of layer l < L-1 is kept iff u01(dropout_seed, l, t, b, j) >= d_dropout and scaled by 1/(1-d_dropout); the
+   * counter-based u01 is restated in oracle/moses_oracle.dropout_masks so a parity run can inject the same mask.  0 = off. */
+  float d_dropout;
+  uint32_t dropout_seed;
 } mvae_moses_desc;
 /* parameters / gradients: host arrays of fp32 device pointers in this order (reference shapes, row-major):
  *   0 x_emb.weight (V,V) | 1-4 encoder_rnn.{weight_ih_l0 (3Hq,V), weight_hh_l0, bias_ih_l0, bias_hh_l0}

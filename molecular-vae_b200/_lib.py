@@ -32,7 +32,9 @@ class MosesDesc(ctypes.Structure):
                                               "mlp_hidden", "pad_id", "precision")] + [("kl_weight", ctypes.c_float),
                                                                                    ("recon_weight", ctypes.c_float),
                                                                                    ("q_bidir", ctypes.c_int32),
-                                                                                   ("q_linear_heads", ctypes.c_int32)]
+                                                                                   ("q_linear_heads", ctypes.c_int32),
+                                                                                   ("d_dropout", ctypes.c_float),
+                                                                                   ("dropout_seed", ctypes.c_uint32)]
 
 
 class BindingDesc(ctypes.Structure):

@@ -28,6 +28,7 @@ struct MDims {
   int bidir, lin, Hin;   // mosesfile.py variant: bidirectional encoder (:21-28), single-Linear heads (:31-32); Hin = Hq*(1+bidir)
   bool bf16;
   float kl_w, rec_w;
+  float drop; unsigned int drop_seed;   // train-mode dropout between decoder layers (0 = off)
 };
 
 int make_dims(const mvae_moses_desc* d, MDims* o) {
@@ -40,6 +41,8 @@ int make_dims(const mvae_moses_desc* d, MDims* o) {
   o->B = d->batch; o->Bp = round_up(d->batch, 256); o->T = d->max_len; o->V = d->vocab; o->CP = 64;
   o->Z = d->d_z; o->Hq = d->q_hidden; o->Hd = d->d_hidden; o->L = d->d_layers; o->MLP = d->mlp_hidden;
   o->pad = d->pad_id; o->bf16 = d->precision == MVAE_PREC_BF16; o->kl_w = d->kl_weight; o->rec_w = d->recon_weight;
+  if (!(d->d_dropout >= 0.f && d->d_dropout < 1.f)) return MVAE_ERR_INVALID;
+  o->drop = d->d_dropout; o->drop_seed = d->dropout_seed;
   o->bidir = d->q_bidir ? 1 : 0; o->lin = d->q_linear_heads ? 1 : 0; o->Hin = o->Hq * (1 + o->bidir);
   return MVAE_OK;
 }
@@ -52,6 +55,7 @@ struct MWS {
   void *OH;         // [T*Bp][CP] TA one-hot of the tokens
   void *gi;         // [T][Bp][3Hd] TA
   void *hs_enc, *sv_enc, *hs[4], *sv[4], *dG, *dX, *dlogits;
+  void *hdrop;                           // [T][Bp][Hd] dropped copy of a decoder layer's outputs (input of the next layer)
   void *hs_encr, *sv_encr, *Whh_encr;   // reverse direction of a bidirectional encoder
   float *bhh_encr, *TBLer, *hlastr, *hcat, *dhcat;
   float *gh, *h32[2], *dh_carry, *logits;
@@ -89,6 +93,7 @@ void carve(const MDims& d, void* base, MWS* w) {
     w->sv[l] = c.take<uint8_t>(T * Bp * 4 * Hd * es);
   }
   w->dG = c.take<uint8_t>(T * Bp * 4 * Hd * es); w->dX = c.take<uint8_t>(T * Bp * Hd * es);
+  w->hdrop = c.take<uint8_t>(T * Bp * Hd * es);
   w->dlogits = c.take<uint8_t>(T * Bp * d.CP * es);
   w->gh = c.take<float>(Bp * 3 * Hd); w->h32[0] = c.take<float>(Bp * Hd); w->h32[1] = c.take<float>(Bp * Hd);
   w->dh_carry = c.take<float>(Bp * Hd); w->logits = c.take<float>(T * Bp * d.CP);
@@ -286,6 +291,24 @@ __global__ void finalize_kernel(const double* __restrict__ kl_sum, const double*
   out[0] = (float)(klw * kl + recw * rec); out[1] = (float)kl; out[2] = (float)rec; out[3] = (float)M[0];
 }
 
+// counter-based uniform in (0,1): the same generator the sampler uses (restated in oracle/moses_oracle.u01_hash)
+__device__ __forceinline__ float u01_hash(unsigned long long seed, unsigned int b, unsigned int i);
+// dropout between decoder layers: element (t, b, j) of layer l is kept iff u01(seed + l, t*B + b, j) >= p.
+// mode 0: out = keep ? x / (1 - p) : 0 (forward copy);  mode 1: x *= keep / (1 - p) in place (backward)
+template <typename TA>
+__global__ void dropout_kernel(const TA* x, TA* out /* may alias x */, unsigned long long seed, float p, int B, int Bp,
+                               int H, int T) {
+  const long long total = (long long)T * Bp * H;
+  const float sc = 1.0f / (1.0f - p);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int j = (int)(i % H);
+    const long long rb = i / H;
+    const int b = (int)(rb % Bp), t = (int)(rb / Bp);
+    float v = 0.f;
+    if (b < B && u01_hash(seed, (unsigned)(t * B + b), (unsigned)j) >= p) v = to_f32<TA>(x[i]) * sc;
+    out[i] = from_f32<TA>(v);
+  }
+}
 template <typename TA>
 __global__ void final_state_kernel(const TA* __restrict__ hsA, const float* __restrict__ h32, long long n, float* __restrict__ out) {
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -422,10 +445,17 @@ int step_t(const MDims& d, const MWS& w, const float* const* P, float* const* G,
   RC(sg(st, P[ix.emb()], V, 1, P[ix.wih(0)], 1, IN0, w.TBLd, 3 * Hd, V, 3 * Hd, V, nullptr, simt::ACT_NONE, 0));
   RC(sg(st, w.z, Z, 1, P[ix.wih(0)] + V, 1, IN0, w.zproj, 3 * Hd, B, 3 * Hd, Z, P[ix.bih(0)], simt::ACT_NONE, 0));
   gather_rows_kernel<TA><<<grid_for((long long)TB * 3 * Hd), 256, 0, st>>>(w.TBLd, 3 * Hd, ids, T, w.zproj, B, Bp, T, (TA*)w.gi); KCHECK();
+  const bool drop = d.drop > 0.f;
   for (int l = 0; l < L; ++l) {
-    if (l >= 1)
-      RC(gemm<TA>(w.err_flag, st, (const TA*)w.hs[l - 1] + (size_t)Bp * Hd, Hd, false, (const TA*)w.Wih[l], Hd, true, w.gi,
-                  3 * Hd, true, TB, 3 * Hd, Hd, w.bih[l], false, 1));
+    if (l >= 1) {
+      const TA* X = (const TA*)w.hs[l - 1] + (size_t)Bp * Hd;
+      if (drop) {   // nn.GRU(dropout=p) in train mode: dropout on the outputs of every layer but the last (mosesvae.py:78)
+        dropout_kernel<TA><<<grid_for((long long)TB * Hd), 256, 0, st>>>(X, (TA*)w.hdrop, (unsigned long long)d.drop_seed + (l - 1), d.drop,
+                                                                        B, Bp, Hd, T); KCHECK();
+        X = (const TA*)w.hdrop;
+      }
+      RC(gemm<TA>(w.err_flag, st, X, Hd, false, (const TA*)w.Wih[l], Hd, true, w.gi, 3 * Hd, true, TB, 3 * Hd, Hd, w.bih[l], false, 1));
+    }
     RC(gru_fwd<TA>(d, w, st, (const TA*)w.gi, (const TA*)w.Whh[l], w.bhh[l], (TA*)w.hs[l], (TA*)w.sv[l], Hd, w.h0, nullptr, nullptr));
   }
   RC(gemm<TA>(w.err_flag, st, (const TA*)w.hs[L - 1] + (size_t)Bp * Hd, Hd, false, (const TA*)w.Wfc, Hd, true, w.logits, CP, false,
@@ -465,10 +495,19 @@ int step_t(const MDims& d, const MWS& w, const float* const* P, float* const* G,
     gate_bias_grads_kernel<<<ceil_div(3 * Hd, 256), 256, 0, st>>>(w.csum, Hd, G[ix.bih(l)], G[ix.bhh(l)]); KCHECK();
     if (l >= 1) {
       const TA* X = (const TA*)w.hs[l - 1] + (size_t)Bp * Hd;
+      if (drop) {   // regenerate the dropped input of this layer (same counter-based mask)
+        dropout_kernel<TA><<<grid_for((long long)TB * Hd), 256, 0, st>>>(X, (TA*)w.hdrop, (unsigned long long)d.drop_seed + (l - 1), d.drop,
+                                                                        B, Bp, Hd, T); KCHECK();
+        X = (const TA*)w.hdrop;
+      }
       RC(memset_async(w.dW_p, (size_t)3 * Hd * Hd * 4, st));
       RC(gemm<TA>(w.err_flag, st, dG, 4 * Hd, true, X, Hd, false, w.dW_p, Hd, false, 3 * Hd, Hd, TB, nullptr, true, wsplits, 256));
       simt::unpad_gate_matrix_kernel<<<grid_for(3ll * Hd * Hd), 256, 0, st>>>(w.dW_p, Hd, Hd, G[ix.wih(l)], Hd, Hd, 2, 0, 1); KCHECK();
       RC(gemm<TA>(w.err_flag, st, dG, 4 * Hd, false, (const TA*)w.Wih_nrz[l], Hd, false, w.dX, Hd, true, TB, Hd, 3 * Hd, nullptr, false, 1));
+      if (drop) {   // gradient wrt the undropped outputs of layer l-1
+        dropout_kernel<TA><<<grid_for((long long)TB * Hd), 256, 0, st>>>((const TA*)w.dX, (TA*)w.dX, (unsigned long long)d.drop_seed + (l - 1),
+                                                                        d.drop, B, Bp, Hd, T); KCHECK();
+      }
     } else {
       // layer 0: table gradient (tensor-core GEMM onehot^T * dgi) and the per-molecule z part (time sum)
       RC(memset_async(w.dTBL, (size_t)CP * 3 * Hd * 4, st));

@@ -54,6 +54,7 @@ class VAE(_MosesVAE):
         self._keys = mosesfile_param_order(config.d_n_layers)
         self._ws = None
         self.eps_override = None
+        self.dropout_seed_override = None
 
     def forward(self, x):
         """mosesfile.py:84-100: returns (kl_loss, recon_loss)."""

@@ -4,8 +4,9 @@ Same constructor (`VAE(vocab)` with the vocab duck-type of vocab.py:10-87), same
 (`encoder`, `decoder`, `vae` -> identical `state_dict()` keys incl. the aliases, and `model.encoder.parameters()` /
 `model.decoder.parameters()` feed separate optimisers as in moses_train_distrib_logp.py:267-268), same
 `forward(list[LongTensor]) -> (kl, recon, z, logvar, x_padded, y)`, `string2tensor` / `tensor2string`.
-`sample(n_batch, max_len, z, temp) -> (list[str], z)`.  `elbo_step()` is the fused fast path.  Not ported this round:
-train-mode dropout between decoder layers (the step treats dropout as the identity, i.e. the reference in eval()).
+`sample(n_batch, max_len, z, temp) -> (list[str], z)`.  `elbo_step()` is the fused fast path.  In train() mode the
+decoder GRU's inter-layer dropout (p = 0.2, mosesvae.py:38,78) is applied with a counter-based mask (the reference's
+cuDNN / torch mask stream cannot be reproduced; parity runs inject the same mask into the oracle); eval() disables it.
 """
 import ctypes
 
@@ -30,7 +31,8 @@ def moses_param_order(d_layers=3):
 class _MosesFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, model, ids, lens, eps, *params):
-        kl, recon, z, logvar, y = model._run(list(params), None, ids, lens, eps, 1.0, 1.0, want_y=True)
+        ctx.dropout = model._dropout()
+        kl, recon, z, logvar, y = model._run(list(params), None, ids, lens, eps, 1.0, 1.0, want_y=True, dropout=ctx.dropout)
         ctx.model, ctx.ids, ctx.lens, ctx.eps = model, ids, lens, eps
         ctx.save_for_backward(*params)
         ctx.mark_non_differentiable(z, logvar, y)
@@ -42,7 +44,7 @@ class _MosesFunction(torch.autograd.Function):
         grads = [torch.empty_like(p) for p in params]
         klw = float(dkl) if dkl is not None else 0.0
         rw = float(drecon) if drecon is not None else 0.0
-        ctx.model._run(params, grads, ctx.ids, ctx.lens, ctx.eps, klw, rw, want_y=False)
+        ctx.model._run(params, grads, ctx.ids, ctx.lens, ctx.eps, klw, rw, want_y=False, dropout=ctx.dropout)
         return (None, None, None, None, *grads)
 
 
@@ -142,6 +144,7 @@ class VAE(nn.Module):
         self._keys = moses_param_order(d_n_layers)
         self._ws = None
         self.eps_override = None
+        self.dropout_seed_override = None   # tests pin the counter-based dropout mask here
 
     @property
     def device(self):
@@ -169,7 +172,16 @@ class VAE(nn.Module):
         return (padded.to(dev), padded.to(device=dev, dtype=torch.uint8).contiguous(),
                 torch.tensor(lens, dtype=torch.int32, device=dev))
 
-    def _run(self, params, grads, ids, lens, eps, kl_weight, recon_weight, want_y):
+    def _dropout(self):
+        """(p, seed) of the train-mode dropout between decoder layers (mosesvae.py:38,78); p = 0 in eval mode."""
+        p = float(getattr(self.decoder_rnn, "dropout", 0.0)) if self.training else 0.0
+        if p <= 0.0:
+            return 0.0, 0
+        if self.dropout_seed_override is not None:
+            return p, int(self.dropout_seed_override)
+        return p, int(torch.randint(0, 2 ** 31 - 1, (1,)).item())
+
+    def _run(self, params, grads, ids, lens, eps, kl_weight, recon_weight, want_y, dropout=(0.0, 0)):
         if not torch.cuda.is_available():
             raise _lib.MvaeError("molecular-vae_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
         B, T = ids.shape
@@ -177,7 +189,7 @@ class VAE(nn.Module):
         prec = {"fp32": _lib.PREC_FP32, "bf16": _lib.PREC_BF16}[self.precision]
         d = MosesDesc(B, T, c["vocab"], c["d_z"], c["q_hidden"], c["d_hidden"], c["d_layers"], c["mlp_hidden"],
                       int(self.pad), prec, float(kl_weight), float(recon_weight), int(c.get("q_bidir", 0)),
-                      int(c.get("q_linear_heads", 0)))
+                      int(c.get("q_linear_heads", 0)), float(dropout[0]), int(dropout[1]))
         need = lib.mvae_moses_workspace_bytes(ctypes.byref(d))
         if need == 0:
             raise ValueError("invalid MOSES VAE description")
@@ -227,7 +239,8 @@ class VAE(nn.Module):
         for p in params:
             if p.grad is None:
                 p.grad = torch.empty_like(p)
-        self._run([p.data for p in params], [p.grad for p in params], ids, lens, eps, kl_weight, recon_weight, False)
+        self._run([p.data for p in params], [p.grad for p in params], ids, lens, eps, kl_weight, recon_weight, False,
+                  dropout=self._dropout())
         return self._last_scalars
 
     def sample_z_prior(self, n_batch):
@@ -244,7 +257,7 @@ class VAE(nn.Module):
         B, c = z.shape[0], self.cfg
         prec = {"fp32": _lib.PREC_FP32, "bf16": _lib.PREC_BF16}[self.precision]
         d = MosesDesc(B, int(max_len), c["vocab"], c["d_z"], c["q_hidden"], c["d_hidden"], c["d_layers"], c["mlp_hidden"],
-                      int(self.pad), prec, 1.0, 1.0, int(c.get("q_bidir", 0)), int(c.get("q_linear_heads", 0)))
+                      int(self.pad), prec, 1.0, 1.0, int(c.get("q_bidir", 0)), int(c.get("q_linear_heads", 0)), 0.0, 0)
         need = lib.mvae_moses_workspace_bytes(ctypes.byref(d))
         dev = z.device
         if self._ws is None or self._ws.numel() < need + 256 or self._ws.device != dev:

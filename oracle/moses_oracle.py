@@ -120,7 +120,28 @@ def _gru_layer_bwd(dout, dh_final, xin, w_ih, w_hh, c):
     return dx, dh, g
 
 
-def moses_step(P, seqs, eps, pad, kl_weight=1.0, need_grads=True, d_layers=3):
+def u01_hash(seed, b, i):
+    """The counter-based uniform of molecular-vae_b200/csrc/moses.cu (u01_hash), vectorised over numpy uint64 arrays."""
+    M = np.uint64(0xFFFFFFFFFFFFFFFF)
+    with np.errstate(over="ignore"):
+        x = (np.uint64(seed) + np.uint64(0x9E3779B97F4A7C15) * (b.astype(np.uint64) * np.uint64(1000003) + i.astype(np.uint64) + np.uint64(1))) & M
+        x ^= x >> np.uint64(30); x = (x * np.uint64(0xBF58476D1CE4E5B9)) & M
+        x ^= x >> np.uint64(27); x = (x * np.uint64(0x94D049BB133111EB)) & M
+        x ^= x >> np.uint64(31)
+    return ((x >> np.uint64(40)).astype(np.float64) + 0.5).astype(np.float32) * np.float32(1.0 / 16777216.0)
+
+
+def dropout_masks(seed, p, B, T, H, d_layers=3, dtype=np.float64):
+    """Scaled keep masks (B,T,H) for the outputs of decoder layers 0..L-2: include/mvae_b200.h (mvae_moses_desc.d_dropout)."""
+    t, b, j = np.meshgrid(np.arange(T), np.arange(B), np.arange(H), indexing="ij")
+    out = []
+    for l in range(d_layers - 1):
+        u = u01_hash(seed + l, (t * B + b).astype(np.uint64), j.astype(np.uint64))
+        out.append(((u >= np.float32(p)).astype(dtype) / (1.0 - p)).transpose(1, 0, 2))
+    return out
+
+
+def moses_step(P, seqs, eps, pad, kl_weight=1.0, need_grads=True, d_layers=3, drop_masks=None):
     """One fwd(+bwd) step of mosesvae.VAE.forward; the scalar differentiated is kl_weight*kl + recon
     (moses_train_distrib_logp.py:302-306)."""
     dt = P["decoder_fc.weight"].dtype
@@ -149,6 +170,8 @@ def moses_step(P, seqs, eps, pad, kl_weight=1.0, need_grads=True, d_layers=3):
     caches, inputs = [], []
     cur = xin
     for l in range(d_layers):
+        if l >= 1 and drop_masks is not None:
+            cur = cur * drop_masks[l - 1]                       # nn.GRU(dropout=p), train mode (mosesvae.py:78)
         inputs.append(cur)
         cur, _, c = _gru_layer_fwd(cur, L, P[f"decoder_rnn.weight_ih_l{l}"], P[f"decoder_rnn.weight_hh_l{l}"],
                                    P[f"decoder_rnn.bias_ih_l{l}"], P[f"decoder_rnn.bias_hh_l{l}"], h0)
@@ -185,7 +208,7 @@ def moses_step(P, seqs, eps, pad, kl_weight=1.0, need_grads=True, d_layers=3):
             key = {"w_ih": "weight_ih", "w_hh": "weight_hh", "b_ih": "bias_ih", "b_hh": "bias_hh"}[nm]
             G[f"decoder_rnn.{key}_l{l}"] = g[nm]
         dh0 += dh0_l
-        dout = dxl
+        dout = dxl if (l == 0 or drop_masks is None) else dxl * drop_masks[l - 1]
     demb = dout[..., :V].copy()
     dz = dout[..., V:].sum(1)
     G["decoder_lat.weight"] = dh0.T @ z
