@@ -359,6 +359,11 @@ int rec_variant(const Dims& d) {
 }
 // the fused path keeps a constant-1 pad column in every hidden-state slab (needs H < Hp)
 bool ones_column(const Dims& d) { return rec_variant(d) >= 3 && d.H < d.Hp; }
+// MVAE_FUSED_HEAD=0 falls back to logits in HBM + the separate softmax/BCE kernel (the parity cross-check)
+bool fuse_head_enabled() {
+  const char* e = getenv("MVAE_FUSED_HEAD");
+  return e ? atoi(e) != 0 : true;
+}
 // gate non-linearities of the fused forward sweep through tanh.approx (one MUFU op per gate, |err| ~ 5e-4, below the
 // bf16 rounding of the saved gates); MVAE_FAST_GATES=0 selects the exp/rcp forms.  fp32 check mode never uses it.
 int fast_gates() {
@@ -433,7 +438,7 @@ int prep_weights(const Dims& d, const WS& w, const float* const* P, cudaStream_t
 // from_z: decode-only entry (z given in w.z); save: keep BPTT state
 template <typename TA>
 int run_forward(const Dims& d, const WS& w, const float* const* P, const uint8_t* ids, const float* eps,
-                cudaStream_t st, bool decode_only, bool save) {
+                cudaStream_t st, bool decode_only, bool save, bool fuse_head = false) {
   const int B = d.B, Bp = d.Bp, T = d.T, Z = d.Z, H = d.H, Hp = d.Hp;
   const size_t slab = (size_t)Bp * Hp;
   RC(memset_async(w.err_flag, 4, st));
@@ -544,6 +549,18 @@ int run_forward(const Dims& d, const WS& w, const float* const* P, const uint8_t
   }
   // vocabulary head logits (models2d.py:44-45)
   const TA* top = (const TA*)w.hs[d.L - 1] + slab;
+  if constexpr (sizeof(TA) == 2) {
+    if (fuse_head) {
+      // fused head (models2d.py:44-46 + train.py:31-35): logits -> softmax -> BCE -> d(logits) inside the GEMM epilogue;
+      // the (T*B, C) logits / probabilities never reach HBM
+      mvae_umma_operand a{top, 0, (long long)T * Bp, Hp, Hp, 1, 0, 0, 0};
+      mvae_umma_operand b{w.W3_p, 0, d.CP, Hp, Hp, 1, 0, 0, 0};
+      mvae_umma_out o{w.logits, d.CP, 0, 0, w.b3_p, 0};
+      mvae_umma_head h{ids, B, Bp, T, d.C, d.max_len / ((float)B * (float)T * (float)d.C), w.dlogits, w.bce_sum, w.hit_count};
+      count();
+      return mvae_umma_gemm(&a, &b, &o, T * Bp, d.CP, Hp, 64, 1, 0, w.err_flag, st, &h);
+    }
+  }
   RC(gemm<TA>(d, w, st, top, Hp, false, (const TA*)w.W3_p, Hp, true, w.logits, d.CP, false, T * Bp, d.CP, Hp, w.b3_p,
               false, 1, 64));
   return MVAE_OK;
@@ -761,8 +778,9 @@ template <typename TA>
 int elbo_step_t(const Dims& d, const WS& w, const float* const* P, float* const* G, const uint8_t* ids,
                 const float* eps, float* out_scalars, float* mu_out, float* lv_out, cudaStream_t st) {
   RC(prep_weights<TA>(d, w, P, st, true));
-  RC(run_forward<TA>(d, w, P, ids, eps, st, false, true));
-  RC(head_fused<TA>(d, w, ids, nullptr, true, st));
+  const bool fuse = sizeof(TA) == 2 && fuse_head_enabled();
+  RC(run_forward<TA>(d, w, P, ids, eps, st, false, true, fuse));
+  if (!fuse) RC(head_fused<TA>(d, w, ids, nullptr, true, st));
   RC(run_backward<TA>(d, w, P, G, ids, eps, st, true, nullptr, nullptr));
   RC(finalize(d, w, out_scalars, mu_out, lv_out, st));
   return MVAE_OK;

@@ -46,6 +46,8 @@ struct KernelParams {
   int out_bf16;        // 1: bf16 output, 0: fp32
   int accumulate;      // fp32 only: D += result (plain RMW, or red.add when splits > 1)
   int* err_flag;
+  int head_mode;       // fused vocabulary-head epilogue (BN == 64 only), see mvae_umma_head
+  mvae_umma_head head;
 };
 
 __device__ __forceinline__ bool wait_bar(uint64_t* bar, uint32_t parity, int* err_flag) {
@@ -199,6 +201,89 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int row = m_blk * BM + q * 32 + lane;
       const bool row_ok = row < p.M;
       const bool add_bias = p.bias != nullptr && split == 0;
+      if constexpr (BN == 64) {
+        if (p.head_mode) {
+          // ---- fused vocabulary head: one thread owns one row's 64 logits (the quarter's second warp only signals)
+          if (chalf == 0) {
+            uint32_t r0[32], r1[32];
+            ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN, r0);
+            ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + 32, r1);
+            ptx::tmem_ld_wait();
+            const mvae_umma_head& h = p.head;
+            double loss = 0.0;
+            if (row_ok) {
+              const int t = row / h.Bp, b = row - t * h.Bp;
+              uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(h.dlogits) + (long long)row * 64);
+              if (b >= h.B) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) o[j] = make_uint4(0u, 0u, 0u, 0u);
+              } else {
+                const int y = h.ids[(long long)b * h.T + t];
+                // v: logits -> probabilities, g: d(loss)/d(p); every loop stops at the (warp-uniform) charset size so the
+                // 4 epilogue warps of a CTA do not pay for the 29 pad columns
+                float v[64], g[64];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) { v[j] = __uint_as_float(r0[j]); v[32 + j] = __uint_as_float(r1[j]); }
+                float m = -INFINITY;
+                int arg = 0;
+#pragma unroll
+                for (int j = 0; j < 64; ++j) {
+                  if (j >= h.C) break;
+                  if (p.bias) v[j] += __ldg(p.bias + j);
+                  if (v[j] > m) { m = v[j]; arg = j; }
+                }
+                float ssum = 0.f;
+#pragma unroll
+                for (int j = 0; j < 64; ++j) {
+                  if (j >= h.C) break;
+                  v[j] = __expf(v[j] - m);
+                  ssum += v[j];
+                }
+                const float inv = 1.0f / ssum;
+                float l = 0.f, gp = 0.f;
+#pragma unroll
+                for (int j = 0; j < 64; ++j) {
+                  if (j >= h.C) break;
+                  const float pj = v[j] * inv;
+                  const float x = (j == y) ? 1.f : 0.f;
+                  const float q1 = 1.f - pj;
+                  l -= fmaxf(__logf(x > 0.f ? pj : q1), -100.f);      // BCELoss clamps each log at -100
+                  const float gj = h.gscale * (pj - x) / fmaxf(pj * q1, 1e-12f);
+                  gp = fmaf(gj, pj, gp);
+                  v[j] = pj; g[j] = gj;
+                }
+#pragma unroll
+                for (int j8 = 0; j8 < 8; ++j8) {
+                  float d[8];
+#pragma unroll
+                  for (int k = 0; k < 8; ++k) {
+                    const int j = j8 * 8 + k;
+                    d[k] = j < h.C ? v[j] * (g[j] - gp) : 0.f;
+                  }
+                  uint4 pk;
+                  __nv_bfloat162 b0 = __floats2bfloat162_rn(d[0], d[1]);
+                  __nv_bfloat162 b1 = __floats2bfloat162_rn(d[2], d[3]);
+                  __nv_bfloat162 b2 = __floats2bfloat162_rn(d[4], d[5]);
+                  __nv_bfloat162 b3 = __floats2bfloat162_rn(d[6], d[7]);
+                  pk.x = *reinterpret_cast<uint32_t*>(&b0);
+                  pk.y = *reinterpret_cast<uint32_t*>(&b1);
+                  pk.z = *reinterpret_cast<uint32_t*>(&b2);
+                  pk.w = *reinterpret_cast<uint32_t*>(&b3);
+                  o[j8] = pk;
+                }
+                loss = (double)l;
+                if (h.hit_count && arg == y) atomicAdd(h.hit_count + b, 1);
+              }
+            }
+            for (int off = 16; off; off >>= 1) loss += __shfl_xor_sync(0xffffffffu, loss, off);
+            if (lane == 0 && h.bce_sum && loss != 0.0) atomicAdd(h.bce_sum, loss);
+          }
+          ptx::tc_fence_before();
+          ptx::mbar_arrive(&tempty_bar[acc]);
+          if (++acc == 2) { acc = 0; acc_ph ^= 1; }
+          continue;
+        }
+      }
 #pragma unroll 1
       for (int c0 = chalf * CH; c0 < (chalf + 1) * CH; c0 += 32) {
         uint32_t r[32];
@@ -365,8 +450,9 @@ int g_num_sms = 0;
 }  // namespace
 
 int mvae_umma_gemm(const mvae_umma_operand* A, const mvae_umma_operand* B, const mvae_umma_out* D, int M, int N, int K,
-                   int bn, int splits, int max_ctas, int* err_flag, cudaStream_t stream) {
+                   int bn, int splits, int max_ctas, int* err_flag, cudaStream_t stream, const mvae_umma_head* head) {
   if (!A || !B || !D || M <= 0 || N <= 0 || K <= 0) return MVAE_ERR_INVALID;
+  if (head && (bn != 64 || splits > 1 || N > 64 || head->C > N || !head->ids || !head->dlogits)) return MVAE_ERR_INVALID;
   if (g_num_sms == 0) {
     int dev = 0;
     MVAE_CUDA_CHECK(cudaGetDevice(&dev));
@@ -389,6 +475,8 @@ int mvae_umma_gemm(const mvae_umma_operand* A, const mvae_umma_operand* B, const
   kp.out = D->ptr; kp.ldc = D->ld; kp.bias = D->bias; kp.out_bf16 = D->bf16; kp.accumulate = D->accumulate;
   kp.err_flag = err_flag;
   kp.out_rb = D->rb;
+  kp.head_mode = head ? 1 : 0;
+  if (head) kp.head = *head;
   if (D->rb && (!D->bf16 || (D->ld & 7) || (N & 7))) return MVAE_ERR_INVALID;
   CUtensorMap tmA, tmB;
   int rc = make_map(&tmA, *A, BM);

@@ -15,6 +15,19 @@ struct mvae_umma_operand {
   int rb;                 // reserved (row-blocked operands are not supported by the TMA path); must be 0
 };
 
+// Optional fused "vocabulary head" epilogue (tile_n must be 64, splits 1): the logits of a row never leave the SM.
+// Per row (t, b) = (row / Bp, row % Bp): softmax over the first C columns, max_len*BCE(mean) loss partial
+// (train.py:31-35) accumulated into bce_sum, the gradient wrt the logits written as bf16 [M][64]
+// (zero for pad rows / columns), and the per-molecule argmax hit count (train.py:110-112).
+struct mvae_umma_head {
+  const unsigned char* ids;   // u8 [B][T] targets
+  int B, Bp, T, C;
+  float gscale;               // max_len / (B*T*C)
+  void* dlogits;              // bf16 [M][64]
+  double* bce_sum;
+  int* hit_count;             // [B]
+};
+
 struct mvae_umma_out {
   void* ptr;          // fp32 or bf16 [M][ld]
   long long ld;
@@ -27,4 +40,4 @@ struct mvae_umma_out {
 // bn: 0 = auto, else 64/128/192/256.  splits: split-K factor (fp32 atomics epilogue when > 1; the
 // caller zeroes D or passes an existing value to accumulate onto).  max_ctas: 0 = #SMs.
 int mvae_umma_gemm(const mvae_umma_operand* A, const mvae_umma_operand* B, const mvae_umma_out* D, int M, int N, int K,
-                   int bn, int splits, int max_ctas, int* err_flag, cudaStream_t stream);
+                   int bn, int splits, int max_ctas, int* err_flag, cudaStream_t stream, const mvae_umma_head* head = nullptr);
