@@ -85,6 +85,18 @@ int mvae_cfgb_elbo_step_graph_create(const mvae_cfgb_desc* d, const float* const
                                      const uint8_t* ids, const float* eps, float* out_scalars, float* mu_out,
                                      float* logvar_out, void* workspace, size_t workspace_bytes,
                                      mvae_graph** out_graph);
+/* The same step cut into `layers` phases for data-parallel runs (train_distributed.py:72): after phase p
+ * the gradients of one contiguous bucket of the state_dict order are final and can be all-reduced while the next phase
+ * runs.  phase 0: forward, loss, head (fc3) and the top GRU layer; phase k: GRU layer L-1-k; phase L-1 additionally the
+ * latent layers and the encoder, and writes out_scalars.  Running phases 0..L-1 in order equals mvae_cfgb_elbo_step.   */
+int mvae_cfgb_elbo_step_phase(const mvae_cfgb_desc* d, const float* const* params, float* const* grads,
+                              const uint8_t* ids, const float* eps, float* out_scalars, float* mu_out,
+                              float* logvar_out, void* workspace, size_t workspace_bytes, int phase,
+                              mvae_stream_t stream);
+int mvae_cfgb_elbo_step_phase_graph_create(const mvae_cfgb_desc* d, const float* const* params, float* const* grads,
+                                           const uint8_t* ids, const float* eps, float* out_scalars, float* mu_out,
+                                           float* logvar_out, void* workspace, size_t workspace_bytes, int phase,
+                                           mvae_graph** out_graph);
 int mvae_graph_launch(mvae_graph* g, mvae_stream_t stream);
 long long mvae_graph_num_kernel_nodes(const mvae_graph* g);
 void mvae_graph_destroy(mvae_graph* g);

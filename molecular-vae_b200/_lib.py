@@ -67,6 +67,9 @@ def _load():
         "mvae_cfgb_elbo_step": (i32, [dp, pp, pp, vp, vp, vp, vp, vp, vp, ctypes.c_size_t, vp]),
         "mvae_cfgb_elbo_step_graph_create": (i32, [dp, pp, pp, vp, vp, vp, vp, vp, vp, ctypes.c_size_t,
                                                    ctypes.POINTER(vp)]),
+        "mvae_cfgb_elbo_step_phase": (i32, [dp, pp, pp, vp, vp, vp, vp, vp, vp, ctypes.c_size_t, i32, vp]),
+        "mvae_cfgb_elbo_step_phase_graph_create": (i32, [dp, pp, pp, vp, vp, vp, vp, vp, vp, ctypes.c_size_t, i32,
+                                                         ctypes.POINTER(vp)]),
         "mvae_graph_launch": (i32, [vp, vp]),
         "mvae_graph_num_kernel_nodes": (ll, [vp]),
         "mvae_graph_destroy": (None, [vp]),
@@ -108,7 +111,8 @@ lib = _load()
 EXPORTED = [
     "mvae_strerror", "mvae_last_cuda_error", "mvae_launch_count", "mvae_reset_launch_count",
     "mvae_profile_enable", "mvae_profile_read",
-    "mvae_cfgb_workspace_bytes", "mvae_cfgb_elbo_step", "mvae_cfgb_elbo_step_graph_create", "mvae_graph_launch",
+    "mvae_cfgb_workspace_bytes", "mvae_cfgb_elbo_step", "mvae_cfgb_elbo_step_graph_create", "mvae_cfgb_elbo_step_phase",
+    "mvae_cfgb_elbo_step_phase_graph_create", "mvae_graph_launch",
     "mvae_graph_num_kernel_nodes", "mvae_graph_destroy", "mvae_cfgb_forward", "mvae_cfgb_backward",
     "mvae_cfgb_decode_greedy", "mvae_onehot_to_ids", "mvae_cfgb_read_error", "mvae_gemm_bf16", "mvae_sgemm",
     "mvae_clip_grad_norm", "mvae_adam_step", "mvae_sgd_momentum_step",

@@ -569,13 +569,18 @@ int run_forward(const Dims& d, const WS& w, const float* const* P, const uint8_t
 // ---- backward -------------------------------------------------------------------------------
 // expects w.dlogits filled.  kl_internal: add the swapped-KL gradient; ext_dmu/ext_dlv optional.
 template <typename TA>
+// phase: -1 = everything; otherwise only the part whose gradients become final in phase p of L (data-parallel bucket
+// order): p = 0 head + top GRU layer, p = k GRU layer L-1-k, p = L-1 additionally latent + encoder.
 int run_backward(const Dims& d, const WS& w, const float* const* P, float* const* G, const uint8_t* ids,
-                 const float* eps, cudaStream_t st, bool kl_internal, const float* ext_dmu, const float* ext_dlv) {
+                 const float* eps, cudaStream_t st, bool kl_internal, const float* ext_dmu, const float* ext_dlv,
+                 int phase = -1) {
   const int B = d.B, Bp = d.Bp, T = d.T, Z = d.Z, H = d.H, Hp = d.Hp, CP = d.CP, L = d.L;
   const size_t slab = (size_t)Bp * Hp;
   const int TB = T * Bp;
   const int wsplits = d.bf16 ? max(1, min(64, (148 * 2) / (ceil_div(3 * Hp, 128) * ceil_div(Hp, 256)))) : 64;
   const TA* dlog = (const TA*)w.dlogits;
+  const bool ones = ones_column(d);
+  if (phase <= 0) {
   // head: dX = dlogits * W3 ; dW3 = dlogits^T * h_top ; db3 = colsum(dlogits)
   RC(gemm<TA>(d, w, st, dlog, CP, false, (const TA*)w.W3_p, Hp, false, w.dX, Hp, true, TB, Hp, CP, nullptr, false, 1, 0,
               rec_variant(d) >= 3));
@@ -584,7 +589,6 @@ int run_backward(const Dims& d, const WS& w, const float* const* P, float* const
               nullptr, true, d.bf16 ? 148 : 64, 256));
   simt::unpad_matrix_kernel<<<grid_for((long long)d.C * H), 256, 0, st>>>(w.dW3_p, Hp, G[P_FC3W(L)], d.C, H);
   KCHECK();
-  const bool ones = ones_column(d);
   if (ones) {  // db3 = ones column of dW3
     strided_copy_kernel<<<1, 64, 0, st>>>(w.dW3_p + (Hp - 1), Hp, G[P_FC3B(L)], d.C);
     KCHECK();
@@ -594,9 +598,11 @@ int run_backward(const Dims& d, const WS& w, const float* const* P, float* const
     copy_prefix_kernel<<<1, 64, 0, st>>>(w.csum, G[P_FC3B(L)], d.C);
     KCHECK();
   }
+  }
 
   const int gate_grid = ceil_div(Bp * Hp, 256);
   for (int l = L - 1; l >= 0; --l) {
+    if (phase >= 0 && l != L - 1 - phase) continue;
     const TA* hs = (const TA*)w.hs[l];
     const TA* sv = (const TA*)w.sv[l];
     TA* dG = (TA*)w.dG;
@@ -695,6 +701,7 @@ int run_backward(const Dims& d, const WS& w, const float* const* P, float* const
       }
     }
   }
+  if (phase >= 0 && phase != L - 1) return MVAE_OK;
   // fc2 (+SELU)
   const long long nBZ = (long long)B * Z;
   simt::selu_bwd_kernel<<<grid_for(nBZ), 256, 0, st>>>(w.zr, w.dzr, w.da5, nBZ);
@@ -776,13 +783,16 @@ int finalize(const Dims& d, const WS& w, float* out_scalars, float* mu_out, floa
 
 template <typename TA>
 int elbo_step_t(const Dims& d, const WS& w, const float* const* P, float* const* G, const uint8_t* ids,
-                const float* eps, float* out_scalars, float* mu_out, float* lv_out, cudaStream_t st) {
-  RC(prep_weights<TA>(d, w, P, st, true));
-  const bool fuse = sizeof(TA) == 2 && fuse_head_enabled();
-  RC(run_forward<TA>(d, w, P, ids, eps, st, false, true, fuse));
-  if (!fuse) RC(head_fused<TA>(d, w, ids, nullptr, true, st));
-  RC(run_backward<TA>(d, w, P, G, ids, eps, st, true, nullptr, nullptr));
-  RC(finalize(d, w, out_scalars, mu_out, lv_out, st));
+                const float* eps, float* out_scalars, float* mu_out, float* lv_out, cudaStream_t st, int phase = -1) {
+  if (phase >= d.L) return MVAE_ERR_INVALID;
+  if (phase <= 0) {
+    RC(prep_weights<TA>(d, w, P, st, true));
+    const bool fuse = sizeof(TA) == 2 && fuse_head_enabled();
+    RC(run_forward<TA>(d, w, P, ids, eps, st, false, true, fuse));
+    if (!fuse) RC(head_fused<TA>(d, w, ids, nullptr, true, st));
+  }
+  RC(run_backward<TA>(d, w, P, G, ids, eps, st, true, nullptr, nullptr, phase));
+  if (phase < 0 || phase == d.L - 1) RC(finalize(d, w, out_scalars, mu_out, lv_out, st));
   return MVAE_OK;
 }
 
@@ -873,6 +883,34 @@ int mvae_cfgb_elbo_step(const mvae_cfgb_desc* desc, const float* const* params, 
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   return d.bf16 ? elbo_step_t<__nv_bfloat16>(d, w, params, grads, ids, eps, out_scalars, mu_out, logvar_out, st)
                 : elbo_step_t<float>(d, w, params, grads, ids, eps, out_scalars, mu_out, logvar_out, st);
+}
+
+int mvae_cfgb_elbo_step_phase(const mvae_cfgb_desc* desc, const float* const* params, float* const* grads,
+                              const uint8_t* ids, const float* eps, float* out_scalars, float* mu_out, float* logvar_out,
+                              void* workspace, size_t workspace_bytes, int phase, mvae_stream_t stream) {
+  Dims d; WS w;
+  RC(check_ws(desc, workspace, workspace_bytes, &d, &w));
+  if (!params || !grads || !ids || (d.train && !eps) || phase < 0 || phase >= d.L) return MVAE_ERR_INVALID;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  return d.bf16 ? elbo_step_t<__nv_bfloat16>(d, w, params, grads, ids, eps, out_scalars, mu_out, logvar_out, st, phase)
+                : elbo_step_t<float>(d, w, params, grads, ids, eps, out_scalars, mu_out, logvar_out, st, phase);
+}
+
+int mvae_cfgb_elbo_step_phase_graph_create(const mvae_cfgb_desc* desc, const float* const* params, float* const* grads,
+                                           const uint8_t* ids, const float* eps, float* out_scalars, float* mu_out,
+                                           float* logvar_out, void* workspace, size_t workspace_bytes, int phase,
+                                           mvae_graph** out_graph) {
+  struct Ctx {
+    const mvae_cfgb_desc* desc; const float* const* params; float* const* grads; const uint8_t* ids; const float* eps;
+    float *out_scalars, *mu_out, *logvar_out; void* ws; size_t ws_bytes; int phase;
+  } c{desc, params, grads, ids, eps, out_scalars, mu_out, logvar_out, workspace, workspace_bytes, phase};
+  return mvae_capture_into_graph(
+      [](void* p, cudaStream_t cs) {
+        Ctx* c = static_cast<Ctx*>(p);
+        return mvae_cfgb_elbo_step_phase(c->desc, c->params, c->grads, c->ids, c->eps, c->out_scalars, c->mu_out,
+                                         c->logvar_out, c->ws, c->ws_bytes, c->phase, reinterpret_cast<mvae_stream_t>(cs));
+      },
+      &c, out_graph);
 }
 
 int mvae_cfgb_elbo_step_graph_create(const mvae_cfgb_desc* desc, const float* const* params, float* const* grads,

@@ -59,6 +59,8 @@ class CfgBEngine:
         self.scalars = torch.zeros(4, dtype=torch.float32, device=self.device)
         self._graph = None
         self._graph_keep = None
+        self._phase_graphs = []
+        self._phase_keep = None
 
     # -- helpers -------------------------------------------------------------------------------
     @property
@@ -115,6 +117,33 @@ class CfgBEngine:
         self._graph_keep = (params, grads, ids, eps, mu_out, logvar_out)
         return lib.mvae_graph_num_kernel_nodes(handle)
 
+    def capture_elbo_step_phases(self, params, grads, ids, eps):
+        """Capture the step as `layers` CUDA graphs (mvae_cfgb_elbo_step_phase): after phase p the gradient bucket
+        `ddp.phase_buckets(...)[p]` is final, so its all-reduce can overlap the next phase."""
+        self.destroy_phase_graphs()
+        P, G = _ptr_table(params), _ptr_table(grads)
+        with torch.cuda.device(self.device):
+            torch.cuda.synchronize()
+            for phase in range(self.desc.layers):
+                handle = ctypes.c_void_p(0)
+                check(lib.mvae_cfgb_elbo_step_phase_graph_create(ctypes.byref(self.desc), P, G, _p(ids), _p(eps),
+                                                                 _p(self.scalars), _p(None), _p(None), self._ws_ptr,
+                                                                 self.ws_bytes, phase, ctypes.byref(handle)))
+                self._phase_graphs.append(handle)
+        self._phase_keep = (params, grads, ids, eps)
+        return [lib.mvae_graph_num_kernel_nodes(h) for h in self._phase_graphs]
+
+    def launch_phase(self, phase):
+        with torch.cuda.device(self.device):
+            check(lib.mvae_graph_launch(self._phase_graphs[phase], _stream()))
+        return self.scalars
+
+    def destroy_phase_graphs(self):
+        for h in getattr(self, "_phase_graphs", []):
+            lib.mvae_graph_destroy(h)
+        self._phase_graphs = []
+        self._phase_keep = None
+
     def launch_graph(self):
         with torch.cuda.device(self.device):
             check(lib.mvae_graph_launch(self._graph, _stream()))
@@ -155,5 +184,6 @@ class CfgBEngine:
     def __del__(self):
         try:
             self.destroy_graph()
+            self.destroy_phase_graphs()
         except Exception:
             pass

@@ -27,7 +27,7 @@ def _worker(rank, world, port, out_dir):
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     import molecular_vae_b200 as m
-    from molecular_vae_b200.ddp import FlatGradBuffer, shard_rows
+    from molecular_vae_b200.ddp import FlatGradBuffer, PhasedAllReduce, phase_buckets, shard_rows
     P = vo.make_params(3, dtype=np.float64, latent=Z, hidden=H, layers=L)
     ids, onehot, eps = vo.make_batch(4, B, latent=Z, dtype=np.float64)
     lo, hi = shard_rows(B, rank, world)
@@ -37,7 +37,15 @@ def _worker(rank, world, port, out_dir):
     buf = FlatGradBuffer(params)
     for p, k in zip(params, keys):
         p.grad.copy_(torch.from_numpy(r["grads"][k]))
-    buf.allreduce_mean()
+    if os.environ.get("MVAE_TEST_PHASED") == "1":
+        # bucketed exchange in the order the phased step finalises the gradients (top GRU layer + head first)
+        buckets = phase_buckets(keys, [p.numel() for p in params], L)
+        ar = PhasedAllReduce(buf.flat, buckets)
+        for ph in range(L):
+            ar.after_phase(ph)
+        ar.finish()
+    else:
+        buf.allreduce_mean()
     loss = torch.tensor([r["loss"]], dtype=torch.float64)
     dist.all_reduce(loss)
     if rank == 0:
@@ -46,7 +54,12 @@ def _worker(rank, world, port, out_dir):
     dist.destroy_process_group()
 
 
-def test_allreduce_mean_matches_full_batch(tmp_path):
+import pytest
+
+
+@pytest.mark.parametrize("phased", ["0", "1"])
+def test_allreduce_mean_matches_full_batch(tmp_path, phased, monkeypatch):
+    monkeypatch.setenv("MVAE_TEST_PHASED", phased)
     world = 2
     mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
     got = np.load(os.path.join(str(tmp_path), "ddp.npz"))
@@ -56,6 +69,19 @@ def test_allreduce_mean_matches_full_batch(tmp_path):
     assert abs(float(got["loss"][0]) - full["loss"]) < 1e-10
     for k, g in full["grads"].items():
         np.testing.assert_allclose(got[k], g, rtol=1e-9, atol=1e-12)
+
+
+def test_phase_buckets_tile_the_flat_buffer():
+    import molecular_vae_b200 as m
+    from molecular_vae_b200.ddp import phase_buckets
+    shapes = vo.config_b_shapes()
+    keys = m.param_order(3)
+    numels = [int(np.prod(shapes[k])) for k in keys]
+    b = phase_buckets(keys, numels, 3)
+    assert len(b) == 3 and b[0][1] == sum(numels) and b[-1][0] == 0
+    assert b[1][1] == b[0][0] and b[2][1] == b[1][0]                       # contiguous, no overlap, full cover
+    off = dict(zip(keys, np.cumsum([0] + numels[:-1])))
+    assert b[0][0] == off["gru.weight_ih_l2"] and b[1][0] == off["gru.weight_ih_l1"]
 
 
 def test_shard_rows_cover_batch():
