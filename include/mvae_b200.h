@@ -249,6 +249,17 @@ int mvae_binding_forward(const mvae_binding_desc* d, const float* const* params,
 int mvae_binding_backward(const mvae_binding_desc* d, const float* const* params, float* const* grads, const float* z,
                           const float* dout, float* dz, void* workspace, size_t workspace_bytes, mvae_stream_t stream);
 
+/* ---- text assembly of decoded / sampled ids (mosesvae.py:258-262 -> vocab.py:62-73 ids2string; hugesample.py:31-35;
+ * featurizer.py:26-37) -----------------------------------------------------------------------------------------------
+ * ids u8 (B,L); lengths int32 (B) or NULL (every row has L tokens).  table: 256 token texts of tok_stride bytes each,
+ * tok_len u8[256] their lengths (0 = emit nothing).  rem_first_id / rem_last_id: drop that id when it is the first /
+ * last token of a row (ids2string's rem_bos / rem_eos), -1 = keep.  strip: drop leading / trailing single-space tokens
+ * (featurizer.py:37).  Output: row b is out_bytes[out_offsets[b] .. out_offsets[b+1]) (bytes beyond `capacity` are
+ * dropped, the offsets stay exact); scratch_row_len: int32 (B).  One D2H of offsets + bytes replaces B Python loops.     */
+int mvae_ids_to_text(const uint8_t* ids, const int32_t* lengths, int B, int L, const uint8_t* table, int tok_stride,
+                     const uint8_t* tok_len, int rem_first_id, int rem_last_id, int strip, uint8_t* out_bytes,
+                     long long capacity, int32_t* out_offsets, int32_t* scratch_row_len, mvae_stream_t stream);
+
 /* ---- optimiser step on flat fp32 buffers (train.py:102-104, train_distributed.py:91-94) ------------------
  * Global-norm clipping = torch.nn.utils.clip_grad_norm(params, max_norm) over ONE flat gradient buffer (the layout
  * molecular-vae_b200/ddp.py uses); the clip coefficient min(1, max_norm/(norm+1e-6)) stays on the device at

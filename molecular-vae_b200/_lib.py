@@ -94,6 +94,7 @@ def _load():
         "mvae_binding_workspace_bytes": (ctypes.c_size_t, [ctypes.POINTER(BindingDesc)]),
         "mvae_binding_forward": (i32, [ctypes.POINTER(BindingDesc), pp, pp, vp, vp, vp, ctypes.c_size_t, vp]),
         "mvae_binding_backward": (i32, [ctypes.POINTER(BindingDesc), pp, pp, vp, vp, vp, vp, ctypes.c_size_t, vp]),
+        "mvae_ids_to_text": (i32, [vp, vp, i32, i32, vp, i32, vp, i32, i32, i32, vp, ll, vp, vp, vp]),
         "mvae_clip_grad_norm": (i32, [vp, ll, ctypes.c_float, vp, vp, i32, vp]),
         "mvae_adam_step": (i32, [vp, vp, vp, vp, ll] + [ctypes.c_float] * 5 + [i32, vp, vp]),
         "mvae_sgd_momentum_step": (i32, [vp, vp, vp, ll] + [ctypes.c_float] * 3 + [i32, vp, vp]),
@@ -118,7 +119,7 @@ EXPORTED = [
     "mvae_clip_grad_norm", "mvae_adam_step", "mvae_sgd_momentum_step",
     "mvae_cfga_workspace_bytes", "mvae_cfga_elbo_step", "mvae_cfga_elbo_step_graph_create", "mvae_cfga_forward",
     "mvae_cfga_backward", "mvae_cfga_decode", "mvae_cfga_read_error",
-    "mvae_binding_workspace_bytes", "mvae_binding_forward", "mvae_binding_backward",
+    "mvae_ids_to_text", "mvae_binding_workspace_bytes", "mvae_binding_forward", "mvae_binding_backward",
     "mvae_moses_workspace_bytes", "mvae_moses_step", "mvae_moses_sample", "mvae_moses_read_error",
 ]
 

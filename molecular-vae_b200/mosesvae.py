@@ -279,5 +279,10 @@ class VAE(nn.Module):
         """mosesvae.py:214-262: returns (list[str], z).  Multinomial draws by default (the reference behaviour),
         greedy=True selects argmax decoding (the bit-exact parity mode)."""
         ids, lens, z = self.sample_ids(n_batch, max_len, z, temp, greedy, seed)
-        ids_h, lens_h = ids.cpu(), lens.cpu().tolist()
-        return [self.tensor2string(ids_h[i, :lens_h[i]]) for i in range(ids_h.shape[0])], z
+        # mosesvae.py:258-262 slices every row and calls tensor2string on it (B .tolist() round trips); here the strings
+        # are assembled on the device and come back in one copy
+        tab = getattr(self, "_token_table", None)
+        if tab is None or tab.table.device != ids.device:
+            from .text import TokenTable
+            tab = self._token_table = TokenTable.from_vocab(self.vocabulary, ids.device)
+        return tab.to_strings(ids, lens), z

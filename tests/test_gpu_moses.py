@@ -271,3 +271,41 @@ def test_binding_model_forward_backward(mode, B):
     if B == 12:   # and directly against the reference-generated fixture
         np.testing.assert_allclose(out.detach().cpu().numpy(), g[f"{mode}/out"], rtol=2e-4, atol=2e-5)
         assert rel_l2(zt.grad.cpu().numpy(), g[f"{mode}/dz"]) <= 5e-5
+
+
+# ---- device-side text assembly (mosesvae.py:258-262, hugesample.py:31-35, featurizer.py:26-37) ----
+def test_ids_to_text_matches_reference_string_building():
+    m = load_pkg()
+    from molecular_vae_b200.text import TokenTable
+    voc = _Vocab()
+    rng = np.random.Generator(np.random.PCG64(3))
+    B, L = 700, 40
+    ids = rng.integers(0, len(voc), size=(B, L)).astype(np.uint8)
+    lens = rng.integers(1, L + 1, size=B).astype(np.int32)
+    ids[:, 0] = voc.bos
+    for b in range(0, B, 2):
+        ids[b, lens[b] - 1] = voc.eos
+    want = [voc.ids2string(ids[b, :lens[b]].tolist(), rem_bos=True, rem_eos=True) for b in range(B)]   # tensor2string
+    tab = TokenTable.from_vocab(voc, "cuda")
+    got = tab.to_strings(torch.from_numpy(ids).cuda(), torch.from_numpy(lens).cuda())
+    assert got == want
+    # hugesample.py:34: "".join('[' + charset[sym] + ']' for sym in res[i]) over the returned string's symbols
+    charset = {c: f"sym{i}" for i, c in enumerate(voc.chars)}
+    tab2 = TokenTable([f"[{charset[c]}]" for c in voc.chars] + ["", "", "[?]", "[?]"], "cuda", voc.bos, voc.eos)
+    keep = ids.copy()
+    got2 = tab2.to_strings(torch.from_numpy(keep).cuda(), torch.from_numpy(lens).cuda())
+    for b in range(0, B, 50):
+        row = keep[b, :lens[b]].tolist()
+        if row and row[0] == voc.bos: row = row[1:]
+        if row and row[-1] == voc.eos: row = row[:-1]
+        ref = "".join(f"[{charset[voc.chars[i]]}]" if i < len(voc.chars) else ("" if i in (voc.bos, voc.eos) else "[?]") for i in row)
+        assert got2[b] == ref
+    # featurizer.py:36-37 decode_smiles_from_index: join over the charset, then strip()
+    cs = [" "] + list("CNO()=#123[]+-cn")
+    tab3 = TokenTable(cs, "cuda", strip=True)
+    ids3 = rng.integers(1, len(cs), size=(64, 120)).astype(np.uint8)
+    l3 = rng.integers(5, 100, size=64)
+    for b in range(64):
+        ids3[b, l3[b]:] = 0
+    got3 = tab3.to_strings(torch.from_numpy(ids3).cuda())
+    assert got3 == ["".join(cs[i] for i in ids3[b]).strip() for b in range(64)]
