@@ -55,6 +55,9 @@ struct MWS {
   void *OH;         // [T*Bp][CP] TA one-hot of the tokens
   void *gi;         // [T][Bp][3Hd] TA
   void *hs_enc, *sv_enc, *hs[4], *sv[4], *dG, *dX, *dlogits;
+  // sampler with the fused GRU-cell GEMM epilogue (bf16 mode): [x | h] operands (ping-pong by step parity), permuted
+  // concatenated weights [W_ih | W_hh] in tiles of 64 units x 4 gate blocks, fp32 master states
+  void *xh[4][2]; void *Wcat[4]; float *bcat[4]; float *hm[4][2];
   void *hdrop;                           // [T][Bp][Hd] dropped copy of a decoder layer's outputs (input of the next layer)
   void *hs_encr, *sv_encr, *Whh_encr;   // reverse direction of a bidirectional encoder
   float *bhh_encr, *TBLer, *hlastr, *hcat, *dhcat;
@@ -94,6 +97,11 @@ void carve(const MDims& d, void* base, MWS* w) {
   }
   w->dG = c.take<uint8_t>(T * Bp * 4 * Hd * es); w->dX = c.take<uint8_t>(T * Bp * Hd * es);
   w->hdrop = c.take<uint8_t>(T * Bp * Hd * es);
+  for (int l = 0; l < d.L; ++l) {
+    for (int k = 0; k < 2; ++k) { w->xh[l][k] = c.take<uint8_t>(Bp * 2 * Hd * 2); w->hm[l][k] = c.take<float>(Bp * Hd); }
+    w->Wcat[l] = c.take<uint8_t>((size_t)4 * Hd * 2 * Hd * 2);
+    w->bcat[l] = c.take<float>(4 * Hd);
+  }
   w->dlogits = c.take<uint8_t>(T * Bp * d.CP * es);
   w->gh = c.take<float>(Bp * 3 * Hd); w->h32[0] = c.take<float>(Bp * Hd); w->h32[1] = c.take<float>(Bp * Hd);
   w->dh_carry = c.take<float>(Bp * Hd); w->logits = c.take<float>(T * Bp * d.CP);
@@ -646,6 +654,106 @@ __global__ void sample_init_kernel(int B, int max_len, int bos, int pad, uint8_t
   if (i < B) { w_cur[i] = (uint8_t)bos; end[i] = max_len; done[i] = 0; }
 }
 
+// Weights of one decoder layer for the fused GRU-cell GEMM (umma_gemm.h mvae_umma_cell): rows in tiles of 64 units x G gate
+// blocks.  first layer (G = 3, K = H): [W_hr | W_hz | W_hn];  other layers (G = 4, K = 2H, operand [x | h]):
+// r: [W_ir | W_hr], z: [W_iz | W_hz], in: [W_in | 0], hn: [0 | W_hn].  bias in the same row order.
+__global__ void cell_weights_kernel(const float* __restrict__ wih, const float* __restrict__ whh, const float* __restrict__ bih,
+                                    const float* __restrict__ bhh, int H, int G, __nv_bfloat16* __restrict__ W,
+                                    float* __restrict__ bias) {
+  const int K = G == 4 ? 2 * H : H;
+  const long long total = (long long)G * H * K;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % K);
+    const int n = (int)(i / K);
+    const int tile = n / (G * 64), g = (n / 64) % G, j = n % 64;
+    const int unit = tile * 64 + j;
+    float v = 0.f;
+    if (G == 3) {
+      v = whh[((long long)g * H + unit) * H + c];
+    } else {
+      const int gate = g < 2 ? g : 2;                       // source gate row block: r, z, n
+      if (c < H) { if (g != 3) v = wih[((long long)gate * H + unit) * H + c]; }
+      else if (g != 2) v = whh[((long long)gate * H + unit) * H + (c - H)];
+    }
+    W[i] = __float2bfloat16_rn(v);
+    if (c == 0) {
+      float b;
+      if (G == 3) b = bhh[g * H + unit];
+      else b = g < 2 ? bih[g * H + unit] + bhh[g * H + unit] : (g == 2 ? bih[2 * H + unit] : bhh[2 * H + unit]);
+      bias[n] = b;
+    }
+  }
+}
+// dst[b][0..H) (row stride ld) = h0[b][:] as bf16, rows >= B zero; optional fp32 copy
+__global__ void init_state_kernel(const float* __restrict__ h0, int B, int Bp, int H, __nv_bfloat16* __restrict__ dst, long long ld,
+                                  float* __restrict__ h32) {
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= (long long)Bp * H) return;
+  const int b = (int)(idx / H), j = (int)(idx - (long long)b * H);
+  const float v = b < B ? h0[idx] : 0.f;
+  dst[(long long)b * ld + j] = __float2bfloat16_rn(v);
+  if (h32) h32[idx] = v;
+}
+
+bool sample_fused_enabled() {
+  const char* e = getenv("MVAE_SAMPLE_FUSED");
+  return e ? atoi(e) != 0 : true;
+}
+
+// VAE.sample with one tensor-core GEMM per decoder layer and step: the GRU cell runs in the GEMM epilogue (r/z
+// contributions of x and h summed by a K = 2H contraction over the concatenated operand), so no gate pre-activations
+// reach HBM and a step is L + 1 GEMMs + 2 small kernels instead of 2L GEMMs + L gate kernels + 3.
+int sample_fused(const MDims& d, const MWS& w, const float* const* P, const float* z, int bos, int eos, int mode, float temp,
+                 unsigned long long seed, uint8_t* ids_out, int* len_out, uint8_t* w_cur, uint8_t* done, cudaStream_t st) {
+  typedef __nv_bfloat16 TA;
+  const int B = d.B, Bp = d.Bp, V = d.V, CP = d.CP, Z = d.Z, Hd = d.Hd, L = d.L, max_len = d.T;
+  const int IN0 = V + Z;
+  const MP ix{d.bidir, d.lin, L};
+  RC(memset_async(w.err_flag, 4, st));
+  for (int l = 0; l < L; ++l) {
+    cell_weights_kernel<<<grid_for((long long)(l ? 4 : 3) * Hd * (l ? 2 : 1) * Hd), 256, 0, st>>>(
+        l ? P[ix.wih(l)] : nullptr, P[ix.whh(l)], l ? P[ix.bih(l)] : nullptr, P[ix.bhh(l)], Hd, l ? 4 : 3, (TA*)w.Wcat[l], w.bcat[l]);
+    KCHECK();
+  }
+  simt::pad_matrix_kernel<TA><<<grid_for((long long)CP * Hd), 256, 0, st>>>(P[ix.fcw()], V, Hd, (TA*)w.Wfc, CP, Hd); KCHECK();
+  simt::pad_matrix_kernel<float><<<1, 64, 0, st>>>(P[ix.fcb()], 1, V, w.bfc, 1, CP); KCHECK();
+  RC(memset_async(w.h0, (size_t)Bp * Hd * 4, st));
+  RC(sg(st, z, Z, 1, P[ix.latw()], 1, Z, w.h0, Hd, B, Hd, Z, P[ix.latb()], simt::ACT_NONE, 0));
+  RC(sg(st, P[ix.emb()], V, 1, P[ix.wih(0)], 1, IN0, w.TBLd, 3 * Hd, V, 3 * Hd, V, nullptr, simt::ACT_NONE, 0));
+  RC(sg(st, z, Z, 1, P[ix.wih(0)] + V, 1, IN0, w.zproj, 3 * Hd, B, 3 * Hd, Z, P[ix.bih(0)], simt::ACT_NONE, 0));
+  const int sgrid = (int)ceil_div64((long long)Bp * Hd, 256);
+  for (int l = 0; l < L; ++l) {
+    // the first step (i = 1) reads parity 1; layer 0's operand is [h] (ld Hd), the others [x | h] (ld 2Hd, h in the right half)
+    for (int k = 0; k < 2; ++k) RC(memset_async(w.xh[l][k], (size_t)Bp * 2 * Hd * 2, st));
+    init_state_kernel<<<sgrid, 256, 0, st>>>(w.h0, B, Bp, Hd, (TA*)w.xh[l][1] + (l ? Hd : 0), l ? 2 * Hd : Hd, w.hm[l][1]); KCHECK();
+  }
+  sample_init_kernel<<<(unsigned)ceil_div64((long long)B * max_len, 256), 256, 0, st>>>(B, max_len, bos, d.pad, w_cur, ids_out, len_out, done); KCHECK();
+  TA* gi0 = (TA*)w.gi;
+  for (int i = 1; i < max_len; ++i) {
+    const int cur = i & 1, nxt = cur ^ 1;
+    gather_rows_kernel<TA><<<grid_for((long long)Bp * 3 * Hd), 256, 0, st>>>(w.TBLd, 3 * Hd, w_cur, 1, w.zproj, B, Bp, 1, gi0); KCHECK();
+    for (int l = 0; l < L; ++l) {
+      const int G = l ? 4 : 3, K = l ? 2 * Hd : Hd;
+      mvae_umma_operand a{w.xh[l][cur], 0, Bp, K, K, 1, 0, 0, 0};
+      mvae_umma_operand b{w.Wcat[l], 0, (long long)G * Hd, K, K, 1, 0, 0, 0};
+      mvae_umma_out o{w.logits, (long long)G * Hd, 0, 0, w.bcat[l], 0};
+      mvae_umma_cell c{};
+      c.gates = G; c.H = Hd; c.gi = l ? nullptr : gi0; c.h_prev32 = w.hm[l][cur]; c.h_next32 = w.hm[l][nxt];
+      c.out_a = (TA*)w.xh[l][nxt] + (l ? Hd : 0); c.ld_a = K;
+      c.out_b = (l + 1 < L) ? w.xh[l + 1][cur] : nullptr; c.ld_b = 2 * Hd;
+      mvae_count_launches(1);
+      RC(mvae_umma_gemm(&a, &b, &o, Bp, G * Hd, K, G * 64, 1, 0, w.err_flag, st, nullptr, &c));
+    }
+    const TA* top = (const TA*)w.xh[L - 1][nxt] + (L > 1 ? Hd : 0);
+    RC(gemm<TA>(w.err_flag, st, top, L > 1 ? 2 * Hd : Hd, false, (const TA*)w.Wfc, Hd, true, w.logits, CP, false, Bp, CP, Hd, w.bfc, false,
+                1, 64));
+    sample_step_kernel<<<ceil_div(B * 32, 256), 256, 0, st>>>(w.logits, CP, V, B, i, max_len, eos, mode, 1.0f / temp, seed, w_cur,
+                                                              ids_out, len_out, done);
+    KCHECK();
+  }
+  return MVAE_OK;
+}
+
 template <typename TA>
 int sample_t(const MDims& d, const MWS& w, const float* const* P, const float* z, int bos, int eos, int mode, float temp,
              unsigned long long seed, uint8_t* ids_out, int* len_out, uint8_t* w_cur, uint8_t* done, cudaStream_t st) {
@@ -751,6 +859,8 @@ int mvae_moses_sample(const mvae_moses_desc* desc, const float* const* params, c
   // small per-sequence state lives at the start of the (unused while sampling) one-hot buffer
   uint8_t* w_cur = reinterpret_cast<uint8_t*>(w.OH);
   uint8_t* done = w_cur + d.Bp;
+  if (d.bf16 && sample_fused_enabled())
+    return sample_fused(d, w, params, z, bos_id, eos_id, mode, temp, seed, ids_out, lengths_out, w_cur, done, st);
   return d.bf16 ? sample_t<__nv_bfloat16>(d, w, params, z, bos_id, eos_id, mode, temp, seed, ids_out, lengths_out, w_cur, done, st)
                 : sample_t<float>(d, w, params, z, bos_id, eos_id, mode, temp, seed, ids_out, lengths_out, w_cur, done, st);
 }

@@ -48,7 +48,20 @@ struct KernelParams {
   int* err_flag;
   int head_mode;       // fused vocabulary-head epilogue (BN == 64 only), see mvae_umma_head
   mvae_umma_head head;
+  int cell_mode;       // fused GRU-cell epilogue (BN == 192 / 256), see mvae_umma_cell
+  mvae_umma_cell cell;
 };
+
+__device__ __forceinline__ float sigmoid_fast(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(0.5f * x));
+  return fmaf(0.5f, y, 0.5f);
+}
+__device__ __forceinline__ float tanh_fast(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
 __device__ __forceinline__ bool wait_bar(uint64_t* bar, uint32_t parity, int* err_flag) {
   uint32_t spins = 0;
@@ -201,6 +214,83 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int row = m_blk * BM + q * 32 + lane;
       const bool row_ok = row < p.M;
       const bool add_bias = p.bias != nullptr && split == 0;
+      if constexpr (BN == 192 || BN == 256) {
+        if (p.cell_mode) {
+          // ---- fused GRU cell: this warp owns 32 rows x 32 hidden units (units n_blk*64 + chalf*32 ..), 16 at a time
+          constexpr int G = BN / 64;
+          const mvae_umma_cell& c = p.cell;
+          const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
+#pragma unroll 1
+          for (int half = 0; half < 2; ++half) {
+            const int ul = chalf * 32 + half * 16;            // unit offset inside the 64-unit tile
+            const int u = n_blk * 64 + ul;                    // first hidden unit of this group of 16
+            uint32_t ar[16], az[16], ai[16], ah[16];
+            ptx::tmem_ld_32x16(tacc + 0 * 64 + ul, ar);
+            ptx::tmem_ld_32x16(tacc + 1 * 64 + ul, az);
+            if (G == 4) ptx::tmem_ld_32x16(tacc + 2 * 64 + ul, ai);
+            ptx::tmem_ld_32x16(tacc + (G - 1) * 64 + ul, ah);
+            ptx::tmem_ld_wait();
+            if (row_ok && u < c.H) {
+              const float* bias = p.bias + (long long)n_blk * BN + ul;   // permuted like the weights: [gate][64]
+              float gr[16], gz[16], gn[16];
+              if (G == 3) {
+                const __nv_bfloat16* gi = reinterpret_cast<const __nv_bfloat16*>(c.gi) + (long long)row * 3 * c.H + u;
+#pragma unroll
+                for (int gk = 0; gk < 3; ++gk) {
+                  const uint4 a = __ldg(reinterpret_cast<const uint4*>(gi + (long long)gk * c.H));
+                  const uint4 b = __ldg(reinterpret_cast<const uint4*>(gi + (long long)gk * c.H) + 1);
+                  const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+                  float* dst = gk == 0 ? gr : (gk == 1 ? gz : gn);
+#pragma unroll
+                  for (int k = 0; k < 8; ++k) { dst[2 * k] = __uint_as_float(w[k] << 16); dst[2 * k + 1] = __uint_as_float(w[k] & 0xFFFF0000u); }
+                }
+              } else {
+#pragma unroll
+                for (int k = 0; k < 16; ++k) { gr[k] = 0.f; gz[k] = 0.f; gn[k] = __uint_as_float(ai[k]) + __ldg(bias + 2 * 64 + k); }
+              }
+              const float* hp = c.h_prev32 + (long long)row * c.H + u;
+              float hn[16];
+#pragma unroll
+              for (int k4 = 0; k4 < 4; ++k4) {
+                const float4 h4 = *reinterpret_cast<const float4*>(hp + 4 * k4);
+                const float hv[4] = {h4.x, h4.y, h4.z, h4.w};
+#pragma unroll
+                for (int k2 = 0; k2 < 4; ++k2) {
+                  const int k = 4 * k4 + k2;
+                  const float r = sigmoid_fast(gr[k] + __uint_as_float(ar[k]) + __ldg(bias + k));
+                  const float z = sigmoid_fast(gz[k] + __uint_as_float(az[k]) + __ldg(bias + 64 + k));
+                  const float ghn = __uint_as_float(ah[k]) + __ldg(bias + (G - 1) * 64 + k);
+                  const float n = tanh_fast(fmaf(r, ghn, gn[k]));
+                  hn[k] = fmaf(z, hv[k2] - n, n);
+                }
+              }
+              float* ho = c.h_next32 + (long long)row * c.H + u;
+#pragma unroll
+              for (int k4 = 0; k4 < 4; ++k4)
+                *reinterpret_cast<float4*>(ho + 4 * k4) = make_float4(hn[4 * k4], hn[4 * k4 + 1], hn[4 * k4 + 2], hn[4 * k4 + 3]);
+              uint4 p0, p1;
+              {
+                __nv_bfloat162 t0 = __floats2bfloat162_rn(hn[0], hn[1]), t1 = __floats2bfloat162_rn(hn[2], hn[3]);
+                __nv_bfloat162 t2 = __floats2bfloat162_rn(hn[4], hn[5]), t3 = __floats2bfloat162_rn(hn[6], hn[7]);
+                __nv_bfloat162 t4 = __floats2bfloat162_rn(hn[8], hn[9]), t5 = __floats2bfloat162_rn(hn[10], hn[11]);
+                __nv_bfloat162 t6 = __floats2bfloat162_rn(hn[12], hn[13]), t7 = __floats2bfloat162_rn(hn[14], hn[15]);
+                p0 = make_uint4(*reinterpret_cast<uint32_t*>(&t0), *reinterpret_cast<uint32_t*>(&t1), *reinterpret_cast<uint32_t*>(&t2), *reinterpret_cast<uint32_t*>(&t3));
+                p1 = make_uint4(*reinterpret_cast<uint32_t*>(&t4), *reinterpret_cast<uint32_t*>(&t5), *reinterpret_cast<uint32_t*>(&t6), *reinterpret_cast<uint32_t*>(&t7));
+              }
+              uint4* oa = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(c.out_a) + (long long)row * c.ld_a + u);
+              oa[0] = p0; oa[1] = p1;
+              if (c.out_b) {
+                uint4* ob = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(c.out_b) + (long long)row * c.ld_b + u);
+                ob[0] = p0; ob[1] = p1;
+              }
+            }
+          }
+          ptx::tc_fence_before();
+          ptx::mbar_arrive(&tempty_bar[acc]);
+          if (++acc == 2) { acc = 0; acc_ph ^= 1; }
+          continue;
+        }
+      }
       if constexpr (BN == 64) {
         if (p.head_mode) {
           // ---- fused vocabulary head: one thread owns one row's 64 logits (the quarter's second warp only signals)
@@ -450,8 +540,13 @@ int g_num_sms = 0;
 }  // namespace
 
 int mvae_umma_gemm(const mvae_umma_operand* A, const mvae_umma_operand* B, const mvae_umma_out* D, int M, int N, int K,
-                   int bn, int splits, int max_ctas, int* err_flag, cudaStream_t stream, const mvae_umma_head* head) {
+                   int bn, int splits, int max_ctas, int* err_flag, cudaStream_t stream, const mvae_umma_head* head,
+                   const mvae_umma_cell* cell) {
   if (!A || !B || !D || M <= 0 || N <= 0 || K <= 0) return MVAE_ERR_INVALID;
+  if (cell && ((cell->gates != 3 && cell->gates != 4) || bn != cell->gates * 64 || splits > 1 || (cell->H & 63) ||
+               N != cell->gates * cell->H || !D->bias || !cell->h_prev32 || !cell->h_next32 || !cell->out_a ||
+               (cell->gates == 3 && !cell->gi) || (cell->ld_a & 7) || (cell->out_b && (cell->ld_b & 7))))
+    return MVAE_ERR_INVALID;
   if (head && (bn != 64 || splits > 1 || N > 64 || head->C > N || !head->ids || !head->dlogits)) return MVAE_ERR_INVALID;
   if (g_num_sms == 0) {
     int dev = 0;
@@ -477,6 +572,8 @@ int mvae_umma_gemm(const mvae_umma_operand* A, const mvae_umma_operand* B, const
   kp.out_rb = D->rb;
   kp.head_mode = head ? 1 : 0;
   if (head) kp.head = *head;
+  kp.cell_mode = cell ? 1 : 0;
+  if (cell) kp.cell = *cell;
   if (D->rb && (!D->bf16 || (D->ld & 7) || (N & 7))) return MVAE_ERR_INVALID;
   CUtensorMap tmA, tmB;
   int rc = make_map(&tmA, *A, BM);

@@ -28,6 +28,22 @@ struct mvae_umma_head {
   int* hit_count;             // [B]
 };
 
+// Optional fused GRU-cell epilogue (decode / per-step engines): the GEMM's N dimension is laid out in tiles of 64 hidden
+// units x G gate blocks ([gate][64 units] inside a tile, weights / bias permuted accordingly by the caller):
+//   gates 3 (tile_n 192): acc = h_prev W_hh^T blocks [r | z | hn];  r,z,n input parts come from `gi` (bf16 [M][3H], (r,z,n))
+//   gates 4 (tile_n 256): acc = [x | h_prev] [W_ih | W_hh]^T blocks [r | z | in | hn]  (r,z already summed over both inputs)
+//   r = s(.), z = s(.), n = tanh(in + r * hn), h' = (1 - z) n + z h_prev     (torch.nn.GRU; bias added to every block)
+// h_prev32 / h_next32: fp32 master state [M][H]; out_a / out_b: bf16 copies of h' (row strides ld_a / ld_b, out_b optional).
+struct mvae_umma_cell {
+  int gates;                  // 3 or 4
+  int H;                      // hidden size (multiple of 64)
+  const void* gi;             // gates == 3 only
+  const float* h_prev32;
+  float* h_next32;
+  void* out_a; long long ld_a;
+  void* out_b; long long ld_b;
+};
+
 struct mvae_umma_out {
   void* ptr;          // fp32 or bf16 [M][ld]
   long long ld;
@@ -40,4 +56,5 @@ struct mvae_umma_out {
 // bn: 0 = auto, else 64/128/192/256.  splits: split-K factor (fp32 atomics epilogue when > 1; the
 // caller zeroes D or passes an existing value to accumulate onto).  max_ctas: 0 = #SMs.
 int mvae_umma_gemm(const mvae_umma_operand* A, const mvae_umma_operand* B, const mvae_umma_out* D, int M, int N, int K,
-                   int bn, int splits, int max_ctas, int* err_flag, cudaStream_t stream, const mvae_umma_head* head = nullptr);
+                   int bn, int splits, int max_ctas, int* err_flag, cudaStream_t stream, const mvae_umma_head* head = nullptr,
+                   const mvae_umma_cell* cell = nullptr);
