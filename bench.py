@@ -145,6 +145,54 @@ def kernel_rooflines(B, peaks):
     return out
 
 
+class _BenchVocab:
+    """vocab.py duck-type (30 characters + <bos>,<eos>,<pad>,<unk>, vocab.py:24) for the sampling side measurement."""
+
+    def __init__(self, n_chars=30):
+        import torch
+        self.chars = [chr(ord("A") + i) for i in range(n_chars)]
+        self.bos, self.eos, self.pad, self.unk = n_chars, n_chars + 1, n_chars + 2, n_chars + 3
+        self.vectors = torch.eye(n_chars + 4)
+
+    def __len__(self):
+        return len(self.chars) + 4
+
+    def string2ids(self, s, add_bos=False, add_eos=False):
+        ids = [self.chars.index(c) if c in self.chars else self.unk for c in s]
+        return ([self.bos] if add_bos else []) + ids + ([self.eos] if add_eos else [])
+
+    def ids2string(self, ids, rem_bos=True, rem_eos=True):
+        if ids and rem_bos and ids[0] == self.bos:
+            ids = ids[1:]
+        if ids and rem_eos and ids[-1] == self.eos:
+            ids = ids[:-1]
+        return "".join(self.chars[i] if i < len(self.chars) else "?" for i in ids)
+
+
+def sampling_rate(batch=8192, max_len=100, reps=3):
+    """BASELINE.json's second metric, 'sampled SMILES/sec' (hugesample.py:113 batch 8192, mosesvae.py:214 max_len 100):
+    greedy decodes of N(0,I) latents through mosesvae.VAE.sample's device path, random-init weights, CUDA events."""
+    import torch
+    import molecular_vae_b200 as m
+    torch.manual_seed(0)
+    model = m.mosesvae.VAE(_BenchVocab(), precision="bf16").cuda().eval()
+    z = torch.randn(batch, 160, device="cuda")
+    model.sample_ids(batch, max_len=max_len, z=z, greedy=True)
+    torch.cuda.synchronize()
+    model.check_device_error()
+    st = torch.cuda.current_stream()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(st)
+    for _ in range(reps):
+        ids, lens, _ = model.sample_ids(batch, max_len=max_len, z=z, greedy=True)
+    e1.record(st)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    return {"metric": "sampled SMILES/sec (greedy, N(0,I) latents)", "value": batch / ms * 1e3, "unit": "SMILES/s",
+            "ms_per_batch": ms, "batch": batch, "max_len": max_len, "mean_len": float(lens.float().mean().item()),
+            "workload": "mosesvae.VAE.sample device path (3x512 GRU decoder, d_z 160, V=34), bf16, random-init weights"}
+
+
 def rec_kernel_times(model, eng, params, ids_dev, eps_dev, steps=3):
     """Average launch duration of the persistent recurrence kernels, CUDA events on the launching stream, measured on
     DIRECT launches of the same fused step right after the timed region (a graph replay cannot carry events)."""
@@ -339,6 +387,10 @@ def run_ours(args):
                 line["roofline"]["kernels"] = kernel_rooflines(B, peaks)
             except Exception as ex:  # never lose the headline over the side measurement
                 line["roofline"]["kernels_error"] = repr(ex)
+            try:
+                line["sampling"] = sampling_rate()
+            except Exception as ex:
+                line["sampling"] = {"error": repr(ex)}
             cores = os.cpu_count() or 1
             rate, _ = cpu_oracle_rate(250, 2, 1)
             line["cpu_baseline"] = {"value": rate, "unit": "molecules/s", "cores": cores, "kind": "port",
