@@ -58,6 +58,7 @@ struct MWS {
   // sampler with the fused GRU-cell GEMM epilogue (bf16 mode): [x | h] operands (ping-pong by step parity), permuted
   // concatenated weights [W_ih | W_hh] in tiles of 64 units x 4 gate blocks, fp32 master states
   void *xh[4][2]; void *Wcat[4]; float *bcat[4]; float *hm[4][2];
+  void *WhhC[4]; float *bhhC[4];         // training decoder: W_hh / b_hh in the fused-cell tile order (G = 3)
   void *hdrop;                           // [T][Bp][Hd] dropped copy of a decoder layer's outputs (input of the next layer)
   void *hs_encr, *sv_encr, *Whh_encr;   // reverse direction of a bidirectional encoder
   float *bhh_encr, *TBLer, *hlastr, *hcat, *dhcat;
@@ -101,6 +102,8 @@ void carve(const MDims& d, void* base, MWS* w) {
     for (int k = 0; k < 2; ++k) { w->xh[l][k] = c.take<uint8_t>(Bp * 2 * Hd * 2); w->hm[l][k] = c.take<float>(Bp * Hd); }
     w->Wcat[l] = c.take<uint8_t>((size_t)4 * Hd * 2 * Hd * 2);
     w->bcat[l] = c.take<float>(4 * Hd);
+    w->WhhC[l] = c.take<uint8_t>((size_t)3 * Hd * Hd * 2);
+    w->bhhC[l] = c.take<float>(3 * Hd);
   }
   w->dlogits = c.take<uint8_t>(T * Bp * d.CP * es);
   w->gh = c.take<float>(Bp * 3 * Hd); w->h32[0] = c.take<float>(Bp * Hd); w->h32[1] = c.take<float>(Bp * Hd);
@@ -334,13 +337,67 @@ __global__ void copy_rows_kernel(const float* __restrict__ src, int sld, int row
 // ---------------------------------------------------------------------------------------------------------
 // per-step GRU engine (one layer), time-major, optional h0 / final-state capture / dh0
 // ---------------------------------------------------------------------------------------------------------
+// Weights of one decoder layer for the fused GRU-cell GEMM (umma_gemm.h mvae_umma_cell): rows in tiles of 64 units x G gate
+// blocks.  first layer (G = 3, K = H): [W_hr | W_hz | W_hn];  other layers (G = 4, K = 2H, operand [x | h]):
+// r: [W_ir | W_hr], z: [W_iz | W_hz], in: [W_in | 0], hn: [0 | W_hn].  bias in the same row order.
+__global__ void cell_weights_kernel(const float* __restrict__ wih, const float* __restrict__ whh, const float* __restrict__ bih,
+                                    const float* __restrict__ bhh, int H, int G, __nv_bfloat16* __restrict__ W,
+                                    float* __restrict__ bias) {
+  const int K = G == 4 ? 2 * H : H;
+  const long long total = (long long)G * H * K;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % K);
+    const int n = (int)(i / K);
+    const int tile = n / (G * 64), g = (n / 64) % G, j = n % 64;
+    const int unit = tile * 64 + j;
+    float v = 0.f;
+    if (G == 3) {
+      v = whh[((long long)g * H + unit) * H + c];
+    } else {
+      const int gate = g < 2 ? g : 2;                       // source gate row block: r, z, n
+      if (c < H) { if (g != 3) v = wih[((long long)gate * H + unit) * H + c]; }
+      else if (g != 2) v = whh[((long long)gate * H + unit) * H + (c - H)];
+    }
+    W[i] = __float2bfloat16_rn(v);
+    if (c == 0) {
+      float b;
+      if (G == 3) b = bhh[g * H + unit];
+      else b = g < 2 ? bih[g * H + unit] + bhh[g * H + unit] : (g == 2 ? bih[2 * H + unit] : bhh[2 * H + unit]);
+      bias[n] = b;
+    }
+  }
+}
+bool train_cell_fused_enabled() {
+  const char* e = getenv("MVAE_TRAIN_CELL_FUSED");
+  return e ? atoi(e) != 0 : true;
+}
 // lens + hlast: capture each sequence's state after its last valid step (right-padded forward direction).
 // lead_pad: reverse direction in processing order (padding first); `final32` then receives the state after the last step.
+// WhhC / bhhC (bf16 mode, decoder layers): W_hh / b_hh in the fused-cell tile order -> the GRU cell runs in the epilogue of
+// the step's GEMM (no gate pre-activations in HBM, no separate gate kernel).
 template <typename TA>
 int gru_fwd(const MDims& d, const MWS& w, cudaStream_t st, const TA* gi, const TA* Whh, const float* bhh, TA* hs, TA* sv,
-            int H, const float* h0, const int* lens, float* hlast, bool lead_pad = false, float* final32 = nullptr) {
+            int H, const float* h0, const int* lens, float* hlast, bool lead_pad = false, float* final32 = nullptr,
+            const void* WhhC = nullptr, const float* bhhC = nullptr) {
   const int Bp = d.Bp, T = d.T;
   const size_t slab = (size_t)Bp * H;
+  if constexpr (sizeof(TA) == 2) {
+    if (WhhC && !lens && !lead_pad && !final32 && train_cell_fused_enabled()) {
+      if (h0) { init_h0_kernel<TA><<<ceil_div((int)slab, 256), 256, 0, st>>>(h0, d.B, Bp, H, hs, w.h32[0]); KCHECK(); }
+      else { RC(memset_async(hs, slab * sizeof(TA), st)); RC(memset_async(w.h32[0], slab * 4, st)); }
+      for (int t = 0; t < T; ++t) {
+        mvae_umma_operand a{hs + t * slab, 0, Bp, H, H, 1, 0, 0, 0};
+        mvae_umma_operand b{WhhC, 0, 3ll * H, H, H, 1, 0, 0, 0};
+        mvae_umma_out o{w.gh, 3ll * H, 0, 0, bhhC, 0};
+        mvae_umma_cell c{};
+        c.gates = 3; c.H = H; c.gi = gi + (size_t)t * Bp * 3 * H; c.h_prev32 = w.h32[t & 1]; c.h_next32 = w.h32[(t + 1) & 1];
+        c.out_a = hs + (t + 1) * slab; c.ld_a = H; c.out_b = nullptr; c.ld_b = 0; c.sv = sv + (size_t)t * Bp * 4 * H;
+        mvae_count_launches(1);
+        RC(mvae_umma_gemm(&a, &b, &o, Bp, 3 * H, H, 192, 1, 0, w.err_flag, st, nullptr, &c));
+      }
+      return MVAE_OK;
+    }
+  }
   if (h0) {
     init_h0_kernel<TA><<<ceil_div((int)slab, 256), 256, 0, st>>>(h0, d.B, Bp, H, hs, d.bf16 ? w.h32[0] : nullptr);
     KCHECK();
@@ -464,7 +521,12 @@ int step_t(const MDims& d, const MWS& w, const float* const* P, float* const* G,
       }
       RC(gemm<TA>(w.err_flag, st, X, Hd, false, (const TA*)w.Wih[l], Hd, true, w.gi, 3 * Hd, true, TB, 3 * Hd, Hd, w.bih[l], false, 1));
     }
-    RC(gru_fwd<TA>(d, w, st, (const TA*)w.gi, (const TA*)w.Whh[l], w.bhh[l], (TA*)w.hs[l], (TA*)w.sv[l], Hd, w.h0, nullptr, nullptr));
+    if (d.bf16) {
+      cell_weights_kernel<<<grid_for(3ll * Hd * Hd), 256, 0, st>>>(nullptr, P[ix.whh(l)], nullptr, P[ix.bhh(l)], Hd, 3,
+                                                                   (__nv_bfloat16*)w.WhhC[l], w.bhhC[l]); KCHECK();
+    }
+    RC(gru_fwd<TA>(d, w, st, (const TA*)w.gi, (const TA*)w.Whh[l], w.bhh[l], (TA*)w.hs[l], (TA*)w.sv[l], Hd, w.h0, nullptr, nullptr,
+                   false, nullptr, d.bf16 ? w.WhhC[l] : nullptr, w.bhhC[l]));
   }
   RC(gemm<TA>(w.err_flag, st, (const TA*)w.hs[L - 1] + (size_t)Bp * Hd, Hd, false, (const TA*)w.Wfc, Hd, true, w.logits, CP, false,
               TB, CP, Hd, w.bfc, false, 1, 64));
@@ -654,36 +716,6 @@ __global__ void sample_init_kernel(int B, int max_len, int bos, int pad, uint8_t
   if (i < B) { w_cur[i] = (uint8_t)bos; end[i] = max_len; done[i] = 0; }
 }
 
-// Weights of one decoder layer for the fused GRU-cell GEMM (umma_gemm.h mvae_umma_cell): rows in tiles of 64 units x G gate
-// blocks.  first layer (G = 3, K = H): [W_hr | W_hz | W_hn];  other layers (G = 4, K = 2H, operand [x | h]):
-// r: [W_ir | W_hr], z: [W_iz | W_hz], in: [W_in | 0], hn: [0 | W_hn].  bias in the same row order.
-__global__ void cell_weights_kernel(const float* __restrict__ wih, const float* __restrict__ whh, const float* __restrict__ bih,
-                                    const float* __restrict__ bhh, int H, int G, __nv_bfloat16* __restrict__ W,
-                                    float* __restrict__ bias) {
-  const int K = G == 4 ? 2 * H : H;
-  const long long total = (long long)G * H * K;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(i % K);
-    const int n = (int)(i / K);
-    const int tile = n / (G * 64), g = (n / 64) % G, j = n % 64;
-    const int unit = tile * 64 + j;
-    float v = 0.f;
-    if (G == 3) {
-      v = whh[((long long)g * H + unit) * H + c];
-    } else {
-      const int gate = g < 2 ? g : 2;                       // source gate row block: r, z, n
-      if (c < H) { if (g != 3) v = wih[((long long)gate * H + unit) * H + c]; }
-      else if (g != 2) v = whh[((long long)gate * H + unit) * H + (c - H)];
-    }
-    W[i] = __float2bfloat16_rn(v);
-    if (c == 0) {
-      float b;
-      if (G == 3) b = bhh[g * H + unit];
-      else b = g < 2 ? bih[g * H + unit] + bhh[g * H + unit] : (g == 2 ? bih[2 * H + unit] : bhh[2 * H + unit]);
-      bias[n] = b;
-    }
-  }
-}
 // dst[b][0..H) (row stride ld) = h0[b][:] as bf16, rows >= B zero; optional fp32 copy
 __global__ void init_state_kernel(const float* __restrict__ h0, int B, int Bp, int H, __nv_bfloat16* __restrict__ dst, long long ld,
                                   float* __restrict__ h32) {

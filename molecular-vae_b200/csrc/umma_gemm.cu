@@ -262,6 +262,24 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                   const float ghn = __uint_as_float(ah[k]) + __ldg(bias + (G - 1) * 64 + k);
                   const float n = tanh_fast(fmaf(r, ghn, gn[k]));
                   hn[k] = fmaf(z, hv[k2] - n, n);
+                  gr[k] = r; gz[k] = z; gn[k] = n; ar[k] = __float_as_uint(ghn);   // reuse as the saved gates
+                }
+              }
+              if (c.sv) {
+                __nv_bfloat16* svp = reinterpret_cast<__nv_bfloat16*>(c.sv) + (long long)row * 4 * c.H + u;
+#pragma unroll
+                for (int blk = 0; blk < 4; ++blk) {
+                  uint32_t w[8];
+#pragma unroll
+                  for (int k = 0; k < 8; ++k) {
+                    const float lo = blk == 0 ? gr[2 * k] : blk == 1 ? gz[2 * k] : blk == 2 ? gn[2 * k] : __uint_as_float(ar[2 * k]);
+                    const float hi = blk == 0 ? gr[2 * k + 1] : blk == 1 ? gz[2 * k + 1] : blk == 2 ? gn[2 * k + 1] : __uint_as_float(ar[2 * k + 1]);
+                    __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+                    w[k] = *reinterpret_cast<uint32_t*>(&t);
+                  }
+                  uint4* o = reinterpret_cast<uint4*>(svp + (long long)blk * c.H);
+                  o[0] = make_uint4(w[0], w[1], w[2], w[3]);
+                  o[1] = make_uint4(w[4], w[5], w[6], w[7]);
                 }
               }
               float* ho = c.h_next32 + (long long)row * c.H + u;

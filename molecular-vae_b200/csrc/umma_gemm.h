@@ -42,6 +42,7 @@ struct mvae_umma_cell {
   float* h_next32;
   void* out_a; long long ld_a;
   void* out_b; long long ld_b;
+  void* sv;                   // optional (training): bf16 [M][4H] saved (r, z, n, W_hn h + b_hn) for BPTT
 };
 
 struct mvae_umma_out {
