@@ -56,6 +56,7 @@ struct AWS {
   int* err_flag; double* bce_sum; double* kl_sum; int* hit_count;
   // weights in operand form
   void *Whh_e[4], *Wih_e[4], *Whh_d[4], *Wih_d[4], *Wc[3], *Wfc;
+  void *WhhC_e[4], *WhhC_d[4];   // W_hh in the fused-cell tile order (tiles of 64 units x [i|f|g|o]), bf16 mode
   float *bsum_e[4], *bsum_d[4], *bfc, *TBLe;
   // activations
   void *gi, *hs_e[4], *sv_e[4], *hs_d[4], *sv_d[4], *cols[3], *OH, *dlogits, *dG, *dX, *da;
@@ -74,10 +75,12 @@ void carve(const ADims& d, void* base, AWS* w) {
   for (int l = 0; l < d.EL; ++l) {
     w->Whh_e[l] = c.take<uint8_t>(4 * EHp * EHp * es); w->Wih_e[l] = c.take<uint8_t>(4 * EHp * EHp * es);
     w->bsum_e[l] = c.take<float>(4 * EHp);
+    w->WhhC_e[l] = c.take<uint8_t>(4 * EHp * EHp * 2);
   }
   for (int l = 0; l < d.DL; ++l) {
     w->Whh_d[l] = c.take<uint8_t>(4 * DH * DH * es); w->Wih_d[l] = c.take<uint8_t>(4 * DH * DH * es);
     w->bsum_d[l] = c.take<float>(4 * DH);
+    w->WhhC_d[l] = c.take<uint8_t>(4 * DH * DH * 2);
   }
   w->Wc[0] = c.take<uint8_t>((size_t)C1 * d.K1p * es); w->Wc[1] = c.take<uint8_t>((size_t)C2 * d.K2p * es);
   w->Wc[2] = c.take<uint8_t>((size_t)C3 * d.K3p * es);
@@ -223,16 +226,50 @@ __global__ void copy_prefix2_kernel(const float* __restrict__ src, float* __rest
   if (i < n) dst[i] = src[i];
 }
 
+// padded W_hh [4Hp][Hp] (gate-major rows) -> fused-cell tile order: row n = tile*256 + gate*64 + j  <-  gate*Hp + tile*64 + j
+__global__ void lstm_cell_weights_kernel(const __nv_bfloat16* __restrict__ src, int Hp, __nv_bfloat16* __restrict__ dst) {
+  const long long total = 4ll * Hp * Hp;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % Hp);
+    const int n = (int)(i / Hp);
+    const int tile = n / 256, g = (n / 64) & 3, j = n & 63;
+    dst[i] = src[((long long)g * Hp + tile * 64 + j) * Hp + c];
+  }
+}
+// Off by default: with H = 1024 the step GEMM has only 512 tiles and the 8 epilogue warps of a CTA become the bottleneck
+// once they also run the full-precision cell math (measured 152 ms/step either way at B = 4096); the GRU variant of the
+// same epilogue pays off in the MOSES path (moses.cu), where tanh.approx gates are within budget.
+bool cell_fused_enabled() {
+  const char* e = getenv("MVAE_LSTM_CELL_FUSED");
+  return e ? atoi(e) != 0 : false;
+}
+
 // ---------------------------------------------------------------------------------------------------------
-// per-step LSTM engine (one layer): one tcgen05 GEMM (h_{t-1} W_hh^T) + one cell kernel per step
+// per-step LSTM engine (one layer): one tcgen05 GEMM (h_{t-1} W_hh^T) per step; in bf16 mode the LSTM cell runs in the
+// GEMM's epilogue (umma_gemm.h mvae_umma_cell, lstm = 1), in fp32 check mode a separate cell kernel follows the SGEMM
 // ---------------------------------------------------------------------------------------------------------
 template <typename TA, typename TG>
 int lstm_fwd(const ADims& d, const AWS& w, cudaStream_t st, const TG* gi, long long gi_tstride, const TA* Whh, TA* hs, TA* sv,
-             int H) {
+             int H, const void* WhhC = nullptr) {
   const int Bp = d.Bp, T = d.T;
   const size_t slab = (size_t)Bp * H;
   RC(memset_async(hs, slab * sizeof(TA), st));
   RC(memset_async(w.c, slab * 4, st));
+  if constexpr (sizeof(TA) == 2) {
+    if (WhhC && cell_fused_enabled()) {
+      for (int t = 0; t < T; ++t) {
+        mvae_umma_operand a{hs + t * slab, 0, Bp, H, H, 1, 0, 0, 0};
+        mvae_umma_operand b{WhhC, 0, 4ll * H, H, H, 1, 0, 0, 0};
+        mvae_umma_out o{w.gh, 4ll * H, 0, 0, nullptr, 0};
+        mvae_umma_cell c{};
+        c.gates = 4; c.H = H; c.lstm = 1; c.gi = gi + (size_t)t * gi_tstride; c.gi_f32 = sizeof(TG) == 4 ? 1 : 0; c.cstate = w.c;
+        c.out_a = hs + (t + 1) * slab; c.ld_a = H; c.sv = sv ? sv + (size_t)t * Bp * 6 * H : nullptr;
+        mvae_count_launches(1);
+        RC(mvae_umma_gemm(&a, &b, &o, Bp, 4 * H, H, 256, 1, 0, w.err_flag, st, nullptr, &c));
+      }
+      return MVAE_OK;
+    }
+  }
   const int gate_grid = (int)ceil_div64((long long)slab, 256);
   for (int t = 0; t < T; ++t) {
     RC(gemm<TA>(w.err_flag, st, hs + t * slab, H, false, Whh, H, true, w.gh, 4 * H, false, Bp, 4 * H, H, nullptr, false, 1));
@@ -272,6 +309,9 @@ int prep_weights(const ADims& d, const AWS& w, const float* const* P, cudaStream
         simt::pad_gates4_kernel<TA><<<grid_for(4ll * EHp * EHp), 256, 0, st>>>(P[ix.e_wih(l)], EH, EH, (TA*)w.Wih_e[l], EHp, EHp); KCHECK();
       }
       simt::pad_bias4_sum_kernel<<<ceil_div(4 * EHp, 256), 256, 0, st>>>(P[ix.e_bih(l)], P[ix.e_bhh(l)], EH, w.bsum_e[l], EHp); KCHECK();
+      if constexpr (sizeof(TA) == 2) {
+        lstm_cell_weights_kernel<<<grid_for(4ll * EHp * EHp), 256, 0, st>>>((const TA*)w.Whh_e[l], EHp, (TA*)w.WhhC_e[l]); KCHECK();
+      }
     }
     const int Kc[3] = {d.K1, d.K2, d.K3}, Kcp[3] = {d.K1p, d.K2p, d.K3p}, Co[3] = {C1, C2, C3};
     for (int i = 0; i < 3; ++i) {
@@ -284,6 +324,9 @@ int prep_weights(const ADims& d, const AWS& w, const float* const* P, cudaStream
       simt::pad_gates4_kernel<TA><<<grid_for(4ll * DH * DH), 256, 0, st>>>(P[ix.d_wih(l)], DH, DH, (TA*)w.Wih_d[l], DH, DH); KCHECK();
     }
     simt::pad_bias4_sum_kernel<<<ceil_div(4 * DH, 256), 256, 0, st>>>(P[ix.d_bih(l)], P[ix.d_bhh(l)], DH, w.bsum_d[l], DH); KCHECK();
+    if constexpr (sizeof(TA) == 2) {
+      lstm_cell_weights_kernel<<<grid_for(4ll * DH * DH), 256, 0, st>>>((const TA*)w.Whh_d[l], DH, (TA*)w.WhhC_d[l]); KCHECK();
+    }
   }
   simt::pad_matrix_kernel<TA><<<grid_for((long long)d.CP * DH), 256, 0, st>>>(P[ix.fc_w()], d.C, DH, (TA*)w.Wfc, d.CP, DH); KCHECK();
   simt::pad_matrix_kernel<float><<<1, 64, 0, st>>>(P[ix.fc_b()], 1, d.C, w.bfc, 1, d.CP); KCHECK();
@@ -324,7 +367,7 @@ int run_forward(const ADims& d, const AWS& w, const float* const* P, const uint8
         RC(gemm<TA>(w.err_flag, st, (const TA*)w.hs_e[l - 1] + (size_t)Bp * EHp, EHp, false, (const TA*)w.Wih_e[l], EHp, true, w.gi,
                     4 * EHp, true, TB, 4 * EHp, EHp, w.bsum_e[l], false, 1));
       RC((lstm_fwd<TA, TA>(d, w, st, (const TA*)w.gi, (long long)Bp * 4 * EHp, (const TA*)w.Whh_e[l], (TA*)w.hs_e[l],
-                           (TA*)w.sv_e[l], EHp)));
+                           (TA*)w.sv_e[l], EHp, d.bf16 ? w.WhhC_e[l] : nullptr)));
     }
     // ---- convolutions: channels = the T positions, length axis = the LSTM features (models.py:129-131)
     const TA* enc_out = (const TA*)w.hs_e[d.EL - 1] + (size_t)Bp * EHp;   // [T][Bp][EHp]
@@ -347,11 +390,12 @@ int run_forward(const ADims& d, const AWS& w, const float* const* P, const uint8
   for (int l = 0; l < d.DL; ++l) {
     TA* sv = save ? (TA*)w.sv_d[l] : nullptr;
     if (l == 0) {
-      RC((lstm_fwd<TA, float>(d, w, st, w.gi0, 0, (const TA*)w.Whh_d[0], (TA*)w.hs_d[0], sv, DH)));
+      RC((lstm_fwd<TA, float>(d, w, st, w.gi0, 0, (const TA*)w.Whh_d[0], (TA*)w.hs_d[0], sv, DH, d.bf16 ? w.WhhC_d[0] : nullptr)));
     } else {
       RC(gemm<TA>(w.err_flag, st, (const TA*)w.hs_d[l - 1] + (size_t)Bp * DH, DH, false, (const TA*)w.Wih_d[l], DH, true, w.gi,
                   4 * DH, true, TB, 4 * DH, DH, w.bsum_d[l], false, 1));
-      RC((lstm_fwd<TA, TA>(d, w, st, (const TA*)w.gi, (long long)Bp * 4 * DH, (const TA*)w.Whh_d[l], (TA*)w.hs_d[l], sv, DH)));
+      RC((lstm_fwd<TA, TA>(d, w, st, (const TA*)w.gi, (long long)Bp * 4 * DH, (const TA*)w.Whh_d[l], (TA*)w.hs_d[l], sv, DH,
+                           d.bf16 ? w.WhhC_d[l] : nullptr)));
     }
   }
   RC(gemm<TA>(w.err_flag, st, (const TA*)w.hs_d[d.DL - 1] + (size_t)Bp * DH, DH, false, (const TA*)w.Wfc, DH, true, w.logits, d.CP,

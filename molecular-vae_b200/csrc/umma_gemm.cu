@@ -220,6 +220,88 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           constexpr int G = BN / 64;
           const mvae_umma_cell& c = p.cell;
           const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
+          if (BN == 256 && c.lstm) {
+            // ---- fused LSTM cell (torch.nn.LSTM, gate rows i,f,g,o; models.py:128,164)
+#pragma unroll 1
+            for (int half = 0; half < 2; ++half) {
+              const int ul = chalf * 32 + half * 16;
+              const int u = n_blk * 64 + ul;
+              uint32_t a4[4][16];
+#pragma unroll
+              for (int g = 0; g < 4; ++g) ptx::tmem_ld_32x16(tacc + g * 64 + ul, a4[g]);
+              ptx::tmem_ld_wait();
+              if (row_ok && u < c.H) {
+                float pre[4][16];
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                  if (c.gi_f32) {
+                    const float* gi = reinterpret_cast<const float*>(c.gi) + (long long)row * 4 * c.H + (long long)g * c.H + u;
+#pragma unroll
+                    for (int k4 = 0; k4 < 4; ++k4) {
+                      const float4 v = __ldg(reinterpret_cast<const float4*>(gi) + k4);
+                      pre[g][4 * k4] = v.x; pre[g][4 * k4 + 1] = v.y; pre[g][4 * k4 + 2] = v.z; pre[g][4 * k4 + 3] = v.w;
+                    }
+                  } else {
+                    const __nv_bfloat16* gi = reinterpret_cast<const __nv_bfloat16*>(c.gi) + (long long)row * 4 * c.H + (long long)g * c.H + u;
+                    const uint4 x0 = __ldg(reinterpret_cast<const uint4*>(gi));
+                    const uint4 x1 = __ldg(reinterpret_cast<const uint4*>(gi) + 1);
+                    const uint32_t w[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) { pre[g][2 * k] = __uint_as_float(w[k] << 16); pre[g][2 * k + 1] = __uint_as_float(w[k] & 0xFFFF0000u); }
+                  }
+#pragma unroll
+                  for (int k = 0; k < 16; ++k) pre[g][k] += __uint_as_float(a4[g][k]);
+                }
+                float* cp = c.cstate + (long long)row * c.H + u;
+                float cprev[16], tc[16], hn[16];
+#pragma unroll
+                for (int k4 = 0; k4 < 4; ++k4) {
+                  const float4 v = *reinterpret_cast<const float4*>(cp + 4 * k4);
+                  cprev[4 * k4] = v.x; cprev[4 * k4 + 1] = v.y; cprev[4 * k4 + 2] = v.z; cprev[4 * k4 + 3] = v.w;
+                }
+#pragma unroll
+                for (int k = 0; k < 16; ++k) {
+                  // full-precision expf / tanhf: the encoder's gradients are within a hair of the 1e-2 bf16 budget
+                  const float ig = 1.f / (1.f + expf(-pre[0][k]));
+                  const float fg = 1.f / (1.f + expf(-pre[1][k]));
+                  const float gg = tanhf(pre[2][k]);
+                  const float og = 1.f / (1.f + expf(-pre[3][k]));
+                  const float cn = fmaf(fg, cprev[k], ig * gg);
+                  const float t = tanhf(cn);
+                  pre[0][k] = ig; pre[1][k] = fg; pre[2][k] = gg; pre[3][k] = og;
+                  tc[k] = t; hn[k] = og * t;
+                  a4[0][k] = __float_as_uint(cn);
+                }
+#pragma unroll
+                for (int k4 = 0; k4 < 4; ++k4)
+                  *reinterpret_cast<float4*>(cp + 4 * k4) = make_float4(__uint_as_float(a4[0][4 * k4]), __uint_as_float(a4[0][4 * k4 + 1]),
+                                                                       __uint_as_float(a4[0][4 * k4 + 2]), __uint_as_float(a4[0][4 * k4 + 3]));
+                auto pack16 = [](const float* v, uint4& lo, uint4& hi) {
+                  uint32_t w[8];
+#pragma unroll
+                  for (int k = 0; k < 8; ++k) { __nv_bfloat162 t = __floats2bfloat162_rn(v[2 * k], v[2 * k + 1]); w[k] = *reinterpret_cast<uint32_t*>(&t); }
+                  lo = make_uint4(w[0], w[1], w[2], w[3]); hi = make_uint4(w[4], w[5], w[6], w[7]);
+                };
+                uint4 lo, hi;
+                pack16(hn, lo, hi);
+                uint4* oa = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(c.out_a) + (long long)row * c.ld_a + u);
+                oa[0] = lo; oa[1] = hi;
+                if (c.sv) {
+                  __nv_bfloat16* svp = reinterpret_cast<__nv_bfloat16*>(c.sv) + (long long)row * 6 * c.H + u;
+#pragma unroll
+                  for (int blk = 0; blk < 6; ++blk) {
+                    pack16(blk < 4 ? pre[blk] : (blk == 4 ? cprev : tc), lo, hi);
+                    uint4* o = reinterpret_cast<uint4*>(svp + (long long)blk * c.H);
+                    o[0] = lo; o[1] = hi;
+                  }
+                }
+              }
+            }
+            ptx::tc_fence_before();
+            ptx::mbar_arrive(&tempty_bar[acc]);
+            if (++acc == 2) { acc = 0; acc_ph ^= 1; }
+            continue;
+          }
 #pragma unroll 1
           for (int half = 0; half < 2; ++half) {
             const int ul = chalf * 32 + half * 16;            // unit offset inside the 64-unit tile
@@ -562,8 +644,10 @@ int mvae_umma_gemm(const mvae_umma_operand* A, const mvae_umma_operand* B, const
                    const mvae_umma_cell* cell) {
   if (!A || !B || !D || M <= 0 || N <= 0 || K <= 0) return MVAE_ERR_INVALID;
   if (cell && ((cell->gates != 3 && cell->gates != 4) || bn != cell->gates * 64 || splits > 1 || (cell->H & 63) ||
-               N != cell->gates * cell->H || !D->bias || !cell->h_prev32 || !cell->h_next32 || !cell->out_a ||
-               (cell->gates == 3 && !cell->gi) || (cell->ld_a & 7) || (cell->out_b && (cell->ld_b & 7))))
+               N != cell->gates * cell->H || !cell->out_a || (cell->ld_a & 7) || (cell->out_b && (cell->ld_b & 7))))
+    return MVAE_ERR_INVALID;
+  if (cell && cell->lstm && (cell->gates != 4 || !cell->gi || !cell->cstate)) return MVAE_ERR_INVALID;
+  if (cell && !cell->lstm && (!D->bias || !cell->h_prev32 || !cell->h_next32 || (cell->gates == 3 && !cell->gi)))
     return MVAE_ERR_INVALID;
   if (head && (bn != 64 || splits > 1 || N > 64 || head->C > N || !head->ids || !head->dlogits)) return MVAE_ERR_INVALID;
   if (g_num_sms == 0) {

@@ -43,6 +43,13 @@ struct mvae_umma_cell {
   void* out_a; long long ld_a;
   void* out_b; long long ld_b;
   void* sv;                   // optional (training): bf16 [M][4H] saved (r, z, n, W_hn h + b_hn) for BPTT
+  // LSTM variant (lstm = 1, gates = 4, tile_n 256): acc = h_prev W_hh^T blocks [i | f | g | o]; gi = x W_ih^T + b_ih + b_hh
+  // ([M][4H], bf16, or fp32 when gi_f32);
+  // c' = f c + i g (fp32 `cstate` [M][H], updated in place), h' = o tanh(c') -> out_a; sv (optional) bf16 [M][6H] =
+  // (i, f, g, o, c_prev, tanh c').  h_prev32 / h_next32 / out_b are unused.
+  int lstm;
+  int gi_f32;
+  float* cstate;
 };
 
 struct mvae_umma_out {

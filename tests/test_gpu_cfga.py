@@ -101,8 +101,10 @@ def test_fused_step_fp32_full_config_matches_reference_fixture():
             assert np.abs(gr.reshape(-1)[g[f"gidx/{k}"]] - g[f"gval/{k}"]).max() <= 5e-4 * scale, k
 
 
-@pytest.mark.parametrize("B", [64, 136])
-def test_fused_step_bf16_full_config(B):
+@pytest.mark.parametrize("B,cell_fused", [(64, "0"), (136, "0"), (64, "1")])
+def test_fused_step_bf16_full_config(B, cell_fused, monkeypatch):
+    """cell_fused = 1: the LSTM cell runs in the epilogue of the step GEMM (umma_gemm.h mvae_umma_cell, lstm)."""
+    monkeypatch.setenv("MVAE_LSTM_CELL_FUSED", cell_fused)
     m = load_pkg()
     P, P64, ids, onehot, eps = _case(71, 72 + B, B, 292, 72, 3, 1024, 4)
     ref = ca.cfga_step(P64, ids.astype(np.int64), eps.astype(np.float64))
