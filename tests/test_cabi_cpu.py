@@ -79,3 +79,30 @@ def test_no_cpu_fallback():
         m.CfgBEngine(4)
     with pytest.raises(m._lib.MvaeError):
         m.models.CfgAEngine(4)
+
+
+def test_descriptor_validation_of_every_family():
+    """Every *_workspace_bytes rejects malformed descriptions with 0 (no GPU needed); compute entry points validate their
+    pointers before touching the device."""
+    L = _lib()
+    M = L.MosesDesc
+    ok = M(64, 40, 34, 160, 256, 512, 3, 256, 32, L.PREC_BF16, 1.0, 1.0, 0, 0, 0.0, 0)
+    assert L.lib.mvae_moses_workspace_bytes(ctypes.byref(ok)) > 0
+    for bad in (M(64, 40, 34, 160, 250, 512, 3, 256, 32, L.PREC_BF16, 1.0, 1.0, 0, 0, 0.0, 0),      # q_hidden % 64
+                M(64, 40, 99, 160, 256, 512, 3, 256, 32, L.PREC_BF16, 1.0, 1.0, 0, 0, 0.0, 0),      # vocab > 64
+                M(64, 1, 34, 160, 256, 512, 3, 256, 32, L.PREC_BF16, 1.0, 1.0, 0, 0, 0.0, 0),       # max_len < 2
+                M(64, 40, 34, 160, 256, 512, 3, 256, 32, L.PREC_BF16, 1.0, 1.0, 0, 0, 1.5, 0)):     # dropout >= 1
+        assert L.lib.mvae_moses_workspace_bytes(ctypes.byref(bad)) == 0
+    bidir = M(64, 40, 34, 128, 256, 512, 3, 256, 32, L.PREC_BF16, 1.0, 1.0, 1, 1, 0.0, 0)
+    assert L.lib.mvae_moses_workspace_bytes(ctypes.byref(bidir)) > L.lib.mvae_moses_workspace_bytes(ctypes.byref(ok)) * 0.9
+    B = L.BindingDesc
+    assert L.lib.mvae_binding_workspace_bytes(ctypes.byref(B(16, 128, 1, 1e-5, 0.1))) > 0
+    assert L.lib.mvae_binding_workspace_bytes(ctypes.byref(B(0, 128, 1, 1e-5, 0.1))) == 0
+    A = L.CfgADesc
+    assert L.lib.mvae_cfga_workspace_bytes(ctypes.byref(A(8, 120, 35, 30, 72, 3, 292, 1000, 4, L.PREC_BF16, 120.0, 1e-2))) == 0  # dec_hidden % 64
+    # null pointers are rejected before any CUDA call
+    d = L.CfgBDesc(8, 120, 35, 292, 501, 3, 435, L.PREC_BF16, 1, 120.0, 1.0)
+    rc = L.lib.mvae_cfgb_elbo_step(ctypes.byref(d), None, None, None, None, None, None, None, None, 0, None)
+    assert rc in (-1, -2)
+    rc = L.lib.mvae_ids_to_text(None, None, 4, 4, None, 1, None, -1, -1, 0, None, 0, None, None, None)
+    assert rc == -1

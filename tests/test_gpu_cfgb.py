@@ -139,6 +139,21 @@ def test_fused_step_bf16_full_config(B, rec, monkeypatch):
     _compare(model, sc, ref, BF16_LOSS_RTOL, BF16_GRAD_RTOL, "bf16-full")
 
 
+@pytest.mark.parametrize("rec", ["3", "32"])
+@pytest.mark.parametrize("H,L,Z", [(250, 2, 64), (256, 1, 32)])
+def test_fused_step_bf16_hidden_256(H, L, Z, rec, monkeypatch):
+    """Hp = 256 (4 pairs / 2 K-split clusters per row group): the other shape the persistent kernels support; H = 256 has
+    no pad unit, so the bias gradients come from the column sums instead of the ones-column."""
+    monkeypatch.setenv("MVAE_REC", rec)
+    m = load_pkg()
+    B = 300
+    P, ids, onehot, eps = make_case(61, 62 + H, B, Z, H, L)
+    ref = oracle_step(P, onehot, eps, L)
+    model = build_model(m, P, Z, H, L, "bf16")
+    sc = _fused(model, ids, eps)
+    _compare(model, sc, ref, BF16_LOSS_RTOL, BF16_GRAD_RTOL, f"bf16-h{H}")
+
+
 def test_graph_replay_matches_direct_launch():
     m = load_pkg()
     B, Z, H, L = 128, 292, 501, 3
