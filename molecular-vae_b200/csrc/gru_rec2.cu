@@ -188,9 +188,11 @@ gru_rec2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
   uint64_t* wfull_bar = tempty_bar + NTILES;         // resident weights landed
   uint64_t* pwfull_bar = wfull_bar + 1;              // leader: peer's weights landed
   uint64_t* epi_bar = pwfull_bar + 1;                // [NTILES] all epilogue threads finished the tile
-  uint64_t* xfull_bar = epi_bar + NTILES;            // KS: the partner pair's partial sums landed in our xbuf
-  uint64_t* xfree_bar = xfull_bar + 1;               // KS: the partner consumed what we last wrote into ITS xbuf
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(xfree_bar + 1);
+  // KS exchange barriers, one per epilogue warp: warp w of this CTA trades only with warp w of the partner CTA (same rows,
+  // same unit group), so no CTA-wide rendezvous sits in the middle of the epilogue
+  uint64_t* xfull_bar = epi_bar + NTILES;            // [EPI_WARPS] the partner warp's partial sums landed in our xbuf
+  uint64_t* xfree_bar = xfull_bar + EPI_WARPS;       // [EPI_WARPS] the partner warp consumed what we last wrote into ITS xbuf
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(xfree_bar + EPI_WARPS);
   float* sBias = reinterpret_cast<float*>(tmem_holder + 2);  // fwd: b_hn for the pair's 64 units
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -221,8 +223,10 @@ gru_rec2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
       ptx::mbar_init(&tempty_bar[i], 2);
       ptx::mbar_init(&epi_bar[i], EPI_WARPS * 32);
     }
-    ptx::mbar_init(xfull_bar, EPI_WARPS);
-    ptx::mbar_init(xfree_bar, EPI_WARPS);
+    for (int i = 0; i < EPI_WARPS; ++i) {
+      ptx::mbar_init(&xfull_bar[i], 1);
+      ptx::mbar_init(&xfree_bar[i], 1);
+    }
     ptx::mbar_init(wfull_bar, 1);
     ptx::mbar_init(pwfull_bar, 1);
     ptx::fence_mbar_init();
@@ -498,17 +502,18 @@ gru_rec2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
               // xbuf[unit][row]: a warp store covers 32 consecutive rows of one unit (128 contiguous bytes)
               const uint32_t xloc = ptx::smem_u32(xbuf + (size_t)uc * 128 + q * 32 + lane);
               const uint32_t xrem = mapa(xloc, partner);
-              if (ev > 0) (void)wait_bar_cluster(xfree_bar, (ev - 1) & 1u, p.err_flag);   // partner read exchange ev-1
+              const int xw = warp - 2;                                                   // this warp's exchange slot
+              if (ev > 0) (void)wait_bar_cluster(&xfree_bar[xw], (ev - 1) & 1u, p.err_flag);   // partner warp read exchange ev-1
 #pragma unroll
               for (int k = 0; k < 16; ++k) st_cluster_f32(xrem + (uint32_t)k * 512u, oth[k]);
               __syncwarp();
-              if (lane == 0) remote_arrive(mapa(ptx::smem_u32(xfull_bar), partner));   // release.cluster, 16 per exchange
-              (void)wait_bar_cluster(xfull_bar, ev & 1u, p.err_flag);
+              if (lane == 0) remote_arrive(mapa(ptx::smem_u32(&xfull_bar[xw]), partner));   // release.cluster
+              (void)wait_bar_cluster(&xfull_bar[xw], ev & 1u, p.err_flag);
               const float* xin = xbuf + (size_t)uc * 128 + q * 32 + lane;
 #pragma unroll
               for (int k = 0; k < 16; ++k) acc[k] = __float_as_uint(__uint_as_float(acc[k]) + xin[k * 128]);
               __syncwarp();
-              if (lane == 0) remote_arrive(mapa(ptx::smem_u32(xfree_bar), partner));
+              if (lane == 0) remote_arrive(mapa(ptx::smem_u32(&xfree_bar[xw]), partner));
             } else {
               ptx::tmem_ld_32x16(tmem_base + lane_off + i * NB + uc, acc);
               ptx::tmem_ld_32x16(master_addr, cm);
@@ -539,19 +544,20 @@ gru_rec2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
           tmem_st_32x16(master_addr, carry);
           __nv_bfloat16* g4 = p.dG + ((long long)t * p.Bp + row) * 4 * p.Hp + u0 + uc;
           if (!nomem) {
-            stg256(g4, n);
+            // the three dgh blocks the other pairs stream next step go first; da_n (only read by the later wgrad / dX
+            // GEMMs) is stored after this tile has been handed to the publisher
             stg256(g4 + p.Hp, ghn);
             stg256(g4 + 2 * p.Hp, dx);
             stg256(g4 + 3 * p.Hp, hp);
           }
-        }
-        if (tr && (p.debug & 64)) p.trace[((size_t)step * NTILES + i) * 12 + 11] = gtime();
-        if (BWD) {
           tmem_st_wait();
           ptx::tc_fence_before();
+          if (tr) p.trace[((size_t)step * NTILES + i) * 12 + 5] = gtime();
+          ptx::mbar_arrive(&epi_bar[i]);
+          if (!nomem) stg256(g4, n);
         }
-        if (tr) p.trace[((size_t)step * NTILES + i) * 12 + 5] = gtime();
-        if (BWD) ptx::mbar_arrive(&epi_bar[i]);
+        if (tr && (p.debug & 64)) p.trace[((size_t)step * NTILES + i) * 12 + 11] = gtime();
+        if (!BWD && tr) p.trace[((size_t)step * NTILES + i) * 12 + 5] = gtime();
       }
       fph ^= 1;
     }
