@@ -760,28 +760,29 @@ int sample_fused(const MDims& d, const MWS& w, const float* const* P, const floa
     init_state_kernel<<<sgrid, 256, 0, st>>>(w.h0, B, Bp, Hd, (TA*)w.xh[l][1] + (l ? Hd : 0), l ? 2 * Hd : Hd, w.hm[l][1]); KCHECK();
   }
   sample_init_kernel<<<(unsigned)ceil_div64((long long)B * max_len, 256), 256, 0, st>>>(B, max_len, bos, d.pad, w_cur, ids_out, len_out, done); KCHECK();
-  TA* gi0 = (TA*)w.gi;
   for (int i = 1; i < max_len; ++i) {
     const int cur = i & 1, nxt = cur ^ 1;
-    gather_rows_kernel<TA><<<grid_for((long long)Bp * 3 * Hd), 256, 0, st>>>(w.TBLd, 3 * Hd, w_cur, 1, w.zproj, B, Bp, 1, gi0); KCHECK();
     for (int l = 0; l < L; ++l) {
       const int G = l ? 4 : 3, K = l ? 2 * Hd : Hd;
       mvae_umma_operand a{w.xh[l][cur], 0, Bp, K, K, 1, 0, 0, 0};
       mvae_umma_operand b{w.Wcat[l], 0, (long long)G * Hd, K, K, 1, 0, 0, 0};
       mvae_umma_out o{w.logits, (long long)G * Hd, 0, 0, w.bcat[l], 0};
       mvae_umma_cell c{};
-      c.gates = G; c.H = Hd; c.gi = l ? nullptr : gi0; c.h_prev32 = w.hm[l][cur]; c.h_next32 = w.hm[l][nxt];
+      c.gates = G; c.H = Hd; c.h_prev32 = w.hm[l][cur]; c.h_next32 = w.hm[l][nxt];
+      if (l == 0) { c.tbl = w.TBLd; c.add = w.zproj; c.tok = w_cur; c.tok_rows = B; }   // emb(w) | z through W_ih_l0: look-up + per-sequence part
       c.out_a = (TA*)w.xh[l][nxt] + (l ? Hd : 0); c.ld_a = K;
       c.out_b = (l + 1 < L) ? w.xh[l + 1][cur] : nullptr; c.ld_b = 2 * Hd;
       mvae_count_launches(1);
       RC(mvae_umma_gemm(&a, &b, &o, Bp, G * Hd, K, G * 64, 1, 0, w.err_flag, st, nullptr, &c));
     }
+    // vocabulary GEMM with the sampling step in its epilogue: logits never reach HBM
     const TA* top = (const TA*)w.xh[L - 1][nxt] + (L > 1 ? Hd : 0);
-    RC(gemm<TA>(w.err_flag, st, top, L > 1 ? 2 * Hd : Hd, false, (const TA*)w.Wfc, Hd, true, w.logits, CP, false, Bp, CP, Hd, w.bfc, false,
-                1, 64));
-    sample_step_kernel<<<ceil_div(B * 32, 256), 256, 0, st>>>(w.logits, CP, V, B, i, max_len, eos, mode, 1.0f / temp, seed, w_cur,
-                                                              ids_out, len_out, done);
-    KCHECK();
+    mvae_umma_operand a{top, 0, Bp, Hd, L > 1 ? 2 * Hd : Hd, 1, 0, 0, 0};
+    mvae_umma_operand b{w.Wfc, 0, CP, Hd, Hd, 1, 0, 0, 0};
+    mvae_umma_out o{w.logits, CP, 0, 0, w.bfc, 0};
+    mvae_umma_sample sp{V, B, i, max_len, eos, mode, 1.0f / temp, seed, w_cur, ids_out, len_out, done};
+    mvae_count_launches(1);
+    RC(mvae_umma_gemm(&a, &b, &o, Bp, CP, Hd, 64, 1, 0, w.err_flag, st, nullptr, nullptr, &sp));
   }
   return MVAE_OK;
 }

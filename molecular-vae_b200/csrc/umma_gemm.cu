@@ -50,7 +50,16 @@ struct KernelParams {
   mvae_umma_head head;
   int cell_mode;       // fused GRU-cell epilogue (BN == 192 / 256), see mvae_umma_cell
   mvae_umma_cell cell;
+  int sample_mode;     // fused sampling epilogue (BN == 64), see mvae_umma_sample
+  mvae_umma_sample sample;
 };
+
+// counter-based uniform in (0,1); must stay identical to u01_hash in moses.cu / oracle/moses_oracle.u01_hash
+__device__ __forceinline__ float u01_hash_gemm(unsigned long long seed, unsigned int b, unsigned int i) {
+  unsigned long long x = seed + 0x9E3779B97F4A7C15ull * ((unsigned long long)b * 1000003ull + i + 1);
+  x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ull; x ^= x >> 27; x *= 0x94D049BB133111EBull; x ^= x >> 31;
+  return (float)((x >> 40) + 0.5) * (1.0f / 16777216.0f);
+}
 
 __device__ __forceinline__ float sigmoid_fast(float x) {
   float y;
@@ -315,7 +324,21 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             if (row_ok && u < c.H) {
               const float* bias = p.bias + (long long)n_blk * BN + ul;   // permuted like the weights: [gate][64]
               float gr[16], gz[16], gn[16];
-              if (G == 3) {
+              if (G == 3 && c.tbl) {
+                const int tok = row < c.tok_rows ? (int)c.tok[row] : 0;
+                const float* tb = c.tbl + (long long)tok * 3 * c.H + u;
+                const float* ad = c.add + (long long)(row < c.tok_rows ? row : 0) * 3 * c.H + u;
+#pragma unroll
+                for (int gk = 0; gk < 3; ++gk) {
+                  float* dst = gk == 0 ? gr : (gk == 1 ? gz : gn);
+#pragma unroll
+                  for (int k4 = 0; k4 < 4; ++k4) {
+                    const float4 a = __ldg(reinterpret_cast<const float4*>(tb + (long long)gk * c.H) + k4);
+                    const float4 b = __ldg(reinterpret_cast<const float4*>(ad + (long long)gk * c.H) + k4);
+                    dst[4 * k4] = a.x + b.x; dst[4 * k4 + 1] = a.y + b.y; dst[4 * k4 + 2] = a.z + b.z; dst[4 * k4 + 3] = a.w + b.w;
+                  }
+                }
+              } else if (G == 3) {
                 const __nv_bfloat16* gi = reinterpret_cast<const __nv_bfloat16*>(c.gi) + (long long)row * 3 * c.H + u;
 #pragma unroll
                 for (int gk = 0; gk < 3; ++gk) {
@@ -392,6 +415,57 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
       }
       if constexpr (BN == 64) {
+        if (p.sample_mode) {
+          // ---- fused sampling step: one thread owns one sequence's logits (the quarter's second warp only signals)
+          if (chalf == 0) {
+            uint32_t r0[32], r1[32];
+            ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN, r0);
+            ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + 32, r1);
+            ptx::tmem_ld_wait();
+            const mvae_umma_sample& sp = p.sample;
+            if (row < sp.B) {
+              float v[64];
+#pragma unroll
+              for (int j = 0; j < 32; ++j) { v[j] = __uint_as_float(r0[j]); v[32 + j] = __uint_as_float(r1[j]); }
+              float m = -INFINITY;
+              int arg = 0;
+#pragma unroll
+              for (int j = 0; j < 64; ++j) {
+                if (j >= sp.V) break;
+                v[j] = (v[j] + (p.bias ? __ldg(p.bias + j) : 0.f)) * sp.inv_temp;
+                if (v[j] > m) { m = v[j]; arg = j; }
+              }
+              int tok = arg;
+              if (sp.mode == 1) {
+                float tot = 0.f;
+#pragma unroll
+                for (int j = 0; j < 64; ++j) {
+                  if (j >= sp.V) break;
+                  v[j] = expf(v[j] - m);
+                  tot += v[j];
+                }
+                const float uu = u01_hash_gemm(sp.seed, (unsigned)row, (unsigned)sp.step) * tot;
+                float cum = 0.f;
+                bool found = false;
+#pragma unroll
+                for (int j = 0; j < 64; ++j) {
+                  if (j >= sp.V) break;
+                  cum += v[j];
+                  if (!found && cum > uu) { tok = j; found = true; }
+                }
+              }
+              sp.w_cur[row] = (unsigned char)tok;
+              if (!sp.done[row]) {
+                sp.x[(long long)row * sp.max_len + sp.step] = (unsigned char)tok;
+                if (tok == sp.eos) { sp.end[row] = sp.step + 1; sp.done[row] = 1; }
+              }
+            }
+          }
+          ptx::tc_fence_before();
+          ptx::mbar_arrive(&tempty_bar[acc]);
+          if (++acc == 2) { acc = 0; acc_ph ^= 1; }
+          continue;
+        }
         if (p.head_mode) {
           // ---- fused vocabulary head: one thread owns one row's 64 logits (the quarter's second warp only signals)
           if (chalf == 0) {
@@ -641,13 +715,16 @@ int g_num_sms = 0;
 
 int mvae_umma_gemm(const mvae_umma_operand* A, const mvae_umma_operand* B, const mvae_umma_out* D, int M, int N, int K,
                    int bn, int splits, int max_ctas, int* err_flag, cudaStream_t stream, const mvae_umma_head* head,
-                   const mvae_umma_cell* cell) {
+                   const mvae_umma_cell* cell, const mvae_umma_sample* sample) {
   if (!A || !B || !D || M <= 0 || N <= 0 || K <= 0) return MVAE_ERR_INVALID;
+  if (sample && (bn != 64 || splits > 1 || N > 64 || sample->V > N || !sample->w_cur || !sample->x || !sample->end || !sample->done))
+    return MVAE_ERR_INVALID;
   if (cell && ((cell->gates != 3 && cell->gates != 4) || bn != cell->gates * 64 || splits > 1 || (cell->H & 63) ||
                N != cell->gates * cell->H || !cell->out_a || (cell->ld_a & 7) || (cell->out_b && (cell->ld_b & 7))))
     return MVAE_ERR_INVALID;
   if (cell && cell->lstm && (cell->gates != 4 || !cell->gi || !cell->cstate)) return MVAE_ERR_INVALID;
-  if (cell && !cell->lstm && (!D->bias || !cell->h_prev32 || !cell->h_next32 || (cell->gates == 3 && !cell->gi)))
+  if (cell && !cell->lstm && (!D->bias || !cell->h_prev32 || !cell->h_next32 ||
+                              (cell->gates == 3 && !cell->gi && !(cell->tbl && cell->add && cell->tok))))
     return MVAE_ERR_INVALID;
   if (head && (bn != 64 || splits > 1 || N > 64 || head->C > N || !head->ids || !head->dlogits)) return MVAE_ERR_INVALID;
   if (g_num_sms == 0) {
@@ -676,6 +753,8 @@ int mvae_umma_gemm(const mvae_umma_operand* A, const mvae_umma_operand* B, const
   if (head) kp.head = *head;
   kp.cell_mode = cell ? 1 : 0;
   if (cell) kp.cell = *cell;
+  kp.sample_mode = sample ? 1 : 0;
+  if (sample) kp.sample = *sample;
   if (D->rb && (!D->bf16 || (D->ld & 7) || (N & 7))) return MVAE_ERR_INVALID;
   CUtensorMap tmA, tmB;
   int rc = make_map(&tmA, *A, BM);

@@ -50,6 +50,24 @@ struct mvae_umma_cell {
   int lstm;
   int gi_f32;
   float* cstate;
+  // gates == 3 alternative to `gi` (sampler): gi(row) = tbl[tok[row]] + add[row], both fp32 with rows of 3H (r,z,n);
+  // rows >= tok_rows use token 0.  (mosesvae.py:244-245: emb(w) | z through W_ih_l0, as a table look-up + per-sequence part)
+  const float* tbl;
+  const float* add;
+  const unsigned char* tok;
+  int tok_rows;
+};
+
+// Optional fused sampling epilogue of the vocabulary GEMM (tile_n 64, mosesvae.py:247-255): per row softmax(y / temp) ->
+// argmax (mode 0) or inverse-CDF draw with the counter-based generator (mode 1) -> masked write + EOS bookkeeping.
+struct mvae_umma_sample {
+  int V, B, step, max_len, eos, mode;
+  float inv_temp;
+  unsigned long long seed;
+  unsigned char* w_cur;       // [B] token fed to the next step
+  unsigned char* x;           // [B][max_len]
+  int* end;                   // [B]
+  unsigned char* done;        // [B]
 };
 
 struct mvae_umma_out {
@@ -65,4 +83,4 @@ struct mvae_umma_out {
 // caller zeroes D or passes an existing value to accumulate onto).  max_ctas: 0 = #SMs.
 int mvae_umma_gemm(const mvae_umma_operand* A, const mvae_umma_operand* B, const mvae_umma_out* D, int M, int N, int K,
                    int bn, int splits, int max_ctas, int* err_flag, cudaStream_t stream, const mvae_umma_head* head = nullptr,
-                   const mvae_umma_cell* cell = nullptr);
+                   const mvae_umma_cell* cell = nullptr, const mvae_umma_sample* sample = nullptr);
