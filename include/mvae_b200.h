@@ -213,10 +213,13 @@ size_t mvae_moses_workspace_bytes(const mvae_moses_desc* d);
 /* One step of VAE.forward (+ backward when grads != NULL; dropout is the identity).  ids: u8 (B,T) right-padded
  * with pad_id; lengths: int32 (B) (incl. bos/eos); eps: fp32 (B,d_z).  out_scalars (device, 4 floats):
  * kl_weight*kl + recon_weight*recon, kl, recon, number of non-pad targets.  z_out, logvar_out (B,d_z) and
- * y_out (B,T,V; the logits the reference returns, decoder_fc bias at padded positions) are optional.           */
+ * y_out (B,T,V; the logits the reference returns, decoder_fc bias at padded positions) are optional.
+ * lengths_host (optional HOST copy of `lengths`): enables torch's packed-sequence batch sizes -- step t of every
+ * recurrence only processes the sequences that are still running (a prefix of the length-sorted batch).            */
 int mvae_moses_step(const mvae_moses_desc* d, const float* const* params, float* const* grads, const uint8_t* ids,
-                    const int32_t* lengths, const float* eps, float* out_scalars, float* z_out, float* logvar_out,
-                    float* y_out, void* workspace, size_t workspace_bytes, mvae_stream_t stream);
+                    const int32_t* lengths, const int32_t* lengths_host, const float* eps, float* out_scalars,
+                    float* z_out, float* logvar_out, float* y_out, void* workspace, size_t workspace_bytes,
+                    mvae_stream_t stream);
 /* VAE.sample (mosesvae.py:214-262; hugesample.py:28): autoregressive decode of B latents z fp32 (B,d_z) for
  * max_len-1 steps (desc->max_len = the sampler's max_len, 100 in the reference).  mode 0 = greedy argmax (ties ->
  * lowest id; the bit-exact parity mode), mode 1 = multinomial over softmax(y/temp) with a counter-based generator

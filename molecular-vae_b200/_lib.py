@@ -87,7 +87,7 @@ def _load():
         "mvae_cfga_decode": (i32, [ap, pp, vp, vp, vp, vp, ctypes.c_size_t, vp]),
         "mvae_cfga_read_error": (i32, [ap, vp, ctypes.c_size_t, ctypes.POINTER(i32), vp]),
         "mvae_moses_workspace_bytes": (ctypes.c_size_t, [ctypes.POINTER(MosesDesc)]),
-        "mvae_moses_step": (i32, [ctypes.POINTER(MosesDesc), pp, pp, vp, vp, vp, vp, vp, vp, vp, vp, ctypes.c_size_t, vp]),
+        "mvae_moses_step": (i32, [ctypes.POINTER(MosesDesc), pp, pp, vp, vp, vp, vp, vp, vp, vp, vp, vp, ctypes.c_size_t, vp]),
         "mvae_moses_sample": (i32, [ctypes.POINTER(MosesDesc), pp, vp, i32, i32, i32, ctypes.c_float, ctypes.c_ulonglong, vp, vp,
                                     vp, ctypes.c_size_t, vp]),
         "mvae_moses_read_error": (i32, [ctypes.POINTER(MosesDesc), vp, ctypes.c_size_t, ctypes.POINTER(i32), vp]),

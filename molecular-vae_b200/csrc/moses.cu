@@ -378,22 +378,27 @@ bool train_cell_fused_enabled() {
 template <typename TA>
 int gru_fwd(const MDims& d, const MWS& w, cudaStream_t st, const TA* gi, const TA* Whh, const float* bhh, TA* hs, TA* sv,
             int H, const float* h0, const int* lens, float* hlast, bool lead_pad = false, float* final32 = nullptr,
-            const void* WhhC = nullptr, const float* bhhC = nullptr) {
+            const void* WhhC = nullptr, const float* bhhC = nullptr, const int* act = nullptr) {
+  // act (host, T entries, optional): rows [0, act[t]) are the sequences still running at step t (the batch is sorted by
+  // length, so they form a prefix -- torch's packed-sequence batch sizes); the step's GEMM / cell work covers only them.
   const int Bp = d.Bp, T = d.T;
   const size_t slab = (size_t)Bp * H;
+  if (act) RC(memset_async(hs, (size_t)(T + 1) * slab * sizeof(TA), st));   // rows past a sequence's end read as zeros
   if constexpr (sizeof(TA) == 2) {
     if (WhhC && !lens && !lead_pad && !final32 && train_cell_fused_enabled()) {
       if (h0) { init_h0_kernel<TA><<<ceil_div((int)slab, 256), 256, 0, st>>>(h0, d.B, Bp, H, hs, w.h32[0]); KCHECK(); }
       else { RC(memset_async(hs, slab * sizeof(TA), st)); RC(memset_async(w.h32[0], slab * 4, st)); }
       for (int t = 0; t < T; ++t) {
-        mvae_umma_operand a{hs + t * slab, 0, Bp, H, H, 1, 0, 0, 0};
+        const int M = act ? act[t] : Bp;
+        if (M <= 0) break;
+        mvae_umma_operand a{hs + t * slab, 0, M, H, H, 1, 0, 0, 0};
         mvae_umma_operand b{WhhC, 0, 3ll * H, H, H, 1, 0, 0, 0};
         mvae_umma_out o{w.gh, 3ll * H, 0, 0, bhhC, 0};
         mvae_umma_cell c{};
         c.gates = 3; c.H = H; c.gi = gi + (size_t)t * Bp * 3 * H; c.h_prev32 = w.h32[t & 1]; c.h_next32 = w.h32[(t + 1) & 1];
         c.out_a = hs + (t + 1) * slab; c.ld_a = H; c.out_b = nullptr; c.ld_b = 0; c.sv = sv + (size_t)t * Bp * 4 * H;
         mvae_count_launches(1);
-        RC(mvae_umma_gemm(&a, &b, &o, Bp, 3 * H, H, 192, 1, 0, w.err_flag, st, nullptr, &c));
+        RC(mvae_umma_gemm(&a, &b, &o, M, 3 * H, H, 192, 1, 0, w.err_flag, st, nullptr, &c));
       }
       return MVAE_OK;
     }
@@ -405,12 +410,13 @@ int gru_fwd(const MDims& d, const MWS& w, cudaStream_t st, const TA* gi, const T
     RC(memset_async(hs, slab * sizeof(TA), st));
     if (d.bf16) RC(memset_async(w.h32[0], slab * 4, st));
   }
-  const int gate_grid = ceil_div((int)slab, 256);
   for (int t = 0; t < T; ++t) {
-    RC(gemm<TA>(w.err_flag, st, hs + t * slab, H, false, Whh, H, true, w.gh, 3 * H, false, Bp, 3 * H, H, bhh, false, 1));
-    simt::gru_gate_fwd_kernel<TA, TA><<<gate_grid, 256, 0, st>>>(
+    const int M = act ? act[t] : Bp;
+    if (M <= 0) break;
+    RC(gemm<TA>(w.err_flag, st, hs + t * slab, H, false, Whh, H, true, w.gh, 3 * H, false, M, 3 * H, H, bhh, false, 1));
+    simt::gru_gate_fwd_kernel<TA, TA><<<(unsigned)ceil_div64((long long)M * H, 256), 256, 0, st>>>(
         gi + (size_t)t * Bp * 3 * H, w.gh, d.bf16 ? w.h32[t & 1] : nullptr, hs + t * slab, hs + (t + 1) * slab,
-        d.bf16 ? w.h32[(t + 1) & 1] : nullptr, sv + (size_t)t * Bp * 4 * H, Bp, H, lens, hlast, t, d.B, lead_pad ? T : 0);
+        d.bf16 ? w.h32[(t + 1) & 1] : nullptr, sv + (size_t)t * Bp * 4 * H, M, H, lens, hlast, t, d.B, lead_pad ? T : 0);
     KCHECK();
   }
   if (final32) {
@@ -424,7 +430,7 @@ int gru_fwd(const MDims& d, const MWS& w, cudaStream_t st, const TA* gi, const T
 // carry_init ([B][carry_ld] fp32, optional): gradient wrt the state after the LAST processed step (reverse encoder direction)
 template <typename TA>
 int gru_bwd(const MDims& d, const MWS& w, cudaStream_t st, const TA* Whh, const TA* hs, const TA* sv, const TA* dX, TA* dG,
-            int H, float* dh0_acc, const float* carry_init = nullptr, int carry_ld = 0) {
+            int H, float* dh0_acc, const float* carry_init = nullptr, int carry_ld = 0, const int* act = nullptr) {
   const int Bp = d.Bp, T = d.T;
   const size_t slab = (size_t)Bp * H;
   RC(memset_async(w.dh_carry, slab * 4, st));
@@ -435,11 +441,12 @@ int gru_bwd(const MDims& d, const MWS& w, cudaStream_t st, const TA* Whh, const 
   const int gate_grid = ceil_div((int)slab, 256);
   for (int t = T - 1; t >= 0; --t) {
     TA* dGt = dG + (size_t)t * Bp * 4 * H;
+    const int M = act ? act[t] : Bp;   // sequences still running at step t; the other rows get zero gradients
     simt::gru_gate_bwd_kernel<TA><<<gate_grid, 256, 0, st>>>(sv + (size_t)t * Bp * 4 * H, hs + t * slab, dX + t * slab,
-                                                             w.dh_carry, dGt, nullptr, Bp, H);
+                                                             w.dh_carry, dGt, nullptr, Bp, H, M);
     KCHECK();
-    if (t > 0 || dh0_acc)
-      RC(gemm<TA>(w.err_flag, st, dGt + H, 4 * H, false, Whh, H, false, w.dh_carry, H, false, Bp, H, 3 * H, nullptr, true, 1));
+    if ((t > 0 || dh0_acc) && M > 0)
+      RC(gemm<TA>(w.err_flag, st, dGt + H, 4 * H, false, Whh, H, false, w.dh_carry, H, false, M, H, 3 * H, nullptr, true, 1));
   }
   if (dh0_acc) {
     add_inplace_kernel<<<grid_for((long long)slab), 256, 0, st>>>(dh0_acc, w.dh_carry, (long long)slab);
@@ -451,7 +458,7 @@ int gru_bwd(const MDims& d, const MWS& w, cudaStream_t st, const TA* Whh, const 
 template <typename TA>
 int step_t(const MDims& d, const MWS& w, const float* const* P, float* const* G, const uint8_t* ids,
            const int* lens, const float* eps, float* out_scalars, float* z_out, float* lv_out, float* y_out,
-           bool backward, cudaStream_t st) {
+           bool backward, cudaStream_t st, const int* act) {
   const int B = d.B, Bp = d.Bp, T = d.T, V = d.V, CP = d.CP, Z = d.Z, Hq = d.Hq, Hd = d.Hd, L = d.L, ML = d.MLP;
   const int TB = T * Bp;
   const int IN0 = V + Z;   // decoder layer-0 input width
@@ -483,7 +490,8 @@ int step_t(const MDims& d, const MWS& w, const float* const* P, float* const* G,
   RC(sg(st, P[ix.emb()], V, 1, P[ix.e_wih(0)], 1, V, w.TBLe, 3 * Hq, V, 3 * Hq, V, P[ix.e_bih(0)], simt::ACT_NONE, 0));
   gather_rows_kernel<TA><<<grid_for((long long)TB * 3 * Hq), 256, 0, st>>>(w.TBLe, 3 * Hq, ids, T, nullptr, B, Bp, T, (TA*)w.gi); KCHECK();
   RC(memset_async(w.hlast, (size_t)Bp * Hq * 4, st));
-  RC(gru_fwd<TA>(d, w, st, (const TA*)w.gi, (const TA*)w.Whh_enc, w.bhh_enc, (TA*)w.hs_enc, (TA*)w.sv_enc, Hq, nullptr, lens, w.hlast));
+  RC(gru_fwd<TA>(d, w, st, (const TA*)w.gi, (const TA*)w.Whh_enc, w.bhh_enc, (TA*)w.hs_enc, (TA*)w.sv_enc, Hq, nullptr, lens, w.hlast,
+                 false, nullptr, nullptr, nullptr, act));
   copy_rows_kernel<<<grid_for((long long)B * Hq), 256, 0, st>>>(w.hlast, Hq, B, Hq, w.hcat, Hin); KCHECK();
   if (d.bidir) {
     // reverse direction (mosesfile.py:21-28,112-116): same engine over the time-reversed token stream, padding first
@@ -526,7 +534,7 @@ int step_t(const MDims& d, const MWS& w, const float* const* P, float* const* G,
                                                                    (__nv_bfloat16*)w.WhhC[l], w.bhhC[l]); KCHECK();
     }
     RC(gru_fwd<TA>(d, w, st, (const TA*)w.gi, (const TA*)w.Whh[l], w.bhh[l], (TA*)w.hs[l], (TA*)w.sv[l], Hd, w.h0, nullptr, nullptr,
-                   false, nullptr, d.bf16 ? w.WhhC[l] : nullptr, w.bhhC[l]));
+                   false, nullptr, d.bf16 ? w.WhhC[l] : nullptr, w.bhhC[l], act));
   }
   RC(gemm<TA>(w.err_flag, st, (const TA*)w.hs[L - 1] + (size_t)Bp * Hd, Hd, false, (const TA*)w.Wfc, Hd, true, w.logits, CP, false,
               TB, CP, Hd, w.bfc, false, 1, 64));
@@ -556,7 +564,7 @@ int step_t(const MDims& d, const MWS& w, const float* const* P, float* const* G,
   for (int l = L - 1; l >= 0; --l) {
     const TA* hs = (const TA*)w.hs[l];
     TA* dG = (TA*)w.dG;
-    RC(gru_bwd<TA>(d, w, st, (const TA*)w.Whh[l], hs, (const TA*)w.sv[l], (const TA*)w.dX, dG, Hd, w.dh0));
+    RC(gru_bwd<TA>(d, w, st, (const TA*)w.Whh[l], hs, (const TA*)w.sv[l], (const TA*)w.dX, dG, Hd, w.dh0, nullptr, 0, act));
     RC(memset_async(w.dW_p, (size_t)3 * Hd * Hd * 4, st));
     RC(gemm<TA>(w.err_flag, st, dG + Hd, 4 * Hd, true, hs, Hd, false, w.dW_p, Hd, false, 3 * Hd, Hd, TB, nullptr, true, wsplits, 256));
     simt::unpad_gate_matrix_kernel<<<grid_for(3ll * Hd * Hd), 256, 0, st>>>(w.dW_p, Hd, Hd, G[ix.whh(l)], Hd, Hd, 0, 1, 2); KCHECK();
@@ -636,7 +644,7 @@ int step_t(const MDims& d, const MWS& w, const float* const* P, float* const* G,
     RC(memset_async(dXe, (size_t)TB * Hq * sizeof(TA), st));
     if (!rev) {
       scatter_final_grad_kernel<TA><<<(unsigned)ceil_div64((long long)B * Hq, 256), 256, 0, st>>>(w.dhenc, Hin, lens, B, Bp, Hq, dXe); KCHECK();
-      RC(gru_bwd<TA>(d, w, st, Whh, hs, sv, dXe, dG, Hq, nullptr));
+      RC(gru_bwd<TA>(d, w, st, Whh, hs, sv, dXe, dG, Hq, nullptr, nullptr, 0, act));
     } else {
       RC(gru_bwd<TA>(d, w, st, Whh, hs, sv, dXe, dG, Hq, nullptr, w.dhenc + Hq, Hin));
     }
@@ -871,15 +879,30 @@ size_t mvae_moses_workspace_bytes(const mvae_moses_desc* desc) {
 }
 
 int mvae_moses_step(const mvae_moses_desc* desc, const float* const* params, float* const* grads, const uint8_t* ids,
-                    const int32_t* lengths, const float* eps, float* out_scalars, float* z_out, float* logvar_out,
-                    float* y_out, void* workspace, size_t workspace_bytes, mvae_stream_t stream) {
+                    const int32_t* lengths, const int32_t* lengths_host, const float* eps, float* out_scalars, float* z_out,
+                    float* logvar_out, float* y_out, void* workspace, size_t workspace_bytes, mvae_stream_t stream) {
   MDims d; MWS w;
   RC(check_ws(desc, workspace, workspace_bytes, &d, &w));
   if (!params || !ids || !lengths || !eps || !out_scalars) return MVAE_ERR_INVALID;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const bool backward = grads != nullptr;
-  return d.bf16 ? step_t<__nv_bfloat16>(d, w, params, grads, ids, lengths, eps, out_scalars, z_out, logvar_out, y_out, backward, st)
-                : step_t<float>(d, w, params, grads, ids, lengths, eps, out_scalars, z_out, logvar_out, y_out, backward, st);
+  // packed-sequence batch sizes (torch pack_sequence): act[t] = number of sequences longer than t; with the batch sorted
+  // by length they are the rows [0, act[t]).  Needs the host copy of the lengths; without it every step covers all rows.
+  int act_buf[512];
+  const int* act = nullptr;
+  if (lengths_host) {
+    for (int b = 0; b + 1 < d.B; ++b)
+      if (lengths_host[b] < lengths_host[b + 1]) return MVAE_ERR_INVALID;          // pack_sequence contract: sorted descending
+    if (lengths_host[0] > d.T || lengths_host[d.B - 1] < 2) return MVAE_ERR_INVALID;
+    int b = d.B;
+    for (int t = 0; t < d.T; ++t) {
+      while (b > 0 && lengths_host[b - 1] <= t) --b;
+      act_buf[t] = b;
+    }
+    act = act_buf;
+  }
+  return d.bf16 ? step_t<__nv_bfloat16>(d, w, params, grads, ids, lengths, eps, out_scalars, z_out, logvar_out, y_out, backward, st, act)
+                : step_t<float>(d, w, params, grads, ids, lengths, eps, out_scalars, z_out, logvar_out, y_out, backward, st, act);
 }
 
 int mvae_moses_sample(const mvae_moses_desc* desc, const float* const* params, const float* z, int bos_id, int eos_id,

@@ -495,11 +495,17 @@ __global__ void gru_gate_fwd_kernel(const TG* __restrict__ gi, const float* __re
 template <typename TA>
 __global__ void gru_gate_bwd_kernel(const TA* __restrict__ sv, const TA* __restrict__ hprevA,
                                     const TA* __restrict__ dX, float* __restrict__ dh_carry, TA* __restrict__ dG,
-                                    float* __restrict__ dgi_sum /*[Bp][3Hp] rzn or null*/, int Bp, int Hp) {
+                                    float* __restrict__ dgi_sum /*[Bp][3Hp] rzn or null*/, int Bp, int Hp,
+                                    int active_rows = 1 << 30) {
   const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (idx >= (long long)Bp * Hp) return;
   const int b = (int)(idx / Hp), j = (int)(idx - (long long)b * Hp);
   const long long s4 = (long long)b * 4 * Hp + j;
+  if (b >= active_rows) {   // packed sequences: this row's sequence has ended before step t -> no gradient, nothing read
+    const TA zero = from_f32<TA>(0.f);
+    dG[s4] = zero; dG[s4 + Hp] = zero; dG[s4 + 2 * Hp] = zero; dG[s4 + 3 * Hp] = zero;
+    return;
+  }
   const float r = to_f32<TA>(sv[s4]), z = to_f32<TA>(sv[s4 + Hp]), n = to_f32<TA>(sv[s4 + 2 * Hp]),
               hn = to_f32<TA>(sv[s4 + 3 * Hp]);
   const float hp = to_f32<TA>(hprevA[idx]);

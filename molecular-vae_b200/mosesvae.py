@@ -169,8 +169,10 @@ class VAE(nn.Module):
             raise RuntimeError("sequences must be sorted by length in decreasing order (pack_sequence contract)")
         padded = nn.utils.rnn.pad_sequence(x, batch_first=True, padding_value=self.pad)
         dev = self.device
-        return (padded.to(dev), padded.to(device=dev, dtype=torch.uint8).contiguous(),
-                torch.tensor(lens, dtype=torch.int32, device=dev))
+        lens_h = torch.tensor(lens, dtype=torch.int32)
+        lens_d = lens_h.to(dev)
+        lens_d._host_copy = lens_h
+        return padded.to(dev), padded.to(device=dev, dtype=torch.uint8).contiguous(), lens_d
 
     def _dropout(self):
         """(p, seed) of the train-mode dropout between decoder layers (mosesvae.py:38,78); p = 0 in eval mode."""
@@ -203,9 +205,10 @@ class VAE(nn.Module):
         y = torch.empty(B, T, c["vocab"], dtype=torch.float32, device=dev) if want_y else None
         P = _ptr_table(params)
         G = _ptr_table(grads) if grads is not None else None
+        lens_host = getattr(lens, "_host_copy", None)      # set by _pack: enables packed-sequence batch sizes per step
         with torch.cuda.device(dev):
-            check(lib.mvae_moses_step(ctypes.byref(d), P, G, _p(ids), _p(lens), _p(eps), _p(out), _p(z), _p(lv), _p(y),
-                                      wsp, need, _stream()))
+            check(lib.mvae_moses_step(ctypes.byref(d), P, G, _p(ids), _p(lens), _p(lens_host), _p(eps), _p(out), _p(z),
+                                      _p(lv), _p(y), wsp, need, _stream()))
         self._last_desc = (d, wsp, need)
         self._last_scalars = out
         return out[1], out[2], z, lv, y
