@@ -335,17 +335,19 @@ def run_ours(args):
     e2e_value = world * B * e2e_steps / sec_e2e
     # second metric of BASELINE.json (hugesample.py): every rank decodes its own latents (replicas only, no exchange);
     # whole-job SMILES/s = batches of all ranks / slowest rank's time
-    sampling = None
     try:
         sampling = sampling_rate()
-        if world > 1:
-            t = torch.tensor([sampling["ms_per_batch"]], dtype=torch.float64, device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    except Exception as ex:
+        sampling = {"error": repr(ex)}
+    if world > 1:   # every rank takes part in the reduction, whether or not its own measurement succeeded
+        t = torch.tensor([sampling.get("ms_per_batch", float("inf"))], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        if "error" not in sampling and t.item() != float("inf"):
             sampling["ms_per_batch"] = float(t.item())
             sampling["value"] = world * sampling["batch"] / sampling["ms_per_batch"] * 1e3
             sampling["replicas"] = world
-    except Exception as ex:
-        sampling = {"error": repr(ex)}
+        elif "error" not in sampling:
+            sampling = {"error": "sampling failed on another rank"}
     if rank == 0:
         peak = peaks["bf16_tflops_sustained"]
         achieved = (value / world) * GFLOP_PER_MOLECULE * 1e-3  # TFLOP/s per GPU
