@@ -49,6 +49,7 @@ int make_dims(const mvae_moses_desc* d, MDims* o) {
 
 struct MWS {
   int* err_flag; double* kl_sum; double* nll_sum; int* M;
+  int* act_dev;    // [T] packed-sequence batch sizes on the device (for the tile / k-block skipping of the big GEMMs)
   float *TBLe, *TBLd, *hlast, *rmu, *rlv, *mu, *lv, *z, *h0, *zproj, *dh0, *dz, *dmu, *dlv, *dr, *dhenc, *dgisum;
   float *dTBL;      // [CP][3Hd] fp32, columns in (n,r,z) order
   float *dWT;       // [3Hd][V] staging
@@ -74,6 +75,7 @@ void carve(const MDims& d, void* base, MWS* w) {
   const size_t es = d.bf16 ? 2 : 4;
   const size_t B = d.B, Bp = d.Bp, T = d.T, Hd = d.Hd, Hq = d.Hq;
   w->err_flag = c.take<int>(1); w->kl_sum = c.take<double>(1); w->nll_sum = c.take<double>(1); w->M = c.take<int>(1);
+  w->act_dev = c.take<int>(512);
   w->TBLe = c.take<float>((size_t)d.V * 3 * Hq); w->TBLd = c.take<float>((size_t)d.V * 3 * Hd);
   w->hlast = c.take<float>(Bp * Hq); w->rmu = c.take<float>(B * d.MLP); w->rlv = c.take<float>(B * d.MLP);
   w->mu = c.take<float>(B * d.Z); w->lv = c.take<float>(B * d.Z); w->z = c.take<float>(B * d.Z);
@@ -177,6 +179,14 @@ __global__ void reparam_kl_std_bwd_kernel(const float* __restrict__ mu, const fl
 __global__ void relu_bwd_kernel(const float* __restrict__ out, float* __restrict__ d, long long n) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     if (!(out[i] > 0.f)) d[i] = 0.f;
+}
+// act[t] = number of sequences longer than t (lengths sorted descending -> they are the rows [0, act[t]))
+__global__ void count_active_kernel(const int* __restrict__ lens, int B, int T, int* __restrict__ act) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  int lo = 0, hi = B;                  // first index with lens <= t
+  while (lo < hi) { const int mid = (lo + hi) >> 1; if (lens[mid] > t) lo = mid + 1; else hi = mid; }
+  act[t] = lo;
 }
 __global__ void count_targets_kernel(const int* __restrict__ lens, int B, int* __restrict__ M) {
   int local = 0;
@@ -367,6 +377,10 @@ __global__ void cell_weights_kernel(const float* __restrict__ wih, const float* 
     }
   }
 }
+bool varlen_gemm_enabled() {
+  const char* e = getenv("MVAE_VARLEN_GEMM");
+  return e ? atoi(e) != 0 : true;
+}
 bool train_cell_fused_enabled() {
   const char* e = getenv("MVAE_TRAIN_CELL_FUSED");
   return e ? atoi(e) != 0 : true;
@@ -468,6 +482,11 @@ int step_t(const MDims& d, const MWS& w, const float* const* P, float* const* G,
   RC(memset_async(w.err_flag, 4, st)); RC(memset_async(w.kl_sum, 8, st)); RC(memset_async(w.nll_sum, 8, st));
   RC(memset_async(w.M, 4, st));
   count_targets_kernel<<<1, 256, 0, st>>>(lens, B, w.M); KCHECK();
+  // packed sequences: the big time-major GEMMs skip output tiles (mode 1) / k-blocks (mode 2) past the running sequences
+  mvae_umma_varlen vlm{w.act_dev, Bp, 1}, vlk{w.act_dev, Bp, 2};
+  const mvae_umma_varlen* VLM = (act && d.bf16 && varlen_gemm_enabled()) ? &vlm : nullptr;
+  const mvae_umma_varlen* VLK = (act && d.bf16 && varlen_gemm_enabled()) ? &vlk : nullptr;
+  if (VLM) { count_active_kernel<<<ceil_div(T, 128), 128, 0, st>>>(lens, B, T, w.act_dev); KCHECK(); }
   simt::pad_gate_matrix_kernel<TA><<<grid_for(3ll * Hq * Hq), 256, 0, st>>>(P[ix.e_whh(0)], Hq, Hq, (TA*)w.Whh_enc, Hq, Hq, 0, 1, 2); KCHECK();
   simt::pad_gate_vector_kernel<<<ceil_div(3 * Hq, 256), 256, 0, st>>>(P[ix.e_bhh(0)], Hq, w.bhh_enc, Hq); KCHECK();
   if (d.bidir) {
@@ -527,7 +546,7 @@ int step_t(const MDims& d, const MWS& w, const float* const* P, float* const* G,
                                                                         B, Bp, Hd, T); KCHECK();
         X = (const TA*)w.hdrop;
       }
-      RC(gemm<TA>(w.err_flag, st, X, Hd, false, (const TA*)w.Wih[l], Hd, true, w.gi, 3 * Hd, true, TB, 3 * Hd, Hd, w.bih[l], false, 1));
+      RC(gemm<TA>(w.err_flag, st, X, Hd, false, (const TA*)w.Wih[l], Hd, true, w.gi, 3 * Hd, true, TB, 3 * Hd, Hd, w.bih[l], false, 1, 0, VLM));
     }
     if (d.bf16) {
       cell_weights_kernel<<<grid_for(3ll * Hd * Hd), 256, 0, st>>>(nullptr, P[ix.whh(l)], nullptr, P[ix.bhh(l)], Hd, 3,
@@ -537,7 +556,7 @@ int step_t(const MDims& d, const MWS& w, const float* const* P, float* const* G,
                    false, nullptr, d.bf16 ? w.WhhC[l] : nullptr, w.bhhC[l], act));
   }
   RC(gemm<TA>(w.err_flag, st, (const TA*)w.hs[L - 1] + (size_t)Bp * Hd, Hd, false, (const TA*)w.Wfc, Hd, true, w.logits, CP, false,
-              TB, CP, Hd, w.bfc, false, 1, 64));
+              TB, CP, Hd, w.bfc, false, 1, 64, VLM));
   head_ce_kernel<TA><<<(unsigned)ceil_div64((long long)TB * 32, 256), 256, 0, st>>>(
       w.logits, CP, V, ids, T, lens, B, Bp, T, w.M, d.rec_w, w.bfc, backward ? (TA*)w.dlogits : nullptr, y_out, w.nll_sum);
   KCHECK();
@@ -551,10 +570,10 @@ int step_t(const MDims& d, const MWS& w, const float* const* P, float* const* G,
   const int wsplits = d.bf16 ? 12 : 64;
   onehot_rows_kernel<TA><<<grid_for((long long)TB * CP), 256, 0, st>>>(ids, T, B, Bp, T, CP, (TA*)w.OH); KCHECK();
   // head
-  RC(gemm<TA>(w.err_flag, st, dlog, CP, false, (const TA*)w.Wfc, Hd, false, w.dX, Hd, true, TB, Hd, CP, nullptr, false, 1));
+  RC(gemm<TA>(w.err_flag, st, dlog, CP, false, (const TA*)w.Wfc, Hd, false, w.dX, Hd, true, TB, Hd, CP, nullptr, false, 1, 0, VLM));
   RC(memset_async(w.dWfc_p, (size_t)CP * Hd * 4, st));
   RC(gemm<TA>(w.err_flag, st, dlog, CP, true, (const TA*)w.hs[L - 1] + (size_t)Bp * Hd, Hd, false, w.dWfc_p, Hd, false, CP, Hd, TB,
-              nullptr, true, d.bf16 ? 148 : 64, 256));
+              nullptr, true, d.bf16 ? 148 : 64, 256, VLK));
   simt::unpad_matrix_kernel<<<grid_for((long long)V * Hd), 256, 0, st>>>(w.dWfc_p, Hd, G[ix.fcw()], V, Hd); KCHECK();
   RC(memset_async(w.csum, (size_t)4 * Hd * 4, st));
   RC(simt::colsum<TA>(st, dlog, TB, CP, CP, w.csum)); mvae_count_launches(1);
@@ -566,7 +585,7 @@ int step_t(const MDims& d, const MWS& w, const float* const* P, float* const* G,
     TA* dG = (TA*)w.dG;
     RC(gru_bwd<TA>(d, w, st, (const TA*)w.Whh[l], hs, (const TA*)w.sv[l], (const TA*)w.dX, dG, Hd, w.dh0, nullptr, 0, act));
     RC(memset_async(w.dW_p, (size_t)3 * Hd * Hd * 4, st));
-    RC(gemm<TA>(w.err_flag, st, dG + Hd, 4 * Hd, true, hs, Hd, false, w.dW_p, Hd, false, 3 * Hd, Hd, TB, nullptr, true, wsplits, 256));
+    RC(gemm<TA>(w.err_flag, st, dG + Hd, 4 * Hd, true, hs, Hd, false, w.dW_p, Hd, false, 3 * Hd, Hd, TB, nullptr, true, wsplits, 256, VLK));
     simt::unpad_gate_matrix_kernel<<<grid_for(3ll * Hd * Hd), 256, 0, st>>>(w.dW_p, Hd, Hd, G[ix.whh(l)], Hd, Hd, 0, 1, 2); KCHECK();
     RC(memset_async(w.csum, (size_t)4 * Hd * 4, st));
     RC(simt::colsum<TA>(st, dG, TB, 4 * Hd, 4 * Hd, w.csum)); mvae_count_launches(1);
@@ -579,9 +598,9 @@ int step_t(const MDims& d, const MWS& w, const float* const* P, float* const* G,
         X = (const TA*)w.hdrop;
       }
       RC(memset_async(w.dW_p, (size_t)3 * Hd * Hd * 4, st));
-      RC(gemm<TA>(w.err_flag, st, dG, 4 * Hd, true, X, Hd, false, w.dW_p, Hd, false, 3 * Hd, Hd, TB, nullptr, true, wsplits, 256));
+      RC(gemm<TA>(w.err_flag, st, dG, 4 * Hd, true, X, Hd, false, w.dW_p, Hd, false, 3 * Hd, Hd, TB, nullptr, true, wsplits, 256, VLK));
       simt::unpad_gate_matrix_kernel<<<grid_for(3ll * Hd * Hd), 256, 0, st>>>(w.dW_p, Hd, Hd, G[ix.wih(l)], Hd, Hd, 2, 0, 1); KCHECK();
-      RC(gemm<TA>(w.err_flag, st, dG, 4 * Hd, false, (const TA*)w.Wih_nrz[l], Hd, false, w.dX, Hd, true, TB, Hd, 3 * Hd, nullptr, false, 1));
+      RC(gemm<TA>(w.err_flag, st, dG, 4 * Hd, false, (const TA*)w.Wih_nrz[l], Hd, false, w.dX, Hd, true, TB, Hd, 3 * Hd, nullptr, false, 1, 0, VLM));
       if (drop) {   // gradient wrt the undropped outputs of layer l-1
         dropout_kernel<TA><<<grid_for((long long)TB * Hd), 256, 0, st>>>((const TA*)w.dX, (TA*)w.dX, (unsigned long long)d.drop_seed + (l - 1),
                                                                         d.drop, B, Bp, Hd, T); KCHECK();
@@ -590,7 +609,7 @@ int step_t(const MDims& d, const MWS& w, const float* const* P, float* const* G,
       // layer 0: table gradient (tensor-core GEMM onehot^T * dgi) and the per-molecule z part (time sum)
       RC(memset_async(w.dTBL, (size_t)CP * 3 * Hd * 4, st));
       RC(gemm<TA>(w.err_flag, st, (const TA*)w.OH, CP, true, dG, 4 * Hd, false, w.dTBL, 3 * Hd, false, CP, 3 * Hd, TB, nullptr, true,
-                  d.bf16 ? 24 : 64, 256));
+                  d.bf16 ? 24 : 64, 256, VLK));
       dgi_time_sum_t_kernel<TA><<<(unsigned)ceil_div64((long long)Bp * 3 * Hd, 256), 256, 0, st>>>(dG, T, Bp, Hd, w.dgisum); KCHECK();
     }
   }
@@ -649,7 +668,8 @@ int step_t(const MDims& d, const MWS& w, const float* const* P, float* const* G,
       RC(gru_bwd<TA>(d, w, st, Whh, hs, sv, dXe, dG, Hq, nullptr, w.dhenc + Hq, Hin));
     }
     RC(memset_async(w.dW_p, (size_t)3 * Hq * Hq * 4, st));
-    RC(gemm<TA>(w.err_flag, st, dG + Hq, 4 * Hq, true, hs, Hq, false, w.dW_p, Hq, false, 3 * Hq, Hq, TB, nullptr, true, wsplits, 256));
+    RC(gemm<TA>(w.err_flag, st, dG + Hq, 4 * Hq, true, hs, Hq, false, w.dW_p, Hq, false, 3 * Hq, Hq, TB, nullptr, true, wsplits, 256,
+                rev ? nullptr : VLK));
     simt::unpad_gate_matrix_kernel<<<grid_for(3ll * Hq * Hq), 256, 0, st>>>(w.dW_p, Hq, Hq, G[ix.e_whh(rev)], Hq, Hq, 0, 1, 2); KCHECK();
     RC(memset_async(w.csum, (size_t)4 * Hd * 4, st));
     RC(simt::colsum<TA>(st, dG, TB, 4 * Hq, 4 * Hq, w.csum)); mvae_count_launches(1);
@@ -657,7 +677,7 @@ int step_t(const MDims& d, const MWS& w, const float* const* P, float* const* G,
     if (rev) { onehot_rows_kernel<TA><<<grid_for((long long)TB * CP), 256, 0, st>>>(ids, T, B, Bp, T, CP, (TA*)w.OH, 1); KCHECK(); }
     RC(memset_async(w.dTBL, (size_t)CP * 3 * Hd * 4, st));
     RC(gemm<TA>(w.err_flag, st, (const TA*)w.OH, CP, true, dG, 4 * Hq, false, w.dTBL, 3 * Hq, false, CP, 3 * Hq, TB, nullptr, true,
-                d.bf16 ? 24 : 64, 256));
+                d.bf16 ? 24 : 64, 256, rev ? nullptr : VLK));
     tbl_grad_to_rzn_T_kernel<<<(unsigned)ceil_div64(3ll * Hq * V, 256), 256, 0, st>>>(w.dTBL, Hq, V, w.dWT); KCHECK();
     RC(sg(st, w.dWT, V, 1, P[ix.emb()], V, 1, G[ix.e_wih(rev)], V, 3 * Hq, V, V, nullptr, simt::ACT_NONE, 0));
     RC(sg(st, w.dWT, 1, V, P[ix.e_wih(rev)], V, 1, G[ix.emb()], V, V, V, 3 * Hq, nullptr, simt::ACT_NONE, 1));   // accumulate onto the decoder part

@@ -52,7 +52,24 @@ struct KernelParams {
   mvae_umma_cell cell;
   int sample_mode;     // fused sampling epilogue (BN == 64), see mvae_umma_sample
   mvae_umma_sample sample;
+  int vl_mode;         // packed-sequence skipping, see mvae_umma_varlen
+  const int* vl_act;
+  int vl_tiles;        // M tiles (mode 1) or k-blocks (mode 2) per slab
 };
+
+// mode 1: is output tile m_blk entirely past the running sequences of its slab?
+__device__ __forceinline__ bool vl_skip_tile(const KernelParams& p, int m_blk) {
+  if (p.vl_mode != 1) return false;
+  const int t = m_blk / p.vl_tiles, r = m_blk - t * p.vl_tiles;
+  return r * BM >= __ldg(p.vl_act + t);
+}
+// mode 2: is k-block kb entirely past the running sequences of its slab?  (the first block of a split is always kept so
+// that the accumulator is written at least once; it contributes zeros)
+__device__ __forceinline__ bool vl_skip_kb(const KernelParams& p, int kb, int kb0) {
+  if (p.vl_mode != 2 || kb == kb0) return false;
+  const int t = kb / p.vl_tiles, r = kb - t * p.vl_tiles;
+  return r * BK >= __ldg(p.vl_act + t);
+}
 
 // counter-based uniform in (0,1); must stay identical to u01_hash in moses.cu / oracle/moses_oracle.u01_hash
 __device__ __forceinline__ float u01_hash_gemm(unsigned long long seed, unsigned int b, unsigned int i) {
@@ -143,7 +160,9 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int m_blk = tile / p.tiles_n, n_blk = tile - m_blk * p.tiles_n;
         const int kb0 = split * p.kb_per_split;
         const int kb1 = min(kb_total, kb0 + p.kb_per_split);
+        if (vl_skip_tile(p, m_blk)) continue;
         for (int kb = kb0; kb < kb1; ++kb) {
+          if (vl_skip_kb(p, kb, kb0)) continue;
           if (!wait_bar(&empty_bar[s], ph ^ 1, p.err_flag)) goto done;
           ptx::mbar_arrive_expect_tx(&full_bar[s], C::STAGE_BYTES);
           uint8_t* a_dst = sA + s * A_STAGE_BYTES;
@@ -179,10 +198,12 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int kb0 = split * p.kb_per_split;
         const int kb1 = min(kb_total, kb0 + p.kb_per_split);
         if (kb0 >= kb1) continue;
+        if (vl_skip_tile(p, tile / p.tiles_n)) continue;
         if (!wait_bar(&tempty_bar[acc], acc_ph ^ 1, p.err_flag)) goto done;
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
         for (int kb = kb0; kb < kb1; ++kb) {
+          if (vl_skip_kb(p, kb, kb0)) continue;
           if (!wait_bar(&full_bar[s], ph, p.err_flag)) goto done;
           ptx::tc_fence_after();
           const uint32_t a_addr = ptx::smem_u32(sA + s * A_STAGE_BYTES);
@@ -218,6 +239,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int kb0 = split * p.kb_per_split;
       const int kb1 = min(kb_total, kb0 + p.kb_per_split);
       if (kb0 >= kb1) continue;
+      if (vl_skip_tile(p, m_blk)) continue;
       if (!wait_bar(&tfull_bar[acc], acc_ph, p.err_flag)) goto done;
       ptx::tc_fence_after();
       const int row = m_blk * BM + q * 32 + lane;
@@ -715,8 +737,11 @@ int g_num_sms = 0;
 
 int mvae_umma_gemm(const mvae_umma_operand* A, const mvae_umma_operand* B, const mvae_umma_out* D, int M, int N, int K,
                    int bn, int splits, int max_ctas, int* err_flag, cudaStream_t stream, const mvae_umma_head* head,
-                   const mvae_umma_cell* cell, const mvae_umma_sample* sample) {
+                   const mvae_umma_cell* cell, const mvae_umma_sample* sample, const mvae_umma_varlen* varlen) {
   if (!A || !B || !D || M <= 0 || N <= 0 || K <= 0) return MVAE_ERR_INVALID;
+  if (varlen && (!varlen->act || (varlen->mode != 1 && varlen->mode != 2) || varlen->rows_per_slab <= 0 ||
+                 (varlen->rows_per_slab % BM) || (varlen->mode == 1 ? M : K) % varlen->rows_per_slab))
+    return MVAE_ERR_INVALID;
   if (sample && (bn != 64 || splits > 1 || N > 64 || sample->V > N || !sample->w_cur || !sample->x || !sample->end || !sample->done))
     return MVAE_ERR_INVALID;
   if (cell && ((cell->gates != 3 && cell->gates != 4) || bn != cell->gates * 64 || splits > 1 || (cell->H & 63) ||
@@ -755,6 +780,9 @@ int mvae_umma_gemm(const mvae_umma_operand* A, const mvae_umma_operand* B, const
   if (cell) kp.cell = *cell;
   kp.sample_mode = sample ? 1 : 0;
   if (sample) kp.sample = *sample;
+  kp.vl_mode = varlen ? varlen->mode : 0;
+  kp.vl_act = varlen ? varlen->act : nullptr;
+  kp.vl_tiles = varlen ? varlen->rows_per_slab / (varlen->mode == 1 ? BM : BK) : 1;
   if (D->rb && (!D->bf16 || (D->ld & 7) || (N & 7))) return MVAE_ERR_INVALID;
   CUtensorMap tmA, tmB;
   int rc = make_map(&tmA, *A, BM);

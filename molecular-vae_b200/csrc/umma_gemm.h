@@ -79,8 +79,21 @@ struct mvae_umma_out {
   int rb;             // bf16 output only: row-blocked layout [M/32][ld/8][32][8] (consumed by the recurrence epilogues)
 };
 
+// Optional packed-sequence skipping for GEMMs over time-major slabs ([T][rows_per_slab][.], rows_per_slab % 128 == 0):
+// act[t] (DEVICE array) = number of leading rows of slab t that belong to sequences still running at step t.
+//   mode 1: the M dimension runs over (t, row): output tiles that lie entirely in the inactive part of their slab are
+//           skipped (their output rows keep whatever they held);
+//   mode 2: the K dimension runs over (t, row): 64-row k-blocks entirely in the inactive part are skipped (the caller
+//           guarantees that they would contribute zeros).
+struct mvae_umma_varlen {
+  const int* act;
+  int rows_per_slab;
+  int mode;
+};
+
 // bn: 0 = auto, else 64/128/192/256.  splits: split-K factor (fp32 atomics epilogue when > 1; the
 // caller zeroes D or passes an existing value to accumulate onto).  max_ctas: 0 = #SMs.
 int mvae_umma_gemm(const mvae_umma_operand* A, const mvae_umma_operand* B, const mvae_umma_out* D, int M, int N, int K,
                    int bn, int splits, int max_ctas, int* err_flag, cudaStream_t stream, const mvae_umma_head* head = nullptr,
-                   const mvae_umma_cell* cell = nullptr, const mvae_umma_sample* sample = nullptr);
+                   const mvae_umma_cell* cell = nullptr, const mvae_umma_sample* sample = nullptr,
+                   const mvae_umma_varlen* varlen = nullptr);
