@@ -224,10 +224,20 @@ int mvae_moses_step(const mvae_moses_desc* d, const float* const* params, float*
  * max_len-1 steps (desc->max_len = the sampler's max_len, 100 in the reference).  mode 0 = greedy argmax (ties ->
  * lowest id; the bit-exact parity mode), mode 1 = multinomial over softmax(y/temp) with a counter-based generator
  * (seed, sequence, step).  ids_out u8 (B,max_len): bos, generated ids up to and including eos, pad after;
- * lengths_out int32 (B) = the reference's end_pads (eos index + 1, or max_len).  All rows run every step.          */
+ * lengths_out int32 (B) = the reference's end_pads (eos index + 1, or max_len).  All rows run every step.
+ * seed_device (optional, DEVICE pointer): when given the generator seed is read from it at run time instead of `seed`,
+ * so a CUDA graph captured around this call can be replayed with fresh draws.                                        */
 int mvae_moses_sample(const mvae_moses_desc* d, const float* const* params, const float* z, int bos_id, int eos_id,
-                      int mode, float temp, unsigned long long seed, uint8_t* ids_out, int32_t* lengths_out,
-                      void* workspace, size_t workspace_bytes, mvae_stream_t stream);
+                      int mode, float temp, unsigned long long seed, const unsigned long long* seed_device,
+                      uint8_t* ids_out, int32_t* lengths_out, void* workspace, size_t workspace_bytes,
+                      mvae_stream_t stream);
+/* The sampler captured once into a CUDA graph over FIXED buffers (params, z, seed_device, ids_out, lengths_out,
+ * workspace); replay with mvae_graph_launch after writing fresh z / seed into the same buffers.  The weights are
+ * re-read from `params` at every replay.  Replaces the 99-iteration Python loop of mosesvae.py:239-251.          */
+int mvae_moses_sample_graph_create(const mvae_moses_desc* d, const float* const* params, const float* z, int bos_id,
+                                   int eos_id, int mode, float temp, const unsigned long long* seed_device,
+                                   uint8_t* ids_out, int32_t* lengths_out, void* workspace, size_t workspace_bytes,
+                                   mvae_graph** out_graph);
 int mvae_moses_read_error(const mvae_moses_desc* d, void* workspace, size_t workspace_bytes, int* flag,
                           mvae_stream_t stream);
 

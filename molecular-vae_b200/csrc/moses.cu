@@ -696,7 +696,7 @@ __device__ __forceinline__ float u01_hash(unsigned long long seed, unsigned int 
   return (float)((x >> 40) + 0.5) * (1.0f / 16777216.0f);
 }
 __global__ void sample_step_kernel(const float* __restrict__ logits, int CP, int V, int B, int step, int max_len,
-                                   int eos, int mode, float inv_temp, unsigned long long seed,
+                                   int eos, int mode, float inv_temp, unsigned long long seed, const unsigned long long* seed_dev,
                                    uint8_t* __restrict__ w_cur, uint8_t* __restrict__ x, int* __restrict__ end,
                                    uint8_t* __restrict__ done) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -722,7 +722,7 @@ __global__ void sample_step_kernel(const float* __restrict__ logits, int CP, int
       if (lane >= o) { c0 += t0; c1 += t1; }
     }
     const float tot0 = __shfl_sync(0xffffffffu, c0, 31), tot1 = __shfl_sync(0xffffffffu, c1, 31);
-    const float u = u01_hash(seed, (unsigned)b, (unsigned)step) * (tot0 + tot1);
+    const float u = u01_hash(seed_dev ? *seed_dev : seed, (unsigned)b, (unsigned)step) * (tot0 + tot1);
     // first id whose cumulative mass exceeds u
     const unsigned m0 = __ballot_sync(0xffffffffu, c0 > u);
     const unsigned m1 = __ballot_sync(0xffffffffu, tot0 + c1 > u);
@@ -764,7 +764,8 @@ bool sample_fused_enabled() {
 // contributions of x and h summed by a K = 2H contraction over the concatenated operand), so no gate pre-activations
 // reach HBM and a step is L + 1 GEMMs + 2 small kernels instead of 2L GEMMs + L gate kernels + 3.
 int sample_fused(const MDims& d, const MWS& w, const float* const* P, const float* z, int bos, int eos, int mode, float temp,
-                 unsigned long long seed, uint8_t* ids_out, int* len_out, uint8_t* w_cur, uint8_t* done, cudaStream_t st) {
+                 unsigned long long seed, const unsigned long long* seed_dev, uint8_t* ids_out, int* len_out, uint8_t* w_cur,
+                 uint8_t* done, cudaStream_t st) {
   typedef __nv_bfloat16 TA;
   const int B = d.B, Bp = d.Bp, V = d.V, CP = d.CP, Z = d.Z, Hd = d.Hd, L = d.L, max_len = d.T;
   const int IN0 = V + Z;
@@ -808,7 +809,7 @@ int sample_fused(const MDims& d, const MWS& w, const float* const* P, const floa
     mvae_umma_operand a{top, 0, Bp, Hd, L > 1 ? 2 * Hd : Hd, 1, 0, 0, 0};
     mvae_umma_operand b{w.Wfc, 0, CP, Hd, Hd, 1, 0, 0, 0};
     mvae_umma_out o{w.logits, CP, 0, 0, w.bfc, 0};
-    mvae_umma_sample sp{V, B, i, max_len, eos, mode, 1.0f / temp, seed, w_cur, ids_out, len_out, done};
+    mvae_umma_sample sp{V, B, i, max_len, eos, mode, 1.0f / temp, seed, seed_dev, w_cur, ids_out, len_out, done};
     mvae_count_launches(1);
     RC(mvae_umma_gemm(&a, &b, &o, Bp, CP, Hd, 64, 1, 0, w.err_flag, st, nullptr, nullptr, &sp));
   }
@@ -817,7 +818,8 @@ int sample_fused(const MDims& d, const MWS& w, const float* const* P, const floa
 
 template <typename TA>
 int sample_t(const MDims& d, const MWS& w, const float* const* P, const float* z, int bos, int eos, int mode, float temp,
-             unsigned long long seed, uint8_t* ids_out, int* len_out, uint8_t* w_cur, uint8_t* done, cudaStream_t st) {
+             unsigned long long seed, const unsigned long long* seed_dev, uint8_t* ids_out, int* len_out, uint8_t* w_cur,
+             uint8_t* done, cudaStream_t st) {
   const int B = d.B, Bp = d.Bp, V = d.V, CP = d.CP, Z = d.Z, Hd = d.Hd, L = d.L, max_len = d.T;
   const int IN0 = V + Z;
   const MP ix{d.bidir, d.lin, L};
@@ -872,7 +874,7 @@ int sample_t(const MDims& d, const MWS& w, const float* const* P, const float* z
     }
     RC(gemm<TA>(w.err_flag, st, (const TA*)w.hs[L - 1] + nxt * slab, Hd, false, (const TA*)w.Wfc, Hd, true, w.logits, CP, false, Bp, CP, Hd,
                 w.bfc, false, 1, 64));
-    sample_step_kernel<<<ceil_div(B * 32, 256), 256, 0, st>>>(w.logits, CP, V, B, i, max_len, eos, mode, 1.0f / temp, seed, w_cur,
+    sample_step_kernel<<<ceil_div(B * 32, 256), 256, 0, st>>>(w.logits, CP, V, B, i, max_len, eos, mode, 1.0f / temp, seed, seed_dev, w_cur,
                                                               ids_out, len_out, done);
     KCHECK();
   }
@@ -926,8 +928,8 @@ int mvae_moses_step(const mvae_moses_desc* desc, const float* const* params, flo
 }
 
 int mvae_moses_sample(const mvae_moses_desc* desc, const float* const* params, const float* z, int bos_id, int eos_id,
-                      int mode, float temp, unsigned long long seed, uint8_t* ids_out, int32_t* lengths_out,
-                      void* workspace, size_t workspace_bytes, mvae_stream_t stream) {
+                      int mode, float temp, unsigned long long seed, const unsigned long long* seed_device, uint8_t* ids_out,
+                      int32_t* lengths_out, void* workspace, size_t workspace_bytes, mvae_stream_t stream) {
   MDims d; MWS w;
   RC(check_ws(desc, workspace, workspace_bytes, &d, &w));
   if (!params || !z || !ids_out || !lengths_out || temp <= 0.f || (mode != 0 && mode != 1)) return MVAE_ERR_INVALID;
@@ -936,9 +938,27 @@ int mvae_moses_sample(const mvae_moses_desc* desc, const float* const* params, c
   uint8_t* w_cur = reinterpret_cast<uint8_t*>(w.OH);
   uint8_t* done = w_cur + d.Bp;
   if (d.bf16 && sample_fused_enabled())
-    return sample_fused(d, w, params, z, bos_id, eos_id, mode, temp, seed, ids_out, lengths_out, w_cur, done, st);
-  return d.bf16 ? sample_t<__nv_bfloat16>(d, w, params, z, bos_id, eos_id, mode, temp, seed, ids_out, lengths_out, w_cur, done, st)
-                : sample_t<float>(d, w, params, z, bos_id, eos_id, mode, temp, seed, ids_out, lengths_out, w_cur, done, st);
+    return sample_fused(d, w, params, z, bos_id, eos_id, mode, temp, seed, seed_device, ids_out, lengths_out, w_cur, done, st);
+  return d.bf16 ? sample_t<__nv_bfloat16>(d, w, params, z, bos_id, eos_id, mode, temp, seed, seed_device, ids_out, lengths_out, w_cur, done, st)
+                : sample_t<float>(d, w, params, z, bos_id, eos_id, mode, temp, seed, seed_device, ids_out, lengths_out, w_cur, done, st);
+}
+
+int mvae_moses_sample_graph_create(const mvae_moses_desc* desc, const float* const* params, const float* z, int bos_id,
+                                   int eos_id, int mode, float temp, const unsigned long long* seed_device,
+                                   uint8_t* ids_out, int32_t* lengths_out, void* workspace, size_t workspace_bytes,
+                                   mvae_graph** out_graph) {
+  if (!seed_device) return MVAE_ERR_INVALID;
+  struct Ctx {
+    const mvae_moses_desc* desc; const float* const* params; const float* z; int bos, eos, mode; float temp;
+    const unsigned long long* seed_dev; uint8_t* ids; int32_t* lens; void* ws; size_t ws_bytes;
+  } c{desc, params, z, bos_id, eos_id, mode, temp, seed_device, ids_out, lengths_out, workspace, workspace_bytes};
+  return mvae_capture_into_graph(
+      [](void* p, cudaStream_t cs) {
+        Ctx* c = static_cast<Ctx*>(p);
+        return mvae_moses_sample(c->desc, c->params, c->z, c->bos, c->eos, c->mode, c->temp, 0ull, c->seed_dev, c->ids,
+                                 c->lens, c->ws, c->ws_bytes, reinterpret_cast<mvae_stream_t>(cs));
+      },
+      &c, out_graph);
 }
 
 int mvae_moses_read_error(const mvae_moses_desc* desc, void* workspace, size_t workspace_bytes, int* flag,

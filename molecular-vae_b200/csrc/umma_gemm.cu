@@ -466,7 +466,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                   v[j] = expf(v[j] - m);
                   tot += v[j];
                 }
-                const float uu = u01_hash_gemm(sp.seed, (unsigned)row, (unsigned)sp.step) * tot;
+                const float uu = u01_hash_gemm(sp.seed_dev ? *sp.seed_dev : sp.seed, (unsigned)row, (unsigned)sp.step) * tot;
                 float cum = 0.f;
                 bool found = false;
 #pragma unroll

@@ -64,6 +64,8 @@ struct mvae_umma_sample {
   int V, B, step, max_len, eos, mode;
   float inv_temp;
   unsigned long long seed;
+  const unsigned long long* seed_dev;   // optional: read the seed from device memory (a captured CUDA graph can then be
+                                        // replayed with fresh draws)
   unsigned char* w_cur;       // [B] token fed to the next step
   unsigned char* x;           // [B][max_len]
   int* end;                   // [B]

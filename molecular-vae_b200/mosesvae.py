@@ -9,6 +9,7 @@ decoder GRU's inter-layer dropout (p = 0.2, mosesvae.py:38,78) is applied with a
 cuDNN / torch mask stream cannot be reproduced; parity runs inject the same mask into the oracle); eval() disables it.
 """
 import ctypes
+import os
 
 import torch
 from torch import nn
@@ -252,8 +253,10 @@ class VAE(nn.Module):
         return torch.randn(n_batch, self.cfg["d_z"], device=self.device)
 
     @torch.no_grad()
-    def sample_ids(self, n_batch, max_len=100, z=None, temp=1.0, greedy=False, seed=None):
-        """Device-side result of sample(): (ids u8 (B,max_len), lengths int32 (B), z)."""
+    def sample_ids(self, n_batch, max_len=100, z=None, temp=1.0, greedy=False, seed=None, use_graph=True):
+        """Device-side result of sample(): (ids u8 (B,max_len), lengths int32 (B), z).  With use_graph the whole decode
+        loop (mosesvae.py:239-251, 99 steps) is one CUDA-graph replay over fixed buffers: z and the generator seed are
+        written into them before each replay, the weights are re-read from the parameters every time."""
         if z is None:
             z = self.sample_z_prior(n_batch)
         z = z.to(self.device, torch.float32).contiguous()
@@ -263,20 +266,53 @@ class VAE(nn.Module):
                       int(self.pad), prec, 1.0, 1.0, int(c.get("q_bidir", 0)), int(c.get("q_linear_heads", 0)), 0.0, 0)
         need = lib.mvae_moses_workspace_bytes(ctypes.byref(d))
         dev = z.device
+        if seed is None:
+            seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+        params = [p.detach() for p in self.ordered_params()]
+        mode = 0 if greedy else 1
+        if use_graph:
+            key = (B, int(max_len), mode, float(temp), self.precision, dev, os.environ.get("MVAE_SAMPLE_FUSED", ""),
+                   tuple(p.data_ptr() for p in params))
+            g = getattr(self, "_sample_graph", None)
+            if g is None or g["key"] != key:
+                self.destroy_sample_graph()
+                ws = torch.empty(need + 256, dtype=torch.uint8, device=dev)
+                g = {"key": key, "ws": ws, "z": torch.empty_like(z), "seed": torch.zeros(1, dtype=torch.int64, device=dev),
+                     "ids": torch.empty(B, int(max_len), dtype=torch.uint8, device=dev),
+                     "lens": torch.empty(B, dtype=torch.int32, device=dev), "desc": d, "params": params,
+                     "ptrs": _ptr_table(params)}
+                g["wsp"] = ctypes.c_void_p(ws.data_ptr() + (-ws.data_ptr()) % 256)
+                handle = ctypes.c_void_p()
+                with torch.cuda.device(dev):
+                    torch.cuda.current_stream().synchronize()
+                    check(lib.mvae_moses_sample_graph_create(ctypes.byref(d), g["ptrs"], _p(g["z"]), int(self.bos),
+                                                             int(self.eos), mode, float(temp), _p(g["seed"]), _p(g["ids"]),
+                                                             _p(g["lens"]), g["wsp"], need, ctypes.byref(handle)))
+                g["handle"] = handle
+                self._sample_graph = g
+            g["z"].copy_(z)
+            g["seed"].fill_(seed)
+            with torch.cuda.device(dev):
+                check(lib.mvae_graph_launch(g["handle"], _stream()))
+            self._last_desc = (g["desc"], g["wsp"], need)
+            return g["ids"].clone(), g["lens"].clone(), z
         if self._ws is None or self._ws.numel() < need + 256 or self._ws.device != dev:
             self._ws = torch.empty(need + 256, dtype=torch.uint8, device=dev)
         wsp = ctypes.c_void_p(self._ws.data_ptr() + (-self._ws.data_ptr()) % 256)
         ids = torch.empty(B, int(max_len), dtype=torch.uint8, device=dev)
         lens = torch.empty(B, dtype=torch.int32, device=dev)
-        if seed is None:
-            seed = int(torch.randint(0, 2 ** 62, (1,)).item())
-        params = [p.detach() for p in self.ordered_params()]
         with torch.cuda.device(dev):
             check(lib.mvae_moses_sample(ctypes.byref(d), _ptr_table(params), _p(z), int(self.bos), int(self.eos),
-                                        0 if greedy else 1, float(temp), ctypes.c_ulonglong(seed), _p(ids), _p(lens), wsp,
+                                        mode, float(temp), ctypes.c_ulonglong(seed), None, _p(ids), _p(lens), wsp,
                                         need, _stream()))
         self._last_desc = (d, wsp, need)
         return ids, lens, z
+
+    def destroy_sample_graph(self):
+        g = getattr(self, "_sample_graph", None)
+        if g is not None:
+            lib.mvae_graph_destroy(g["handle"])
+            self._sample_graph = None
 
     def sample(self, n_batch, max_len=100, z=None, temp=1.0, greedy=False, seed=None):
         """mosesvae.py:214-262: returns (list[str], z).  Multinomial draws by default (the reference behaviour),

@@ -333,3 +333,26 @@ def test_moses_sample_fused_cell_gemm_bf16(monkeypatch):
     same_unfused = np.mean([(ids_f[b] == ids_u[b]).all() for b in range(B)])
     first_tok = (ids_f[:, 1] == x_ref[:, 1]).mean()
     assert first_tok >= 0.97 and same_oracle >= 0.6 and same_unfused >= 0.6, (first_tok, same_oracle, same_unfused)
+
+
+def test_moses_sample_graph_replay_equals_direct_launch():
+    """The decode loop captured into one CUDA graph (mvae_moses_sample_graph_create, seed / z read from device buffers at
+    replay time) returns exactly what the direct launch returns, for new latents and new seeds without re-capture."""
+    m = load_pkg()
+    P, seqs, eps, pad, model = _setup(m, "bf16", 317, 417, 4)
+    B, max_len = 300, 30
+    gen = torch.Generator().manual_seed(9)
+    for it, (greedy, seed) in enumerate(((True, 1), (False, 5), (False, 6), (False, 5))):
+        z = torch.randn(B, 160, generator=gen).cuda()
+        ids_d, len_d, _ = model.sample_ids(B, max_len=max_len, z=z, greedy=greedy, seed=seed, use_graph=False)
+        ids_g, len_g, _ = model.sample_ids(B, max_len=max_len, z=z, greedy=greedy, seed=seed, use_graph=True)
+        torch.cuda.synchronize()
+        model.check_device_error()
+        assert torch.equal(ids_d, ids_g) and torch.equal(len_d, len_g), (it, greedy, seed)
+    handle = model._sample_graph["handle"].value
+    z = torch.randn(B, 160, generator=gen).cuda()
+    a, _, _ = model.sample_ids(B, max_len=max_len, z=z, greedy=False, seed=8)
+    b, _, _ = model.sample_ids(B, max_len=max_len, z=z, greedy=False, seed=9)
+    assert model._sample_graph["handle"].value == handle              # same graph, fresh draws
+    assert (a != b).float().mean().item() > 0.1
+    model.destroy_sample_graph()
