@@ -21,6 +21,14 @@ struct mvae_gru_rec_args {
   int ones_col;              // gru_rec2 fwd: hidden-unit index whose h is forced to 1.0 (-1: none)
   int debug;                 // timing experiments only (gru_rec2): bit0 skip counter waits, bit1 de-share operand rows
   unsigned long long* trace; // optional debug timestamps [T][tiles per CTA][8] of CTA (0,0), may be null
+  const float* h0;           // gru_rec2 fwd, optional: fp32 initial state [Bp][Hp]; hs slab 0 must hold its bf16 copy
+  float* carry_out;          // gru_rec2 bwd, optional: fp32 [Bp][Hp] <- dh_0 * z_0 (add dgh_0 * W_hh for dL/dh0)
+  // gru_rec2 fwd, optional token-table input projection: gi(row, t) = tbl[tok[t][row]] (+ gi when gi != null)
+  const float* tbl;          // [V][3Hp] fp32 (r,z,n), biases folded in
+  const unsigned char* tok;  // [T][Bp]
+  int V;                     // <= 64
+  // gru_rec2 fwd, optional: hlast[row][:] = fp32 state after step lens[row]-1, rows < nrows
+  const int* lens; float* hlast; int nrows;
 };
 
 // rows (molecules) one cooperative launch can cover on a device with num_sms SMs (0: shape unsupported)

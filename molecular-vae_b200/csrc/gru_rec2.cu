@@ -47,6 +47,17 @@ struct Params2 {
   int a_box_rows;            // rows per operand TMA box (128, 64 or 32): a stage is loaded as 128/a_box_rows boxes
   int ones_col;              // fwd: hidden-unit index forced to 1.0 (bias-gradient trick) or -1
   int debug;                 // timing experiments only: bit0 skip counter waits, bit1 de-share operand rows
+  const float* h0;           // fwd, optional: fp32 initial state [Bp][Hp] (hs slab 0 holds its bf16 copy); null = zeros
+  float* carry_out;          // bwd, optional: fp32 [Bp][Hp], receives dh_t * z_t of the last processed step (t = 0); the
+                             // gradient wrt the initial state is carry_out + dgh_0 * W_hh (one GEMM, done by the caller)
+  // fwd, optional token-table input projection (embedding layers: x_t W_ih^T is a row of a [V][3Hp] table): the pair's
+  // slice of the table lives in shared memory (bf16) and gi(row, t) = table[tok[t][row]] (+ gi if gi != null)
+  const float* tbl;          // [V][3Hp] fp32, (r,z,n) blocks, biases folded in by the caller
+  const unsigned char* tok;  // [T][Bp] token ids (time-major)
+  int V;
+  int nst;                   // operand stages actually used (<= NST; the table takes the place of the others)
+  // fwd, optional: state after each row's last valid step, hlast[row][:] = h_{lens[row]-1} (fp32, rows < nrows)
+  const int* lens; float* hlast; int nrows;
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -178,8 +189,11 @@ gru_rec2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
   const int KCS = (p.debug & 256) ? KC / 2 : KC;   // timing experiment: stream only half of K (wrong results)
   uint8_t* sW = smem;
   uint8_t* sA = smem + (size_t)KC * CHUNK;
-  float* xbuf = reinterpret_cast<float*>(sA + NST * A_STAGE);   // KS: [64 units][128 rows], reused by consecutive tile-steps
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sA + NST * A_STAGE + (KS ? XBUF : 0));
+  const int nst = p.nst;                                        // stages in use (NST unless a token table needs the room)
+  float* xbuf = reinterpret_cast<float*>(sA + nst * A_STAGE);   // KS: [64 units][128 rows], reused by consecutive tile-steps
+  __nv_bfloat16* sTbl = reinterpret_cast<__nv_bfloat16*>(sA + nst * A_STAGE + (KS ? XBUF : 0));   // fwd: [V][3][64]
+  const int tbl_bytes = (!BWD && p.tbl) ? ((p.V * 3 * RU * 2 + 1023) & ~1023) : 0;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sA + nst * A_STAGE + (KS ? XBUF : 0) + tbl_bytes);
   uint64_t* full_bar = bars;                         // [NST] own operand stage landed (tx)
   uint64_t* empty_bar = bars + NST;                  // [NST] all pairs that share the stage consumed it
   uint64_t* pfull_bar = bars + 2 * NST;              // [NST] leader: peer's stage landed (relayed)
@@ -232,6 +246,11 @@ gru_rec2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
     ptx::fence_mbar_init();
   }
   if (!BWD) for (int i = threadIdx.x; i < RU; i += THREADS) sBias[i] = p.bhn[u0 + i];
+  if (!BWD && p.tbl)
+    for (int i = threadIdx.x; i < p.V * 3 * RU; i += THREADS) {
+      const int v = i / (3 * RU), g = (i / RU) % 3, u = i % RU;
+      sTbl[i] = __float2bfloat16_rn(p.tbl[(size_t)v * 3 * p.Hp + g * p.Hp + u0 + u]);
+    }
   if (warp == 1) tmem_alloc2(tmem_holder, TMEM_COLS);
   ptx::tc_fence_before();
   __syncthreads();
@@ -266,7 +285,7 @@ gru_rec2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
         }
       }
       int s = 0; uint32_t ph = 0;
-      for (int step = 1; step < p.T; ++step) {
+      for (int step = (!BWD && p.h0) ? 0 : 1; step < p.T; ++step) {
         int slab = BWD ? (p.T - step) : step;
         if (p.debug & 2) slab = (slab + pair * 5) % p.T;
         if (p.debug & 16) slab = 0;   // timing experiment: operand that nobody writes during the sweep
@@ -295,7 +314,7 @@ gru_rec2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
               ptx::mbar_arrive_expect_tx(&full_bar[s], A_STAGE);
               tma_load_3d_mc(sA + s * A_STAGE + qd * A_PART, &tmA, &full_bar[s], mask_par, kc * 64, row0, slab);
             }
-            if (++s == NST) { s = 0; ph ^= 1; }
+            if (++s == nst) { s = 0; ph ^= 1; }
           }
           if (p.trace && blockIdx.x == 0 && blockIdx.y == 0) p.trace[((size_t)step * NTILES + i) * 12 + 1] = gtime();
         }
@@ -318,7 +337,7 @@ gru_rec2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
             for (int kc = 0; kc < KC; ++kc) {
               if (!wait_bar(&full_bar[s], ph, p.err_flag)) goto done;
               remote_arrive_relaxed(mapa(ptx::smem_u32(&pfull_bar[s]), lrank));
-              if (++s == NST) { s = 0; ph ^= 1; }
+              if (++s == nst) { s = 0; ph ^= 1; }
             }
       } else {
         // ===================== MMA issuer (even CTA, one thread for the pair) =====================
@@ -328,8 +347,8 @@ gru_rec2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
         int s = 0; uint32_t ph = 0;
         for (int step = 0; step < p.T; ++step) {
           for (int i = 0; i < ntiles; ++i) {
-            if (step > 0) {
-              if (!wait_bar(&tempty_bar[i], (uint32_t)((step - 1) & 1), p.err_flag)) goto done;
+            if (step > 0 || (!BWD && p.h0)) {
+              if (step > 0 && !wait_bar(&tempty_bar[i], (uint32_t)((step - 1) & 1), p.err_flag)) goto done;
               ptx::tc_fence_after();
               const uint32_t d_tmem = tmem_base + i * NB;
               for (int kc0 = 0; kc0 < KCS; ++kc0) {
@@ -351,7 +370,7 @@ gru_rec2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
                 }
                 // stage s is free (for this pair) in every CTA that shares it: the pair itself, or the whole multicast cluster
                 commit2_mc(&empty_bar[s], CL == 2 ? mask_pair : (uint16_t)((1u << CL) - 1));
-                if (++s == NST) { s = 0; ph ^= 1; }
+                if (++s == nst) { s = 0; ph ^= 1; }
               }
             }
             const unsigned long long t_issue = (p.debug & 8) ? gtime() : 0ull;
@@ -411,6 +430,7 @@ gru_rec2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
         // this thread's 16 units of its row are two 16-byte pieces 512 B apart; a warp access is 512 B contiguous.
         const long long rblk = row >> 5;   // = tile*8 + parity*4 + q ; row & 31 == lane
         u32x8 pre[BWD ? 6 : 3];
+        int tokv = 0;
         const bool nomem = (p.debug & 32) != 0;   // timing experiment: epilogue without global traffic
         if (nomem) {
 #pragma unroll
@@ -418,10 +438,18 @@ gru_rec2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
 #pragma unroll
             for (int k = 0; k < 8; ++k) pre[a].v[k] = 0x3c003c00u;
         } else if (!BWD) {
-          const __nv_bfloat16* g = p.gi + (long long)t * p.gi_tstride +
-                                   (rblk * (3 * p.Hp / 8) + ((u0 + uc) >> 3)) * 256 + lane * 8;
+          if (p.gi) {
+            const __nv_bfloat16* g = p.gi + (long long)t * p.gi_tstride +
+                                     (rblk * (3 * p.Hp / 8) + ((u0 + uc) >> 3)) * 256 + lane * 8;
 #pragma unroll
-          for (int gate = 0; gate < 3; ++gate) pre[gate] = ldg2x128(g + (long long)gate * (p.Hp / 8) * 256);
+            for (int gate = 0; gate < 3; ++gate) pre[gate] = ldg2x128(g + (long long)gate * (p.Hp / 8) * 256);
+          } else {
+#pragma unroll
+            for (int gate = 0; gate < 3; ++gate)
+#pragma unroll
+              for (int k = 0; k < 8; ++k) pre[gate].v[k] = 0u;
+          }
+          if (p.tok) tokv = p.tok[(long long)t * p.Bp + row];
         } else {
 #pragma unroll
           for (int blk = 0; blk < 4; ++blk) pre[blk] = ldg2x128(svp + blk * 2048);
@@ -442,6 +470,20 @@ gru_rec2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
             ptx::tmem_ld_32x16(acc + 2 * RU, an);
             ptx::tmem_ld_32x16(master_addr, hm);
             ptx::tmem_ld_wait();
+          } else if (p.h0) {
+            // non-zero initial state: the step-0 MMAs contracted over hs slab 0 (= bf16 h0), the fp32 master starts from h0
+            const uint32_t acc = tmem_base + lane_off + i * NB + uc;
+            ptx::tmem_ld_32x16(acc, ar);
+            ptx::tmem_ld_32x16(acc + RU, az);
+            ptx::tmem_ld_32x16(acc + 2 * RU, an);
+            const float4* h0p = reinterpret_cast<const float4*>(p.h0 + row * p.Hp + u0 + uc);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const float4 v = __ldg(h0p + k);
+              hm[4 * k] = __float_as_uint(v.x); hm[4 * k + 1] = __float_as_uint(v.y);
+              hm[4 * k + 2] = __float_as_uint(v.z); hm[4 * k + 3] = __float_as_uint(v.w);
+            }
+            ptx::tmem_ld_wait();
           } else {
 #pragma unroll
             for (int k = 0; k < 16; ++k) { ar[k] = 0u; az[k] = 0u; an[k] = 0u; hm[k] = 0u; }
@@ -452,6 +494,21 @@ gru_rec2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
           unpack16(pre[0], gr);
           unpack16(pre[1], gz);
           unpack16(pre[2], gn);
+          if (p.tok) {
+            // token-table part of the input projection: this row's token selects one bf16 row per gate in shared memory
+            const uint4* tr = reinterpret_cast<const uint4*>(sTbl + (size_t)tokv * 3 * RU + uc);
+            float tv[16];
+            u32x8 tq;
+#pragma unroll
+            for (int gate = 0; gate < 3; ++gate) {
+              const uint4 a = tr[gate * (RU / 8)], b = tr[gate * (RU / 8) + 1];
+              tq.v[0] = a.x; tq.v[1] = a.y; tq.v[2] = a.z; tq.v[3] = a.w; tq.v[4] = b.x; tq.v[5] = b.y; tq.v[6] = b.z; tq.v[7] = b.w;
+              unpack16(tq, tv);
+              float* dst = gate == 0 ? gr : gate == 1 ? gz : gn;
+#pragma unroll
+              for (int k = 0; k < 16; ++k) dst[k] += tv[k];
+            }
+          }
           float h[16];
 #pragma unroll
           for (int k = 0; k < 16; ++k) {
@@ -467,6 +524,11 @@ gru_rec2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
             an[k] = __float_as_uint(ghn);
           }
           if (tr2) p.trace[((size_t)step * NTILES + i) * 12 + 9] = gtime();
+          if (p.hlast && row < p.nrows && t == p.lens[row] - 1) {
+            float4* hl = reinterpret_cast<float4*>(p.hlast + row * p.Hp + u0 + uc);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) hl[k] = make_float4(h[4 * k], h[4 * k + 1], h[4 * k + 2], h[4 * k + 3]);
+          }
           tmem_st_32x16(master_addr, h);
           if (!nomem) stg256(p.hs + ((long long)(t + 1) * p.Bp + row) * p.Hp + u0 + uc, h);
           // everything other CTAs / the MMA wait for is issued: let the publisher go before the saved-gate stores
@@ -542,6 +604,11 @@ gru_rec2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
             n[k] = dan; ghn[k] = dar; dx[k] = daz;
           }
           tmem_st_32x16(master_addr, carry);
+          if (p.carry_out && t == 0) {
+            float4* co = reinterpret_cast<float4*>(p.carry_out + row * p.Hp + u0 + uc);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) co[k] = make_float4(carry[4 * k], carry[4 * k + 1], carry[4 * k + 2], carry[4 * k + 3]);
+          }
           __nv_bfloat16* g4 = p.dG + ((long long)t * p.Bp + row) * 4 * p.Hp + u0 + uc;
           if (!nomem) {
             // the three dgh blocks the other pairs stream next step go first; da_n (only read by the later wgrad / dX
@@ -602,7 +669,13 @@ int launch2(const mvae_gru_rec_args& a, cudaStream_t st) {
   const int Hp = a.Hp, Bp = a.Bp, T = a.T;
   constexpr int NBH = (BWD ? (KS ? 2 * RU : RU) : 3 * RU) / 2;
   const int KC = (BWD ? 3 * Hp : Hp) / 64 / (KS ? 2 : 1);
-  const size_t smem = (size_t)KC * NBH * 128 + (size_t)(KS ? 6 : STAGES) * A_STAGE + (KS ? 128 * RU * 4 : 0) + 1024 + 1024;
+  const bool use_tbl = !BWD && a.tbl && a.tok;
+  if (use_tbl && (a.V < 1 || a.V > 64)) return MVAE_ERR_INVALID;
+  const size_t tbl_bytes = use_tbl ? (((size_t)a.V * 3 * RU * 2 + 1023) & ~(size_t)1023) : 0;
+  int nst = KS ? 6 : STAGES;
+  const size_t fixed = (size_t)KC * NBH * 128 + (KS ? 128 * RU * 4 : 0) + tbl_bytes + 1024 + 1024;
+  while (nst > 2 && fixed + (size_t)nst * A_STAGE > 232448) --nst;   // the token table takes the room of operand stages
+  const size_t smem = fixed + (size_t)nst * A_STAGE;
   if (smem > 232448) return MVAE_ERR_UNSUPPORTED;
   CUtensorMap tmW, tmA;
   {
@@ -632,11 +705,15 @@ int launch2(const mvae_gru_rec_args& a, cudaStream_t st) {
   p.gi = a.gi; p.gi_tstride = a.gi_tstride; p.bhn = a.bhh; p.hs = a.hs; p.sv = a.sv; p.dX = a.dX; p.dG = a.dG;
   p.counters = a.counters; p.err_flag = a.err_flag; p.trace = a.trace; p.debug = a.debug; p.ones_col = a.ones_col;
   p.a_box_rows = a.a_box_rows > 0 ? a.a_box_rows : 128;
+  p.h0 = BWD ? nullptr : a.h0; p.carry_out = BWD ? a.carry_out : nullptr;
+  p.nst = nst;
+  p.tbl = use_tbl ? a.tbl : nullptr; p.tok = use_tbl ? a.tok : nullptr; p.V = use_tbl ? a.V : 0;
+  p.lens = BWD ? nullptr : a.lens; p.hlast = (BWD || !a.lens) ? nullptr : a.hlast; p.nrows = a.nrows;
   auto kern = gru_rec2_kernel<BWD, FAST, CL, KS>;
-  static bool attr = false;
-  if (!attr) {
+  static size_t attr_smem = 0;
+  if (smem > attr_smem) {
     MVAE_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = true;
+    attr_smem = smem;
   }
   MVAE_CUDA_CHECK(cudaMemsetAsync(a.counters, 0, sizeof(unsigned int) * 2 * (Bp / 256), st));
   cudaLaunchConfig_t cfg{};

@@ -36,17 +36,17 @@ inline int memset_async(void* p, size_t bytes, cudaStream_t st) {
 template <typename TA>
 int gemm(int* err_flag, cudaStream_t st, const TA* A, long long lda, bool a_trans, const TA* B, long long ldb,
          bool b_kmajor, void* out, long long ldc, bool out_is_ta, int M, int N, int K, const float* bias,
-         bool accumulate, int splits, int bn = 0, const mvae_umma_varlen* vl = nullptr) {
+         bool accumulate, int splits, int bn = 0, const mvae_umma_varlen* vl = nullptr, bool out_rb = false) {
   mvae_count_launches(1);
   if constexpr (sizeof(TA) == 4) {
-    (void)out_is_ta; (void)bn; (void)err_flag; (void)vl;
+    (void)out_is_ta; (void)bn; (void)err_flag; (void)vl; (void)out_rb;
     return simt::sgemm(st, reinterpret_cast<const float*>(A), a_trans ? 1 : lda, a_trans ? lda : 1,
                        reinterpret_cast<const float*>(B), b_kmajor ? 1 : ldb, b_kmajor ? ldb : 1,
                        reinterpret_cast<float*>(out), ldc, M, N, K, bias, simt::ACT_NONE, accumulate ? 1 : 0, splits);
   } else {
     mvae_umma_operand a{A, a_trans ? 1 : 0, M, K, lda, 1, 0, 0, 0};
     mvae_umma_operand b{B, b_kmajor ? 0 : 1, N, K, ldb, 1, 0, 0, 0};
-    mvae_umma_out o{out, ldc, out_is_ta ? 1 : 0, accumulate ? 1 : 0, bias, 0};
+    mvae_umma_out o{out, ldc, out_is_ta ? 1 : 0, accumulate ? 1 : 0, bias, out_rb ? 1 : 0};
     return mvae_umma_gemm(&a, &b, &o, M, N, K, bn, splits, 0, err_flag, st, nullptr, nullptr, nullptr, vl);
   }
 }

@@ -20,6 +20,7 @@
 #include "simt_kernels.cuh"
 #include "umma_gemm.h"
 #include "host_common.cuh"
+#include "gru_rec.h"
 
 namespace {
 
@@ -67,6 +68,9 @@ struct MWS {
   void *Whh_enc, *Whh[4], *Wih[4], *Wih_nrz[4], *Wfc;
   float *bhh_enc, *bih[4], *bhh[4], *bfc;
   float *dW_p, *dWfc_p, *csum;
+  // persistent decoder recurrence (gru_rec2.cu): W_hh^T [Hd][3Hd] bf16, b_ih + (b_hr, b_hz, 0), inter-CTA step counters
+  void *WhhT[4]; float *bcomb[4]; unsigned int* counters;
+  void *WhhT_enc; float *tbl_comb; uint8_t* tokT; void* zproj_rb;   // encoder W_hh^T, table + (b_hr, b_hz, 0), ids^T [T][Bp], zproj RB bf16
   size_t total;
 };
 
@@ -93,10 +97,10 @@ void carve(const MDims& d, void* base, MWS* w) {
   }
   w->OH = c.take<uint8_t>(T * Bp * d.CP * es);
   w->gi = c.take<uint8_t>(T * Bp * 3 * Hd * es);
-  w->hs_enc = c.take<uint8_t>((T + 1) * Bp * Hq * es); w->sv_enc = c.take<uint8_t>(T * Bp * 4 * Hq * es);
+  w->hs_enc = c.take<uint8_t>((T + 1) * Bp * Hq * es); w->sv_enc = c.take<uint8_t>(T * Bp * 5 * Hq * es);
   for (int l = 0; l < d.L; ++l) {
     w->hs[l] = c.take<uint8_t>((T + 1) * Bp * Hd * es);
-    w->sv[l] = c.take<uint8_t>(T * Bp * 4 * Hd * es);
+    w->sv[l] = c.take<uint8_t>(T * Bp * 5 * Hd * es);   // 5: the persistent kernels also save h_{t-1} (fragment layout)
   }
   w->dG = c.take<uint8_t>(T * Bp * 4 * Hd * es); w->dX = c.take<uint8_t>(T * Bp * Hd * es);
   w->hdrop = c.take<uint8_t>(T * Bp * Hd * es);
@@ -117,6 +121,10 @@ void carve(const MDims& d, void* base, MWS* w) {
     w->bih[l] = c.take<float>(3 * Hd); w->bhh[l] = c.take<float>(3 * Hd);
   }
   w->Wfc = c.take<uint8_t>(d.CP * Hd * es); w->bfc = c.take<float>(d.CP);
+  for (int l = 0; l < d.L; ++l) { w->WhhT[l] = c.take<uint8_t>(3 * Hd * Hd * 2); w->bcomb[l] = c.take<float>(3 * Hd); }
+  w->counters = c.take<unsigned int>(2 * (Bp / 256) + 64);
+  w->WhhT_enc = c.take<uint8_t>(3 * Hq * Hq * 2); w->tbl_comb = c.take<float>((size_t)64 * 3 * (Hd > Hq ? Hd : Hq));
+  w->tokT = c.take<uint8_t>(T * Bp); w->zproj_rb = c.take<uint8_t>(Bp * 3 * Hd * 2);
   w->dW_p = c.take<float>(3 * Hd * Hd); w->dWfc_p = c.take<float>(d.CP * Hd); w->csum = c.take<float>(4 * Hd);
   w->total = (c.off + 255) & ~size_t(255);
 }
@@ -312,23 +320,71 @@ __global__ void finalize_kernel(const double* __restrict__ kl_sum, const double*
   out[0] = (float)(klw * kl + recw * rec); out[1] = (float)kl; out[2] = (float)rec; out[3] = (float)M[0];
 }
 
+template <typename TA> __device__ __forceinline__ void load8(const TA* p, float (&v)[8]);
+template <> __device__ __forceinline__ void load8<float>(const float* p, float (&v)[8]) {
+  const float4 a = reinterpret_cast<const float4*>(p)[0], b = reinterpret_cast<const float4*>(p)[1];
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+template <> __device__ __forceinline__ void load8<__nv_bfloat16>(const __nv_bfloat16* p, float (&v)[8]) {
+  const uint4 a = *reinterpret_cast<const uint4*>(p);
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&a);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { const float2 f = __bfloat1622float2(h[k]); v[2 * k] = f.x; v[2 * k + 1] = f.y; }
+}
+template <typename TA> __device__ __forceinline__ void store8(TA* p, const float (&v)[8]);
+template <> __device__ __forceinline__ void store8<float>(float* p, const float (&v)[8]) {
+  reinterpret_cast<float4*>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
+  reinterpret_cast<float4*>(p)[1] = make_float4(v[4], v[5], v[6], v[7]);
+}
+template <> __device__ __forceinline__ void store8<__nv_bfloat16>(__nv_bfloat16* p, const float (&v)[8]) {
+  __nv_bfloat162 o[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) o[k] = __floats2bfloat162_rn(v[2 * k], v[2 * k + 1]);
+  *reinterpret_cast<uint4*>(p) = *reinterpret_cast<const uint4*>(o);
+}
 // counter-based uniform in (0,1): the same generator the sampler uses (restated in oracle/moses_oracle.u01_hash)
 __device__ __forceinline__ float u01_hash(unsigned long long seed, unsigned int b, unsigned int i);
 // dropout between decoder layers: element (t, b, j) of layer l is kept iff u01(seed + l, t*B + b, j) >= p.
 // mode 0: out = keep ? x / (1 - p) : 0 (forward copy);  mode 1: x *= keep / (1 - p) in place (backward)
 template <typename TA>
 __global__ void dropout_kernel(const TA* x, TA* out /* may alias x */, unsigned long long seed, float p, int B, int Bp,
-                               int H, int T) {
-  const long long total = (long long)T * Bp * H;
+                               int H, int T, int rb) {
+  // One thread = 8 consecutive hidden units of one (t, b) row (one 16-byte piece in bf16); blockIdx.y = t.
+  // rb: x / out use the row-blocked layout [row/32][H/8][32][8] inside each time slab (dX of the persistent BPTT sweep).
+  const int t = blockIdx.y;
+  const int H8 = H >> 3;
+  const unsigned pieces = (unsigned)Bp * (unsigned)H8;
   const float sc = 1.0f / (1.0f - p);
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int j = (int)(i % H);
-    const long long rb = i / H;
-    const int b = (int)(rb % Bp), t = (int)(rb / Bp);
-    float v = 0.f;
-    if (b < B && u01_hash(seed, (unsigned)(t * B + b), (unsigned)j) >= p) v = to_f32<TA>(x[i]) * sc;
-    out[i] = from_f32<TA>(v);
+  const TA* xs = x + (size_t)t * Bp * H;
+  TA* os = out + (size_t)t * Bp * H;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < pieces; i += gridDim.x * blockDim.x) {
+    int b, cg;
+    if (rb) { const unsigned q = i >> 5; cg = (int)(q % (unsigned)H8); b = (int)(q / (unsigned)H8) * 32 + (int)(i & 31u); }
+    else { cg = (int)(i % (unsigned)H8); b = (int)(i / (unsigned)H8); }
+    float v[8];
+    load8<TA>(xs + (size_t)i * 8, v);
+    // u01_hash(seed, t*B + b, j): the 64-bit counter advances by the golden-ratio constant from one unit to the next
+    unsigned long long c = seed + 0x9E3779B97F4A7C15ull * ((unsigned long long)(unsigned)(t * B + b) * 1000003ull + (unsigned)(cg * 8) + 1);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      unsigned long long h = c;
+      h ^= h >> 30; h *= 0xBF58476D1CE4E5B9ull; h ^= h >> 27; h *= 0x94D049BB133111EBull; h ^= h >> 31;
+      // (float)((h >> 40) + 0.5): the 24-bit integer is exact in fp32 and the single rounding of n + 0.5 is the same
+      const float u = __fadd_rn(__uint2float_rn((unsigned)(h >> 40)), 0.5f) * (1.0f / 16777216.0f);
+      v[k] = (b < B && u >= p) ? v[k] * sc : 0.f;
+      c += 0x9E3779B97F4A7C15ull;
+    }
+    store8<TA>(os + (size_t)i * 8, v);
   }
+}
+template <typename TA>
+int dropout_launch(cudaStream_t st, const TA* x, TA* out, unsigned long long seed, float p, int B, int Bp, int H, int T, int rb = 0) {
+  const unsigned pieces = (unsigned)Bp * (unsigned)(H / 8);
+  const long long gx = ceil_div64((long long)pieces, 256);
+  dim3 grid((unsigned)(gx < 148 * 8 ? gx : 148 * 8), (unsigned)T);
+  dropout_kernel<TA><<<grid, 256, 0, st>>>(x, out, seed, p, B, Bp, H, T, rb);
+  KCHECK();
+  return MVAE_OK;
 }
 template <typename TA>
 __global__ void final_state_kernel(const TA* __restrict__ hsA, const float* __restrict__ h32, long long n, float* __restrict__ out) {
@@ -376,6 +432,64 @@ __global__ void cell_weights_kernel(const float* __restrict__ wih, const float* 
       bias[n] = b;
     }
   }
+}
+// Decoder recurrences on the persistent kernels of gru_rec2.cu (forward pair kernel + K-split BPTT sweep, one launch per
+// layer and direction instead of one GEMM per step); bf16 mode, hidden size 256 or 512.  MVAE_MOSES_REC=0 keeps the
+// per-step engine (the cross-check).
+bool persistent_decoder(const MDims& d) {
+  const char* e = getenv("MVAE_MOSES_REC");
+  if (e && atoi(e) == 0) return false;
+  return d.bf16 && (d.Hd == 256 || d.Hd == 512) && d.Bp % 256 == 0;
+}
+bool persistent_encoder(const MDims& d) {
+  const char* e = getenv("MVAE_MOSES_REC");
+  if (e && atoi(e) == 0) return false;
+  return d.bf16 && (d.Hq == 256 || d.Hq == 512) && d.Bp % 256 == 0;
+}
+// W_hh^T for the BPTT sweep: dst[j][g*H + i] = W_hh[g*H + i][j]
+__global__ void whh_transpose_kernel(const float* __restrict__ src, int H, __nv_bfloat16* __restrict__ dst) {
+  const long long total = 3ll * H * H;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(idx % (3 * H)), j = (int)(idx / (3 * H));
+    dst[idx] = __float2bfloat16_rn(src[(long long)k * H + j]);
+  }
+}
+__global__ void combine_gate_bias_kernel(const float* __restrict__ bih, const float* __restrict__ bhh, float* __restrict__ out, int H) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < 3 * H) out[i] = (bih ? bih[i] : 0.f) + (i < 2 * H ? bhh[i] : 0.f);
+}
+// per-molecule part of the decoder's layer-0 projection in the row-blocked layout [row/32][W/8][32][8] the persistent
+// kernel's epilogue reads (time-invariant: gi_tstride 0): out[b][c] = src[b][c] + brz[c]; pad rows carry brz only
+__global__ void rows_to_rb_kernel(const float* __restrict__ src, const float* __restrict__ brz, int B, int Bp, int W,
+                                  __nv_bfloat16* __restrict__ out) {
+  const long long total = (long long)Bp * W;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % W), b = (int)(i / W);
+    const long long o = ((long long)(b >> 5) * (W / 8) + (c >> 3)) * 256 + (b & 31) * 8 + (c & 7);
+    out[o] = __float2bfloat16_rn((b < B ? src[i] : 0.f) + brz[c]);
+  }
+}
+// table rows + (b_hr, b_hz, 0): what the persistent kernel stages into shared memory
+__global__ void table_add_bias_kernel(const float* __restrict__ tbl, const float* __restrict__ brz, int V, int W, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < V * W) out[i] = tbl[i] + (brz ? brz[i % W] : 0.f);
+}
+// tokT[t][b] = ids[b][t] (token 0 for pad rows)
+__global__ void transpose_ids_kernel(const uint8_t* __restrict__ ids, int ids_ld, int B, int Bp, int T, uint8_t* __restrict__ out) {
+  const long long total = (long long)T * Bp;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(i % Bp), t = (int)(i / Bp);
+    out[i] = b < B ? ids[(long long)b * ids_ld + t] : (uint8_t)0;
+  }
+}
+// dX_enc (row-blocked [row/32][H/8][32][8] per slab) [L_b - 1][b][:] = dh_enc[b][:]; dX zeroed beforehand
+__global__ void scatter_final_grad_rb_kernel(const float* __restrict__ dh, int dh_ld, const int* __restrict__ lens, int B, int Bp,
+                                             int H, __nv_bfloat16* __restrict__ dX) {
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= (long long)B * H) return;
+  const int b = (int)(idx / H), j = (int)(idx - (long long)b * H);
+  const long long o = (long long)(lens[b] - 1) * Bp * H + ((long long)(b >> 5) * (H / 8) + (j >> 3)) * 256 + (b & 31) * 8 + (j & 7);
+  dX[o] = __float2bfloat16_rn(dh[(long long)b * dh_ld + j]);
 }
 bool varlen_gemm_enabled() {
   const char* e = getenv("MVAE_VARLEN_GEMM");
@@ -507,10 +621,35 @@ int step_t(const MDims& d, const MWS& w, const float* const* P, float* const* G,
 
   // ---- encoder: table look-up projection, GRU, final state, MLP heads, reparametrise + KL
   RC(sg(st, P[ix.emb()], V, 1, P[ix.e_wih(0)], 1, V, w.TBLe, 3 * Hq, V, 3 * Hq, V, P[ix.e_bih(0)], simt::ACT_NONE, 0));
-  gather_rows_kernel<TA><<<grid_for((long long)TB * 3 * Hq), 256, 0, st>>>(w.TBLe, 3 * Hq, ids, T, nullptr, B, Bp, T, (TA*)w.gi); KCHECK();
   RC(memset_async(w.hlast, (size_t)Bp * Hq * 4, st));
-  RC(gru_fwd<TA>(d, w, st, (const TA*)w.gi, (const TA*)w.Whh_enc, w.bhh_enc, (TA*)w.hs_enc, (TA*)w.sv_enc, Hq, nullptr, lens, w.hlast,
-                 false, nullptr, nullptr, nullptr, act));
+  const bool prec_enc = sizeof(TA) == 2 && persistent_encoder(d);
+  const bool prec = sizeof(TA) == 2 && persistent_decoder(d);
+  if (prec_enc || prec) {
+    transpose_ids_kernel<<<grid_for((long long)TB), 256, 0, st>>>(ids, T, B, Bp, T, w.tokT); KCHECK();
+  }
+  bool enc_swept = false;
+  if constexpr (sizeof(TA) == 2) {
+    if (prec_enc) {
+      // forward direction of the encoder GRU as one persistent launch: x_t W_ih^T + b_ih is a row of the V x 3Hq table
+      // (x_emb . W_ih^T), looked up by token inside the kernel; each row's state after its last token goes to hlast
+      combine_gate_bias_kernel<<<ceil_div(3 * Hq, 256), 256, 0, st>>>(nullptr, w.bhh_enc, w.bcomb[0], Hq); KCHECK();
+      table_add_bias_kernel<<<ceil_div(V * 3 * Hq, 256), 256, 0, st>>>(w.TBLe, w.bcomb[0], V, 3 * Hq, w.tbl_comb); KCHECK();
+      RC(memset_async(w.hs_enc, (size_t)Bp * Hq * sizeof(TA), st));
+      mvae_gru_rec_args ra{};
+      ra.backward = 0; ra.variant = 32; ra.Bp = Bp; ra.Hp = Hq; ra.T = T;
+      ra.W = (const __nv_bfloat16*)w.Whh_enc; ra.gi = nullptr; ra.gi_tstride = 0; ra.bhh = w.bhh_enc + 2 * Hq;
+      ra.hs = (__nv_bfloat16*)w.hs_enc; ra.sv = (__nv_bfloat16*)w.sv_enc; ra.counters = w.counters; ra.err_flag = w.err_flag;
+      ra.ones_col = -1; ra.tbl = w.tbl_comb; ra.tok = w.tokT; ra.V = V; ra.lens = lens; ra.hlast = w.hlast; ra.nrows = B;
+      mvae_count_launches(2);
+      RC(mvae_gru_rec2_launch(&ra, 1, st));
+      enc_swept = true;
+    }
+  }
+  if (!enc_swept) {
+    gather_rows_kernel<TA><<<grid_for((long long)TB * 3 * Hq), 256, 0, st>>>(w.TBLe, 3 * Hq, ids, T, nullptr, B, Bp, T, (TA*)w.gi); KCHECK();
+    RC(gru_fwd<TA>(d, w, st, (const TA*)w.gi, (const TA*)w.Whh_enc, w.bhh_enc, (TA*)w.hs_enc, (TA*)w.sv_enc, Hq, nullptr, lens, w.hlast,
+                   false, nullptr, nullptr, nullptr, act));
+  }
   copy_rows_kernel<<<grid_for((long long)B * Hq), 256, 0, st>>>(w.hlast, Hq, B, Hq, w.hcat, Hin); KCHECK();
   if (d.bidir) {
     // reverse direction (mosesfile.py:21-28,112-116): same engine over the time-reversed token stream, padding first
@@ -536,17 +675,46 @@ int step_t(const MDims& d, const MWS& w, const float* const* P, float* const* G,
   RC(sg(st, w.z, Z, 1, P[ix.latw()], 1, Z, w.h0, Hd, B, Hd, Z, P[ix.latb()], simt::ACT_NONE, 0));
   RC(sg(st, P[ix.emb()], V, 1, P[ix.wih(0)], 1, IN0, w.TBLd, 3 * Hd, V, 3 * Hd, V, nullptr, simt::ACT_NONE, 0));
   RC(sg(st, w.z, Z, 1, P[ix.wih(0)] + V, 1, IN0, w.zproj, 3 * Hd, B, 3 * Hd, Z, P[ix.bih(0)], simt::ACT_NONE, 0));
-  gather_rows_kernel<TA><<<grid_for((long long)TB * 3 * Hd), 256, 0, st>>>(w.TBLd, 3 * Hd, ids, T, w.zproj, B, Bp, T, (TA*)w.gi); KCHECK();
+  if (prec) {
+    // layer 0: the token part of the projection is looked up inside the kernel (table in shared memory), the per-molecule
+    // z part (+ b_ih + (b_hr, b_hz, 0)) is one time-invariant row-blocked slab
+    combine_gate_bias_kernel<<<ceil_div(3 * Hd, 256), 256, 0, st>>>(nullptr, w.bhh[0], w.bcomb[0], Hd); KCHECK();
+    rows_to_rb_kernel<<<grid_for((long long)Bp * 3 * Hd), 256, 0, st>>>(w.zproj, w.bcomb[0], B, Bp, 3 * Hd, (__nv_bfloat16*)w.zproj_rb); KCHECK();
+  } else {
+    gather_rows_kernel<TA><<<grid_for((long long)TB * 3 * Hd), 256, 0, st>>>(w.TBLd, 3 * Hd, ids, T, w.zproj, B, Bp, T, (TA*)w.gi); KCHECK();
+  }
   const bool drop = d.drop > 0.f;
   for (int l = 0; l < L; ++l) {
     if (l >= 1) {
       const TA* X = (const TA*)w.hs[l - 1] + (size_t)Bp * Hd;
       if (drop) {   // nn.GRU(dropout=p) in train mode: dropout on the outputs of every layer but the last (mosesvae.py:78)
-        dropout_kernel<TA><<<grid_for((long long)TB * Hd), 256, 0, st>>>(X, (TA*)w.hdrop, (unsigned long long)d.drop_seed + (l - 1), d.drop,
-                                                                        B, Bp, Hd, T); KCHECK();
+        RC(dropout_launch<TA>(st, X, (TA*)w.hdrop, (unsigned long long)d.drop_seed + (l - 1), d.drop, B, Bp, Hd, T));
         X = (const TA*)w.hdrop;
       }
-      RC(gemm<TA>(w.err_flag, st, X, Hd, false, (const TA*)w.Wih[l], Hd, true, w.gi, 3 * Hd, true, TB, 3 * Hd, Hd, w.bih[l], false, 1, 0, VLM));
+      if (prec) {
+        // every row of every slab is written (no tile skipping): the persistent sweep runs all rows through all T steps, and
+        // what it computes past a sequence's end must stay finite (it meets zero gradients in the K = T*B wgrad GEMMs)
+        combine_gate_bias_kernel<<<ceil_div(3 * Hd, 256), 256, 0, st>>>(w.bih[l], w.bhh[l], w.bcomb[l], Hd); KCHECK();
+        RC(gemm<TA>(w.err_flag, st, X, Hd, false, (const TA*)w.Wih[l], Hd, true, w.gi, 3 * Hd, true, TB, 3 * Hd, Hd, w.bcomb[l], false, 1, 0,
+                    nullptr, true));
+      } else {
+        RC(gemm<TA>(w.err_flag, st, X, Hd, false, (const TA*)w.Wih[l], Hd, true, w.gi, 3 * Hd, true, TB, 3 * Hd, Hd, w.bih[l], false, 1, 0, VLM));
+      }
+    }
+    if constexpr (sizeof(TA) == 2) {
+      if (prec) {
+        // one launch = all T steps of this layer: h0 = decoder_lat(z) (mosesvae.py:180-181), saved gates in the fragment layout
+        init_h0_kernel<TA><<<ceil_div(Bp * Hd, 256), 256, 0, st>>>(w.h0, B, Bp, Hd, (TA*)w.hs[l], nullptr); KCHECK();
+        mvae_gru_rec_args ra{};
+        ra.backward = 0; ra.variant = 32; ra.Bp = Bp; ra.Hp = Hd; ra.T = T;
+        ra.W = (const __nv_bfloat16*)w.Whh[l]; ra.gi = (const __nv_bfloat16*)w.gi; ra.gi_tstride = (long long)Bp * 3 * Hd;
+        if (l == 0) { ra.gi = (const __nv_bfloat16*)w.zproj_rb; ra.gi_tstride = 0; ra.tbl = w.TBLd; ra.tok = w.tokT; ra.V = V; }
+        ra.bhh = w.bhh[l] + 2 * Hd; ra.hs = (__nv_bfloat16*)w.hs[l]; ra.sv = (__nv_bfloat16*)w.sv[l]; ra.counters = w.counters;
+        ra.err_flag = w.err_flag; ra.ones_col = -1; ra.h0 = w.h0;
+        mvae_count_launches(2);
+        RC(mvae_gru_rec2_launch(&ra, 1, st));
+        continue;
+      }
     }
     if (d.bf16) {
       cell_weights_kernel<<<grid_for(3ll * Hd * Hd), 256, 0, st>>>(nullptr, P[ix.whh(l)], nullptr, P[ix.bhh(l)], Hd, 3,
@@ -570,7 +738,9 @@ int step_t(const MDims& d, const MWS& w, const float* const* P, float* const* G,
   const int wsplits = d.bf16 ? 12 : 64;
   onehot_rows_kernel<TA><<<grid_for((long long)TB * CP), 256, 0, st>>>(ids, T, B, Bp, T, CP, (TA*)w.OH); KCHECK();
   // head
-  RC(gemm<TA>(w.err_flag, st, dlog, CP, false, (const TA*)w.Wfc, Hd, false, w.dX, Hd, true, TB, Hd, CP, nullptr, false, 1, 0, VLM));
+  // persistent BPTT: dX in the row-blocked layout, every row written (zeros past a sequence's end, where dlogits is zero)
+  RC(gemm<TA>(w.err_flag, st, dlog, CP, false, (const TA*)w.Wfc, Hd, false, w.dX, Hd, true, TB, Hd, CP, nullptr, false, 1, 0,
+              prec ? nullptr : VLM, prec));
   RC(memset_async(w.dWfc_p, (size_t)CP * Hd * 4, st));
   RC(gemm<TA>(w.err_flag, st, dlog, CP, true, (const TA*)w.hs[L - 1] + (size_t)Bp * Hd, Hd, false, w.dWfc_p, Hd, false, CP, Hd, TB,
               nullptr, true, d.bf16 ? 148 : 64, 256, VLK));
@@ -583,7 +753,26 @@ int step_t(const MDims& d, const MWS& w, const float* const* P, float* const* G,
   for (int l = L - 1; l >= 0; --l) {
     const TA* hs = (const TA*)w.hs[l];
     TA* dG = (TA*)w.dG;
-    RC(gru_bwd<TA>(d, w, st, (const TA*)w.Whh[l], hs, (const TA*)w.sv[l], (const TA*)w.dX, dG, Hd, w.dh0, nullptr, 0, act));
+    bool swept = false;
+    if constexpr (sizeof(TA) == 2) {
+      if (prec) {
+        whh_transpose_kernel<<<grid_for(3ll * Hd * Hd), 256, 0, st>>>(P[ix.whh(l)], Hd, (__nv_bfloat16*)w.WhhT[l]); KCHECK();
+        mvae_gru_rec_args ra{};
+        ra.backward = 1; ra.variant = 32; ra.Bp = Bp; ra.Hp = Hd; ra.T = T;
+        ra.W = (const __nv_bfloat16*)w.WhhT[l]; ra.hs = (__nv_bfloat16*)w.hs[l]; ra.sv = (__nv_bfloat16*)w.sv[l];
+        ra.dX = (const __nv_bfloat16*)w.dX; ra.dG = (__nv_bfloat16*)dG; ra.counters = w.counters; ra.err_flag = w.err_flag;
+        ra.carry_out = w.dh_carry;
+        mvae_count_launches(2);
+        RC(mvae_gru_rec2_launch(&ra, 0, st));
+        // dL/dh0 of this layer = dh_0 * z_0 (carry_out) + dgh_0 * W_hh
+        RC(gemm<TA>(w.err_flag, st, dG + Hd, 4 * Hd, false, (const TA*)w.Whh[l], Hd, false, w.dh_carry, Hd, false, Bp, Hd, 3 * Hd, nullptr,
+                    true, 1));
+        add_inplace_kernel<<<grid_for((long long)Bp * Hd), 256, 0, st>>>(w.dh0, w.dh_carry, (long long)Bp * Hd); KCHECK();
+        swept = true;
+      }
+    }
+    if (!swept)
+      RC(gru_bwd<TA>(d, w, st, (const TA*)w.Whh[l], hs, (const TA*)w.sv[l], (const TA*)w.dX, dG, Hd, w.dh0, nullptr, 0, act));
     RC(memset_async(w.dW_p, (size_t)3 * Hd * Hd * 4, st));
     RC(gemm<TA>(w.err_flag, st, dG + Hd, 4 * Hd, true, hs, Hd, false, w.dW_p, Hd, false, 3 * Hd, Hd, TB, nullptr, true, wsplits, 256, VLK));
     simt::unpad_gate_matrix_kernel<<<grid_for(3ll * Hd * Hd), 256, 0, st>>>(w.dW_p, Hd, Hd, G[ix.whh(l)], Hd, Hd, 0, 1, 2); KCHECK();
@@ -593,17 +782,16 @@ int step_t(const MDims& d, const MWS& w, const float* const* P, float* const* G,
     if (l >= 1) {
       const TA* X = (const TA*)w.hs[l - 1] + (size_t)Bp * Hd;
       if (drop) {   // regenerate the dropped input of this layer (same counter-based mask)
-        dropout_kernel<TA><<<grid_for((long long)TB * Hd), 256, 0, st>>>(X, (TA*)w.hdrop, (unsigned long long)d.drop_seed + (l - 1), d.drop,
-                                                                        B, Bp, Hd, T); KCHECK();
+        RC(dropout_launch<TA>(st, X, (TA*)w.hdrop, (unsigned long long)d.drop_seed + (l - 1), d.drop, B, Bp, Hd, T));
         X = (const TA*)w.hdrop;
       }
       RC(memset_async(w.dW_p, (size_t)3 * Hd * Hd * 4, st));
       RC(gemm<TA>(w.err_flag, st, dG, 4 * Hd, true, X, Hd, false, w.dW_p, Hd, false, 3 * Hd, Hd, TB, nullptr, true, wsplits, 256, VLK));
       simt::unpad_gate_matrix_kernel<<<grid_for(3ll * Hd * Hd), 256, 0, st>>>(w.dW_p, Hd, Hd, G[ix.wih(l)], Hd, Hd, 2, 0, 1); KCHECK();
-      RC(gemm<TA>(w.err_flag, st, dG, 4 * Hd, false, (const TA*)w.Wih_nrz[l], Hd, false, w.dX, Hd, true, TB, Hd, 3 * Hd, nullptr, false, 1, 0, VLM));
+      RC(gemm<TA>(w.err_flag, st, dG, 4 * Hd, false, (const TA*)w.Wih_nrz[l], Hd, false, w.dX, Hd, true, TB, Hd, 3 * Hd, nullptr, false, 1, 0,
+                  prec ? nullptr : VLM, prec));
       if (drop) {   // gradient wrt the undropped outputs of layer l-1
-        dropout_kernel<TA><<<grid_for((long long)TB * Hd), 256, 0, st>>>((const TA*)w.dX, (TA*)w.dX, (unsigned long long)d.drop_seed + (l - 1),
-                                                                        d.drop, B, Bp, Hd, T); KCHECK();
+        RC(dropout_launch<TA>(st, (const TA*)w.dX, (TA*)w.dX, (unsigned long long)d.drop_seed + (l - 1), d.drop, B, Bp, Hd, T, prec ? 1 : 0));
       }
     } else {
       // layer 0: table gradient (tensor-core GEMM onehot^T * dgi) and the per-molecule z part (time sum)
@@ -661,7 +849,23 @@ int step_t(const MDims& d, const MWS& w, const float* const* P, float* const* G,
     const TA* hs = (const TA*)(rev ? w.hs_encr : w.hs_enc);
     const TA* sv = (const TA*)(rev ? w.sv_encr : w.sv_enc);
     RC(memset_async(dXe, (size_t)TB * Hq * sizeof(TA), st));
-    if (!rev) {
+    bool swept = false;
+    if constexpr (sizeof(TA) == 2) {
+      if (!rev && prec_enc) {
+        scatter_final_grad_rb_kernel<<<(unsigned)ceil_div64((long long)B * Hq, 256), 256, 0, st>>>(w.dhenc, Hin, lens, B, Bp, Hq,
+                                                                                                 (__nv_bfloat16*)dXe); KCHECK();
+        whh_transpose_kernel<<<grid_for(3ll * Hq * Hq), 256, 0, st>>>(P[ix.e_whh(0)], Hq, (__nv_bfloat16*)w.WhhT_enc); KCHECK();
+        mvae_gru_rec_args ra{};
+        ra.backward = 1; ra.variant = 32; ra.Bp = Bp; ra.Hp = Hq; ra.T = T;
+        ra.W = (const __nv_bfloat16*)w.WhhT_enc; ra.hs = (__nv_bfloat16*)w.hs_enc; ra.sv = (__nv_bfloat16*)w.sv_enc;
+        ra.dX = (const __nv_bfloat16*)dXe; ra.dG = (__nv_bfloat16*)dG; ra.counters = w.counters; ra.err_flag = w.err_flag;
+        mvae_count_launches(2);
+        RC(mvae_gru_rec2_launch(&ra, 0, st));
+        swept = true;
+      }
+    }
+    if (swept) {
+    } else if (!rev) {
       scatter_final_grad_kernel<TA><<<(unsigned)ceil_div64((long long)B * Hq, 256), 256, 0, st>>>(w.dhenc, Hin, lens, B, Bp, Hq, dXe); KCHECK();
       RC(gru_bwd<TA>(d, w, st, Whh, hs, sv, dXe, dG, Hq, nullptr, nullptr, 0, act));
     } else {
