@@ -31,8 +31,13 @@ constexpr int NTILES = 2;                 // pair-tiles (256 rows) per pair
 constexpr int RU = 64;                    // hidden units per pair
 constexpr int A_STAGE = 128 * 64 * 2;     // this CTA's 128 rows x 64 k, bf16
 constexpr int EPI_WARPS = 16;
-constexpr int THREADS = (3 + EPI_WARPS) * 32;   // + producer, MMA issuer, publisher
-constexpr int PUB_WARP = 2 + EPI_WARPS;
+// warps 0..3 = control warpgroup (TMA producer, MMA issuer, publisher, one idle), warps 4..19 = epilogue.  The control
+// warpgroup hands most of its registers to the epilogue warps (setmaxnreg), whose gate math otherwise spills at the
+// 96 registers a 640-thread CTA starts with.
+constexpr int CTRL_WARPS = 4;
+constexpr int THREADS = (CTRL_WARPS + EPI_WARPS) * 32;
+constexpr int PUB_WARP = 2;
+constexpr int CTRL_REGS = 32, EPI_REGS = 112;   // (96 - 24) * 128 released >= (112 - 96) * 512 claimed
 constexpr int EPI_BAR = 1;
 
 struct Params2 {
@@ -168,7 +173,9 @@ __device__ __forceinline__ void commit2_mc(uint64_t* bar, uint16_t mask) {
       : "memory");
 }
 
-template <bool BWD, bool FAST, int CL, bool KS>
+// IN (forward only): where the input projection of a step comes from -- 0: the gi tensor (GEMM output); 1: gi (time-
+// invariant per-row part) + a token table in shared memory; 2: the token table only, plus the final-state capture (lens / hlast)
+template <bool BWD, bool FAST, int CL, bool KS, int IN = 0>
 __global__ void __launch_bounds__(THREADS, 1)
 gru_rec2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmA, const Params2 p) {
   static_assert(!KS || (BWD && CL == 2), "K-split is a BPTT variant of the pair kernel");
@@ -192,7 +199,7 @@ gru_rec2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
   const int nst = p.nst;                                        // stages in use (NST unless a token table needs the room)
   float* xbuf = reinterpret_cast<float*>(sA + nst * A_STAGE);   // KS: [64 units][128 rows], reused by consecutive tile-steps
   __nv_bfloat16* sTbl = reinterpret_cast<__nv_bfloat16*>(sA + nst * A_STAGE + (KS ? XBUF : 0));   // fwd: [V][3][64]
-  const int tbl_bytes = (!BWD && p.tbl) ? ((p.V * 3 * RU * 2 + 1023) & ~1023) : 0;
+  const int tbl_bytes = (!BWD && IN > 0) ? ((p.V * 3 * RU * 2 + 1023) & ~1023) : 0;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sA + nst * A_STAGE + (KS ? XBUF : 0) + tbl_bytes);
   uint64_t* full_bar = bars;                         // [NST] own operand stage landed (tx)
   uint64_t* empty_bar = bars + NST;                  // [NST] all pairs that share the stage consumed it
@@ -246,7 +253,7 @@ gru_rec2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
     ptx::fence_mbar_init();
   }
   if (!BWD) for (int i = threadIdx.x; i < RU; i += THREADS) sBias[i] = p.bhn[u0 + i];
-  if (!BWD && p.tbl)
+  if (!BWD && IN > 0)
     for (int i = threadIdx.x; i < p.V * 3 * RU; i += THREADS) {
       const int v = i / (3 * RU), g = (i / RU) % 3, u = i % RU;
       sTbl[i] = __float2bfloat16_rn(p.tbl[(size_t)v * 3 * p.Hp + g * p.Hp + u0 + u]);
@@ -258,6 +265,8 @@ gru_rec2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
 
+  if (warp < CTRL_WARPS) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(CTRL_REGS));
   if (warp == 0) {
     // ===================== TMA producer (every CTA) =====================
     if (lane == 0) {
@@ -285,7 +294,8 @@ gru_rec2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
         }
       }
       int s = 0; uint32_t ph = 0;
-      for (int step = (!BWD && p.h0) ? 0 : 1; step < p.T; ++step) {
+      // forward: step 0 contracts over slab 0 (the initial state; zeros when there is none) like every other step
+      for (int step = BWD ? 1 : 0; step < p.T; ++step) {
         int slab = BWD ? (p.T - step) : step;
         if (p.debug & 2) slab = (slab + pair * 5) % p.T;
         if (p.debug & 16) slab = 0;   // timing experiment: operand that nobody writes during the sweep
@@ -347,7 +357,7 @@ gru_rec2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
         int s = 0; uint32_t ph = 0;
         for (int step = 0; step < p.T; ++step) {
           for (int i = 0; i < ntiles; ++i) {
-            if (step > 0 || (!BWD && p.h0)) {
+            if (step > 0 || !BWD) {
               if (step > 0 && !wait_bar(&tempty_bar[i], (uint32_t)((step - 1) & 1), p.err_flag)) goto done;
               ptx::tc_fence_after();
               const uint32_t d_tmem = tmem_base + i * NB;
@@ -408,13 +418,34 @@ gru_rec2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
           if (tr) p.trace[((size_t)step * NTILES + i) * 12 + 7] = gtime();
         }
     }
+  }
   } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(EPI_REGS));
     // ===================== epilogue warps (every CTA: own 128 rows x 64 units) =====================
     const int q = warp & 3;
-    const int part = (warp - 2) >> 2;          // 0..3 -> 16 units each
+    const int part = (warp - CTRL_WARPS) >> 2;   // 0..3 -> 16 units each
     const int uc = part * 16;
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     uint32_t fph = 0;
+    if constexpr (!BWD) {
+      // fp32 master copy of the initial state (zeros without h0) into this thread's TMEM columns of every tile
+      for (int i = 0; i < ntiles; ++i) {
+        const long long row = (long long)(tile0 + i) * 256 + parity * 128 + q * 32 + lane;
+        float h[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) h[k] = 0.f;
+        if (p.h0) {
+          const float4* h0p = reinterpret_cast<const float4*>(p.h0 + row * p.Hp + u0 + uc);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float4 v = __ldg(h0p + k);
+            h[4 * k] = v.x; h[4 * k + 1] = v.y; h[4 * k + 2] = v.z; h[4 * k + 3] = v.w;
+          }
+        }
+        tmem_st_32x16(tmem_base + lane_off + MASTER0 + i * RU + uc, h);
+      }
+      tmem_st_wait();
+    }
     for (int step = 0; step < p.T; ++step) {
       const int t = BWD ? (p.T - 1 - step) : step;
       for (int i = 0; i < ntiles; ++i) {
@@ -438,18 +469,13 @@ gru_rec2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
 #pragma unroll
             for (int k = 0; k < 8; ++k) pre[a].v[k] = 0x3c003c00u;
         } else if (!BWD) {
-          if (p.gi) {
+          if constexpr (IN != 2) {
             const __nv_bfloat16* g = p.gi + (long long)t * p.gi_tstride +
                                      (rblk * (3 * p.Hp / 8) + ((u0 + uc) >> 3)) * 256 + lane * 8;
 #pragma unroll
             for (int gate = 0; gate < 3; ++gate) pre[gate] = ldg2x128(g + (long long)gate * (p.Hp / 8) * 256);
-          } else {
-#pragma unroll
-            for (int gate = 0; gate < 3; ++gate)
-#pragma unroll
-              for (int k = 0; k < 8; ++k) pre[gate].v[k] = 0u;
           }
-          if (p.tok) tokv = p.tok[(long long)t * p.Bp + row];
+          if constexpr (IN > 0) tokv = p.tok[(long long)t * p.Bp + row];
         } else {
 #pragma unroll
           for (int blk = 0; blk < 4; ++blk) pre[blk] = ldg2x128(svp + blk * 2048);
@@ -458,55 +484,44 @@ gru_rec2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
         }
         (void)wait_bar(&tfull_bar[i], fph, p.err_flag);   // on failure keep walking: barriers below must be reached
         ptx::tc_fence_after();
-        const bool tr = p.trace && blockIdx.x == 0 && blockIdx.y == 0 && warp == 2 && lane == 0;
+        const bool tr = p.trace && blockIdx.x == 0 && blockIdx.y == 0 && warp == CTRL_WARPS && lane == 0;
         if (tr) p.trace[((size_t)step * NTILES + i) * 12 + 4] = gtime();
         const uint32_t master_addr = tmem_base + lane_off + MASTER0 + i * RU + uc;
         if (!BWD) {
           uint32_t ar[16], az[16], an[16], hm[16];
-          if (step > 0) {
+          {
             const uint32_t acc = tmem_base + lane_off + i * NB + uc;
             ptx::tmem_ld_32x16(acc, ar);
             ptx::tmem_ld_32x16(acc + RU, az);
             ptx::tmem_ld_32x16(acc + 2 * RU, an);
             ptx::tmem_ld_32x16(master_addr, hm);
             ptx::tmem_ld_wait();
-          } else if (p.h0) {
-            // non-zero initial state: the step-0 MMAs contracted over hs slab 0 (= bf16 h0), the fp32 master starts from h0
-            const uint32_t acc = tmem_base + lane_off + i * NB + uc;
-            ptx::tmem_ld_32x16(acc, ar);
-            ptx::tmem_ld_32x16(acc + RU, az);
-            ptx::tmem_ld_32x16(acc + 2 * RU, an);
-            const float4* h0p = reinterpret_cast<const float4*>(p.h0 + row * p.Hp + u0 + uc);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const float4 v = __ldg(h0p + k);
-              hm[4 * k] = __float_as_uint(v.x); hm[4 * k + 1] = __float_as_uint(v.y);
-              hm[4 * k + 2] = __float_as_uint(v.z); hm[4 * k + 3] = __float_as_uint(v.w);
-            }
-            ptx::tmem_ld_wait();
-          } else {
-#pragma unroll
-            for (int k = 0; k < 16; ++k) { ar[k] = 0u; az[k] = 0u; an[k] = 0u; hm[k] = 0u; }
           }
           const bool tr2 = tr && (p.debug & 64);
           if (tr2) p.trace[((size_t)step * NTILES + i) * 12 + 8] = gtime();
           float gr[16], gz[16], gn[16];
-          unpack16(pre[0], gr);
-          unpack16(pre[1], gz);
-          unpack16(pre[2], gn);
-          if (p.tok) {
+          if constexpr (IN != 2) {
+            unpack16(pre[0], gr);
+            unpack16(pre[1], gz);
+            unpack16(pre[2], gn);
+          }
+          if constexpr (IN > 0) {
             // token-table part of the input projection: this row's token selects one bf16 row per gate in shared memory
             const uint4* tr = reinterpret_cast<const uint4*>(sTbl + (size_t)tokv * 3 * RU + uc);
-            float tv[16];
-            u32x8 tq;
 #pragma unroll
             for (int gate = 0; gate < 3; ++gate) {
-              const uint4 a = tr[gate * (RU / 8)], b = tr[gate * (RU / 8) + 1];
-              tq.v[0] = a.x; tq.v[1] = a.y; tq.v[2] = a.z; tq.v[3] = a.w; tq.v[4] = b.x; tq.v[5] = b.y; tq.v[6] = b.z; tq.v[7] = b.w;
-              unpack16(tq, tv);
               float* dst = gate == 0 ? gr : gate == 1 ? gz : gn;
 #pragma unroll
-              for (int k = 0; k < 16; ++k) dst[k] += tv[k];
+              for (int hf = 0; hf < 2; ++hf) {
+                const uint4 a = tr[gate * (RU / 8) + hf];
+                const uint32_t w4[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  const float lo = __uint_as_float(w4[k] << 16), hi = __uint_as_float(w4[k] & 0xFFFF0000u);
+                  if constexpr (IN == 2) { dst[hf * 8 + 2 * k] = lo; dst[hf * 8 + 2 * k + 1] = hi; }
+                  else { dst[hf * 8 + 2 * k] += lo; dst[hf * 8 + 2 * k + 1] += hi; }
+                }
+              }
             }
           }
           float h[16];
@@ -524,7 +539,7 @@ gru_rec2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
             an[k] = __float_as_uint(ghn);
           }
           if (tr2) p.trace[((size_t)step * NTILES + i) * 12 + 9] = gtime();
-          if (p.hlast && row < p.nrows && t == p.lens[row] - 1) {
+          if (IN == 2 && p.hlast && row < p.nrows && t == p.lens[row] - 1) {
             float4* hl = reinterpret_cast<float4*>(p.hlast + row * p.Hp + u0 + uc);
 #pragma unroll
             for (int k = 0; k < 4; ++k) hl[k] = make_float4(h[4 * k], h[4 * k + 1], h[4 * k + 2], h[4 * k + 3]);
@@ -564,7 +579,7 @@ gru_rec2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
               // xbuf[unit][row]: a warp store covers 32 consecutive rows of one unit (128 contiguous bytes)
               const uint32_t xloc = ptx::smem_u32(xbuf + (size_t)uc * 128 + q * 32 + lane);
               const uint32_t xrem = mapa(xloc, partner);
-              const int xw = warp - 2;                                                   // this warp's exchange slot
+              const int xw = warp - CTRL_WARPS;                                          // this warp's exchange slot
               if (ev > 0) (void)wait_bar_cluster(&xfree_bar[xw], (ev - 1) & 1u, p.err_flag);   // partner warp read exchange ev-1
 #pragma unroll
               for (int k = 0; k < 16; ++k) st_cluster_f32(xrem + (uint32_t)k * 512u, oth[k]);
@@ -664,13 +679,14 @@ int encode(CUtensorMap* map, const void* ptr, int rank, const cuuint64_t* dims, 
   return r == CUDA_SUCCESS ? MVAE_OK : MVAE_ERR_DRIVER;
 }
 
-template <bool BWD, bool FAST, int CL, bool KS = false>
+template <bool BWD, bool FAST, int CL, bool KS = false, int IN = 0>
 int launch2(const mvae_gru_rec_args& a, cudaStream_t st) {
   const int Hp = a.Hp, Bp = a.Bp, T = a.T;
   constexpr int NBH = (BWD ? (KS ? 2 * RU : RU) : 3 * RU) / 2;
   const int KC = (BWD ? 3 * Hp : Hp) / 64 / (KS ? 2 : 1);
-  const bool use_tbl = !BWD && a.tbl && a.tok;
-  if (use_tbl && (a.V < 1 || a.V > 64)) return MVAE_ERR_INVALID;
+  const bool use_tbl = !BWD && IN > 0;
+  if (use_tbl && (!a.tbl || !a.tok || a.V < 1 || a.V > 64)) return MVAE_ERR_INVALID;
+  if (!BWD && IN != 2 && !a.gi) return MVAE_ERR_INVALID;
   const size_t tbl_bytes = use_tbl ? (((size_t)a.V * 3 * RU * 2 + 1023) & ~(size_t)1023) : 0;
   int nst = KS ? 6 : STAGES;
   const size_t fixed = (size_t)KC * NBH * 128 + (KS ? 128 * RU * 4 : 0) + tbl_bytes + 1024 + 1024;
@@ -709,7 +725,7 @@ int launch2(const mvae_gru_rec_args& a, cudaStream_t st) {
   p.nst = nst;
   p.tbl = use_tbl ? a.tbl : nullptr; p.tok = use_tbl ? a.tok : nullptr; p.V = use_tbl ? a.V : 0;
   p.lens = BWD ? nullptr : a.lens; p.hlast = (BWD || !a.lens) ? nullptr : a.hlast; p.nrows = a.nrows;
-  auto kern = gru_rec2_kernel<BWD, FAST, CL, KS>;
+  auto kern = gru_rec2_kernel<BWD, FAST, CL, KS, IN>;
   static size_t attr_smem = 0;
   if (smem > attr_smem) {
     MVAE_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -754,6 +770,10 @@ int mvae_gru_rec2_launch(const mvae_gru_rec_args* a, int fast_gates, cudaStream_
   if (!a || a->Bp % 256 || (a->Hp != 256 && a->Hp != 512) || a->T < 1) return MVAE_ERR_INVALID;
   const int cl = a->variant == 38 ? 8 : a->variant == 34 ? 4 : 2;
   if (a->variant == 32 && a->backward) return launch2<true, false, 2, true>(*a, stream);
+  if (!a->backward && a->tbl) {   // token-table input projection (pair clusters, fast gates only)
+    if (cl != 2) return MVAE_ERR_UNSUPPORTED;
+    return a->gi ? launch2<false, true, 2, false, 1>(*a, stream) : launch2<false, true, 2, false, 2>(*a, stream);
+  }
 #define MVAE_DISPATCH(CLV)                                                                     \
   if (a->backward) return launch2<true, false, CLV>(*a, stream);                                \
   return fast_gates ? launch2<false, true, CLV>(*a, stream) : launch2<false, false, CLV>(*a, stream);
