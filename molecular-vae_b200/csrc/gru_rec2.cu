@@ -63,6 +63,7 @@ struct Params2 {
   int nst;                   // operand stages actually used (<= NST; the table takes the place of the others)
   // fwd, optional: state after each row's last valid step, hlast[row][:] = h_{lens[row]-1} (fp32, rows < nrows)
   const int* lens; float* hlast; int nrows;
+  int tpp;                   // row tiles per pair actually used (1 or NTILES)
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -225,8 +226,8 @@ gru_rec2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
   const int kh = KS ? (pair & 1) : 0;                 // KS: which half of K this pair contracts over
   const int koff = KS ? kh * (3 * p.Hp / 2) : 0;      // first dgh column (= first W_hh^T column) of that half
   const int U0 = KS ? (pair >> 1) * 2 * RU : u0;      // KS: first of the 128 units of the two-pair cluster
-  const int tile0 = blockIdx.y * NTILES;
-  const int ntiles = min(NTILES, p.pair_tiles - tile0);
+  const int tile0 = blockIdx.y * p.tpp;
+  const int ntiles = min(p.tpp, p.pair_tiles - tile0);
   const uint16_t mask_par = (uint16_t)((CL == 8 ? 0x55 : CL == 4 ? 0x5 : 0x1) << parity);  // same-parity CTAs
   const uint16_t mask_pair = (uint16_t)(3u << (rank & ~1u));
   const int qd = CL == 2 ? 0 : (int)(rank >> 1);      // multicast clusters: which part of the operand tile this CTA loads
@@ -427,6 +428,14 @@ gru_rec2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
     const int uc = part * 16;
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     uint32_t fph = 0;
+    int lastv[NTILES] = {-1, -1};   // IN == 2: step after which this thread's row of tile i hands its state to hlast
+    if constexpr (!BWD && IN == 2) {
+      if (p.hlast)
+        for (int i = 0; i < ntiles; ++i) {
+          const long long row = (long long)(tile0 + i) * 256 + parity * 128 + q * 32 + lane;
+          if (row < p.nrows) lastv[i] = p.lens[row] - 1;
+        }
+    }
     if constexpr (!BWD) {
       // fp32 master copy of the initial state (zeros without h0) into this thread's TMEM columns of every tile
       for (int i = 0; i < ntiles; ++i) {
@@ -539,7 +548,7 @@ gru_rec2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
             an[k] = __float_as_uint(ghn);
           }
           if (tr2) p.trace[((size_t)step * NTILES + i) * 12 + 9] = gtime();
-          if (IN == 2 && p.hlast && row < p.nrows && t == p.lens[row] - 1) {
+          if (IN == 2 && t == lastv[i]) {
             float4* hl = reinterpret_cast<float4*>(p.hlast + row * p.Hp + u0 + uc);
 #pragma unroll
             for (int k = 0; k < 4; ++k) hl[k] = make_float4(h[4 * k], h[4 * k + 1], h[4 * k + 2], h[4 * k + 3]);
@@ -551,7 +560,7 @@ gru_rec2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
           ptx::tc_fence_before();
           ptx::mbar_arrive(&epi_bar[i]);
           if (tr2) p.trace[((size_t)step * NTILES + i) * 12 + 10] = gtime();
-          if (svp && !nomem) {
+          if (svp && !nomem && !(p.debug & 1024)) {   // debug 1024: timing experiment without the saved-gate stores
             stg2x128(svp, gr);
             stg2x128(svp + 2048, gz);
             stg2x128(svp + 2 * 2048, gn);
@@ -733,7 +742,10 @@ int launch2(const mvae_gru_rec_args& a, cudaStream_t st) {
   }
   MVAE_CUDA_CHECK(cudaMemsetAsync(a.counters, 0, sizeof(unsigned int) * 2 * (Bp / 256), st));
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(Hp / 32, ceil_div(Bp / 256, NTILES), 1);
+  // one row tile per pair when every CTA is co-resident anyway (small hidden sizes): twice the SMs, half the chain per step
+  const int tpp = ((Hp / 32) * (Bp / 256) <= 148 && !(a.debug & 4096)) ? 1 : NTILES;
+  p.tpp = tpp;
+  cfg.gridDim = dim3(Hp / 32, ceil_div(Bp / 256, tpp), 1);
   cfg.blockDim = dim3(THREADS, 1, 1);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;

@@ -61,7 +61,7 @@ struct MWS {
   // concatenated weights [W_ih | W_hh] in tiles of 64 units x 4 gate blocks, fp32 master states
   void *xh[4][2]; void *Wcat[4]; float *bcat[4]; float *hm[4][2];
   void *WhhC[4]; float *bhhC[4];         // training decoder: W_hh / b_hh in the fused-cell tile order (G = 3)
-  void *hdrop;                           // [T][Bp][Hd] dropped copy of a decoder layer's outputs (input of the next layer)
+  void *hdrop[4];                        // [l]: [T][Bp][Hd] dropped copy of decoder layer l-1's outputs (input of layer l), kept for backward
   void *hs_encr, *sv_encr, *Whh_encr;   // reverse direction of a bidirectional encoder
   float *bhh_encr, *TBLer, *hlastr, *hcat, *dhcat;
   float *gh, *h32[2], *dh_carry, *logits;
@@ -103,7 +103,8 @@ void carve(const MDims& d, void* base, MWS* w) {
     w->sv[l] = c.take<uint8_t>(T * Bp * 5 * Hd * es);   // 5: the persistent kernels also save h_{t-1} (fragment layout)
   }
   w->dG = c.take<uint8_t>(T * Bp * 4 * Hd * es); w->dX = c.take<uint8_t>(T * Bp * Hd * es);
-  w->hdrop = c.take<uint8_t>(T * Bp * Hd * es);
+  for (int l = 1; l < d.L; ++l) w->hdrop[l] = d.drop > 0.f ? c.take<uint8_t>(T * Bp * Hd * es) : nullptr;
+  w->hdrop[0] = nullptr;
   for (int l = 0; l < d.L; ++l) {
     for (int k = 0; k < 2; ++k) { w->xh[l][k] = c.take<uint8_t>(Bp * 2 * Hd * 2); w->hm[l][k] = c.take<float>(Bp * Hd); }
     w->Wcat[l] = c.take<uint8_t>((size_t)4 * Hd * 2 * Hd * 2);
@@ -286,6 +287,28 @@ __global__ void dgi_time_sum_t_kernel(const TA* __restrict__ dG, int T, int Bp, 
   float s = 0.f;
   for (int t = 0; t < T; ++t) s += to_f32<TA>(p[(long long)t * Bp * 4 * H]);
   out[idx] = s;
+}
+// bf16 variant: one thread per (row, 8 consecutive columns of the (n,r,z) dgi window), 16-byte loads
+__global__ void dgi_time_sum_bf16x8_kernel(const __nv_bfloat16* __restrict__ dG, int T, int Bp, int H, float* __restrict__ out) {
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const int cpr = 3 * H / 8;
+  if (idx >= (long long)Bp * cpr) return;
+  const int c8 = (int)(idx % cpr) * 8, b = (int)(idx / cpr);
+  const int blk = c8 / H, j = c8 - blk * H;      // blk: 0 = n, 1 = r, 2 = z
+  const int g = (blk == 0) ? 2 : (blk - 1);      // -> (r,z,n) order of the output
+  const uint4* p = reinterpret_cast<const uint4*>(dG + (long long)b * 4 * H + c8);
+  const long long tstride = (long long)Bp * 4 * H / 8;
+  float s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll 4
+  for (int t = 0; t < T; ++t) {
+    const uint4 v = __ldg(p + (long long)t * tstride);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { s[2 * k] += __uint_as_float(w[k] << 16); s[2 * k + 1] += __uint_as_float(w[k] & 0xFFFF0000u); }
+  }
+  float4* o = reinterpret_cast<float4*>(out + (long long)b * 3 * H + g * H + j);
+  o[0] = make_float4(s[0], s[1], s[2], s[3]);
+  o[1] = make_float4(s[4], s[5], s[6], s[7]);
 }
 // dW[(r,z,n) row g*H+j][v] = dTBL[v][blk(g)*H + j]   : transposes the (n,r,z)-ordered table gradient into torch's order
 __global__ void tbl_grad_to_rzn_T_kernel(const float* __restrict__ dTBL, int H, int V, float* __restrict__ out /*[3H][V]*/) {
@@ -688,8 +711,8 @@ int step_t(const MDims& d, const MWS& w, const float* const* P, float* const* G,
     if (l >= 1) {
       const TA* X = (const TA*)w.hs[l - 1] + (size_t)Bp * Hd;
       if (drop) {   // nn.GRU(dropout=p) in train mode: dropout on the outputs of every layer but the last (mosesvae.py:78)
-        RC(dropout_launch<TA>(st, X, (TA*)w.hdrop, (unsigned long long)d.drop_seed + (l - 1), d.drop, B, Bp, Hd, T));
-        X = (const TA*)w.hdrop;
+        RC(dropout_launch<TA>(st, X, (TA*)w.hdrop[l], (unsigned long long)d.drop_seed + (l - 1), d.drop, B, Bp, Hd, T));
+        X = (const TA*)w.hdrop[l];
       }
       if (prec) {
         // every row of every slab is written (no tile skipping): the persistent sweep runs all rows through all T steps, and
@@ -781,10 +804,7 @@ int step_t(const MDims& d, const MWS& w, const float* const* P, float* const* G,
     gate_bias_grads_kernel<<<ceil_div(3 * Hd, 256), 256, 0, st>>>(w.csum, Hd, G[ix.bih(l)], G[ix.bhh(l)]); KCHECK();
     if (l >= 1) {
       const TA* X = (const TA*)w.hs[l - 1] + (size_t)Bp * Hd;
-      if (drop) {   // regenerate the dropped input of this layer (same counter-based mask)
-        RC(dropout_launch<TA>(st, X, (TA*)w.hdrop, (unsigned long long)d.drop_seed + (l - 1), d.drop, B, Bp, Hd, T));
-        X = (const TA*)w.hdrop;
-      }
+      if (drop) X = (const TA*)w.hdrop[l];   // the dropped input of this layer, kept by the forward pass
       RC(memset_async(w.dW_p, (size_t)3 * Hd * Hd * 4, st));
       RC(gemm<TA>(w.err_flag, st, dG, 4 * Hd, true, X, Hd, false, w.dW_p, Hd, false, 3 * Hd, Hd, TB, nullptr, true, wsplits, 256, VLK));
       simt::unpad_gate_matrix_kernel<<<grid_for(3ll * Hd * Hd), 256, 0, st>>>(w.dW_p, Hd, Hd, G[ix.wih(l)], Hd, Hd, 2, 0, 1); KCHECK();
@@ -798,7 +818,11 @@ int step_t(const MDims& d, const MWS& w, const float* const* P, float* const* G,
       RC(memset_async(w.dTBL, (size_t)CP * 3 * Hd * 4, st));
       RC(gemm<TA>(w.err_flag, st, (const TA*)w.OH, CP, true, dG, 4 * Hd, false, w.dTBL, 3 * Hd, false, CP, 3 * Hd, TB, nullptr, true,
                   d.bf16 ? 24 : 64, 256, VLK));
-      dgi_time_sum_t_kernel<TA><<<(unsigned)ceil_div64((long long)Bp * 3 * Hd, 256), 256, 0, st>>>(dG, T, Bp, Hd, w.dgisum); KCHECK();
+      if constexpr (sizeof(TA) == 2) {
+        dgi_time_sum_bf16x8_kernel<<<(unsigned)ceil_div64((long long)Bp * 3 * Hd / 8, 256), 256, 0, st>>>((const __nv_bfloat16*)dG, T, Bp, Hd, w.dgisum); KCHECK();
+      } else {
+        dgi_time_sum_t_kernel<TA><<<(unsigned)ceil_div64((long long)Bp * 3 * Hd, 256), 256, 0, st>>>(dG, T, Bp, Hd, w.dgisum); KCHECK();
+      }
     }
   }
   // decoder layer-0 input weights: W_ih[:, :V] through the table, W_ih[:, V:] through z
