@@ -716,11 +716,13 @@ int launch2(const mvae_gru_rec_args& a, cudaStream_t st) {
     if (BWD) {
       cuuint64_t dims[3] = {(cuuint64_t)3 * Hp, (cuuint64_t)Bp, (cuuint64_t)T};
       cuuint64_t str[2] = {(cuuint64_t)4 * Hp * 2, (cuuint64_t)Bp * 4 * Hp * 2};
+      if (a.debug & 8192) str[0] = 128;   // timing experiment (wrong data): every operand stage is one contiguous 16 KB region
       int rc = encode(&tmA, a.dG + Hp, 3, dims, str, box);
       if (rc) return rc;
     } else {
       cuuint64_t dims[3] = {(cuuint64_t)Hp, (cuuint64_t)Bp, (cuuint64_t)(T + 1)};
       cuuint64_t str[2] = {(cuuint64_t)Hp * 2, (cuuint64_t)Bp * Hp * 2};
+      if (a.debug & 8192) str[0] = 128;
       int rc = encode(&tmA, a.hs, 3, dims, str, box);
       if (rc) return rc;
     }

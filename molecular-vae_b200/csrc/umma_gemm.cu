@@ -570,6 +570,56 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           continue;
         }
       }
+      // Fast path (full bf16 output tile, aligned): the TMEM load of chunk c+1 is in flight while chunk c is biased, packed and
+      // stored; the bias comes in 16-byte pieces.  K-short GEMMs (the input projections: 8 k-blocks per tile) are otherwise
+      // bound by this epilogue, not by the tensor pipe.
+      if (p.out_bf16 && p.splits == 1 && (m_blk + 1) * BM <= p.M && (long long)(n_blk + 1) * BN <= p.N && (p.ldc & 7) == 0 &&
+          (reinterpret_cast<uintptr_t>(p.out) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0) {
+        constexpr int NCH = CH / 32;
+        const uint32_t tb = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + chalf * CH;
+        uint32_t r0[32], r1[32];
+        auto process = [&](const uint32_t (&rr)[32], int c) {
+          const int col0 = n_blk * BN + chalf * CH + c * 32;
+#pragma unroll
+          for (int h = 0; h < 4; ++h) {
+            float4 ba = make_float4(0.f, 0.f, 0.f, 0.f), bb = ba;
+            if (add_bias) {
+              ba = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + h * 8));
+              bb = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + h * 8) + 1);
+            }
+            uint4 pk;
+            __nv_bfloat162 b0 = __floats2bfloat162_rn(__uint_as_float(rr[h * 8 + 0]) + ba.x, __uint_as_float(rr[h * 8 + 1]) + ba.y);
+            __nv_bfloat162 b1 = __floats2bfloat162_rn(__uint_as_float(rr[h * 8 + 2]) + ba.z, __uint_as_float(rr[h * 8 + 3]) + ba.w);
+            __nv_bfloat162 b2 = __floats2bfloat162_rn(__uint_as_float(rr[h * 8 + 4]) + bb.x, __uint_as_float(rr[h * 8 + 5]) + bb.y);
+            __nv_bfloat162 b3 = __floats2bfloat162_rn(__uint_as_float(rr[h * 8 + 6]) + bb.z, __uint_as_float(rr[h * 8 + 7]) + bb.w);
+            pk.x = *reinterpret_cast<uint32_t*>(&b0);
+            pk.y = *reinterpret_cast<uint32_t*>(&b1);
+            pk.z = *reinterpret_cast<uint32_t*>(&b2);
+            pk.w = *reinterpret_cast<uint32_t*>(&b3);
+            const int col = col0 + h * 8;
+            __nv_bfloat16* o = p.out_rb ? reinterpret_cast<__nv_bfloat16*>(p.out) +
+                                              ((long long)(row >> 5) * (p.ldc >> 3) + (col >> 3)) * 256 + (row & 31) * 8
+                                        : reinterpret_cast<__nv_bfloat16*>(p.out) + (long long)row * p.ldc + col;
+            *reinterpret_cast<uint4*>(o) = pk;
+          }
+        };
+        ptx::tmem_ld_32x32(tb, r0);
+#pragma unroll 1
+        for (int c = 0; c < NCH; c += 2) {
+          ptx::tmem_ld_wait();
+          if (c + 1 < NCH) ptx::tmem_ld_32x32(tb + (c + 1) * 32, r1);
+          process(r0, c);
+          if (c + 1 < NCH) {
+            ptx::tmem_ld_wait();
+            if (c + 2 < NCH) ptx::tmem_ld_32x32(tb + (c + 2) * 32, r0);
+            process(r1, c + 1);
+          }
+        }
+        ptx::tc_fence_before();
+        ptx::mbar_arrive(&tempty_bar[acc]);
+        if (++acc == 2) { acc = 0; acc_ph ^= 1; }
+        continue;
+      }
 #pragma unroll 1
       for (int c0 = chalf * CH; c0 < (chalf + 1) * CH; c0 += 32) {
         uint32_t r[32];
