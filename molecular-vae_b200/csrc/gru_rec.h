@@ -29,6 +29,9 @@ struct mvae_gru_rec_args {
   int V;                     // <= 64
   // gru_rec2 fwd, optional: hlast[row][:] = fp32 state after step lens[row]-1, rows < nrows
   const int* lens; float* hlast; int nrows;
+  // gru_rec2, optional (packed sequences, batch sorted by length descending): DEVICE array [Bp/256], tile j runs only its
+  // first tile_T[j] time steps (what lies beyond is neither read nor written); null = every tile runs T steps
+  const int* tile_T;
 };
 
 // rows (molecules) one cooperative launch can cover on a device with num_sms SMs (0: shape unsupported)

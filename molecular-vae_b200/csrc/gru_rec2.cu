@@ -37,7 +37,7 @@ constexpr int EPI_WARPS = 16;
 constexpr int CTRL_WARPS = 4;
 constexpr int THREADS = (CTRL_WARPS + EPI_WARPS) * 32;
 constexpr int PUB_WARP = 2;
-constexpr int CTRL_REGS = 32, EPI_REGS = 112;   // (96 - 24) * 128 released >= (112 - 96) * 512 claimed
+constexpr int CTRL_REGS = 32, EPI_REGS = 112;   // (96 - 32) * 128 released >= (112 - 96) * 512 claimed
 constexpr int EPI_BAR = 1;
 
 struct Params2 {
@@ -64,6 +64,10 @@ struct Params2 {
   // fwd, optional: state after each row's last valid step, hlast[row][:] = h_{lens[row]-1} (fp32, rows < nrows)
   const int* lens; float* hlast; int nrows;
   int tpp;                   // row tiles per pair actually used (1 or NTILES)
+  // packed sequences (batch sorted by length, descending): tile j only runs its first tile_T[j] time steps (forward: steps
+  // [0, tile_T[j]); BPTT: t from tile_T[j]-1 down to 0).  With `mirror` pair-row y owns tiles y and pair_tiles-1-y, so a
+  // long tile shares its SMs with a short one.
+  const int* tile_T; int mirror;
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -176,7 +180,9 @@ __device__ __forceinline__ void commit2_mc(uint64_t* bar, uint16_t mask) {
 
 // IN (forward only): where the input projection of a step comes from -- 0: the gi tensor (GEMM output); 1: gi (time-
 // invariant per-row part) + a token table in shared memory; 2: the token table only, plus the final-state capture (lens / hlast)
-template <bool BWD, bool FAST, int CL, bool KS, int IN = 0>
+// VL: packed sequences -- per-tile step windows (tile_T) and the mirrored tile assignment; without it every tile runs all T
+// steps and the window arithmetic folds away
+template <bool BWD, bool FAST, int CL, bool KS, int IN = 0, bool VL = false>
 __global__ void __launch_bounds__(THREADS, 1)
 gru_rec2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmA, const Params2 p) {
   static_assert(!KS || (BWD && CL == 2), "K-split is a BPTT variant of the pair kernel");
@@ -226,8 +232,20 @@ gru_rec2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
   const int kh = KS ? (pair & 1) : 0;                 // KS: which half of K this pair contracts over
   const int koff = KS ? kh * (3 * p.Hp / 2) : 0;      // first dgh column (= first W_hh^T column) of that half
   const int U0 = KS ? (pair >> 1) * 2 * RU : u0;      // KS: first of the 128 units of the two-pair cluster
-  const int tile0 = blockIdx.y * p.tpp;
-  const int ntiles = min(p.tpp, p.pair_tiles - tile0);
+  const bool mirror = VL && p.mirror;
+  const int ntiles = mirror ? NTILES : min(p.tpp, p.pair_tiles - (int)blockIdx.y * p.tpp);
+  // per slot (scalars, selected with i ? b : a, so that nothing is indexed dynamically): row tile, first global step at
+  // which it is active, one past its last active step
+  static_assert(NTILES == 2, "slot scalars");
+  const int tid_a = mirror ? (int)blockIdx.y : (int)blockIdx.y * p.tpp;
+  const int tid_b = mirror ? p.pair_tiles - 1 - (int)blockIdx.y : (int)blockIdx.y * p.tpp + 1;
+  const int Tn_a = (VL && p.tile_T) ? min(p.T, p.tile_T[tid_a]) : p.T;
+  const int Tn_b = (VL && p.tile_T && ntiles > 1) ? min(p.T, p.tile_T[tid_b]) : p.T;
+  const int fs_a = (VL && BWD) ? p.T - Tn_a : 0, fs_b = (VL && BWD) ? p.T - Tn_b : 0;
+  const int es_a = (VL && !BWD) ? Tn_a : p.T, es_b = (VL && !BWD) ? Tn_b : p.T;
+#define TILE_ID(i) ((i) ? tid_b : tid_a)
+#define F_STEP(i) ((i) ? fs_b : fs_a)
+#define E_STEP(i) ((i) ? es_b : es_a)
   const uint16_t mask_par = (uint16_t)((CL == 8 ? 0x55 : CL == 4 ? 0x5 : 0x1) << parity);  // same-parity CTAs
   const uint16_t mask_pair = (uint16_t)(3u << (rank & ~1u));
   const int qd = CL == 2 ? 0 : (int)(rank >> 1);      // multicast clusters: which part of the operand tile this CTA loads
@@ -301,8 +319,10 @@ gru_rec2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
         if (p.debug & 2) slab = (slab + pair * 5) % p.T;
         if (p.debug & 16) slab = 0;   // timing experiment: operand that nobody writes during the sweep
         for (int i = 0; i < ntiles; ++i) {
-          const int tile = tile0 + i;
-          if (!(p.debug & 1) && !wait_counter(p.counters + tile * 2 + parity, (unsigned)(p.npairs * step), p.err_flag)) goto done;
+          const int tile = TILE_ID(i);
+          const int ls = step - F_STEP(i);                       // steps this tile has completed so far
+          if (step >= E_STEP(i) || ls < (BWD ? 1 : 0)) continue;   // BPTT: the tile's first step has no operand
+          if (!(p.debug & 1) && !wait_counter(p.counters + tile * 2 + parity, (unsigned)(p.npairs * ls), p.err_flag)) goto done;
           ptx::fence_proxy_async_all();
           if (p.trace && blockIdx.x == 0 && blockIdx.y == 0) p.trace[((size_t)step * NTILES + i) * 12 + 0] = gtime();
           const int row0 = tile * 256 + parity * 128 + qd * A_PART_ROWS;
@@ -358,8 +378,10 @@ gru_rec2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
         int s = 0; uint32_t ph = 0;
         for (int step = 0; step < p.T; ++step) {
           for (int i = 0; i < ntiles; ++i) {
-            if (step > 0 || !BWD) {
-              if (step > 0 && !wait_bar(&tempty_bar[i], (uint32_t)((step - 1) & 1), p.err_flag)) goto done;
+            const int ls = step - F_STEP(i);
+            if (ls < 0 || step >= E_STEP(i)) continue;
+            if (ls > 0 || !BWD) {
+              if (ls > 0 && !wait_bar(&tempty_bar[i], (uint32_t)((ls - 1) & 1), p.err_flag)) goto done;
               ptx::tc_fence_after();
               const uint32_t d_tmem = tmem_base + i * NB;
               for (int kc0 = 0; kc0 < KCS; ++kc0) {
@@ -388,7 +410,7 @@ gru_rec2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
             commit2_mc(&tfull_bar[i], mask_pair);     // accumulator i complete -> both epilogues
             if ((p.debug & 8) && p.trace && blockIdx.x == 0 && blockIdx.y == 0) {
               // timing experiment: how long until the tensor pipe has really finished this tile's MMAs
-              wait_bar(&tfull_bar[i], (uint32_t)(step & 1), p.err_flag);
+              wait_bar(&tfull_bar[i], (uint32_t)(ls & 1), p.err_flag);
               p.trace[((size_t)step * NTILES + i) * 12 + 9] = t_issue;
               p.trace[((size_t)step * NTILES + i) * 12 + 10] = gtime();
             }
@@ -403,8 +425,10 @@ gru_rec2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
       const uint32_t tempty_remote = mapa(ptx::smem_u32(&tempty_bar[0]), rank & ~1u);
       for (int step = 0; step < p.T; ++step)
         for (int i = 0; i < ntiles; ++i) {
-          const int tile = tile0 + i;
-          if (!wait_bar(&epi_bar[i], (uint32_t)(step & 1), p.err_flag)) goto done;
+          const int tile = TILE_ID(i);
+          const int ls = step - F_STEP(i);
+          if (ls < 0 || step >= E_STEP(i)) continue;
+          if (!wait_bar(&epi_bar[i], (uint32_t)(ls & 1), p.err_flag)) goto done;
           remote_arrive(tempty_remote + (uint32_t)(i * 8));    // accumulator i drained in this CTA -> pair leader
           const bool tr = p.trace && blockIdx.x == 0 && blockIdx.y == 0;
           if (tr) p.trace[((size_t)step * NTILES + i) * 12 + 6] = gtime();
@@ -427,19 +451,19 @@ gru_rec2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
     const int part = (warp - CTRL_WARPS) >> 2;   // 0..3 -> 16 units each
     const int uc = part * 16;
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
-    uint32_t fph = 0;
-    int lastv[NTILES] = {-1, -1};   // IN == 2: step after which this thread's row of tile i hands its state to hlast
+    uint32_t nx = 0;   // KS: exchanges this warp has done so far (the partner warp runs the same tile / step sequence)
+    int lastv_a = -1, lastv_b = -1;   // IN == 2: step after which this thread's row of slot a / b hands its state to hlast
     if constexpr (!BWD && IN == 2) {
       if (p.hlast)
         for (int i = 0; i < ntiles; ++i) {
-          const long long row = (long long)(tile0 + i) * 256 + parity * 128 + q * 32 + lane;
-          if (row < p.nrows) lastv[i] = p.lens[row] - 1;
+          const long long row = (long long)TILE_ID(i) * 256 + parity * 128 + q * 32 + lane;
+          if (row < p.nrows) { if (i) lastv_b = p.lens[row] - 1; else lastv_a = p.lens[row] - 1; }
         }
     }
     if constexpr (!BWD) {
       // fp32 master copy of the initial state (zeros without h0) into this thread's TMEM columns of every tile
       for (int i = 0; i < ntiles; ++i) {
-        const long long row = (long long)(tile0 + i) * 256 + parity * 128 + q * 32 + lane;
+        const long long row = (long long)TILE_ID(i) * 256 + parity * 128 + q * 32 + lane;
         float h[16];
 #pragma unroll
         for (int k = 0; k < 16; ++k) h[k] = 0.f;
@@ -458,7 +482,9 @@ gru_rec2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
     for (int step = 0; step < p.T; ++step) {
       const int t = BWD ? (p.T - 1 - step) : step;
       for (int i = 0; i < ntiles; ++i) {
-        const int tile = tile0 + i;
+        const int tile = TILE_ID(i);
+        const int ls = step - F_STEP(i);
+        if (ls < 0 || step >= E_STEP(i)) continue;
         const long long row = (long long)tile * 256 + parity * 128 + q * 32 + lane;
         // saved activations use a per-thread "fragment" layout (consumed only by the BPTT epilogue with the same
         // thread mapping): block (t, tile, pair, parity, part, array) of 4 KB, thread (q, lane) owns 32 B -> every
@@ -491,7 +517,7 @@ gru_rec2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
           pre[4] = ldg2x128(svp + 4 * 2048);   // h_{t-1} (saved by the forward sweep next to the gates)
           pre[5] = ldg2x128(p.dX + (long long)t * p.Bp * p.Hp + (rblk * (p.Hp / 8) + ((u0 + uc) >> 3)) * 256 + lane * 8);
         }
-        (void)wait_bar(&tfull_bar[i], fph, p.err_flag);   // on failure keep walking: barriers below must be reached
+        (void)wait_bar(&tfull_bar[i], (uint32_t)(ls & 1), p.err_flag);   // on failure keep walking: barriers below must be reached
         ptx::tc_fence_after();
         const bool tr = p.trace && blockIdx.x == 0 && blockIdx.y == 0 && warp == CTRL_WARPS && lane == 0;
         if (tr) p.trace[((size_t)step * NTILES + i) * 12 + 4] = gtime();
@@ -548,7 +574,7 @@ gru_rec2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
             an[k] = __float_as_uint(ghn);
           }
           if (tr2) p.trace[((size_t)step * NTILES + i) * 12 + 9] = gtime();
-          if (IN == 2 && t == lastv[i]) {
+          if (IN == 2 && t == (i ? lastv_b : lastv_a)) {
             float4* hl = reinterpret_cast<float4*>(p.hlast + row * p.Hp + u0 + uc);
 #pragma unroll
             for (int k = 0; k < 4; ++k) hl[k] = make_float4(h[4 * k], h[4 * k + 1], h[4 * k + 2], h[4 * k + 3]);
@@ -573,7 +599,7 @@ gru_rec2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
           }
         } else {
           uint32_t acc[16], cm[16];
-          if (step > 0) {
+          if (ls > 0) {
             if (KS) {
               // this pair contracted over ONE half of K for all 128 units of the cluster: hand the partial sums of the 64
               // units the partner pair finalises to the partner CTA (same parity -> same rows) through its shared memory,
@@ -584,7 +610,7 @@ gru_rec2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
               ptx::tmem_ld_32x16(master_addr, cm);
               ptx::tmem_ld_wait();
               const uint32_t partner = rank ^ 2u;
-              const uint32_t ev = (uint32_t)((step - 1) * ntiles + i);   // exchange number (tile-steps alternate strictly)
+              const uint32_t ev = nx++;                                  // exchange number
               // xbuf[unit][row]: a warp store covers 32 consecutive rows of one unit (128 contiguous bytes)
               const uint32_t xloc = ptx::smem_u32(xbuf + (size_t)uc * 128 + q * 32 + lane);
               const uint32_t xrem = mapa(xloc, partner);
@@ -650,7 +676,6 @@ gru_rec2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
         if (tr && (p.debug & 64)) p.trace[((size_t)step * NTILES + i) * 12 + 11] = gtime();
         if (!BWD && tr) p.trace[((size_t)step * NTILES + i) * 12 + 5] = gtime();
       }
-      fph ^= 1;
     }
   }
 done:
@@ -688,7 +713,7 @@ int encode(CUtensorMap* map, const void* ptr, int rank, const cuuint64_t* dims, 
   return r == CUDA_SUCCESS ? MVAE_OK : MVAE_ERR_DRIVER;
 }
 
-template <bool BWD, bool FAST, int CL, bool KS = false, int IN = 0>
+template <bool BWD, bool FAST, int CL, bool KS = false, int IN = 0, bool VL = false>
 int launch2(const mvae_gru_rec_args& a, cudaStream_t st) {
   const int Hp = a.Hp, Bp = a.Bp, T = a.T;
   constexpr int NBH = (BWD ? (KS ? 2 * RU : RU) : 3 * RU) / 2;
@@ -736,7 +761,7 @@ int launch2(const mvae_gru_rec_args& a, cudaStream_t st) {
   p.nst = nst;
   p.tbl = use_tbl ? a.tbl : nullptr; p.tok = use_tbl ? a.tok : nullptr; p.V = use_tbl ? a.V : 0;
   p.lens = BWD ? nullptr : a.lens; p.hlast = (BWD || !a.lens) ? nullptr : a.hlast; p.nrows = a.nrows;
-  auto kern = gru_rec2_kernel<BWD, FAST, CL, KS, IN>;
+  auto kern = gru_rec2_kernel<BWD, FAST, CL, KS, IN, VL>;
   static size_t attr_smem = 0;
   if (smem > attr_smem) {
     MVAE_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -747,6 +772,8 @@ int launch2(const mvae_gru_rec_args& a, cudaStream_t st) {
   // one row tile per pair when every CTA is co-resident anyway (small hidden sizes): twice the SMs, half the chain per step
   const int tpp = ((Hp / 32) * (Bp / 256) <= 148 && !(a.debug & 4096)) ? 1 : NTILES;
   p.tpp = tpp;
+  p.tile_T = VL ? a.tile_T : nullptr;
+  p.mirror = (VL && a.tile_T && tpp == NTILES && (Bp / 256) % 2 == 0) ? 1 : 0;
   cfg.gridDim = dim3(Hp / 32, ceil_div(Bp / 256, tpp), 1);
   cfg.blockDim = dim3(THREADS, 1, 1);
   cfg.dynamicSmemBytes = smem;
@@ -783,6 +810,12 @@ int mvae_gru_rec2_max_clusters(int backward, int cluster) {
 int mvae_gru_rec2_launch(const mvae_gru_rec_args* a, int fast_gates, cudaStream_t stream) {
   if (!a || a->Bp % 256 || (a->Hp != 256 && a->Hp != 512) || a->T < 1) return MVAE_ERR_INVALID;
   const int cl = a->variant == 38 ? 8 : a->variant == 34 ? 4 : 2;
+  if (a->tile_T) {   // packed sequences: K-split BPTT / pair forward kernel with per-tile step windows (fast gates only)
+    if (a->backward) return a->variant == 32 ? launch2<true, false, 2, true, 0, true>(*a, stream) : MVAE_ERR_UNSUPPORTED;
+    if (cl != 2 || !fast_gates) return MVAE_ERR_UNSUPPORTED;
+    if (!a->tbl) return launch2<false, true, 2, false, 0, true>(*a, stream);
+    return a->gi ? launch2<false, true, 2, false, 1, true>(*a, stream) : launch2<false, true, 2, false, 2, true>(*a, stream);
+  }
   if (a->variant == 32 && a->backward) return launch2<true, false, 2, true>(*a, stream);
   if (!a->backward && a->tbl) {   // token-table input projection (pair clusters, fast gates only)
     if (cl != 2) return MVAE_ERR_UNSUPPORTED;

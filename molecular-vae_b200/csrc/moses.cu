@@ -51,6 +51,8 @@ int make_dims(const mvae_moses_desc* d, MDims* o) {
 struct MWS {
   int* err_flag; double* kl_sum; double* nll_sum; int* M;
   int* act_dev;    // [T] packed-sequence batch sizes on the device (for the tile / k-block skipping of the big GEMMs)
+  int* act256_dev; // [T] the same rounded up to the 256-row tiles of the persistent sweeps
+  int* tileT;      // [Bp/256] time steps row tile j of the persistent sweeps has to run (= its longest sequence)
   float *TBLe, *TBLd, *hlast, *rmu, *rlv, *mu, *lv, *z, *h0, *zproj, *dh0, *dz, *dmu, *dlv, *dr, *dhenc, *dgisum;
   float *dTBL;      // [CP][3Hd] fp32, columns in (n,r,z) order
   float *dWT;       // [3Hd][V] staging
@@ -79,7 +81,7 @@ void carve(const MDims& d, void* base, MWS* w) {
   const size_t es = d.bf16 ? 2 : 4;
   const size_t B = d.B, Bp = d.Bp, T = d.T, Hd = d.Hd, Hq = d.Hq;
   w->err_flag = c.take<int>(1); w->kl_sum = c.take<double>(1); w->nll_sum = c.take<double>(1); w->M = c.take<int>(1);
-  w->act_dev = c.take<int>(512);
+  w->act_dev = c.take<int>(512); w->act256_dev = c.take<int>(512); w->tileT = c.take<int>(Bp / 256 + 8);
   w->TBLe = c.take<float>((size_t)d.V * 3 * Hq); w->TBLd = c.take<float>((size_t)d.V * 3 * Hd);
   w->hlast = c.take<float>(Bp * Hq); w->rmu = c.take<float>(B * d.MLP); w->rlv = c.take<float>(B * d.MLP);
   w->mu = c.take<float>(B * d.Z); w->lv = c.take<float>(B * d.Z); w->z = c.take<float>(B * d.Z);
@@ -190,12 +192,15 @@ __global__ void relu_bwd_kernel(const float* __restrict__ out, float* __restrict
     if (!(out[i] > 0.f)) d[i] = 0.f;
 }
 // act[t] = number of sequences longer than t (lengths sorted descending -> they are the rows [0, act[t]))
-__global__ void count_active_kernel(const int* __restrict__ lens, int B, int T, int* __restrict__ act) {
+__global__ void count_active_kernel(const int* __restrict__ lens, int B, int T, int* __restrict__ act, int* __restrict__ act256,
+                                    int* __restrict__ tileT, int Bp) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < Bp / 256) tileT[t] = t * 256 < B ? min(T, lens[t * 256]) : 0;   // sorted descending: the tile's first row is its longest
   if (t >= T) return;
   int lo = 0, hi = B;                  // first index with lens <= t
   while (lo < hi) { const int mid = (lo + hi) >> 1; if (lens[mid] > t) lo = mid + 1; else hi = mid; }
   act[t] = lo;
+  act256[t] = min(Bp, (lo + 255) & ~255);
 }
 __global__ void count_targets_kernel(const int* __restrict__ lens, int B, int* __restrict__ M) {
   int local = 0;
@@ -289,7 +294,9 @@ __global__ void dgi_time_sum_t_kernel(const TA* __restrict__ dG, int T, int Bp, 
   out[idx] = s;
 }
 // bf16 variant: one thread per (row, 8 consecutive columns of the (n,r,z) dgi window), 16-byte loads
-__global__ void dgi_time_sum_bf16x8_kernel(const __nv_bfloat16* __restrict__ dG, int T, int Bp, int H, float* __restrict__ out) {
+// tileT (optional): rows of 256-row tile j only hold valid data for t < tileT[j]
+__global__ void dgi_time_sum_bf16x8_kernel(const __nv_bfloat16* __restrict__ dG, int T, int Bp, int H, float* __restrict__ out,
+                                           const int* __restrict__ tileT = nullptr) {
   const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   const int cpr = 3 * H / 8;
   if (idx >= (long long)Bp * cpr) return;
@@ -299,6 +306,7 @@ __global__ void dgi_time_sum_bf16x8_kernel(const __nv_bfloat16* __restrict__ dG,
   const uint4* p = reinterpret_cast<const uint4*>(dG + (long long)b * 4 * H + c8);
   const long long tstride = (long long)Bp * 4 * H / 8;
   float s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (tileT) T = min(T, tileT[b >> 8]);
 #pragma unroll 4
   for (int t = 0; t < T; ++t) {
     const uint4 v = __ldg(p + (long long)t * tstride);
@@ -623,7 +631,13 @@ int step_t(const MDims& d, const MWS& w, const float* const* P, float* const* G,
   mvae_umma_varlen vlm{w.act_dev, Bp, 1}, vlk{w.act_dev, Bp, 2};
   const mvae_umma_varlen* VLM = (act && d.bf16 && varlen_gemm_enabled()) ? &vlm : nullptr;
   const mvae_umma_varlen* VLK = (act && d.bf16 && varlen_gemm_enabled()) ? &vlk : nullptr;
-  if (VLM) { count_active_kernel<<<ceil_div(T, 128), 128, 0, st>>>(lens, B, T, w.act_dev); KCHECK(); }
+  if (VLM) { count_active_kernel<<<ceil_div(max(T, Bp / 256), 128), 128, 0, st>>>(lens, B, T, w.act_dev, w.act256_dev, w.tileT, Bp); KCHECK(); }
+  // persistent sweeps over packed sequences: row tile j runs only tileT[j] steps; the GEMMs that feed / follow them skip the
+  // same (t, 256-row tile) regions, which are then neither written nor read
+  mvae_umma_varlen vlm256{w.act256_dev, Bp, 1};
+  const mvae_umma_varlen* VLS = VLM ? &vlm256 : nullptr;
+  const int* tileT = VLM ? w.tileT : nullptr;
+  const int* lim256 = VLM ? w.act256_dev : nullptr;
   simt::pad_gate_matrix_kernel<TA><<<grid_for(3ll * Hq * Hq), 256, 0, st>>>(P[ix.e_whh(0)], Hq, Hq, (TA*)w.Whh_enc, Hq, Hq, 0, 1, 2); KCHECK();
   simt::pad_gate_vector_kernel<<<ceil_div(3 * Hq, 256), 256, 0, st>>>(P[ix.e_bhh(0)], Hq, w.bhh_enc, Hq); KCHECK();
   if (d.bidir) {
@@ -663,6 +677,7 @@ int step_t(const MDims& d, const MWS& w, const float* const* P, float* const* G,
       ra.W = (const __nv_bfloat16*)w.Whh_enc; ra.gi = nullptr; ra.gi_tstride = 0; ra.bhh = w.bhh_enc + 2 * Hq;
       ra.hs = (__nv_bfloat16*)w.hs_enc; ra.sv = (__nv_bfloat16*)w.sv_enc; ra.counters = w.counters; ra.err_flag = w.err_flag;
       ra.ones_col = -1; ra.tbl = w.tbl_comb; ra.tok = w.tokT; ra.V = V; ra.lens = lens; ra.hlast = w.hlast; ra.nrows = B;
+      ra.tile_T = tileT;
       mvae_count_launches(2);
       RC(mvae_gru_rec2_launch(&ra, 1, st));
       enc_swept = true;
@@ -719,7 +734,7 @@ int step_t(const MDims& d, const MWS& w, const float* const* P, float* const* G,
         // what it computes past a sequence's end must stay finite (it meets zero gradients in the K = T*B wgrad GEMMs)
         combine_gate_bias_kernel<<<ceil_div(3 * Hd, 256), 256, 0, st>>>(w.bih[l], w.bhh[l], w.bcomb[l], Hd); KCHECK();
         RC(gemm<TA>(w.err_flag, st, X, Hd, false, (const TA*)w.Wih[l], Hd, true, w.gi, 3 * Hd, true, TB, 3 * Hd, Hd, w.bcomb[l], false, 1, 0,
-                    nullptr, true));
+                    VLS, true));
       } else {
         RC(gemm<TA>(w.err_flag, st, X, Hd, false, (const TA*)w.Wih[l], Hd, true, w.gi, 3 * Hd, true, TB, 3 * Hd, Hd, w.bih[l], false, 1, 0, VLM));
       }
@@ -733,7 +748,7 @@ int step_t(const MDims& d, const MWS& w, const float* const* P, float* const* G,
         ra.W = (const __nv_bfloat16*)w.Whh[l]; ra.gi = (const __nv_bfloat16*)w.gi; ra.gi_tstride = (long long)Bp * 3 * Hd;
         if (l == 0) { ra.gi = (const __nv_bfloat16*)w.zproj_rb; ra.gi_tstride = 0; ra.tbl = w.TBLd; ra.tok = w.tokT; ra.V = V; }
         ra.bhh = w.bhh[l] + 2 * Hd; ra.hs = (__nv_bfloat16*)w.hs[l]; ra.sv = (__nv_bfloat16*)w.sv[l]; ra.counters = w.counters;
-        ra.err_flag = w.err_flag; ra.ones_col = -1; ra.h0 = w.h0;
+        ra.err_flag = w.err_flag; ra.ones_col = -1; ra.h0 = w.h0; ra.tile_T = tileT;
         mvae_count_launches(2);
         RC(mvae_gru_rec2_launch(&ra, 1, st));
         continue;
@@ -763,7 +778,7 @@ int step_t(const MDims& d, const MWS& w, const float* const* P, float* const* G,
   // head
   // persistent BPTT: dX in the row-blocked layout, every row written (zeros past a sequence's end, where dlogits is zero)
   RC(gemm<TA>(w.err_flag, st, dlog, CP, false, (const TA*)w.Wfc, Hd, false, w.dX, Hd, true, TB, Hd, CP, nullptr, false, 1, 0,
-              prec ? nullptr : VLM, prec));
+              prec ? VLS : VLM, prec));
   RC(memset_async(w.dWfc_p, (size_t)CP * Hd * 4, st));
   RC(gemm<TA>(w.err_flag, st, dlog, CP, true, (const TA*)w.hs[L - 1] + (size_t)Bp * Hd, Hd, false, w.dWfc_p, Hd, false, CP, Hd, TB,
               nullptr, true, d.bf16 ? 148 : 64, 256, VLK));
@@ -784,7 +799,7 @@ int step_t(const MDims& d, const MWS& w, const float* const* P, float* const* G,
         ra.backward = 1; ra.variant = 32; ra.Bp = Bp; ra.Hp = Hd; ra.T = T;
         ra.W = (const __nv_bfloat16*)w.WhhT[l]; ra.hs = (__nv_bfloat16*)w.hs[l]; ra.sv = (__nv_bfloat16*)w.sv[l];
         ra.dX = (const __nv_bfloat16*)w.dX; ra.dG = (__nv_bfloat16*)dG; ra.counters = w.counters; ra.err_flag = w.err_flag;
-        ra.carry_out = w.dh_carry;
+        ra.carry_out = w.dh_carry; ra.tile_T = tileT;
         mvae_count_launches(2);
         RC(mvae_gru_rec2_launch(&ra, 0, st));
         // dL/dh0 of this layer = dh_0 * z_0 (carry_out) + dgh_0 * W_hh
@@ -800,7 +815,7 @@ int step_t(const MDims& d, const MWS& w, const float* const* P, float* const* G,
     RC(gemm<TA>(w.err_flag, st, dG + Hd, 4 * Hd, true, hs, Hd, false, w.dW_p, Hd, false, 3 * Hd, Hd, TB, nullptr, true, wsplits, 256, VLK));
     simt::unpad_gate_matrix_kernel<<<grid_for(3ll * Hd * Hd), 256, 0, st>>>(w.dW_p, Hd, Hd, G[ix.whh(l)], Hd, Hd, 0, 1, 2); KCHECK();
     RC(memset_async(w.csum, (size_t)4 * Hd * 4, st));
-    RC(simt::colsum<TA>(st, dG, TB, 4 * Hd, 4 * Hd, w.csum)); mvae_count_launches(1);
+    RC(simt::colsum<TA>(st, dG, TB, 4 * Hd, 4 * Hd, w.csum, swept ? lim256 : nullptr, Bp)); mvae_count_launches(1);
     gate_bias_grads_kernel<<<ceil_div(3 * Hd, 256), 256, 0, st>>>(w.csum, Hd, G[ix.bih(l)], G[ix.bhh(l)]); KCHECK();
     if (l >= 1) {
       const TA* X = (const TA*)w.hs[l - 1] + (size_t)Bp * Hd;
@@ -809,7 +824,7 @@ int step_t(const MDims& d, const MWS& w, const float* const* P, float* const* G,
       RC(gemm<TA>(w.err_flag, st, dG, 4 * Hd, true, X, Hd, false, w.dW_p, Hd, false, 3 * Hd, Hd, TB, nullptr, true, wsplits, 256, VLK));
       simt::unpad_gate_matrix_kernel<<<grid_for(3ll * Hd * Hd), 256, 0, st>>>(w.dW_p, Hd, Hd, G[ix.wih(l)], Hd, Hd, 2, 0, 1); KCHECK();
       RC(gemm<TA>(w.err_flag, st, dG, 4 * Hd, false, (const TA*)w.Wih_nrz[l], Hd, false, w.dX, Hd, true, TB, Hd, 3 * Hd, nullptr, false, 1, 0,
-                  prec ? nullptr : VLM, prec));
+                  prec ? VLS : VLM, prec));
       if (drop) {   // gradient wrt the undropped outputs of layer l-1
         RC(dropout_launch<TA>(st, (const TA*)w.dX, (TA*)w.dX, (unsigned long long)d.drop_seed + (l - 1), d.drop, B, Bp, Hd, T, prec ? 1 : 0));
       }
@@ -819,7 +834,8 @@ int step_t(const MDims& d, const MWS& w, const float* const* P, float* const* G,
       RC(gemm<TA>(w.err_flag, st, (const TA*)w.OH, CP, true, dG, 4 * Hd, false, w.dTBL, 3 * Hd, false, CP, 3 * Hd, TB, nullptr, true,
                   d.bf16 ? 24 : 64, 256, VLK));
       if constexpr (sizeof(TA) == 2) {
-        dgi_time_sum_bf16x8_kernel<<<(unsigned)ceil_div64((long long)Bp * 3 * Hd / 8, 256), 256, 0, st>>>((const __nv_bfloat16*)dG, T, Bp, Hd, w.dgisum); KCHECK();
+        dgi_time_sum_bf16x8_kernel<<<(unsigned)ceil_div64((long long)Bp * 3 * Hd / 8, 256), 256, 0, st>>>((const __nv_bfloat16*)dG, T, Bp, Hd, w.dgisum,
+                                                                                                             swept ? tileT : nullptr); KCHECK();
       } else {
         dgi_time_sum_t_kernel<TA><<<(unsigned)ceil_div64((long long)Bp * 3 * Hd, 256), 256, 0, st>>>(dG, T, Bp, Hd, w.dgisum); KCHECK();
       }
@@ -883,6 +899,7 @@ int step_t(const MDims& d, const MWS& w, const float* const* P, float* const* G,
         ra.backward = 1; ra.variant = 32; ra.Bp = Bp; ra.Hp = Hq; ra.T = T;
         ra.W = (const __nv_bfloat16*)w.WhhT_enc; ra.hs = (__nv_bfloat16*)w.hs_enc; ra.sv = (__nv_bfloat16*)w.sv_enc;
         ra.dX = (const __nv_bfloat16*)dXe; ra.dG = (__nv_bfloat16*)dG; ra.counters = w.counters; ra.err_flag = w.err_flag;
+        ra.tile_T = tileT;
         mvae_count_launches(2);
         RC(mvae_gru_rec2_launch(&ra, 0, st));
         swept = true;
@@ -900,7 +917,7 @@ int step_t(const MDims& d, const MWS& w, const float* const* P, float* const* G,
                 rev ? nullptr : VLK));
     simt::unpad_gate_matrix_kernel<<<grid_for(3ll * Hq * Hq), 256, 0, st>>>(w.dW_p, Hq, Hq, G[ix.e_whh(rev)], Hq, Hq, 0, 1, 2); KCHECK();
     RC(memset_async(w.csum, (size_t)4 * Hd * 4, st));
-    RC(simt::colsum<TA>(st, dG, TB, 4 * Hq, 4 * Hq, w.csum)); mvae_count_launches(1);
+    RC(simt::colsum<TA>(st, dG, TB, 4 * Hq, 4 * Hq, w.csum, swept ? lim256 : nullptr, Bp)); mvae_count_launches(1);
     gate_bias_grads_kernel<<<ceil_div(3 * Hq, 256), 256, 0, st>>>(w.csum, Hq, G[ix.e_bih(rev)], G[ix.e_bhh(rev)]); KCHECK();
     if (rev) { onehot_rows_kernel<TA><<<grid_for((long long)TB * CP), 256, 0, st>>>(ids, T, B, Bp, T, CP, (TA*)w.OH, 1); KCHECK(); }
     RC(memset_async(w.dTBL, (size_t)CP * 3 * Hd * 4, st));

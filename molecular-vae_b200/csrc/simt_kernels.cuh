@@ -218,11 +218,38 @@ __global__ void colsum_kernel(const T* __restrict__ x, long long rows, long long
     atomicAdd(out + c, t);
   }
 }
+// packed sequences: the rows form slabs of rps rows (blockIdx.y = slab); only the first lim[slab] rows of a slab count
+// (the rest may hold anything, it is not read)
 template <typename T>
-inline int colsum(cudaStream_t st, const T* x, long long rows, long long ld, int cols, float* out_zeroed) {
-  const int rpb = 2048;
-  dim3 grid(ceil_div(cols, 32), (unsigned)ceil_div64(rows, rpb));
-  colsum_kernel<T><<<grid, dim3(32, 8), 0, st>>>(x, rows, ld, cols, out_zeroed, rpb);
+__global__ void colsum_slabs_kernel(const T* __restrict__ x, int rps, long long ld, int cols, float* __restrict__ out,
+                                    const int* __restrict__ lim) {
+  __shared__ float red[8][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  const int n = min(rps, __ldg(lim + blockIdx.y));
+  const T* xs = x + (long long)blockIdx.y * rps * ld;
+  float s = 0.f;
+  if (c < cols)
+    for (int r = threadIdx.y; r < n; r += 8) s += to_f32<T>(xs[(long long)r * ld + c]);
+  red[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < cols && n > 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x];
+    atomicAdd(out + c, t);
+  }
+}
+template <typename T>
+inline int colsum(cudaStream_t st, const T* x, long long rows, long long ld, int cols, float* out_zeroed,
+                  const int* lim = nullptr, int rps = 1) {
+  if (lim) {
+    dim3 grid(ceil_div(cols, 32), (unsigned)(rows / rps));
+    colsum_slabs_kernel<T><<<grid, dim3(32, 8), 0, st>>>(x, rps, ld, cols, out_zeroed, lim);
+  } else {
+    const int rpb = 2048;
+    dim3 grid(ceil_div(cols, 32), (unsigned)ceil_div64(rows, rpb));
+    colsum_kernel<T><<<grid, dim3(32, 8), 0, st>>>(x, rows, ld, cols, out_zeroed, rpb);
+  }
   MVAE_CUDA_CHECK(cudaGetLastError());
   return MVAE_OK;
 }

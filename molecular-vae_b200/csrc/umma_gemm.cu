@@ -70,6 +70,13 @@ __device__ __forceinline__ bool vl_skip_kb(const KernelParams& p, int kb, int kb
   const int t = kb / p.vl_tiles, r = kb - t * p.vl_tiles;
   return r * BK >= __ldg(p.vl_act + t);
 }
+// the first k-block of a split is never skipped; when it lies in the inactive part (whose contents are undefined) the
+// producer loads it from beyond the K extent instead, where TMA fills zeros
+__device__ __forceinline__ bool vl_first_kb_inactive(const KernelParams& p, int kb, int kb0) {
+  if (p.vl_mode != 2 || kb != kb0) return false;
+  const int t = kb / p.vl_tiles, r = kb - t * p.vl_tiles;
+  return r * BK >= __ldg(p.vl_act + t);
+}
 
 // counter-based uniform in (0,1); must stay identical to u01_hash in moses.cu / oracle/moses_oracle.u01_hash
 __device__ __forceinline__ float u01_hash_gemm(unsigned long long seed, unsigned int b, unsigned int i) {
@@ -167,19 +174,20 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           ptx::mbar_arrive_expect_tx(&full_bar[s], C::STAGE_BYTES);
           uint8_t* a_dst = sA + s * A_STAGE_BYTES;
           uint8_t* b_dst = sB + s * C::B_STAGE_BYTES;
+          const int kc = (vl_first_kb_inactive(p, kb, kb0) ? kb_total : kb) * BK;   // k coordinate (past K: zero fill)
           if (A_MN) {
 #pragma unroll
             for (int c = 0; c < BM / 64; ++c)
-              ptx::tma_load_3d(a_dst + c * 8192, &tmA, &full_bar[s], m_blk * BM + c * 64, kb * BK, p.slabA);
+              ptx::tma_load_3d(a_dst + c * 8192, &tmA, &full_bar[s], m_blk * BM + c * 64, kc, p.slabA);
           } else {
-            ptx::tma_load_3d(a_dst, &tmA, &full_bar[s], kb * BK, m_blk * BM, p.slabA);
+            ptx::tma_load_3d(a_dst, &tmA, &full_bar[s], kc, m_blk * BM, p.slabA);
           }
           if (B_MN) {
 #pragma unroll
             for (int c = 0; c < BN / 64; ++c)
-              ptx::tma_load_3d(b_dst + c * 8192, &tmB, &full_bar[s], n_blk * BN + c * 64, kb * BK, p.slabB);
+              ptx::tma_load_3d(b_dst + c * 8192, &tmB, &full_bar[s], n_blk * BN + c * 64, kc, p.slabB);
           } else {
-            ptx::tma_load_3d(b_dst, &tmB, &full_bar[s], kb * BK, n_blk * BN, p.slabB);
+            ptx::tma_load_3d(b_dst, &tmB, &full_bar[s], kc, n_blk * BN, p.slabB);
           }
           if (++s == C::STAGES) { s = 0; ph ^= 1; }
         }

@@ -53,6 +53,9 @@ def test_moses_fused_step(precision, B, ltol, gtol):
     P, seqs, eps, pad, model = _setup(m, precision, 311, 411 + B, B)
     ref = mo.moses_step({k: v.astype(np.float64) for k, v in P.items()}, seqs, eps.astype(np.float64), pad, kl_weight=klw)
     x = [torch.from_numpy(s).cuda() for s in seqs]
+    model.elbo_step(x, kl_weight=klw, eps=torch.from_numpy(eps).cuda())
+    torch.cuda.synchronize()
+    model._ws.fill_(0xFF)   # poison the workspace (bf16 / fp32 NaN patterns): nothing may depend on stale contents
     out = model.elbo_step(x, kl_weight=klw, eps=torch.from_numpy(eps).cuda())
     torch.cuda.synchronize()
     model.check_device_error()
@@ -185,6 +188,9 @@ def test_mosesfile_bidirectional_fused_step(precision, B, ltol, gtol):
     P, seqs, eps, pad, model = _setup_file(m, precision, 331, 431 + B, B)
     ref = mo.mosesfile_step({k: v.astype(np.float64) for k, v in P.items()}, seqs, eps.astype(np.float64), pad, kl_weight=klw)
     x = [torch.from_numpy(s).cuda() for s in seqs]
+    model.elbo_step(x, kl_weight=klw, eps=torch.from_numpy(eps).cuda())
+    torch.cuda.synchronize()
+    model._ws.fill_(0xFF)   # poison the workspace (bf16 / fp32 NaN patterns): nothing may depend on stale contents
     out = model.elbo_step(x, kl_weight=klw, eps=torch.from_numpy(eps).cuda())
     torch.cuda.synchronize()
     model.check_device_error()
@@ -356,3 +362,36 @@ def test_moses_sample_graph_replay_equals_direct_launch():
     assert model._sample_graph["handle"].value == handle              # same graph, fresh draws
     assert (a != b).float().mean().item() > 0.1
     model.destroy_sample_graph()
+
+
+@pytest.mark.parametrize("B,drop", [(2600, 0.0), (4096, 0.0), (4096, 0.2)])
+def test_moses_persistent_sweeps_equal_per_step_engine_large_batch(monkeypatch, B, drop):
+    """Batches of several 256-row tiles (per-tile step windows over the packed sequences, mirrored tile assignment at 16
+    tiles, K-split BPTT, token-table encoder): the persistent-kernel path against the per-step engine (MVAE_MOSES_REC=0,
+    itself held to the oracle above) on the same weights, batch, eps and dropout mask -- two bf16 paths, so loss terms
+    within 2e-3 and every gradient within 3e-2 relative L2."""
+    m = load_pkg()
+    P, seqs, eps, pad, model = _setup(m, "bf16", 321, 500 + B, B)
+    if drop > 0:
+        model.train()
+        model.decoder_rnn.dropout = drop
+        model.dropout_seed_override = 12345
+    x = [torch.from_numpy(s).cuda() for s in seqs]
+    epst = torch.from_numpy(eps).cuda()
+    res = {}
+    for rec in ("1", "0"):
+        monkeypatch.setenv("MVAE_MOSES_REC", rec)
+        for p in model.parameters():
+            p.grad = None
+        if getattr(model, "_ws", None) is not None:
+            model._ws.fill_(0xFF)   # poisoned workspace: regions the packed-sequence sweeps skip must never be read
+        out = model.elbo_step(x, kl_weight=0.1, eps=epst)
+        torch.cuda.synchronize()
+        model.check_device_error()
+        res[rec] = (out.cpu().numpy().copy(), {k: p.grad.detach().cpu().numpy().copy() for k, p in model.named_parameters()})
+    s1, g1 = res["1"]
+    s0, g0 = res["0"]
+    assert np.isfinite(s1).all() and all(np.isfinite(v).all() for v in g1.values())
+    assert abs(s1[1] - s0[1]) <= 2e-3 * abs(s0[1]) and abs(s1[2] - s0[2]) <= 2e-3 * abs(s0[2]) and s1[3] == s0[3], (s1, s0)
+    bad = {k: rel_l2(g1[k], g0[k]) for k in g0 if not rel_l2(g1[k], g0[k]) <= 3e-2}
+    assert not bad, bad
