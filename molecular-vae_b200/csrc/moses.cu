@@ -1000,6 +1000,41 @@ __global__ void init_state_kernel(const float* __restrict__ h0, int B, int Bp, i
   if (h32) h32[idx] = v;
 }
 
+// Layer 0 of the sampler as ONE K-concatenated contraction (no look-ups in the epilogue): operand row = [onehot(token) : 64 |
+// z : ZP | h : H], weights [TBL^T | W_ih[:, V:] | W_hh] in tiles of 64 units x 4 gate blocks (r and z summed over all three
+// parts, `in` from the input parts only, `hn` from the hidden part only).  TBL = x_emb . W_ih[:, :V]^T ([V][3H], fp32).
+__global__ void cell_weights_l0_kernel(const float* __restrict__ tbl, const float* __restrict__ wih, const float* __restrict__ whh,
+                                       const float* __restrict__ bih, const float* __restrict__ bhh, int H, int V, int Z, int ZP,
+                                       __nv_bfloat16* __restrict__ W, float* __restrict__ bias) {
+  const int K = 64 + ZP + H;
+  const long long total = 4ll * H * K;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % K);
+    const int n = (int)(i / K);
+    const int tile = n / 256, g = (n / 64) % 4, j = n % 64;
+    const int unit = tile * 64 + j;
+    const int gate = g < 2 ? g : 2;
+    float v = 0.f;
+    if (c < 64) { if (g != 3 && c < V) v = tbl[(long long)c * 3 * H + gate * H + unit]; }
+    else if (c < 64 + ZP) { if (g != 3 && c - 64 < Z) v = wih[((long long)gate * H + unit) * (V + Z) + V + (c - 64)]; }
+    else if (g != 2) v = whh[((long long)gate * H + unit) * H + (c - 64 - ZP)];
+    W[i] = __float2bfloat16_rn(v);
+    if (c == 0) bias[n] = g < 2 ? bih[g * H + unit] + bhh[g * H + unit] : (g == 2 ? bih[2 * H + unit] : bhh[2 * H + unit]);
+  }
+}
+// constant parts of the layer-0 operand rows: one-hot(bos) in columns [0,64) (buffer `oh` only) and z in [64, 64+ZP)
+__global__ void sample_l0_operand_kernel(const float* __restrict__ z, int B, int Bp, int Z, int ZP, long long ld, int bos,
+                                         __nv_bfloat16* __restrict__ buf0, __nv_bfloat16* __restrict__ buf1) {
+  const long long total = (long long)Bp * (64 + ZP);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % (64 + ZP)), b = (int)(i / (64 + ZP));
+    float v0 = 0.f, v1 = 0.f;
+    if (c >= 64) { if (b < B && c - 64 < Z) v0 = v1 = z[(long long)b * Z + (c - 64)]; }
+    else if (c == bos) v1 = 1.f;                       // the first step reads buffer 1
+    buf0[(long long)b * ld + c] = __float2bfloat16_rn(v0);
+    buf1[(long long)b * ld + c] = __float2bfloat16_rn(v1);
+  }
+}
 bool sample_fused_enabled() {
   const char* e = getenv("MVAE_SAMPLE_FUSED");
   return e ? atoi(e) != 0 : true;
@@ -1016,7 +1051,10 @@ int sample_fused(const MDims& d, const MWS& w, const float* const* P, const floa
   const int IN0 = V + Z;
   const MP ix{d.bidir, d.lin, L};
   RC(memset_async(w.err_flag, 4, st));
-  for (int l = 0; l < L; ++l) {
+  // layer 0 as one contraction over [onehot | z | h] when that operand fits the [x | h] buffers (64 + ZP <= Hd)
+  const int ZP = round_up(Z, 64), K0 = 64 + ZP + Hd;
+  const bool kcat = V <= 64 && 64 + ZP <= Hd && getenv("MVAE_SAMPLE_KCAT0") == nullptr;
+  for (int l = kcat ? 1 : 0; l < L; ++l) {
     cell_weights_kernel<<<grid_for((long long)(l ? 4 : 3) * Hd * (l ? 2 : 1) * Hd), 256, 0, st>>>(
         l ? P[ix.wih(l)] : nullptr, P[ix.whh(l)], l ? P[ix.bih(l)] : nullptr, P[ix.bhh(l)], Hd, l ? 4 : 3, (TA*)w.Wcat[l], w.bcat[l]);
     KCHECK();
@@ -1026,25 +1064,35 @@ int sample_fused(const MDims& d, const MWS& w, const float* const* P, const floa
   RC(memset_async(w.h0, (size_t)Bp * Hd * 4, st));
   RC(sg(st, z, Z, 1, P[ix.latw()], 1, Z, w.h0, Hd, B, Hd, Z, P[ix.latb()], simt::ACT_NONE, 0));
   RC(sg(st, P[ix.emb()], V, 1, P[ix.wih(0)], 1, IN0, w.TBLd, 3 * Hd, V, 3 * Hd, V, nullptr, simt::ACT_NONE, 0));
-  RC(sg(st, z, Z, 1, P[ix.wih(0)] + V, 1, IN0, w.zproj, 3 * Hd, B, 3 * Hd, Z, P[ix.bih(0)], simt::ACT_NONE, 0));
+  if (kcat) {
+    cell_weights_l0_kernel<<<grid_for(4ll * Hd * K0), 256, 0, st>>>(w.TBLd, P[ix.wih(0)], P[ix.whh(0)], P[ix.bih(0)], P[ix.bhh(0)], Hd, V, Z,
+                                                                   ZP, (TA*)w.Wcat[0], w.bcat[0]); KCHECK();
+  } else {
+    RC(sg(st, z, Z, 1, P[ix.wih(0)] + V, 1, IN0, w.zproj, 3 * Hd, B, 3 * Hd, Z, P[ix.bih(0)], simt::ACT_NONE, 0));
+  }
   const int sgrid = (int)ceil_div64((long long)Bp * Hd, 256);
+  const int h_off0 = kcat ? 64 + ZP : 0, ld0 = kcat ? K0 : Hd;   // where h sits in layer 0's operand rows
   for (int l = 0; l < L; ++l) {
-    // the first step (i = 1) reads parity 1; layer 0's operand is [h] (ld Hd), the others [x | h] (ld 2Hd, h in the right half)
+    // the first step (i = 1) reads parity 1; layer 0's operand is [h] (ld Hd) or [onehot | z | h] (ld K0), the others [x | h]
+    // (ld 2Hd, h in the right half)
     for (int k = 0; k < 2; ++k) RC(memset_async(w.xh[l][k], (size_t)Bp * 2 * Hd * 2, st));
-    init_state_kernel<<<sgrid, 256, 0, st>>>(w.h0, B, Bp, Hd, (TA*)w.xh[l][1] + (l ? Hd : 0), l ? 2 * Hd : Hd, w.hm[l][1]); KCHECK();
+    init_state_kernel<<<sgrid, 256, 0, st>>>(w.h0, B, Bp, Hd, (TA*)w.xh[l][1] + (l ? Hd : h_off0), l ? 2 * Hd : ld0, w.hm[l][1]); KCHECK();
+  }
+  if (kcat) {
+    sample_l0_operand_kernel<<<grid_for((long long)Bp * (64 + ZP)), 256, 0, st>>>(z, B, Bp, Z, ZP, K0, bos, (TA*)w.xh[0][0], (TA*)w.xh[0][1]); KCHECK();
   }
   sample_init_kernel<<<(unsigned)ceil_div64((long long)B * max_len, 256), 256, 0, st>>>(B, max_len, bos, d.pad, w_cur, ids_out, len_out, done); KCHECK();
   for (int i = 1; i < max_len; ++i) {
     const int cur = i & 1, nxt = cur ^ 1;
     for (int l = 0; l < L; ++l) {
-      const int G = l ? 4 : 3, K = l ? 2 * Hd : Hd;
+      const int G = (l || kcat) ? 4 : 3, K = l ? 2 * Hd : ld0;
       mvae_umma_operand a{w.xh[l][cur], 0, Bp, K, K, 1, 0, 0, 0};
       mvae_umma_operand b{w.Wcat[l], 0, (long long)G * Hd, K, K, 1, 0, 0, 0};
       mvae_umma_out o{w.logits, (long long)G * Hd, 0, 0, w.bcat[l], 0};
       mvae_umma_cell c{};
       c.gates = G; c.H = Hd; c.h_prev32 = w.hm[l][cur]; c.h_next32 = w.hm[l][nxt];
-      if (l == 0) { c.tbl = w.TBLd; c.add = w.zproj; c.tok = w_cur; c.tok_rows = B; }   // emb(w) | z through W_ih_l0: look-up + per-sequence part
-      c.out_a = (TA*)w.xh[l][nxt] + (l ? Hd : 0); c.ld_a = K;
+      if (l == 0 && !kcat) { c.tbl = w.TBLd; c.add = w.zproj; c.tok = w_cur; c.tok_rows = B; }   // emb(w) | z through W_ih_l0: look-up + per-sequence part
+      c.out_a = (TA*)w.xh[l][nxt] + (l ? Hd : h_off0); c.ld_a = K;
       c.out_b = (l + 1 < L) ? w.xh[l + 1][cur] : nullptr; c.ld_b = 2 * Hd;
       mvae_count_launches(1);
       RC(mvae_umma_gemm(&a, &b, &o, Bp, G * Hd, K, G * 64, 1, 0, w.err_flag, st, nullptr, &c));
@@ -1054,7 +1102,7 @@ int sample_fused(const MDims& d, const MWS& w, const float* const* P, const floa
     mvae_umma_operand a{top, 0, Bp, Hd, L > 1 ? 2 * Hd : Hd, 1, 0, 0, 0};
     mvae_umma_operand b{w.Wfc, 0, CP, Hd, Hd, 1, 0, 0, 0};
     mvae_umma_out o{w.logits, CP, 0, 0, w.bfc, 0};
-    mvae_umma_sample sp{V, B, i, max_len, eos, mode, 1.0f / temp, seed, seed_dev, w_cur, ids_out, len_out, done};
+    mvae_umma_sample sp{V, B, i, max_len, eos, mode, 1.0f / temp, seed, seed_dev, w_cur, kcat ? w.xh[0][nxt] : nullptr, K0, ids_out, len_out, done};
     mvae_count_launches(1);
     RC(mvae_umma_gemm(&a, &b, &o, Bp, CP, Hd, 64, 1, 0, w.err_flag, st, nullptr, nullptr, &sp));
   }

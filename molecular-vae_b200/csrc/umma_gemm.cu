@@ -485,6 +485,19 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 }
               }
               sp.w_cur[row] = (unsigned char)tok;
+              if (sp.onehot_next) {
+                uint4* oh = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(sp.onehot_next) + (long long)row * sp.oh_ld);
+#pragma unroll
+                for (int j8 = 0; j8 < 8; ++j8) {
+                  uint4 o = make_uint4(0u, 0u, 0u, 0u);
+                  if ((tok >> 3) == j8) {
+                    const uint32_t one = (tok & 1) ? 0x3F800000u : 0x00003F80u;   // bf16 1.0 in the high / low half
+                    const int w2 = (tok & 7) >> 1;
+                    o.x = w2 == 0 ? one : 0u; o.y = w2 == 1 ? one : 0u; o.z = w2 == 2 ? one : 0u; o.w = w2 == 3 ? one : 0u;
+                  }
+                  oh[j8] = o;
+                }
+              }
               if (!sp.done[row]) {
                 sp.x[(long long)row * sp.max_len + sp.step] = (unsigned char)tok;
                 if (tok == sp.eos) { sp.end[row] = sp.step + 1; sp.done[row] = 1; }

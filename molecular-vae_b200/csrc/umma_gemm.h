@@ -67,6 +67,8 @@ struct mvae_umma_sample {
   const unsigned long long* seed_dev;   // optional: read the seed from device memory (a captured CUDA graph can then be
                                         // replayed with fresh draws)
   unsigned char* w_cur;       // [B] token fed to the next step
+  void* onehot_next;          // optional: bf16 [rows][oh_ld], columns [0,64) of row b <- one-hot of the sampled token (the token
+  long long oh_ld;            // part of the next step's [onehot | z | h] layer-0 operand)
   unsigned char* x;           // [B][max_len]
   int* end;                   // [B]
   unsigned char* done;        // [B]
