@@ -195,8 +195,9 @@ typedef struct mvae_moses_desc {
   int32_t q_bidir;        /* 1: bidirectional encoder GRU (mosesfile.py:21-28), heads read cat(h_fwd, h_bwd) (:115-116) */
   int32_t q_linear_heads; /* 1: q_mu / q_logvar are single Linear(Hq*(1+bidir), d_z) (mosesfile.py:31-32); 0: the 2-layer MLPs */
   /* train-mode dropout between decoder GRU layers (nn.GRU(dropout=0.2), mosesvae.py:38,78): element (l, t, b, j) of the
-   * output of layer l < L-1 is kept iff u01(dropout_seed, l, t, b, j) >= d_dropout and scaled by 1/(1-d_dropout); the
-   * counter-based u01 is restated in oracle/moses_oracle.dropout_masks so a parity run can inject the same mask.  0 = off. */
+   * output of layer l < L-1 is kept iff u16(dropout_seed, l, t, b, j) >= d_dropout and scaled by 1/(1-d_dropout); the
+   * counter-based 16-bit uniform (one 64-bit hash per four consecutive units) is restated in
+   * oracle/moses_oracle.dropout_masks so a parity run can inject the same mask.  0 = off. */
   float d_dropout;
   uint32_t dropout_seed;
 } mvae_moses_desc;

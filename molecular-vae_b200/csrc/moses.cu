@@ -375,7 +375,7 @@ template <> __device__ __forceinline__ void store8<__nv_bfloat16>(__nv_bfloat16*
 }
 // counter-based uniform in (0,1): the same generator the sampler uses (restated in oracle/moses_oracle.u01_hash)
 __device__ __forceinline__ float u01_hash(unsigned long long seed, unsigned int b, unsigned int i);
-// dropout between decoder layers: element (t, b, j) of layer l is kept iff u01(seed + l, t*B + b, j) >= p.
+// dropout between decoder layers: element (t, b, j) of layer l is kept iff its 16-bit uniform (see the kernel) >= p.
 // mode 0: out = keep ? x / (1 - p) : 0 (forward copy);  mode 1: x *= keep / (1 - p) in place (backward)
 template <typename TA>
 __global__ void dropout_kernel(const TA* x, TA* out /* may alias x */, unsigned long long seed, float p, int B, int Bp,
@@ -394,15 +394,18 @@ __global__ void dropout_kernel(const TA* x, TA* out /* may alias x */, unsigned 
     else { cg = (int)(i % (unsigned)H8); b = (int)(i / (unsigned)H8); }
     float v[8];
     load8<TA>(xs + (size_t)i * 8, v);
-    // u01_hash(seed, t*B + b, j): the 64-bit counter advances by the golden-ratio constant from one unit to the next
-    unsigned long long c = seed + 0x9E3779B97F4A7C15ull * ((unsigned long long)(unsigned)(t * B + b) * 1000003ull + (unsigned)(cg * 8) + 1);
+    // one 64-bit hash (the generator of u01_hash with counter j / 4) serves four consecutive units, 16 bits each:
+    // keep(t, b, j) iff ((h >> 16 (j & 3)) & 0xFFFF + 0.5) / 65536 >= p      (restated in oracle/moses_oracle.dropout_masks)
+    unsigned long long c = seed + 0x9E3779B97F4A7C15ull * ((unsigned long long)(unsigned)(t * B + b) * 1000003ull + (unsigned)(cg * 2) + 1);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
+    for (int hq = 0; hq < 2; ++hq) {
       unsigned long long h = c;
       h ^= h >> 30; h *= 0xBF58476D1CE4E5B9ull; h ^= h >> 27; h *= 0x94D049BB133111EBull; h ^= h >> 31;
-      // (float)((h >> 40) + 0.5): the 24-bit integer is exact in fp32 and the single rounding of n + 0.5 is the same
-      const float u = __fadd_rn(__uint2float_rn((unsigned)(h >> 40)), 0.5f) * (1.0f / 16777216.0f);
-      v[k] = (b < B && u >= p) ? v[k] * sc : 0.f;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float u = ((float)((unsigned)(h >> (16 * k)) & 0xFFFFu) + 0.5f) * (1.0f / 65536.0f);
+        v[hq * 4 + k] = (b < B && u >= p) ? v[hq * 4 + k] * sc : 0.f;
+      }
       c += 0x9E3779B97F4A7C15ull;
     }
     store8<TA>(os + (size_t)i * 8, v);

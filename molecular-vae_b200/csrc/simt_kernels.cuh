@@ -226,13 +226,25 @@ __global__ void colsum_slabs_kernel(const T* __restrict__ x, int rps, long long 
   __shared__ float red[8][33];
   const int c = blockIdx.x * 32 + threadIdx.x;
   const int n = min(rps, __ldg(lim + blockIdx.y));
+  // blockIdx.z: chunk of the slab's rows (the active part of a slab is split over gridDim.z blocks)
+  const int per = (rps + gridDim.z - 1) / gridDim.z;
+  const int r0 = blockIdx.z * per, r1 = min(n, r0 + per);
   const T* xs = x + (long long)blockIdx.y * rps * ld;
-  float s = 0.f;
-  if (c < cols)
-    for (int r = threadIdx.y; r < n; r += 8) s += to_f32<T>(xs[(long long)r * ld + c]);
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  if (c < cols) {
+    int r = r0 + threadIdx.y;
+    for (; r + 24 < r1; r += 32) {      // four independent loads in flight per thread
+      s0 += to_f32<T>(xs[(long long)r * ld + c]);
+      s1 += to_f32<T>(xs[(long long)(r + 8) * ld + c]);
+      s2 += to_f32<T>(xs[(long long)(r + 16) * ld + c]);
+      s3 += to_f32<T>(xs[(long long)(r + 24) * ld + c]);
+    }
+    for (; r < r1; r += 8) s0 += to_f32<T>(xs[(long long)r * ld + c]);
+  }
+  const float s = (s0 + s1) + (s2 + s3);
   red[threadIdx.y][threadIdx.x] = s;
   __syncthreads();
-  if (threadIdx.y == 0 && c < cols && n > 0) {
+  if (threadIdx.y == 0 && c < cols && r1 > r0) {
     float t = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x];
@@ -243,7 +255,7 @@ template <typename T>
 inline int colsum(cudaStream_t st, const T* x, long long rows, long long ld, int cols, float* out_zeroed,
                   const int* lim = nullptr, int rps = 1) {
   if (lim) {
-    dim3 grid(ceil_div(cols, 32), (unsigned)(rows / rps));
+    dim3 grid(ceil_div(cols, 32), (unsigned)(rows / rps), (unsigned)(rps >= 1024 ? 8 : 1));
     colsum_slabs_kernel<T><<<grid, dim3(32, 8), 0, st>>>(x, rps, ld, cols, out_zeroed, lim);
   } else {
     const int rpb = 2048;

@@ -131,12 +131,26 @@ def u01_hash(seed, b, i):
     return ((x >> np.uint64(40)).astype(np.float64) + 0.5).astype(np.float32) * np.float32(1.0 / 16777216.0)
 
 
+def hash64(seed, b, i):
+    """The 64-bit value behind u01_hash (same counter construction and mixing)."""
+    M = np.uint64(0xFFFFFFFFFFFFFFFF)
+    with np.errstate(over="ignore"):
+        x = (np.uint64(seed) + np.uint64(0x9E3779B97F4A7C15) * (b.astype(np.uint64) * np.uint64(1000003) + i.astype(np.uint64) + np.uint64(1))) & M
+        x ^= x >> np.uint64(30); x = (x * np.uint64(0xBF58476D1CE4E5B9)) & M
+        x ^= x >> np.uint64(27); x = (x * np.uint64(0x94D049BB133111EB)) & M
+        x ^= x >> np.uint64(31)
+    return x
+
+
 def dropout_masks(seed, p, B, T, H, d_layers=3, dtype=np.float64):
-    """Scaled keep masks (B,T,H) for the outputs of decoder layers 0..L-2: include/mvae_b200.h (mvae_moses_desc.d_dropout)."""
+    """Scaled keep masks (B,T,H) for the outputs of decoder layers 0..L-2: include/mvae_b200.h (mvae_moses_desc.d_dropout).
+    One 64-bit hash with counter j // 4 serves four consecutive hidden units, 16 bits each (dropout_kernel in moses.cu)."""
     t, b, j = np.meshgrid(np.arange(T), np.arange(B), np.arange(H), indexing="ij")
     out = []
     for l in range(d_layers - 1):
-        u = u01_hash(seed + l, (t * B + b).astype(np.uint64), j.astype(np.uint64))
+        h = hash64(seed + l, (t * B + b).astype(np.uint64), (j // 4).astype(np.uint64))
+        u16 = (h >> (np.uint64(16) * (j % 4).astype(np.uint64))) & np.uint64(0xFFFF)
+        u = (u16.astype(np.float32) + np.float32(0.5)) * np.float32(1.0 / 65536.0)
         out.append(((u >= np.float32(p)).astype(dtype) / (1.0 - p)).transpose(1, 0, 2))
     return out
 

@@ -150,7 +150,7 @@ def test_moses_train_mode_dropout_with_injected_mask(precision, B, ltol, gtol):
                         drop_masks=masks)
     ref0 = mo.moses_step({k: v.astype(np.float64) for k, v in P.items()}, seqs, eps.astype(np.float64), pad, kl_weight=0.3,
                          need_grads=False)
-    assert abs(ref["recon"] - ref0["recon"]) > 1e-4 * abs(ref0["recon"])          # the mask does something
+    assert abs(ref["recon"] - ref0["recon"]) > 2e-5 * abs(ref0["recon"])          # the mask does something
     out = model.elbo_step([torch.from_numpy(s).cuda() for s in seqs], kl_weight=0.3, eps=torch.from_numpy(eps).cuda())
     torch.cuda.synchronize()
     model.check_device_error()
