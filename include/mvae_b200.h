@@ -274,6 +274,15 @@ int mvae_ids_to_text(const uint8_t* ids, const int32_t* lengths, int B, int L, c
                      const uint8_t* tok_len, int rem_first_id, int rem_last_id, int strip, uint8_t* out_bytes,
                      long long capacity, int32_t* out_offsets, int32_t* scratch_row_len, mvae_stream_t stream);
 
+/* ---- input featurisation on the device (featurizer.py:8-24 OneHotFeaturizer.featurize,
+ * data_loader.py:26-31): `text` holds the B strings back to back (bytes), row b = text[offsets[b] .. offsets[b+1]);
+ * lut u8[256] maps a byte to its charset index (255 = not in the charset).  ids_out u8 (B,T): the string's ids, then pad_id
+ * (the charset index of ' ', i.e. ljust(T), featurizer.py:19-20).  bad_flag (device int32): bit 0 = a character outside
+ * the charset (featurizer.py:17 raises ValueError there), bit 1 = a string longer than T.  The model entry points take
+ * these ids directly, so the (B,T,C) one-hot never exists on the host or crosses PCIe.                                   */
+int mvae_text_to_ids(const uint8_t* text, const int32_t* offsets, int B, int T, const uint8_t* lut, int pad_id,
+                     uint8_t* ids_out, int32_t* bad_flag, mvae_stream_t stream);
+
 /* ---- optimiser step on flat fp32 buffers (train.py:102-104, train_distributed.py:91-94) ------------------
  * Global-norm clipping = torch.nn.utils.clip_grad_norm(params, max_norm) over ONE flat gradient buffer (the layout
  * molecular-vae_b200/ddp.py uses); the clip coefficient min(1, max_norm/(norm+1e-6)) stays on the device at

@@ -7,6 +7,6 @@ Public surface (mirrors the reference's Python contract for this path, SURVEY.md
   _lib.lib                                the ctypes handle of the C ABI (include/mvae_b200.h)
 Importing this package requires the built CUDA library; there is no CPU fallback.
 """
-from . import _lib, checkpoint, ddp, engine, models, models2d, mosesfile, mosesvae, optim, text  # noqa: F401
+from . import _lib, checkpoint, ddp, engine, featurizer, models, models2d, mosesfile, mosesvae, optim, text  # noqa: F401
 from .engine import CfgBEngine, param_order  # noqa: F401
 from .models2d import VAE, loss_function  # noqa: F401

@@ -92,6 +92,7 @@ def _load():
                                     vp, ctypes.c_size_t, vp]),
         "mvae_moses_sample_graph_create": (i32, [ctypes.POINTER(MosesDesc), pp, vp, i32, i32, i32, ctypes.c_float, vp, vp, vp,
                                                  vp, ctypes.c_size_t, ctypes.POINTER(vp)]),
+        "mvae_text_to_ids": (i32, [vp, vp, i32, i32, vp, i32, vp, vp, vp]),
         "mvae_moses_read_error": (i32, [ctypes.POINTER(MosesDesc), vp, ctypes.c_size_t, ctypes.POINTER(i32), vp]),
         "mvae_binding_workspace_bytes": (ctypes.c_size_t, [ctypes.POINTER(BindingDesc)]),
         "mvae_binding_forward": (i32, [ctypes.POINTER(BindingDesc), pp, pp, vp, vp, vp, ctypes.c_size_t, vp]),
@@ -121,7 +122,7 @@ EXPORTED = [
     "mvae_clip_grad_norm", "mvae_adam_step", "mvae_sgd_momentum_step",
     "mvae_cfga_workspace_bytes", "mvae_cfga_elbo_step", "mvae_cfga_elbo_step_graph_create", "mvae_cfga_forward",
     "mvae_cfga_backward", "mvae_cfga_decode", "mvae_cfga_read_error",
-    "mvae_ids_to_text", "mvae_binding_workspace_bytes", "mvae_binding_forward", "mvae_binding_backward",
+    "mvae_ids_to_text", "mvae_text_to_ids", "mvae_binding_workspace_bytes", "mvae_binding_forward", "mvae_binding_backward",
     "mvae_moses_workspace_bytes", "mvae_moses_step", "mvae_moses_sample", "mvae_moses_sample_graph_create", "mvae_moses_read_error",
 ]
 

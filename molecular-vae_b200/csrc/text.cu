@@ -77,6 +77,24 @@ __global__ void text_write_kernel(const uint8_t* __restrict__ ids, const int* __
   }
 }
 
+// ---- featurisation (featurizer.py:8-24, data_loader.py:26-31): packed SMILES bytes -> u8 ids (B,T), right-padded ----
+// one thread per output position; a character without an id (lut == 255) or a string longer than T raises bad_flag
+__global__ void text_to_ids_kernel(const uint8_t* __restrict__ text, const int* __restrict__ offsets, int B, int T,
+                                   const uint8_t* __restrict__ lut, int pad_id, uint8_t* __restrict__ ids,
+                                   int* __restrict__ bad_flag) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= (long long)B * T) return;
+  const int b = (int)(i / T), t = (int)(i - (long long)b * T);
+  const int o0 = offsets[b], n = offsets[b + 1] - o0;
+  if (t == 0 && n > T) atomicOr(bad_flag, 2);
+  int id = pad_id;
+  if (t < n) {
+    id = lut[text[o0 + t]];
+    if (id == 255) { atomicOr(bad_flag, 1); id = pad_id; }
+  }
+  ids[i] = (uint8_t)id;
+}
+
 }  // namespace
 
 extern "C" int mvae_ids_to_text(const uint8_t* ids, const int32_t* lengths, int B, int L, const uint8_t* table, int tok_stride,
@@ -91,5 +109,15 @@ extern "C" int mvae_ids_to_text(const uint8_t* ids, const int32_t* lengths, int 
   text_scan_kernel<<<1, 1024, 0, st>>>(scratch_row_len, B, out_offsets); KCHECK();
   text_write_kernel<<<ceil_div(B, 128), 128, 0, st>>>(ids, lengths, B, L, rem_first_id, rem_last_id, strip, table, tok_stride,
                                                       tok_len, out_offsets, capacity, out_bytes); KCHECK();
+  return MVAE_OK;
+}
+
+extern "C" int mvae_text_to_ids(const uint8_t* text, const int32_t* offsets, int B, int T, const uint8_t* lut, int pad_id,
+                                uint8_t* ids_out, int32_t* bad_flag, mvae_stream_t stream) {
+  if (!text || !offsets || !lut || !ids_out || !bad_flag || B <= 0 || T <= 0 || pad_id < 0 || pad_id > 254) return MVAE_ERR_INVALID;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  mvae_count_launches(1);
+  MVAE_CUDA_CHECK(cudaMemsetAsync(bad_flag, 0, 4, st));
+  text_to_ids_kernel<<<(unsigned)ceil_div64((long long)B * T, 256), 256, 0, st>>>(text, offsets, B, T, lut, pad_id, ids_out, bad_flag); KCHECK();
   return MVAE_OK;
 }
