@@ -193,6 +193,44 @@ def sampling_rate(batch=8192, max_len=100, reps=3):
             "workload": "mosesvae.VAE.sample device path (3x512 GRU decoder, d_z 160, V=34), bf16, random-init weights"}
 
 
+def moses_step_rate(batch=4096, reps=5):
+    """Side measurement for BASELINE.json configs[3] on ONE GPU: fused fwd+bwd step of mosesvae.VAE (encoder GRU 256, d_z 160,
+    decoder GRU 3x512, V=34; SURVEY.md 8d config 4 inputs: lengths ~ clip(N(44,9),10,98) + bos/eos, sorted descending), bf16,
+    train mode (dropout 0.2), batch 4096, CUDA-graph replay of the step over resident inputs, CUDA events."""
+    import numpy as np
+    import torch
+    import molecular_vae_b200 as m
+    torch.manual_seed(0)
+    rng = np.random.Generator(np.random.PCG64(1))
+    lens = np.sort(np.clip(np.rint(rng.normal(44.0, 9.0, size=batch)), 10, 98).astype(np.int64))[::-1]
+    x = [torch.from_numpy(np.concatenate([[30], rng.integers(0, 30, size=int(l)), [31]]).astype(np.int64)).cuda() for l in lens]
+    model = m.mosesvae.VAE(_BenchVocab(), precision="bf16").cuda()
+    eps = torch.randn(batch, 160, device="cuda")
+    model.elbo_step(x, kl_weight=0.1, eps=eps)
+    torch.cuda.synchronize()
+    model.check_device_error()
+    _, ids_p, lens_p = model._pack(x)
+    params = model.ordered_params()
+    P, G = [p.data for p in params], [p.grad for p in params]
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        model._run(P, G, ids_p, lens_p, eps, 0.1, 1.0, False, dropout=(0.2, 1234))
+    g.replay()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        g.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    model.check_device_error()
+    ms = e0.elapsed_time(e1) / reps
+    tokens = int(sum(int(l) + 2 for l in lens))
+    return {"metric": "train molecules/sec (fwd+bwd, mosesvae.VAE)", "value": batch / ms * 1e3, "unit": "molecules/s", "ms_per_step": ms,
+            "batch": batch, "mean_len": tokens / batch, "max_len": int(lens[0]) + 2, "loss": float(model._last_scalars[0].item()),
+            "workload": "mosesvae.VAE fused step (packed sequences, train-mode dropout 0.2), bf16, random-init weights, one GPU"}
+
+
 def rec_kernel_times(model, eng, params, ids_dev, eps_dev, steps=3):
     """Average launch duration of the persistent recurrence kernels, CUDA events on the launching stream, measured on
     DIRECT launches of the same fused step right after the timed region (a graph replay cannot carry events)."""
@@ -408,6 +446,11 @@ def run_ours(args):
                                     "sample": "2 timed steps of 250 molecules (BASELINE config[0] batch) after 1 "
                                               "warm-up, fp32 numpy port oracle/vae_oracle.py, BLAS on all cores"}
         line["sampling"] = sampling
+        if world == 1:
+            try:
+                line["moses_step"] = moses_step_rate()
+            except Exception as ex:
+                line["moses_step"] = {"error": repr(ex)}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
