@@ -849,7 +849,9 @@ int step_t(const MDims& d, const MWS& w, const float* const* P, float* const* G,
   //   dW_ih[:, :V] = dTBL_rzn^T(3Hd x V) * E (V x V)
   RC(sg(st, w.dWT, V, 1, P[ix.emb()], V, 1, G[ix.wih(0)], IN0, 3 * Hd, V, V, nullptr, simt::ACT_NONE, 0));
   //   dE = dTBL_rzn (V x 3Hd) * W_ih[:, :V] (3Hd x V)
-  RC(sg(st, w.dWT, 1, V, P[ix.wih(0)], IN0, 1, G[ix.emb()], V, V, V, 3 * Hd, nullptr, simt::ACT_NONE, 0));
+  //   (a V x V output with K = 3Hd: split-K over 24 blocks instead of one block walking the whole contraction)
+  RC(memset_async(G[ix.emb()], (size_t)V * V * 4, st));
+  RC(sg(st, w.dWT, 1, V, P[ix.wih(0)], IN0, 1, G[ix.emb()], V, V, V, 3 * Hd, nullptr, simt::ACT_NONE, 1, 24));
   //   dW_ih[:, V:] = dgisum^T * z ; dz = dgisum * W_ih[:, V:]
   RC(sg_wgrad(st, w.dgisum, 1, 3 * Hd, w.z, Z, 1, G[ix.wih(0)] + V, IN0, 3 * Hd, Z, B));
   RC(sg(st, w.dgisum, 3 * Hd, 1, P[ix.wih(0)] + V, IN0, 1, w.dz, Z, B, Z, 3 * Hd, nullptr, simt::ACT_NONE, 0));
@@ -928,7 +930,7 @@ int step_t(const MDims& d, const MWS& w, const float* const* P, float* const* G,
                 d.bf16 ? 24 : 64, 256, rev ? nullptr : VLK));
     tbl_grad_to_rzn_T_kernel<<<(unsigned)ceil_div64(3ll * Hq * V, 256), 256, 0, st>>>(w.dTBL, Hq, V, w.dWT); KCHECK();
     RC(sg(st, w.dWT, V, 1, P[ix.emb()], V, 1, G[ix.e_wih(rev)], V, 3 * Hq, V, V, nullptr, simt::ACT_NONE, 0));
-    RC(sg(st, w.dWT, 1, V, P[ix.e_wih(rev)], V, 1, G[ix.emb()], V, V, V, 3 * Hq, nullptr, simt::ACT_NONE, 1));   // accumulate onto the decoder part
+    RC(sg(st, w.dWT, 1, V, P[ix.e_wih(rev)], V, 1, G[ix.emb()], V, V, V, 3 * Hq, nullptr, simt::ACT_NONE, 1, 24));   // accumulate onto the decoder part
   }
   if (d.pad >= 0 && d.pad < V) {   // nn.Embedding(padding_idx = pad): the pad row receives no gradient
     zero_row_kernel<<<1, 64, 0, st>>>(G[ix.emb()], d.pad, V); KCHECK();
