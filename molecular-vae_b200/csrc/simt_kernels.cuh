@@ -38,8 +38,8 @@ struct SgemmArgs {
 };
 
 __global__ void __launch_bounds__(256) sgemm_kernel(const SgemmArgs a) {
-  __shared__ float As[16][64 + 4];
-  __shared__ float Bs[16][64 + 4];
+  __shared__ __align__(16) float As[16][64 + 4];
+  __shared__ __align__(16) float Bs[16][64 + 4];
   const int tid = threadIdx.x;
   const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
   const int kbeg = blockIdx.z * a.k_per_split;
@@ -52,19 +52,46 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const SgemmArgs a) {
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
   const bool a_kfast = (a.sak == 1);
   const bool b_kfast = (a.sbk == 1);
+  // 16-byte loads along the contiguous dimension for full, aligned tiles (k-fast: 4 consecutive k of one row; otherwise 4
+  // consecutive rows / columns of one k); edge tiles and odd strides take the scalar path below
+  const bool a_vec = ((reinterpret_cast<uintptr_t>(a.A) & 15) == 0) && m0 + 64 <= a.M &&
+                     (a_kfast ? (a.sam % 4 == 0) : (a.sam == 1 && a.sak % 4 == 0));
+  const bool b_vec = ((reinterpret_cast<uintptr_t>(a.B) & 15) == 0) && n0 + 64 <= a.N &&
+                     (b_kfast ? (a.sbn % 4 == 0) : (a.sbn == 1 && a.sbk % 4 == 0));
   for (int k0 = kbeg; k0 < kend; k0 += 16) {
+    const bool kfull = k0 + 16 <= kend;
+    if (a_vec && kfull) {
+      if (a_kfast) {
+        const int m = tid >> 2, k4 = (tid & 3) * 4;
+        const float4 v = __ldg(reinterpret_cast<const float4*>(a.A + (long long)(m0 + m) * a.sam + (k0 + k4)));
+        As[k4][m] = v.x; As[k4 + 1][m] = v.y; As[k4 + 2][m] = v.z; As[k4 + 3][m] = v.w;
+      } else {
+        const int k = tid >> 4, m4 = (tid & 15) * 4;
+        *reinterpret_cast<float4*>(&As[k][m4]) = __ldg(reinterpret_cast<const float4*>(a.A + (m0 + m4) + (long long)(k0 + k) * a.sak));
+      }
+    }
+    if (b_vec && kfull) {
+      if (b_kfast) {
+        const int n = tid >> 2, k4 = (tid & 3) * 4;
+        const float4 v = __ldg(reinterpret_cast<const float4*>(a.B + (long long)(n0 + n) * a.sbn + (k0 + k4)));
+        Bs[k4][n] = v.x; Bs[k4 + 1][n] = v.y; Bs[k4 + 2][n] = v.z; Bs[k4 + 3][n] = v.w;
+      } else {
+        const int k = tid >> 4, n4 = (tid & 15) * 4;
+        *reinterpret_cast<float4*>(&Bs[k][n4]) = __ldg(reinterpret_cast<const float4*>(a.B + (n0 + n4) + (long long)(k0 + k) * a.sbk));
+      }
+    }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       int m, k;
       if (a_kfast) { k = tid & 15; m = (tid >> 4) + 16 * i; }
       else { m = tid & 63; k = (tid >> 6) + 4 * i; }
       const int gm = m0 + m, gk = k0 + k;
-      As[k][m] = (gm < a.M && gk < kend) ? __ldg(a.A + gm * a.sam + gk * a.sak) : 0.f;
+      if (!(a_vec && kfull)) As[k][m] = (gm < a.M && gk < kend) ? __ldg(a.A + gm * a.sam + gk * a.sak) : 0.f;
       int n, kk;
       if (b_kfast) { kk = tid & 15; n = (tid >> 4) + 16 * i; }
       else { n = tid & 63; kk = (tid >> 6) + 4 * i; }
       const int gn = n0 + n, gk2 = k0 + kk;
-      Bs[kk][n] = (gn < a.N && gk2 < kend) ? __ldg(a.B + gk2 * a.sbk + gn * a.sbn) : 0.f;
+      if (!(b_vec && kfull)) Bs[kk][n] = (gn < a.N && gk2 < kend) ? __ldg(a.B + gk2 * a.sbk + gn * a.sbn) : 0.f;
     }
     __syncthreads();
 #pragma unroll
@@ -258,7 +285,7 @@ inline int colsum(cudaStream_t st, const T* x, long long rows, long long ld, int
     dim3 grid(ceil_div(cols, 32), (unsigned)(rows / rps), (unsigned)(rps >= 1024 ? 8 : 1));
     colsum_slabs_kernel<T><<<grid, dim3(32, 8), 0, st>>>(x, rps, ld, cols, out_zeroed, lim);
   } else {
-    const int rpb = 2048;
+    const int rpb = rows >= 65536 ? 2048 : 256;   // small inputs (per-molecule bias sums): enough blocks to fill the GPU
     dim3 grid(ceil_div(cols, 32), (unsigned)ceil_div64(rows, rpb));
     colsum_kernel<T><<<grid, dim3(32, 8), 0, st>>>(x, rows, ld, cols, out_zeroed, rpb);
   }
