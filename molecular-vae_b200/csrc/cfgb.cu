@@ -743,11 +743,8 @@ int run_backward(const Dims& d, const WS& w, const float* const* P, float* const
     simt::ConvDims cd{T, d.C, d.L1, d.L2, d.L3};
     const size_t smem = (size_t)(9 * T * 9 + 729 + 990 + 32 + 729 + 990 + 9 * d.L1 + 9 * d.L2 + 10 * d.L3 + 9 * d.L2 +
                                  9 * d.L1) * 4 + round_up(T, 4);
-    static bool attr = false;
-    if (!attr) {
-      MVAE_CUDA_CHECK(cudaFuncSetAttribute(simt::enc_conv_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-      attr = true;
-    }
+    static size_t attr_cache[64] = {0};
+    MVAE_CUDA_CHECK(mvae_ensure_dyn_smem(reinterpret_cast<const void*>(simt::enc_conv_bwd_kernel), 100 * 1024, attr_cache));
     if (smem > 100 * 1024) return MVAE_ERR_UNSUPPORTED;
     simt::enc_conv_bwd_kernel<<<min(B, 148 * 2), 256, smem, st>>>(ids, B, cd, P[P_C2W], P[P_C3W], w.h1, w.h2, w.h3,
                                                                    w.dflat, G[P_C1W], G[P_C1B], G[P_C2W], G[P_C2B],

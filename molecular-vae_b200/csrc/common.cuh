@@ -28,6 +28,20 @@
 extern "C" void mvae_set_last_cuda_error(int code, const char* file, int line);
 
 static inline __host__ __device__ int ceil_div(int a, int b) { return (a + b - 1) / b; }
+// Opt-in dynamic shared memory is a PER-DEVICE function attribute: cache what has been set per device, so that one process
+// driving several GPUs (nn.DataParallel threads, train_distributed.py:72) configures the kernel on each of them.
+static inline cudaError_t mvae_ensure_dyn_smem(const void* kernel, size_t bytes, size_t* per_device_cache /* [64] */) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  dev &= 63;
+  if (bytes > per_device_cache[dev]) {
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return e;
+    per_device_cache[dev] = bytes;
+  }
+  return cudaSuccess;
+}
 static inline __host__ __device__ int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 static inline __host__ __device__ int round_up(int a, int b) { return ceil_div(a, b) * b; }
 

@@ -359,11 +359,8 @@ int launch_t(const mvae_gru_rec_args& a, cudaStream_t st) {
   p.gi = a.gi; p.gi_tstride = a.gi_tstride; p.bhh = a.bhh; p.hs = a.hs; p.sv = a.sv; p.dX = a.dX; p.dG = a.dG;
   p.counters = a.counters; p.err_flag = a.err_flag; p.trace = a.trace;
   auto kern = gru_rec_kernel<RU, NTILES, STAGES, BWD>;
-  static bool attr = false;
-  if (!attr) {
-    MVAE_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = true;
-  }
+  static size_t attr_cache[64] = {0};
+  MVAE_CUDA_CHECK(mvae_ensure_dyn_smem(reinterpret_cast<const void*>(kern), smem, attr_cache));
   dim3 grid(Hp / RU, ceil_div(Bp / 128, NTILES));
   MVAE_CUDA_CHECK(cudaMemsetAsync(a.counters, 0, sizeof(unsigned int) * (Bp / 128), st));
   void* args[3] = {(void*)&tmW, (void*)&tmA, (void*)&p};

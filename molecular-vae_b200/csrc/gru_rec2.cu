@@ -762,11 +762,8 @@ int launch2(const mvae_gru_rec_args& a, cudaStream_t st) {
   p.tbl = use_tbl ? a.tbl : nullptr; p.tok = use_tbl ? a.tok : nullptr; p.V = use_tbl ? a.V : 0;
   p.lens = BWD ? nullptr : a.lens; p.hlast = (BWD || !a.lens) ? nullptr : a.hlast; p.nrows = a.nrows;
   auto kern = gru_rec2_kernel<BWD, FAST, CL, KS, IN, VL>;
-  static size_t attr_smem = 0;
-  if (smem > attr_smem) {
-    MVAE_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_smem = smem;
-  }
+  static size_t attr_cache[64] = {0};
+  MVAE_CUDA_CHECK(mvae_ensure_dyn_smem(reinterpret_cast<const void*>(kern), smem, attr_cache));
   MVAE_CUDA_CHECK(cudaMemsetAsync(a.counters, 0, sizeof(unsigned int) * 2 * (Bp / 256), st));
   cudaLaunchConfig_t cfg{};
   // one row tile per pair when every CTA is co-resident anyway (small hidden sizes): twice the SMs, half the chain per step

@@ -783,11 +783,8 @@ int make_map(CUtensorMap* map, const mvae_umma_operand& op, int box_rows) {
 template <int BN, int A_MN, int B_MN>
 int launch_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const KernelParams& kp, int grid, cudaStream_t st) {
   auto kern = umma_gemm_kernel<BN, A_MN, B_MN>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    MVAE_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM_BYTES));
-    attr_set = true;
-  }
+  static size_t attr_cache[64] = {0};
+  MVAE_CUDA_CHECK(mvae_ensure_dyn_smem(reinterpret_cast<const void*>(kern), Cfg<BN>::SMEM_BYTES, attr_cache));
   kern<<<grid, NUM_THREADS, Cfg<BN>::SMEM_BYTES, st>>>(tmA, tmB, kp);
   MVAE_CUDA_CHECK(cudaGetLastError());
   return MVAE_OK;
