@@ -278,10 +278,6 @@ __global__ void pad_gate_matrix_T_kernel(const float* __restrict__ src, int H, _
     dst[idx] = __float2bfloat16_rn(v);
   }
 }
-__global__ void f32_to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long n) {
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-    dst[i] = __float2bfloat16_rn(src[i]);
-}
 // layer 0: sum over time of the dgi window of dG ([T][Bp][4Hp], blocks n,r,z) -> fp32 [Bp][3Hp] in (r,z,n) order
 __global__ void dgi_time_sum_kernel(const __nv_bfloat16* __restrict__ dG, int T, int Bp, int Hp,
                                     float* __restrict__ out, __nv_bfloat16* __restrict__ out_bf = nullptr) {

@@ -1,9 +1,7 @@
 #include "common.cuh"
 #include <stdio.h>
-static int g_last_code = 0;
 static char g_last_msg[512] = "";
 extern "C" void mvae_set_last_cuda_error(int code, const char* file, int line) {
-  g_last_code = code;
   snprintf(g_last_msg, sizeof(g_last_msg), "%s:%d: %s (%d)", file, line, cudaGetErrorString((cudaError_t)code), code);
 }
 extern "C" const char* mvae_last_cuda_error(void) { return g_last_msg; }

@@ -38,7 +38,6 @@ constexpr int CTRL_WARPS = 4;
 constexpr int THREADS = (CTRL_WARPS + EPI_WARPS) * 32;
 constexpr int PUB_WARP = 2;
 constexpr int CTRL_REGS = 32, EPI_REGS = 112;   // (96 - 32) * 128 released >= (112 - 96) * 512 claimed
-constexpr int EPI_BAR = 1;
 
 struct Params2 {
   int Bp, Hp, T, pair_tiles, npairs;
