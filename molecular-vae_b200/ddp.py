@@ -79,3 +79,28 @@ def shard_rows(n_rows, rank, world):
     base, rem = divmod(n_rows, world)
     lo = rank * base + min(rank, rem)
     return lo, lo + base + (1 if rank < rem else 0)
+
+
+def shard_sorted(seqs, rank, world):
+    """Shard of a length-sorted list of sequences (the pack_sequence contract of mosesvae.py:151): every world-th sequence,
+    so each shard stays sorted and the shards' length distributions (= work) match."""
+    return list(seqs[rank::world])
+
+
+def moses_rank_weights(n_sequences, n_targets, group=None):
+    """Per-rank scales (kl_scale, recon_scale) for the MOSES VAE step under data parallelism: the reference
+    computes KL as a mean over the GLOBAL batch (mosesvae.py:162) and the reconstruction CE as a mean over the GLOBAL count of
+    non-pad targets (mosesvae.py:193-197).  With rank r holding B_r sequences and M_r targets,
+        kl_global = sum_r (B_r / B) kl_r,   recon_global = sum_r (M_r / M) recon_r,
+    so a step run with kl_weight * kl_scale and recon_weight * recon_scale, followed by the usual gradient all-reduce MEAN over
+    the N ranks, yields exactly the full-batch gradient: kl_scale = N B_r / B, recon_scale = N M_r / M (both 1 for equal
+    shards with equal target counts).  Two scalars are all-reduced; the tensors stay on the host."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return 1.0, 1.0
+    world = dist.get_world_size(group)
+    t = torch.tensor([float(n_sequences), float(n_targets)], dtype=torch.float64)
+    if dist.get_backend(group) == "nccl":
+        t = t.cuda()
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    tot_b, tot_m = (float(v) for v in t.cpu())
+    return world * float(n_sequences) / tot_b, world * float(n_targets) / tot_m

@@ -90,3 +90,41 @@ def test_shard_rows_cover_batch():
         spans = [shard_rows(n, r, w) for r in range(w)]
         assert spans[0][0] == 0 and spans[-1][1] == n
         assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
+
+
+# ---- MOSES VAE under data parallelism: global token-mean CE and global batch-mean KL ----
+def _moses_worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from molecular_vae_b200.ddp import FlatGradBuffer, moses_rank_weights
+    from oracle import moses_oracle as mo
+    P = mo.make_moses_params(5, dtype=np.float64)
+    seqs, eps, pad = mo.make_moses_batch(6, 7, dtype=np.float64)
+    # deliberately unequal shards (4 + 3 sequences, different target counts): rows rank::world keep each shard sorted
+    mine, eps_mine = seqs[rank::world], eps[rank::world]
+    n_tgt = sum(len(s) - 1 for s in mine)
+    ks, rs = moses_rank_weights(len(mine), n_tgt)
+    klw = 0.3
+    r = mo.moses_step(P, mine, eps_mine, pad, kl_weight=klw * ks / rs)     # grads of (klw ks kl + rs recon) = rs * these
+    keys = sorted(r["grads"].keys())
+    params = [torch.nn.Parameter(torch.from_numpy(np.asarray(P[k])).clone()) for k in keys]
+    buf = FlatGradBuffer(params)
+    for p, k in zip(params, keys):
+        p.grad.copy_(torch.from_numpy(rs * r["grads"][k]))
+    buf.allreduce_mean()
+    if rank == 0:
+        np.savez(os.path.join(out_dir, "moses_ddp.npz"), **{k: p.grad.numpy() for k, p in zip(keys, params)})
+    dist.destroy_process_group()
+
+
+def test_moses_rank_weights_reproduce_full_batch_gradients(tmp_path):
+    from oracle import moses_oracle as mo
+    world = 2
+    mp.spawn(_moses_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    got = np.load(os.path.join(str(tmp_path), "moses_ddp.npz"))
+    P = mo.make_moses_params(5, dtype=np.float64)
+    seqs, eps, pad = mo.make_moses_batch(6, 7, dtype=np.float64)
+    full = mo.moses_step(P, seqs, eps, pad, kl_weight=0.3)
+    for k, g in full["grads"].items():
+        np.testing.assert_allclose(got[k], g, rtol=1e-8, atol=1e-11)
