@@ -278,12 +278,58 @@ __global__ void colsum_slabs_kernel(const T* __restrict__ x, int rps, long long 
     atomicAdd(out + c, t);
   }
 }
+// bf16 fast path of the slab-wise column sums: 16-byte loads (one thread = 8 consecutive columns, a warp = 256 columns of one
+// row), 8 row lanes per block, four rows in flight per thread.  cols % 256 == 0, ld % 8 == 0, x 16-byte aligned.
+__global__ void __launch_bounds__(256) colsum_slabs_bf16x8_kernel(const __nv_bfloat16* __restrict__ x, int rps, long long ld, int cols,
+                                                                   float* __restrict__ out, const int* __restrict__ lim) {
+  __shared__ float red[8][256 + 8];
+  const int lane = threadIdx.x & 31, wy = threadIdx.x >> 5;
+  const int c8 = blockIdx.x * 256 + lane * 8;
+  const int n = min(rps, __ldg(lim + blockIdx.y));
+  const int per = (rps + gridDim.z - 1) / gridDim.z;
+  const int r0 = blockIdx.z * per, r1 = min(n, r0 + per);
+  if (r1 <= r0) return;                                        // uniform over the block
+  const __nv_bfloat16* xs = x + (long long)blockIdx.y * rps * ld + c8;
+  float s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  auto add = [&](const uint4& v) {
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { s[2 * k] += __uint_as_float(w[k] << 16); s[2 * k + 1] += __uint_as_float(w[k] & 0xFFFF0000u); }
+  };
+  int r = r0 + wy;
+  for (; r + 24 < r1; r += 32) {
+    const uint4 a = __ldg(reinterpret_cast<const uint4*>(xs + (long long)r * ld));
+    const uint4 b = __ldg(reinterpret_cast<const uint4*>(xs + (long long)(r + 8) * ld));
+    const uint4 c = __ldg(reinterpret_cast<const uint4*>(xs + (long long)(r + 16) * ld));
+    const uint4 d = __ldg(reinterpret_cast<const uint4*>(xs + (long long)(r + 24) * ld));
+    add(a); add(b); add(c); add(d);
+  }
+  for (; r < r1; r += 8) add(__ldg(reinterpret_cast<const uint4*>(xs + (long long)r * ld)));
+#pragma unroll
+  for (int k = 0; k < 8; ++k) red[wy][lane * 8 + k] = s[k];
+  __syncthreads();
+  const int c = threadIdx.x;                                   // 256 threads -> 256 columns of the block
+  float t = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) t += red[i][c];
+  atomicAdd(out + blockIdx.x * 256 + c, t);
+}
 template <typename T>
 inline int colsum(cudaStream_t st, const T* x, long long rows, long long ld, int cols, float* out_zeroed,
                   const int* lim = nullptr, int rps = 1) {
   if (lim) {
-    dim3 grid(ceil_div(cols, 32), (unsigned)(rows / rps), (unsigned)(rps >= 1024 ? 8 : 1));
-    colsum_slabs_kernel<T><<<grid, dim3(32, 8), 0, st>>>(x, rps, ld, cols, out_zeroed, lim);
+    bool fast = false;
+    if constexpr (sizeof(T) == 2) {
+      if (cols % 256 == 0 && ld % 8 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+        dim3 grid(cols / 256, (unsigned)(rows / rps), (unsigned)(rps >= 1024 ? 4 : 1));
+        colsum_slabs_bf16x8_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), rps, ld, cols, out_zeroed, lim);
+        fast = true;
+      }
+    }
+    if (!fast) {
+      dim3 grid(ceil_div(cols, 32), (unsigned)(rows / rps), (unsigned)(rps >= 1024 ? 8 : 1));
+      colsum_slabs_kernel<T><<<grid, dim3(32, 8), 0, st>>>(x, rps, ld, cols, out_zeroed, lim);
+    }
   } else {
     const int rpb = rows >= 65536 ? 2048 : 256;   // small inputs (per-molecule bias sums): enough blocks to fill the GPU
     dim3 grid(ceil_div(cols, 32), (unsigned)ceil_div64(rows, rpb));
