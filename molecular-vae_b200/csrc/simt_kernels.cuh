@@ -285,7 +285,7 @@ __global__ void __launch_bounds__(256) colsum_slabs_bf16x8_kernel(const __nv_bfl
   __shared__ float red[8][256 + 8];
   const int lane = threadIdx.x & 31, wy = threadIdx.x >> 5;
   const int c8 = blockIdx.x * 256 + lane * 8;
-  const int n = min(rps, __ldg(lim + blockIdx.y));
+  const int n = lim ? min(rps, __ldg(lim + blockIdx.y)) : rps;   // lim == nullptr: every row of the (single) slab counts
   const int per = (rps + gridDim.z - 1) / gridDim.z;
   const int r0 = blockIdx.z * per, r1 = min(n, r0 + per);
   if (r1 <= r0) return;                                        // uniform over the block
@@ -331,6 +331,14 @@ inline int colsum(cudaStream_t st, const T* x, long long rows, long long ld, int
       colsum_slabs_kernel<T><<<grid, dim3(32, 8), 0, st>>>(x, rps, ld, cols, out_zeroed, lim);
     }
   } else {
+    if constexpr (sizeof(T) == 2) {
+      if (cols % 256 == 0 && ld % 8 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && rows >= 4096 && rows < (1ll << 31)) {
+        dim3 grid(cols / 256, 1, (unsigned)ceil_div64(rows, 1024));
+        colsum_slabs_bf16x8_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), (int)rows, ld, cols, out_zeroed, nullptr);
+        MVAE_CUDA_CHECK(cudaGetLastError());
+        return MVAE_OK;
+      }
+    }
     const int rpb = rows >= 65536 ? 2048 : 256;   // small inputs (per-molecule bias sums): enough blocks to fill the GPU
     dim3 grid(ceil_div(cols, 32), (unsigned)ceil_div64(rows, rpb));
     colsum_kernel<T><<<grid, dim3(32, 8), 0, st>>>(x, rows, ld, cols, out_zeroed, rpb);
