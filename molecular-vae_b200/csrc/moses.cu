@@ -854,12 +854,14 @@ int step_t(const MDims& d, const MWS& w, const float* const* P, float* const* G,
   RC(sg(st, w.dWT, 1, V, P[ix.wih(0)], IN0, 1, G[ix.emb()], V, V, V, 3 * Hd, nullptr, simt::ACT_NONE, 1, 24));
   //   dW_ih[:, V:] = dgisum^T * z ; dz = dgisum * W_ih[:, V:]
   RC(sg_wgrad(st, w.dgisum, 1, 3 * Hd, w.z, Z, 1, G[ix.wih(0)] + V, IN0, 3 * Hd, Z, B));
-  RC(sg(st, w.dgisum, 3 * Hd, 1, P[ix.wih(0)] + V, IN0, 1, w.dz, Z, B, Z, 3 * Hd, nullptr, simt::ACT_NONE, 0));
+  //   (skinny output, long contraction: split-K so that more than 3 x B/64 blocks share the work)
+  RC(memset_async(w.dz, (size_t)B * Z * 4, st));
+  RC(sg(st, w.dgisum, 3 * Hd, 1, P[ix.wih(0)] + V, IN0, 1, w.dz, Z, B, Z, 3 * Hd, nullptr, simt::ACT_NONE, 1, 4));
   // decoder_lat: h0 = z W^T + b, shared by all layers (dh0 already summed over layers)
   RC(sg_wgrad(st, w.dh0, 1, Hd, w.z, Z, 1, G[ix.latw()], Z, Hd, Z, B));
   RC(memset_async(G[ix.latb()], (size_t)Hd * 4, st));
   RC(simt::colsum<float>(st, w.dh0, B, Hd, Hd, G[ix.latb()])); mvae_count_launches(1);
-  RC(sg(st, w.dh0, Hd, 1, P[ix.latw()], Z, 1, w.dz, Z, B, Z, Hd, nullptr, simt::ACT_NONE, 1));
+  RC(sg(st, w.dh0, Hd, 1, P[ix.latw()], Z, 1, w.dz, Z, B, Z, Hd, nullptr, simt::ACT_NONE, 1, 4));
   // reparametrisation + KL
   const long long nBZ = (long long)B * Z;
   reparam_kl_std_bwd_kernel<<<grid_for(nBZ), 256, 0, st>>>(w.mu, w.lv, eps, w.dz, d.kl_w / (float)B, nBZ, w.dmu, w.dlv); KCHECK();
