@@ -78,6 +78,20 @@ def cpu_oracle_rate(sample_b, steps, warmup):
     return sample_b * steps / dt, dt / steps
 
 
+def cpu_reference_rate(sample_b, steps, warmup):
+    """(molecules/s, s/step, kind, description) of the reference's CPU path on all host cores: the UNMODIFIED reference
+    modules from baseline/_ref (models2d.py:8-52 + train.py:31-38 under torch CPU, kind "reference") when the recipe
+    baseline/make_ref.py has been run, else the numpy oracle port (kind "port")."""
+    from baseline import ref_arm
+    cores = os.cpu_count() or 1
+    if ref_arm.have_ref():
+        rate, sec, _ = ref_arm.step_rate(sample_b, steps, warmup, device="cpu", threads=cores)
+        return rate, sec, "reference", (f"{sample_b} molecules/step, unmodified reference models2d.py + train.py:31-38 (latent 292) under "
+                                        f"torch {__import__('torch').__version__} CPU fp32, torch.set_num_threads({cores})")
+    rate, sec = cpu_oracle_rate(sample_b, steps, warmup)
+    return rate, sec, "port", f"{sample_b} molecules/step, fp32 numpy port oracle/vae_oracle.py (baseline/_ref absent), BLAS on all cores"
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -85,17 +99,31 @@ def run_reference(args):
     cores = os.cpu_count() or 1
     total = args.steps + args.warmup
     sample_b = int(max(8, min(250, 6000 // max(total, 1))))
-    rate, sec = cpu_oracle_rate(sample_b, args.steps, args.warmup)
-    sample = f"{sample_b} molecules/step (BASELINE config[0] shape, fp32 numpy port of models2d.py+train.py:31-38)"
+    rate, sec, kind, sample = cpu_reference_rate(sample_b, args.steps, args.warmup)
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": "molecules/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "sample_batch": sample_b},
-        "cpu_baseline": {"value": rate, "unit": "molecules/s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": rate, "unit": "molecules/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": rate, "unit": "molecules/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
+
+
+def gpu_eager_baseline(B):
+    """The kernel to beat on the same box: the unmodified reference modules in stock PyTorch eager on
+    cuda:0 (cuDNN GRU, cuBLAS, ATen) at the benchmarked batch, fp32 as shipped and under bf16 autocast."""
+    import torch
+    from baseline import ref_arm
+    if not ref_arm.have_ref():
+        return {"unavailable": "baseline/_ref absent (run baseline/make_ref.py where /root/reference exists)"}
+    out = {"unit": "molecules/s", "batch": B, "impl": "reference models2d.py + train.py:31-38, torch " + torch.__version__ + " eager, cuda:0"}
+    for name, ac in (("fp32", False), ("bf16_autocast", True)):
+        rate, sec, loss = ref_arm.step_rate(B, 3, 2, device="cuda", autocast=ac)
+        out[name] = {"value": rate, "ms_per_step": sec * 1e3, "loss": loss}
+        torch.cuda.empty_cache()
+    return out
 
 
 def time_kernel(fn, iters=5):
@@ -441,10 +469,13 @@ def run_ours(args):
             except Exception as ex:  # never lose the headline over the side measurement
                 line["roofline"]["kernels_error"] = repr(ex)
             cores = os.cpu_count() or 1
-            rate, _ = cpu_oracle_rate(250, 2, 1)
-            line["cpu_baseline"] = {"value": rate, "unit": "molecules/s", "cores": cores, "kind": "port",
-                                    "sample": "2 timed steps of 250 molecules (BASELINE config[0] batch) after 1 "
-                                              "warm-up, fp32 numpy port oracle/vae_oracle.py, BLAS on all cores"}
+            rate, _, kind, sample = cpu_reference_rate(250, 4, 1)
+            line["cpu_baseline"] = {"value": rate, "unit": "molecules/s", "cores": cores, "kind": kind,
+                                    "sample": "4 timed steps after 1 warm-up (BASELINE config[0] batch): " + sample}
+            try:
+                line["gpu_eager_baseline"] = gpu_eager_baseline(B)
+            except Exception as ex:
+                line["gpu_eager_baseline"] = {"error": repr(ex)}
         line["sampling"] = sampling
         if world == 1:
             try:

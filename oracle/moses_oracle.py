@@ -253,10 +253,12 @@ def moses_step(P, seqs, eps, pad, kl_weight=1.0, need_grads=True, d_layers=3, dr
     return res
 
 
-def moses_sample_greedy(P, z, bos, eos, pad, max_len=100, d_layers=3):
+def moses_sample_greedy(P, z, bos, eos, pad, max_len=100, d_layers=3, return_margins=False):
     """Greedy restatement of VAE.sample (mosesvae.py:214-262; the shipped uint8 eos_mask / undefined d_z are fixed as
     SURVEY.md 8c prescribes: bool mask, argmax instead of torch.multinomial, ties -> lowest id).  All rows run all
-    max_len-1 steps; tokens after EOS are not written; returns ids (B,max_len) filled with pad, lengths end_pads."""
+    max_len-1 steps; tokens after EOS are not written; returns ids (B,max_len) filled with pad, lengths end_pads.
+    return_margins: the third value is the (B, max_len) top-2 logit margin of every decode step (column 0 = inf), so a
+    bit-exactness test can tell a wrong token from a near-tie the oracle's own float64 could have flipped."""
     B = z.shape[0]
     E = P["x_emb.weight"]
     V = E.shape[0]
@@ -268,6 +270,7 @@ def moses_sample_greedy(P, z, bos, eos, pad, max_len=100, d_layers=3):
     x[:, 0] = bos
     end = np.full(B, max_len, dtype=np.int64)
     done = np.zeros(B, dtype=bool)
+    margins = np.full((B, max_len), np.inf)
     for i in range(1, max_len):
         inp = np.concatenate([E[w], z], 1)
         for l in range(d_layers):
@@ -281,11 +284,13 @@ def moses_sample_greedy(P, z, bos, eos, pad, max_len=100, d_layers=3):
             inp = h[l]
         y = inp @ P["decoder_fc.weight"].T + P["decoder_fc.bias"]
         w = y.argmax(-1)
+        srt = np.sort(y, -1)
+        margins[:, i] = srt[:, -1] - srt[:, -2]
         x[~done, i] = w[~done]
         new_eos = ~done & (w == eos)
         end[new_eos] = i + 1
         done |= new_eos
-    return x, end, y
+    return x, end, (margins if return_margins else y)
 
 
 # ---------------------------------------------------------------------------------------------------------

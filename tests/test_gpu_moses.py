@@ -104,15 +104,25 @@ def test_moses_sample_greedy_bit_exact_fp32():
     P, seqs, eps, pad, model = _setup(m, "fp32", 313, 413, 4)
     B, max_len = 24, 40
     z = np.random.Generator(np.random.PCG64(5)).standard_normal((B, 160)).astype(np.float32)
-    x_ref, end_ref, _ = mo.moses_sample_greedy({k: v.astype(np.float64) for k, v in P.items()}, z.astype(np.float64),
-                                               model.bos, model.eos, model.pad, max_len=max_len)
+    x_ref, end_ref, margins = mo.moses_sample_greedy({k: v.astype(np.float64) for k, v in P.items()}, z.astype(np.float64),
+                                                     model.bos, model.eos, model.pad, max_len=max_len, return_margins=True)
     ids, lens, _ = model.sample_ids(B, max_len=max_len, z=torch.from_numpy(z).cuda(), greedy=True)
     torch.cuda.synchronize()
     model.check_device_error()
     ids, lens = ids.cpu().numpy(), lens.cpu().numpy()
-    # a sequence is comparable up to the first step where the oracle's own top-2 margin is tiny; require most to match fully
-    same = [(ids[b] == x_ref[b]).all() and lens[b] == end_ref[b] for b in range(B)]
-    assert np.mean(same) >= 0.9, np.mean(same)
+    # Bit-exact wherever the oracle's own top-2 logit margin exceeds fp32 resolution (the rule of
+    # test_gpu_cfgb.py::test_greedy_decode_bit_exact_fp32).  Decoding is autoregressive, so a row is comparable up to
+    # (not including) its first near-tie step -- after a flipped near-tie the two decodes see different inputs.
+    unsafe = margins < 1e-4
+    first_unsafe = np.where(unsafe.any(1), unsafe.argmax(1), max_len)
+    # steps after the oracle's EOS are never written: a near-tie there cannot matter
+    first_unsafe = np.where(first_unsafe >= end_ref, max_len, first_unsafe)
+    for b in range(B):
+        k = int(first_unsafe[b])
+        assert (ids[b, :k] == x_ref[b, :k]).all(), (b, k, ids[b], x_ref[b])
+        if k == max_len:
+            assert lens[b] == end_ref[b], (b, lens[b], end_ref[b])
+    assert (first_unsafe == max_len).mean() >= 0.9      # the case is decisive: most rows have no near-tie at all
     strs, _ = model.sample(B, max_len=max_len, z=torch.from_numpy(z).cuda(), greedy=True)
     assert len(strs) == B and all(isinstance(s, str) for s in strs)
 
