@@ -22,10 +22,13 @@ def strip_module_prefix(state_dict):
     return out
 
 
-def load_reference_checkpoint(model, source, map_location="cpu", strict=True):
+def load_reference_checkpoint(model, source, map_location="cpu", strict=True, allow_pickle=False):
     """Load a checkpoint written by the reference (path or already-loaded object) into `model` (a drop-in module of this
-    package or the reference's own class).  Returns the metadata dict of the train.py layout (empty for bare state_dicts)."""
-    obj = torch.load(source, map_location=map_location, weights_only=False) if isinstance(source, (str, bytes)) or hasattr(source, "read") else source
+    package or the reference's own class).  Returns the metadata dict of the train.py layout (empty for bare state_dicts).
+    The reference layouts hold only tensors, dicts, lists, ints, floats and strings, so files are read with
+    `weights_only=True` (no arbitrary pickle code); `allow_pickle=True` is the explicit opt-in for anything else."""
+    obj = (torch.load(source, map_location=map_location, weights_only=not allow_pickle)
+           if isinstance(source, (str, bytes)) or hasattr(source, "read") else source)
     meta = {}
     if isinstance(obj, dict) and "model_state_dict" in obj:
         meta = {k: obj[k] for k in META_KEYS if k in obj}

@@ -568,7 +568,7 @@ int finalize(const ADims& d, const AWS& w, float* out_scalars, float* mu_out, fl
   if (out_scalars) {
     simt::finalize_scalars_kernel<<<1, 256, 0, st>>>(w.bce_sum, w.kl_sum, w.hit_count, d.B, d.T,
                                                     (double)d.max_len / ((double)d.B * d.T * d.C), 1.0 / ((double)d.B * d.Z),
-                                                    out_scalars);
+                                                    out_scalars, w.err_flag);
     KCHECK();
   }
   const size_t n = (size_t)d.B * d.Z * 4;

@@ -772,7 +772,7 @@ int step_t(const MDims& d, const MWS& w, const float* const* P, float* const* G,
   finalize_kernel<<<1, 1, 0, st>>>(w.kl_sum, w.nll_sum, w.M, B, d.kl_w, d.rec_w, out_scalars); KCHECK();
   if (z_out) { mvae_count_launches(1); MVAE_CUDA_CHECK(cudaMemcpyAsync(z_out, w.z, (size_t)B * Z * 4, cudaMemcpyDeviceToDevice, st)); }
   if (lv_out) { mvae_count_launches(1); MVAE_CUDA_CHECK(cudaMemcpyAsync(lv_out, w.lv, (size_t)B * Z * 4, cudaMemcpyDeviceToDevice, st)); }
-  if (!backward) return MVAE_OK;
+  if (!backward) { simt::nan_if_error_kernel<<<1, 1, 0, st>>>(w.err_flag, out_scalars); KCHECK(); return MVAE_OK; }
 
   // =================================== backward ===================================
   const TA* dlog = (const TA*)w.dlogits;
@@ -937,6 +937,8 @@ int step_t(const MDims& d, const MWS& w, const float* const* P, float* const* G,
   if (d.pad >= 0 && d.pad < V) {   // nn.Embedding(padding_idx = pad): the pad row receives no gradient
     zero_row_kernel<<<1, 64, 0, st>>>(G[ix.emb()], d.pad, V); KCHECK();
   }
+  // a fired pipeline watchdog poisons the returned loss (the scalars were finalised before the backward kernels ran)
+  simt::nan_if_error_kernel<<<1, 1, 0, st>>>(w.err_flag, out_scalars); KCHECK();
   return MVAE_OK;
 }
 

@@ -96,7 +96,8 @@ int mvae_adam_step(float* params, const float* grads, float* exp_avg, float* exp
                    float beta1, float beta2, float eps, float weight_decay, int step, const float* clip_coef,
                    mvae_stream_t stream) {
   if (!params || !grads || !exp_avg || !exp_avg_sq || n <= 0 || step < 1) return MVAE_ERR_INVALID;
-  const float bias1 = 1.f - powf(beta1, (float)step), bias2 = 1.f - powf(beta2, (float)step);
+  // bias corrections in double on the host, as torch.optim.Adam computes them (1 - beta ** step in Python floats)
+  const float bias1 = (float)(1.0 - pow((double)beta1, (double)step)), bias2 = (float)(1.0 - pow((double)beta2, (double)step));
   adam_kernel<<<grid_for(n), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(params, grads, exp_avg, exp_avg_sq, n, lr,
                                                                               beta1, beta2, eps, weight_decay, bias1,
                                                                               bias2, clip_coef);

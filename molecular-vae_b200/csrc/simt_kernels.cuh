@@ -862,7 +862,7 @@ __global__ void head_argmax_kernel(const float* __restrict__ logits, int CP, int
 // out[0]=loss, [1]=max_len*bce_mean, [2]=kl, [3]=#molecules reconstructed exactly
 __global__ void finalize_scalars_kernel(const double* __restrict__ bce_sum, const double* __restrict__ kl_sum,
                                         const int* __restrict__ hit_count, int B, int T, double bce_scale,
-                                        double kl_scale, float* __restrict__ out) {
+                                        double kl_scale, float* __restrict__ out, const int* __restrict__ err_flag = nullptr) {
   __shared__ int cnt;
   if (threadIdx.x == 0) cnt = 0;
   __syncthreads();
@@ -873,11 +873,18 @@ __global__ void finalize_scalars_kernel(const double* __restrict__ bce_sum, cons
   if (threadIdx.x == 0) {
     const double bce = bce_sum[0] * bce_scale;
     const double kl = -0.5 * kl_sum[0] * kl_scale;
-    out[0] = (float)(bce + kl);
+    // a fired pipeline watchdog (bounded waits of the tcgen05 / persistent kernels) poisons the returned loss, so a caller
+    // that never polls the device error flag still cannot train on garbage silently
+    const bool bad = err_flag && *err_flag != 0;
+    out[0] = bad ? __int_as_float(0x7fc00000) : (float)(bce + kl);
     out[1] = (float)bce;
     out[2] = (float)kl;
     out[3] = (float)cnt;
   }
+}
+// same guard for step functions whose scalars are final before their last kernels ran
+__global__ void nan_if_error_kernel(const int* __restrict__ err_flag, float* __restrict__ out) {
+  if (*err_flag != 0) out[0] = __int_as_float(0x7fc00000);
 }
 
 }  // namespace

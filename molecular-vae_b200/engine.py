@@ -61,6 +61,9 @@ class CfgBEngine:
         self._graph_keep = None
         self._phase_graphs = []
         self._phase_keep = None
+        # every call that rewrites the workspace bumps this; an autograd backward checks that the activations it is about
+        # to read are still the ones its own forward left there (one shared workspace per engine)
+        self.generation = 0
 
     # -- helpers -------------------------------------------------------------------------------
     @property
@@ -98,6 +101,7 @@ class CfgBEngine:
     def elbo_step(self, params, grads, ids, eps, mu_out=None, logvar_out=None):
         """Fused forward + loss + backward.  Returns the device tensor [loss, max_len*bce, kl, n_exact]."""
         P, G = _ptr_table(params), _ptr_table(grads)
+        self.generation += 1
         with torch.cuda.device(self.device):
             check(lib.mvae_cfgb_elbo_step(ctypes.byref(self.desc), P, G, _p(ids), _p(eps), _p(self.scalars),
                                           _p(mu_out), _p(logvar_out), self._ws_ptr, self.ws_bytes, _stream()))
@@ -134,6 +138,7 @@ class CfgBEngine:
         return [lib.mvae_graph_num_kernel_nodes(h) for h in self._phase_graphs]
 
     def launch_phase(self, phase):
+        self.generation += 1
         with torch.cuda.device(self.device):
             check(lib.mvae_graph_launch(self._phase_graphs[phase], _stream()))
         return self.scalars
@@ -145,6 +150,7 @@ class CfgBEngine:
         self._phase_keep = None
 
     def launch_graph(self):
+        self.generation += 1
         with torch.cuda.device(self.device):
             check(lib.mvae_graph_launch(self._graph, _stream()))
         return self.scalars
@@ -161,12 +167,18 @@ class CfgBEngine:
         probs = torch.empty(d.batch, d.seq_len, d.charset, dtype=torch.float32, device=self.device)
         mu = torch.empty(d.batch, d.latent, dtype=torch.float32, device=self.device)
         logvar = torch.empty_like(mu)
+        self.generation += 1
         with torch.cuda.device(self.device):
             check(lib.mvae_cfgb_forward(ctypes.byref(d), _ptr_table(params), _p(ids), _p(eps), _p(probs), _p(mu),
                                         _p(logvar), self._ws_ptr, self.ws_bytes, _stream()))
         return probs, mu, logvar
 
-    def backward(self, params, grads, ids, eps, dprobs, dmu, dlogvar):
+    def backward(self, params, grads, ids, eps, dprobs, dmu, dlogvar, generation=None):
+        if generation is not None and generation != self.generation:
+            raise _lib.MvaeError(
+                "backward() of a forward whose saved activations were overwritten: another forward / decode / fused step ran "
+                "on this model between model(x) and loss.backward().  Call backward first, or use a second model instance "
+                "(the engine keeps ONE workspace per module; it does not recompute the forward)")
         with torch.cuda.device(self.device):
             check(lib.mvae_cfgb_backward(ctypes.byref(self.desc), _ptr_table(params), _ptr_table(grads), _p(ids),
                                          _p(eps), _p(dprobs), _p(dmu), _p(dlogvar), self._ws_ptr, self.ws_bytes,
@@ -176,6 +188,7 @@ class CfgBEngine:
         d = self.desc
         ids = torch.empty(d.batch, d.seq_len, dtype=torch.uint8, device=self.device)
         probs = torch.empty(d.batch, d.seq_len, d.charset, dtype=torch.float32, device=self.device) if want_probs else None
+        self.generation += 1
         with torch.cuda.device(self.device):
             check(lib.mvae_cfgb_decode_greedy(ctypes.byref(d), _ptr_table(params), _p(z), _p(ids), _p(probs),
                                               self._ws_ptr, self.ws_bytes, _stream()))

@@ -9,6 +9,7 @@ The nn.Modules only HOLD the parameters; all arithmetic runs in libmvae_b200.so 
 `elbo_step()` is the fused fast path for train.py:98-101.
 """
 import ctypes
+import threading
 
 import torch
 from torch import nn
@@ -16,6 +17,8 @@ from torch import nn
 from . import _lib
 from ._lib import CfgADesc, check, lib
 from .engine import _p, _ptr_table, _stream
+
+_ENGINE_LOCK = threading.Lock()   # guards the per-device engine caches (DataParallel worker threads)
 
 
 def cfga_param_order(enc_layers=3, dec_layers=4):
@@ -53,6 +56,7 @@ class CfgAEngine:
         self.scalars = torch.zeros(4, dtype=torch.float32, device=self.device)
         self._graph = None
         self._graph_keep = None
+        self.generation = 0   # bumped by every call that rewrites the workspace (see CfgBEngine.generation)
 
     def _args(self):
         return self._ws_ptr, self.ws_bytes, _stream()
@@ -65,6 +69,7 @@ class CfgAEngine:
             raise _lib.MvaeError("tcgen05 pipeline watchdog fired (device-side error flag set)")
 
     def elbo_step(self, params, grads, ids, eps, mu_out=None, logvar_out=None):
+        self.generation += 1
         with torch.cuda.device(self.device):
             check(lib.mvae_cfga_elbo_step(ctypes.byref(self.desc), _ptr_table(params), _ptr_table(grads), _p(ids), _p(eps),
                                           _p(self.scalars), _p(mu_out), _p(logvar_out), *self._args()))
@@ -83,6 +88,7 @@ class CfgAEngine:
         return lib.mvae_graph_num_kernel_nodes(handle)
 
     def launch_graph(self):
+        self.generation += 1
         with torch.cuda.device(self.device):
             check(lib.mvae_graph_launch(self._graph, _stream()))
         return self.scalars
@@ -98,12 +104,17 @@ class CfgAEngine:
         probs = torch.empty(d.batch, d.seq_len, d.charset, dtype=torch.float32, device=self.device)
         mu = torch.empty(d.batch, d.latent, dtype=torch.float32, device=self.device)
         logvar = torch.empty_like(mu)
+        self.generation += 1
         with torch.cuda.device(self.device):
             check(lib.mvae_cfga_forward(ctypes.byref(d), _ptr_table(params), _p(ids), _p(eps), _p(probs), _p(mu), _p(logvar),
                                         *self._args()))
         return probs, mu, logvar
 
-    def backward(self, params, grads, ids, eps, dprobs, dmu, dlogvar):
+    def backward(self, params, grads, ids, eps, dprobs, dmu, dlogvar, generation=None):
+        if generation is not None and generation != self.generation:
+            raise _lib.MvaeError(
+                "backward() of a forward whose saved activations were overwritten: another forward / decode / fused step ran "
+                "on this model between model(x) and loss.backward() (one workspace per module, no forward recomputation)")
         with torch.cuda.device(self.device):
             check(lib.mvae_cfga_backward(ctypes.byref(self.desc), _ptr_table(params), _ptr_table(grads), _p(ids), _p(eps),
                                          _p(dprobs), _p(dmu), _p(dlogvar), *self._args()))
@@ -112,6 +123,7 @@ class CfgAEngine:
         d = self.desc
         ids = torch.empty(d.batch, d.seq_len, dtype=torch.uint8, device=self.device)
         probs = torch.empty(d.batch, d.seq_len, d.charset, dtype=torch.float32, device=self.device) if want_probs else None
+        self.generation += 1
         with torch.cuda.device(self.device):
             check(lib.mvae_cfga_decode(ctypes.byref(d), _ptr_table(params), _p(z), _p(ids), _p(probs), *self._args()))
         return ids, probs
@@ -200,7 +212,7 @@ class _CfgAFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, engine, ids, eps, *params):
         probs, mu, logvar = engine.forward(list(params), ids, eps)
-        ctx.engine, ctx.ids, ctx.eps = engine, ids, eps
+        ctx.engine, ctx.ids, ctx.eps, ctx.generation = engine, ids, eps, engine.generation
         ctx.save_for_backward(*params)
         return probs, mu, logvar
 
@@ -209,7 +221,7 @@ class _CfgAFunction(torch.autograd.Function):
         params = list(ctx.saved_tensors)
         grads = [torch.empty_like(p) for p in params]
         c = lambda t: None if t is None else t.contiguous().float()
-        ctx.engine.backward(params, grads, ctx.ids, ctx.eps, c(dprobs), c(dmu), c(dlogvar))
+        ctx.engine.backward(params, grads, ctx.ids, ctx.eps, c(dprobs), c(dmu), c(dlogvar), generation=ctx.generation)
         return (None, None, None, *grads)
 
 
@@ -233,7 +245,7 @@ class MolecularVAE(nn.Module):
             self.encoder = encoder
         if decoder is not None:
             self.decoder = decoder
-        self._engines = {}
+        self._engines.clear()
         self._bind()
 
     # -- plumbing --------------------------------------------------------------------------------------------
@@ -244,17 +256,28 @@ class MolecularVAE(nn.Module):
                     dec_hidden=d.gru.hidden_size, dec_layers=d.gru.num_layers, eps_scale=e.lmbd.scale)
 
     def ordered_params(self):
-        named = dict(self.named_parameters())
-        return [named[k] for k in cfga_param_order(self.encoder.gru.num_layers, self.decoder.gru.num_layers)]
+        """Parameters in the C ABI's order, fetched by attribute path (nn.DataParallel's replicas carry their broadcast
+        copies as plain tensor attributes; their named_parameters() is empty -- train_distributed.py:72)."""
+        out = []
+        for k in cfga_param_order(self.encoder.gru.num_layers, self.decoder.gru.num_layers):
+            obj = self
+            for part in k.split("."):
+                obj = getattr(obj, part)
+            out.append(obj)
+        return out
 
     def engine(self, batch, max_len=None):
-        dev = next(self.parameters()).device
-        key = (batch, self.precision, str(dev))
-        eng = self._engines.get(key)
-        if eng is None:
-            cfg = self._cfg()
-            eng = CfgAEngine(batch, precision=self.precision, max_len=float(max_len or cfg["seq_len"]), device=dev, **cfg)
-            self._engines = {key: eng}
+        dev = self.encoder.embedding.weight.device
+        key = (batch, self.precision)
+        # one workspace per (module, device); the dict is shared by nn.DataParallel's per-forward replicas
+        with _ENGINE_LOCK:
+            slot = self._engines.get(str(dev))
+            if slot is None or slot[0] != key:
+                cfg = self._cfg()
+                eng = CfgAEngine(batch, precision=self.precision, max_len=float(max_len or cfg["seq_len"]), device=dev, **cfg)
+                self._engines[str(dev)] = (key, eng)
+            else:
+                eng = slot[1]
         return eng
 
     def _eps(self, batch, device):

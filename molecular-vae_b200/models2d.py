@@ -8,17 +8,21 @@ libmvae_b200.so.  Differences a caller can see: the latent / hidden sizes are co
 reference hard-codes 2 / 501), the input may be u8/long ids (B,T) as well as the reference's float one-hot
 (B,T,C), and `precision` selects fp32 check mode or bf16 tensor-core mode.
 """
+import threading
+
 import torch
 from torch import nn
 
 from .engine import CfgBEngine, param_order
+
+_ENGINE_LOCK = threading.Lock()   # guards the per-device engine caches (DataParallel worker threads)
 
 
 class _CfgBFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, engine, ids, eps, *params):
         probs, mu, logvar = engine.forward(list(params), ids, eps)
-        ctx.engine, ctx.ids, ctx.eps = engine, ids, eps
+        ctx.engine, ctx.ids, ctx.eps, ctx.generation = engine, ids, eps, engine.generation
         ctx.save_for_backward(*params)
         return probs, mu, logvar
 
@@ -27,7 +31,7 @@ class _CfgBFunction(torch.autograd.Function):
         params = list(ctx.saved_tensors)
         grads = [torch.empty_like(p) for p in params]
         c = lambda t: None if t is None else t.contiguous().float()
-        ctx.engine.backward(params, grads, ctx.ids, ctx.eps, c(dprobs), c(dmu), c(dlogvar))
+        ctx.engine.backward(params, grads, ctx.ids, ctx.eps, c(dprobs), c(dmu), c(dlogvar), generation=ctx.generation)
         return (None, None, None, *grads)
 
 
@@ -47,22 +51,36 @@ class VAE(nn.Module):
         self.cfg = dict(seq_len=seq_len, charset=charset, latent=latent, hidden=hidden, layers=layers, fc0=435,
                         eps_scale=eps_scale)
         self.precision = precision
+        # one live workspace per (module, device).  The dict is shared, not copied, by the replicas
+        # nn.DataParallel makes of this module on every forward (train_distributed.py:72: `replica.__dict__` is a shallow
+        # copy), so each device's engine is built once and re-used by that device's worker thread.
         self._engines = {}
         self._keys = param_order(layers)
         self.eps_override = None  # tests inject the normal draws here (models2d.py:34 draws them internally)
 
     # -- plumbing ----------------------------------------------------------------------------------
     def ordered_params(self):
-        named = dict(self.named_parameters())
-        return [named[k] for k in self._keys]
+        """Parameters in the C ABI's order, fetched by attribute path: nn.DataParallel's replicas carry their broadcast
+        copies as plain tensor attributes (their named_parameters() is empty)."""
+        out = []
+        for k in self._keys:
+            obj = self
+            for part in k.split("."):
+                obj = getattr(obj, part)
+            out.append(obj)
+        return out
 
     def engine(self, batch, max_len=None):
-        key = (batch, self.precision, str(next(self.parameters()).device))
-        eng = self._engines.get(key)
-        if eng is None:
-            eng = CfgBEngine(batch, precision=self.precision, max_len=float(max_len or self.cfg["seq_len"]),
-                             device=next(self.parameters()).device, **self.cfg)
-            self._engines = {key: eng}  # one live workspace per module
+        dev = self.fc3.weight.device
+        key = (batch, self.precision)
+        with _ENGINE_LOCK:
+            slot = self._engines.get(str(dev))
+            if slot is None or slot[0] != key:
+                eng = CfgBEngine(batch, precision=self.precision, max_len=float(max_len or self.cfg["seq_len"]),
+                                 device=dev, **self.cfg)
+                self._engines[str(dev)] = (key, eng)
+            else:
+                eng = slot[1]
         eng.set_train(self.training)
         return eng
 
@@ -90,6 +108,9 @@ class VAE(nn.Module):
 
     @torch.no_grad()
     def decode(self, z):
+        """probabilities (B,T,C) for latents z (models2d.py:40-47).  INFERENCE ONLY on this path: the result carries no
+        autograd graph (training goes through forward() / elbo_step(), which differentiate the whole encode ->
+        reparametrize -> decode chain in one call), and it overwrites the activations a pending backward would read."""
         eng = self.engine(z.shape[0])
         params = [p.detach() for p in self.ordered_params()]
         _, probs = eng.decode_greedy(params, z.detach().float().contiguous(), want_probs=True)

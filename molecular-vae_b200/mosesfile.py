@@ -9,7 +9,7 @@ the hard-coded bidirectional encoder); that case raises here instead of failing 
 import torch
 from torch import nn
 
-from .mosesvae import VAE as _MosesVAE
+from .mosesvae import VAE as _MosesVAE, _check_moses_shapes
 
 
 def mosesfile_param_order(d_layers=3):
@@ -35,6 +35,11 @@ class VAE(_MosesVAE):
         for ss in ("bos", "eos", "unk", "pad"):
             setattr(self, ss, getattr(vocab, ss))
         n_vocab, d_emb = len(vocab), vocab.vectors.size(1)
+        if config.q_d_h != 256:
+            # mosesfile.py:22-28 hard-codes the encoder GRU's hidden size to 256 while q_mu / q_logvar are sized from
+            # config.q_d_h * 2 (:30-32): any other value fails inside the reference's first matmul
+            raise ValueError("mosesfile.VAE: config.q_d_h must be 256 (the encoder GRU's hard-coded hidden size, mosesfile.py:22-28)")
+        _check_moses_shapes(n_vocab, d_emb, self.pad, 256, config.d_d_h)
         self.x_emb = nn.Embedding(n_vocab, d_emb, self.pad)
         self.x_emb.weight.data.copy_(vocab.vectors)
         self.encoder_rnn = nn.GRU(d_emb, 256, num_layers=config.q_n_layers, batch_first=True, dropout=0.0, bidirectional=True)

@@ -29,6 +29,22 @@ def moses_param_order(d_layers=3):
     return keys + ["decoder_lat.weight", "decoder_lat.bias", "decoder_fc.weight", "decoder_fc.bias"]
 
 
+MAX_VOCAB = 64   # the kernels keep token tables / logits rows in 64-wide tiles (moses.cu make_dims)
+
+
+def _check_moses_shapes(n_vocab, d_emb, pad, q_d_h, d_d_h):
+    """What the kernels assume and torch would otherwise catch as a shape / index error (moses.cu treats x_emb.weight as
+    V x V -- the one-hot-initialised table of mosesvae.py:44-50 -- and sizes every table by V)."""
+    if d_emb != n_vocab:
+        raise ValueError(f"vocab.vectors must be (V, V) one-hot-initialised vectors (vocab.py:87); got width {d_emb} for V={n_vocab}")
+    if not 5 <= n_vocab <= MAX_VOCAB:
+        raise ValueError(f"vocabulary size {n_vocab} outside the supported range [5, {MAX_VOCAB}]")
+    if not 0 <= int(pad) < n_vocab:
+        raise ValueError(f"pad id {pad} outside the vocabulary")
+    if q_d_h % 64 or d_d_h % 64:
+        raise ValueError("GRU hidden sizes must be multiples of 64")
+
+
 class _MosesFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, model, ids, lens, eps, *params):
@@ -53,12 +69,15 @@ class _BindingFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, model, z, *params):
         out = model._forward(z, list(params))
-        ctx.model, ctx.z = model, z
+        ctx.model, ctx.z, ctx.generation = model, z, model._generation
         ctx.save_for_backward(*params)
         return out
 
     @staticmethod
     def backward(ctx, dout):
+        if ctx.generation != ctx.model._generation:
+            raise _lib.MvaeError("BindingModel.backward(): another forward of this module overwrote the saved activations "
+                                 "(one workspace per module; call backward before the next forward)")
         params = list(ctx.saved_tensors)
         grads = [torch.empty_like(p) for p in params]
         dz = ctx.model._backward(ctx.z, params, grads, dout.contiguous().float().view(-1), ctx.needs_input_grad[1])
@@ -81,6 +100,7 @@ class BindingModel(nn.Module):
             nn.Linear(64, 1))
         self.z_size = z_size
         self._ws = None
+        self._generation = 0
 
     def _desc(self, B):
         bn = self.binding_model[1]
@@ -99,6 +119,7 @@ class BindingModel(nn.Module):
         bn1, bn2 = self.binding_model[1], self.binding_model[6]
         running = _ptr_table([bn1.running_mean, bn1.running_var, bn2.running_mean, bn2.running_var])
         out = torch.empty(B, dtype=torch.float32, device=z.device)
+        self._generation += 1
         with torch.cuda.device(z.device):
             check(lib.mvae_binding_forward(ctypes.byref(d), _ptr_table(params), running, _p(z), _p(out), wsp, need, _stream()))
         if self.training:
@@ -129,6 +150,7 @@ class VAE(nn.Module):
         for ss in ("bos", "eos", "unk", "pad"):
             setattr(self, ss, getattr(vocab, ss))
         n_vocab, d_emb = len(vocab), vocab.vectors.size(1)
+        _check_moses_shapes(n_vocab, d_emb, self.pad, q_d_h, d_d_h)
         self.x_emb = nn.Embedding(n_vocab, d_emb, self.pad)
         self.x_emb.weight.data.copy_(vocab.vectors)
         self.encoder_rnn = nn.GRU(d_emb, q_d_h, num_layers=q_n_layers, batch_first=True, dropout=0, bidirectional=False)
@@ -168,12 +190,27 @@ class VAE(nn.Module):
         lens = [int(t.numel()) for t in x]
         if any(lens[i] < lens[i + 1] for i in range(len(lens) - 1)):
             raise RuntimeError("sequences must be sorted by length in decreasing order (pack_sequence contract)")
-        padded = nn.utils.rnn.pad_sequence(x, batch_first=True, padding_value=self.pad)
+        if min(lens) < 2:
+            raise RuntimeError("every sequence needs at least <bos> and <eos>")
         dev = self.device
         lens_h = torch.tensor(lens, dtype=torch.int32)
+        # one concatenation + one scatter instead of pad_sequence's per-sequence copies (4096 tiny kernels at B = 4096)
+        B, T = len(x), lens[0]
+        flat = torch.cat([t.reshape(-1) for t in x]).to(device=dev, dtype=torch.long)
+        row = torch.repeat_interleave(torch.arange(B), lens_h.long())
+        col = torch.arange(int(lens_h.sum())) - torch.repeat_interleave(torch.cumsum(lens_h.long(), 0) - lens_h.long(), lens_h.long())
+        padded = torch.full((B, T), int(self.pad), dtype=torch.long, device=dev)
+        padded.view(-1).index_copy_(0, (row * T + col).to(dev), flat)
+        # token ids index device tables: an id outside the vocabulary is an error the way it is for nn.Embedding.  The
+        # check is asynchronous (no host sync on the training path): ids are clamped for the kernels and the flag is
+        # raised by check_device_error() / the next forward().
+        V = self.cfg["vocab"]
+        bad = ((padded < 0) | (padded >= V)).any()
+        self._bad_ids = bad if getattr(self, "_bad_ids", None) is None else (self._bad_ids | bad)
+        padded_c = padded.clamp(0, V - 1)
         lens_d = lens_h.to(dev)
         lens_d._host_copy = lens_h
-        return padded.to(dev), padded.to(device=dev, dtype=torch.uint8).contiguous(), lens_d
+        return padded, padded_c.to(torch.uint8).contiguous(), lens_d
 
     def _dropout(self):
         """(p, seed) of the train-mode dropout between decoder layers (mosesvae.py:38,78); p = 0 in eval mode."""
@@ -215,6 +252,11 @@ class VAE(nn.Module):
         return out[1], out[2], z, lv, y
 
     def check_device_error(self):
+        bad = getattr(self, "_bad_ids", None)
+        if bad is not None:
+            self._bad_ids = None
+            if bool(bad.item()):
+                raise IndexError("token id outside the vocabulary (as nn.Embedding would raise, mosesvae.py:150)")
         d, wsp, need = self._last_desc
         flag = ctypes.c_int(0)
         check(lib.mvae_moses_read_error(ctypes.byref(d), wsp, need, ctypes.byref(flag), _stream()))

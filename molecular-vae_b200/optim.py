@@ -44,6 +44,73 @@ class FusedOptimizer:
         self.norm = torch.zeros(1, dtype=torch.float32, device=dev)
         self.steps = 0
 
+    # -- torch.optim surface the reference's loops touch (train.py:81-83,104,170-177: ReduceLROnPlateau reads / writes
+    #    param_groups[0]['lr'], the checkpoint stores optimizer.state_dict()) ------------------------------------------
+    @property
+    def param_groups(self):
+        outer = self
+
+        class _Group(dict):
+            def __setitem__(g, k, v):
+                dict.__setitem__(g, k, v)
+                if k == "lr":
+                    outer.lr = float(v)
+
+        g = _Group(params=self.fp.params, lr=self.lr, weight_decay=self.weight_decay)
+        if self.kind == "adam":
+            g.update(betas=self.betas, eps=self.eps)
+        else:
+            g.update(momentum=self.momentum)
+        return [g]
+
+    def zero_grad(self, set_to_none=False):
+        self.fp.grads.flat.zero_()
+
+    def _slices(self):
+        off = 0
+        for i, p in enumerate(self.fp.params):
+            yield i, p, off, off + p.numel()
+            off += p.numel()
+
+    def state_dict(self):
+        """torch.optim.Adam / SGD layout: per-parameter `exp_avg`, `exp_avg_sq`, `step` (Adam) or `momentum_buffer` (SGD)
+        cut out of the flat state buffers, and one param group -- what train.py:170-177 stores as optimizer_state_dict."""
+        state = {}
+        if self.steps > 0:
+            for i, p, lo, hi in self._slices():
+                if self.kind == "adam":
+                    state[i] = {"step": torch.tensor(float(self.steps)), "exp_avg": self.state1[lo:hi].view_as(p).clone(),
+                                "exp_avg_sq": self.state2[lo:hi].view_as(p).clone()}
+                else:
+                    state[i] = {"momentum_buffer": self.state1[lo:hi].view_as(p).clone()}
+        group = {k: v for k, v in self.param_groups[0].items() if k != "params"}
+        group["params"] = list(range(len(self.fp.params)))
+        return {"state": state, "param_groups": [group]}
+
+    def load_state_dict(self, sd):
+        group = sd["param_groups"][0]
+        self.lr = float(group["lr"])
+        self.weight_decay = float(group.get("weight_decay", self.weight_decay))
+        if self.kind == "adam":
+            self.betas, self.eps = tuple(group.get("betas", self.betas)), float(group.get("eps", self.eps))
+        else:
+            self.momentum = float(group.get("momentum", self.momentum))
+        self.steps = 0
+        self.state1.zero_()
+        if self.state2 is not None:
+            self.state2.zero_()
+        for i, p, lo, hi in self._slices():
+            st = sd["state"].get(i, sd["state"].get(str(i)))
+            if st is None:
+                continue
+            if self.kind == "adam":
+                self.state1[lo:hi].copy_(st["exp_avg"].reshape(-1))
+                self.state2[lo:hi].copy_(st["exp_avg_sq"].reshape(-1))
+                self.steps = max(self.steps, int(float(st["step"])))
+            else:
+                self.state1[lo:hi].copy_(st["momentum_buffer"].reshape(-1))
+                self.steps = max(self.steps, 1)
+
     def step(self):
         fp, n = self.fp, self.fp.flat.numel()
         coef = ctypes.c_void_p(0)

@@ -45,8 +45,20 @@ def _setup(m, precision, pseed, bseed, B):
     return P, seqs, eps, pad, model
 
 
-@pytest.mark.parametrize("precision,B,ltol,gtol", [("fp32", 6, 2e-5, 3e-5), ("fp32", 70, 2e-5, 3e-5),
-                                                   ("bf16", 64, 2e-3, 2e-2), ("bf16", 300, 2e-3, 2e-2)])
+# north_star tolerances: loss terms 1e-3 / gradients 1e-2 relative in bf16, 1e-5 in the fp32 check mode.  The reference's own
+# float32 run deviates from its float64 run by < 5e-7 on these shapes (tests/golden/moses_fp32_budget.npz, written by
+# tests/golden/make_golden_large.py from the reference modules), so 1e-5 is a bound on THIS path, not on the anchor.
+FP32_LTOL, FP32_GTOL, BF16_LTOL, BF16_GTOL = 1e-5, 1e-5, 1e-3, 1e-2
+
+
+def test_reference_fp32_budget_is_below_the_check_mode_tolerance():
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "moses_fp32_budget.npz"))
+    assert max(float(g[k]) for k in g.files) < 1e-6
+
+
+@pytest.mark.parametrize("precision,B,ltol,gtol", [("fp32", 6, FP32_LTOL, FP32_GTOL), ("fp32", 70, FP32_LTOL, FP32_GTOL),
+                                                   ("bf16", 64, BF16_LTOL, BF16_GTOL), ("bf16", 300, BF16_LTOL, BF16_GTOL)])
 def test_moses_fused_step(precision, B, ltol, gtol):
     m = load_pkg()
     klw = 0.1
@@ -90,9 +102,9 @@ def test_moses_dropin_forward_backward_and_state_dict():
     loss = 0.25 * kl + recon
     loss.backward()
     torch.cuda.synchronize()
-    assert abs(float(loss.detach()) - ref["loss"]) <= 2e-5 * abs(ref["loss"])
+    assert abs(float(loss.detach()) - ref["loss"]) <= FP32_LTOL * abs(ref["loss"])
     bad = {k: rel_l2(p.grad.cpu().numpy(), ref["grads"][k]) for k, p in model.named_parameters()
-           if k in ref["grads"] and rel_l2(p.grad.cpu().numpy(), ref["grads"][k]) > 3e-5}
+           if k in ref["grads"] and rel_l2(p.grad.cpu().numpy(), ref["grads"][k]) > FP32_GTOL}
     assert not bad, bad
     with pytest.raises(RuntimeError):
         model([torch.from_numpy(s).cuda() for s in seqs[::-1]])       # not length-sorted
@@ -145,7 +157,7 @@ def test_moses_sample_multinomial_distribution():
     assert (s_ids != g_ids).float().mean().item() > 0.2               # actually stochastic
 
 
-@pytest.mark.parametrize("precision,B,ltol,gtol", [("fp32", 9, 2e-5, 3e-5), ("bf16", 130, 2e-3, 2e-2)])
+@pytest.mark.parametrize("precision,B,ltol,gtol", [("fp32", 9, FP32_LTOL, FP32_GTOL), ("bf16", 130, BF16_LTOL, BF16_GTOL)])
 def test_moses_train_mode_dropout_with_injected_mask(precision, B, ltol, gtol):
     """train(): nn.GRU(dropout=0.2) between decoder layers (mosesvae.py:38,78).  The counter-based mask of the CUDA path is
     restated in the oracle (moses_oracle.dropout_masks) and injected there."""
@@ -191,7 +203,8 @@ def _setup_file(m, precision, pseed, bseed, B):
     return P, seqs, eps, pad, model.cuda()
 
 
-@pytest.mark.parametrize("precision,B,ltol,gtol", [("fp32", 7, 2e-5, 3e-5), ("fp32", 70, 2e-5, 3e-5), ("bf16", 200, 2e-3, 2e-2)])
+@pytest.mark.parametrize("precision,B,ltol,gtol", [("fp32", 7, FP32_LTOL, FP32_GTOL), ("fp32", 70, FP32_LTOL, FP32_GTOL),
+                                                   ("bf16", 200, BF16_LTOL, BF16_GTOL)])
 def test_mosesfile_bidirectional_fused_step(precision, B, ltol, gtol):
     m = load_pkg()
     klw = 0.5
@@ -236,14 +249,14 @@ def test_mosesfile_dropin_contract_and_reference_fixture():
     kl, recon = out
     (klw * kl + recon).backward()
     torch.cuda.synchronize()
-    assert abs(float(kl.detach()) - float(g["f64/kl"])) <= 2e-5 * abs(float(g["f64/kl"]))
-    assert abs(float(recon.detach()) - float(g["f64/recon"])) <= 2e-5 * abs(float(g["f64/recon"]))
+    assert abs(float(kl.detach()) - float(g["f64/kl"])) <= FP32_LTOL * abs(float(g["f64/kl"]))
+    assert abs(float(recon.detach()) - float(g["f64/recon"])) <= FP32_LTOL * abs(float(g["f64/recon"]))
     for k, p in model.named_parameters():
         if f"f64/gfull/{k}" in g:
-            assert rel_l2(p.grad.cpu().numpy(), g[f"f64/gfull/{k}"]) <= 3e-5, k
+            assert rel_l2(p.grad.cpu().numpy(), g[f"f64/gfull/{k}"]) <= FP32_GTOL, k
         elif f"f64/gnorm/{k}" in g:
             gn = float(g[f"f64/gnorm/{k}"])
-            assert abs(np.sqrt((p.grad.double() ** 2).sum().item()) - gn) <= 3e-5 * gn, k
+            assert abs(np.sqrt((p.grad.double() ** 2).sum().item()) - gn) <= FP32_GTOL * gn, k
     strs = model.sample(8, max_len=20, greedy=True)
     assert isinstance(strs, list) and len(strs) == 8 and all(isinstance(s, str) for s in strs)
 
@@ -372,6 +385,42 @@ def test_moses_sample_graph_replay_equals_direct_launch():
     assert model._sample_graph["handle"].value == handle              # same graph, fresh draws
     assert (a != b).float().mean().item() > 0.1
     model.destroy_sample_graph()
+
+
+def test_moses_fused_step_bf16_batch4096_matches_reference_fixture():
+    """BASELINE.json configs[3] batch (4096 per GPU = 16 row tiles: per-tile step windows over the packed sequences,
+    mirrored tile assignment, K-split BPTT, token-table encoder) against the fixture the reference's own mosesvae.VAE
+    wrote at that batch size (tests/golden/make_golden_large.py, float64).  north_star tolerances; poisoned workspace."""
+    import os
+    m = load_pkg()
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "moses_b4096.npz"))
+    ps, bs, B, M = [int(v) for v in g["meta"]]
+    klw = float(g["kl_weight"][0])
+    assert B == 4096 and "MVAE_MOSES_REC" not in os.environ
+    P, seqs, eps, pad, model = _setup(m, "bf16", ps, bs, B)
+    x = [torch.from_numpy(s).cuda() for s in seqs]
+    model.elbo_step(x, kl_weight=klw, eps=torch.from_numpy(eps).cuda())
+    torch.cuda.synchronize()
+    model._ws.fill_(0xFF)
+    out = model.elbo_step(x, kl_weight=klw, eps=torch.from_numpy(eps).cuda())
+    torch.cuda.synchronize()
+    model.check_device_error()
+    sc = out.cpu().numpy()
+    assert abs(sc[1] - g["f64/kl"]) <= BF16_LTOL * abs(g["f64/kl"]), (sc, float(g["f64/kl"]))
+    assert abs(sc[2] - g["f64/recon"]) <= BF16_LTOL * abs(g["f64/recon"]), (sc, float(g["f64/recon"]))
+    assert int(sc[3]) == M
+    bad = {}
+    for k, p in model.named_parameters():
+        if f"f64/gnorm/{k}" not in g:
+            continue
+        gr = p.grad.cpu().numpy()
+        gn = float(g[f"f64/gnorm/{k}"])
+        en = abs(np.sqrt((gr.astype(np.float64) ** 2).sum()) - gn) / gn
+        e = (rel_l2(gr, g[f"f64/gfull/{k}"]) if f"f64/gfull/{k}" in g
+             else rel_l2(gr.reshape(-1)[g[f"f64/gidx/{k}"]], g[f"f64/gval/{k}"]))
+        if not (e <= BF16_GTOL and en <= BF16_GTOL):
+            bad[k] = (e, en)
+    assert not bad, bad
 
 
 @pytest.mark.parametrize("B,drop", [(2600, 0.0), (4096, 0.0), (4096, 0.2)])
