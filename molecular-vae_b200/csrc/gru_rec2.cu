@@ -39,6 +39,39 @@ constexpr int THREADS = (CTRL_WARPS + EPI_WARPS) * 32;
 constexpr int PUB_WARP = 2;
 constexpr int CTRL_REGS = 32, EPI_REGS = 112;   // (96 - 32) * 128 released >= (112 - 96) * 512 claimed
 
+// Saved gates (forward -> BPTT): per (t, tile, pair, parity, part, q) -- i.e. per epilogue WARP -- one contiguous block of
+// SV_NARR arrays x 1 KB, array a at +a*512 elements, inside it [half][lane][8 units] (thread (q, lane) owns two 16-byte
+// halves 512 B apart).  Only the BPTT epilogue with the same thread mapping reads it.
+//   MVAE_SV_BULK 1: the forward epilogue stages its arrays in shared memory and writes them with cp.async.bulk
+//     (shared -> global): the 80 KB per tile-step no longer sit in the LSU / outstanding-store queue in front of the h'
+//     stores and the release that the next step of the other CTAs waits for (profiles/r01_rec_trace_notes.txt: the plain
+//     sv stores were the forward sweep's largest single cost).  Paid for with two operand stages (8 -> 6).
+//   MVAE_SV_HP 0: h_{t-1} is not saved; the BPTT epilogue reads it from the hs slab (same bf16 value).
+#ifndef MVAE_SV_BULK
+#define MVAE_SV_BULK 1
+#endif
+#ifndef MVAE_SV_HP
+#define MVAE_SV_HP 0
+#endif
+constexpr int SV_NARR = MVAE_SV_HP ? 5 : 4;
+constexpr int SV_STAGE_BYTES = 2048;      // per epilogue warp: two arrays per bulk store
+
+__device__ __forceinline__ void bulk_s2g(void* gdst, const void* ssrc, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(gdst), "r"(ptx::smem_u32(ssrc)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory"); }
+// 16 bf16 of this thread into a warp's 1 KB staging array: [half][lane][16 B]
+__device__ __forceinline__ void sts2x128(uint8_t* arr_base, int lane, const float (&v)[16]) {
+  uint4 a, b;
+  a.x = rec::pack_bf2(v[0], v[1]); a.y = rec::pack_bf2(v[2], v[3]); a.z = rec::pack_bf2(v[4], v[5]); a.w = rec::pack_bf2(v[6], v[7]);
+  b.x = rec::pack_bf2(v[8], v[9]); b.y = rec::pack_bf2(v[10], v[11]); b.z = rec::pack_bf2(v[12], v[13]); b.w = rec::pack_bf2(v[14], v[15]);
+  *reinterpret_cast<uint4*>(arr_base + lane * 16) = a;
+  *reinterpret_cast<uint4*>(arr_base + 512 + lane * 16) = b;
+}
+
 struct Params2 {
   int Bp, Hp, T, pair_tiles, npairs;
   const __nv_bfloat16* gi; long long gi_tstride;
@@ -206,7 +239,10 @@ gru_rec2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
   float* xbuf = reinterpret_cast<float*>(sA + nst * A_STAGE);   // KS: [64 units][128 rows], reused by consecutive tile-steps
   __nv_bfloat16* sTbl = reinterpret_cast<__nv_bfloat16*>(sA + nst * A_STAGE + (KS ? XBUF : 0));   // fwd: [V][3][64]
   const int tbl_bytes = (!BWD && IN > 0) ? ((p.V * 3 * RU * 2 + 1023) & ~1023) : 0;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sA + nst * A_STAGE + (KS ? XBUF : 0) + tbl_bytes);
+  constexpr bool SVB = !BWD && MVAE_SV_BULK;                     // saved gates leave through cp.async.bulk
+  constexpr int STG_BYTES = SVB ? EPI_WARPS * SV_STAGE_BYTES : 0;
+  uint8_t* sStage = sA + nst * A_STAGE + (KS ? XBUF : 0) + tbl_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sStage + STG_BYTES);
   uint64_t* full_bar = bars;                         // [NST] own operand stage landed (tx)
   uint64_t* empty_bar = bars + NST;                  // [NST] all pairs that share the stage consumed it
   uint64_t* pfull_bar = bars + 2 * NST;              // [NST] leader: peer's stage landed (relayed)
@@ -488,9 +524,10 @@ gru_rec2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
         // saved activations use a per-thread "fragment" layout (consumed only by the BPTT epilogue with the same
         // thread mapping): block (t, tile, pair, parity, part, array) of 4 KB, thread (q, lane) owns 32 B -> every
         // warp-wide 256-bit access is 1 KB contiguous.
-        const size_t sv_blk = ((((size_t)t * p.pair_tiles + tile) * p.npairs + pair) * 2 + parity) * 4 + part;
-        // inside a 4 KB block: [q][half][lane][8 units] -> this thread's two 16-byte halves are 512 B apart
-        __nv_bfloat16* svp = p.sv ? p.sv + sv_blk * 5 * 2048 + (size_t)q * 512 + lane * 8 : nullptr;
+        const size_t sv_blk = (((((size_t)t * p.pair_tiles + tile) * p.npairs + pair) * 2 + parity) * 4 + part) * 4 + q;
+        // this warp's block: SV_NARR arrays of [half][lane][8 units] -> a thread's two 16-byte halves are 512 B apart
+        __nv_bfloat16* svw = p.sv ? p.sv + sv_blk * (SV_NARR * 512) : nullptr;
+        __nv_bfloat16* svp = svw ? svw + lane * 8 : nullptr;
         // gi / dX are produced by the GEMM epilogues in the row-blocked layout [row/32][width/8][32][8]:
         // this thread's 16 units of its row are two 16-byte pieces 512 B apart; a warp access is 512 B contiguous.
         const long long rblk = row >> 5;   // = tile*8 + parity*4 + q ; row & 31 == lane
@@ -512,8 +549,9 @@ gru_rec2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
           if constexpr (IN > 0) tokv = p.tok[(long long)t * p.Bp + row];
         } else {
 #pragma unroll
-          for (int blk = 0; blk < 4; ++blk) pre[blk] = ldg2x128(svp + blk * 2048);
-          pre[4] = ldg2x128(svp + 4 * 2048);   // h_{t-1} (saved by the forward sweep next to the gates)
+          for (int blk = 0; blk < 4; ++blk) pre[blk] = ldg2x128(svp + blk * 512);
+          if (MVAE_SV_HP) pre[4] = ldg2x128(svp + 4 * 512);   // h_{t-1} saved by the forward sweep next to the gates
+          else pre[4] = ldg256(p.hs + ((long long)t * p.Bp + row) * p.Hp + u0 + uc);   // h_{t-1} = slab t of the hidden states
           pre[5] = ldg2x128(p.dX + (long long)t * p.Bp * p.Hp + (rblk * (p.Hp / 8) + ((u0 + uc) >> 3)) * 256 + lane * 8);
         }
         (void)wait_bar(&tfull_bar[i], (uint32_t)(ls & 1), p.err_flag);   // on failure keep walking: barriers below must be reached
@@ -586,15 +624,48 @@ gru_rec2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
           ptx::mbar_arrive(&epi_bar[i]);
           if (tr2) p.trace[((size_t)step * NTILES + i) * 12 + 10] = gtime();
           if (svp && !nomem && !(p.debug & 1024)) {   // debug 1024: timing experiment without the saved-gate stores
-            stg2x128(svp, gr);
-            stg2x128(svp + 2048, gz);
-            stg2x128(svp + 2 * 2048, gn);
+            if constexpr (SVB) {
+              // stage two arrays (2 KB per warp), hand them to the bulk-copy engine, re-use the staging buffer once the
+              // engine has READ it; the global writes themselves complete asynchronously, off the LSU path
+              uint8_t* stg = sStage + (warp - CTRL_WARPS) * SV_STAGE_BYTES;
+              if (lane == 0) bulk_wait_read0();
+              __syncwarp();
+              sts2x128(stg, lane, gr);
+              sts2x128(stg + 1024, lane, gz);
+              ptx::fence_proxy_async_smem();
+              __syncwarp();
+              if (lane == 0) { bulk_s2g(svw, stg, 2048); bulk_commit(); bulk_wait_read0(); }
+              __syncwarp();
 #pragma unroll
-            for (int k = 0; k < 16; ++k) h[k] = __uint_as_float(an[k]);
-            stg2x128(svp + 3 * 2048, h);
+              for (int k = 0; k < 16; ++k) h[k] = __uint_as_float(an[k]);
+              sts2x128(stg, lane, gn);
+              sts2x128(stg + 1024, lane, h);
+              ptx::fence_proxy_async_smem();
+              __syncwarp();
+              if (lane == 0) { bulk_s2g(svw + 2 * 512, stg, 2048); bulk_commit(); }
+              if (MVAE_SV_HP) {
+                if (lane == 0) bulk_wait_read0();
+                __syncwarp();
 #pragma unroll
-            for (int k = 0; k < 16; ++k) h[k] = __uint_as_float(hm[k]);
-            stg2x128(svp + 4 * 2048, h);   // h_{t-1}: lets the BPTT epilogue skip the row-major hs read
+                for (int k = 0; k < 16; ++k) h[k] = __uint_as_float(hm[k]);
+                sts2x128(stg, lane, h);
+                ptx::fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) { bulk_s2g(svw + 4 * 512, stg, 1024); bulk_commit(); }
+              }
+            } else {
+              stg2x128(svp, gr);
+              stg2x128(svp + 512, gz);
+              stg2x128(svp + 2 * 512, gn);
+#pragma unroll
+              for (int k = 0; k < 16; ++k) h[k] = __uint_as_float(an[k]);
+              stg2x128(svp + 3 * 512, h);
+              if (MVAE_SV_HP) {
+#pragma unroll
+                for (int k = 0; k < 16; ++k) h[k] = __uint_as_float(hm[k]);
+                stg2x128(svp + 4 * 512, h);   // h_{t-1}: lets the BPTT epilogue skip the row-major hs read
+              }
+            }
           }
         } else {
           uint32_t acc[16], cm[16];
@@ -676,6 +747,7 @@ gru_rec2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
         if (!BWD && tr) p.trace[((size_t)step * NTILES + i) * 12 + 5] = gtime();
       }
     }
+    if constexpr (SVB) { if (lane == 0) bulk_wait_all0(); }   // the last saved-gate blocks must be in memory at kernel end
   }
 done:
   ptx::tc_fence_before();
@@ -722,7 +794,8 @@ int launch2(const mvae_gru_rec_args& a, cudaStream_t st) {
   if (!BWD && IN != 2 && !a.gi) return MVAE_ERR_INVALID;
   const size_t tbl_bytes = use_tbl ? (((size_t)a.V * 3 * RU * 2 + 1023) & ~(size_t)1023) : 0;
   int nst = KS ? 6 : STAGES;
-  const size_t fixed = (size_t)KC * NBH * 128 + (KS ? 128 * RU * 4 : 0) + tbl_bytes + 1024 + 1024;
+  const size_t stg_bytes = (!BWD && MVAE_SV_BULK) ? (size_t)EPI_WARPS * SV_STAGE_BYTES : 0;   // saved-gate staging (forward)
+  const size_t fixed = (size_t)KC * NBH * 128 + (KS ? 128 * RU * 4 : 0) + tbl_bytes + stg_bytes + 1024 + 1024;
   while (nst > 2 && fixed + (size_t)nst * A_STAGE > 232448) --nst;   // the token table takes the room of operand stages
   const size_t smem = fixed + (size_t)nst * A_STAGE;
   if (smem > 232448) return MVAE_ERR_UNSUPPORTED;
