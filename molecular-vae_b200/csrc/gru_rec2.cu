@@ -46,12 +46,28 @@ constexpr int CTRL_REGS = 32, EPI_REGS = 112;   // (96 - 32) * 128 released >= (
 //     (shared -> global): the 80 KB per tile-step no longer sit in the LSU / outstanding-store queue in front of the h'
 //     stores and the release that the next step of the other CTAs waits for (profiles/r01_rec_trace_notes.txt: the plain
 //     sv stores were the forward sweep's largest single cost).  Paid for with two operand stages (8 -> 6).
-//   MVAE_SV_HP 0: h_{t-1} is not saved; the BPTT epilogue reads it from the hs slab (same bf16 value).
+//   MVAE_SV_HP 0: h_{t-1} is not saved; the BPTT epilogue reads it from the hs slab (same bf16 value).  Measured (B200,
+//     B=4096, T=120): forward 10.55 -> 10.45 us/step, BPTT 18.98 -> 20.58 (32 scattered 32-byte sectors per warp load
+//     instead of one contiguous KB), so the copy stays (default 1).
 #ifndef MVAE_SV_BULK
 #define MVAE_SV_BULK 1
 #endif
 #ifndef MVAE_SV_HP
-#define MVAE_SV_HP 0
+#define MVAE_SV_HP 1
+#endif
+//   MVAE_OUT_TMA 1: the row-major outputs other CTAs stream next step (forward: h' into the hs slab; BPTT: the dG blocks) are
+//     staged per warp ([32 rows][32 B]) and written with TMA tensor stores instead of 32 scattered 32-byte sectors per warp
+//     store instruction; the issuing lane waits for their completion before the tile is handed to the publisher.
+#ifndef MVAE_OUT_TMA
+#define MVAE_OUT_TMA 1
+#endif
+// operand stages.  Measured (B200, B=4096, T=120, us/step fwd / K-split BPTT): 6 stages 10.60 / 19.11, 5: 10.62 / 19.18,
+// 4: 10.13 / 17.71, 3: 10.57 / 17.99 -- deeper prefetch only adds queueing in front of the epilogue's traffic.
+#ifndef MVAE_NST_FWD
+#define MVAE_NST_FWD 4
+#endif
+#ifndef MVAE_NST_BWD
+#define MVAE_NST_BWD 3
 #endif
 constexpr int SV_NARR = MVAE_SV_HP ? 5 : 4;
 constexpr int SV_STAGE_BYTES = 2048;      // per epilogue warp: two arrays per bulk store
@@ -59,6 +75,21 @@ constexpr int SV_STAGE_BYTES = 2048;      // per epilogue warp: two arrays per b
 __device__ __forceinline__ void bulk_s2g(void* gdst, const void* ssrc, uint32_t bytes) {
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(gdst), "r"(ptx::smem_u32(ssrc)), "r"(bytes)
                : "memory");
+}
+// TMA tensor store of a [32 rows][32 B] staging block (dense, no swizzle) to (col c0, row c1, slab c2)
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* ssrc, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];\n" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(ptx::smem_u32(ssrc)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+// this thread's 16 bf16 (32 B) into row `lane` of a dense [32][32 B] block
+__device__ __forceinline__ void sts_row32(uint8_t* blk, int lane, const float (&v)[16]) {
+  uint4 a, b;
+  a.x = rec::pack_bf2(v[0], v[1]); a.y = rec::pack_bf2(v[2], v[3]); a.z = rec::pack_bf2(v[4], v[5]); a.w = rec::pack_bf2(v[6], v[7]);
+  b.x = rec::pack_bf2(v[8], v[9]); b.y = rec::pack_bf2(v[10], v[11]); b.z = rec::pack_bf2(v[12], v[13]); b.w = rec::pack_bf2(v[14], v[15]);
+  *reinterpret_cast<uint4*>(blk + lane * 32) = a;
+  *reinterpret_cast<uint4*>(blk + lane * 32 + 16) = b;
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory"); }
@@ -159,6 +190,9 @@ __device__ __forceinline__ void tma_load_3d_2sm_mc(void* smem_dst, const CUtenso
 __device__ __forceinline__ void st_cluster_f32(uint32_t cluster_addr, uint32_t v) {
   asm volatile("st.shared::cluster.b32 [%0], %1;" ::"r"(cluster_addr), "r"(v) : "memory");
 }
+__device__ __forceinline__ void st_cluster_v4(uint32_t cluster_addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(cluster_addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
 // wait on a LOCAL mbarrier whose arrivals come from another CTA of the cluster (release.cluster): acquire at cluster scope
 __device__ __forceinline__ bool wait_bar_cluster(uint64_t* bar, uint32_t parity, int* err_flag) {
   uint32_t spins = 0;
@@ -216,9 +250,10 @@ __device__ __forceinline__ void commit2_mc(uint64_t* bar, uint16_t mask) {
 // steps and the window arithmetic folds away
 template <bool BWD, bool FAST, int CL, bool KS, int IN = 0, bool VL = false>
 __global__ void __launch_bounds__(THREADS, 1)
-gru_rec2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmA, const Params2 p) {
+gru_rec2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmA,
+                const __grid_constant__ CUtensorMap tmS, const Params2 p) {
   static_assert(!KS || (BWD && CL == 2), "K-split is a BPTT variant of the pair kernel");
-  constexpr int NST = KS ? 6 : STAGES;         // operand stages (KS gives 32 KB to the exchange buffer)
+  constexpr int NST = STAGES;                  // upper bound of the operand stages (barrier arrays); p.nst are in use
   constexpr int XBUF = 128 * RU * 4;           // KS: one tile's incoming partial sums (128 rows x 64 units fp32)
   constexpr int NB = BWD ? (KS ? 2 * RU : RU) : 3 * RU;        // MMA N of the pair
   constexpr int NBH = NB / 2;                  // resident rows per CTA
@@ -241,8 +276,13 @@ gru_rec2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
   const int tbl_bytes = (!BWD && IN > 0) ? ((p.V * 3 * RU * 2 + 1023) & ~1023) : 0;
   constexpr bool SVB = !BWD && MVAE_SV_BULK;                     // saved gates leave through cp.async.bulk
   constexpr int STG_BYTES = SVB ? EPI_WARPS * SV_STAGE_BYTES : 0;
+  // row-major outputs through TMA tensor stores: BPTT only (measured: BPTT 17.91 -> 17.55 us/step, forward 10.22 -> 10.62,
+  // where the single h' block per warp does not pay for the completion wait)
+  constexpr bool OTMA = BWD && MVAE_OUT_TMA != 0;
+  constexpr int OUT_BYTES = OTMA ? EPI_WARPS * (BWD ? 3 : 1) * 1024 : 0;
   uint8_t* sStage = sA + nst * A_STAGE + (KS ? XBUF : 0) + tbl_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sStage + STG_BYTES);
+  uint8_t* sOut = sStage + STG_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sOut + OUT_BYTES);
   uint64_t* full_bar = bars;                         // [NST] own operand stage landed (tx)
   uint64_t* empty_bar = bars + NST;                  // [NST] all pairs that share the stage consumed it
   uint64_t* pfull_bar = bars + 2 * NST;              // [NST] leader: peer's stage landed (relayed)
@@ -288,6 +328,7 @@ gru_rec2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
   if (threadIdx.x == 0) {
     ptx::tma_prefetch_desc(&tmW);
     ptx::tma_prefetch_desc(&tmA);
+    if (OTMA) ptx::tma_prefetch_desc(&tmS);
     for (int s = 0; s < NST; ++s) {
       ptx::mbar_init(&full_bar[s], 1);
       ptx::mbar_init(&empty_bar[s], NSAME);
@@ -617,7 +658,22 @@ gru_rec2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
             for (int k = 0; k < 4; ++k) hl[k] = make_float4(h[4 * k], h[4 * k + 1], h[4 * k + 2], h[4 * k + 3]);
           }
           tmem_st_32x16(master_addr, h);
-          if (!nomem) stg256(p.hs + ((long long)(t + 1) * p.Bp + row) * p.Hp + u0 + uc, h);
+          if (!nomem) {
+            if constexpr (OTMA) {
+              uint8_t* ob = sOut + (warp - CTRL_WARPS) * 1024;
+              sts_row32(ob, lane, h);          // (the previous tile-step's store of this buffer completed before its arrive)
+              ptx::fence_proxy_async_smem();
+              __syncwarp();
+              if (lane == 0) {
+                tma_store_3d(&tmS, ob, u0 + uc, (int)(row - lane), t + 1);
+                bulk_commit();
+                bulk_wait_all0();              // h' is in memory: the tile can be published
+              }
+              __syncwarp();
+            } else {
+              stg256(p.hs + ((long long)(t + 1) * p.Bp + row) * p.Hp + u0 + uc, h);
+            }
+          }
           // everything other CTAs / the MMA wait for is issued: let the publisher go before the saved-gate stores
           tmem_st_wait();
           ptx::tc_fence_before();
@@ -627,14 +683,15 @@ gru_rec2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
             if constexpr (SVB) {
               // stage two arrays (2 KB per warp), hand them to the bulk-copy engine, re-use the staging buffer once the
               // engine has READ it; the global writes themselves complete asynchronously, off the LSU path
+              // (lane 1 issues them: bulk groups are per thread, and lane 0's wait for the h' store must not wait for these)
               uint8_t* stg = sStage + (warp - CTRL_WARPS) * SV_STAGE_BYTES;
-              if (lane == 0) bulk_wait_read0();
+              if (lane == 1) bulk_wait_read0();
               __syncwarp();
               sts2x128(stg, lane, gr);
               sts2x128(stg + 1024, lane, gz);
               ptx::fence_proxy_async_smem();
               __syncwarp();
-              if (lane == 0) { bulk_s2g(svw, stg, 2048); bulk_commit(); bulk_wait_read0(); }
+              if (lane == 1) { bulk_s2g(svw, stg, 2048); bulk_commit(); bulk_wait_read0(); }
               __syncwarp();
 #pragma unroll
               for (int k = 0; k < 16; ++k) h[k] = __uint_as_float(an[k]);
@@ -642,16 +699,16 @@ gru_rec2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
               sts2x128(stg + 1024, lane, h);
               ptx::fence_proxy_async_smem();
               __syncwarp();
-              if (lane == 0) { bulk_s2g(svw + 2 * 512, stg, 2048); bulk_commit(); }
+              if (lane == 1) { bulk_s2g(svw + 2 * 512, stg, 2048); bulk_commit(); }
               if (MVAE_SV_HP) {
-                if (lane == 0) bulk_wait_read0();
+                if (lane == 1) bulk_wait_read0();
                 __syncwarp();
 #pragma unroll
                 for (int k = 0; k < 16; ++k) h[k] = __uint_as_float(hm[k]);
                 sts2x128(stg, lane, h);
                 ptx::fence_proxy_async_smem();
                 __syncwarp();
-                if (lane == 0) { bulk_s2g(svw + 4 * 512, stg, 1024); bulk_commit(); }
+                if (lane == 1) { bulk_s2g(svw + 4 * 512, stg, 1024); bulk_commit(); }
               }
             } else {
               stg2x128(svp, gr);
@@ -681,7 +738,9 @@ gru_rec2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
               ptx::tmem_ld_wait();
               const uint32_t partner = rank ^ 2u;
               const uint32_t ev = nx++;                                  // exchange number
-              // xbuf[unit][row]: a warp store covers 32 consecutive rows of one unit (128 contiguous bytes)
+              // xbuf[unit][row]: a warp store covers 32 consecutive rows of one unit (128 contiguous bytes = one DSMEM
+              // transaction).  (A [row][unit] layout with 128-bit stores -- 4 instructions instead of 16, but 32 separate
+              // 16-byte remote transactions per instruction -- was measured slower: push 1.5 -> 2.4 us, sweep 17.55 -> 18.9 us/step.)
               const uint32_t xloc = ptx::smem_u32(xbuf + (size_t)uc * 128 + q * 32 + lane);
               const uint32_t xrem = mapa(xloc, partner);
               const int xw = warp - CTRL_WARPS;                                          // this warp's exchange slot
@@ -705,6 +764,7 @@ gru_rec2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
 #pragma unroll
             for (int k = 0; k < 16; ++k) { acc[k] = 0u; cm[k] = 0u; }
           }
+          if (tr && (p.debug & 64)) p.trace[((size_t)step * NTILES + i) * 12 + 8] = gtime();    // exchange done
           float r[16], z[16], n[16], ghn[16], hp[16], dx[16];
           unpack16(pre[0], r);
           unpack16(pre[1], z);
@@ -729,25 +789,56 @@ gru_rec2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
 #pragma unroll
             for (int k = 0; k < 4; ++k) co[k] = make_float4(carry[4 * k], carry[4 * k + 1], carry[4 * k + 2], carry[4 * k + 3]);
           }
+          if (tr && (p.debug & 64)) p.trace[((size_t)step * NTILES + i) * 12 + 9] = gtime();    // gate math done
           __nv_bfloat16* g4 = p.dG + ((long long)t * p.Bp + row) * 4 * p.Hp + u0 + uc;
+          uint8_t* ob = sOut + (warp - CTRL_WARPS) * 3072;
           if (!nomem) {
             // the three dgh blocks the other pairs stream next step go first; da_n (only read by the later wgrad / dX
             // GEMMs) is stored after this tile has been handed to the publisher
-            stg256(g4 + p.Hp, ghn);
-            stg256(g4 + 2 * p.Hp, dx);
-            stg256(g4 + 3 * p.Hp, hp);
+            if constexpr (OTMA) {
+              if (lane == 1) bulk_wait_read0();     // the da_n store of the previous tile-step (lane 1's group) has read block 0
+              __syncwarp();
+              sts_row32(ob, lane, ghn);
+              sts_row32(ob + 1024, lane, dx);
+              sts_row32(ob + 2048, lane, hp);
+              ptx::fence_proxy_async_smem();
+              __syncwarp();
+              if (lane == 0) {
+                const int r0 = (int)(row - lane);
+                tma_store_3d(&tmS, ob, p.Hp + u0 + uc, r0, t);
+                tma_store_3d(&tmS, ob + 1024, 2 * p.Hp + u0 + uc, r0, t);
+                tma_store_3d(&tmS, ob + 2048, 3 * p.Hp + u0 + uc, r0, t);
+                bulk_commit();
+                if (tr && (p.debug & 64)) p.trace[((size_t)step * NTILES + i) * 12 + 10] = gtime();   // stores issued
+                bulk_wait_all0();                   // dgh of this tile-step is in memory: the tile can be published
+              }
+              __syncwarp();
+            } else {
+              stg256(g4 + p.Hp, ghn);
+              stg256(g4 + 2 * p.Hp, dx);
+              stg256(g4 + 3 * p.Hp, hp);
+            }
           }
           tmem_st_wait();
           ptx::tc_fence_before();
           if (tr) p.trace[((size_t)step * NTILES + i) * 12 + 5] = gtime();
           ptx::mbar_arrive(&epi_bar[i]);
-          if (!nomem) stg256(g4, n);
+          if (!nomem) {
+            if constexpr (OTMA) {
+              sts_row32(ob, lane, n);               // block 0 is free: its dgh store completed above
+              ptx::fence_proxy_async_smem();
+              __syncwarp();
+              if (lane == 1) { tma_store_3d(&tmS, ob, u0 + uc, (int)(row - lane), t); bulk_commit(); }
+            } else {
+              stg256(g4, n);
+            }
+          }
         }
         if (tr && (p.debug & 64)) p.trace[((size_t)step * NTILES + i) * 12 + 11] = gtime();
         if (!BWD && tr) p.trace[((size_t)step * NTILES + i) * 12 + 5] = gtime();
       }
     }
-    if constexpr (SVB) { if (lane == 0) bulk_wait_all0(); }   // the last saved-gate blocks must be in memory at kernel end
+    if constexpr (SVB || OTMA) { if (lane < 2) bulk_wait_all0(); }   // the last bulk / TMA stores must be in memory at kernel end
   }
 done:
   ptx::tc_fence_before();
@@ -774,13 +865,13 @@ PFN_encodeTiled get_encode_fn() {
   return fn;
 }
 int encode(CUtensorMap* map, const void* ptr, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
-           const cuuint32_t* box) {
+           const cuuint32_t* box, bool swizzle = true) {
   PFN_encodeTiled enc = get_encode_fn();
   if (!enc) return MVAE_ERR_DRIVER;
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(ptr), dims, strides_bytes, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? MVAE_OK : MVAE_ERR_DRIVER;
 }
 
@@ -793,13 +884,29 @@ int launch2(const mvae_gru_rec_args& a, cudaStream_t st) {
   if (use_tbl && (!a.tbl || !a.tok || a.V < 1 || a.V > 64)) return MVAE_ERR_INVALID;
   if (!BWD && IN != 2 && !a.gi) return MVAE_ERR_INVALID;
   const size_t tbl_bytes = use_tbl ? (((size_t)a.V * 3 * RU * 2 + 1023) & ~(size_t)1023) : 0;
-  int nst = KS ? 6 : STAGES;
-  const size_t stg_bytes = (!BWD && MVAE_SV_BULK) ? (size_t)EPI_WARPS * SV_STAGE_BYTES : 0;   // saved-gate staging (forward)
+  int nst = BWD ? MVAE_NST_BWD : MVAE_NST_FWD;
+  const size_t stg_bytes = ((!BWD && MVAE_SV_BULK) ? (size_t)EPI_WARPS * SV_STAGE_BYTES : 0) +        // saved-gate staging (forward)
+                           ((BWD && MVAE_OUT_TMA) ? (size_t)EPI_WARPS * 3 * 1024 : 0);                  // output staging (BPTT)
   const size_t fixed = (size_t)KC * NBH * 128 + (KS ? 128 * RU * 4 : 0) + tbl_bytes + stg_bytes + 1024 + 1024;
   while (nst > 2 && fixed + (size_t)nst * A_STAGE > 232448) --nst;   // the token table takes the room of operand stages
+  if (((a.debug >> 16) & 0xF) >= 2 && ((a.debug >> 16) & 0xF) < nst) nst = (a.debug >> 16) & 0xF;   // timing experiment: fewer stages
   const size_t smem = fixed + (size_t)nst * A_STAGE;
   if (smem > 232448) return MVAE_ERR_UNSUPPORTED;
-  CUtensorMap tmW, tmA;
+  CUtensorMap tmW, tmA, tmS;
+  {   // store map: [32 rows][16 columns] boxes of the row-major output (forward: hs slabs; BPTT: dG), dense shared memory
+    cuuint32_t box[3] = {16, 32, 1};
+    if (BWD) {
+      cuuint64_t dims[3] = {(cuuint64_t)4 * Hp, (cuuint64_t)Bp, (cuuint64_t)T};
+      cuuint64_t str[2] = {(cuuint64_t)4 * Hp * 2, (cuuint64_t)Bp * 4 * Hp * 2};
+      int rc = encode(&tmS, a.dG, 3, dims, str, box, false);
+      if (rc) return rc;
+    } else {
+      cuuint64_t dims[3] = {(cuuint64_t)Hp, (cuuint64_t)Bp, (cuuint64_t)(T + 1)};
+      cuuint64_t str[2] = {(cuuint64_t)Hp * 2, (cuuint64_t)Bp * Hp * 2};
+      int rc = encode(&tmS, a.hs, 3, dims, str, box, false);
+      if (rc) return rc;
+    }
+  }
   {
     cuuint64_t dims[2] = {(cuuint64_t)(BWD ? 3 * Hp : Hp), (cuuint64_t)(BWD ? Hp : 3 * Hp)};
     cuuint64_t str[1] = {(cuuint64_t)(BWD ? 3 * Hp : Hp) * 2};
@@ -851,7 +958,7 @@ int launch2(const mvae_gru_rec_args& a, cudaStream_t st) {
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = KS ? 4 : CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at; cfg.numAttrs = 1;
-  MVAE_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, tmW, tmA, p));
+  MVAE_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, tmW, tmA, tmS, p));
   return MVAE_OK;
 }
 
