@@ -221,6 +221,19 @@ int mvae_moses_step(const mvae_moses_desc* d, const float* const* params, float*
                     const int32_t* lengths, const int32_t* lengths_host, const float* eps, float* out_scalars,
                     float* z_out, float* logvar_out, float* y_out, void* workspace, size_t workspace_bytes,
                     mvae_stream_t stream);
+/* mvae_moses_step with two more inputs (grads must be given when phase >= 0):
+ *   dz_ext  optional fp32 (B,d_z): gradient wrt z from a consumer of z outside the VAE (autograd of a property head,
+ *           trainbinding.py:216-217); added to the decoder's gradient wrt z before the reparametrisation backward.
+ *   phase   -1 = the whole step.  0..d_layers-1 = the part of the step whose gradients become final in phase p, in
+ *           backward order (the data-parallel bucket order, as mvae_cfgb_elbo_step_phase): phase 0 = forward + loss +
+ *           decoder_fc + top decoder layer; phase k = decoder layer d_layers-1-k; the last phase additionally the layer-0
+ *           input weights, decoder_lat, the mu / logvar heads, the encoder GRU(s) and x_emb.  Run all phases in order on
+ *           one stream with the same buffers; between two phases the finished slice can be all-reduced
+ *           (moses_train_distrib.py:30-42,176,191 -- the reference's commented-out DDP).                               */
+int mvae_moses_step_ex(const mvae_moses_desc* d, const float* const* params, float* const* grads, const uint8_t* ids,
+                       const int32_t* lengths, const int32_t* lengths_host, const float* eps, const float* dz_ext,
+                       float* out_scalars, float* z_out, float* logvar_out, float* y_out, void* workspace,
+                       size_t workspace_bytes, int phase, mvae_stream_t stream);
 /* VAE.sample (mosesvae.py:214-262; hugesample.py:28): autoregressive decode of B latents z fp32 (B,d_z) for
  * max_len-1 steps (desc->max_len = the sampler's max_len, 100 in the reference).  mode 0 = greedy argmax (ties ->
  * lowest id; the bit-exact parity mode), mode 1 = multinomial over softmax(y/temp) with a counter-based generator
@@ -258,6 +271,22 @@ typedef struct mvae_binding_desc {
   float bn_momentum; /* 0.1 */
 } mvae_binding_desc;
 size_t mvae_binding_workspace_bytes(const mvae_binding_desc* d);
+/* The VAE step with the property head on z in ONE call: the historical `VAE.forward(x, binding) -> (kl, recon,
+ * binding_loss, z)` that moses_train_distrib.py:274, trainbinding.py:216 and mosesanalyize.py:192 call (no shipped class
+ * implements it; BASELINE.json configs[3] "with the logP property head").  binding_loss = binding_weight *
+ * mean_b (BindingModel(z)_b - target_b)^2 with target fp32 (B) (the min-max scaled score / logP of
+ * moses_train_distrib.py:143); the differentiated scalar is kl_weight*kl + recon_weight*recon + binding_loss, so the
+ * head's gradient wrt z reaches the encoder.  bparams / bgrads / brunning as for mvae_binding_forward / _backward
+ * (bgrads overwritten); out_scalars as mvae_moses_step; binding_loss_out: 1 device float; `extra`: device scratch of
+ * mvae_moses_joint_extra_bytes(d) bytes (256-byte aligned); phase as mvae_moses_step_ex (the head runs in phase 0).    */
+size_t mvae_moses_joint_extra_bytes(const mvae_moses_desc* d);
+int mvae_moses_joint_step(const mvae_moses_desc* d, const float* const* params, float* const* grads, const uint8_t* ids,
+                          const int32_t* lengths, const int32_t* lengths_host, const float* eps,
+                          const mvae_binding_desc* bd, const float* const* bparams, float* const* bgrads,
+                          float* const* brunning, const float* target, float binding_weight, float* out_scalars,
+                          float* binding_loss_out, float* z_out, void* workspace, size_t workspace_bytes,
+                          void* binding_workspace, size_t binding_workspace_bytes, void* extra, size_t extra_bytes,
+                          int phase, mvae_stream_t stream);
 int mvae_binding_forward(const mvae_binding_desc* d, const float* const* params, float* const* running, const float* z,
                          float* out, void* workspace, size_t workspace_bytes, mvae_stream_t stream);
 int mvae_binding_backward(const mvae_binding_desc* d, const float* const* params, float* const* grads, const float* z,

@@ -88,6 +88,10 @@ def _load():
         "mvae_cfga_read_error": (i32, [ap, vp, ctypes.c_size_t, ctypes.POINTER(i32), vp]),
         "mvae_moses_workspace_bytes": (ctypes.c_size_t, [ctypes.POINTER(MosesDesc)]),
         "mvae_moses_step": (i32, [ctypes.POINTER(MosesDesc), pp, pp, vp, vp, vp, vp, vp, vp, vp, vp, vp, ctypes.c_size_t, vp]),
+        "mvae_moses_step_ex": (i32, [ctypes.POINTER(MosesDesc), pp, pp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, ctypes.c_size_t, i32, vp]),
+        "mvae_moses_joint_extra_bytes": (ctypes.c_size_t, [ctypes.POINTER(MosesDesc)]),
+        "mvae_moses_joint_step": (i32, [ctypes.POINTER(MosesDesc), pp, pp, vp, vp, vp, vp, ctypes.POINTER(BindingDesc), pp, pp, pp, vp,
+                                        ctypes.c_float, vp, vp, vp, vp, ctypes.c_size_t, vp, ctypes.c_size_t, vp, ctypes.c_size_t, i32, vp]),
         "mvae_moses_sample": (i32, [ctypes.POINTER(MosesDesc), pp, vp, i32, i32, i32, ctypes.c_float, ctypes.c_ulonglong, vp, vp, vp,
                                     vp, ctypes.c_size_t, vp]),
         "mvae_moses_sample_graph_create": (i32, [ctypes.POINTER(MosesDesc), pp, vp, i32, i32, i32, ctypes.c_float, vp, vp, vp,
@@ -123,7 +127,8 @@ EXPORTED = [
     "mvae_cfga_workspace_bytes", "mvae_cfga_elbo_step", "mvae_cfga_elbo_step_graph_create", "mvae_cfga_forward",
     "mvae_cfga_backward", "mvae_cfga_decode", "mvae_cfga_read_error",
     "mvae_ids_to_text", "mvae_text_to_ids", "mvae_binding_workspace_bytes", "mvae_binding_forward", "mvae_binding_backward",
-    "mvae_moses_workspace_bytes", "mvae_moses_step", "mvae_moses_sample", "mvae_moses_sample_graph_create", "mvae_moses_read_error",
+    "mvae_moses_workspace_bytes", "mvae_moses_step", "mvae_moses_step_ex", "mvae_moses_joint_extra_bytes", "mvae_moses_joint_step",
+    "mvae_moses_sample", "mvae_moses_sample_graph_create", "mvae_moses_read_error",
 ]
 
 

@@ -617,30 +617,69 @@ int gru_bwd(const MDims& d, const MWS& w, cudaStream_t st, const TA* Whh, const 
   return MVAE_OK;
 }
 
+// Property head on z (BindingModel, mosesvae.py:6-25) run between the VAE's forward and backward halves of ONE step: the
+// historical VAE.forward(x, binding) -> (kl, recon, binding_loss, z) that moses_train_distrib.py:274 / trainbinding.py:216
+// call.  binding_loss = weight * mean_b (BindingModel(z)_b - target_b)^2; its gradient wrt z joins the decoder's.
+struct JointHead {
+  const mvae_binding_desc* desc; const float* const* params; float* const* grads; float* const* running;
+  const float* target; float weight; float* pred; float* dout; float* dz; float* loss_out; void* ws; size_t ws_bytes;
+};
+__global__ void mse_head_kernel(const float* __restrict__ pred, const float* __restrict__ target, int B, float weight,
+                                float* __restrict__ dout, float* __restrict__ loss_out) {
+  // one block: loss = weight * mean (pred - target)^2 ; dout = weight * 2 (pred - target) / B
+  double local = 0.0;
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    const float e = pred[b] - target[b];
+    local += (double)e * e;
+    dout[b] = weight * 2.0f * e / (float)B;
+  }
+  for (int o = 16; o; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+  __shared__ double red[32];
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = local;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int w = 0; w < (blockDim.x >> 5); ++w) s += red[w];
+    *loss_out = (float)(weight * s / B);
+  }
+}
+
+// phase: -1 = the whole step; 0..L-1 = the part whose gradients become final in phase p (data-parallel bucket order, as
+// mvae_cfgb_elbo_step_phase): 0 = forward + head + top decoder layer, k = decoder layer L-1-k, L-1 additionally the
+// layer-0 input weights, decoder_lat, the encoder heads / GRU and x_emb.
+// dz_ext (optional, [B][Z]): gradient wrt z arriving from outside (autograd of a consumer of z); jh (optional): property head.
 template <typename TA>
 int step_t(const MDims& d, const MWS& w, const float* const* P, float* const* G, const uint8_t* ids,
            const int* lens, const float* eps, float* out_scalars, float* z_out, float* lv_out, float* y_out,
-           bool backward, cudaStream_t st, const int* act) {
+           bool backward, cudaStream_t st, const int* act, int phase = -1, const float* dz_ext = nullptr,
+           const JointHead* jh = nullptr) {
   const int B = d.B, Bp = d.Bp, T = d.T, V = d.V, CP = d.CP, Z = d.Z, Hq = d.Hq, Hd = d.Hd, L = d.L, ML = d.MLP;
   const int TB = T * Bp;
   const int IN0 = V + Z;   // decoder layer-0 input width
   const int Hin = d.Hin;
   const MP ix{d.bidir, d.lin, L};
-  // ---- control + weight preparation
-  RC(memset_async(w.err_flag, 4, st)); RC(memset_async(w.kl_sum, 8, st)); RC(memset_async(w.nll_sum, 8, st));
-  RC(memset_async(w.M, 4, st));
-  count_targets_kernel<<<1, 256, 0, st>>>(lens, B, w.M); KCHECK();
+  if (phase >= L) return MVAE_ERR_INVALID;
   // packed sequences: the big time-major GEMMs skip output tiles (mode 1) / k-blocks (mode 2) past the running sequences
   mvae_umma_varlen vlm{w.act_dev, Bp, 1}, vlk{w.act_dev, Bp, 2};
   const mvae_umma_varlen* VLM = (act && d.bf16 && varlen_gemm_enabled()) ? &vlm : nullptr;
   const mvae_umma_varlen* VLK = (act && d.bf16 && varlen_gemm_enabled()) ? &vlk : nullptr;
+  const bool prec_enc = sizeof(TA) == 2 && persistent_encoder(d);
+  const bool prec = sizeof(TA) == 2 && persistent_decoder(d);
+  const bool drop = d.drop > 0.f;
+  if (phase <= 0) {
+  // ---- control + weight preparation
+  RC(memset_async(w.err_flag, 4, st)); RC(memset_async(w.kl_sum, 8, st)); RC(memset_async(w.nll_sum, 8, st));
+  RC(memset_async(w.M, 4, st));
+  count_targets_kernel<<<1, 256, 0, st>>>(lens, B, w.M); KCHECK();
   if (VLM) { count_active_kernel<<<ceil_div(max(T, Bp / 256), 128), 128, 0, st>>>(lens, B, T, w.act_dev, w.act256_dev, w.tileT, Bp); KCHECK(); }
+  }
   // persistent sweeps over packed sequences: row tile j runs only tileT[j] steps; the GEMMs that feed / follow them skip the
   // same (t, 256-row tile) regions, which are then neither written nor read
   mvae_umma_varlen vlm256{w.act256_dev, Bp, 1};
   const mvae_umma_varlen* VLS = VLM ? &vlm256 : nullptr;
   const int* tileT = VLM ? w.tileT : nullptr;
   const int* lim256 = VLM ? w.act256_dev : nullptr;
+  if (phase <= 0) {
   simt::pad_gate_matrix_kernel<TA><<<grid_for(3ll * Hq * Hq), 256, 0, st>>>(P[ix.e_whh(0)], Hq, Hq, (TA*)w.Whh_enc, Hq, Hq, 0, 1, 2); KCHECK();
   simt::pad_gate_vector_kernel<<<ceil_div(3 * Hq, 256), 256, 0, st>>>(P[ix.e_bhh(0)], Hq, w.bhh_enc, Hq); KCHECK();
   if (d.bidir) {
@@ -662,8 +701,6 @@ int step_t(const MDims& d, const MWS& w, const float* const* P, float* const* G,
   // ---- encoder: table look-up projection, GRU, final state, MLP heads, reparametrise + KL
   RC(sg(st, P[ix.emb()], V, 1, P[ix.e_wih(0)], 1, V, w.TBLe, 3 * Hq, V, 3 * Hq, V, P[ix.e_bih(0)], simt::ACT_NONE, 0));
   RC(memset_async(w.hlast, (size_t)Bp * Hq * 4, st));
-  const bool prec_enc = sizeof(TA) == 2 && persistent_encoder(d);
-  const bool prec = sizeof(TA) == 2 && persistent_decoder(d);
   if (prec_enc || prec) {
     transpose_ids_kernel<<<grid_for((long long)TB), 256, 0, st>>>(ids, T, B, Bp, T, w.tokT); KCHECK();
   }
@@ -724,7 +761,6 @@ int step_t(const MDims& d, const MWS& w, const float* const* P, float* const* G,
   } else {
     gather_rows_kernel<TA><<<grid_for((long long)TB * 3 * Hd), 256, 0, st>>>(w.TBLd, 3 * Hd, ids, T, w.zproj, B, Bp, T, (TA*)w.gi); KCHECK();
   }
-  const bool drop = d.drop > 0.f;
   for (int l = 0; l < L; ++l) {
     if (l >= 1) {
       const TA* X = (const TA*)w.hs[l - 1] + (size_t)Bp * Hd;
@@ -772,11 +808,22 @@ int step_t(const MDims& d, const MWS& w, const float* const* P, float* const* G,
   finalize_kernel<<<1, 1, 0, st>>>(w.kl_sum, w.nll_sum, w.M, B, d.kl_w, d.rec_w, out_scalars); KCHECK();
   if (z_out) { mvae_count_launches(1); MVAE_CUDA_CHECK(cudaMemcpyAsync(z_out, w.z, (size_t)B * Z * 4, cudaMemcpyDeviceToDevice, st)); }
   if (lv_out) { mvae_count_launches(1); MVAE_CUDA_CHECK(cudaMemcpyAsync(lv_out, w.lv, (size_t)B * Z * 4, cudaMemcpyDeviceToDevice, st)); }
+  if (jh) {
+    // property head between the two halves of the step: prediction, MSE against the target, its backward (parameter
+    // gradients + dL/dz, which joins the decoder's gradient wrt z below)
+    RC(mvae_binding_forward(jh->desc, jh->params, jh->running, w.z, jh->pred, jh->ws, jh->ws_bytes, reinterpret_cast<mvae_stream_t>(st)));
+    mse_head_kernel<<<1, 256, 0, st>>>(jh->pred, jh->target, B, jh->weight, jh->dout, jh->loss_out); KCHECK();
+    if (backward)
+      RC(mvae_binding_backward(jh->desc, jh->params, jh->grads, w.z, jh->dout, jh->dz, jh->ws, jh->ws_bytes, reinterpret_cast<mvae_stream_t>(st)));
+    mvae_count_launches(24);
+  }
   if (!backward) { simt::nan_if_error_kernel<<<1, 1, 0, st>>>(w.err_flag, out_scalars); KCHECK(); return MVAE_OK; }
+  }   // phase <= 0: forward half
 
   // =================================== backward ===================================
   const TA* dlog = (const TA*)w.dlogits;
   const int wsplits = d.bf16 ? 12 : 64;
+  if (phase <= 0) {
   onehot_rows_kernel<TA><<<grid_for((long long)TB * CP), 256, 0, st>>>(ids, T, B, Bp, T, CP, (TA*)w.OH); KCHECK();
   // head
   // persistent BPTT: dX in the row-blocked layout, every row written (zeros past a sequence's end, where dlogits is zero)
@@ -789,9 +836,11 @@ int step_t(const MDims& d, const MWS& w, const float* const* P, float* const* G,
   RC(memset_async(w.csum, (size_t)4 * Hd * 4, st));
   RC(simt::colsum<TA>(st, dlog, TB, CP, CP, w.csum)); mvae_count_launches(1);
   simt::pad_matrix_kernel<float><<<1, 64, 0, st>>>(w.csum, 1, V, G[ix.fcb()], 1, V); KCHECK();
-  // decoder GRU stack
   RC(memset_async(w.dh0, (size_t)Bp * Hd * 4, st));
+  }   // phase <= 0: head
+  // decoder GRU stack
   for (int l = L - 1; l >= 0; --l) {
+    if (phase >= 0 && l != L - 1 - phase) continue;
     const TA* hs = (const TA*)w.hs[l];
     TA* dG = (TA*)w.dG;
     bool swept = false;
@@ -844,6 +893,7 @@ int step_t(const MDims& d, const MWS& w, const float* const* P, float* const* G,
       }
     }
   }
+  if (phase >= 0 && phase != L - 1) return MVAE_OK;
   // decoder layer-0 input weights: W_ih[:, :V] through the table, W_ih[:, V:] through z
   tbl_grad_to_rzn_T_kernel<<<(unsigned)ceil_div64(3ll * Hd * V, 256), 256, 0, st>>>(w.dTBL, Hd, V, w.dWT); KCHECK();
   //   dW_ih[:, :V] = dTBL_rzn^T(3Hd x V) * E (V x V)
@@ -862,6 +912,9 @@ int step_t(const MDims& d, const MWS& w, const float* const* P, float* const* G,
   RC(memset_async(G[ix.latb()], (size_t)Hd * 4, st));
   RC(simt::colsum<float>(st, w.dh0, B, Hd, Hd, G[ix.latb()])); mvae_count_launches(1);
   RC(sg(st, w.dh0, Hd, 1, P[ix.latw()], Z, 1, w.dz, Z, B, Z, Hd, nullptr, simt::ACT_NONE, 1, 4));
+  // gradient wrt z from consumers of z outside the VAE (autograd) / from the property head
+  if (dz_ext) { add_inplace_kernel<<<grid_for((long long)B * Z), 256, 0, st>>>(w.dz, dz_ext, (long long)B * Z); KCHECK(); }
+  if (jh) { add_inplace_kernel<<<grid_for((long long)B * Z), 256, 0, st>>>(w.dz, jh->dz, (long long)B * Z); KCHECK(); }
   // reparametrisation + KL
   const long long nBZ = (long long)B * Z;
   reparam_kl_std_bwd_kernel<<<grid_for(nBZ), 256, 0, st>>>(w.mu, w.lv, eps, w.dz, d.kl_w / (float)B, nBZ, w.dmu, w.dlv); KCHECK();
@@ -1202,14 +1255,16 @@ size_t mvae_moses_workspace_bytes(const mvae_moses_desc* desc) {
   return w.total;
 }
 
-int mvae_moses_step(const mvae_moses_desc* desc, const float* const* params, float* const* grads, const uint8_t* ids,
-                    const int32_t* lengths, const int32_t* lengths_host, const float* eps, float* out_scalars, float* z_out,
-                    float* logvar_out, float* y_out, void* workspace, size_t workspace_bytes, mvae_stream_t stream) {
+static int moses_step_impl(const mvae_moses_desc* desc, const float* const* params, float* const* grads, const uint8_t* ids,
+                           const int32_t* lengths, const int32_t* lengths_host, const float* eps, float* out_scalars, float* z_out,
+                           float* logvar_out, float* y_out, void* workspace, size_t workspace_bytes, mvae_stream_t stream,
+                           int phase, const float* dz_ext, const JointHead* jh) {
   MDims d; MWS w;
   RC(check_ws(desc, workspace, workspace_bytes, &d, &w));
   if (!params || !ids || !lengths || !eps || !out_scalars) return MVAE_ERR_INVALID;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const bool backward = grads != nullptr;
+  if (phase >= 0 && !backward) return MVAE_ERR_INVALID;
   // packed-sequence batch sizes (torch pack_sequence): act[t] = number of sequences longer than t; with the batch sorted
   // by length they are the rows [0, act[t]).  Needs the host copy of the lengths; without it every step covers all rows.
   int act_buf[512];
@@ -1225,8 +1280,57 @@ int mvae_moses_step(const mvae_moses_desc* desc, const float* const* params, flo
     }
     act = act_buf;
   }
-  return d.bf16 ? step_t<__nv_bfloat16>(d, w, params, grads, ids, lengths, eps, out_scalars, z_out, logvar_out, y_out, backward, st, act)
-                : step_t<float>(d, w, params, grads, ids, lengths, eps, out_scalars, z_out, logvar_out, y_out, backward, st, act);
+  return d.bf16 ? step_t<__nv_bfloat16>(d, w, params, grads, ids, lengths, eps, out_scalars, z_out, logvar_out, y_out, backward, st, act,
+                                        phase, dz_ext, jh)
+                : step_t<float>(d, w, params, grads, ids, lengths, eps, out_scalars, z_out, logvar_out, y_out, backward, st, act, phase,
+                                dz_ext, jh);
+}
+
+int mvae_moses_step(const mvae_moses_desc* desc, const float* const* params, float* const* grads, const uint8_t* ids,
+                    const int32_t* lengths, const int32_t* lengths_host, const float* eps, float* out_scalars, float* z_out,
+                    float* logvar_out, float* y_out, void* workspace, size_t workspace_bytes, mvae_stream_t stream) {
+  return moses_step_impl(desc, params, grads, ids, lengths, lengths_host, eps, out_scalars, z_out, logvar_out, y_out, workspace,
+                         workspace_bytes, stream, -1, nullptr, nullptr);
+}
+
+int mvae_moses_step_ex(const mvae_moses_desc* desc, const float* const* params, float* const* grads, const uint8_t* ids,
+                       const int32_t* lengths, const int32_t* lengths_host, const float* eps, const float* dz_ext,
+                       float* out_scalars, float* z_out, float* logvar_out, float* y_out, void* workspace,
+                       size_t workspace_bytes, int phase, mvae_stream_t stream) {
+  return moses_step_impl(desc, params, grads, ids, lengths, lengths_host, eps, out_scalars, z_out, logvar_out, y_out, workspace,
+                         workspace_bytes, stream, phase, dz_ext, nullptr);
+}
+
+size_t mvae_moses_joint_extra_bytes(const mvae_moses_desc* desc) {
+  // pred [B] + dout [B] + dz [B][Z] + loss (16 B), each 256-byte aligned
+  if (!desc || desc->batch <= 0 || desc->d_z <= 0) return 0;
+  const size_t B = desc->batch, Z = desc->d_z;
+  auto up = [](size_t n) { return (n + 255) & ~size_t(255); };
+  return up(B * 4) * 2 + up(B * Z * 4) + 256;
+}
+
+int mvae_moses_joint_step(const mvae_moses_desc* desc, const float* const* params, float* const* grads, const uint8_t* ids,
+                          const int32_t* lengths, const int32_t* lengths_host, const float* eps,
+                          const mvae_binding_desc* bdesc, const float* const* bparams, float* const* bgrads,
+                          float* const* brunning, const float* target, float binding_weight, float* out_scalars,
+                          float* binding_loss_out, float* z_out, void* workspace, size_t workspace_bytes,
+                          void* binding_workspace, size_t binding_workspace_bytes, void* extra, size_t extra_bytes, int phase,
+                          mvae_stream_t stream) {
+  if (!bdesc || !bparams || !brunning || !target || !binding_loss_out || !binding_workspace || !extra) return MVAE_ERR_INVALID;
+  if (grads && !bgrads) return MVAE_ERR_INVALID;
+  if (bdesc->batch != desc->batch || bdesc->z_size != desc->d_z) return MVAE_ERR_INVALID;
+  if (extra_bytes < mvae_moses_joint_extra_bytes(desc) || (reinterpret_cast<uintptr_t>(extra) & 255)) return MVAE_ERR_WORKSPACE;
+  const size_t B = desc->batch, Z = desc->d_z;
+  auto up = [](size_t n) { return (n + 255) & ~size_t(255); };
+  uint8_t* e = reinterpret_cast<uint8_t*>(extra);
+  JointHead jh{bdesc, bparams, bgrads, brunning, target, binding_weight, nullptr, nullptr, nullptr, binding_loss_out,
+               binding_workspace, binding_workspace_bytes};
+  jh.pred = reinterpret_cast<float*>(e); e += up(B * 4);
+  jh.dout = reinterpret_cast<float*>(e); e += up(B * 4);
+  jh.dz = reinterpret_cast<float*>(e);
+  (void)Z;
+  return moses_step_impl(desc, params, grads, ids, lengths, lengths_host, eps, out_scalars, z_out, nullptr, nullptr, workspace,
+                         workspace_bytes, stream, phase, nullptr, &jh);
 }
 
 int mvae_moses_sample(const mvae_moses_desc* desc, const float* const* params, const float* z, int bos_id, int eos_id,

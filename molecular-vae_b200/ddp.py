@@ -53,24 +53,28 @@ def phase_buckets(keys, numels, layers):
 
 class PhasedAllReduce:
     """Bucketed gradient exchange overlapped with the backward sweep: launch phase p, start the all-reduce of its bucket
-    on NCCL's stream (it waits for the work enqueued so far), launch phase p+1 meanwhile; finish() joins and averages."""
+    on NCCL's stream (it waits for the work enqueued so far), launch phase p+1 meanwhile; finish() joins.  The mean over
+    the ranks is taken by the collective itself (NCCL's AVG reduction) -- no separate pass over the flat buffer; backends
+    without AVG (gloo, the CPU tests) sum and divide."""
 
     def __init__(self, flat, buckets, group=None):
         self.flat, self.buckets, self.group = flat, buckets, group
         self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        self._avg = self.world > 1 and dist.get_backend(group) == "nccl"
         self._pending = []
 
     def after_phase(self, p):
         if self.world == 1:
             return
         lo, hi = self.buckets[p]
-        self._pending.append(dist.all_reduce(self.flat[lo:hi], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+        op = dist.ReduceOp.AVG if self._avg else dist.ReduceOp.SUM
+        self._pending.append(dist.all_reduce(self.flat[lo:hi], op=op, group=self.group, async_op=True))
 
     def finish(self):
         for w in self._pending:
             w.wait()
         self._pending = []
-        if self.world > 1:
+        if self.world > 1 and not self._avg:
             self.flat.div_(self.world)
 
 
@@ -104,3 +108,80 @@ def moses_rank_weights(n_sequences, n_targets, group=None):
     dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
     tot_b, tot_m = (float(v) for v in t.cpu())
     return world * float(n_sequences) / tot_b, world * float(n_targets) / tot_m
+
+
+def moses_readiness_order(keys, d_layers, head_keys=()):
+    """Backward-readiness order of the MOSES VAE's parameters (`keys` in C-ABI order, mosesvae.moses_param_order /
+    mosesfile.mosesfile_param_order; `head_keys` = the property head's parameters) and, per phase of
+    mvae_moses_step_ex / mvae_moses_joint_step, how many leading keys of that order are final after the phase:
+      phase 0   decoder_fc, the top decoder layer, the property head
+      phase k   decoder layer d_layers-1-k
+      last      decoder layer 0, decoder_lat, the mu / logvar heads, the encoder GRU(s), x_emb
+    A FlatGradBuffer laid out in this order makes every phase's bucket one contiguous slice."""
+    layer = lambda l: [k for k in keys if k.startswith("decoder_rnn.") and k.endswith(f"_l{l}")]
+    order, cuts = [], []
+    top = d_layers - 1
+    order += [k for k in keys if k.startswith("decoder_fc.")] + layer(top) + list(head_keys)
+    for p in range(d_layers):
+        if p > 0:
+            order += layer(top - p)
+        if p == d_layers - 1:
+            order += [k for k in keys if k not in order]
+        cuts.append(len(order))
+    return order, cuts
+
+
+class MosesPhasedStep:
+    """Data-parallel step of the MOSES VAE (optionally with the property head) over FIXED buffers: one CUDA graph per phase
+    of the fused step, the gradient bucket a phase finalises is all-reduced on NCCL's stream while the next phase's BPTT sweep
+    runs (the reference's only multi-GPU mechanism for this model is the commented-out DDP of moses_train_distrib.py:30-42,191).
+    Loss semantics: KL and the property loss are means over the GLOBAL batch, the reconstruction CE a mean over
+    the GLOBAL count of non-pad targets, so rank r runs with kl_weight * N B_r / B, recon_weight * N M_r / M and
+    binding_weight * N B_r / B (moses_rank_weights) and the exchange averages."""
+
+    def __init__(self, model, x, eps, kl_weight=1.0, recon_weight=1.0, binding=None, binding_weight=1.0, dropout=None,
+                 group=None):
+        self.model, self.group = model, group
+        _, self.ids, self.lens = model._pack(x)
+        dev = self.ids.device
+        self.eps = eps.to(dev, torch.float32).contiguous()
+        B = self.ids.shape[0]
+        M = int(self.lens._host_copy.sum()) - B
+        ks, rs = moses_rank_weights(B, M, group)
+        self.kl_weight, self.recon_weight = kl_weight * ks, recon_weight * rs
+        self.dropout = dropout if dropout is not None else model._dropout()
+        L = model.cfg["d_layers"]
+        named = dict(model.named_parameters())
+        head = getattr(model, "binding_model", None) if binding is not None else None
+        head_keys = [f"binding_model.binding_model.{k}" for k in head.KEYS] if head is not None else []
+        order, cuts = moses_readiness_order(model._keys, L, head_keys)
+        self.gbuf = FlatGradBuffer([named[k] for k in order])
+        numel = [named[k].numel() for k in order]
+        ends = [sum(numel[:c]) for c in cuts]
+        self.buckets = [(0 if i == 0 else ends[i - 1], ends[i]) for i in range(L)]
+        self.params = [named[k].data for k in model._keys]
+        self.grads = [named[k].grad for k in model._keys]
+        self.joint = None
+        if head is not None:
+            self.target = binding.to(dev, torch.float32).contiguous().view(-1)
+            self.joint = (head, self.target, binding_weight * ks, [named[k].grad for k in head_keys])
+        self.reducer = PhasedAllReduce(self.gbuf.flat, self.buckets, group)
+        self.graphs = []
+        self._run_phase(-1)                      # warm-up outside capture: workspaces, scratch, opt-in shared memory
+        torch.cuda.synchronize()
+        for p in range(L):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._run_phase(p)
+            self.graphs.append(g)
+
+    def _run_phase(self, p):
+        self.model._run(self.params, self.grads, self.ids, self.lens, self.eps, self.kl_weight, self.recon_weight, False,
+                        dropout=self.dropout, phase=p, joint=self.joint)
+
+    def step(self):
+        for p, g in enumerate(self.graphs):
+            g.replay()
+            self.reducer.after_phase(p)
+        self.reducer.finish()
+        return self.model._last_scalars

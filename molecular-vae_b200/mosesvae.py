@@ -52,7 +52,9 @@ class _MosesFunction(torch.autograd.Function):
         kl, recon, z, logvar, y = model._run(list(params), None, ids, lens, eps, 1.0, 1.0, want_y=True, dropout=ctx.dropout)
         ctx.model, ctx.ids, ctx.lens, ctx.eps = model, ids, lens, eps
         ctx.save_for_backward(*params)
-        ctx.mark_non_differentiable(z, logvar, y)
+        # z stays differentiable: a property head that consumes it (BindingModel, trainbinding.py:216-217 /
+        # moses_train_distrib.py:274) sends its gradient back through dz
+        ctx.mark_non_differentiable(logvar, y)
         return kl, recon, z, logvar, y
 
     @staticmethod
@@ -61,7 +63,8 @@ class _MosesFunction(torch.autograd.Function):
         grads = [torch.empty_like(p) for p in params]
         klw = float(dkl) if dkl is not None else 0.0
         rw = float(drecon) if drecon is not None else 0.0
-        ctx.model._run(params, grads, ctx.ids, ctx.lens, ctx.eps, klw, rw, want_y=False, dropout=ctx.dropout)
+        dz_ext = None if dz is None else dz.contiguous().float()
+        ctx.model._run(params, grads, ctx.ids, ctx.lens, ctx.eps, klw, rw, want_y=False, dropout=ctx.dropout, dz_ext=dz_ext)
         return (None, None, None, None, *grads)
 
 
@@ -143,7 +146,7 @@ class BindingModel(nn.Module):
 
 
 class VAE(nn.Module):
-    def __init__(self, vocab, precision="bf16"):
+    def __init__(self, vocab, precision="bf16", property_head=False):
         super().__init__()
         q_d_h, q_n_layers, d_n_layers, d_dropout, d_z, d_d_h = 256, 1, 3, 0.2, 160, 512
         self.vocabulary = vocab
@@ -168,6 +171,15 @@ class VAE(nn.Module):
         self._ws = None
         self.eps_override = None
         self.dropout_seed_override = None   # tests pin the counter-based dropout mask here
+        if property_head:
+            self.attach_property_head()
+
+    def attach_property_head(self, head=None):
+        """`model.binding_model`: the BindingModel MLP on z that the historical VAE carried (mosesanalyize.py:177 optimises
+        `model.binding_model.parameters()`; moses_train_distrib.py:274 calls `model(input_batch, binding)`).  It is not a
+        member of the encoder / decoder / vae ModuleLists, so those optimiser groups stay as in mosesvae.py:90-105."""
+        self.binding_model = head if head is not None else BindingModel(self.cfg["d_z"])
+        return self.binding_model
 
     @property
     def device(self):
@@ -221,15 +233,22 @@ class VAE(nn.Module):
             return p, int(self.dropout_seed_override)
         return p, int(torch.randint(0, 2 ** 31 - 1, (1,)).item())
 
-    def _run(self, params, grads, ids, lens, eps, kl_weight, recon_weight, want_y, dropout=(0.0, 0)):
+    def _desc(self, B, T, kl_weight=1.0, recon_weight=1.0, dropout=(0.0, 0)):
+        c = self.cfg
+        prec = {"fp32": _lib.PREC_FP32, "bf16": _lib.PREC_BF16}[self.precision]
+        return MosesDesc(B, T, c["vocab"], c["d_z"], c["q_hidden"], c["d_hidden"], c["d_layers"], c["mlp_hidden"],
+                         int(self.pad), prec, float(kl_weight), float(recon_weight), int(c.get("q_bidir", 0)),
+                         int(c.get("q_linear_heads", 0)), float(dropout[0]), int(dropout[1]))
+
+    def _run(self, params, grads, ids, lens, eps, kl_weight, recon_weight, want_y, dropout=(0.0, 0), dz_ext=None, phase=-1,
+             joint=None):
+        """One call into the C ABI.  joint = (binding_model, target fp32 (B), weight, binding_grads or None): the VAE step with
+        the property head inside (mvae_moses_joint_step); otherwise mvae_moses_step_ex."""
         if not torch.cuda.is_available():
             raise _lib.MvaeError("molecular-vae_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
         B, T = ids.shape
         c = self.cfg
-        prec = {"fp32": _lib.PREC_FP32, "bf16": _lib.PREC_BF16}[self.precision]
-        d = MosesDesc(B, T, c["vocab"], c["d_z"], c["q_hidden"], c["d_hidden"], c["d_layers"], c["mlp_hidden"],
-                      int(self.pad), prec, float(kl_weight), float(recon_weight), int(c.get("q_bidir", 0)),
-                      int(c.get("q_linear_heads", 0)), float(dropout[0]), int(dropout[1]))
+        d = self._desc(B, T, kl_weight, recon_weight, dropout)
         need = lib.mvae_moses_workspace_bytes(ctypes.byref(d))
         if need == 0:
             raise ValueError("invalid MOSES VAE description")
@@ -237,16 +256,44 @@ class VAE(nn.Module):
         if self._ws is None or self._ws.numel() < need + 256 or self._ws.device != dev:
             self._ws = torch.empty(need + 256, dtype=torch.uint8, device=dev)
         wsp = ctypes.c_void_p(self._ws.data_ptr() + (-self._ws.data_ptr()) % 256)
-        out = torch.zeros(4, dtype=torch.float32, device=dev)
-        z = torch.empty(B, c["d_z"], dtype=torch.float32, device=dev)
-        lv = torch.empty_like(z)
+        # later phases of a phased step keep writing the scalars / z of phase 0
+        keep = getattr(self, "_phase_outputs", None) if phase > 0 else None
+        out = keep[0] if keep else torch.zeros(4, dtype=torch.float32, device=dev)
+        z = keep[1] if keep else torch.empty(B, c["d_z"], dtype=torch.float32, device=dev)
+        lv = keep[2] if keep else torch.empty_like(z)
+        if phase == 0:
+            self._phase_outputs = (out, z, lv)
         y = torch.empty(B, T, c["vocab"], dtype=torch.float32, device=dev) if want_y else None
         P = _ptr_table(params)
         G = _ptr_table(grads) if grads is not None else None
         lens_host = getattr(lens, "_host_copy", None)      # set by _pack: enables packed-sequence batch sizes per step
         with torch.cuda.device(dev):
-            check(lib.mvae_moses_step(ctypes.byref(d), P, G, _p(ids), _p(lens), _p(lens_host), _p(eps), _p(out), _p(z),
-                                      _p(lv), _p(y), wsp, need, _stream()))
+            if joint is None:
+                check(lib.mvae_moses_step_ex(ctypes.byref(d), P, G, _p(ids), _p(lens), _p(lens_host), _p(eps), _p(dz_ext), _p(out),
+                                             _p(z), _p(lv), _p(y), wsp, need, int(phase), _stream()))
+            else:
+                head, target, weight, bgrads = joint
+                bd, bneed = head._desc(B)
+                if head._ws is None or head._ws.numel() < bneed + 256 or head._ws.device != dev:
+                    head._ws = torch.empty(bneed + 256, dtype=torch.uint8, device=dev)
+                bwsp = ctypes.c_void_p(head._ws.data_ptr() + (-head._ws.data_ptr()) % 256)
+                xneed = lib.mvae_moses_joint_extra_bytes(ctypes.byref(d))
+                if getattr(self, "_joint_extra", None) is None or self._joint_extra.numel() < xneed + 256 or self._joint_extra.device != dev:
+                    self._joint_extra = torch.empty(xneed + 256, dtype=torch.uint8, device=dev)
+                    self._joint_loss = torch.zeros(1, dtype=torch.float32, device=dev)
+                xp = ctypes.c_void_p(self._joint_extra.data_ptr() + (-self._joint_extra.data_ptr()) % 256)
+                bn1, bn2 = head.binding_model[1], head.binding_model[6]
+                named = dict(head.binding_model.named_parameters())
+                bparams = [named[k].data for k in head.KEYS]
+                running = _ptr_table([bn1.running_mean, bn1.running_var, bn2.running_mean, bn2.running_var])
+                check(lib.mvae_moses_joint_step(ctypes.byref(d), P, G, _p(ids), _p(lens), _p(lens_host), _p(eps), ctypes.byref(bd),
+                                                _ptr_table(bparams), _ptr_table(bgrads) if bgrads is not None else None, running,
+                                                _p(target), float(weight), _p(out), _p(self._joint_loss), _p(z), wsp, need, bwsp,
+                                                bneed, xp, xneed, int(phase), _stream()))
+                head._generation += 1
+                if head.training and phase <= 0:
+                    bn1.num_batches_tracked += 1
+                    bn2.num_batches_tracked += 1
         self._last_desc = (d, wsp, need)
         self._last_scalars = out
         return out[1], out[2], z, lv, y
@@ -269,24 +316,46 @@ class VAE(nn.Module):
         return torch.randn(B, self.cfg["d_z"], device=dev, dtype=torch.float32)
 
     # -- reference API (mosesvae.py:126-140) ------------------------------------------------------------
-    def forward(self, x):
+    def forward(self, x, binding=None):
+        """mosesvae.py:126-140: (kl, recon, z, logvar, x_padded, y).  With `binding` (the property target, (B,) or (B,1)) the
+        historical signature of moses_train_distrib.py:274 / trainbinding.py:216: (kl, recon, binding_loss, z), where
+        binding_loss = mse(self.binding_model(z), binding) and z carries the autograd graph back into the encoder."""
         x_pad, ids, lens = self._pack(x)
         eps = self._eps(ids.shape[0], ids.device)
         params = [p if p.is_contiguous() else p.contiguous() for p in self.ordered_params()]
         kl, recon, z, logvar, y = _MosesFunction.apply(self, ids, lens, eps, *params)
-        return kl, recon, z, logvar, x_pad, y
+        if binding is None:
+            return kl, recon, z, logvar, x_pad, y
+        if getattr(self, "binding_model", None) is None:
+            raise RuntimeError("forward(x, binding) needs the property head: VAE(vocab, property_head=True) or attach_property_head()")
+        pred = self.binding_model(z)
+        binding_loss = nn.functional.mse_loss(pred, binding.to(pred.device, torch.float32).view(-1, 1))
+        return kl, recon, binding_loss, z
 
-    def elbo_step(self, x, kl_weight=1.0, recon_weight=1.0, eps=None):
-        """Fused forward + backward of kl_weight*kl + recon_weight*recon: fills p.grad and returns the device tensor
-        [loss, kl, recon, n_targets]."""
+    def elbo_step(self, x, kl_weight=1.0, recon_weight=1.0, eps=None, binding=None, binding_weight=1.0):
+        """Fused forward + backward of kl_weight*kl + recon_weight*recon (+ binding_weight*mse(binding_model(z), binding) when
+        a property target is given): fills p.grad (also of the property head) and returns the device tensor
+        [loss, kl, recon, n_targets]; the head's loss term is `self.last_binding_loss` (1-element device tensor)."""
         _, ids, lens = self._pack(x)
         eps = self._eps(ids.shape[0], ids.device) if eps is None else eps.to(ids.device, torch.float32).contiguous()
         params = self.ordered_params()
         for p in params:
             if p.grad is None:
                 p.grad = torch.empty_like(p)
+        joint = None
+        if binding is not None:
+            head = getattr(self, "binding_model", None)
+            if head is None:
+                raise RuntimeError("elbo_step(binding=...) needs the property head: VAE(vocab, property_head=True)")
+            named = dict(head.binding_model.named_parameters())
+            for k in head.KEYS:
+                if named[k].grad is None:
+                    named[k].grad = torch.empty_like(named[k])
+            joint = (head, binding.to(ids.device, torch.float32).contiguous().view(-1), binding_weight, [named[k].grad for k in head.KEYS])
         self._run([p.data for p in params], [p.grad for p in params], ids, lens, eps, kl_weight, recon_weight, False,
-                  dropout=self._dropout())
+                  dropout=self._dropout(), joint=joint)
+        if joint is not None:
+            self.last_binding_loss = self._joint_loss
         return self._last_scalars
 
     def sample_z_prior(self, n_batch):

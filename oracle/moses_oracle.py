@@ -155,9 +155,10 @@ def dropout_masks(seed, p, B, T, H, d_layers=3, dtype=np.float64):
     return out
 
 
-def moses_step(P, seqs, eps, pad, kl_weight=1.0, need_grads=True, d_layers=3, drop_masks=None):
+def moses_step(P, seqs, eps, pad, kl_weight=1.0, need_grads=True, d_layers=3, drop_masks=None, dz_ext=None):
     """One fwd(+bwd) step of mosesvae.VAE.forward; the scalar differentiated is kl_weight*kl + recon
-    (moses_train_distrib_logp.py:302-306)."""
+    (moses_train_distrib_logp.py:302-306).  dz_ext (B,d_z), optional: gradient wrt z of a loss term computed on z outside
+    the VAE (the property head of moses_train_distrib.py:274 / trainbinding.py:216-217), added where autograd would add it."""
     dt = P["decoder_fc.weight"].dtype
     x, L = pad_batch(seqs, pad)
     B, T = x.shape
@@ -228,6 +229,8 @@ def moses_step(P, seqs, eps, pad, kl_weight=1.0, need_grads=True, d_layers=3, dr
     G["decoder_lat.weight"] = dh0.T @ z
     G["decoder_lat.bias"] = dh0.sum(0)
     dz = dz + dh0 @ P["decoder_lat.weight"]
+    if dz_ext is not None:
+        dz = dz + dz_ext
     # ---- reparametrisation + KL (weights: kl_weight on kl, 1 on recon)
     dmu = dz + kl_weight * mu / B
     dlv = dz * eps.astype(dt) * std * 0.5 + kl_weight * 0.5 * (np.exp(lv) - 1) / B

@@ -128,3 +128,22 @@ def test_moses_rank_weights_reproduce_full_batch_gradients(tmp_path):
     full = mo.moses_step(P, seqs, eps, pad, kl_weight=0.3)
     for k, g in full["grads"].items():
         np.testing.assert_allclose(got[k], g, rtol=1e-8, atol=1e-11)
+
+
+def test_moses_readiness_order_tiles_the_parameters():
+    """ddp.moses_readiness_order: every C-ABI key (+ the property head's) exactly once, phase cuts increasing, the top
+    decoder layer / decoder_fc / head in phase 0 and decoder layer 0, encoder and x_emb in the last phase."""
+    import molecular_vae_b200 as m
+    from molecular_vae_b200.mosesfile import mosesfile_param_order
+    from molecular_vae_b200.mosesvae import BindingModel, moses_param_order
+    head = [f"binding_model.binding_model.{k}" for k in BindingModel.KEYS]
+    for keys in (moses_param_order(3), mosesfile_param_order(3), moses_param_order(1)):
+        L = 3 if any(k.endswith("_l2") for k in keys) else 1
+        for hk in ((), head):
+            order, cuts = m.ddp.moses_readiness_order(keys, L, hk)
+            assert sorted(order) == sorted(list(keys) + list(hk)) and len(cuts) == L and cuts[-1] == len(order)
+            assert all(a < b for a, b in zip(cuts, cuts[1:]))
+            first = order[:cuts[0]]
+            assert "decoder_fc.weight" in first and f"decoder_rnn.weight_hh_l{L - 1}" in first and all(k in first for k in hk)
+            last = order[cuts[-2] if L > 1 else 0:]
+            assert "x_emb.weight" in last and "decoder_rnn.weight_ih_l0" in last and "encoder_rnn.weight_hh_l0" in last

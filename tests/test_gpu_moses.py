@@ -98,7 +98,7 @@ def test_moses_dropin_forward_backward_and_state_dict():
     kl, recon, z, logvar, x_pad, y = model([torch.from_numpy(s).cuda() for s in seqs])
     assert y.shape == ref["y"].shape and x_pad.shape == ref["x"].shape
     np.testing.assert_allclose(y.detach().cpu().numpy(), ref["y"], rtol=2e-4, atol=2e-5)
-    np.testing.assert_allclose(z.cpu().numpy(), ref["z"], rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(z.detach().cpu().numpy(), ref["z"], rtol=1e-4, atol=1e-5)
     loss = 0.25 * kl + recon
     loss.backward()
     torch.cuda.synchronize()
@@ -454,3 +454,114 @@ def test_moses_persistent_sweeps_equal_per_step_engine_large_batch(monkeypatch, 
     assert abs(s1[1] - s0[1]) <= 2e-3 * abs(s0[1]) and abs(s1[2] - s0[2]) <= 2e-3 * abs(s0[2]) and s1[3] == s0[3], (s1, s0)
     bad = {k: rel_l2(g1[k], g0[k]) for k in g0 if not rel_l2(g1[k], g0[k]) <= 3e-2}
     assert not bad, bad
+
+
+# ---- BASELINE.json configs[3]: the VAE step with the property head, phases for data parallelism ----
+def _joint_oracle(P, Pb, run, seqs, eps, pad, target, klw, bw):
+    fwd = mo.moses_step({k: v.astype(np.float64) for k, v in P.items()}, seqs, eps.astype(np.float64), pad, kl_weight=klw, need_grads=False)
+    from oracle import binding_oracle as bo
+    P64 = {k: v.astype(np.float64) for k, v in Pb.items()}
+    R64 = {k: v.astype(np.float64) for k, v in run.items()}
+    pred = bo.binding_step(P64, R64, fwd["z"], None, train=True)["out"].reshape(-1)
+    B = len(seqs)
+    bloss = bw * float(((pred - target) ** 2).mean())
+    head = bo.binding_step(P64, R64, fwd["z"], bw * 2.0 * (pred - target) / B, train=True)
+    ref = mo.moses_step({k: v.astype(np.float64) for k, v in P.items()}, seqs, eps.astype(np.float64), pad, kl_weight=klw,
+                        dz_ext=head["dz"])
+    return ref, head, bloss
+
+
+def _joint_setup(m, precision, B):
+    from oracle import binding_oracle as bo
+    P, seqs, eps, pad, model = _setup(m, precision, 351, 451 + B, B)
+    Pb, run = bo.make_binding_params(551, 160, dtype=np.float32)
+    head = model.attach_property_head()
+    sd = head.state_dict()
+    with torch.no_grad():
+        for k, v in {**Pb, **run}.items():
+            sd["binding_model." + k].copy_(torch.from_numpy(v))
+    model = model.cuda()
+    model.eval()                 # VAE dropout off (fixtures / oracle have none) ...
+    head.train()                 # ... while the head's BatchNorm uses batch statistics, as in moses_train_distrib.py:262-264
+    target = np.random.Generator(np.random.PCG64(9)).uniform(0, 1, size=B).astype(np.float32)
+    return P, Pb, run, seqs, eps, pad, model, head, target
+
+
+@pytest.mark.parametrize("precision,B,ltol,gtol", [("fp32", 24, 1e-5, 2e-5), ("bf16", 300, BF16_LTOL, BF16_GTOL)])
+def test_moses_joint_step_with_property_head(precision, B, ltol, gtol):
+    """mvae_moses_joint_step: kl_weight*kl + recon + binding_weight*mse(BindingModel(z), target) differentiated in one fused
+    call -- VAE gradients incl. the head's gradient through z, and the head's own gradients -- against the two oracles."""
+    m = load_pkg()
+    klw, bw = 0.3, 2.0
+    P, Pb, run, seqs, eps, pad, model, head, target = _joint_setup(m, precision, B)
+    ref, href, bloss = _joint_oracle(P, Pb, run, seqs, eps, pad, target.astype(np.float64), klw, bw)
+    x = [torch.from_numpy(s).cuda() for s in seqs]
+    out = model.elbo_step(x, kl_weight=klw, eps=torch.from_numpy(eps).cuda(), binding=torch.from_numpy(target), binding_weight=bw)
+    torch.cuda.synchronize()
+    model.check_device_error()
+    sc = out.cpu().numpy()
+    assert abs(sc[1] - ref["kl"]) <= ltol * abs(ref["kl"]) and abs(sc[2] - ref["recon"]) <= ltol * abs(ref["recon"])
+    assert abs(float(model.last_binding_loss) - bloss) <= max(ltol, 2e-5) * abs(bloss) * (50 if precision == "bf16" else 1)
+    bad = {k: rel_l2(p.grad.cpu().numpy(), ref["grads"][k]) for k, p in model.named_parameters() if k in ref["grads"]}
+    bad = {k: e for k, e in bad.items() if not e <= gtol}
+    assert not bad, bad
+    for k, p in head.binding_model.named_parameters():
+        got, want = p.grad.cpu().numpy().astype(np.float64), href["grads"][k]
+        tol = 5e-5 if precision == "fp32" else 2e-2     # in bf16 mode z itself carries the VAE's bf16 error
+        assert np.sqrt(((got - want) ** 2).sum()) <= tol * np.sqrt((want ** 2).sum()) + 5e-5, k
+
+
+def test_moses_forward_with_binding_signature_and_autograd():
+    """Historical call `kl, recon, binding_loss, z = model(input_batch, binding)` (moses_train_distrib.py:274): the drop-in
+    composes the VAE autograd function, the BindingModel autograd function and mse; gradients equal the fused joint step."""
+    m = load_pkg()
+    klw = 0.3
+    P, Pb, run, seqs, eps, pad, model, head, target = _joint_setup(m, "fp32", 17)
+    ref, href, bloss = _joint_oracle(P, Pb, run, seqs, eps, pad, target.astype(np.float64), klw, 1.0)
+    model.eps_override = torch.from_numpy(eps)
+    out = model([torch.from_numpy(s).cuda() for s in seqs], torch.from_numpy(target).cuda().view(-1, 1))
+    assert len(out) == 4
+    kl, recon, binding_loss, z = out
+    assert z.shape == (17, 160) and z.requires_grad
+    loss = min(1.0, klw) * kl + recon + binding_loss          # moses_train_distrib.py:287
+    loss.backward()
+    torch.cuda.synchronize()
+    assert abs(float(binding_loss.detach()) - bloss) <= 2e-5 * abs(bloss)
+    bad = {k: rel_l2(p.grad.cpu().numpy(), ref["grads"][k]) for k, p in model.named_parameters() if k in ref["grads"]}
+    bad = {k: e for k, e in bad.items() if not e <= 2e-5}
+    assert not bad, bad
+    for k, p in head.binding_model.named_parameters():
+        got, want = p.grad.cpu().numpy().astype(np.float64), href["grads"][k]
+        assert np.sqrt(((got - want) ** 2).sum()) <= 5e-5 * np.sqrt((want ** 2).sum()) + 5e-5, k
+
+
+@pytest.mark.parametrize("with_head", [False, True])
+def test_moses_phased_step_equals_fused_step(with_head):
+    """mvae_moses_step_ex / mvae_moses_joint_step phases 0..L-1 (data-parallel bucket order) == the one-call step, and after
+    phase p the contiguous bucket p of the readiness-ordered flat gradient buffer is already final (ddp.MosesPhasedStep)."""
+    m = load_pkg()
+    B, klw = 300, 0.1
+    P, Pb, run, seqs, eps, pad, model, head, target = _joint_setup(m, "bf16", B)
+    x = [torch.from_numpy(s).cuda() for s in seqs]
+    epst = torch.from_numpy(eps).cuda()
+    tgt = torch.from_numpy(target) if with_head else None
+    model.elbo_step(x, kl_weight=klw, eps=epst, binding=tgt, binding_weight=1.5)
+    torch.cuda.synchronize()
+    want = {k: p.grad.detach().clone() for k, p in model.named_parameters() if p.grad is not None}
+    sc_ref = model._last_scalars.clone()
+    step = m.ddp.MosesPhasedStep(model, x, epst, kl_weight=klw, binding=tgt, binding_weight=1.5)
+    assert len(step.graphs) == 3 and step.buckets[0][0] == 0 and step.buckets[-1][1] == step.gbuf.flat.numel()
+    step.gbuf.flat.fill_(float("nan"))
+    for p, g in enumerate(step.graphs):
+        g.replay()
+        torch.cuda.synchronize()
+        lo, hi = step.buckets[p]
+        assert torch.isfinite(step.gbuf.flat[lo:hi]).all(), p
+    model.check_device_error()
+    named = dict(model.named_parameters())
+    for k, w_ in want.items():
+        if not with_head and k.startswith("binding_model."):
+            continue
+        err = float((named[k].grad - w_).norm() / (w_.norm() + 1e-30))
+        assert err < 2e-3, (k, err)                           # split-K atomics reorder fp32 sums between runs
+    assert abs(float(model._last_scalars[0]) - float(sc_ref[0])) <= 1e-5 * abs(float(sc_ref[0]))
