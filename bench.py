@@ -197,15 +197,29 @@ class _BenchVocab:
         return "".join(self.chars[i] if i < len(self.chars) else "?" for i in ids)
 
 
-def sampling_rate(batch=8192, max_len=100, reps=3):
+def sampling_rate(batch=8192, max_len=100, reps=3, n_total=0, target_mean_len=45.0):
     """BASELINE.json's second metric, 'sampled SMILES/sec' (hugesample.py:113 batch 8192, mosesvae.py:214 max_len 100):
-    greedy decodes of N(0,I) latents through mosesvae.VAE.sample's device path, random-init weights, CUDA events."""
+    greedy decodes of N(0,I) latents through mosesvae.VAE.sample.  `value`: device rate of the decode loop alone (CUDA events,
+    ids stay on the device).  `e2e`: the reference's own definition (hugesample.py:94: strings delivered per wall second) --
+    n_total latents through VAE.sample_many: prior draw, decode, device-side text assembly, device -> host copy, Python strings.
+    No trained checkpoint exists (the data blobs are absent), so the weights are random-init; the <eos> bias of decoder_fc is
+    calibrated so that greedy decodes end after ~target_mean_len tokens (ZINC-like) instead of never."""
     import torch
     import molecular_vae_b200 as m
     torch.manual_seed(0)
     model = m.mosesvae.VAE(_BenchVocab(), precision="bf16").cuda().eval()
     z = torch.randn(batch, 160, device="cuda")
-    model.sample_ids(batch, max_len=max_len, z=z, greedy=True)
+    lo, hi = -1.0, 3.0
+    for _ in range(12):          # bisection on the <eos> logit bias (monotone: larger bias -> earlier <eos>)
+        mid = 0.5 * (lo + hi)
+        with torch.no_grad():
+            model.decoder_fc.bias[model.eos] = mid
+        _, lens, _ = model.sample_ids(batch, max_len=max_len, z=z, greedy=True)
+        ml = float(lens.float().mean().item())
+        if ml > target_mean_len:
+            lo = mid
+        else:
+            hi = mid
     torch.cuda.synchronize()
     model.check_device_error()
     st = torch.cuda.current_stream()
@@ -216,47 +230,80 @@ def sampling_rate(batch=8192, max_len=100, reps=3):
     e1.record(st)
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
-    return {"metric": "sampled SMILES/sec (greedy, N(0,I) latents)", "value": batch / ms * 1e3, "unit": "SMILES/s",
-            "ms_per_batch": ms, "batch": batch, "max_len": max_len, "mean_len": float(lens.float().mean().item()),
-            "workload": "mosesvae.VAE.sample device path (3x512 GRU decoder, d_z 160, V=34), bf16, random-init weights"}
+    out = {"metric": "sampled SMILES/sec (greedy, N(0,I) latents)", "value": batch / ms * 1e3, "unit": "SMILES/s",
+           "ms_per_batch": ms, "batch": batch, "max_len": max_len, "mean_len": float(lens.float().mean().item()),
+           "workload": "mosesvae.VAE.sample device path (3x512 GRU decoder, d_z 160, V=34), bf16, random-init weights, <eos> bias calibrated"}
+    if n_total > 0:
+        for strs in model.sample_many(2 * batch, n_batch=batch, max_len=max_len, greedy=True, seed=1):   # warm
+            pass
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        n, nbytes = 0, 0
+        for strs in model.sample_many(n_total, n_batch=batch, max_len=max_len, greedy=True, seed=2):
+            n += len(strs)
+            nbytes += len(strs[0])
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        out["e2e"] = {"value": n / dt, "unit": "SMILES/s", "strings": n, "seconds": dt, "sample": strs[0][:60],
+                      "d2h_bytes_per_batch": batch * max_len + 4 * (batch + 1), "h2d_bytes_per_batch": 8,
+                      "path": "VAE.sample_many: prior draw -> 99-step decode (CUDA graph) -> ids_to_text on device -> one D2H -> list[str]"}
+    return out
 
 
-def moses_step_rate(batch=4096, reps=5):
-    """Side measurement for BASELINE.json configs[3] on ONE GPU: fused fwd+bwd step of mosesvae.VAE (encoder GRU 256, d_z 160,
-    decoder GRU 3x512, V=34; SURVEY.md 8d config 4 inputs: lengths ~ clip(N(44,9),10,98) + bos/eos, sorted descending), bf16,
-    train mode (dropout 0.2), batch 4096, CUDA-graph replay of the step over resident inputs, CUDA events."""
+class _BenchCfg:   # config.py:4-85 defaults with --q_bidir (BASELINE.json configs[3]: bidirectional encoder, latent 128)
+    q_cell, q_bidir, q_d_h, q_n_layers, q_dropout = "gru", True, 256, 1, 0.5
+    d_cell, d_n_layers, d_dropout, d_z, d_d_h, freeze_embeddings = "gru", 3, 0, 128, 512, False
+
+
+def moses_step_rate(batch=4096, reps=5, variant="mosesfile+head", rank=0, world=1):
+    """BASELINE.json configs[3] at N GPUs: fused fwd+bwd step of the MOSES VAE -- mosesfile.VAE (bidirectional GRU encoder 2x256,
+    latent 128, decoder GRU 3x512, V=34) with the BindingModel property head on z (logP target), or mosesvae.VAE (unidirectional,
+    d_z 160, train-mode dropout 0.2) for variant "mosesvae" -- bf16, batch 4096 per GPU (SURVEY.md 8d config 4 inputs: lengths ~
+    clip(N(44,9),10,98) + bos/eos, sorted descending).  One CUDA graph per phase of the step over resident inputs; with N > 1 the
+    gradient bucket a phase finalises is all-reduced (NCCL AVG) while the next phase runs.  CUDA events, max over ranks by the caller."""
     import numpy as np
     import torch
     import molecular_vae_b200 as m
     torch.manual_seed(0)
-    rng = np.random.Generator(np.random.PCG64(1))
+    rng = np.random.Generator(np.random.PCG64(1 + rank))
     lens = np.sort(np.clip(np.rint(rng.normal(44.0, 9.0, size=batch)), 10, 98).astype(np.int64))[::-1]
     x = [torch.from_numpy(np.concatenate([[30], rng.integers(0, 30, size=int(l)), [31]]).astype(np.int64)).cuda() for l in lens]
-    model = m.mosesvae.VAE(_BenchVocab(), precision="bf16").cuda()
-    eps = torch.randn(batch, 160, device="cuda")
-    model.elbo_step(x, kl_weight=0.1, eps=eps)
+    if variant == "mosesvae":
+        model = m.mosesvae.VAE(_BenchVocab(), precision="bf16").cuda()
+        target, dropout, dz = None, (0.2, 1234), 160
+    else:
+        model = m.mosesfile.VAE(_BenchVocab(), _BenchCfg(), precision="bf16")
+        model.attach_property_head()
+        model = model.cuda()
+        target, dropout, dz = torch.from_numpy(rng.uniform(0, 1, size=batch).astype(np.float32)).cuda(), (0.0, 0), 128
+    eps = torch.randn(batch, dz, device="cuda")
+    step = m.ddp.MosesPhasedStep(model, x, eps, kl_weight=0.1, binding=target, binding_weight=1.0, dropout=dropout)
+    for _ in range(2):
+        step.step()
     torch.cuda.synchronize()
     model.check_device_error()
-    _, ids_p, lens_p = model._pack(x)
-    params = model.ordered_params()
-    P, G = [p.data for p in params], [p.grad for p in params]
-    g = torch.cuda.CUDAGraph()
-    with torch.cuda.graph(g):
-        model._run(P, G, ids_p, lens_p, eps, 0.1, 1.0, False, dropout=(0.2, 1234))
-    g.replay()
-    torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+    torch.cuda.synchronize()
     e0.record()
     for _ in range(reps):
-        g.replay()
+        step.step()
     e1.record()
     torch.cuda.synchronize()
     model.check_device_error()
     ms = e0.elapsed_time(e1) / reps
     tokens = int(sum(int(l) + 2 for l in lens))
-    return {"metric": "train molecules/sec (fwd+bwd, mosesvae.VAE)", "value": batch / ms * 1e3, "unit": "molecules/s", "ms_per_step": ms,
-            "batch": batch, "mean_len": tokens / batch, "max_len": int(lens[0]) + 2, "loss": float(model._last_scalars[0].item()),
-            "workload": "mosesvae.VAE fused step (packed sequences, train-mode dropout 0.2), bf16, random-init weights, one GPU"}
+    out = {"metric": "train molecules/sec (fwd+bwd, MOSES VAE" + (" + property head)" if target is not None else ")"),
+           "value": batch / ms * 1e3, "unit": "molecules/s", "ms_per_step": ms,
+           "batch": batch, "mean_len": tokens / batch, "max_len": int(lens[0]) + 2, "loss": float(model._last_scalars[0].item()),
+           "workload": ("mosesfile.VAE (bidirectional encoder, d_z 128) + BindingModel head on z, joint fused step"
+                        if target is not None else "mosesvae.VAE fused step (train-mode dropout 0.2)") +
+                       ", packed sequences, bf16, random-init weights, batch 4096/GPU"}
+    if target is not None:
+        out["binding_loss"] = float(model.last_binding_loss.item())
+    return out
 
 
 def rec_kernel_times(model, eng, params, ids_dev, eps_dev, steps=3):
@@ -401,30 +448,65 @@ def run_ours(args):
     e2e_value = world * B * e2e_steps / sec_e2e
     # second metric of BASELINE.json (hugesample.py): every rank decodes its own latents (replicas only, no exchange);
     # whole-job SMILES/s = batches of all ranks / slowest rank's time
+    per_rank = -(-args.samples // world)
     try:
-        sampling = sampling_rate()
+        sampling = sampling_rate(n_total=per_rank)
     except Exception as ex:
         sampling = {"error": repr(ex)}
     if world > 1:   # every rank takes part in the reduction, whether or not its own measurement succeeded
-        t = torch.tensor([sampling.get("ms_per_batch", float("inf"))], dtype=torch.float64, device="cuda")
+        t = torch.tensor([sampling.get("ms_per_batch", float("inf")), sampling.get("e2e", {}).get("seconds", float("inf"))],
+                         dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        if "error" not in sampling and t.item() != float("inf"):
-            sampling["ms_per_batch"] = float(t.item())
+        if "error" not in sampling and t[0].item() != float("inf"):
+            sampling["ms_per_batch"] = float(t[0].item())
             sampling["value"] = world * sampling["batch"] / sampling["ms_per_batch"] * 1e3
             sampling["replicas"] = world
+            if "e2e" in sampling and t[1].item() != float("inf"):
+                sampling["e2e"]["seconds"] = float(t[1].item())
+                sampling["e2e"]["strings"] = world * sampling["e2e"]["strings"]
+                sampling["e2e"]["value"] = sampling["e2e"]["strings"] / sampling["e2e"]["seconds"]
         elif "error" not in sampling:
             sampling = {"error": "sampling failed on another rank"}
+    # dominant kernel = the BPTT sweep of one GRU layer (gru_rec2_kernel<BWD>): one launch = all T steps, timed live with CUDA
+    # events on direct launches of the same step (rank 0)
+    rec, rec_err = None, None
     if rank == 0:
-        peak = peaks["bf16_tflops_sustained"]
-        achieved = (value / world) * GFLOP_PER_MOLECULE * 1e-3  # TFLOP/s per GPU
-        step_ms = sec / args.steps * 1e3
-        # dominant kernel = the BPTT sweep of one GRU layer (gru_rec2_kernel<BWD>): one launch = all T steps.
-        # algorithmic FLOPs per launch = 2 * (3H x H) MACs per molecule-step (dh_{t-1} = dgh_t W_hh, SURVEY.md A.4) x T x B
-        rec = None
         try:
             rec = rec_kernel_times(model, eng, params, ids_dev, eps_dev)
         except Exception as ex:
             rec_err = repr(ex)
+    # BASELINE.json configs[3]: the MOSES VAE + property head step at N GPUs (every rank runs it; whole-job rate = all ranks'
+    # molecules / slowest rank's time)
+    eng.destroy_graph()
+    eng.destroy_phase_graphs()
+    del eng
+    model._engines.clear()
+    torch.cuda.empty_cache()
+    moses_uni = None
+    try:
+        moses = moses_step_rate(rank=rank, world=world)
+    except Exception as ex:
+        moses = {"error": repr(ex)}
+    if world > 1:
+        t = torch.tensor([moses.get("ms_per_step", float("inf"))], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        if "error" not in moses and t.item() != float("inf"):
+            moses["ms_per_step"] = float(t.item())
+            moses["value"] = world * moses["batch"] / moses["ms_per_step"] * 1e3
+            moses["n_gpus"] = world
+            moses["allreduce"] = "3 gradient buckets (readiness order), NCCL AVG, overlapped with the next phase"
+        elif "error" not in moses:
+            moses = {"error": "moses step failed on another rank"}
+    else:
+        try:
+            moses_uni = moses_step_rate(variant="mosesvae")
+        except Exception as ex:
+            moses_uni = {"error": repr(ex)}
+    if rank == 0:
+        peak = peaks["bf16_tflops_sustained"]
+        achieved = (value / world) * GFLOP_PER_MOLECULE * 1e-3  # TFLOP/s per GPU
+        step_ms = sec / args.steps * 1e3
+        # algorithmic FLOPs per launch = 2 * (3H x H) MACs per molecule-step (dh_{t-1} = dgh_t W_hh, SURVEY.md A.4) x T x B
         H, T = CFG["hidden"], CFG["seq_len"]
         flops_launch = 2.0 * 3 * H * H * T * B
         line = {
@@ -462,7 +544,7 @@ def run_ours(args):
         else:
             line["roofline"] = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                                 "frac": achieved / peak, "traffic": None, "peak_source": peak_src + " bf16_tflops_sustained",
-                                "scope": whole["scope"], "kernel_timing_error": locals().get("rec_err")}
+                                "scope": whole["scope"], "kernel_timing_error": rec_err}
         if world == 1:
             try:
                 line["roofline"]["kernels"] = kernel_rooflines(B, peaks)
@@ -477,11 +559,9 @@ def run_ours(args):
             except Exception as ex:
                 line["gpu_eager_baseline"] = {"error": repr(ex)}
         line["sampling"] = sampling
-        if world == 1:
-            try:
-                line["moses_step"] = moses_step_rate()
-            except Exception as ex:
-                line["moses_step"] = {"error": repr(ex)}
+        line["moses_step"] = moses
+        if moses_uni is not None:
+            line["moses_step_unidirectional"] = moses_uni
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -494,6 +574,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=4096)
+    ap.add_argument("--samples", type=int, default=10_000_000,
+                    help="latents decoded end to end for the sampling metric (BASELINE.json configs[4]: 10M), split over the ranks")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     args = ap.parse_args()
     if args.impl == "reference":

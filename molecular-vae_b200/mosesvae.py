@@ -291,6 +291,7 @@ class VAE(nn.Module):
                                                 _p(target), float(weight), _p(out), _p(self._joint_loss), _p(z), wsp, need, bwsp,
                                                 bneed, xp, xneed, int(phase), _stream()))
                 head._generation += 1
+                self.last_binding_loss = self._joint_loss
                 if head.training and phase <= 0:
                     bn1.num_batches_tracked += 1
                     bn2.num_batches_tracked += 1
@@ -354,8 +355,6 @@ class VAE(nn.Module):
             joint = (head, binding.to(ids.device, torch.float32).contiguous().view(-1), binding_weight, [named[k].grad for k in head.KEYS])
         self._run([p.data for p in params], [p.grad for p in params], ids, lens, eps, kl_weight, recon_weight, False,
                   dropout=self._dropout(), joint=joint)
-        if joint is not None:
-            self.last_binding_loss = self._joint_loss
         return self._last_scalars
 
     def sample_z_prior(self, n_batch):
@@ -418,6 +417,30 @@ class VAE(nn.Module):
                                         need, _stream()))
         self._last_desc = (d, wsp, need)
         return ids, lens, z
+
+    def sample_many(self, n_total, n_batch=8192, max_len=100, temp=1.0, greedy=False, seed=None, table=None):
+        """hugesample.py:25-40 as a generator: decodes n_total latents from the prior in batches of n_batch and yields one
+        list[str] per batch.  The GPU decodes batch k+1 (one CUDA-graph replay) while the host turns batch k's bytes into
+        Python strings; per batch one device-side text assembly and one device -> pinned-host copy.  `table`: a
+        text.TokenTable (e.g. the "[sym]" join of hugesample.py:34); default = the vocabulary's ids2string."""
+        if table is None:
+            table = getattr(self, "_token_table", None)
+            if table is None or table.table.device != self.device:
+                from .text import TokenTable
+                table = self._token_table = TokenTable.from_vocab(self.vocabulary, self.device)
+        gen = torch.Generator().manual_seed(int(seed)) if seed is not None else None
+        pending, done = None, 0
+        while done < n_total:
+            b = n_batch   # fixed batch: one captured graph; the last batch is trimmed on the host
+            s = int(torch.randint(0, 2 ** 62, (1,), generator=gen).item())
+            ids, lens, _ = self.sample_ids(b, max_len=max_len, temp=temp, greedy=greedy, seed=s)
+            nxt = table.to_strings_async(ids, lens)
+            if pending is not None:
+                yield pending[0].result()[:pending[1]]
+            pending = (nxt, min(b, n_total - done))
+            done += b
+        if pending is not None:
+            yield pending[0].result()[:pending[1]]
 
     def destroy_sample_graph(self):
         g = getattr(self, "_sample_graph", None)

@@ -565,3 +565,22 @@ def test_moses_phased_step_equals_fused_step(with_head):
         err = float((named[k].grad - w_).norm() / (w_.norm() + 1e-30))
         assert err < 2e-3, (k, err)                           # split-K atomics reorder fp32 sums between runs
     assert abs(float(model._last_scalars[0]) - float(sc_ref[0])) <= 1e-5 * abs(float(sc_ref[0]))
+
+
+def test_sample_many_pipelined_strings_equal_batchwise_sample():
+    """VAE.sample_many (hugesample.py:25-40 as a generator: decode of batch k+1 overlapped with the host-side string building
+    of batch k, device text assembly, one pinned D2H per batch) returns exactly what batch-wise VAE.sample returns."""
+    m = load_pkg()
+    P, seqs, eps, pad, model = _setup(m, "bf16", 318, 418, 4)
+    B, n_total = 256, 3 * 256 + 37
+    torch.manual_seed(7)
+    torch.cuda.manual_seed(7)
+    got = [s for chunk in model.sample_many(n_total, n_batch=B, max_len=30, greedy=True, seed=3) for s in chunk]
+    torch.manual_seed(7)
+    torch.cuda.manual_seed(7)
+    want = []
+    for _ in range(4):
+        strs, _ = model.sample(B, max_len=30, greedy=True)
+        want += strs
+    assert len(got) == n_total and got == want[:n_total]
+    model.check_device_error()
