@@ -86,17 +86,21 @@ __global__ void gather_rows_kernel(const float* __restrict__ tbl, int W, const u
   }
 }
 // OH[t*Bp + b][v] = 1 iff b < B and ids[b][t] == v   (CP columns)
+// reverse 1: the whole time axis is reversed (t -> T-1-t, padding first); reverse 2 (needs lens): every row is reversed
+// inside its own length (t -> lens[b]-1-t for t < lens[b], zero rows past it), so the padding stays at the end
 template <typename TA>
 __global__ void onehot_rows_kernel(const uint8_t* __restrict__ ids, int ids_ld, int B, int Bp, int T, int CP,
-                                   TA* __restrict__ out, int reverse = 0) {
+                                   TA* __restrict__ out, int reverse = 0, const int* __restrict__ lens = nullptr) {
   const long long total = (long long)T * Bp * CP;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int c = (int)(i % CP);
     const long long rb = i / CP;
     const int b = (int)(rb % Bp);
     int t = (int)(rb / Bp);
-    if (reverse) t = T - 1 - t;
-    out[i] = from_f32<TA>((b < B && ids[(long long)b * ids_ld + t] == c) ? 1.f : 0.f);
+    bool live = b < B;
+    if (reverse == 1) t = T - 1 - t;
+    else if (reverse == 2 && live) { const int L = lens[b]; live = t < L; t = L - 1 - t; }
+    out[i] = from_f32<TA>((live && ids[(long long)b * ids_ld + t] == c) ? 1.f : 0.f);
   }
 }
 

@@ -72,6 +72,7 @@ struct MWS {
   float *dW_p, *dWfc_p, *csum;
   // persistent decoder recurrence (gru_rec2.cu): W_hh^T [Hd][3Hd] bf16, b_ih + (b_hr, b_hz, 0), inter-CTA step counters
   void *WhhT[4]; float *bcomb[4]; unsigned int* counters;
+  uint8_t* tokTr;   // ids^T with every row reversed inside its own length (reverse encoder direction on the persistent kernel)
   void *WhhT_enc; float *tbl_comb; uint8_t* tokT; void* zproj_rb;   // encoder W_hh^T, table + (b_hr, b_hz, 0), ids^T [T][Bp], zproj RB bf16
   size_t total;
 };
@@ -92,7 +93,7 @@ void carve(const MDims& d, void* base, MWS* w) {
   w->hcat = c.take<float>(B * d.Hin); w->dhcat = c.take<float>(B * d.Hin);
   if (d.bidir) {
     w->TBLer = c.take<float>((size_t)d.V * 3 * Hq); w->hlastr = c.take<float>(Bp * Hq);
-    w->hs_encr = c.take<uint8_t>((T + 1) * Bp * Hq * es); w->sv_encr = c.take<uint8_t>(T * Bp * 4 * Hq * es);
+    w->hs_encr = c.take<uint8_t>((T + 1) * Bp * Hq * es); w->sv_encr = c.take<uint8_t>(T * Bp * 5 * Hq * es);
     w->Whh_encr = c.take<uint8_t>(3 * Hq * Hq * es); w->bhh_encr = c.take<float>(3 * Hq);
   } else {
     w->TBLer = nullptr; w->hlastr = nullptr; w->hs_encr = nullptr; w->sv_encr = nullptr; w->Whh_encr = nullptr; w->bhh_encr = nullptr;
@@ -128,6 +129,7 @@ void carve(const MDims& d, void* base, MWS* w) {
   w->counters = c.take<unsigned int>(2 * (Bp / 256) + 64);
   w->WhhT_enc = c.take<uint8_t>(3 * Hq * Hq * 2); w->tbl_comb = c.take<float>((size_t)64 * 3 * (Hd > Hq ? Hd : Hq));
   w->tokT = c.take<uint8_t>(T * Bp); w->zproj_rb = c.take<uint8_t>(Bp * 3 * Hd * 2);
+  w->tokTr = d.bidir ? c.take<uint8_t>(T * Bp) : nullptr;
   w->dW_p = c.take<float>(3 * Hd * Hd); w->dWfc_p = c.take<float>(d.CP * Hd); w->csum = c.take<float>(4 * Hd);
   w->total = (c.off + 255) & ~size_t(255);
 }
@@ -508,12 +510,19 @@ __global__ void table_add_bias_kernel(const float* __restrict__ tbl, const float
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < V * W) out[i] = tbl[i] + (brz ? brz[i % W] : 0.f);
 }
-// tokT[t][b] = ids[b][t] (token 0 for pad rows)
-__global__ void transpose_ids_kernel(const uint8_t* __restrict__ ids, int ids_ld, int B, int Bp, int T, uint8_t* __restrict__ out) {
+// tokT[t][b] = ids[b][t] (token 0 for pad rows); with lens: ids[b][lens[b]-1-t] for t < lens[b] (each row reversed inside its
+// own length: the reverse GRU direction as a forward sweep whose padding still comes last), token 0 past the row's end
+__global__ void transpose_ids_kernel(const uint8_t* __restrict__ ids, int ids_ld, int B, int Bp, int T, uint8_t* __restrict__ out,
+                                     const int* __restrict__ lens = nullptr) {
   const long long total = (long long)T * Bp;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int b = (int)(i % Bp), t = (int)(i / Bp);
-    out[i] = b < B ? ids[(long long)b * ids_ld + t] : (uint8_t)0;
+    uint8_t v = 0;
+    if (b < B) {
+      if (!lens) v = ids[(long long)b * ids_ld + t];
+      else if (t < lens[b]) v = ids[(long long)b * ids_ld + (lens[b] - 1 - t)];
+    }
+    out[i] = v;
   }
 }
 // dX_enc (row-blocked [row/32][H/8][32][8] per slab) [L_b - 1][b][:] = dh_enc[b][:]; dX zeroed beforehand
@@ -732,9 +741,33 @@ int step_t(const MDims& d, const MWS& w, const float* const* P, float* const* G,
   if (d.bidir) {
     // reverse direction (mosesfile.py:21-28,112-116): same engine over the time-reversed token stream, padding first
     RC(sg(st, P[ix.emb()], V, 1, P[ix.e_wih(1)], 1, V, w.TBLer, 3 * Hq, V, 3 * Hq, V, P[ix.e_bih(1)], simt::ACT_NONE, 0));
-    gather_rows_kernel<TA><<<grid_for((long long)TB * 3 * Hq), 256, 0, st>>>(w.TBLer, 3 * Hq, ids, T, nullptr, B, Bp, T, (TA*)w.gi, 1); KCHECK();
-    RC(gru_fwd<TA>(d, w, st, (const TA*)w.gi, (const TA*)w.Whh_encr, w.bhh_encr, (TA*)w.hs_encr, (TA*)w.sv_encr, Hq, nullptr, lens,
-                   nullptr, true, w.hlastr));
+    bool rev_swept = false;
+    if constexpr (sizeof(TA) == 2) {
+      if (prec_enc) {
+        // the reverse direction as a FORWARD sweep of the persistent kernel over every row reversed inside its own length:
+        // the padding still comes last, the direction's final state (after the row's first token) is the state after step
+        // lens[b]-1, and the per-tile step windows of the packed batch apply unchanged
+        transpose_ids_kernel<<<grid_for((long long)TB), 256, 0, st>>>(ids, T, B, Bp, T, w.tokTr, lens); KCHECK();
+        combine_gate_bias_kernel<<<ceil_div(3 * Hq, 256), 256, 0, st>>>(nullptr, w.bhh_encr, w.bcomb[0], Hq); KCHECK();
+        table_add_bias_kernel<<<ceil_div(V * 3 * Hq, 256), 256, 0, st>>>(w.TBLer, w.bcomb[0], V, 3 * Hq, w.tbl_comb); KCHECK();
+        RC(memset_async(w.hs_encr, (size_t)Bp * Hq * sizeof(TA), st));
+        RC(memset_async(w.hlastr, (size_t)Bp * Hq * 4, st));
+        mvae_gru_rec_args ra{};
+        ra.backward = 0; ra.variant = 32; ra.Bp = Bp; ra.Hp = Hq; ra.T = T;
+        ra.W = (const __nv_bfloat16*)w.Whh_encr; ra.gi = nullptr; ra.gi_tstride = 0; ra.bhh = w.bhh_encr + 2 * Hq;
+        ra.hs = (__nv_bfloat16*)w.hs_encr; ra.sv = (__nv_bfloat16*)w.sv_encr; ra.counters = w.counters; ra.err_flag = w.err_flag;
+        ra.ones_col = -1; ra.tbl = w.tbl_comb; ra.tok = w.tokTr; ra.V = V; ra.lens = lens; ra.hlast = w.hlastr; ra.nrows = B;
+        ra.tile_T = tileT;
+        mvae_count_launches(2);
+        RC(mvae_gru_rec2_launch(&ra, 1, st));
+        rev_swept = true;
+      }
+    }
+    if (!rev_swept) {
+      gather_rows_kernel<TA><<<grid_for((long long)TB * 3 * Hq), 256, 0, st>>>(w.TBLer, 3 * Hq, ids, T, nullptr, B, Bp, T, (TA*)w.gi, 1); KCHECK();
+      RC(gru_fwd<TA>(d, w, st, (const TA*)w.gi, (const TA*)w.Whh_encr, w.bhh_encr, (TA*)w.hs_encr, (TA*)w.sv_encr, Hq, nullptr, lens,
+                     nullptr, true, w.hlastr));
+    }
     copy_rows_kernel<<<grid_for((long long)B * Hq), 256, 0, st>>>(w.hlastr, Hq, B, Hq, w.hcat + Hq, Hin); KCHECK();
   }
   if (d.lin) {   // mosesfile.py:31-32,118: single Linear heads on cat(h_fwd, h_bwd)
@@ -951,13 +984,16 @@ int step_t(const MDims& d, const MWS& w, const float* const* P, float* const* G,
     RC(memset_async(dXe, (size_t)TB * Hq * sizeof(TA), st));
     bool swept = false;
     if constexpr (sizeof(TA) == 2) {
-      if (!rev && prec_enc) {
-        scatter_final_grad_rb_kernel<<<(unsigned)ceil_div64((long long)B * Hq, 256), 256, 0, st>>>(w.dhenc, Hin, lens, B, Bp, Hq,
-                                                                                                 (__nv_bfloat16*)dXe); KCHECK();
-        whh_transpose_kernel<<<grid_for(3ll * Hq * Hq), 256, 0, st>>>(P[ix.e_whh(0)], Hq, (__nv_bfloat16*)w.WhhT_enc); KCHECK();
+      if (prec_enc) {
+        // both directions: the gradient enters at the row's last processed step (the reverse direction runs over the row
+        // reversed inside its own length, see the forward pass)
+        scatter_final_grad_rb_kernel<<<(unsigned)ceil_div64((long long)B * Hq, 256), 256, 0, st>>>(w.dhenc + (size_t)rev * Hq, Hin, lens, B,
+                                                                                                 Bp, Hq, (__nv_bfloat16*)dXe); KCHECK();
+        whh_transpose_kernel<<<grid_for(3ll * Hq * Hq), 256, 0, st>>>(P[ix.e_whh(rev)], Hq, (__nv_bfloat16*)w.WhhT_enc); KCHECK();
         mvae_gru_rec_args ra{};
         ra.backward = 1; ra.variant = 32; ra.Bp = Bp; ra.Hp = Hq; ra.T = T;
-        ra.W = (const __nv_bfloat16*)w.WhhT_enc; ra.hs = (__nv_bfloat16*)w.hs_enc; ra.sv = (__nv_bfloat16*)w.sv_enc;
+        ra.W = (const __nv_bfloat16*)w.WhhT_enc; ra.hs = (__nv_bfloat16*)(rev ? w.hs_encr : w.hs_enc);
+        ra.sv = (__nv_bfloat16*)(rev ? w.sv_encr : w.sv_enc);
         ra.dX = (const __nv_bfloat16*)dXe; ra.dG = (__nv_bfloat16*)dG; ra.counters = w.counters; ra.err_flag = w.err_flag;
         ra.tile_T = tileT;
         mvae_count_launches(2);
@@ -974,15 +1010,17 @@ int step_t(const MDims& d, const MWS& w, const float* const* P, float* const* G,
     }
     RC(memset_async(w.dW_p, (size_t)3 * Hq * Hq * 4, st));
     RC(gemm<TA>(w.err_flag, st, dG + Hq, 4 * Hq, true, hs, Hq, false, w.dW_p, Hq, false, 3 * Hq, Hq, TB, nullptr, true, wsplits, 256,
-                rev ? nullptr : VLK));
+                (rev && !swept) ? nullptr : VLK));
     simt::unpad_gate_matrix_kernel<<<grid_for(3ll * Hq * Hq), 256, 0, st>>>(w.dW_p, Hq, Hq, G[ix.e_whh(rev)], Hq, Hq, 0, 1, 2); KCHECK();
     RC(memset_async(w.csum, (size_t)4 * Hd * 4, st));
     RC(simt::colsum<TA>(st, dG, TB, 4 * Hq, 4 * Hq, w.csum, swept ? lim256 : nullptr, Bp)); mvae_count_launches(1);
     gate_bias_grads_kernel<<<ceil_div(3 * Hq, 256), 256, 0, st>>>(w.csum, Hq, G[ix.e_bih(rev)], G[ix.e_bhh(rev)]); KCHECK();
-    if (rev) { onehot_rows_kernel<TA><<<grid_for((long long)TB * CP), 256, 0, st>>>(ids, T, B, Bp, T, CP, (TA*)w.OH, 1); KCHECK(); }
+    if (rev) {   // one-hot rows of the reverse direction's token stream (per-row reversal when it ran on the persistent kernel)
+      onehot_rows_kernel<TA><<<grid_for((long long)TB * CP), 256, 0, st>>>(ids, T, B, Bp, T, CP, (TA*)w.OH, swept ? 2 : 1, lens); KCHECK();
+    }
     RC(memset_async(w.dTBL, (size_t)CP * 3 * Hd * 4, st));
     RC(gemm<TA>(w.err_flag, st, (const TA*)w.OH, CP, true, dG, 4 * Hq, false, w.dTBL, 3 * Hq, false, CP, 3 * Hq, TB, nullptr, true,
-                d.bf16 ? 24 : 64, 256, rev ? nullptr : VLK));
+                d.bf16 ? 24 : 64, 256, (rev && !swept) ? nullptr : VLK));
     tbl_grad_to_rzn_T_kernel<<<(unsigned)ceil_div64(3ll * Hq * V, 256), 256, 0, st>>>(w.dTBL, Hq, V, w.dWT); KCHECK();
     RC(sg(st, w.dWT, V, 1, P[ix.emb()], V, 1, G[ix.e_wih(rev)], V, 3 * Hq, V, V, nullptr, simt::ACT_NONE, 0));
     RC(sg(st, w.dWT, 1, V, P[ix.e_wih(rev)], V, 1, G[ix.emb()], V, V, V, 3 * Hq, nullptr, simt::ACT_NONE, 1, 24));   // accumulate onto the decoder part

@@ -204,7 +204,7 @@ def _setup_file(m, precision, pseed, bseed, B):
 
 
 @pytest.mark.parametrize("precision,B,ltol,gtol", [("fp32", 7, FP32_LTOL, FP32_GTOL), ("fp32", 70, FP32_LTOL, FP32_GTOL),
-                                                   ("bf16", 200, BF16_LTOL, BF16_GTOL)])
+                                                   ("bf16", 200, BF16_LTOL, BF16_GTOL), ("bf16", 700, BF16_LTOL, BF16_GTOL)])
 def test_mosesfile_bidirectional_fused_step(precision, B, ltol, gtol):
     m = load_pkg()
     klw = 0.5
