@@ -181,7 +181,7 @@ int mvae_cfga_read_error(const mvae_cfga_desc* d, void* workspace, size_t worksp
 typedef struct mvae_moses_desc {
   int32_t batch;      /* B sequences, sorted by length descending as the reference's collate does             */
   int32_t max_len;    /* T: padded length of `ids` in this call (= longest sequence incl. bos/eos)             */
-  int32_t vocab;      /* V = len(vocab) <= 64 (chars + bos,eos,pad,unk; vocab.py:24); embedding is V x V       */
+  int32_t vocab;      /* V = len(vocab) <= 256 (chars / SELFIES symbols + bos,eos,pad,unk; vocab.py:24; ids are u8); embedding V x V; for V > 64 the token-table projections are materialised instead of looked up inside the sweeps */
   int32_t d_z;        /* 160 (mosesvae.py:39)                                                                 */
   int32_t q_hidden;   /* 256 encoder GRU (mosesvae.py:33), multiple of 64                                     */
   int32_t d_hidden;   /* 512 decoder GRU (mosesvae.py:40), multiple of 64                                     */

@@ -529,7 +529,7 @@ gru_rec2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     uint32_t nx = 0;   // KS: exchanges this warp has done so far (the partner warp runs the same tile / step sequence)
     int lastv_a = -1, lastv_b = -1;   // IN == 2: step after which this thread's row of slot a / b hands its state to hlast
-    if constexpr (!BWD && IN == 2) {
+    if constexpr (!BWD && (IN == 2 || (IN == 0 && VL))) {   // IN 0 + packed sequences: embedding layer with a materialised projection
       if (p.hlast)
         for (int i = 0; i < ntiles; ++i) {
           const long long row = (long long)TILE_ID(i) * 256 + parity * 128 + q * 32 + lane;
@@ -652,7 +652,7 @@ gru_rec2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
             an[k] = __float_as_uint(ghn);
           }
           if (tr2) p.trace[((size_t)step * NTILES + i) * 12 + 9] = gtime();
-          if (IN == 2 && t == (i ? lastv_b : lastv_a)) {
+          if ((IN == 2 || (IN == 0 && VL)) && t == (i ? lastv_b : lastv_a)) {
             float4* hl = reinterpret_cast<float4*>(p.hlast + row * p.Hp + u0 + uc);
 #pragma unroll
             for (int k = 0; k < 4; ++k) hl[k] = make_float4(h[4 * k], h[4 * k + 1], h[4 * k + 2], h[4 * k + 3]);

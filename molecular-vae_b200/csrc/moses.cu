@@ -34,12 +34,12 @@ struct MDims {
 
 int make_dims(const mvae_moses_desc* d, MDims* o) {
   if (!d) return MVAE_ERR_INVALID;
-  if (d->batch <= 0 || d->max_len < 2 || d->max_len > 512 || d->vocab < 5 || d->vocab > 64 || d->d_z <= 0 ||
+  if (d->batch <= 0 || d->max_len < 2 || d->max_len > 512 || d->vocab < 5 || d->vocab > 256 || d->d_z <= 0 ||
       d->q_hidden <= 0 || d->d_hidden <= 0 || d->d_layers < 1 || d->d_layers > 4 || d->mlp_hidden <= 0)
     return MVAE_ERR_INVALID;
   if ((d->q_hidden & 63) || (d->d_hidden & 63)) return MVAE_ERR_UNSUPPORTED;   // hidden sizes must be multiples of 64
   if (d->precision != MVAE_PREC_FP32 && d->precision != MVAE_PREC_BF16) return MVAE_ERR_INVALID;
-  o->B = d->batch; o->Bp = round_up(d->batch, 256); o->T = d->max_len; o->V = d->vocab; o->CP = 64;
+  o->B = d->batch; o->Bp = round_up(d->batch, 256); o->T = d->max_len; o->V = d->vocab; o->CP = round_up(d->vocab, 64);   // logits / one-hot rows in 64-wide tiles
   o->Z = d->d_z; o->Hq = d->q_hidden; o->Hd = d->d_hidden; o->L = d->d_layers; o->MLP = d->mlp_hidden;
   o->pad = d->pad_id; o->bf16 = d->precision == MVAE_PREC_BF16; o->kl_w = d->kl_weight; o->rec_w = d->recon_weight;
   if (!(d->d_dropout >= 0.f && d->d_dropout < 1.f)) return MVAE_ERR_INVALID;
@@ -127,7 +127,7 @@ void carve(const MDims& d, void* base, MWS* w) {
   w->Wfc = c.take<uint8_t>(d.CP * Hd * es); w->bfc = c.take<float>(d.CP);
   for (int l = 0; l < d.L; ++l) { w->WhhT[l] = c.take<uint8_t>(3 * Hd * Hd * 2); w->bcomb[l] = c.take<float>(3 * Hd); }
   w->counters = c.take<unsigned int>(2 * (Bp / 256) + 64);
-  w->WhhT_enc = c.take<uint8_t>(3 * Hq * Hq * 2); w->tbl_comb = c.take<float>((size_t)64 * 3 * (Hd > Hq ? Hd : Hq));
+  w->WhhT_enc = c.take<uint8_t>(3 * Hq * Hq * 2); w->tbl_comb = c.take<float>((size_t)d.CP * 3 * (Hd > Hq ? Hd : Hq));
   w->tokT = c.take<uint8_t>(T * Bp); w->zproj_rb = c.take<uint8_t>(Bp * 3 * Hd * 2);
   w->tokTr = d.bidir ? c.take<uint8_t>(T * Bp) : nullptr;
   w->dW_p = c.take<float>(3 * Hd * Hd); w->dWfc_p = c.take<float>(d.CP * Hd); w->csum = c.take<float>(4 * Hd);
@@ -229,38 +229,53 @@ __global__ void head_ce_kernel(const float* __restrict__ logits, int CP, int V, 
                                const int* __restrict__ Mcount, float rec_w, const float* __restrict__ bias,
                                TA* __restrict__ dlogits,
                                float* __restrict__ y, double* __restrict__ nll_sum) {
+  // lane l owns the vocabulary ids l, l + 32, ... (NV = CP / 32 <= 8 of them)
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
+  const int NV = CP >> 5;
   double local = 0.0;
   if (warp < (long long)T * Bp) {
     const int t = warp / Bp, b = warp - t * Bp;
     const long long row = warp;
     const int L = b < B ? lens[b] : 0;
     const bool target = b < B && (t + 1 < L);
-    const float a0 = lane < V ? logits[row * CP + lane] : -INFINITY;
-    const float a1 = (lane + 32) < V ? logits[row * CP + lane + 32] : -INFINITY;
+    float a[8], dv[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int v = lane + 32 * k;
+      a[k] = (k < NV && v < V) ? logits[row * CP + v] : -INFINITY;
+      dv[k] = 0.f;
+    }
     if (y && b < B) {
       float* yr = y + ((long long)b * T + t) * V;
-      if (lane < V) yr[lane] = t < L ? a0 : bias[lane];
-      if (lane + 32 < V) yr[lane + 32] = t < L ? a1 : bias[lane + 32];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { const int v = lane + 32 * k; if (k < NV && v < V) yr[v] = t < L ? a[k] : bias[v]; }
     }
-    float d0 = 0.f, d1 = 0.f;
     if (target) {
-      float m = fmaxf(a0, a1);
+      float m = a[0];
+#pragma unroll
+      for (int k = 1; k < 8; ++k) m = fmaxf(m, a[k]);
       for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-      const float e0 = lane < V ? expf(a0 - m) : 0.f, e1 = (lane + 32) < V ? expf(a1 - m) : 0.f;
-      float s = e0 + e1;
+      float e[8], s = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { e[k] = (k < NV && lane + 32 * k < V) ? expf(a[k] - m) : 0.f; s += e[k]; }
       for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
       const int tgt = ids[(long long)b * ids_ld + t + 1];
       const float inv = rec_w / (float)Mcount[0];
-      d0 = (e0 / s - (lane == tgt ? 1.f : 0.f)) * inv;
-      d1 = (e1 / s - (lane + 32 == tgt ? 1.f : 0.f)) * inv;
-      const float at = __shfl_sync(0xffffffffu, tgt < 32 ? a0 : a1, tgt & 31);
+      float at_l = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const bool hit = (lane + 32 * k) == tgt;
+        dv[k] = (e[k] / s - (hit ? 1.f : 0.f)) * inv;
+        if (hit) at_l = a[k];
+      }
+      const float at = __shfl_sync(0xffffffffu, at_l, tgt & 31);
       if (lane == 0) local = (double)(m + logf(s) - at);
     }
     if (dlogits) {
-      dlogits[row * CP + lane] = from_f32<TA>(lane < V ? d0 : 0.f);
-      dlogits[row * CP + lane + 32] = from_f32<TA>((lane + 32) < V ? d1 : 0.f);
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if (k < NV) dlogits[row * CP + lane + 32 * k] = from_f32<TA>((lane + 32 * k) < V ? dv[k] : 0.f);
     }
   }
   __shared__ double red[32];
@@ -505,6 +520,34 @@ __global__ void rows_to_rb_kernel(const float* __restrict__ src, const float* __
     out[o] = __float2bfloat16_rn((b < B ? src[i] : 0.f) + brz[c]);
   }
 }
+// Input projection of an embedding layer materialised for the persistent sweeps when the token table does not fit their
+// shared memory (V > 64): out[t][b][:] = tbl[tok[t][b]][:] (+ add[b][:], row-blocked bf16) in the row-blocked layout
+// [t][row/32][W/8][32][8]; one thread = 8 columns of one (t, row).  lim (optional, [T]): rows >= lim[t] are not written.
+__global__ void gather_rb_kernel(const float* __restrict__ tbl, const uint8_t* __restrict__ tokT, const __nv_bfloat16* __restrict__ add_rb,
+                                 int T, int Bp, int W, __nv_bfloat16* __restrict__ out, const int* __restrict__ lim) {
+  const long long per_t = (long long)Bp * (W / 8);
+  const long long total = (long long)T * per_t;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int t = (int)(i / per_t);
+    const long long j = i - (long long)t * per_t;          // ((rblk * (W/8) + cg) * 32 + r)
+    const int r = (int)(j & 31);
+    const long long q = j >> 5;
+    const int cg = (int)(q % (W / 8));
+    const int b = (int)(q / (W / 8)) * 32 + r;
+    if (lim && b >= lim[t]) continue;
+    const float* src = tbl + (long long)tokT[(long long)t * Bp + b] * W + cg * 8;
+    float v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = src[k];
+    if (add_rb) {
+      float a[8];
+      load8<__nv_bfloat16>(add_rb + j * 8, a);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] += a[k];
+    }
+    store8<__nv_bfloat16>(out + (long long)t * Bp * W + j * 8, v);
+  }
+}
 // table rows + (b_hr, b_hz, 0): what the persistent kernel stages into shared memory
 __global__ void table_add_bias_kernel(const float* __restrict__ tbl, const float* __restrict__ brz, int V, int W, float* __restrict__ out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -705,7 +748,7 @@ int step_t(const MDims& d, const MWS& w, const float* const* P, float* const* G,
     }
   }
   simt::pad_matrix_kernel<TA><<<grid_for((long long)CP * Hd), 256, 0, st>>>(P[ix.fcw()], V, Hd, (TA*)w.Wfc, CP, Hd); KCHECK();
-  simt::pad_matrix_kernel<float><<<1, 64, 0, st>>>(P[ix.fcb()], 1, V, w.bfc, 1, CP); KCHECK();
+  simt::pad_matrix_kernel<float><<<1, 256, 0, st>>>(P[ix.fcb()], 1, V, w.bfc, 1, CP); KCHECK();
 
   // ---- encoder: table look-up projection, GRU, final state, MLP heads, reparametrise + KL
   RC(sg(st, P[ix.emb()], V, 1, P[ix.e_wih(0)], 1, V, w.TBLe, 3 * Hq, V, 3 * Hq, V, P[ix.e_bih(0)], simt::ACT_NONE, 0));
@@ -725,7 +768,13 @@ int step_t(const MDims& d, const MWS& w, const float* const* P, float* const* G,
       ra.backward = 0; ra.variant = 32; ra.Bp = Bp; ra.Hp = Hq; ra.T = T;
       ra.W = (const __nv_bfloat16*)w.Whh_enc; ra.gi = nullptr; ra.gi_tstride = 0; ra.bhh = w.bhh_enc + 2 * Hq;
       ra.hs = (__nv_bfloat16*)w.hs_enc; ra.sv = (__nv_bfloat16*)w.sv_enc; ra.counters = w.counters; ra.err_flag = w.err_flag;
-      ra.ones_col = -1; ra.tbl = w.tbl_comb; ra.tok = w.tokT; ra.V = V; ra.lens = lens; ra.hlast = w.hlast; ra.nrows = B;
+      ra.ones_col = -1; ra.lens = lens; ra.hlast = w.hlast; ra.nrows = B;
+      if (V <= 64) { ra.tbl = w.tbl_comb; ra.tok = w.tokT; ra.V = V; }
+      else {   // large vocabulary: the projection is materialised (table gather) instead of looked up inside the sweep
+        gather_rb_kernel<<<grid_for((long long)TB * (3 * Hq / 8)), 256, 0, st>>>(w.tbl_comb, w.tokT, nullptr, T, Bp, 3 * Hq,
+                                                                               (__nv_bfloat16*)w.gi, lim256); KCHECK();
+        ra.gi = (const __nv_bfloat16*)w.gi; ra.gi_tstride = (long long)Bp * 3 * Hq;
+      }
       ra.tile_T = tileT;
       mvae_count_launches(2);
       RC(mvae_gru_rec2_launch(&ra, 1, st));
@@ -756,7 +805,13 @@ int step_t(const MDims& d, const MWS& w, const float* const* P, float* const* G,
         ra.backward = 0; ra.variant = 32; ra.Bp = Bp; ra.Hp = Hq; ra.T = T;
         ra.W = (const __nv_bfloat16*)w.Whh_encr; ra.gi = nullptr; ra.gi_tstride = 0; ra.bhh = w.bhh_encr + 2 * Hq;
         ra.hs = (__nv_bfloat16*)w.hs_encr; ra.sv = (__nv_bfloat16*)w.sv_encr; ra.counters = w.counters; ra.err_flag = w.err_flag;
-        ra.ones_col = -1; ra.tbl = w.tbl_comb; ra.tok = w.tokTr; ra.V = V; ra.lens = lens; ra.hlast = w.hlastr; ra.nrows = B;
+        ra.ones_col = -1; ra.lens = lens; ra.hlast = w.hlastr; ra.nrows = B;
+        if (V <= 64) { ra.tbl = w.tbl_comb; ra.tok = w.tokTr; ra.V = V; }
+        else {
+          gather_rb_kernel<<<grid_for((long long)TB * (3 * Hq / 8)), 256, 0, st>>>(w.tbl_comb, w.tokTr, nullptr, T, Bp, 3 * Hq,
+                                                                                 (__nv_bfloat16*)w.gi, lim256); KCHECK();
+          ra.gi = (const __nv_bfloat16*)w.gi; ra.gi_tstride = (long long)Bp * 3 * Hq;
+        }
         ra.tile_T = tileT;
         mvae_count_launches(2);
         RC(mvae_gru_rec2_launch(&ra, 1, st));
@@ -818,7 +873,11 @@ int step_t(const MDims& d, const MWS& w, const float* const* P, float* const* G,
         mvae_gru_rec_args ra{};
         ra.backward = 0; ra.variant = 32; ra.Bp = Bp; ra.Hp = Hd; ra.T = T;
         ra.W = (const __nv_bfloat16*)w.Whh[l]; ra.gi = (const __nv_bfloat16*)w.gi; ra.gi_tstride = (long long)Bp * 3 * Hd;
-        if (l == 0) { ra.gi = (const __nv_bfloat16*)w.zproj_rb; ra.gi_tstride = 0; ra.tbl = w.TBLd; ra.tok = w.tokT; ra.V = V; }
+        if (l == 0 && V <= 64) { ra.gi = (const __nv_bfloat16*)w.zproj_rb; ra.gi_tstride = 0; ra.tbl = w.TBLd; ra.tok = w.tokT; ra.V = V; }
+        else if (l == 0) {   // large vocabulary: token part + per-molecule z part materialised once for all steps
+          gather_rb_kernel<<<grid_for((long long)TB * (3 * Hd / 8)), 256, 0, st>>>(w.TBLd, w.tokT, (const __nv_bfloat16*)w.zproj_rb, T, Bp,
+                                                                                 3 * Hd, (__nv_bfloat16*)w.gi, lim256); KCHECK();
+        }
         ra.bhh = w.bhh[l] + 2 * Hd; ra.hs = (__nv_bfloat16*)w.hs[l]; ra.sv = (__nv_bfloat16*)w.sv[l]; ra.counters = w.counters;
         ra.err_flag = w.err_flag; ra.ones_col = -1; ra.h0 = w.h0; ra.tile_T = tileT;
         mvae_count_launches(2);
@@ -868,7 +927,7 @@ int step_t(const MDims& d, const MWS& w, const float* const* P, float* const* G,
   simt::unpad_matrix_kernel<<<grid_for((long long)V * Hd), 256, 0, st>>>(w.dWfc_p, Hd, G[ix.fcw()], V, Hd); KCHECK();
   RC(memset_async(w.csum, (size_t)4 * Hd * 4, st));
   RC(simt::colsum<TA>(st, dlog, TB, CP, CP, w.csum)); mvae_count_launches(1);
-  simt::pad_matrix_kernel<float><<<1, 64, 0, st>>>(w.csum, 1, V, G[ix.fcb()], 1, V); KCHECK();
+  simt::pad_matrix_kernel<float><<<1, 256, 0, st>>>(w.csum, 1, V, G[ix.fcb()], 1, V); KCHECK();
   RC(memset_async(w.dh0, (size_t)Bp * Hd * 4, st));
   }   // phase <= 0: head
   // decoder GRU stack
@@ -1026,7 +1085,7 @@ int step_t(const MDims& d, const MWS& w, const float* const* P, float* const* G,
     RC(sg(st, w.dWT, 1, V, P[ix.e_wih(rev)], V, 1, G[ix.emb()], V, V, V, 3 * Hq, nullptr, simt::ACT_NONE, 1, 24));   // accumulate onto the decoder part
   }
   if (d.pad >= 0 && d.pad < V) {   // nn.Embedding(padding_idx = pad): the pad row receives no gradient
-    zero_row_kernel<<<1, 64, 0, st>>>(G[ix.emb()], d.pad, V); KCHECK();
+    zero_row_kernel<<<1, 256, 0, st>>>(G[ix.emb()], d.pad, V); KCHECK();
   }
   // a fired pipeline watchdog poisons the returned loss (the scalars were finalised before the backward kernels ran)
   simt::nan_if_error_kernel<<<1, 1, 0, st>>>(w.err_flag, out_scalars); KCHECK();
@@ -1044,14 +1103,21 @@ __global__ void sample_step_kernel(const float* __restrict__ logits, int CP, int
                                    int eos, int mode, float inv_temp, unsigned long long seed, const unsigned long long* seed_dev,
                                    uint8_t* __restrict__ w_cur, uint8_t* __restrict__ x, int* __restrict__ end,
                                    uint8_t* __restrict__ done) {
+  // one warp per sequence; lane l owns the ids l, l + 32, ... (NV = CP / 32 <= 8 of them)
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= B) return;
-  const int b = warp;
-  const float a0 = lane < V ? logits[(long long)b * CP + lane] * inv_temp : -INFINITY;
-  const float a1 = (lane + 32) < V ? logits[(long long)b * CP + lane + 32] * inv_temp : -INFINITY;
-  float m = fmaxf(a0, a1);
-  int arg = a0 >= a1 ? lane : lane + 32;
+  const int b = warp, NV = CP >> 5;
+  float a[8];
+  float m = -INFINITY;
+  int arg = 0x7fffffff;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int v = lane + 32 * k;
+    a[k] = (k < NV && v < V) ? logits[(long long)b * CP + v] * inv_temp : -INFINITY;
+    if (a[k] > m) { m = a[k]; arg = v; }          // strict: ties keep the lower id (k ascending = id ascending per lane)
+  }
+  if (arg == 0x7fffffff) arg = lane;
   for (int o = 16; o; o >>= 1) {
     const float om = __shfl_xor_sync(0xffffffffu, m, o);
     const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
@@ -1059,20 +1125,28 @@ __global__ void sample_step_kernel(const float* __restrict__ logits, int CP, int
   }
   int tok = arg;
   if (mode == 1) {
-    const float e0 = lane < V ? expf(a0 - m) : 0.f, e1 = (lane + 32) < V ? expf(a1 - m) : 0.f;
-    // inclusive prefix sums over the 64 candidate ids (ids 0..31 in e0, 32..63 in e1)
-    float c0 = e0, c1 = e1;
-    for (int o = 1; o < 32; o <<= 1) {
-      const float t0 = __shfl_up_sync(0xffffffffu, c0, o), t1 = __shfl_up_sync(0xffffffffu, c1, o);
-      if (lane >= o) { c0 += t0; c1 += t1; }
+    // inverse-CDF draw over the ids in ascending order: chunk k holds the ids [32k, 32k + 32); inclusive prefix sums inside a
+    // chunk over the lanes, chunk totals accumulated in order
+    float c[8], tot[8], base = 0.f, total = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      c[k] = (k < NV && lane + 32 * k < V) ? expf(a[k] - m) : 0.f;
+      for (int o = 1; o < 32; o <<= 1) {
+        const float t0 = __shfl_up_sync(0xffffffffu, c[k], o);
+        if (lane >= o) c[k] += t0;
+      }
+      tot[k] = __shfl_sync(0xffffffffu, c[k], 31);
+      total += tot[k];
     }
-    const float tot0 = __shfl_sync(0xffffffffu, c0, 31), tot1 = __shfl_sync(0xffffffffu, c1, 31);
-    const float u = u01_hash(seed_dev ? *seed_dev : seed, (unsigned)b, (unsigned)step) * (tot0 + tot1);
-    // first id whose cumulative mass exceeds u
-    const unsigned m0 = __ballot_sync(0xffffffffu, c0 > u);
-    const unsigned m1 = __ballot_sync(0xffffffffu, tot0 + c1 > u);
-    tok = m0 ? (__ffs(m0) - 1) : (m1 ? 32 + __ffs(m1) - 1 : arg);
-    if (tok >= V) tok = arg;
+    const float u = u01_hash(seed_dev ? *seed_dev : seed, (unsigned)b, (unsigned)step) * total;
+    tok = -1;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const unsigned mk = __ballot_sync(0xffffffffu, base + c[k] > u);
+      if (tok < 0 && mk) tok = 32 * k + __ffs(mk) - 1;
+      base += tot[k];
+    }
+    if (tok < 0 || tok >= V) tok = arg;
   }
   if (lane == 0) {
     w_cur[b] = (uint8_t)tok;
@@ -1160,7 +1234,7 @@ int sample_fused(const MDims& d, const MWS& w, const float* const* P, const floa
     KCHECK();
   }
   simt::pad_matrix_kernel<TA><<<grid_for((long long)CP * Hd), 256, 0, st>>>(P[ix.fcw()], V, Hd, (TA*)w.Wfc, CP, Hd); KCHECK();
-  simt::pad_matrix_kernel<float><<<1, 64, 0, st>>>(P[ix.fcb()], 1, V, w.bfc, 1, CP); KCHECK();
+  simt::pad_matrix_kernel<float><<<1, 256, 0, st>>>(P[ix.fcb()], 1, V, w.bfc, 1, CP); KCHECK();
   RC(memset_async(w.h0, (size_t)Bp * Hd * 4, st));
   RC(sg(st, z, Z, 1, P[ix.latw()], 1, Z, w.h0, Hd, B, Hd, Z, P[ix.latb()], simt::ACT_NONE, 0));
   RC(sg(st, P[ix.emb()], V, 1, P[ix.wih(0)], 1, IN0, w.TBLd, 3 * Hd, V, 3 * Hd, V, nullptr, simt::ACT_NONE, 0));
@@ -1202,9 +1276,16 @@ int sample_fused(const MDims& d, const MWS& w, const float* const* P, const floa
     mvae_umma_operand a{top, 0, Bp, Hd, L > 1 ? 2 * Hd : Hd, 1, 0, 0, 0};
     mvae_umma_operand b{w.Wfc, 0, CP, Hd, Hd, 1, 0, 0, 0};
     mvae_umma_out o{w.logits, CP, 0, 0, w.bfc, 0};
-    mvae_umma_sample sp{V, B, i, max_len, eos, mode, 1.0f / temp, seed, seed_dev, w_cur, kcat ? w.xh[0][nxt] : nullptr, K0, ids_out, len_out, done};
     mvae_count_launches(1);
-    RC(mvae_umma_gemm(&a, &b, &o, Bp, CP, Hd, 64, 1, 0, w.err_flag, st, nullptr, nullptr, &sp));
+    if (CP == 64) {
+      mvae_umma_sample sp{V, B, i, max_len, eos, mode, 1.0f / temp, seed, seed_dev, w_cur, kcat ? w.xh[0][nxt] : nullptr, K0, ids_out, len_out, done};
+      RC(mvae_umma_gemm(&a, &b, &o, Bp, CP, Hd, 64, 1, 0, w.err_flag, st, nullptr, nullptr, &sp));
+    } else {   // large vocabulary: logits of all CP / 64 tiles to memory, then one warp per sequence picks the token
+      RC(mvae_umma_gemm(&a, &b, &o, Bp, CP, Hd, 64, 1, 0, w.err_flag, st));
+      sample_step_kernel<<<ceil_div(B * 32, 256), 256, 0, st>>>(w.logits, CP, V, B, i, max_len, eos, mode, 1.0f / temp, seed, seed_dev, w_cur,
+                                                                ids_out, len_out, done);
+      KCHECK();
+    }
   }
   return MVAE_OK;
 }
@@ -1227,7 +1308,7 @@ int sample_t(const MDims& d, const MWS& w, const float* const* P, const float* z
     }
   }
   simt::pad_matrix_kernel<TA><<<grid_for((long long)CP * Hd), 256, 0, st>>>(P[ix.fcw()], V, Hd, (TA*)w.Wfc, CP, Hd); KCHECK();
-  simt::pad_matrix_kernel<float><<<1, 64, 0, st>>>(P[ix.fcb()], 1, V, w.bfc, 1, CP); KCHECK();
+  simt::pad_matrix_kernel<float><<<1, 256, 0, st>>>(P[ix.fcb()], 1, V, w.bfc, 1, CP); KCHECK();
   // h0 (mosesvae.py:229-230), token table and the per-sequence z part of the layer-0 projection
   RC(memset_async(w.h0, (size_t)Bp * Hd * 4, st));
   RC(sg(st, z, Z, 1, P[ix.latw()], 1, Z, w.h0, Hd, B, Hd, Z, P[ix.latb()], simt::ACT_NONE, 0));

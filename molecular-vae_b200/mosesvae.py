@@ -29,7 +29,7 @@ def moses_param_order(d_layers=3):
     return keys + ["decoder_lat.weight", "decoder_lat.bias", "decoder_fc.weight", "decoder_fc.bias"]
 
 
-MAX_VOCAB = 64   # the kernels keep token tables / logits rows in 64-wide tiles (moses.cu make_dims)
+MAX_VOCAB = 256   # token ids travel as u8; logits / one-hot rows are kept in 64-wide tiles (moses.cu make_dims)
 
 
 def _check_moses_shapes(n_vocab, d_emb, pad, q_d_h, d_d_h):

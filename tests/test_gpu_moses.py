@@ -584,3 +584,70 @@ def test_sample_many_pipelined_strings_equal_batchwise_sample():
         want += strs
     assert len(got) == n_total and got == want[:n_total]
     model.check_device_error()
+
+
+# ---- large vocabularies (SELFIES symbol tables of moses_train_distrib_logp.py:173-217: V is data dependent, >> 64) ----
+def _setup_v(m, precision, V, B, pseed=361, bseed=461):
+    P = mo.make_moses_params(pseed, dtype=np.float32, V=V)
+    seqs, eps, pad = mo.make_moses_batch(bseed + B, B, V=V, dtype=np.float32)
+    model = m.mosesvae.VAE(_Vocab(V - 4), precision=precision)
+    sd = model.state_dict()
+    with torch.no_grad():
+        for k, v in P.items():
+            sd[k].copy_(torch.from_numpy(v))
+    return P, seqs, eps, pad, model.cuda().eval()
+
+
+@pytest.mark.parametrize("precision,V,B,ltol,gtol", [("fp32", 200, 12, FP32_LTOL, FP32_GTOL), ("bf16", 200, 300, BF16_LTOL, BF16_GTOL),
+                                                     ("bf16", 70, 600, BF16_LTOL, BF16_GTOL), ("bf16", 256, 130, BF16_LTOL, BF16_GTOL)])
+def test_moses_fused_step_large_vocabulary(precision, V, B, ltol, gtol):
+    """V > 64: logits / one-hot rows span several 64-wide tiles, the token-table projections of the persistent sweeps are
+    materialised (the table no longer fits their shared memory) -- same oracle, same tolerances."""
+    m = load_pkg()
+    klw = 0.1
+    P, seqs, eps, pad, model = _setup_v(m, precision, V, B)
+    ref = mo.moses_step({k: v.astype(np.float64) for k, v in P.items()}, seqs, eps.astype(np.float64), pad, kl_weight=klw)
+    x = [torch.from_numpy(s).cuda() for s in seqs]
+    model.elbo_step(x, kl_weight=klw, eps=torch.from_numpy(eps).cuda())
+    torch.cuda.synchronize()
+    model._ws.fill_(0xFF)
+    out = model.elbo_step(x, kl_weight=klw, eps=torch.from_numpy(eps).cuda())
+    torch.cuda.synchronize()
+    model.check_device_error()
+    sc = out.cpu().numpy()
+    assert abs(sc[1] - ref["kl"]) <= ltol * abs(ref["kl"]), (sc, ref["kl"])
+    assert abs(sc[2] - ref["recon"]) <= ltol * abs(ref["recon"]), (sc, ref["recon"])
+    assert int(sc[3]) == ref["M"]
+    bad = {k: rel_l2(p.grad.cpu().numpy(), ref["grads"][k]) for k, p in model.named_parameters() if k in ref["grads"]}
+    bad = {k: e for k, e in bad.items() if not e <= gtol}
+    assert not bad, bad
+
+
+def test_moses_sample_large_vocabulary_greedy_bit_exact_fp32_and_bf16_runs():
+    m = load_pkg()
+    V, B, max_len = 200, 24, 30
+    P, seqs, eps, pad, model = _setup_v(m, "fp32", V, 4)
+    z = np.random.Generator(np.random.PCG64(5)).standard_normal((B, 160)).astype(np.float32)
+    x_ref, end_ref, margins = mo.moses_sample_greedy({k: v.astype(np.float64) for k, v in P.items()}, z.astype(np.float64),
+                                                     model.bos, model.eos, model.pad, max_len=max_len, return_margins=True)
+    ids, lens, _ = model.sample_ids(B, max_len=max_len, z=torch.from_numpy(z).cuda(), greedy=True)
+    torch.cuda.synchronize()
+    model.check_device_error()
+    ids, lens = ids.cpu().numpy(), lens.cpu().numpy()
+    unsafe = margins < 1e-4
+    first_unsafe = np.where(unsafe.any(1), unsafe.argmax(1), max_len)
+    first_unsafe = np.where(first_unsafe >= end_ref, max_len, first_unsafe)
+    for b in range(B):
+        k = int(first_unsafe[b])
+        assert (ids[b, :k] == x_ref[b, :k]).all(), (b, k)
+    assert (first_unsafe == max_len).mean() >= 0.8
+    # bf16 fused sampler with the vocabulary GEMM's logits in memory (4 tiles): valid ids, reproducible multinomial draws
+    _, _, _, _, model16 = _setup_v(m, "bf16", V, 4)
+    zt = torch.from_numpy(z).cuda()
+    a, la, _ = model16.sample_ids(B, max_len=max_len, z=zt, temp=1.0, seed=5)
+    b2, _, _ = model16.sample_ids(B, max_len=max_len, z=zt, temp=1.0, seed=5)
+    g16, _, _ = model16.sample_ids(B, max_len=max_len, z=zt, greedy=True)
+    torch.cuda.synchronize()
+    model16.check_device_error()
+    assert torch.equal(a, b2) and int(a.max()) < V and (a[:, 0] == model16.bos).all()
+    assert (g16.cpu().numpy()[:, 1] == x_ref[:, 1]).mean() >= 0.9       # first decoded token agrees with the oracle almost always
