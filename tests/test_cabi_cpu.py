@@ -89,7 +89,7 @@ def test_descriptor_validation_of_every_family():
     ok = M(64, 40, 34, 160, 256, 512, 3, 256, 32, L.PREC_BF16, 1.0, 1.0, 0, 0, 0.0, 0)
     assert L.lib.mvae_moses_workspace_bytes(ctypes.byref(ok)) > 0
     for bad in (M(64, 40, 34, 160, 250, 512, 3, 256, 32, L.PREC_BF16, 1.0, 1.0, 0, 0, 0.0, 0),      # q_hidden % 64
-                M(64, 40, 99, 160, 256, 512, 3, 256, 32, L.PREC_BF16, 1.0, 1.0, 0, 0, 0.0, 0),      # vocab > 64
+                M(64, 40, 300, 160, 256, 512, 3, 256, 32, L.PREC_BF16, 1.0, 1.0, 0, 0, 0.0, 0),     # vocab > 256
                 M(64, 1, 34, 160, 256, 512, 3, 256, 32, L.PREC_BF16, 1.0, 1.0, 0, 0, 0.0, 0),       # max_len < 2
                 M(64, 40, 34, 160, 256, 512, 3, 256, 32, L.PREC_BF16, 1.0, 1.0, 0, 0, 1.5, 0)):     # dropout >= 1
         assert L.lib.mvae_moses_workspace_bytes(ctypes.byref(bad)) == 0
