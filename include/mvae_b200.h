@@ -337,6 +337,16 @@ int mvae_gemm_bf16(const void* A, long long lda, int a_mn_major, const void* B, 
 int mvae_sgemm(const float* A, long long sam, long long sak, const float* B, long long sbk, long long sbn, float* C,
                long long ldc, int M, int N, int K, const float* bias, int act, int accumulate, int splits,
                mvae_stream_t stream);
+/* The same product on the tensor cores at fp32-class accuracy (bf16 mode's path for the small latent / encoder Linears:
+ * models2d.py:28-29,41, mosesvae.py:68-69,95): each operand is split into bf16 hi + lo parts and A*B ~ Ah*Bh + Ah*Bl + Al*Bh
+ * runs as ONE tcgen05 GEMM over a 3x longer contraction (fp32 accumulation, ~2^-17 relative per product).  `scratch`
+ * (mvae_sgemm_tc_scratch_bytes(max rows, max cols of either operand), 256-byte aligned) holds the converted operands.
+ * Strides must be contiguous along k or along m / n; returns MVAE_ERR_UNSUPPORTED (nothing enqueued) otherwise, for tiny
+ * products (M*N*K < 2^22) or when the scratch is too small.  act: 0 none, 1 SELU, 2 ReLU (after the bias).                 */
+int mvae_sgemm_tc(const float* A, long long sam, long long sak, const float* B, long long sbk, long long sbn, float* C,
+                  long long ldc, int M, int N, int K, const float* bias, int act, int accumulate, void* scratch,
+                  size_t scratch_bytes, int* err_flag, mvae_stream_t stream);
+size_t mvae_sgemm_tc_scratch_bytes(long long rows_max, long long cols_max);
 
 #ifdef __cplusplus
 }

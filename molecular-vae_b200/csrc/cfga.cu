@@ -63,6 +63,7 @@ struct AWS {
   float *h[3], *flat, *h4, *mu, *lv, *z, *zr, *gi0, *gh, *c, *logits;
   // backward scratch
   float *dh_carry, *dc_carry, *dgisum, *dW_p, *dWc_p, *dWfc_p, *csum, *dTBL, *dhc, *dflat, *dh4, *dmu, *dlv, *dz, *dzr, *da5;
+  void* tcs; size_t tcs_bytes;   // bf16 mode: converted operands of the bf16x3 tensor-core path of the small fp32 GEMMs
   size_t total;
 };
 
@@ -113,6 +114,11 @@ void carve(const ADims& d, void* base, AWS* w) {
   w->dflat = c.take<float>(B * d.FLAT); w->dh4 = c.take<float>(B * D1);
   w->dmu = c.take<float>(B * Z); w->dlv = c.take<float>(B * Z); w->dz = c.take<float>(B * Z);
   w->dzr = c.take<float>(B * Z); w->da5 = c.take<float>(B * Z);
+  {
+    const long long rmax = (long long)max(Bp, 4 * DH), cmax = max(max((long long)4 * DH, (long long)d.FLAT), max((long long)D1, (long long)Z));
+    w->tcs_bytes = d.bf16 ? mvae_tc_sgemm_scratch_bytes(rmax, cmax) : 0;
+    w->tcs = c.take<uint8_t>(w->tcs_bytes);
+  }
   w->total = (c.off + 255) & ~size_t(255);
 }
 
@@ -350,7 +356,7 @@ int conv_fwd(const ADims& d, const AWS& w, const float* const* P, cudaStream_t s
 // forward up to the logits.  decode_only: start from w.z (no encoder, no saved activations needed for BPTT).
 template <typename TA>
 int run_forward(const ADims& d, const AWS& w, const float* const* P, const uint8_t* ids, const float* eps, cudaStream_t st,
-                bool decode_only, bool save) {
+                bool decode_only, bool save, bool fuse_head = false) {
   const PIdx ix{d.EL, d.DL};
   const int B = d.B, Bp = d.Bp, T = d.T, C = d.C, E = d.E, EH = d.EH, EHp = d.EHp, Z = d.Z, DH = d.DH;
   const int TB = T * Bp;
@@ -396,6 +402,18 @@ int run_forward(const ADims& d, const AWS& w, const float* const* P, const uint8
                   4 * DH, true, TB, 4 * DH, DH, w.bsum_d[l], false, 1));
       RC((lstm_fwd<TA, TA>(d, w, st, (const TA*)w.gi, (long long)Bp * 4 * DH, (const TA*)w.Whh_d[l], (TA*)w.hs_d[l], sv, DH,
                            d.bf16 ? w.WhhC_d[l] : nullptr)));
+    }
+  }
+  if constexpr (sizeof(TA) == 2) {
+    if (fuse_head) {
+      // fused head (models.py:165 softmax + train.py:31-35 BCE): logits -> softmax -> BCE -> d(logits) inside the epilogue of the
+      // vocabulary GEMM; the (T*B, C) logits / probabilities never reach HBM in the training step
+      mvae_umma_operand a{(const TA*)w.hs_d[d.DL - 1] + (size_t)Bp * DH, 0, (long long)TB, DH, DH, 1, 0, 0, 0};
+      mvae_umma_operand b{w.Wfc, 0, d.CP, DH, DH, 1, 0, 0, 0};
+      mvae_umma_out o{w.logits, d.CP, 0, 0, w.bfc, 0};
+      mvae_umma_head h{ids, B, Bp, T, d.C, d.max_len / ((float)B * (float)T * (float)d.C), w.dlogits, w.bce_sum, w.hit_count};
+      mvae_count_launches(1);
+      return mvae_umma_gemm(&a, &b, &o, TB, d.CP, DH, 64, 1, 0, w.err_flag, st, &h);
     }
   }
   RC(gemm<TA>(w.err_flag, st, (const TA*)w.hs_d[d.DL - 1] + (size_t)Bp * DH, DH, false, (const TA*)w.Wfc, DH, true, w.logits, d.CP,
@@ -581,8 +599,10 @@ template <typename TA>
 int elbo_step_t(const ADims& d, const AWS& w, const float* const* P, float* const* G, const uint8_t* ids, const float* eps,
                 float* out_scalars, float* mu_out, float* lv_out, cudaStream_t st) {
   RC(prep_weights<TA>(d, w, P, st, true));
-  RC(run_forward<TA>(d, w, P, ids, eps, st, false, true));
-  RC(head_fused<TA>(d, w, ids, nullptr, true, st));
+  const char* fe = getenv("MVAE_FUSED_HEAD");
+  const bool fuse = sizeof(TA) == 2 && d.CP == 64 && (fe ? atoi(fe) != 0 : true);
+  RC(run_forward<TA>(d, w, P, ids, eps, st, false, true, fuse));
+  if (!fuse) RC(head_fused<TA>(d, w, ids, nullptr, true, st));
   RC(run_backward<TA>(d, w, P, G, ids, eps, st, true, nullptr, nullptr));
   return finalize(d, w, out_scalars, mu_out, lv_out, st);
 }
@@ -592,6 +612,7 @@ int check_ws(const mvae_cfga_desc* desc, void* ws, size_t ws_bytes, ADims* d, AW
   if (!ws || (reinterpret_cast<uintptr_t>(ws) & 255)) return MVAE_ERR_INVALID;
   carve(*d, ws, w);
   if (ws_bytes < w->total) return MVAE_ERR_WORKSPACE;
+  g_tc = mvae_tc_ctx{(d->bf16 && tc_sgemm_enabled()) ? w->tcs : nullptr, w->tcs_bytes, w->err_flag};
   return MVAE_OK;
 }
 

@@ -109,6 +109,7 @@ struct WS {
   float* dW_p;   // [3Hp][Hp]
   float* dW3_p;  // [CP][Hp]
   float* csum;   // [4Hp]
+  void* tcs; size_t tcs_bytes;   // bf16 mode: converted operands of the bf16x3 tensor-core path of the small fp32 GEMMs
   size_t total;
 };
 
@@ -184,6 +185,8 @@ void carve(const Dims& d, void* base, WS* w) {
     w->dWih0_p = c.take<float>(3 * Hp * Zp);
   }
   w->counters = c.take<unsigned int>(Bp / 128 + 1);
+  w->tcs_bytes = d.bf16 ? mvae_tc_sgemm_scratch_bytes((long long)max((size_t)Bp, 3 * Hp), (long long)max(max(d.F0, d.Z), max(d.FLAT, (int)Hp))) : 0;
+  w->tcs = c.take<uint8_t>(w->tcs_bytes);
   w->total = (c.off + 255) & ~size_t(255);
 }
 
@@ -230,9 +233,22 @@ int gemm(const Dims& d, const WS& w, cudaStream_t st, const TA* A, long long lda
   }
 }
 
+// bf16 mode: the small fp32 GEMMs of the latent / encoder Linears go through the tensor cores (bf16x3 split, fp32-class
+// accuracy, umma_gemm.h); set per call by check_ws.  MVAE_TC_SGEMM=0 keeps them on the CUDA cores.
+thread_local mvae_tc_ctx g_tc{nullptr, 0, nullptr};
+bool tc_sgemm_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("MVAE_TC_SGEMM"); v = e ? (atoi(e) != 0) : 1; }
+  return v != 0;
+}
 inline int sg(cudaStream_t st, const float* A, long long sam, long long sak, const float* B, long long sbk,
               long long sbn, float* C, long long ldc, int M, int N, int K, const float* bias, int act, int accumulate,
               int splits = 1) {
+  if (g_tc.scratch) {
+    int n = 0;
+    const int rc = mvae_tc_sgemm(&g_tc, st, A, sam, sak, B, sbk, sbn, C, ldc, M, N, K, bias, act, accumulate, &n);
+    if (rc != MVAE_ERR_UNSUPPORTED) { count(n); return rc; }
+  }
   count();
   return simt::sgemm(st, A, sam, sak, B, sbk, sbn, C, ldc, M, N, K, bias, act, accumulate, splits);
 }
@@ -794,6 +810,7 @@ int check_ws(const mvae_cfgb_desc* desc, void* ws, size_t ws_bytes, Dims* d, WS*
   if (!ws || (reinterpret_cast<uintptr_t>(ws) & 255)) return MVAE_ERR_INVALID;
   carve(*d, ws, w);
   if (ws_bytes < w->total) return MVAE_ERR_WORKSPACE;
+  g_tc = mvae_tc_ctx{(d->bf16 && tc_sgemm_enabled()) ? w->tcs : nullptr, w->tcs_bytes, w->err_flag};
   return MVAE_OK;
 }
 
@@ -1044,5 +1061,17 @@ int mvae_sgemm(const float* A, long long sam, long long sak, const float* B, lon
   return simt::sgemm(reinterpret_cast<cudaStream_t>(stream), A, sam, sak, B, sbk, sbn, C, ldc, M, N, K, bias, act,
                      accumulate, splits);
 }
+
+int mvae_sgemm_tc(const float* A, long long sam, long long sak, const float* B, long long sbk, long long sbn, float* C,
+                  long long ldc, int M, int N, int K, const float* bias, int act, int accumulate, void* scratch,
+                  size_t scratch_bytes, int* err_flag, mvae_stream_t stream) {
+  mvae_tc_ctx ctx{scratch, scratch_bytes, err_flag};
+  int n = 0;
+  const int rc = mvae_tc_sgemm(&ctx, reinterpret_cast<cudaStream_t>(stream), A, sam, sak, B, sbk, sbn, C, ldc, M, N, K, bias, act,
+                               accumulate, &n);
+  if (rc == MVAE_OK) count(n);
+  return rc;
+}
+size_t mvae_sgemm_tc_scratch_bytes(long long rows_max, long long cols_max) { return mvae_tc_sgemm_scratch_bytes(rows_max, cols_max); }
 
 }  // extern "C"

@@ -4,6 +4,7 @@
 #include "common.cuh"
 #include "simt_kernels.cuh"
 #include "umma_gemm.h"
+#include <stdlib.h>
 
 void mvae_count_launches(int n);   // cfgb.cu
 struct mvae_graph;
@@ -50,9 +51,22 @@ int gemm(int* err_flag, cudaStream_t st, const TA* A, long long lda, bool a_tran
     return mvae_umma_gemm(&a, &b, &o, M, N, K, bn, splits, 0, err_flag, st, nullptr, nullptr, nullptr, vl);
   }
 }
+// bf16 mode: the small fp32 GEMMs (latent / encoder Linears, token tables) go through the tensor cores (bf16x3 split,
+// fp32-class accuracy, umma_gemm.h); the context is set per call by the unit's check_ws.  MVAE_TC_SGEMM=0: CUDA cores only.
+thread_local mvae_tc_ctx g_tc{nullptr, 0, nullptr};
+inline bool tc_sgemm_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("MVAE_TC_SGEMM"); v = e ? (atoi(e) != 0) : 1; }
+  return v != 0;
+}
 inline int sg(cudaStream_t st, const float* A, long long sam, long long sak, const float* B, long long sbk,
               long long sbn, float* C, long long ldc, int M, int N, int K, const float* bias, int act, int accumulate,
               int splits = 1) {
+  if (g_tc.scratch) {
+    int n = 0;
+    const int rc = mvae_tc_sgemm(&g_tc, st, A, sam, sak, B, sbk, sbn, C, ldc, M, N, K, bias, act, accumulate, &n);
+    if (rc != MVAE_ERR_UNSUPPORTED) { mvae_count_launches(n); return rc; }
+  }
   mvae_count_launches(1);
   return simt::sgemm(st, A, sam, sak, B, sbk, sbn, C, ldc, M, N, K, bias, act, accumulate, splits);
 }

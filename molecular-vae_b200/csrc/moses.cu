@@ -32,6 +32,11 @@ struct MDims {
   float drop; unsigned int drop_seed;   // train-mode dropout between decoder layers (0 = off)
 };
 
+bool moses_fused_head_enabled() {
+  const char* e = getenv("MVAE_FUSED_HEAD");
+  return e ? atoi(e) != 0 : true;
+}
+
 int make_dims(const mvae_moses_desc* d, MDims* o) {
   if (!d) return MVAE_ERR_INVALID;
   if (d->batch <= 0 || d->max_len < 2 || d->max_len > 512 || d->vocab < 5 || d->vocab > 256 || d->d_z <= 0 ||
@@ -74,6 +79,7 @@ struct MWS {
   void *WhhT[4]; float *bcomb[4]; unsigned int* counters;
   uint8_t* tokTr;   // ids^T with every row reversed inside its own length (reverse encoder direction on the persistent kernel)
   void *WhhT_enc; float *tbl_comb; uint8_t* tokT; void* zproj_rb;   // encoder W_hh^T, table + (b_hr, b_hz, 0), ids^T [T][Bp], zproj RB bf16
+  void* tcs; size_t tcs_bytes;   // bf16 mode: converted operands of the bf16x3 tensor-core path of the small fp32 GEMMs
   size_t total;
 };
 
@@ -131,6 +137,11 @@ void carve(const MDims& d, void* base, MWS* w) {
   w->tokT = c.take<uint8_t>(T * Bp); w->zproj_rb = c.take<uint8_t>(Bp * 3 * Hd * 2);
   w->tokTr = d.bidir ? c.take<uint8_t>(T * Bp) : nullptr;
   w->dW_p = c.take<float>(3 * Hd * Hd); w->dWfc_p = c.take<float>(d.CP * Hd); w->csum = c.take<float>(4 * Hd);
+  {
+    const long long rmax = (long long)max(Bp, 3 * Hd), cmax = max(max((long long)3 * Hd, (long long)d.Hin), max((long long)d.MLP, max((long long)d.Z, (long long)d.CP)));
+    w->tcs_bytes = d.bf16 ? mvae_tc_sgemm_scratch_bytes(rmax, cmax) : 0;
+    w->tcs = c.take<uint8_t>(w->tcs_bytes);
+  }
   w->total = (c.off + 255) & ~size_t(255);
 }
 
@@ -892,11 +903,30 @@ int step_t(const MDims& d, const MWS& w, const float* const* P, float* const* G,
     RC(gru_fwd<TA>(d, w, st, (const TA*)w.gi, (const TA*)w.Whh[l], w.bhh[l], (TA*)w.hs[l], (TA*)w.sv[l], Hd, w.h0, nullptr, nullptr,
                    false, nullptr, d.bf16 ? w.WhhC[l] : nullptr, w.bhhC[l], act));
   }
+  bool ce_fused = false;
+  if constexpr (sizeof(TA) == 2) {
+    // fused CE head (mosesvae.py:190-197): logits -> log-softmax -> NLL -> d(logits) inside the epilogue of the vocabulary GEMM;
+    // the (T*B, V) logits never reach HBM.  Needs the vocabulary in one 64-wide tile and nobody asking for the logits (y_out);
+    // MVAE_FUSED_HEAD=0 keeps the two-kernel form (the cross-check).  Row tiles past every running sequence are skipped by the
+    // GEMM, so their d(logits) rows are zeroed first (the bias sum below reads every row).
+    if (CP == 64 && !y_out && backward && moses_fused_head_enabled()) {
+      if (VLM) RC(memset_async(w.dlogits, (size_t)TB * CP * sizeof(TA), st));
+      mvae_umma_operand a{(const TA*)w.hs[L - 1] + (size_t)Bp * Hd, 0, (long long)TB, Hd, Hd, 1, 0, 0, 0};
+      mvae_umma_operand b{w.Wfc, 0, CP, Hd, Hd, 1, 0, 0, 0};
+      mvae_umma_out o{w.logits, CP, 0, 0, w.bfc, 0};
+      mvae_umma_head h{ids, B, Bp, T, V, 0.f, w.dlogits, w.nll_sum, nullptr, 1, lens, w.M, d.rec_w};
+      mvae_count_launches(1);
+      RC(mvae_umma_gemm(&a, &b, &o, TB, CP, Hd, 64, 1, 0, w.err_flag, st, &h, nullptr, nullptr, VLM));
+      ce_fused = true;
+    }
+  }
+  if (!ce_fused) {
   RC(gemm<TA>(w.err_flag, st, (const TA*)w.hs[L - 1] + (size_t)Bp * Hd, Hd, false, (const TA*)w.Wfc, Hd, true, w.logits, CP, false,
               TB, CP, Hd, w.bfc, false, 1, 64, VLM));
   head_ce_kernel<TA><<<(unsigned)ceil_div64((long long)TB * 32, 256), 256, 0, st>>>(
       w.logits, CP, V, ids, T, lens, B, Bp, T, w.M, d.rec_w, w.bfc, backward ? (TA*)w.dlogits : nullptr, y_out, w.nll_sum);
   KCHECK();
+  }
   finalize_kernel<<<1, 1, 0, st>>>(w.kl_sum, w.nll_sum, w.M, B, d.kl_w, d.rec_w, out_scalars); KCHECK();
   if (z_out) { mvae_count_launches(1); MVAE_CUDA_CHECK(cudaMemcpyAsync(z_out, w.z, (size_t)B * Z * 4, cudaMemcpyDeviceToDevice, st)); }
   if (lv_out) { mvae_count_launches(1); MVAE_CUDA_CHECK(cudaMemcpyAsync(lv_out, w.lv, (size_t)B * Z * 4, cudaMemcpyDeviceToDevice, st)); }
@@ -1360,6 +1390,7 @@ int check_ws(const mvae_moses_desc* desc, void* ws, size_t ws_bytes, MDims* d, M
   if (!ws || (reinterpret_cast<uintptr_t>(ws) & 255)) return MVAE_ERR_INVALID;
   carve(*d, ws, w);
   if (ws_bytes < w->total) return MVAE_ERR_WORKSPACE;
+  g_tc = mvae_tc_ctx{(d->bf16 && tc_sgemm_enabled()) ? w->tcs : nullptr, w->tcs_bytes, w->err_flag};
   return MVAE_OK;
 }
 

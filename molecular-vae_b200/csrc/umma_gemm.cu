@@ -43,6 +43,7 @@ struct KernelParams {
   long long ldc;
   const float* bias;   // per-N, may be null
   int out_rb;          // bf16 output in the row-blocked layout
+  int out_act;         // generic epilogue, splits == 1: 0 none, 1 SELU, 2 ReLU (after the bias)
   int out_bf16;        // 1: bf16 output, 0: fp32
   int accumulate;      // fp32 only: D += result (plain RMW, or red.add when splits > 1)
   int* err_flag;
@@ -521,7 +522,56 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             if (row_ok) {
               const int t = row / h.Bp, b = row - t * h.Bp;
               uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(h.dlogits) + (long long)row * 64);
-              if (b >= h.B) {
+              if (h.mode == 1) {
+                // ---- shifted cross entropy (MOSES VAE): log-softmax + NLL + its gradient, full-precision exp / log
+                const int L = b < h.B ? __ldg(h.lens + b) : 0;
+                if (!(b < h.B && t + 1 < L)) {
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) o[j] = make_uint4(0u, 0u, 0u, 0u);
+                } else {
+                  const int y = h.ids[(long long)b * h.T + t + 1];
+                  float v[64];
+#pragma unroll
+                  for (int j = 0; j < 32; ++j) { v[j] = __uint_as_float(r0[j]); v[32 + j] = __uint_as_float(r1[j]); }
+                  float m = -INFINITY, at = 0.f;
+#pragma unroll
+                  for (int j = 0; j < 64; ++j) {
+                    if (j >= h.C) break;
+                    if (p.bias) v[j] += __ldg(p.bias + j);
+                    m = fmaxf(m, v[j]);
+                    if (j == y) at = v[j];
+                  }
+                  float ssum = 0.f;
+#pragma unroll
+                  for (int j = 0; j < 64; ++j) {
+                    if (j >= h.C) break;
+                    v[j] = expf(v[j] - m);
+                    ssum += v[j];
+                  }
+                  const float sc = h.rec_w / (float)__ldg(h.Mcount);
+                  const float inv = sc / ssum;
+#pragma unroll
+                  for (int j8 = 0; j8 < 8; ++j8) {
+                    float d[8];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                      const int j = j8 * 8 + k;
+                      d[k] = j < h.C ? fmaf(v[j], inv, j == y ? -sc : 0.f) : 0.f;
+                    }
+                    uint4 pk;
+                    __nv_bfloat162 b0 = __floats2bfloat162_rn(d[0], d[1]);
+                    __nv_bfloat162 b1 = __floats2bfloat162_rn(d[2], d[3]);
+                    __nv_bfloat162 b2 = __floats2bfloat162_rn(d[4], d[5]);
+                    __nv_bfloat162 b3 = __floats2bfloat162_rn(d[6], d[7]);
+                    pk.x = *reinterpret_cast<uint32_t*>(&b0);
+                    pk.y = *reinterpret_cast<uint32_t*>(&b1);
+                    pk.z = *reinterpret_cast<uint32_t*>(&b2);
+                    pk.w = *reinterpret_cast<uint32_t*>(&b3);
+                    o[j8] = pk;
+                  }
+                  loss = (double)(m + logf(ssum) - at);
+                }
+              } else if (b >= h.B) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) o[j] = make_uint4(0u, 0u, 0u, 0u);
               } else {
@@ -655,6 +705,14 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
             for (int j = 0; j < 32; ++j)
               if (col0 + j < p.N) v[j] += __ldg(p.bias + col0 + j);
+          }
+          if (p.out_act == 1) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              v[j] = 1.0507009873554804934193349852946f * (v[j] > 0.f ? v[j] : 1.6732632423543772848170429916717f * expm1f(v[j]));
+          } else if (p.out_act == 2) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
           }
           const bool full = (col0 + 32 <= p.N);
           if (p.out_bf16 && p.out_rb) {
@@ -820,6 +878,7 @@ int mvae_umma_gemm(const mvae_umma_operand* A, const mvae_umma_operand* B, const
                               (cell->gates == 3 && !cell->gi && !(cell->tbl && cell->add && cell->tok))))
     return MVAE_ERR_INVALID;
   if (head && (bn != 64 || splits > 1 || N > 64 || head->C > N || !head->ids || !head->dlogits)) return MVAE_ERR_INVALID;
+  if (head && head->mode == 1 && (!head->lens || !head->Mcount)) return MVAE_ERR_INVALID;
   if (g_num_sms == 0) {
     int dev = 0;
     MVAE_CUDA_CHECK(cudaGetDevice(&dev));
@@ -830,6 +889,7 @@ int mvae_umma_gemm(const mvae_umma_operand* A, const mvae_umma_operand* B, const
   if (splits < 1) splits = 1;
   if (splits > 1 && (D->bf16 || D->bias)) return MVAE_ERR_INVALID;  // split-K reduces with fp32 red.add
   if (D->bf16 && D->accumulate) return MVAE_ERR_INVALID;
+  if (D->act && (splits > 1 || D->bf16 || D->accumulate || head || cell || sample)) return MVAE_ERR_INVALID;
   KernelParams kp{};
   kp.M = M; kp.N = N; kp.K = K;
   kp.slabA = A->slab; kp.slabB = B->slab;
@@ -842,6 +902,7 @@ int mvae_umma_gemm(const mvae_umma_operand* A, const mvae_umma_operand* B, const
   kp.out = D->ptr; kp.ldc = D->ld; kp.bias = D->bias; kp.out_bf16 = D->bf16; kp.accumulate = D->accumulate;
   kp.err_flag = err_flag;
   kp.out_rb = D->rb;
+  kp.out_act = D->act;
   kp.head_mode = head ? 1 : 0;
   if (head) kp.head = *head;
   kp.cell_mode = cell ? 1 : 0;
@@ -867,4 +928,101 @@ int mvae_umma_gemm(const mvae_umma_operand* A, const mvae_umma_operand* B, const
     case 192: return launch_bn<192>(a_mn, b_mn, tmA, tmB, kp, grid, stream);
     default: return launch_bn<256>(a_mn, b_mn, tmA, tmB, kp, grid, stream);
   }
+}
+
+// ---------------------------------------------------------------------------------------
+// fp32 GEMM on the tensor cores at fp32-class accuracy ("bf16x3"): every fp32 operand element x is split into
+// hi = bf16(x), lo = bf16(x - hi); A*B ~ A_hi*B_hi + A_hi*B_lo + A_lo*B_hi is ONE bf16 GEMM over a three times longer
+// contraction, K' = [hi | hi | lo] (A) against [hi | lo | hi] (B), fp32 accumulation in TMEM.  The dropped terms are
+// ~2^-17 relative per product.  Used for the small latent / encoder Linears (K, N of a few hundred; M = the batch) that
+// were CUDA-core SGEMMs: two conversion launches + one tcgen05 GEMM instead of a latency-bound SIMT kernel.
+// ---------------------------------------------------------------------------------------
+namespace {
+
+// One thread converts 8 consecutive elements along the source's contiguous dimension.
+//   layout 0 (K-major operand):  X(mn, k) = src[mn * so + k];  dst[mn][seg * Kp + k]            (ldd = 3 * Kp)
+//   layout 1 (MN-major operand): X(mn, k) = src[k * so + mn];  dst[seg * Kp + k][mn]            (ldd = roundup(MN, 8))
+// role 0: segments (hi, hi, lo); role 1: (hi, lo, hi).  Pads (k in [K, Kp), mn in [MN, ldd)) are zero-filled.
+__global__ void split3_kernel(const float* __restrict__ src, long long so, int n_outer, int n_outer_p, int n_inner, int n_inner_p,
+                              __nv_bfloat16* __restrict__ dst, int layout, int Kp, long long ldd, int role) {
+  const int groups = n_inner_p >> 3;
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= (long long)n_outer_p * groups) return;
+  const int o = (int)(idx / groups), c0 = (int)(idx % groups) * 8;
+  uint32_t hi[4], lo[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float x[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int c = c0 + 2 * j + e;
+      x[e] = (o < n_outer && c < n_inner) ? __ldg(src + (long long)o * so + c) : 0.f;
+    }
+    const __nv_bfloat16 h0 = __float2bfloat16_rn(x[0]), h1 = __float2bfloat16_rn(x[1]);
+    const __nv_bfloat16 l0 = __float2bfloat16_rn(x[0] - __bfloat162float(h0)), l1 = __float2bfloat16_rn(x[1] - __bfloat162float(h1));
+    hi[j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+    lo[j] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+  }
+  const uint4 H = make_uint4(hi[0], hi[1], hi[2], hi[3]), L = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+#pragma unroll
+  for (int seg = 0; seg < 3; ++seg) {
+    const bool low = role == 0 ? seg == 2 : seg == 1;
+    __nv_bfloat16* d = layout == 0 ? dst + (long long)o * ldd + (long long)seg * Kp + c0
+                                   : dst + ((long long)seg * Kp + o) * ldd + c0;
+    *reinterpret_cast<uint4*>(d) = low ? L : H;
+  }
+}
+
+}  // namespace
+
+size_t mvae_tc_sgemm_scratch_bytes(long long rows_max, long long cols_max) {
+  const size_t r = (size_t)((rows_max + 7) & ~7ll), c = (size_t)((cols_max + 7) & ~7ll);
+  return 2 * (3 * r * c * 2 + 256);
+}
+
+int mvae_tc_sgemm(const mvae_tc_ctx* ctx, cudaStream_t st, const float* A, long long sam, long long sak, const float* B,
+                  long long sbk, long long sbn, float* C, long long ldc, int M, int N, int K, const float* bias, int act,
+                  int accumulate, int* launches) {
+  if (!ctx || !ctx->scratch || M <= 0 || N <= 0 || K <= 0) return MVAE_ERR_UNSUPPORTED;
+  if ((long long)M * N * K < (1ll << 22)) return MVAE_ERR_UNSUPPORTED;     // tiny products: one SIMT launch is cheaper
+  const bool a_k = sak == 1, b_k = sbk == 1;
+  if ((!a_k && sam != 1) || (!b_k && sbn != 1)) return MVAE_ERR_UNSUPPORTED;
+  if (act && accumulate) return MVAE_ERR_UNSUPPORTED;
+  const int Kp = (K + 7) & ~7, Mp = (M + 7) & ~7, Np = (N + 7) & ~7;
+  const size_t a_bytes = (a_k ? (size_t)M * 3 * Kp : (size_t)3 * Kp * Mp) * 2;
+  const size_t b_bytes = (b_k ? (size_t)N * 3 * Kp : (size_t)3 * Kp * Np) * 2;
+  const size_t a_off = 0, b_off = (a_bytes + 255) & ~(size_t)255;
+  if (b_off + b_bytes > ctx->bytes) return MVAE_ERR_UNSUPPORTED;
+  __nv_bfloat16* dA = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(ctx->scratch) + a_off);
+  __nv_bfloat16* dB = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(ctx->scratch) + b_off);
+  auto conv = [&](const float* src, bool kfast, long long so, int MN, int MNp, __nv_bfloat16* dst, int role) {
+    // kfast: outer = mn (no pad rows), inner = k;  else: outer = k (padded to Kp), inner = mn
+    const int n_outer = kfast ? MN : K, n_outer_p = kfast ? MN : Kp, n_inner = kfast ? K : MN, n_inner_p = kfast ? Kp : MNp;
+    const long long total = (long long)n_outer_p * (n_inner_p >> 3);
+    split3_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(src, so, n_outer, n_outer_p, n_inner, n_inner_p, dst,
+                                                                   kfast ? 0 : 1, Kp, kfast ? 3ll * Kp : (long long)MNp, role);
+  };
+  conv(A, a_k, a_k ? sam : sak, M, Mp, dA, 0);
+  conv(B, b_k, b_k ? sbn : sbk, N, Np, dB, 1);
+  MVAE_CUDA_CHECK(cudaGetLastError());
+  int n_launch = 3;
+  const int bn = N <= 64 ? 64 : (N <= 1024 ? 128 : 256);
+  const int units = ((M + BM - 1) / BM) * ((N + bn - 1) / bn);
+  const int kb_total = (3 * Kp + BK - 1) / BK;
+  int splits = 1;
+  if (!bias && !act && units <= 48 && kb_total >= 16) {
+    splits = (148 + units - 1) / units;
+    if (splits > kb_total / 4) splits = kb_total / 4;
+    if (splits < 1) splits = 1;
+  }
+  if (splits > 1 && !accumulate) {
+    if (ldc == N) MVAE_CUDA_CHECK(cudaMemsetAsync(C, 0, (size_t)M * N * 4, st));
+    else MVAE_CUDA_CHECK(cudaMemset2DAsync(C, (size_t)ldc * 4, 0, (size_t)N * 4, M, st));
+    ++n_launch;
+  }
+  if (launches) *launches = n_launch;
+  mvae_umma_operand a{dA, a_k ? 0 : 1, M, 3ll * Kp, a_k ? 3ll * Kp : (long long)Mp, 1, 0, 0, 0};
+  mvae_umma_operand b{dB, b_k ? 0 : 1, N, 3ll * Kp, b_k ? 3ll * Kp : (long long)Np, 1, 0, 0, 0};
+  mvae_umma_out o{C, ldc, 0, (accumulate || splits > 1) ? 1 : 0, bias, 0, act};
+  return mvae_umma_gemm(&a, &b, &o, M, N, 3 * Kp, bn, splits, 0, ctx->err_flag, st);
 }

@@ -26,6 +26,13 @@ struct mvae_umma_head {
   void* dlogits;              // bf16 [M][64]
   double* bce_sum;
   int* hit_count;             // [B]
+  // mode 1: shifted cross entropy with ignore_index (mosesvae.py:190-197) instead of the BCE: row (t, b) is a target
+  // position iff t + 1 < lens[b]; target token ids[b][t + 1] (ids rows of T entries); bce_sum receives sum(-log softmax[tgt]);
+  // dlogits = (softmax - onehot) * rec_w / *Mcount on target rows, zeros elsewhere (C = vocabulary size <= 64)
+  int mode;
+  const int* lens;            // [B]
+  const int* Mcount;          // device scalar: number of target positions of the batch
+  float rec_w;
 };
 
 // Optional fused GRU-cell epilogue (decode / per-step engines): the GEMM's N dimension is laid out in tiles of 64 hidden
@@ -81,6 +88,7 @@ struct mvae_umma_out {
   int accumulate;     // fp32 only: D += A*B
   const float* bias;  // optional per-column bias (fp32)
   int rb;             // bf16 output only: row-blocked layout [M/32][ld/8][32][8] (consumed by the recurrence epilogues)
+  int act;            // fp32 output, splits 1, no accumulate: 0 none, 1 SELU, 2 ReLU applied after the bias
 };
 
 // Optional packed-sequence skipping for GEMMs over time-major slabs ([T][rows_per_slab][.], rows_per_slab % 128 == 0):
@@ -101,3 +109,14 @@ int mvae_umma_gemm(const mvae_umma_operand* A, const mvae_umma_operand* B, const
                    int bn, int splits, int max_ctas, int* err_flag, cudaStream_t stream, const mvae_umma_head* head = nullptr,
                    const mvae_umma_cell* cell = nullptr, const mvae_umma_sample* sample = nullptr,
                    const mvae_umma_varlen* varlen = nullptr);
+
+// fp32-in / fp32-out GEMM with simt::sgemm's strided interface (A(m,k) = A[m*sam + k*sak], B(k,n) = B[k*sbk + n*sbn]) on the
+// tensor cores: operands split into bf16 (hi, lo) parts on the fly ("bf16x3", ~2^-17 relative per product), one tcgen05 GEMM
+// over K' = 3 * roundup(K, 8).  `ctx->scratch` holds the two converted operands.  Returns MVAE_ERR_UNSUPPORTED (nothing
+// enqueued) when the strides are not one of the two contiguous forms, the product is tiny, or the scratch is too small --
+// the caller then takes the CUDA-core path.  *launches (optional) receives the number of enqueued operations.
+struct mvae_tc_ctx { void* scratch; size_t bytes; int* err_flag; };
+size_t mvae_tc_sgemm_scratch_bytes(long long rows_max, long long cols_max);
+int mvae_tc_sgemm(const mvae_tc_ctx* ctx, cudaStream_t st, const float* A, long long sam, long long sak, const float* B,
+                  long long sbk, long long sbn, float* C, long long ldc, int M, int N, int K, const float* bias, int act,
+                  int accumulate, int* launches);

@@ -235,6 +235,57 @@ def test_gemm_bf16_c_abi():
     assert (d.double() - ref).abs().max().item() < 1e-2
 
 
+@pytest.mark.parametrize("shape", [
+    # (M, N, K, A k-contiguous, B k-contiguous, bias, act, accumulate): the forms the model units use
+    (4096, 435, 90, True, True, True, 1, 0),      # fc0 + SELU (models2d.py:28)
+    (4096, 292, 435, True, True, True, 0, 0),     # fc11 / fc12
+    (292, 435, 4096, False, False, False, 0, 0),  # weight gradient: contraction over the batch rows, split-K
+    (4096, 435, 292, True, False, False, 0, 1),   # input gradient accumulated onto an existing value
+    (300, 70, 1000, True, False, True, 2, 0),     # ragged everything + ReLU
+])
+def test_tc_sgemm_bf16x3_is_fp32_class(shape):
+    """The tensor-core path of the small fp32 GEMMs (bf16 hi/lo split, one tcgen05 GEMM over 3K) against an fp64 product:
+    max error <= 2e-5 of the output scale -- 100x below the bf16 budget, the same class as the CUDA-core fp32 SGEMM."""
+    import ctypes
+    m = load_pkg()
+    lib, vp = m._lib.lib, ctypes.c_void_p
+    M, N, K, a_k, b_k, has_bias, act, acc = shape
+    g = torch.Generator(device="cuda").manual_seed(5)
+    A = torch.randn(M, K, device="cuda", generator=g)
+    Bm = torch.randn(K, N, device="cuda", generator=g) * 0.1
+    bias = torch.randn(N, device="cuda", generator=g) if has_bias else None
+    C0 = torch.randn(M, N, device="cuda", generator=g)
+    a_st = A.contiguous() if a_k else A.t().contiguous()          # [M][K] or [K][M]
+    b_st = Bm.t().contiguous() if b_k else Bm.contiguous()        # [N][K] or [K][N]
+    sam, sak = (K, 1) if a_k else (1, M)
+    sbk, sbn = (1, K) if b_k else (N, 1)
+    C = C0.clone()
+    nbytes = lib.mvae_sgemm_tc_scratch_bytes(max(M, N, K), max(M, N, K))
+    scratch = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    err = torch.zeros(1, dtype=torch.int32, device="cuda")
+    rc = lib.mvae_sgemm_tc(vp(a_st.data_ptr()), sam, sak, vp(b_st.data_ptr()), sbk, sbn, vp(C.data_ptr()), N, M, N, K,
+                           vp(bias.data_ptr() if has_bias else 0), act, acc, vp(scratch.data_ptr()), nbytes, vp(err.data_ptr()),
+                           vp(torch.cuda.current_stream().cuda_stream))
+    assert rc == 0
+    torch.cuda.synchronize()
+    assert int(err.item()) == 0
+    ref = A.double() @ Bm.double()
+    if has_bias:
+        ref = ref + bias.double()
+    if acc:
+        ref = ref + C0.double()
+    if act == 1:
+        ref = torch.nn.functional.selu(ref)
+    elif act == 2:
+        ref = torch.relu(ref)
+    scale = ref.abs().max().item()
+    assert (C.double() - ref).abs().max().item() <= 2e-5 * scale
+    # tiny products are declined (the caller keeps its CUDA-core launch)
+    rc = lib.mvae_sgemm_tc(vp(a_st.data_ptr()), sam, sak, vp(b_st.data_ptr()), sbk, sbn, vp(C.data_ptr()), N, 8, 8, 8,
+                           vp(0), 0, 0, vp(scratch.data_ptr()), nbytes, vp(err.data_ptr()), vp(torch.cuda.current_stream().cuda_stream))
+    assert rc == -4
+
+
 @pytest.mark.parametrize("kind", ["adam", "sgd"])
 def test_fused_clip_and_optimizer_match_torch(kind):
     """clip_grad_norm + Adam (train.py:81,102-104) / SGD momentum (train_distributed.py:73,91-94) on flat buffers."""

@@ -456,6 +456,33 @@ def test_moses_persistent_sweeps_equal_per_step_engine_large_batch(monkeypatch, 
     assert not bad, bad
 
 
+@pytest.mark.parametrize("B", [300, 1100])
+def test_moses_fused_ce_head_equals_two_kernel_head(monkeypatch, B):
+    """The cross-entropy head inside the vocabulary GEMM's epilogue (logits never in HBM, mosesvae.py:190-197) against the
+    two-kernel form (GEMM -> logits -> head_ce_kernel, MVAE_FUSED_HEAD=0) on the same bf16 path: same softmax inputs, so the
+    loss terms agree to 1e-5 and every gradient to 2e-3 relative L2 (bf16 rounding of d(logits) happens in both)."""
+    m = load_pkg()
+    P, seqs, eps, pad, model = _setup(m, "bf16", 331, 600 + B, B)
+    x = [torch.from_numpy(s).cuda() for s in seqs]
+    epst = torch.from_numpy(eps).cuda()
+    res = {}
+    for fused in ("1", "0"):
+        monkeypatch.setenv("MVAE_FUSED_HEAD", fused)
+        for p in model.parameters():
+            p.grad = None
+        if getattr(model, "_ws", None) is not None:
+            model._ws.fill_(0xFF)
+        out = model.elbo_step(x, kl_weight=0.1, eps=epst)
+        torch.cuda.synchronize()
+        model.check_device_error()
+        res[fused] = (out.cpu().numpy().copy(), {k: p.grad.detach().cpu().numpy().copy() for k, p in model.named_parameters()})
+    (s1, g1), (s0, g0) = res["1"], res["0"]
+    assert np.isfinite(s1).all() and all(np.isfinite(v).all() for v in g1.values())
+    assert abs(s1[1] - s0[1]) <= 1e-5 * abs(s0[1]) and abs(s1[2] - s0[2]) <= 1e-5 * abs(s0[2]), (s1, s0)
+    bad = {k: rel_l2(g1[k], g0[k]) for k in g0 if not rel_l2(g1[k], g0[k]) <= 2e-3}
+    assert not bad, bad
+
+
 # ---- BASELINE.json configs[3]: the VAE step with the property head, phases for data parallelism ----
 def _joint_oracle(P, Pb, run, seqs, eps, pad, target, klw, bw):
     fwd = mo.moses_step({k: v.astype(np.float64) for k, v in P.items()}, seqs, eps.astype(np.float64), pad, kl_weight=klw, need_grads=False)
