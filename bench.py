@@ -329,6 +329,29 @@ def rec_kernel_times(model, eng, params, ids_dev, eps_dev, steps=3):
     return out
 
 
+def l2_fabric_probe():
+    """Measured L2 <-> SM delivery rate of this GPU (mvae_l2_probe: all SMs stream a 32 MiB L2-resident buffer with 16-byte
+    L1-bypassing accesses): read-only and read+write.  The recurrence sweeps are bound by this fabric, not by the tensor pipe."""
+    import ctypes
+    import torch
+    import molecular_vae_b200 as m
+    lib, vp = m._lib.lib, ctypes.c_void_p
+    nbytes, passes = 32 << 20, 24
+    buf = torch.zeros(nbytes, dtype=torch.uint8, device="cuda")
+    st = vp(torch.cuda.current_stream().cuda_stream)
+    out = {}
+    for mode, name in ((0, "read"), (1, "copy")):
+        best = 0.0
+        for ctas in (148 * 2, 148 * 4):
+            fn = lambda: m._lib.check(lib.mvae_l2_probe(vp(buf.data_ptr()), nbytes, passes, mode, ctas, st))
+            t = time_kernel(fn, iters=5)
+            moved = nbytes * passes if mode == 0 else (nbytes // 2) * passes * 2
+            best = max(best, moved / t * 1e-9)
+        out[name + "_gbs"] = best
+    out["probe"] = "32 MiB L2-resident buffer, 24 passes, 16-byte ld.global.cg / st.global.cg from every SM, best of 296 / 592 CTAs x 512 threads"
+    return out
+
+
 def ncu_traffic(path, kernel_substr):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel_substr` from a committed ncu --set full summary."""
     try:
@@ -377,15 +400,28 @@ def run_ours(args):
     eng = model.engine(B, max_len=120)
     eng.set_train(True)
     nodes = eng.capture_elbo_step([p.data for p in params], [p.grad for p in params], ids_dev, eps_dev)
-    phased = None
+    phased, graphed = None, None
+    dp_mode = "none"
     if world > 1:
-        # data parallel: the step is cut into one CUDA graph per GRU layer; the all-reduce of the gradient bucket a
-        # phase finalises runs on NCCL's stream while the next phase's BPTT sweep runs (train_distributed.py:72)
-        eng.capture_elbo_step_phases([p.data for p in params], [p.grad for p in params], ids_dev, eps_dev)
+        # data parallel (train_distributed.py:72): the step runs as one phase per GRU layer; the gradient bucket a phase
+        # finalises is all-reduced (NCCL AVG) on NCCL's stream while the next phase's BPTT sweep runs.  Default: the phases
+        # AND the all-reduces are captured into ONE CUDA graph (ddp.GraphedDataParallelStep); MVAE_DP_GRAPH=0 keeps one graph
+        # per phase with the collectives issued from the host between them.
         buckets = m.ddp.phase_buckets(m.param_order(CFG["layers"]), [p.numel() for p in params], CFG["layers"])
-        phased = m.ddp.PhasedAllReduce(flat, buckets)
+        P_, G_ = [p.data for p in params], [p.grad for p in params]
+        if os.environ.get("MVAE_DP_GRAPH", "1") != "0":
+            graphed = m.ddp.GraphedDataParallelStep(lambda ph: eng.elbo_step_phase(P_, G_, ids_dev, eps_dev, ph),
+                                                    CFG["layers"], flat, buckets)
+            dp_mode = "one CUDA graph: 3 phases + 3 bucket all-reduces (NCCL AVG) as forked branches"
+        else:
+            eng.capture_elbo_step_phases(P_, G_, ids_dev, eps_dev)
+            phased = m.ddp.PhasedAllReduce(flat, buckets)
+            dp_mode = "3 phase graphs, bucket all-reduces (NCCL AVG) issued from the host between them"
 
     def step_resident():
+        if graphed is not None:
+            graphed.step()
+            return
         if phased is None:
             eng.launch_graph()
             return
@@ -415,9 +451,28 @@ def run_ours(args):
     e1.record(st)
     barrier()
     launches = int(m._lib.lib.mvae_launch_count())
+    if graphed is not None:     # torch replays the captured graph: count what the capture enqueued, per replay
+        launches = graphed.launches_per_step * args.steps
     sec = e0.elapsed_time(e1) * 1e-3
     scal = eng.scalars.cpu().numpy().tolist()
 
+    solo_ms = None
+    if world > 1:
+        # every rank's own step WITHOUT the exchange (its local CUDA graph of the fused step, no barrier): the spread between
+        # the GPUs of the box bounds the weak-scaling efficiency, since the collective makes all ranks wait for the slowest
+        for _ in range(2):
+            eng.launch_graph()
+        torch.cuda.synchronize()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record(st)
+        for _ in range(5):
+            eng.launch_graph()
+        s1.record(st)
+        torch.cuda.synchronize()
+        solo = torch.tensor([s0.elapsed_time(s1) / 5], dtype=torch.float64, device="cuda")
+        allsolo = [torch.zeros_like(solo) for _ in range(world)]
+        dist.all_gather(allsolo, solo)
+        solo_ms = [float(t.item()) for t in allsolo]
     # end to end through the public API: pinned host ids -> H2D, device-side eps draw, fused step, loss D2H
     def step_e2e():
         x = ids_host.to("cuda", non_blocking=True)
@@ -441,7 +496,11 @@ def run_ours(args):
     sampler.join(timeout=2)
 
     tmax = torch.tensor([sec, sec_e2e], dtype=torch.float64, device="cuda")
+    per_rank_ms = [sec / args.steps * 1e3]
     if world > 1:
+        allt = [torch.zeros_like(tmax) for _ in range(world)]
+        dist.all_gather(allt, tmax)
+        per_rank_ms = [float(t[0].item()) / args.steps * 1e3 for t in allt]   # device time of every rank's own timed region
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     sec, sec_e2e = tmax.tolist()
     value = world * B * args.steps / sec
@@ -516,7 +575,8 @@ def run_ours(args):
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "batch_per_gpu": B, "global_batch": B * world,
                        "parallelism": f"dp{world}",
-                       "allreduce": "none" if world == 1 else "3 gradient buckets (per GRU layer), NCCL, overlapped with the next BPTT sweep",
+                       "allreduce": "none" if world == 1 else "3 gradient buckets (per GRU layer), overlapped with the next BPTT sweep; " + dp_mode,
+                       "per_rank_ms_per_step": per_rank_ms, "per_rank_ms_per_step_without_exchange": solo_ms,
                        "cache": "per-step working set ~12 GB of activations >> 126 MB L2",
                        "graph_nodes": int(nodes), "loss": scal[0]},
             "e2e": {"value": e2e_value, "unit": "molecules/s", "h2d_bytes_per_step": int(ids_host.numel()),
@@ -545,6 +605,23 @@ def run_ours(args):
             line["roofline"] = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                                 "frac": achieved / peak, "traffic": None, "peak_source": peak_src + " bf16_tflops_sustained",
                                 "scope": whole["scope"], "kernel_timing_error": rec_err}
+        if world == 1 and rec and rec["bwd"][1] > 0:
+            try:
+                # what actually bounds the sweeps: bytes moved between L2 and the SMs per launch (streamed operand
+                # re-read by the unit slices + saved gates + dX / gi in, dG / hs / saved gates out) against the measured fabric rate
+                Bp, Hp = -(-B // 256) * 256, -(-H // 64) * 64
+                slab = Bp * Hp * 2.0
+                bwd_bytes = T * (4 * 3 * slab + 5 * slab + slab + 4 * slab)          # 4 unit-slice clusters x dgh, sv, dX, dG
+                fwd_bytes = T * (8 * slab + 3 * slab + 5 * slab + slab)              # 8 unit slices x h, gi, sv, hs
+                l2 = l2_fabric_probe()
+                l2["bwd_sweep"] = {"l2_bytes_per_launch": bwd_bytes, "achieved_gbs": bwd_bytes / (rec["bwd"][0] * 1e-3) * 1e-9}
+                l2["fwd_sweep"] = {"l2_bytes_per_launch": fwd_bytes, "achieved_gbs": fwd_bytes / (rec["fwd"][0] * 1e-3) * 1e-9}
+                for k in ("bwd_sweep", "fwd_sweep"):
+                    l2[k]["frac_of_copy_probe"] = l2[k]["achieved_gbs"] / l2["copy_gbs"]
+                    l2[k]["frac_of_read_probe"] = l2[k]["achieved_gbs"] / l2["read_gbs"]
+                line["roofline"]["l2_fabric"] = l2
+            except Exception as ex:
+                line["roofline"]["l2_fabric_error"] = repr(ex)
         if world == 1:
             try:
                 line["roofline"]["kernels"] = kernel_rooflines(B, peaks)
@@ -564,7 +641,16 @@ def run_ours(args):
             line["moses_step_unidirectional"] = moses_uni
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # CUDA graphs that hold captured NCCL kernels must be gone before the communicator is torn down; the tear-down itself
+        # (ncclCommDestroy behind destroy_process_group) was seen to hang after such graphs on this image, so every rank leaves
+        # through a final barrier + _exit once its line is out (exit status 0, nothing left to flush)
+        graphed = None
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():

@@ -347,6 +347,11 @@ int mvae_sgemm_tc(const float* A, long long sam, long long sak, const float* B, 
                   long long ldc, int M, int N, int K, const float* bias, int act, int accumulate, void* scratch,
                   size_t scratch_bytes, int* err_flag, mvae_stream_t stream);
 size_t mvae_sgemm_tc_scratch_bytes(long long rows_max, long long cols_max);
+/* L2 <-> SM fabric probe (the roofline denominator bench.py reports for the persistent recurrence sweeps): `ctas` blocks of
+ * 512 threads stream `buf` (`bytes`, keep it well inside the L2: 32 MiB) `passes` times with 16-byte L1-bypassing accesses.
+ * mode 0: read only (bytes * passes move L2 -> SM); mode 1: the first half is copied onto the second (bytes/2 * passes read
+ * plus the same written).  The caller times the launch with CUDA events.                                                  */
+int mvae_l2_probe(void* buf, size_t bytes, int passes, int mode, int ctas, mvae_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -109,6 +109,7 @@ def _load():
         "mvae_sgemm": (i32, [vp, ll, ll, vp, ll, ll, vp, ll, i32, i32, i32, vp, i32, i32, i32, vp]),
         "mvae_sgemm_tc": (i32, [vp, ll, ll, vp, ll, ll, vp, ll, i32, i32, i32, vp, i32, i32, vp, ctypes.c_size_t, vp, vp]),
         "mvae_sgemm_tc_scratch_bytes": (ctypes.c_size_t, [ll, ll]),
+        "mvae_l2_probe": (i32, [vp, ctypes.c_size_t, i32, i32, i32, vp]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(lib, name)  # AttributeError here == header and library out of sync
@@ -124,7 +125,7 @@ EXPORTED = [
     "mvae_cfgb_workspace_bytes", "mvae_cfgb_elbo_step", "mvae_cfgb_elbo_step_graph_create", "mvae_cfgb_elbo_step_phase",
     "mvae_cfgb_elbo_step_phase_graph_create", "mvae_graph_launch",
     "mvae_graph_num_kernel_nodes", "mvae_graph_destroy", "mvae_cfgb_forward", "mvae_cfgb_backward",
-    "mvae_cfgb_decode_greedy", "mvae_onehot_to_ids", "mvae_cfgb_read_error", "mvae_gemm_bf16", "mvae_sgemm", "mvae_sgemm_tc", "mvae_sgemm_tc_scratch_bytes",
+    "mvae_cfgb_decode_greedy", "mvae_onehot_to_ids", "mvae_cfgb_read_error", "mvae_gemm_bf16", "mvae_sgemm", "mvae_sgemm_tc", "mvae_sgemm_tc_scratch_bytes", "mvae_l2_probe",
     "mvae_clip_grad_norm", "mvae_adam_step", "mvae_sgd_momentum_step",
     "mvae_cfga_workspace_bytes", "mvae_cfga_elbo_step", "mvae_cfga_elbo_step_graph_create", "mvae_cfga_forward",
     "mvae_cfga_backward", "mvae_cfga_decode", "mvae_cfga_read_error",

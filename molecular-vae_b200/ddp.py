@@ -78,6 +78,35 @@ class PhasedAllReduce:
             self.flat.div_(self.world)
 
 
+class GraphedDataParallelStep:
+    """The whole data-parallel step as ONE CUDA graph: the phases of the fused step and, forked off after each phase, the
+    all-reduce (NCCL AVG, captured on NCCL's stream) of the gradient bucket that phase finalised; the branches join at the end.
+    One graph launch per step -- no host work between the phases, no separate division pass.  `run_phase(p)` must enqueue
+    phase p on the current stream over FIXED buffers (e.g. CfgBEngine.elbo_step_phase)."""
+
+    def __init__(self, run_phase, n_phases, flat, buckets, group=None, warmup=True):
+        self.reducer = PhasedAllReduce(flat, buckets, group)
+        self.n_phases = n_phases
+        if warmup:                       # outside capture: lazy allocations, opt-in shared memory, NCCL communicator set-up
+            for p in range(n_phases):
+                run_phase(p)
+                self.reducer.after_phase(p)
+            self.reducer.finish()
+        torch.cuda.synchronize()
+        from ._lib import lib
+        n0 = lib.mvae_launch_count()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            for p in range(n_phases):
+                run_phase(p)
+                self.reducer.after_phase(p)
+            self.reducer.finish()
+        self.launches_per_step = int(lib.mvae_launch_count() - n0)   # this library's kernels / memsets inside the graph
+
+    def step(self):
+        self.graph.replay()
+
+
 def shard_rows(n_rows, rank, world):
     """Rows [lo, hi) of a global batch owned by `rank` (equal shards, remainder to the low ranks)."""
     base, rem = divmod(n_rows, world)
@@ -140,7 +169,7 @@ class MosesPhasedStep:
     binding_weight * N B_r / B (moses_rank_weights) and the exchange averages."""
 
     def __init__(self, model, x, eps, kl_weight=1.0, recon_weight=1.0, binding=None, binding_weight=1.0, dropout=None,
-                 group=None):
+                 group=None, single_graph=True):
         self.model, self.group = model, group
         _, self.ids, self.lens = model._pack(x)
         dev = self.ids.device
@@ -167,8 +196,13 @@ class MosesPhasedStep:
             self.joint = (head, self.target, binding_weight * ks, [named[k].grad for k in head_keys])
         self.reducer = PhasedAllReduce(self.gbuf.flat, self.buckets, group)
         self.graphs = []
+        self.single = None
         self._run_phase(-1)                      # warm-up outside capture: workspaces, scratch, opt-in shared memory
         torch.cuda.synchronize()
+        if single_graph:
+            # one graph for the whole step: phases + the bucket all-reduces as forked branches (GraphedDataParallelStep)
+            self.single = GraphedDataParallelStep(self._run_phase, L, self.gbuf.flat, self.buckets, group, warmup=self.reducer.world > 1)
+            return
         for p in range(L):
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
@@ -180,6 +214,9 @@ class MosesPhasedStep:
                         dropout=self.dropout, phase=p, joint=self.joint)
 
     def step(self):
+        if self.single is not None:
+            self.single.step()
+            return self.model._last_scalars
         for p, g in enumerate(self.graphs):
             g.replay()
             self.reducer.after_phase(p)

@@ -137,6 +137,16 @@ class CfgBEngine:
         self._phase_keep = (params, grads, ids, eps)
         return [lib.mvae_graph_num_kernel_nodes(h) for h in self._phase_graphs]
 
+    def elbo_step_phase(self, params, grads, ids, eps, phase):
+        """One phase of the fused step as a direct launch on the current stream (mvae_cfgb_elbo_step_phase): used inside a
+        torch.cuda.graph capture that also holds the gradient all-reduces (ddp.GraphedDataParallelStep)."""
+        P, G = _ptr_table(params), _ptr_table(grads)
+        self.generation += 1
+        with torch.cuda.device(self.device):
+            check(lib.mvae_cfgb_elbo_step_phase(ctypes.byref(self.desc), P, G, _p(ids), _p(eps), _p(self.scalars), _p(None),
+                                                _p(None), self._ws_ptr, self.ws_bytes, int(phase), _stream()))
+        return self.scalars
+
     def launch_phase(self, phase):
         self.generation += 1
         with torch.cuda.device(self.device):
