@@ -592,7 +592,7 @@ def run_ours(args):
             line["roofline"] = {
                 "bound": "tensor", "kernel": "gru_rec2_kernel<BWD> (persistent BPTT sweep of one GRU layer, T steps per launch)",
                 "achieved": a, "peak": peak, "unit": "TFLOP/s", "frac": a / peak,
-                "traffic": ncu_traffic(os.path.join(ROOT, "profiles", "r01_rec2_ncu_full.txt"), "gru_rec2_kernel<1"),
+                "traffic": ncu_traffic(os.path.join(ROOT, "profiles", "r02_rec2_ncu_full.txt"), "gru_rec2_kernel<1"),
                 "peak_source": peak_src + " bf16_tflops_sustained (kernel timed inside back-to-back steps)",
                 "flops_per_launch": flops_launch, "launch_ms": bwd_ms, "launches_timed": rec["bwd"][1],
                 "share_of_step": CFG["layers"] * bwd_ms / step_ms,

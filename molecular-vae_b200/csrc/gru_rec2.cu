@@ -69,8 +69,26 @@ constexpr int CTRL_REGS = 32, EPI_REGS = 112;   // (96 - 32) * 128 released >= (
 #ifndef MVAE_NST_BWD
 #define MVAE_NST_BWD 3
 #endif
+//   MVAE_XCHG_ASYNC 1 (K-split BPTT): the partial sums cross to the partner CTA with st.async (the store itself reports its
+//     bytes to the partner's mbarrier, complete_tx), so the sending warp needs no release fence -- ncu's stall sampling put
+//     21 % of the epilogue warps' time into the MEMBAR + ERRBAR of the two mbarrier.arrive.release.cluster per tile-step
+//     (profiles/r02_rec2_stalls.txt).  The receiving warp arms its own barrier (arrive.expect_tx) and hands the buffer back
+//     with a relaxed remote arrive that is data-dependent on the values it read.  0: st.shared::cluster + release arrives.
+//     Measured (B200, B=4096, T=120): K-split BPTT 17.47 -> 16.45 us/step, results identical (tools/rec_test 32).
+#ifndef MVAE_XCHG_ASYNC
+#define MVAE_XCHG_ASYNC 1
+#endif
 constexpr int SV_NARR = MVAE_SV_HP ? 5 : 4;
-constexpr int SV_STAGE_BYTES = 2048;      // per epilogue warp: two arrays per bulk store
+//   MVAE_SV_STAGE2 1 (forward, with MVAE_SV_BULK): two 2 KB staging buffers per epilogue warp, one per bulk store ([r | z] and
+//     [n | W_hn h]), and the h_{t-1} copy goes out as a plain store right after the accumulators have been read -- no
+//     cp.async.bulk.wait_group.read between the stores of one tile-step (ncu stall sampling: 14 % of all warp samples of the
+//     forward sweep sat in those waits: the bulk engine takes ~1 us to report that it has read its source)
+//     Measured (B200, B=4096, T=120): forward 10.12 -> 11.60 us/step -- the LSU store of the fifth array costs more than the
+//     two waits it removes (the same per-SM outstanding-store throttling that made MVAE_SV_BULK pay), so it stays off.
+#ifndef MVAE_SV_STAGE2
+#define MVAE_SV_STAGE2 0
+#endif
+constexpr int SV_STAGE_BYTES = MVAE_SV_STAGE2 ? 4096 : 2048;      // per epilogue warp: two arrays per bulk store
 
 __device__ __forceinline__ void bulk_s2g(void* gdst, const void* ssrc, uint32_t bytes) {
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(gdst), "r"(ptx::smem_u32(ssrc)), "r"(bytes)
@@ -192,6 +210,18 @@ __device__ __forceinline__ void st_cluster_f32(uint32_t cluster_addr, uint32_t v
 }
 __device__ __forceinline__ void st_cluster_v4(uint32_t cluster_addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(cluster_addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+// asynchronous remote store: 4 bytes into the partner CTA's shared memory, reported (complete_tx) to an mbarrier of that CTA
+__device__ __forceinline__ void st_async_b32(uint32_t cluster_addr, uint32_t v, uint32_t cluster_bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(cluster_addr), "r"(v),
+               "r"(cluster_bar)
+               : "memory");
+}
+// relaxed remote arrive that cannot be issued before `dep` has been computed (orders the loads feeding `dep` in front of it)
+__device__ __forceinline__ void remote_arrive_relaxed_dep(uint32_t cluster_addr, uint32_t dep) {
+  asm volatile("{\n\t.reg .b32 t;\n\tand.b32 t, %1, 0;\n\tadd.u32 t, t, %0;\n\t"
+               "mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [t];\n\t}" ::"r"(cluster_addr), "r"(dep)
+               : "memory");
 }
 // wait on a LOCAL mbarrier whose arrivals come from another CTA of the cluster (release.cluster): acquire at cluster scope
 __device__ __forceinline__ bool wait_bar_cluster(uint64_t* bar, uint32_t parity, int* err_flag) {
@@ -505,7 +535,6 @@ gru_rec2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
           const int ls = step - F_STEP(i);
           if (ls < 0 || step >= E_STEP(i)) continue;
           if (!wait_bar(&epi_bar[i], (uint32_t)(ls & 1), p.err_flag)) goto done;
-          remote_arrive(tempty_remote + (uint32_t)(i * 8));    // accumulator i drained in this CTA -> pair leader
           const bool tr = p.trace && blockIdx.x == 0 && blockIdx.y == 0;
           if (tr) p.trace[((size_t)step * NTILES + i) * 12 + 6] = gtime();
           // The release of the red is cumulative over the epilogue threads' stores this thread observed through the
@@ -517,6 +546,10 @@ gru_rec2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
           }
           red_release_add(p.counters + tile * 2 + parity, 1u);
           if (tr) p.trace[((size_t)step * NTILES + i) * 12 + 7] = gtime();
+          // accumulator i drained in this CTA -> pair leader.  After the publication: the other pairs' next step waits for the
+          // counter, while the leader's MMA into this accumulator is a whole tile-stream away (the release fence of this arrive
+          // cost the chain ~0.8 us per tile-step when it came first)
+          remote_arrive(tempty_remote + (uint32_t)(i * 8));
         }
     }
   }
@@ -685,6 +718,51 @@ gru_rec2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
               // engine has READ it; the global writes themselves complete asynchronously, off the LSU path
               // (lane 1 issues them: bulk groups are per thread, and lane 0's wait for the h' store must not wait for these)
               uint8_t* stg = sStage + (warp - CTRL_WARPS) * SV_STAGE_BYTES;
+#if MVAE_SV_STAGE2 == 2
+              // two staging buffers, three bulk stores: [r | z] from A, [n | W_hn h] from B, h_{t-1} from A again -- the only
+              // wait inside a tile-step is for the oldest store (A), issued two stagings earlier
+              if (lane == 1) bulk_wait_read0();
+              __syncwarp();
+              sts2x128(stg, lane, gr);
+              sts2x128(stg + 1024, lane, gz);
+              ptx::fence_proxy_async_smem();
+              __syncwarp();
+              if (lane == 1) { bulk_s2g(svw, stg, 2048); bulk_commit(); }
+#pragma unroll
+              for (int k = 0; k < 16; ++k) h[k] = __uint_as_float(an[k]);
+              sts2x128(stg + 2048, lane, gn);
+              sts2x128(stg + 3072, lane, h);
+              ptx::fence_proxy_async_smem();
+              __syncwarp();
+              if (lane == 1) { bulk_s2g(svw + 2 * 512, stg + 2048, 2048); bulk_commit(); }
+              if (MVAE_SV_HP) {
+                if (lane == 1) asm volatile("cp.async.bulk.wait_group.read 1;\n" ::: "memory");   // A's store has read its source
+                __syncwarp();
+#pragma unroll
+                for (int k = 0; k < 16; ++k) h[k] = __uint_as_float(hm[k]);
+                sts2x128(stg, lane, h);
+                ptx::fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 1) { bulk_s2g(svw + 4 * 512, stg, 1024); bulk_commit(); }
+              }
+#elif MVAE_SV_STAGE2
+              if (lane == 1) bulk_wait_read0();          // the previous tile-step's two stores have read their buffers
+              __syncwarp();
+              sts2x128(stg, lane, gr);
+              sts2x128(stg + 1024, lane, gz);
+#pragma unroll
+              for (int k = 0; k < 16; ++k) h[k] = __uint_as_float(an[k]);
+              sts2x128(stg + 2048, lane, gn);
+              sts2x128(stg + 3072, lane, h);
+              ptx::fence_proxy_async_smem();
+              __syncwarp();
+              if (lane == 1) { bulk_s2g(svw, stg, 4096); bulk_commit(); }
+              if (MVAE_SV_HP) {
+#pragma unroll
+                for (int k = 0; k < 16; ++k) h[k] = __uint_as_float(hm[k]);
+                stg2x128(svp + 4 * 512, h);               // h_{t-1}: 1 KB per warp straight through the LSU
+              }
+#else
               if (lane == 1) bulk_wait_read0();
               __syncwarp();
               sts2x128(stg, lane, gr);
@@ -710,6 +788,7 @@ gru_rec2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
                 __syncwarp();
                 if (lane == 1) { bulk_s2g(svw + 4 * 512, stg, 1024); bulk_commit(); }
               }
+#endif
             } else {
               stg2x128(svp, gr);
               stg2x128(svp + 512, gz);
@@ -745,16 +824,38 @@ gru_rec2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
               const uint32_t xrem = mapa(xloc, partner);
               const int xw = warp - CTRL_WARPS;                                          // this warp's exchange slot
               if (ev > 0) (void)wait_bar_cluster(&xfree_bar[xw], (ev - 1) & 1u, p.err_flag);   // partner warp read exchange ev-1
+              const float* xin = xbuf + (size_t)uc * 128 + q * 32 + lane;
+#if MVAE_XCHG_ASYNC
+              // arm our own barrier for the 2 KB the partner warp sends (bytes that land before this only drive the tx-count
+              // negative), then fire the stores: no fence, no arrive on the sending side
+              if (lane == 0) ptx::mbar_arrive_expect_tx(&xfull_bar[xw], 16u * 32u * 4u);
+              {
+                const uint32_t xbar_rem = mapa(ptx::smem_u32(&xfull_bar[xw]), partner);
+#pragma unroll
+                for (int k = 0; k < 16; ++k) st_async_b32(xrem + (uint32_t)k * 512u, oth[k], xbar_rem);
+              }
+              (void)wait_bar_cluster(&xfull_bar[xw], ev & 1u, p.err_flag);
+              uint32_t seen = 0u;
+#pragma unroll
+              for (int k = 0; k < 16; ++k) {
+                const float xv = xin[k * 128];
+                seen |= __float_as_uint(xv);
+                acc[k] = __float_as_uint(__uint_as_float(acc[k]) + xv);
+              }
+              // every lane's reads are complete once the warp-wide OR of what they returned exists
+              seen = __reduce_or_sync(0xffffffffu, seen);
+              if (lane == 0) remote_arrive_relaxed_dep(mapa(ptx::smem_u32(&xfree_bar[xw]), partner), seen);
+#else
 #pragma unroll
               for (int k = 0; k < 16; ++k) st_cluster_f32(xrem + (uint32_t)k * 512u, oth[k]);
               __syncwarp();
               if (lane == 0) remote_arrive(mapa(ptx::smem_u32(&xfull_bar[xw]), partner));   // release.cluster
               (void)wait_bar_cluster(&xfull_bar[xw], ev & 1u, p.err_flag);
-              const float* xin = xbuf + (size_t)uc * 128 + q * 32 + lane;
 #pragma unroll
               for (int k = 0; k < 16; ++k) acc[k] = __float_as_uint(__uint_as_float(acc[k]) + xin[k * 128]);
               __syncwarp();
               if (lane == 0) remote_arrive(mapa(ptx::smem_u32(&xfree_bar[xw]), partner));
+#endif
             } else {
               ptx::tmem_ld_32x16(tmem_base + lane_off + i * NB + uc, acc);
               ptx::tmem_ld_32x16(master_addr, cm);

@@ -344,3 +344,32 @@ def test_phased_step_equals_fused_step():
         assert float(err) < 2e-3, (ph, float(err))          # split-K atomics reorder fp32 sums between runs
     eng.check_device_error()
     assert abs(float(eng.scalars[0]) - float(sc_ref[0])) <= 1e-5 * abs(float(sc_ref[0]))
+
+
+def test_graphed_data_parallel_step_replays_the_fused_step():
+    """ddp.GraphedDataParallelStep (one CUDA graph: the phases and, in a process group, the bucket all-reduces forked off after
+    each of them) at world size 1: a replay over poisoned gradients reproduces the fused step, and reports the launches it holds."""
+    m = load_pkg()
+    B, Z, H, L = 300, 292, 501, 3
+    P, ids, onehot, eps = make_case(43, 44, B, Z, H, L)
+    model = build_model(m, P, Z, H, L, "bf16")
+    params = model.ordered_params()
+    gbuf = m.ddp.FlatGradBuffer(params)
+    ids_d, eps_d = torch.from_numpy(ids).cuda(), torch.from_numpy(eps).cuda()
+    eng = model.engine(B, max_len=120)
+    eng.set_train(True)
+    P_, G_ = [p.data for p in params], gbuf.grads()
+    sc_ref = eng.elbo_step(P_, G_, ids_d, eps_d).clone()
+    torch.cuda.synchronize()
+    ref = gbuf.flat.clone()
+    buckets = m.ddp.phase_buckets(m.param_order(L), [p.numel() for p in params], L)
+    step = m.ddp.GraphedDataParallelStep(lambda ph: eng.elbo_step_phase(P_, G_, ids_d, eps_d, ph), L, gbuf.flat, buckets)
+    assert step.launches_per_step > 50
+    for _ in range(2):
+        gbuf.flat.fill_(float("nan"))
+        step.step()
+        torch.cuda.synchronize()
+        assert torch.isfinite(gbuf.flat).all()
+        assert float((gbuf.flat - ref).norm() / ref.norm()) < 2e-3
+    eng.check_device_error()
+    assert abs(float(eng.scalars[0]) - float(sc_ref[0])) <= 1e-5 * abs(float(sc_ref[0]))

@@ -576,7 +576,7 @@ def test_moses_phased_step_equals_fused_step(with_head):
     torch.cuda.synchronize()
     want = {k: p.grad.detach().clone() for k, p in model.named_parameters() if p.grad is not None}
     sc_ref = model._last_scalars.clone()
-    step = m.ddp.MosesPhasedStep(model, x, epst, kl_weight=klw, binding=tgt, binding_weight=1.5)
+    step = m.ddp.MosesPhasedStep(model, x, epst, kl_weight=klw, binding=tgt, binding_weight=1.5, single_graph=False)
     assert len(step.graphs) == 3 and step.buckets[0][0] == 0 and step.buckets[-1][1] == step.gbuf.flat.numel()
     step.gbuf.flat.fill_(float("nan"))
     for p, g in enumerate(step.graphs):
@@ -592,6 +592,19 @@ def test_moses_phased_step_equals_fused_step(with_head):
         err = float((named[k].grad - w_).norm() / (w_.norm() + 1e-30))
         assert err < 2e-3, (k, err)                           # split-K atomics reorder fp32 sums between runs
     assert abs(float(model._last_scalars[0]) - float(sc_ref[0])) <= 1e-5 * abs(float(sc_ref[0]))
+    # default form: all phases (and, in a process group, the bucket all-reduces) in ONE CUDA graph
+    one = m.ddp.MosesPhasedStep(model, x, epst, kl_weight=klw, binding=tgt, binding_weight=1.5)
+    assert one.single is not None and not one.graphs
+    one.gbuf.flat.fill_(float("nan"))
+    one.step()
+    torch.cuda.synchronize()
+    model.check_device_error()
+    named = dict(model.named_parameters())
+    for k, w_ in want.items():
+        if not with_head and k.startswith("binding_model."):
+            continue
+        err = float((named[k].grad - w_).norm() / (w_.norm() + 1e-30))
+        assert err < 2e-3, (k, err)
 
 
 def test_sample_many_pipelined_strings_equal_batchwise_sample():
