@@ -510,6 +510,11 @@ def run_ours(args):
     per_rank = -(-args.samples // world)
     try:
         sampling = sampling_rate(n_total=per_rank)
+        if world == 1:
+            # the same decode at a batch that fills whole waves of the 148 SMs: 9472 = 74 x 128 rows -> 592 = 4 x 148 work units
+            # per cell GEMM (hugesample.py's 8192 gives 512 units = 3.46 waves)
+            wa = sampling_rate(batch=9472, n_total=0)
+            sampling["wave_aligned_batch"] = {k: wa[k] for k in ("value", "unit", "ms_per_batch", "batch", "mean_len")}
     except Exception as ex:
         sampling = {"error": repr(ex)}
     if world > 1:   # every rank takes part in the reduction, whether or not its own measurement succeeded
