@@ -306,6 +306,44 @@ def moses_step_rate(batch=4096, reps=5, variant="mosesfile+head", rank=0, world=
     return out
 
 
+def cfga_step_rate(batch=4096, reps=3):
+    """Side measurement: the model train.py / train_distributed.py instantiate as shipped (models.py MolecularVAE, "Config A":
+    Embedding + LSTM 3x72 + 3 x ConvSELU(k18) encoder, LSTM 4x1024 decoder, 32.3 M parameters) -- fused fwd + loss + bwd step,
+    bf16, CUDA-graph replay over resident inputs, CUDA events.  21.39 GFLOP per molecule."""
+    import numpy as np
+    import torch
+    import molecular_vae_b200 as m
+    from oracle import vae_oracle as vo
+    torch.manual_seed(42)
+    model = m.models.MolecularVAE(precision="bf16").cuda()
+    ids, _, eps = vo.make_batch(1, batch)
+    ids, eps = torch.from_numpy(ids).cuda(), torch.from_numpy(eps).cuda()
+    out = model.elbo_step(ids, eps, max_len=120)
+    torch.cuda.synchronize()
+    eng = model.engine(batch)
+    eng.check_device_error()
+    nodes = int(m._lib.lib.mvae_graph_num_kernel_nodes(eng._graph))
+    eng.launch_graph()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        eng.launch_graph()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    res = {"metric": "train molecules/sec (fwd+bwd ELBO, models.py as shipped)", "value": batch / ms * 1e3, "unit": "molecules/s",
+           "ms_per_step": ms, "batch": batch, "graph_nodes": nodes, "loss": float(out[0].item()),
+           "tflops_algorithmic": batch / ms * 1e3 * 21.3859e-3,
+           "workload": "models.py MolecularVAE (LSTM 3x72 + 3 conv encoder, LSTM 4x1024 decoder), bf16, batch 4096, per-step tcgen05 GEMMs + fused head"}
+    eng.destroy_graph()
+    del eng
+    model._engines.clear()
+    del model
+    torch.cuda.empty_cache()
+    return res
+
+
 def rec_kernel_times(model, eng, params, ids_dev, eps_dev, steps=3):
     """Average launch duration of the persistent recurrence kernels, CUDA events on the launching stream, measured on
     DIRECT launches of the same fused step right after the timed region (a graph replay cannot carry events)."""
@@ -642,6 +680,11 @@ def run_ours(args):
                 line["gpu_eager_baseline"] = {"error": repr(ex)}
         line["sampling"] = sampling
         line["moses_step"] = moses
+        if world == 1:
+            try:
+                line["cfga_step"] = cfga_step_rate()
+            except Exception as ex:
+                line["cfga_step"] = {"error": repr(ex)}
         if moses_uni is not None:
             line["moses_step_unidirectional"] = moses_uni
         print(json.dumps(line), flush=True)
