@@ -78,6 +78,14 @@ constexpr int CTRL_REGS = 32, EPI_REGS = 112;   // (96 - 32) * 128 released >= (
 #ifndef MVAE_XCHG_ASYNC
 #define MVAE_XCHG_ASYNC 1
 #endif
+//   MVAE_XBUF_STAGE 1 (K-split BPTT with MVAE_OUT_TMA and MVAE_XCHG_ASYNC): once a warp has read the partner's partial sums, its
+//     2 KB slot of the exchange buffer doubles as the staging area of two of the three dgh blocks; the slot is handed back to
+//     the partner (xfree) only after those TMA stores have completed, and the slots are contiguous 2 KB blocks per warp.
+//     Measured (B200, B=4096, T=120, us/step): 16.16 -> 15.08 at 3 operand stages; the 32 KB of dG staging it frees would
+//     allow 5 stages, which are slower again (4: 15.58, 5: 15.55, 2: 16.83) -- 3 stays.
+#ifndef MVAE_XBUF_STAGE
+#define MVAE_XBUF_STAGE 1
+#endif
 constexpr int SV_NARR = MVAE_SV_HP ? 5 : 4;
 //   MVAE_SV_STAGE2 1 (forward, with MVAE_SV_BULK): two 2 KB staging buffers per epilogue warp, one per bulk store ([r | z] and
 //     [n | W_hn h]), and the h_{t-1} copy goes out as a plain store right after the accumulators have been read -- no
@@ -309,7 +317,8 @@ gru_rec2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
   // row-major outputs through TMA tensor stores: BPTT only (measured: BPTT 17.91 -> 17.55 us/step, forward 10.22 -> 10.62,
   // where the single h' block per warp does not pay for the completion wait)
   constexpr bool OTMA = BWD && MVAE_OUT_TMA != 0;
-  constexpr int OUT_BYTES = OTMA ? EPI_WARPS * (BWD ? 3 : 1) * 1024 : 0;
+  constexpr bool XST = KS && OTMA && MVAE_XCHG_ASYNC != 0 && MVAE_XBUF_STAGE != 0;   // dgh staging inside the exchange slots
+  constexpr int OUT_BYTES = OTMA ? EPI_WARPS * (BWD ? (XST ? 1 : 3) : 1) * 1024 : 0;
   uint8_t* sStage = sA + nst * A_STAGE + (KS ? XBUF : 0) + tbl_bytes;
   uint8_t* sOut = sStage + STG_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sOut + OUT_BYTES);
@@ -561,6 +570,7 @@ gru_rec2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
     const int uc = part * 16;
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     uint32_t nx = 0;   // KS: exchanges this warp has done so far (the partner warp runs the same tile / step sequence)
+    uint32_t nts = 0;  // XST: tile-steps this warp has finished (every one of them ends with an xfree arrive)
     int lastv_a = -1, lastv_b = -1;   // IN == 2: step after which this thread's row of slot a / b hands its state to hlast
     if constexpr (!BWD && (IN == 2 || (IN == 0 && VL))) {   // IN 0 + packed sequences: embedding layer with a materialised projection
       if (p.hlast)
@@ -805,6 +815,7 @@ gru_rec2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
           }
         } else {
           uint32_t acc[16], cm[16];
+          uint32_t xdep = 0u;   // XST: what the xfree arrive of this tile-step is made data-dependent on
           if (ls > 0) {
             if (KS) {
               // this pair contracted over ONE half of K for all 128 units of the cluster: hand the partial sums of the 64
@@ -820,11 +831,18 @@ gru_rec2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
               // xbuf[unit][row]: a warp store covers 32 consecutive rows of one unit (128 contiguous bytes = one DSMEM
               // transaction).  (A [row][unit] layout with 128-bit stores -- 4 instructions instead of 16, but 32 separate
               // 16-byte remote transactions per instruction -- was measured slower: push 1.5 -> 2.4 us, sweep 17.55 -> 18.9 us/step.)
-              const uint32_t xloc = ptx::smem_u32(xbuf + (size_t)uc * 128 + q * 32 + lane);
-              const uint32_t xrem = mapa(xloc, partner);
               const int xw = warp - CTRL_WARPS;                                          // this warp's exchange slot
-              if (ev > 0) (void)wait_bar_cluster(&xfree_bar[xw], (ev - 1) & 1u, p.err_flag);   // partner warp read exchange ev-1
-              const float* xin = xbuf + (size_t)uc * 128 + q * 32 + lane;
+              // XST: the slot is one contiguous 2 KB block per warp, [unit][lane] (it doubles as TMA-store staging below)
+              const float* xin = XST ? xbuf + (size_t)xw * 512 + lane : xbuf + (size_t)uc * 128 + q * 32 + lane;
+              constexpr uint32_t XSTRIDE = XST ? 128u : 512u;                            // bytes between units in a slot
+              constexpr int XIN_STRIDE = XST ? 32 : 128;
+              const uint32_t xloc = ptx::smem_u32(xin);
+              const uint32_t xrem = mapa(xloc, partner);
+              if constexpr (XST) {
+                if (nts > 0) (void)wait_bar_cluster(&xfree_bar[xw], (nts - 1) & 1u, p.err_flag);   // partner's previous tile-step left its slot
+              } else {
+                if (ev > 0) (void)wait_bar_cluster(&xfree_bar[xw], (ev - 1) & 1u, p.err_flag);     // partner warp read exchange ev-1
+              }
 #if MVAE_XCHG_ASYNC
               // arm our own barrier for the 2 KB the partner warp sends (bytes that land before this only drive the tx-count
               // negative), then fire the stores: no fence, no arrive on the sending side
@@ -832,19 +850,23 @@ gru_rec2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
               {
                 const uint32_t xbar_rem = mapa(ptx::smem_u32(&xfull_bar[xw]), partner);
 #pragma unroll
-                for (int k = 0; k < 16; ++k) st_async_b32(xrem + (uint32_t)k * 512u, oth[k], xbar_rem);
+                for (int k = 0; k < 16; ++k) st_async_b32(xrem + (uint32_t)k * XSTRIDE, oth[k], xbar_rem);
               }
               (void)wait_bar_cluster(&xfull_bar[xw], ev & 1u, p.err_flag);
               uint32_t seen = 0u;
 #pragma unroll
               for (int k = 0; k < 16; ++k) {
-                const float xv = xin[k * 128];
+                const float xv = xin[k * XIN_STRIDE];
                 seen |= __float_as_uint(xv);
                 acc[k] = __float_as_uint(__uint_as_float(acc[k]) + xv);
               }
               // every lane's reads are complete once the warp-wide OR of what they returned exists
               seen = __reduce_or_sync(0xffffffffu, seen);
-              if (lane == 0) remote_arrive_relaxed_dep(mapa(ptx::smem_u32(&xfree_bar[xw]), partner), seen);
+              if constexpr (!XST) {
+                if (lane == 0) remote_arrive_relaxed_dep(mapa(ptx::smem_u32(&xfree_bar[xw]), partner), seen);
+              } else {
+                xdep = seen;   // the slot goes back at the end of the tile-step, after it has served as store staging
+              }
 #else
 #pragma unroll
               for (int k = 0; k < 16; ++k) st_cluster_f32(xrem + (uint32_t)k * 512u, oth[k]);
@@ -892,23 +914,27 @@ gru_rec2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
           }
           if (tr && (p.debug & 64)) p.trace[((size_t)step * NTILES + i) * 12 + 9] = gtime();    // gate math done
           __nv_bfloat16* g4 = p.dG + ((long long)t * p.Bp + row) * 4 * p.Hp + u0 + uc;
-          uint8_t* ob = sOut + (warp - CTRL_WARPS) * 3072;
+          // staging blocks of the three dgh stores: own 3 KB, or (XST) this warp's exchange slot for the first two + own 1 KB
+          uint8_t* ob = XST ? sOut + (warp - CTRL_WARPS) * 1024 : sOut + (warp - CTRL_WARPS) * 3072;
+          uint8_t* ob_r = XST ? reinterpret_cast<uint8_t*>(xbuf + (size_t)(warp - CTRL_WARPS) * 512) : ob;
+          uint8_t* ob_z = XST ? ob_r + 1024 : ob + 1024;
+          uint8_t* ob_nr = XST ? ob : ob + 2048;
           if (!nomem) {
             // the three dgh blocks the other pairs stream next step go first; da_n (only read by the later wgrad / dX
             // GEMMs) is stored after this tile has been handed to the publisher
             if constexpr (OTMA) {
               if (lane == 1) bulk_wait_read0();     // the da_n store of the previous tile-step (lane 1's group) has read block 0
               __syncwarp();
-              sts_row32(ob, lane, ghn);
-              sts_row32(ob + 1024, lane, dx);
-              sts_row32(ob + 2048, lane, hp);
+              sts_row32(ob_r, lane, ghn);
+              sts_row32(ob_z, lane, dx);
+              sts_row32(ob_nr, lane, hp);
               ptx::fence_proxy_async_smem();
               __syncwarp();
               if (lane == 0) {
                 const int r0 = (int)(row - lane);
-                tma_store_3d(&tmS, ob, p.Hp + u0 + uc, r0, t);
-                tma_store_3d(&tmS, ob + 1024, 2 * p.Hp + u0 + uc, r0, t);
-                tma_store_3d(&tmS, ob + 2048, 3 * p.Hp + u0 + uc, r0, t);
+                tma_store_3d(&tmS, ob_r, p.Hp + u0 + uc, r0, t);
+                tma_store_3d(&tmS, ob_z, 2 * p.Hp + u0 + uc, r0, t);
+                tma_store_3d(&tmS, ob_nr, 3 * p.Hp + u0 + uc, r0, t);
                 bulk_commit();
                 if (tr && (p.debug & 64)) p.trace[((size_t)step * NTILES + i) * 12 + 10] = gtime();   // stores issued
                 bulk_wait_all0();                   // dgh of this tile-step is in memory: the tile can be published
@@ -919,6 +945,11 @@ gru_rec2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
               stg256(g4 + 2 * p.Hp, dx);
               stg256(g4 + 3 * p.Hp, hp);
             }
+          }
+          if constexpr (XST) {
+            // the exchange slot is free again (its stores completed, or nothing was staged): the partner may push its next sums
+            ++nts;
+            if (lane == 0) remote_arrive_relaxed_dep(mapa(ptx::smem_u32(&xfree_bar[warp - CTRL_WARPS]), rank ^ 2u), xdep);
           }
           tmem_st_wait();
           ptx::tc_fence_before();
@@ -987,7 +1018,7 @@ int launch2(const mvae_gru_rec_args& a, cudaStream_t st) {
   const size_t tbl_bytes = use_tbl ? (((size_t)a.V * 3 * RU * 2 + 1023) & ~(size_t)1023) : 0;
   int nst = BWD ? MVAE_NST_BWD : MVAE_NST_FWD;
   const size_t stg_bytes = ((!BWD && MVAE_SV_BULK) ? (size_t)EPI_WARPS * SV_STAGE_BYTES : 0) +        // saved-gate staging (forward)
-                           ((BWD && MVAE_OUT_TMA) ? (size_t)EPI_WARPS * 3 * 1024 : 0);                  // output staging (BPTT)
+                           ((BWD && MVAE_OUT_TMA) ? (size_t)EPI_WARPS * ((KS && MVAE_XCHG_ASYNC && MVAE_XBUF_STAGE) ? 1 : 3) * 1024 : 0);   // output staging (BPTT)
   const size_t fixed = (size_t)KC * NBH * 128 + (KS ? 128 * RU * 4 : 0) + tbl_bytes + stg_bytes + 1024 + 1024;
   while (nst > 2 && fixed + (size_t)nst * A_STAGE > 232448) --nst;   // the token table takes the room of operand stages
   if (((a.debug >> 16) & 0xF) >= 2 && ((a.debug >> 16) & 0xF) < nst) nst = (a.debug >> 16) & 0xF;   // timing experiment: fewer stages

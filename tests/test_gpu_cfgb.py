@@ -373,3 +373,24 @@ def test_graphed_data_parallel_step_replays_the_fused_step():
         assert float((gbuf.flat - ref).norm() / ref.norm()) < 2e-3
     eng.check_device_error()
     assert abs(float(eng.scalars[0]) - float(sc_ref[0])) <= 1e-5 * abs(float(sc_ref[0]))
+
+
+@pytest.mark.parametrize("B", [200, 1100])
+def test_fused_step_bf16_does_not_depend_on_stale_workspace(B):
+    """compute-sanitizer is closed on this pool, so stale-read bugs are hunted the way the MOSES tests do it: the whole
+    workspace (activations, padded weights, staging, step counters) is filled with 0xFF -- NaN patterns in bf16 and fp32,
+    garbage counters -- between two steps on the same inputs; the second step must reproduce the oracle (and the first)."""
+    m = load_pkg()
+    Z, H, L = 292, 501, 3
+    P, ids, onehot, eps = make_case(71, 72 + B, B, Z, H, L)
+    ref = oracle_step(P, onehot, eps, L)
+    model = build_model(m, P, Z, H, L, "bf16")
+    sc0 = _fused(model, ids, eps, use_graph=False)
+    eng = model.engine(B)
+    eng.ws.fill_(0xFF)
+    for p in model.parameters():
+        p.grad.fill_(float("nan"))
+    sc = _fused(model, ids, eps, use_graph=False)
+    assert np.isfinite(sc).all()
+    _compare(model, sc, ref, BF16_LOSS_RTOL, BF16_GRAD_RTOL, "bf16-poisoned")
+    np.testing.assert_allclose(sc[:3], sc0[:3], rtol=2e-5)
