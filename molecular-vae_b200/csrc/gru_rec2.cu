@@ -83,6 +83,11 @@ constexpr int CTRL_REGS = 32, EPI_REGS = 112;   // (96 - 32) * 128 released >= (
 //     the partner (xfree) only after those TMA stores have completed, and the slots are contiguous 2 KB blocks per warp.
 //     Measured (B200, B=4096, T=120, us/step): 16.16 -> 15.08 at 3 operand stages; the 32 KB of dG staging it frees would
 //     allow 5 stages, which are slower again (4: 15.58, 5: 15.55, 2: 16.83) -- 3 stays.
+//   MVAE_XCHG_V4 1 (with MVAE_XBUF_STAGE): 16-byte st.async per lane (4 per warp and tile-step instead of 16 of 4 bytes).
+//     Measured: 14.75 -> 14.87 us/step, no gain (the exchange sits at the DSMEM rate, 32 KB per CTA and tile-step), so off.
+#ifndef MVAE_XCHG_V4
+#define MVAE_XCHG_V4 0
+#endif
 #ifndef MVAE_XBUF_STAGE
 #define MVAE_XBUF_STAGE 1
 #endif
@@ -223,6 +228,11 @@ __device__ __forceinline__ void st_cluster_v4(uint32_t cluster_addr, uint32_t a,
 __device__ __forceinline__ void st_async_b32(uint32_t cluster_addr, uint32_t v, uint32_t cluster_bar) {
   asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(cluster_addr), "r"(v),
                "r"(cluster_bar)
+               : "memory");
+}
+__device__ __forceinline__ void st_async_v4(uint32_t cluster_addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t cluster_bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(cluster_addr),
+               "r"(a), "r"(b), "r"(c), "r"(d), "r"(cluster_bar)
                : "memory");
 }
 // relaxed remote arrive that cannot be issued before `dep` has been computed (orders the loads feeding `dep` in front of it)
@@ -850,15 +860,44 @@ gru_rec2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
               {
                 const uint32_t xbar_rem = mapa(ptx::smem_u32(&xfull_bar[xw]), partner);
 #pragma unroll
-                for (int k = 0; k < 16; ++k) st_async_b32(xrem + (uint32_t)k * XSTRIDE, oth[k], xbar_rem);
+#if MVAE_XCHG_V4
+                if constexpr (XST) {
+                  // slot layout [4 unit groups][lane][4 units]: one 16-byte store per lane and group = 512 contiguous bytes per
+                  // warp instruction (4 instead of 16 remote stores)
+                  const uint32_t xr4 = mapa(ptx::smem_u32(xbuf + (size_t)xw * 512 + lane * 4), partner);
+#pragma unroll
+                  for (int g = 0; g < 4; ++g)
+                    st_async_v4(xr4 + (uint32_t)g * 512u, oth[4 * g], oth[4 * g + 1], oth[4 * g + 2], oth[4 * g + 3], xbar_rem);
+                } else
+#endif
+                {
+#pragma unroll
+                  for (int k = 0; k < 16; ++k) st_async_b32(xrem + (uint32_t)k * XSTRIDE, oth[k], xbar_rem);
+                }
               }
               (void)wait_bar_cluster(&xfull_bar[xw], ev & 1u, p.err_flag);
               uint32_t seen = 0u;
+#if MVAE_XCHG_V4
+              if constexpr (XST) {
+                const float4* x4 = reinterpret_cast<const float4*>(xbuf + (size_t)xw * 512 + lane * 4);
 #pragma unroll
-              for (int k = 0; k < 16; ++k) {
-                const float xv = xin[k * XIN_STRIDE];
-                seen |= __float_as_uint(xv);
-                acc[k] = __float_as_uint(__uint_as_float(acc[k]) + xv);
+                for (int g = 0; g < 4; ++g) {
+                  const float4 v = x4[g * 32];
+                  seen |= __float_as_uint(v.x) | __float_as_uint(v.y) | __float_as_uint(v.z) | __float_as_uint(v.w);
+                  acc[4 * g] = __float_as_uint(__uint_as_float(acc[4 * g]) + v.x);
+                  acc[4 * g + 1] = __float_as_uint(__uint_as_float(acc[4 * g + 1]) + v.y);
+                  acc[4 * g + 2] = __float_as_uint(__uint_as_float(acc[4 * g + 2]) + v.z);
+                  acc[4 * g + 3] = __float_as_uint(__uint_as_float(acc[4 * g + 3]) + v.w);
+                }
+              } else
+#endif
+              {
+#pragma unroll
+                for (int k = 0; k < 16; ++k) {
+                  const float xv = xin[k * XIN_STRIDE];
+                  seen |= __float_as_uint(xv);
+                  acc[k] = __float_as_uint(__uint_as_float(acc[k]) + xv);
+                }
               }
               // every lane's reads are complete once the warp-wide OR of what they returned exists
               seen = __reduce_or_sync(0xffffffffu, seen);
