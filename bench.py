@@ -232,7 +232,8 @@ def sampling_rate(batch=8192, max_len=100, reps=3, n_total=0, target_mean_len=45
     ms = e0.elapsed_time(e1) / reps
     out = {"metric": "sampled SMILES/sec (greedy, N(0,I) latents)", "value": batch / ms * 1e3, "unit": "SMILES/s",
            "ms_per_batch": ms, "batch": batch, "max_len": max_len, "mean_len": float(lens.float().mean().item()),
-           "workload": "mosesvae.VAE.sample device path (3x512 GRU decoder, d_z 160, V=34), bf16, random-init weights, <eos> bias calibrated"}
+           "workload": "mosesvae.VAE.sample device path (3x512 GRU decoder, d_z 160, V=34), bf16, random-init weights, <eos> bias calibrated; "
+                       "persistent decode kernel (99 steps x (3 cell GEMMs + head) in one launch)"}
     if n_total > 0:
         for strs in model.sample_many(2 * batch, n_batch=batch, max_len=max_len, greedy=True, seed=1):   # warm
             pass

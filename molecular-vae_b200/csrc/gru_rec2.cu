@@ -218,10 +218,10 @@ __device__ __forceinline__ void tma_load_3d_2sm_mc(void* smem_dst, const CUtenso
       "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_addr), "h"(mask), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
-__device__ __forceinline__ void st_cluster_f32(uint32_t cluster_addr, uint32_t v) {
+[[maybe_unused]] __device__ __forceinline__ void st_cluster_f32(uint32_t cluster_addr, uint32_t v) {
   asm volatile("st.shared::cluster.b32 [%0], %1;" ::"r"(cluster_addr), "r"(v) : "memory");
 }
-__device__ __forceinline__ void st_cluster_v4(uint32_t cluster_addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+[[maybe_unused]] __device__ __forceinline__ void st_cluster_v4(uint32_t cluster_addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(cluster_addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 // asynchronous remote store: 4 bytes into the partner CTA's shared memory, reported (complete_tx) to an mbarrier of that CTA
@@ -230,7 +230,7 @@ __device__ __forceinline__ void st_async_b32(uint32_t cluster_addr, uint32_t v, 
                "r"(cluster_bar)
                : "memory");
 }
-__device__ __forceinline__ void st_async_v4(uint32_t cluster_addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t cluster_bar) {
+[[maybe_unused]] __device__ __forceinline__ void st_async_v4(uint32_t cluster_addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t cluster_bar) {
   asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(cluster_addr),
                "r"(a), "r"(b), "r"(c), "r"(d), "r"(cluster_bar)
                : "memory");
@@ -859,7 +859,6 @@ gru_rec2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
               if (lane == 0) ptx::mbar_arrive_expect_tx(&xfull_bar[xw], 16u * 32u * 4u);
               {
                 const uint32_t xbar_rem = mapa(ptx::smem_u32(&xfull_bar[xw]), partner);
-#pragma unroll
 #if MVAE_XCHG_V4
                 if constexpr (XST) {
                   // slot layout [4 unit groups][lane][4 units]: one 16-byte store per lane and group = 512 contiguous bytes per

@@ -21,6 +21,7 @@
 #include "umma_gemm.h"
 #include "host_common.cuh"
 #include "gru_rec.h"
+#include "decode_persist.h"
 
 namespace {
 
@@ -80,6 +81,7 @@ struct MWS {
   uint8_t* tokTr;   // ids^T with every row reversed inside its own length (reverse encoder direction on the persistent kernel)
   void *WhhT_enc; float *tbl_comb; uint8_t* tokT; void* zproj_rb;   // encoder W_hh^T, table + (b_hr, b_hz, 0), ids^T [T][Bp], zproj RB bf16
   void* tcs; size_t tcs_bytes;   // bf16 mode: converted operands of the bf16x3 tensor-core path of the small fp32 GEMMs
+  unsigned int* dec_scratch;     // persistent decode kernel: completion counters + unit schedule
   size_t total;
 };
 
@@ -142,6 +144,7 @@ void carve(const MDims& d, void* base, MWS* w) {
     w->tcs_bytes = d.bf16 ? mvae_tc_sgemm_scratch_bytes(rmax, cmax) : 0;
     w->tcs = c.take<uint8_t>(w->tcs_bytes);
   }
+  w->dec_scratch = reinterpret_cast<unsigned int*>(c.take<uint8_t>(mvae_decode_persistent_scratch_bytes((int)Bp, d.L)));
   w->total = (c.off + 255) & ~size_t(255);
 }
 
@@ -1239,6 +1242,10 @@ __global__ void sample_l0_operand_kernel(const float* __restrict__ z, int B, int
     buf1[(long long)b * ld + c] = __float2bfloat16_rn(v1);
   }
 }
+bool sample_persistent_enabled() {
+  const char* e = getenv("MVAE_SAMPLE_PERSISTENT");
+  return e ? atoi(e) != 0 : true;
+}
 bool sample_fused_enabled() {
   const char* e = getenv("MVAE_SAMPLE_FUSED");
   return e ? atoi(e) != 0 : true;
@@ -1286,6 +1293,22 @@ int sample_fused(const MDims& d, const MWS& w, const float* const* P, const floa
     sample_l0_operand_kernel<<<grid_for((long long)Bp * (64 + ZP)), 256, 0, st>>>(z, B, Bp, Z, ZP, K0, bos, (TA*)w.xh[0][0], (TA*)w.xh[0][1]); KCHECK();
   }
   sample_init_kernel<<<(unsigned)ceil_div64((long long)B * max_len, 256), 256, 0, st>>>(B, max_len, bos, d.pad, w_cur, ids_out, len_out, done); KCHECK();
+  if (kcat && CP == 64 && L >= 2 && sample_persistent_enabled()) {
+    // the whole decode loop as ONE launch (decode_persist.cu): same GEMM pipeline and epilogues, units of all layers and steps
+    // in one dependency-ordered list; falls through to the per-step launches when the shape is not supported
+    mvae_decode_args da{};
+    da.B = B; da.Bp = Bp; da.Hd = Hd; da.L = L; da.V = V; da.K0 = K0; da.max_len = max_len; da.eos = eos; da.mode = mode;
+    da.inv_temp = 1.0f / temp; da.seed = seed; da.seed_dev = seed_dev;
+    for (int l = 0; l < L; ++l) {
+      da.Wcat[l] = w.Wcat[l]; da.bcat[l] = w.bcat[l];
+      for (int k = 0; k < 2; ++k) { da.xh[l][k] = w.xh[l][k]; da.hm[l][k] = w.hm[l][k]; }
+    }
+    da.Wfc = w.Wfc; da.bfc = w.bfc; da.w_cur = w_cur; da.x = ids_out; da.end = len_out; da.done = done;
+    da.counters = w.dec_scratch; da.sched = w.dec_scratch + (size_t)(L + 1) * (Bp / 128); da.err_flag = w.err_flag;
+    const int rc = mvae_decode_persistent_launch(&da, st);
+    if (rc == MVAE_OK) { mvae_count_launches(3); return MVAE_OK; }
+    if (rc != MVAE_ERR_UNSUPPORTED) return rc;
+  }
   for (int i = 1; i < max_len; ++i) {
     const int cur = i & 1, nxt = cur ^ 1;
     for (int l = 0; l < L; ++l) {

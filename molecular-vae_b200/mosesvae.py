@@ -382,6 +382,7 @@ class VAE(nn.Module):
         mode = 0 if greedy else 1
         if use_graph:
             key = (B, int(max_len), mode, float(temp), self.precision, dev, os.environ.get("MVAE_SAMPLE_FUSED", ""),
+                   os.environ.get("MVAE_SAMPLE_PERSISTENT", ""),
                    tuple(p.data_ptr() for p in params))
             g = getattr(self, "_sample_graph", None)
             if g is None or g["key"] != key:

@@ -364,6 +364,37 @@ def test_moses_sample_fused_cell_gemm_bf16(monkeypatch):
     assert first_tok >= 0.97 and same_oracle >= 0.6 and same_unfused >= 0.6, (first_tok, same_oracle, same_unfused)
 
 
+@pytest.mark.parametrize("B,greedy", [(300, True), (3000, True), (8192, True), (3000, False)])
+def test_moses_sample_persistent_kernel_equals_per_step_launches(monkeypatch, B, greedy):
+    """The persistent decode kernel (decode_persist.cu: all 99 steps x (3 cell GEMMs + head) as one dependency-ordered unit list
+    in ONE launch) against the per-step launches of the same GEMM pipeline (MVAE_SAMPLE_PERSISTENT=0): identical arithmetic, so
+    every token and every length is identical -- greedy and multinomial (same counter-based draws).  B = 300: fewer row tiles
+    than the head lag; 3000 / 8192: 24 / 64 row tiles, units of several layers and steps in flight at once."""
+    m = load_pkg()
+    P = mo.make_moses_params(341, dtype=np.float32)
+    model = m.mosesvae.VAE(_Vocab(), precision="bf16")
+    sd = model.state_dict()
+    with torch.no_grad():
+        for k, v in P.items():
+            sd[k].copy_(torch.from_numpy(v))
+        model.decoder_fc.bias[model.eos] += 1.5          # make <eos> fire at mixed positions
+    model = model.cuda().eval()
+    z = torch.randn(B, 160, generator=torch.Generator().manual_seed(3)).cuda()
+    res = {}
+    for flag in ("1", "0"):
+        monkeypatch.setenv("MVAE_SAMPLE_PERSISTENT", flag)
+        ids, lens, _ = model.sample_ids(B, max_len=100, z=z, greedy=greedy, seed=77, use_graph=False)
+        torch.cuda.synchronize()
+        model.check_device_error()
+        res[flag] = (ids.cpu().numpy().copy(), lens.cpu().numpy().copy())
+    assert (res["1"][1] == res["0"][1]).all()
+    assert (res["1"][0] == res["0"][0]).all()
+    # and through the CUDA graph of the public path
+    monkeypatch.setenv("MVAE_SAMPLE_PERSISTENT", "1")
+    ids_g, lens_g, _ = model.sample_ids(B, max_len=100, z=z, greedy=greedy, seed=77, use_graph=True)
+    assert (ids_g.cpu().numpy() == res["0"][0]).all() and (lens_g.cpu().numpy() == res["0"][1]).all()
+
+
 def test_moses_sample_graph_replay_equals_direct_launch():
     """The decode loop captured into one CUDA graph (mvae_moses_sample_graph_create, seed / z read from device buffers at
     replay time) returns exactly what the direct launch returns, for new latents and new seeds without re-capture."""
