@@ -21,6 +21,7 @@ struct mvae_decode_args {
   unsigned int* counters;    // [(L + 1) * Bp / 128] completion counters, zeroed by the launcher
   unsigned int* sched;       // [(8 L + 1) * Bp / 128] unit order of one step, written by the launcher
   int* err_flag;
+  int variant;               // 2: CTA pairs (tcgen05 cta_group::2, units of 256 rows; Bp % 256 == 0), else one CTA per unit of 128 rows
 };
 
 // workspace the caller must provide for counters + schedule (bytes)

@@ -1242,10 +1242,12 @@ __global__ void sample_l0_operand_kernel(const float* __restrict__ z, int B, int
     buf1[(long long)b * ld + c] = __float2bfloat16_rn(v1);
   }
 }
-bool sample_persistent_enabled() {
+// MVAE_SAMPLE_PERSISTENT: 0 = per-step launches, 1 = persistent kernel with one CTA per unit, 2 (default) = CTA pairs
+int sample_persistent_variant() {
   const char* e = getenv("MVAE_SAMPLE_PERSISTENT");
-  return e ? atoi(e) != 0 : true;
+  return e ? atoi(e) : 2;
 }
+bool sample_persistent_enabled() { return sample_persistent_variant() != 0; }
 bool sample_fused_enabled() {
   const char* e = getenv("MVAE_SAMPLE_FUSED");
   return e ? atoi(e) != 0 : true;
@@ -1305,6 +1307,7 @@ int sample_fused(const MDims& d, const MWS& w, const float* const* P, const floa
     }
     da.Wfc = w.Wfc; da.bfc = w.bfc; da.w_cur = w_cur; da.x = ids_out; da.end = len_out; da.done = done;
     da.counters = w.dec_scratch; da.sched = w.dec_scratch + (size_t)(L + 1) * (Bp / 128); da.err_flag = w.err_flag;
+    da.variant = sample_persistent_variant();
     const int rc = mvae_decode_persistent_launch(&da, st);
     if (rc == MVAE_OK) { mvae_count_launches(3); return MVAE_OK; }
     if (rc != MVAE_ERR_UNSUPPORTED) return rc;

@@ -381,16 +381,17 @@ def test_moses_sample_persistent_kernel_equals_per_step_launches(monkeypatch, B,
     model = model.cuda().eval()
     z = torch.randn(B, 160, generator=torch.Generator().manual_seed(3)).cuda()
     res = {}
-    for flag in ("1", "0"):
+    for flag in ("2", "1", "0"):     # CTA pairs (default) / one CTA per unit / per-step launches
         monkeypatch.setenv("MVAE_SAMPLE_PERSISTENT", flag)
         ids, lens, _ = model.sample_ids(B, max_len=100, z=z, greedy=greedy, seed=77, use_graph=False)
         torch.cuda.synchronize()
         model.check_device_error()
         res[flag] = (ids.cpu().numpy().copy(), lens.cpu().numpy().copy())
-    assert (res["1"][1] == res["0"][1]).all()
-    assert (res["1"][0] == res["0"][0]).all()
+    for flag in ("2", "1"):
+        assert (res[flag][1] == res["0"][1]).all(), flag
+        assert (res[flag][0] == res["0"][0]).all(), flag
     # and through the CUDA graph of the public path
-    monkeypatch.setenv("MVAE_SAMPLE_PERSISTENT", "1")
+    monkeypatch.setenv("MVAE_SAMPLE_PERSISTENT", "2")
     ids_g, lens_g, _ = model.sample_ids(B, max_len=100, z=z, greedy=greedy, seed=77, use_graph=True)
     assert (ids_g.cpu().numpy() == res["0"][0]).all() and (lens_g.cpu().numpy() == res["0"][1]).all()
 
