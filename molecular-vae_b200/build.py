@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmvae_b200.so")
-SOURCES = ["cfgb.cu", "umma_gemm.cu", "gru_rec.cu", "gru_rec2.cu", "optim.cu", "moses.cu", "cfga.cu", "binding.cu", "text.cu", "errors.cu", "probe.cu", "decode_persist.cu"]
+SOURCES = ["cfgb.cu", "umma_gemm.cu", "gru_rec.cu", "gru_rec2.cu", "optim.cu", "moses.cu", "cfga.cu", "binding.cu", "text.cu", "errors.cu", "probe.cu", "decode_persist.cu", "umma_gemm2.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-shared", "--use_fast_math=false" if False else "-Xptxas=-v",

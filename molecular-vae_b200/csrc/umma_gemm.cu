@@ -15,6 +15,7 @@
 //   * split-K work units (fp32 red.add epilogue) give the skinny wgrad GEMMs a full grid.
 #include "common.cuh"
 #include "umma_gemm.h"
+#include <stdlib.h>
 
 namespace {
 
@@ -883,6 +884,14 @@ int mvae_umma_gemm(const mvae_umma_operand* A, const mvae_umma_operand* B, const
     int dev = 0;
     MVAE_CUDA_CHECK(cudaGetDevice(&dev));
     MVAE_CUDA_CHECK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  if (!head && !cell && !sample && !varlen && splits <= 1 && (bn == 0 || bn == 256) && max_ctas == 0) {
+    // plain K-major projection with a bf16 result: CTA pairs (M = 256 tiles, half a B tile per CTA) when the shape allows
+    const char* e = getenv("MVAE_GEMM_PAIRS");
+    if (!e || atoi(e) != 0) {
+      const int rc = mvae_umma_gemm_pairs(A, B, D, M, N, K, err_flag, stream);
+      if (rc != MVAE_ERR_UNSUPPORTED) return rc;
+    }
   }
   if (bn == 0) bn = (N > 128) ? 256 : (N > 64 ? 128 : 64);
   if (bn != 64 && bn != 128 && bn != 192 && bn != 256) return MVAE_ERR_INVALID;

@@ -394,3 +394,35 @@ def test_fused_step_bf16_does_not_depend_on_stale_workspace(B):
     assert np.isfinite(sc).all()
     _compare(model, sc, ref, BF16_LOSS_RTOL, BF16_GRAD_RTOL, "bf16-poisoned")
     np.testing.assert_allclose(sc[:3], sc0[:3], rtol=2e-5)
+
+
+@pytest.mark.parametrize("M,N,K,rb", [(512, 256, 512, 0), (2048, 1536, 512, 1), (4096, 1536, 296, 1), (1024, 512, 1000, 0)])
+def test_gemm_pairs_equals_single_cta_gemm(monkeypatch, M, N, K, rb):
+    """The 2-CTA projection GEMM (umma_gemm2.cu: tcgen05 cta_group::2, 256 x 256 tiles, half a B tile per CTA) against the
+    one-CTA kernel on the same operands -- same k order and fp32 accumulation, so the bf16 results are identical -- and against
+    an fp64 product.  Covers ragged K (TMA zero fill) and both output layouts through the plain row-major check."""
+    import ctypes
+    m = load_pkg()
+    lib, vp = m._lib.lib, ctypes.c_void_p
+    g = torch.Generator(device="cuda").manual_seed(11)
+    Kp = (K + 7) // 8 * 8
+    a = torch.zeros(M, Kp, device="cuda", dtype=torch.bfloat16)
+    b = torch.zeros(N, Kp, device="cuda", dtype=torch.bfloat16)
+    a[:, :K] = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    b[:, :K] = (torch.randn(N, K, device="cuda", generator=g) * 0.05).bfloat16()
+    bias = torch.randn(N, device="cuda", generator=g)
+    err = torch.zeros(1, dtype=torch.int32, device="cuda")
+    outs = {}
+    for flag in ("1", "0"):
+        monkeypatch.setenv("MVAE_GEMM_PAIRS", flag)
+        d = torch.full((M, N), float("nan"), device="cuda", dtype=torch.bfloat16)
+        rc = lib.mvae_gemm_bf16(vp(a.data_ptr()), Kp, 0, vp(b.data_ptr()), Kp, 0, vp(d.data_ptr()), N, 1, 0, vp(bias.data_ptr()), M, N, K,
+                                0, 1, vp(err.data_ptr()), vp(torch.cuda.current_stream().cuda_stream))
+        assert rc == 0
+        torch.cuda.synchronize()
+        assert int(err.item()) == 0
+        outs[flag] = d.float()
+    assert torch.isfinite(outs["1"]).all()
+    assert torch.equal(outs["1"], outs["0"])
+    ref = a[:, :K].double() @ b[:, :K].double().t() + bias.double()
+    assert (outs["1"].double() - ref).abs().max().item() <= 2e-2 * ref.abs().max().item()
