@@ -885,11 +885,12 @@ int mvae_umma_gemm(const mvae_umma_operand* A, const mvae_umma_operand* B, const
     MVAE_CUDA_CHECK(cudaGetDevice(&dev));
     MVAE_CUDA_CHECK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
-  if (!head && !cell && !sample && !varlen && splits <= 1 && (bn == 0 || bn == 256) && max_ctas == 0) {
-    // plain K-major projection with a bf16 result: CTA pairs (M = 256 tiles, half a B tile per CTA) when the shape allows
+  if (!head && !cell && !sample && !varlen && (bn == 0 || bn == 256) && max_ctas == 0) {
+    // CTA pairs (256 x 256 tiles, half a B tile per CTA) when the shape allows: projections with a bf16 result, dX, and the
+    // split-K weight gradients (fp32 red.add)
     const char* e = getenv("MVAE_GEMM_PAIRS");
     if (!e || atoi(e) != 0) {
-      const int rc = mvae_umma_gemm_pairs(A, B, D, M, N, K, err_flag, stream);
+      const int rc = mvae_umma_gemm_pairs(A, B, D, M, N, K, splits, err_flag, stream);
       if (rc != MVAE_ERR_UNSUPPORTED) return rc;
     }
   }

@@ -121,8 +121,8 @@ int mvae_tc_sgemm(const mvae_tc_ctx* ctx, cudaStream_t st, const float* A, long 
                   long long sbk, long long sbn, float* C, long long ldc, int M, int N, int K, const float* bias, int act,
                   int accumulate, int* launches);
 
-// 2-CTA (tcgen05 cta_group::2) variant for plain projections: A, B K-major, bf16 output (+ bias), M % 256 == N % 256 == 0
+// 2-CTA (tcgen05 cta_group::2) variant: K- or MN-major operands, M % 256 == N % 256 == 0, bf16 output (+ bias) or fp32 split-K red.add
 // (umma_gemm2.cu).  mvae_umma_gemm routes matching calls there (MVAE_GEMM_PAIRS=0 disables it); returns
 // MVAE_ERR_UNSUPPORTED, with nothing enqueued, for anything else.
 int mvae_umma_gemm_pairs(const mvae_umma_operand* A, const mvae_umma_operand* B, const mvae_umma_out* D, int M, int N, int K,
-                         int* err_flag, cudaStream_t stream);
+                         int splits, int* err_flag, cudaStream_t stream);

@@ -1,6 +1,7 @@
-// 2-CTA (tcgen05.mma.cta_group::2) variant of the tcgen05 / TMA GEMM for the K-short input projections.
+// 2-CTA (tcgen05.mma.cta_group::2) variant of the tcgen05 / TMA GEMM.
 //
-//   D[M,N] = A[M,K] * B[N,K]^T + bias[N]      A, B bf16 K-major, D bf16 (row-major or row-blocked), M % 256 == N % 256 == 0
+//   D[M,N] = A * B + bias[N]     bf16 operands, K-major or MN-major (as umma_gemm.cu), M % 256 == N % 256 == 0;
+//   D bf16 (row-major or row-blocked), or fp32 accumulated with red.add over split-K work units (the K = T*B weight gradients)
 //
 // Why: the projection GEMMs (x W_ih^T over all T*B rows, K = 512) are 8 k-blocks per output tile; with one CTA per
 // 128 x 256 tile every k-block costs 48 KB of operand traffic per SM and the kernel runs at the rate L2 delivers them
@@ -24,7 +25,8 @@ constexpr int SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 1024 + 256
 
 struct Params2 {
   int M, N, K, tiles_m, tiles_n;   // tiles_m counts 256-row pair tiles
-  void* out; long long ldc; const float* bias; int out_rb;
+  int splits, kb_per_split;        // split-K (fp32 output only)
+  void* out; long long ldc; const float* bias; int out_rb; int out_bf16;
   int* err_flag;
 };
 
@@ -92,6 +94,7 @@ __device__ __forceinline__ void commit2_mc(uint64_t* bar, uint16_t mask) {
                : "memory");
 }
 
+template <int A_MN, int B_MN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 umma_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params2 p) {
   extern __shared__ uint8_t smem_raw[];
@@ -129,7 +132,7 @@ umma_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const uint32_t tmem_base = *tmem_holder;
 
   const int kb_total = (p.K + BK - 1) / BK;
-  const int n_units = p.tiles_m * p.tiles_n;
+  const int n_units = p.tiles_m * p.tiles_n * p.splits;
   const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
 
   if (warp == 0) {
@@ -138,13 +141,28 @@ umma_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       int s = 0;
       uint32_t ph = 0;
       for (int unit = pair; unit < n_units; unit += npairs) {
-        const int m_blk = unit / p.tiles_n, n_blk = unit - m_blk * p.tiles_n;
-        for (int kb = 0; kb < kb_total; ++kb) {
+        const int tile = unit / p.splits, split = unit - tile * p.splits;
+        const int m_blk = tile / p.tiles_n, n_blk = tile - m_blk * p.tiles_n;
+        const int kb0 = split * p.kb_per_split, kb1 = min(kb_total, kb0 + p.kb_per_split);
+        const int m0 = m_blk * 2 * BM + (int)rank * BM, n0 = n_blk * BN + (int)rank * (BN / 2);
+        for (int kb = kb0; kb < kb1; ++kb) {
           if (!wait_bar(&empty_bar[s], ph ^ 1, p.err_flag)) goto done;
           if (leader) ptx::mbar_arrive_expect_tx(&full_bar[s], 2u * (A_STAGE_BYTES + B_STAGE_BYTES));
           const uint32_t fb = mapa(ptx::smem_u32(&full_bar[s]), 0u);
-          tma_load_3d_2sm(sA + s * A_STAGE_BYTES, &tmA, fb, kb * BK, m_blk * 2 * BM + (int)rank * BM, 0);
-          tma_load_3d_2sm(sB + s * B_STAGE_BYTES, &tmB, fb, kb * BK, n_blk * BN + (int)rank * (BN / 2), 0);
+          uint8_t* a_dst = sA + s * A_STAGE_BYTES;
+          uint8_t* b_dst = sB + s * B_STAGE_BYTES;
+          if (A_MN) {     // stored [K][M]: 64 (m) x 64 (k) boxes, 8 KB apart
+#pragma unroll
+            for (int c = 0; c < BM / 64; ++c) tma_load_3d_2sm(a_dst + c * 8192, &tmA, fb, m0 + c * 64, kb * BK, 0);
+          } else {
+            tma_load_3d_2sm(a_dst, &tmA, fb, kb * BK, m0, 0);
+          }
+          if (B_MN) {
+#pragma unroll
+            for (int c = 0; c < BN / 2 / 64; ++c) tma_load_3d_2sm(b_dst + c * 8192, &tmB, fb, n0 + c * 64, kb * BK, 0);
+          } else {
+            tma_load_3d_2sm(b_dst, &tmB, fb, kb * BK, n0, 0);
+          }
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
       }
@@ -152,25 +170,31 @@ umma_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   } else if (warp == 1) {
     // ===================== MMA issuer (pair leader, one thread) =====================
     if (lane == 0 && leader) {
-      constexpr uint32_t idesc = ptx::umma_idesc_bf16(2 * BM, BN, 0, 0);
+      constexpr uint32_t idesc = ptx::umma_idesc_bf16(2 * BM, BN, A_MN, B_MN);
       int s = 0;
       uint32_t ph = 0;
       int acc = 0;
       uint32_t acc_ph = 0;
       for (int unit = pair; unit < n_units; unit += npairs) {
+        const int split = unit % p.splits;
+        const int kb0 = split * p.kb_per_split, kb1 = min(kb_total, kb0 + p.kb_per_split);
         if (!wait_bar(&tempty_bar[acc], acc_ph ^ 1, p.err_flag)) goto done;
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = 0; kb < kb_total; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           if (!wait_bar(&full_bar[s], ph, p.err_flag)) goto done;
           ptx::tc_fence_after();
           const uint32_t a_addr = ptx::smem_u32(sA + s * A_STAGE_BYTES);
           const uint32_t b_addr = ptx::smem_u32(sB + s * B_STAGE_BYTES);
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
-            const uint64_t adesc = ptx::umma_smem_desc_sw128(a_addr + k * 32, 16, 1024);
-            const uint64_t bdesc = ptx::umma_smem_desc_sw128(b_addr + k * 32, 16, 1024);
-            umma2_bf16(d_tmem, adesc, bdesc, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            // K-major SW128: 8-row groups 1024 B apart, 32 B per K = 16 inside the swizzle row; MN-major SW128: 64-wide MN
+            // chunks 8192 B apart (LBO), 8-k-row groups 1024 B apart (SBO), two k-groups (2048 B) per K = 16
+            const uint64_t adesc = A_MN ? ptx::umma_smem_desc_sw128(a_addr + k * 2048, 8192, 1024)
+                                        : ptx::umma_smem_desc_sw128(a_addr + k * 32, 16, 1024);
+            const uint64_t bdesc = B_MN ? ptx::umma_smem_desc_sw128(b_addr + k * 2048, 8192, 1024)
+                                        : ptx::umma_smem_desc_sw128(b_addr + k * 32, 16, 1024);
+            umma2_bf16(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
           commit2_mc(&empty_bar[s], (uint16_t)3);
           if (++s == STAGES) { s = 0; ph ^= 1; }
@@ -188,12 +212,31 @@ umma_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     uint32_t acc_ph = 0;
     const uint32_t tempty_leader = mapa(ptx::smem_u32(&tempty_bar[0]), 0u);
     for (int unit = pair; unit < n_units; unit += npairs) {
-      const int m_blk = unit / p.tiles_n, n_blk = unit - m_blk * p.tiles_n;
+      const int tile = unit / p.splits, split = unit - tile * p.splits;
+      const int m_blk = tile / p.tiles_n, n_blk = tile - m_blk * p.tiles_n;
       if (!wait_bar(&tfull_bar[acc], acc_ph, p.err_flag)) goto done;
       ptx::tc_fence_after();
       const int row = m_blk * 2 * BM + (int)rank * BM + q * 32 + lane;
       const uint32_t tb = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + chalf * CH;
       uint32_t r0[32], r1[32];
+      if (!p.out_bf16) {
+        // fp32 result accumulated over the split-K units with red.add (the caller zeroes D or passes what to add onto)
+#pragma unroll 1
+        for (int c = 0; c < NCH; ++c) {
+          ptx::tmem_ld_32x32(tb + c * 32, r0);
+          ptx::tmem_ld_wait();
+          float* o = reinterpret_cast<float*>(p.out) + (long long)row * p.ldc + n_blk * BN + chalf * CH + c * 32;
+          const bool add_bias = p.bias != nullptr && split == 0;
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            atomicAdd(o + j, __uint_as_float(r0[j]) + (add_bias ? __ldg(p.bias + n_blk * BN + chalf * CH + c * 32 + j) : 0.f));
+        }
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) remote_arrive(tempty_leader + (uint32_t)(acc * 8));
+        if (++acc == 2) { acc = 0; acc_ph ^= 1; }
+        continue;
+      }
       auto process = [&](const uint32_t (&rr)[32], int c) {
         const int col0 = n_blk * BN + chalf * CH + c * 32;
 #pragma unroll
@@ -261,15 +304,17 @@ PFN_encodeTiled get_encode_fn() {
   fn = reinterpret_cast<PFN_encodeTiled>(p);
   return fn;
 }
+// K-major: dims {K, rows(MN)}, box {64, box_rows}.  MN-major (stored [K][MN]): dims {MN, K}, box {64, 64}.
 int make_map(CUtensorMap* map, const mvae_umma_operand& op, int box_rows) {
   PFN_encodeTiled enc = get_encode_fn();
   if (!enc) return MVAE_ERR_DRIVER;
   if ((reinterpret_cast<uintptr_t>(op.ptr) & 15) || (op.ld & 7)) return MVAE_ERR_INVALID;
   const long long slabs = op.slabs > 0 ? op.slabs : 1;
+  const long long rows = op.mn_major ? op.k : op.mn, cols = op.mn_major ? op.mn : op.k;
   cuuint32_t estr[3] = {1, 1, 1};
-  cuuint64_t dims[3] = {(cuuint64_t)op.k, (cuuint64_t)op.mn, (cuuint64_t)slabs};
-  cuuint64_t strides[2] = {(cuuint64_t)op.ld * 2, (cuuint64_t)(slabs > 1 ? op.slab_stride : op.ld * op.mn) * 2};
-  cuuint32_t box[3] = {64, (cuuint32_t)box_rows, 1};
+  cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)slabs};
+  cuuint64_t strides[2] = {(cuuint64_t)op.ld * 2, (cuuint64_t)(slabs > 1 ? op.slab_stride : op.ld * rows) * 2};
+  cuuint32_t box[3] = {64, (cuuint32_t)(op.mn_major ? 64 : box_rows), 1};
   if ((strides[0] & 15) || (strides[1] & 15)) return MVAE_ERR_INVALID;
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(op.ptr), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -279,14 +324,36 @@ int make_map(CUtensorMap* map, const mvae_umma_operand& op, int box_rows) {
 
 }  // namespace
 
-// Returns MVAE_ERR_UNSUPPORTED (nothing enqueued) unless: A, B K-major single-slab operands, bf16 output without accumulation,
-// M and N multiples of 256, 16-byte aligned output rows / bias.
+template <int A_MN, int B_MN>
+static int launch_pairs_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const Params2& p, int pairs, cudaStream_t stream) {
+  auto kern = umma_gemm2_kernel<A_MN, B_MN>;
+  static size_t attr_cache[64] = {0};
+  MVAE_CUDA_CHECK(mvae_ensure_dyn_smem(reinterpret_cast<const void*>(kern), SMEM_BYTES, attr_cache));
+  cudaLaunchConfig_t cfg{};
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.gridDim = dim3((unsigned)(2 * pairs), 1, 1); cfg.blockDim = dim3(NUM_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = SMEM_BYTES; cfg.stream = stream; cfg.attrs = at; cfg.numAttrs = 1;
+  MVAE_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p));
+  return MVAE_OK;
+}
+
+// Returns MVAE_ERR_UNSUPPORTED (nothing enqueued) unless: single-slab operands, M and N multiples of 256, and either a bf16
+// result without accumulation / split-K (16-byte aligned rows and bias) or an fp32 result that is ACCUMULATED (red.add, any
+// split-K factor; the caller zeroed D or passes the value to add onto).
 int mvae_umma_gemm_pairs(const mvae_umma_operand* A, const mvae_umma_operand* B, const mvae_umma_out* D, int M, int N, int K,
-                         int* err_flag, cudaStream_t stream) {
-  if (!A || !B || !D || A->mn_major || B->mn_major || A->slabs > 1 || B->slabs > 1 || A->slab || B->slab || !D->bf16 || D->accumulate ||
-      D->act || (M % (2 * BM)) || (N % BN) || K < 1 || (D->ld & 7) || (reinterpret_cast<uintptr_t>(D->ptr) & 15) ||
-      (reinterpret_cast<uintptr_t>(D->bias) & 15))
+                         int splits, int* err_flag, cudaStream_t stream) {
+  if (!A || !B || !D || A->slabs > 1 || B->slabs > 1 || A->slab || B->slab || D->act || D->rb && !D->bf16 ||
+      (M % (2 * BM)) || (N % BN) || K < 1)
     return MVAE_ERR_UNSUPPORTED;
+  if (splits < 1) splits = 1;
+  if (D->bf16) {
+    if (D->accumulate || splits > 1 || (D->ld & 7) || (reinterpret_cast<uintptr_t>(D->ptr) & 15) || (reinterpret_cast<uintptr_t>(D->bias) & 15))
+      return MVAE_ERR_UNSUPPORTED;
+  } else {
+    if (!D->accumulate || splits <= 1) return MVAE_ERR_UNSUPPORTED;   // the fp32 epilogue only knows red.add: split-K reductions
+  }
   CUtensorMap tmA, tmB;
   int rc = make_map(&tmA, *A, BM);
   if (rc) return rc;
@@ -294,21 +361,19 @@ int mvae_umma_gemm_pairs(const mvae_umma_operand* A, const mvae_umma_operand* B,
   if (rc) return rc;
   Params2 p{};
   p.M = M; p.N = N; p.K = K; p.tiles_m = M / (2 * BM); p.tiles_n = N / BN;
-  p.out = D->ptr; p.ldc = D->ld; p.bias = D->bias; p.out_rb = D->rb; p.err_flag = err_flag;
+  const int kb_total = (K + BK - 1) / BK;
+  if (splits > kb_total) splits = kb_total;
+  p.kb_per_split = (kb_total + splits - 1) / splits;
+  p.splits = (kb_total + p.kb_per_split - 1) / p.kb_per_split;
+  p.out = D->ptr; p.ldc = D->ld; p.bias = D->bias; p.out_rb = D->rb; p.out_bf16 = D->bf16; p.err_flag = err_flag;
   int dev = 0, sms = 0;
   MVAE_CUDA_CHECK(cudaGetDevice(&dev));
   MVAE_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  static size_t attr_cache[64] = {0};
-  MVAE_CUDA_CHECK(mvae_ensure_dyn_smem(reinterpret_cast<const void*>(umma_gemm2_kernel), SMEM_BYTES, attr_cache));
-  const long long units = (long long)p.tiles_m * p.tiles_n;
+  const long long units = (long long)p.tiles_m * p.tiles_n * p.splits;
   long long pairs = sms / 2;
   if (pairs > units) pairs = units;
-  cudaLaunchConfig_t cfg{};
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeClusterDimension;
-  at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-  cfg.gridDim = dim3((unsigned)(2 * pairs), 1, 1); cfg.blockDim = dim3(NUM_THREADS, 1, 1);
-  cfg.dynamicSmemBytes = SMEM_BYTES; cfg.stream = stream; cfg.attrs = at; cfg.numAttrs = 1;
-  MVAE_CUDA_CHECK(cudaLaunchKernelEx(&cfg, umma_gemm2_kernel, tmA, tmB, p));
-  return MVAE_OK;
+  if (!A->mn_major && !B->mn_major) return launch_pairs_t<0, 0>(tmA, tmB, p, (int)pairs, stream);
+  if (!A->mn_major && B->mn_major) return launch_pairs_t<0, 1>(tmA, tmB, p, (int)pairs, stream);
+  if (A->mn_major && !B->mn_major) return launch_pairs_t<1, 0>(tmA, tmB, p, (int)pairs, stream);
+  return launch_pairs_t<1, 1>(tmA, tmB, p, (int)pairs, stream);
 }

@@ -426,3 +426,37 @@ def test_gemm_pairs_equals_single_cta_gemm(monkeypatch, M, N, K, rb):
     assert torch.equal(outs["1"], outs["0"])
     ref = a[:, :K].double() @ b[:, :K].double().t() + bias.double()
     assert (outs["1"].double() - ref).abs().max().item() <= 2e-2 * ref.abs().max().item()
+
+
+@pytest.mark.parametrize("M,N,K,a_mn,b_mn,splits", [(2048, 512, 1536, 0, 1, 1),      # dX = dgi * W_ih (B stored [K][N]), bf16 result
+                                                    (1536, 512, 8192, 1, 1, 12),     # dW = dG^T * X: both operands [K][.], split-K fp32
+                                                    (512, 256, 4096, 1, 0, 4)])
+def test_gemm_pairs_mn_major_and_split_k(monkeypatch, M, N, K, a_mn, b_mn, splits):
+    """The 2-CTA GEMM with MN-major operands (transposing shared-memory descriptors) and with the split-K fp32 red.add epilogue,
+    against the one-CTA kernel and an fp64 product."""
+    import ctypes
+    m = load_pkg()
+    lib, vp = m._lib.lib, ctypes.c_void_p
+    g = torch.Generator(device="cuda").manual_seed(13)
+    A = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    Bm = (torch.randn(K, N, device="cuda", generator=g) * 0.05).bfloat16()
+    a_st = A.t().contiguous() if a_mn else A.contiguous()          # [K][M] or [M][K]
+    b_st = Bm.contiguous() if b_mn else Bm.t().contiguous()        # [K][N] or [N][K]
+    lda, ldb = (M if a_mn else K), (N if b_mn else K)
+    err = torch.zeros(1, dtype=torch.int32, device="cuda")
+    is_bf16 = splits == 1
+    outs = {}
+    for flag in ("1", "0"):
+        monkeypatch.setenv("MVAE_GEMM_PAIRS", flag)
+        d = torch.zeros(M, N, device="cuda", dtype=torch.bfloat16 if is_bf16 else torch.float32)
+        rc = lib.mvae_gemm_bf16(vp(a_st.data_ptr()), lda, a_mn, vp(b_st.data_ptr()), ldb, b_mn, vp(d.data_ptr()), N, int(is_bf16),
+                                0 if is_bf16 else 1, vp(0), M, N, K, 256, splits, vp(err.data_ptr()),
+                                vp(torch.cuda.current_stream().cuda_stream))
+        assert rc == 0
+        torch.cuda.synchronize()
+        assert int(err.item()) == 0
+        outs[flag] = d.double()
+    ref = A.double() @ Bm.double()
+    scale = ref.abs().max().item()
+    assert (outs["1"] - ref).abs().max().item() <= (2e-2 if is_bf16 else 1e-4) * scale
+    assert (outs["1"] - outs["0"]).abs().max().item() <= (0 if is_bf16 else 1e-5 * scale)
