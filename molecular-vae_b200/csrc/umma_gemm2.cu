@@ -27,6 +27,7 @@ struct Params2 {
   int M, N, K, tiles_m, tiles_n;   // tiles_m counts 256-row pair tiles
   int splits, kb_per_split;        // split-K (fp32 output only)
   void* out; long long ldc; const float* bias; int out_rb; int out_bf16;
+  int accumulate;                  // fp32 output, splits == 1: D += result (plain read-modify-write)
   int* err_flag;
 };
 
@@ -219,6 +220,34 @@ umma_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const int row = m_blk * 2 * BM + (int)rank * BM + q * 32 + lane;
       const uint32_t tb = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + chalf * CH;
       uint32_t r0[32], r1[32];
+      if (!p.out_bf16 && p.splits == 1) {
+        // fp32 result of a whole-K unit: plain 16-byte stores (or read-modify-write when accumulating; nobody else owns the tile)
+#pragma unroll 1
+        for (int c = 0; c < NCH; ++c) {
+          ptx::tmem_ld_32x32(tb + c * 32, r0);
+          ptx::tmem_ld_wait();
+          const int col0 = n_blk * BN + chalf * CH + c * 32;
+          float* o = reinterpret_cast<float*>(p.out) + (long long)row * p.ldc + col0;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float4 w = make_float4(__uint_as_float(r0[j]), __uint_as_float(r0[j + 1]), __uint_as_float(r0[j + 2]), __uint_as_float(r0[j + 3]));
+            if (p.bias) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
+              w.x += b4.x; w.y += b4.y; w.z += b4.z; w.w += b4.w;
+            }
+            if (p.accumulate) {
+              const float4 old = *reinterpret_cast<const float4*>(o + j);
+              w.x += old.x; w.y += old.y; w.z += old.z; w.w += old.w;
+            }
+            *reinterpret_cast<float4*>(o + j) = w;
+          }
+        }
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) remote_arrive(tempty_leader + (uint32_t)(acc * 8));
+        if (++acc == 2) { acc = 0; acc_ph ^= 1; }
+        continue;
+      }
       if (!p.out_bf16) {
         // fp32 result accumulated over the split-K units with red.add (the caller zeroes D or passes what to add onto)
 #pragma unroll 1
@@ -352,7 +381,8 @@ int mvae_umma_gemm_pairs(const mvae_umma_operand* A, const mvae_umma_operand* B,
     if (D->accumulate || splits > 1 || (D->ld & 7) || (reinterpret_cast<uintptr_t>(D->ptr) & 15) || (reinterpret_cast<uintptr_t>(D->bias) & 15))
       return MVAE_ERR_UNSUPPORTED;
   } else {
-    if (!D->accumulate || splits <= 1) return MVAE_ERR_UNSUPPORTED;   // the fp32 epilogue only knows red.add: split-K reductions
+    if (splits > 1 ? !D->accumulate : ((D->ld & 3) || (reinterpret_cast<uintptr_t>(D->ptr) & 15) || (reinterpret_cast<uintptr_t>(D->bias) & 15)))
+      return MVAE_ERR_UNSUPPORTED;   // split-K: red.add onto D; whole-K: 16-byte stores / read-modify-write
   }
   CUtensorMap tmA, tmB;
   int rc = make_map(&tmA, *A, BM);
@@ -365,7 +395,7 @@ int mvae_umma_gemm_pairs(const mvae_umma_operand* A, const mvae_umma_operand* B,
   if (splits > kb_total) splits = kb_total;
   p.kb_per_split = (kb_total + splits - 1) / splits;
   p.splits = (kb_total + p.kb_per_split - 1) / p.kb_per_split;
-  p.out = D->ptr; p.ldc = D->ld; p.bias = D->bias; p.out_rb = D->rb; p.out_bf16 = D->bf16; p.err_flag = err_flag;
+  p.out = D->ptr; p.ldc = D->ld; p.bias = D->bias; p.out_rb = D->rb; p.out_bf16 = D->bf16; p.accumulate = D->accumulate; p.err_flag = err_flag;
   int dev = 0, sms = 0;
   MVAE_CUDA_CHECK(cudaGetDevice(&dev));
   MVAE_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));

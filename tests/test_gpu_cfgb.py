@@ -430,7 +430,9 @@ def test_gemm_pairs_equals_single_cta_gemm(monkeypatch, M, N, K, rb):
 
 @pytest.mark.parametrize("M,N,K,a_mn,b_mn,splits", [(2048, 512, 1536, 0, 1, 1),      # dX = dgi * W_ih (B stored [K][N]), bf16 result
                                                     (1536, 512, 8192, 1, 1, 12),     # dW = dG^T * X: both operands [K][.], split-K fp32
-                                                    (512, 256, 4096, 1, 0, 4)])
+                                                    (512, 256, 4096, 1, 0, 4),
+                                                    (1024, 1024, 1024, 0, 0, -1),    # whole-K fp32 result (per-step LSTM GEMM)
+                                                    (512, 512, 2048, 0, 1, -2)])     # whole-K fp32 accumulated onto D (per-step BPTT GEMM)
 def test_gemm_pairs_mn_major_and_split_k(monkeypatch, M, N, K, a_mn, b_mn, splits):
     """The 2-CTA GEMM with MN-major operands (transposing shared-memory descriptors) and with the split-K fp32 red.add epilogue,
     against the one-CTA kernel and an fp64 product."""
@@ -445,18 +447,23 @@ def test_gemm_pairs_mn_major_and_split_k(monkeypatch, M, N, K, a_mn, b_mn, split
     lda, ldb = (M if a_mn else K), (N if b_mn else K)
     err = torch.zeros(1, dtype=torch.int32, device="cuda")
     is_bf16 = splits == 1
+    whole_fp32, acc_whole = splits < 0, splits == -2
+    d0 = torch.randn(M, N, device="cuda", generator=g) if acc_whole else torch.zeros(M, N, device="cuda")
+    if whole_fp32:
+        splits = 1
     outs = {}
     for flag in ("1", "0"):
         monkeypatch.setenv("MVAE_GEMM_PAIRS", flag)
-        d = torch.zeros(M, N, device="cuda", dtype=torch.bfloat16 if is_bf16 else torch.float32)
+        d = torch.zeros(M, N, device="cuda", dtype=torch.bfloat16) if is_bf16 else d0.clone()
+        acc_flag = 0 if (is_bf16 or (whole_fp32 and not acc_whole)) else 1
         rc = lib.mvae_gemm_bf16(vp(a_st.data_ptr()), lda, a_mn, vp(b_st.data_ptr()), ldb, b_mn, vp(d.data_ptr()), N, int(is_bf16),
-                                0 if is_bf16 else 1, vp(0), M, N, K, 256, splits, vp(err.data_ptr()),
+                                acc_flag, vp(0), M, N, K, 256, splits, vp(err.data_ptr()),
                                 vp(torch.cuda.current_stream().cuda_stream))
         assert rc == 0
         torch.cuda.synchronize()
         assert int(err.item()) == 0
         outs[flag] = d.double()
-    ref = A.double() @ Bm.double()
+    ref = A.double() @ Bm.double() + (d0.double() if acc_whole else 0.0)
     scale = ref.abs().max().item()
     assert (outs["1"] - ref).abs().max().item() <= (2e-2 if is_bf16 else 1e-4) * scale
-    assert (outs["1"] - outs["0"]).abs().max().item() <= (0 if is_bf16 else 1e-5 * scale)
+    assert (outs["1"] - outs["0"]).abs().max().item() <= (0 if (is_bf16 or whole_fp32) else 1e-5 * scale)
