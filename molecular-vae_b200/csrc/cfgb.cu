@@ -400,9 +400,82 @@ __global__ void gi0_to_bf16_kernel(const float* __restrict__ src, const float* _
 }
 
 // ---- weight preparation ---------------------------------------------------------------------
+// bf16 fast path: every padded / permuted / transposed weight copy of the step in ONE launch (a table of up to 32 jobs in the
+// kernel parameters, blockIdx.y = job) instead of ~22 launches of a few microseconds each.
+struct PrepJob {
+  const float* src; const float* src2; void* dst;
+  int type;            // 0 gate matrix -> bf16, 1 W_hh^T -> bf16, 2 gate vector, 3 b_ih + (b_hr, b_hz, 0), 4 matrix -> bf16, 5 matrix fp32
+  int H, cols, Hp, cols_p, g0, g1, g2;
+  long long total;
+};
+struct PrepJobs { PrepJob j[32]; int n; };
+__global__ void prep_weights_fused_kernel(const __grid_constant__ PrepJobs jobs) {
+  const PrepJob& jb = jobs.j[blockIdx.y];
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < jb.total; i += (long long)gridDim.x * blockDim.x) {
+    if (jb.type == 0) {          // src [3H][cols] -> dst [3Hp][cols_p], block order (g0,g1,g2) names the source gate
+      const int c = (int)(i % jb.cols_p), r = (int)(i / jb.cols_p);
+      const int blk = r / jb.Hp, j = r - blk * jb.Hp;
+      const int g = blk == 0 ? jb.g0 : (blk == 1 ? jb.g1 : jb.g2);
+      float v = 0.f;
+      if (j < jb.H && c < jb.cols) v = jb.src[((long long)g * jb.H + j) * jb.cols + c];
+      reinterpret_cast<__nv_bfloat16*>(jb.dst)[i] = __float2bfloat16_rn(v);
+    } else if (jb.type == 1) {   // dst[j][g*Hp + i] = W_hh[g*H + i][j]
+      const int k = (int)(i % (3 * jb.Hp)), j = (int)(i / (3 * jb.Hp));
+      const int g = k / jb.Hp, ii = k - g * jb.Hp;
+      float v = 0.f;
+      if (ii < jb.H && j < jb.H) v = jb.src[((long long)g * jb.H + ii) * jb.H + j];
+      reinterpret_cast<__nv_bfloat16*>(jb.dst)[i] = __float2bfloat16_rn(v);
+    } else if (jb.type == 2) {   // padded gate vector
+      const int g = (int)(i / jb.Hp), j = (int)(i - (long long)g * jb.Hp);
+      reinterpret_cast<float*>(jb.dst)[i] = j < jb.H ? jb.src[g * jb.H + j] : 0.f;
+    } else if (jb.type == 3) {   // b_ih + (b_hr, b_hz, 0), padded
+      const int g = (int)(i / jb.Hp), j = (int)(i - (long long)g * jb.Hp);
+      reinterpret_cast<float*>(jb.dst)[i] = j < jb.H ? jb.src[g * jb.H + j] + (g < 2 ? jb.src2[g * jb.H + j] : 0.f) : 0.f;
+    } else {                     // src [H][cols] -> dst [Hp][cols_p] (H / Hp = rows here)
+      const int c = (int)(i % jb.cols_p), r = (int)(i / jb.cols_p);
+      const float v = (r < jb.H && c < jb.cols) ? jb.src[(long long)r * jb.cols + c] : 0.f;
+      if (jb.type == 4) reinterpret_cast<__nv_bfloat16*>(jb.dst)[i] = __float2bfloat16_rn(v);
+      else reinterpret_cast<float*>(jb.dst)[i] = v;
+    }
+  }
+}
+bool prep_fused_enabled() {
+  const char* e = getenv("MVAE_PREP_FUSED");
+  return e ? atoi(e) != 0 : true;
+}
+
 template <typename TA>
 int prep_weights(const Dims& d, const WS& w, const float* const* P, cudaStream_t st, bool need_bwd) {
   const int H = d.H, Hp = d.Hp;
+  if constexpr (sizeof(TA) == 2) {
+    if (rec_variant(d) >= 3 && prep_fused_enabled()) {
+      PrepJobs jobs{};
+      int n = 0;
+      auto add = [&](int type, const float* src, const float* src2, void* dst, int h, int cols, int hp, int cols_p, int g0, int g1, int g2, long long total) {
+        jobs.j[n++] = PrepJob{src, src2, dst, type, h, cols, hp, cols_p, g0, g1, g2, total};
+      };
+      const int Zp = round_up(d.Z, 8);
+      for (int l = 0; l < d.L; ++l) {
+        add(0, P[P_WHH(l)], nullptr, w.Whh_p[l], H, H, Hp, Hp, 0, 1, 2, 3ll * Hp * Hp);
+        if (need_bwd) add(1, P[P_WHH(l)], nullptr, w.WhhT_p[l], H, H, Hp, Hp, 0, 1, 2, 3ll * Hp * Hp);
+        add(2, P[P_BHH(l)], nullptr, w.bhh_p[l], H, 1, Hp, 1, 0, 1, 2, 3ll * Hp);
+        add(2, P[P_BIH(l)], nullptr, w.bih_p[l], H, 1, Hp, 1, 0, 1, 2, 3ll * Hp);
+        add(3, P[P_BIH(l)], P[P_BHH(l)], w.bcomb_p[l], H, 1, Hp, 1, 0, 1, 2, 3ll * Hp);
+        if (l >= 1) {
+          add(0, P[P_WIH(l)], nullptr, w.Wih_p[l], H, H, Hp, Hp, 0, 1, 2, 3ll * Hp * Hp);
+          if (need_bwd) add(0, P[P_WIH(l)], nullptr, w.Wih_nrz[l], H, H, Hp, Hp, 2, 0, 1, 3ll * Hp * Hp);
+        } else {
+          add(0, P[P_WIH(0)], nullptr, w.Wih0_p, H, d.Z, Hp, Zp, 0, 1, 2, 3ll * Hp * Zp);
+        }
+      }
+      add(4, P[P_FC3W(d.L)], nullptr, w.W3_p, d.C, H, d.CP, Hp, 0, 1, 2, (long long)d.CP * Hp);
+      add(5, P[P_FC3B(d.L)], nullptr, w.b3_p, 1, d.C, 1, d.CP, 0, 1, 2, (long long)d.CP);
+      jobs.n = n;
+      prep_weights_fused_kernel<<<dim3(96, n), 256, 0, st>>>(jobs);
+      KCHECK();
+      return MVAE_OK;
+    }
+  }
   const int g = grid_for(3ll * Hp * Hp);
   for (int l = 0; l < d.L; ++l) {
     simt::pad_gate_matrix_kernel<TA><<<g, 256, 0, st>>>(P[P_WHH(l)], H, H, (TA*)w.Whh_p[l], Hp, Hp, 0, 1, 2);
