@@ -33,6 +33,10 @@ struct MDims {
   float drop; unsigned int drop_seed;   // train-mode dropout between decoder layers (0 = off)
 };
 
+bool balanced_splits_enabled() {
+  const char* e = getenv("MVAE_BALANCED_SPLITS");
+  return e ? atoi(e) != 0 : true;
+}
 bool moses_fused_head_enabled() {
   const char* e = getenv("MVAE_FUSED_HEAD");
   return e ? atoi(e) != 0 : true;
@@ -726,7 +730,7 @@ int step_t(const MDims& d, const MWS& w, const float* const* P, float* const* G,
   const MP ix{d.bidir, d.lin, L};
   if (phase >= L) return MVAE_ERR_INVALID;
   // packed sequences: the big time-major GEMMs skip output tiles (mode 1) / k-blocks (mode 2) past the running sequences
-  mvae_umma_varlen vlm{w.act_dev, Bp, 1}, vlk{w.act_dev, Bp, 2};
+  mvae_umma_varlen vlm{w.act_dev, Bp, 1, nullptr}, vlk{w.act_dev, Bp, 2, balanced_splits_enabled() ? act : nullptr};
   const mvae_umma_varlen* VLM = (act && d.bf16 && varlen_gemm_enabled()) ? &vlm : nullptr;
   const mvae_umma_varlen* VLK = (act && d.bf16 && varlen_gemm_enabled()) ? &vlk : nullptr;
   const bool prec_enc = sizeof(TA) == 2 && persistent_encoder(d);
@@ -741,7 +745,7 @@ int step_t(const MDims& d, const MWS& w, const float* const* P, float* const* G,
   }
   // persistent sweeps over packed sequences: row tile j runs only tileT[j] steps; the GEMMs that feed / follow them skip the
   // same (t, 256-row tile) regions, which are then neither written nor read
-  mvae_umma_varlen vlm256{w.act256_dev, Bp, 1};
+  mvae_umma_varlen vlm256{w.act256_dev, Bp, 1, nullptr};
   const mvae_umma_varlen* VLS = VLM ? &vlm256 : nullptr;
   const int* tileT = VLM ? w.tileT : nullptr;
   const int* lim256 = VLM ? w.act256_dev : nullptr;

@@ -57,7 +57,15 @@ struct KernelParams {
   int vl_mode;         // packed-sequence skipping, see mvae_umma_varlen
   const int* vl_act;
   int vl_tiles;        // M tiles (mode 1) or k-blocks (mode 2) per slab
+  int vl_nb;           // > 0: explicit split-K boundaries (k-block indices) in vl_bounds[0 .. splits]
+  int vl_bounds[160];
 };
+
+// k-block range [kb0, kb1) of split `split`
+__device__ __forceinline__ void split_range(const KernelParams& p, int split, int kb_total, int& kb0, int& kb1) {
+  if (p.vl_nb) { kb0 = p.vl_bounds[split]; kb1 = p.vl_bounds[split + 1]; }
+  else { kb0 = split * p.kb_per_split; kb1 = min(kb_total, kb0 + p.kb_per_split); }
+}
 
 // mode 1: is output tile m_blk entirely past the running sequences of its slab?
 __device__ __forceinline__ bool vl_skip_tile(const KernelParams& p, int m_blk) {
@@ -72,6 +80,8 @@ __device__ __forceinline__ bool vl_skip_kb(const KernelParams& p, int kb, int kb
   const int t = kb / p.vl_tiles, r = kb - t * p.vl_tiles;
   return r * BK >= __ldg(p.vl_act + t);
 }
+// first k-block of the slab after the one kb lies in (once one block of a slab is inactive, the remaining ones are as well)
+__device__ __forceinline__ int vl_slab_end(const KernelParams& p, int kb) { return (kb / p.vl_tiles + 1) * p.vl_tiles; }
 // the first k-block of a split is never skipped; when it lies in the inactive part (whose contents are undefined) the
 // producer loads it from beyond the K extent instead, where TMA fills zeros
 __device__ __forceinline__ bool vl_first_kb_inactive(const KernelParams& p, int kb, int kb0) {
@@ -118,7 +128,7 @@ __device__ __forceinline__ bool wait_bar(uint64_t* bar, uint32_t parity, int* er
 template <int BN, int A_MN, int B_MN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 const KernelParams p) {
+                 const __grid_constant__ KernelParams p) {
   using C = Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -167,11 +177,11 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
         const int tile = unit / p.splits, split = unit - tile * p.splits;
         const int m_blk = tile / p.tiles_n, n_blk = tile - m_blk * p.tiles_n;
-        const int kb0 = split * p.kb_per_split;
-        const int kb1 = min(kb_total, kb0 + p.kb_per_split);
+        int kb0, kb1;
+        split_range(p, split, kb_total, kb0, kb1);
         if (vl_skip_tile(p, m_blk)) continue;
         for (int kb = kb0; kb < kb1; ++kb) {
-          if (vl_skip_kb(p, kb, kb0)) continue;
+          if (vl_skip_kb(p, kb, kb0)) { kb = vl_slab_end(p, kb) - 1; continue; }   // the rest of this slab is inactive too
           if (!wait_bar(&empty_bar[s], ph ^ 1, p.err_flag)) goto done;
           ptx::mbar_arrive_expect_tx(&full_bar[s], C::STAGE_BYTES);
           uint8_t* a_dst = sA + s * A_STAGE_BYTES;
@@ -205,15 +215,15 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       uint32_t acc_ph = 0;
       for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
         const int tile = unit / p.splits, split = unit - tile * p.splits;
-        const int kb0 = split * p.kb_per_split;
-        const int kb1 = min(kb_total, kb0 + p.kb_per_split);
+        int kb0, kb1;
+        split_range(p, split, kb_total, kb0, kb1);
         if (kb0 >= kb1) continue;
         if (vl_skip_tile(p, tile / p.tiles_n)) continue;
         if (!wait_bar(&tempty_bar[acc], acc_ph ^ 1, p.err_flag)) goto done;
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
         for (int kb = kb0; kb < kb1; ++kb) {
-          if (vl_skip_kb(p, kb, kb0)) continue;
+          if (vl_skip_kb(p, kb, kb0)) { kb = vl_slab_end(p, kb) - 1; continue; }
           if (!wait_bar(&full_bar[s], ph, p.err_flag)) goto done;
           ptx::tc_fence_after();
           const uint32_t a_addr = ptx::smem_u32(sA + s * A_STAGE_BYTES);
@@ -246,8 +256,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
       const int tile = unit / p.splits, split = unit - tile * p.splits;
       const int m_blk = tile / p.tiles_n, n_blk = tile - m_blk * p.tiles_n;
-      const int kb0 = split * p.kb_per_split;
-      const int kb1 = min(kb_total, kb0 + p.kb_per_split);
+      int kb0, kb1;
+      split_range(p, split, kb_total, kb0, kb1);
       if (kb0 >= kb1) continue;
       if (vl_skip_tile(p, m_blk)) continue;
       if (!wait_bar(&tfull_bar[acc], acc_ph, p.err_flag)) goto done;
@@ -922,6 +932,31 @@ int mvae_umma_gemm(const mvae_umma_operand* A, const mvae_umma_operand* B, const
   kp.vl_mode = varlen ? varlen->mode : 0;
   kp.vl_act = varlen ? varlen->act : nullptr;
   kp.vl_tiles = varlen ? varlen->rows_per_slab / (varlen->mode == 1 ? BM : BK) : 1;
+  kp.vl_nb = 0;
+  if (varlen && varlen->mode == 2 && varlen->act_host && kp.splits > 1 && kp.splits < 160) {
+    // balanced split-K: equal numbers of active k-blocks per split (slab t has ceil(act[t] / 64) active blocks, the leading ones)
+    const int slabs = K / varlen->rows_per_slab;
+    long long total_active = 0;
+    for (int t = 0; t < slabs; ++t) {
+      const int a = ceil_div(varlen->act_host[t], BK);
+      total_active += a < kp.vl_tiles ? a : kp.vl_tiles;
+    }
+    if (total_active >= kp.splits) {
+      int sidx = 1;
+      long long cum = 0;
+      kp.vl_bounds[0] = 0;
+      for (int t = 0; t < slabs && sidx < kp.splits; ++t) {
+        int a = ceil_div(varlen->act_host[t], BK);
+        if (a > kp.vl_tiles) a = kp.vl_tiles;
+        for (int r = 0; r < a && sidx < kp.splits; ++r) {
+          ++cum;
+          if (cum * kp.splits >= total_active * sidx) kp.vl_bounds[sidx++] = t * kp.vl_tiles + r + 1;
+        }
+      }
+      while (sidx <= kp.splits) kp.vl_bounds[sidx++] = kb_total;
+      kp.vl_nb = kp.splits;
+    }
+  }
   if (D->rb && (!D->bf16 || (D->ld & 7) || (N & 7))) return MVAE_ERR_INVALID;
   CUtensorMap tmA, tmB;
   int rc = make_map(&tmA, *A, BM);

@@ -101,6 +101,10 @@ struct mvae_umma_varlen {
   const int* act;
   int rows_per_slab;
   int mode;
+  // optional HOST copy of act (mode 2 with split-K): the split boundaries are then placed so that every split gets the same
+  // number of ACTIVE k-blocks -- with uniform boundaries the splits over the late time slabs of a packed batch are nearly
+  // empty and the early ones carry the work
+  const int* act_host;
 };
 
 // bn: 0 = auto, else 64/128/192/256.  splits: split-K factor (fp32 atomics epilogue when > 1; the
