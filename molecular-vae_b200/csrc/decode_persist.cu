@@ -100,6 +100,13 @@ __device__ __forceinline__ bool wait_count(const unsigned int* ctr, unsigned int
   return true;
 }
 
+// accumulator hand-back: the tcgen05 fences order the TMEM reads, no generic-proxy data rides on these arrives
+__device__ __forceinline__ void arrive_relaxed_local(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.relaxed.cta.shared::cta.b64 _, [%0];" ::"r"(ptx::smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void remote_arrive_relaxed(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
 // schedule entry: layer (8 bits, L = head) | unit slice n (8 bits) | row tile m (16 bits)
 __global__ void build_sched_kernel(unsigned int* sched, int tiles_m, int L) {
   if (blockIdx.x != 0 || threadIdx.x != 0) return;
@@ -116,7 +123,12 @@ __global__ void build_sched_kernel(unsigned int* sched, int tiles_m, int L) {
 }
 
 // the fused GRU cell of one warp (32 rows x 32 units of a 64-unit tile) and the token choice: shared by both kernel versions
-__device__ __forceinline__ void cell_epilogue(const DecodeParams& p, uint32_t tacc, int layer, int n, int row, int chalf, int cur, int nxt) {
+// `release_acc()` hands the accumulator back to the MMA issuer; it is called as soon as this warp's LAST TMEM load of the unit
+// has completed -- before the second half's gate math and global stores -- so that the next-but-one unit's MMAs do not wait
+// for this unit's stores (ncu: the tensor pipe was 48 % active with the epilogue warps 24 % of their time in release fences).
+template <typename F>
+__device__ __forceinline__ void cell_epilogue(const DecodeParams& p, uint32_t tacc, int layer, int n, int row, int chalf, int cur, int nxt,
+                                              F release_acc) {
   const int H = p.Hd, L = p.L;
   const int ldx = layer == 0 ? p.K0 : 2 * H, hoff = layer == 0 ? p.K0 - H : H;
   const float* hprev = p.hm[layer][cur];
@@ -133,10 +145,19 @@ __device__ __forceinline__ void cell_epilogue(const DecodeParams& p, uint32_t ta
     ptx::tmem_ld_32x16(tacc + 2 * 64 + ul, ai);
     ptx::tmem_ld_32x16(tacc + 3 * 64 + ul, ah);
     ptx::tmem_ld_wait();
+    if (half == 1) release_acc();
     const float* bias = p.bcat[layer] + (long long)n * BN_CELL + ul;   // permuted like the weights: [gate][64]
+    float bg[4][16];                                                     // the 16 biases of each gate block as 16-byte loads
+#pragma unroll
+    for (int g = 0; g < 4; ++g)
+#pragma unroll
+      for (int k4 = 0; k4 < 4; ++k4) {
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + g * 64) + k4);
+        bg[g][4 * k4] = b4.x; bg[g][4 * k4 + 1] = b4.y; bg[g][4 * k4 + 2] = b4.z; bg[g][4 * k4 + 3] = b4.w;
+      }
     float gn[16];
 #pragma unroll
-    for (int k = 0; k < 16; ++k) gn[k] = __uint_as_float(ai[k]) + __ldg(bias + 2 * 64 + k);
+    for (int k = 0; k < 16; ++k) gn[k] = __uint_as_float(ai[k]) + bg[2][k];
     const float* hp = hprev + (long long)row * H + u;
     float hn[16];
 #pragma unroll
@@ -146,9 +167,9 @@ __device__ __forceinline__ void cell_epilogue(const DecodeParams& p, uint32_t ta
 #pragma unroll
       for (int k2 = 0; k2 < 4; ++k2) {
         const int k = 4 * k4 + k2;
-        const float r = sigmoid_fast(0.f + __uint_as_float(ar[k]) + __ldg(bias + k));
-        const float z = sigmoid_fast(0.f + __uint_as_float(az[k]) + __ldg(bias + 64 + k));
-        const float ghn = __uint_as_float(ah[k]) + __ldg(bias + 3 * 64 + k);
+        const float r = sigmoid_fast(0.f + __uint_as_float(ar[k]) + bg[0][k]);
+        const float z = sigmoid_fast(0.f + __uint_as_float(az[k]) + bg[1][k]);
+        const float ghn = __uint_as_float(ah[k]) + bg[3][k];
         const float nn = tanh_fast(fmaf(r, ghn, gn[k]));
         hn[k] = fmaf(z, hv[k2] - nn, nn);
       }
@@ -174,11 +195,13 @@ __device__ __forceinline__ void cell_epilogue(const DecodeParams& p, uint32_t ta
     }
   }
 }
-__device__ __forceinline__ void head_epilogue(const DecodeParams& p, uint32_t tacc, int row, int i, int nxt) {
+template <typename F>
+__device__ __forceinline__ void head_epilogue(const DecodeParams& p, uint32_t tacc, int row, int i, int nxt, F release_acc) {
   uint32_t r0[32], r1[32];
   ptx::tmem_ld_32x32(tacc, r0);
   ptx::tmem_ld_32x32(tacc + 32, r1);
   ptx::tmem_ld_wait();
+  release_acc();
   if (row >= p.B) return;
   float v[64];
 #pragma unroll
@@ -251,7 +274,7 @@ decode_persist_kernel(const __grid_constant__ DecodeMaps maps, const DecodeParam
     }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(&tfull_bar[a], 1);
-      ptx::mbar_init(&tempty_bar[a], NUM_EPI_WARPS * 32);
+      ptx::mbar_init(&tempty_bar[a], NUM_EPI_WARPS);
     }
     ptx::fence_mbar_init();
   }
@@ -355,12 +378,18 @@ decode_persist_kernel(const __grid_constant__ DecodeMaps maps, const DecodeParam
       ptx::tc_fence_after();
       const int row = m * BM + q * 32 + lane;
       const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN_CELL;
-      if (!head) cell_epilogue(p, tacc, layer, n, row, chalf, cur, nxt);
-      else if (chalf == 0) head_epilogue(p, tacc, row, i, nxt);
-      ptx::tc_fence_before();
-      ptx::mbar_arrive(&tempty_bar[acc]);
+      auto release_acc = [&]() {     // this warp has read its part of accumulator `acc` out of TMEM
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) arrive_relaxed_local(&tempty_bar[acc]);
+      };
+      if (!head) cell_epilogue(p, tacc, layer, n, row, chalf, cur, nxt, release_acc);
+      else if (chalf == 0) head_epilogue(p, tacc, row, i, nxt, release_acc);
+      else release_acc();
       if (++acc == 2) { acc = 0; acc_ph ^= 1; }
-      // publish: this warp's stores of the unit are ordered before the counter increment (warp barrier + release)
+      // publish: this warp's stores of the unit are ordered before the counter increment (warp barrier + release).  (Deferring
+      // this into the next unit's epilogue, where the fence would find the stores long completed, was measured slower:
+      // 771 k -> 749 k SMILES/s -- the units that wait for the counter wait longer than the fence costs.)
       __syncwarp();
       if (lane == 0)
         asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p.counters + layer * tm + m), "r"(1u) : "memory");
@@ -400,9 +429,6 @@ __device__ __forceinline__ uint32_t mapa(uint32_t local_smem_addr, uint32_t rank
   uint32_t r;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(rank));
   return r;
-}
-__device__ __forceinline__ void remote_arrive(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ void tma_load_3d_2sm(void* smem_dst, const CUtensorMap* m, uint32_t bar_cluster_addr, int c0, int c1, int c2) {
   asm volatile(
@@ -581,14 +607,17 @@ decode_persist2_kernel(const __grid_constant__ DecodeMaps2 maps, const DecodePar
       ptx::tc_fence_after();
       const int row = m * 2 * BM + (int)rank * BM + q * 32 + lane;
       const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN_CELL;
-      if (!head) cell_epilogue(p, tacc, layer, n, row, chalf, cur, nxt);
-      else if (chalf == 0) head_epilogue(p, tacc, row, i, nxt);
-      ptx::tc_fence_before();
+      auto release_acc = [&]() {     // this warp has read its part of accumulator `acc` out of TMEM -> pair leader's MMA thread
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) remote_arrive_relaxed(tempty_leader + (uint32_t)(acc * 8));
+      };
+      if (!head) cell_epilogue(p, tacc, layer, n, row, chalf, cur, nxt, release_acc);
+      else if (chalf == 0) head_epilogue(p, tacc, row, i, nxt, release_acc);
+      else release_acc();
       __syncwarp();
-      if (lane == 0) {
-        remote_arrive(tempty_leader + (uint32_t)(acc * 8));   // this warp drained accumulator `acc` -> pair leader's MMA thread
+      if (lane == 0)
         asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p.counters + layer * tm2 + m), "r"(1u) : "memory");
-      }
       if (++acc == 2) { acc = 0; acc_ph ^= 1; }
     }
   }
