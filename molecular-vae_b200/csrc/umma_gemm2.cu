@@ -12,6 +12,7 @@
 // packed bf16 stores), two accumulators in TMEM, persistent over the output tiles.
 #include "common.cuh"
 #include "umma_gemm.h"
+#include <stdlib.h>
 
 namespace {
 
@@ -28,6 +29,7 @@ struct Params2 {
   int splits, kb_per_split;        // split-K (fp32 output only)
   void* out; long long ldc; const float* bias; int out_rb; int out_bf16;
   int accumulate;                  // fp32 output, splits == 1: D += result (plain read-modify-write)
+  int late_release;                // A/B switch (MVAE_GEMM_EARLY_RELEASE=0): hand the accumulator back after the tile's stores
   int* err_flag;
 };
 
@@ -63,8 +65,9 @@ __device__ __forceinline__ uint32_t mapa(uint32_t local_smem_addr, uint32_t rank
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(rank));
   return r;
 }
-__device__ __forceinline__ void remote_arrive(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+// accumulator hand-back: the tcgen05 fences order the TMEM reads, no generic-proxy data rides on this arrive
+__device__ __forceinline__ void remote_arrive_relaxed(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ void tma_load_3d_2sm(void* smem_dst, const CUtensorMap* m, uint32_t bar_cluster_addr, int c0, int c1, int c2) {
   asm volatile(
@@ -220,12 +223,21 @@ umma_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const int row = m_blk * 2 * BM + (int)rank * BM + q * 32 + lane;
       const uint32_t tb = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + chalf * CH;
       uint32_t r0[32], r1[32];
+      // the accumulator goes back to the MMA issuer as soon as this warp's LAST TMEM load of the tile has completed, i.e. before
+      // the final chunk's global stores / atomics (a release arrive after them would wait for those stores)
+      auto release_now = [&]() {
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) remote_arrive_relaxed(tempty_leader + (uint32_t)(acc * 8));
+      };
+      auto release_acc = [&]() { if (!p.late_release) release_now(); };
       if (!p.out_bf16 && p.splits == 1) {
         // fp32 result of a whole-K unit: plain 16-byte stores (or read-modify-write when accumulating; nobody else owns the tile)
 #pragma unroll 1
         for (int c = 0; c < NCH; ++c) {
           ptx::tmem_ld_32x32(tb + c * 32, r0);
           ptx::tmem_ld_wait();
+          if (c == NCH - 1) release_acc();
           const int col0 = n_blk * BN + chalf * CH + c * 32;
           float* o = reinterpret_cast<float*>(p.out) + (long long)row * p.ldc + col0;
 #pragma unroll
@@ -242,9 +254,7 @@ umma_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             *reinterpret_cast<float4*>(o + j) = w;
           }
         }
-        ptx::tc_fence_before();
-        __syncwarp();
-        if (lane == 0) remote_arrive(tempty_leader + (uint32_t)(acc * 8));
+        if (p.late_release) release_now();
         if (++acc == 2) { acc = 0; acc_ph ^= 1; }
         continue;
       }
@@ -254,15 +264,14 @@ umma_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         for (int c = 0; c < NCH; ++c) {
           ptx::tmem_ld_32x32(tb + c * 32, r0);
           ptx::tmem_ld_wait();
+          if (c == NCH - 1) release_acc();
           float* o = reinterpret_cast<float*>(p.out) + (long long)row * p.ldc + n_blk * BN + chalf * CH + c * 32;
           const bool add_bias = p.bias != nullptr && split == 0;
 #pragma unroll
           for (int j = 0; j < 32; ++j)
             atomicAdd(o + j, __uint_as_float(r0[j]) + (add_bias ? __ldg(p.bias + n_blk * BN + chalf * CH + c * 32 + j) : 0.f));
         }
-        ptx::tc_fence_before();
-        __syncwarp();
-        if (lane == 0) remote_arrive(tempty_leader + (uint32_t)(acc * 8));
+        if (p.late_release) release_now();
         if (++acc == 2) { acc = 0; acc_ph ^= 1; }
         continue;
       }
@@ -296,16 +305,16 @@ umma_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       for (int c = 0; c < NCH; c += 2) {
         ptx::tmem_ld_wait();
         if (c + 1 < NCH) ptx::tmem_ld_32x32(tb + (c + 1) * 32, r1);
+        else release_acc();
         process(r0, c);
         if (c + 1 < NCH) {
           ptx::tmem_ld_wait();
           if (c + 2 < NCH) ptx::tmem_ld_32x32(tb + (c + 2) * 32, r0);
+          else release_acc();
           process(r1, c + 1);
         }
       }
-      ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) remote_arrive(tempty_leader + (uint32_t)(acc * 8));
+      if (p.late_release) release_now();
       if (++acc == 2) { acc = 0; acc_ph ^= 1; }
     }
   }
@@ -396,6 +405,7 @@ int mvae_umma_gemm_pairs(const mvae_umma_operand* A, const mvae_umma_operand* B,
   p.kb_per_split = (kb_total + splits - 1) / splits;
   p.splits = (kb_total + p.kb_per_split - 1) / p.kb_per_split;
   p.out = D->ptr; p.ldc = D->ld; p.bias = D->bias; p.out_rb = D->rb; p.out_bf16 = D->bf16; p.accumulate = D->accumulate; p.err_flag = err_flag;
+  { const char* e = getenv("MVAE_GEMM_EARLY_RELEASE"); p.late_release = (e && atoi(e) == 0) ? 1 : 0; }
   int dev = 0, sms = 0;
   MVAE_CUDA_CHECK(cudaGetDevice(&dev));
   MVAE_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
