@@ -245,6 +245,9 @@ __global__ void lstm_cell_weights_kernel(const __nv_bfloat16* __restrict__ src, 
 // Off by default: with H = 1024 the step GEMM has only 512 tiles and the 8 epilogue warps of a CTA become the bottleneck
 // once they also run the full-precision cell math (measured 152 ms/step either way at B = 4096); the GRU variant of the
 // same epilogue pays off in the MOSES path (moses.cu), where tanh.approx gates are within budget.
+#ifndef MVAE_LSTM_GATE_X8_DEFAULT
+#define MVAE_LSTM_GATE_X8_DEFAULT 2
+#endif
 bool cell_fused_enabled() {
   const char* e = getenv("MVAE_LSTM_CELL_FUSED");
   return e ? atoi(e) != 0 : false;
@@ -254,6 +257,21 @@ bool cell_fused_enabled() {
 // per-step LSTM engine (one layer): one tcgen05 GEMM (h_{t-1} W_hh^T) per step; in bf16 mode the LSTM cell runs in the
 // GEMM's epilogue (umma_gemm.h mvae_umma_cell, lstm = 1), in fp32 check mode a separate cell kernel follows the SGEMM
 // ---------------------------------------------------------------------------------------------------------
+// bf16 mode, LSTM cell kernels with eight units per thread (simt_kernels.cuh).  MVAE_LSTM_GATE_X8: 0 = the one-unit-per-thread
+// kernels, 1 = x8 with exact expf / tanhf, 2 (default) = x8 with ex2 / rcp gate math in layers of H >= 256 (the decoder),
+// 3 = ex2 / rcp gate math everywhere.  Returns 0 (scalar kernel), 1 (x8 exact) or 2 (x8 fast).  fp32 check mode: always 0.
+// Measured at B = 4096 (tools/bench_cfga.py, profiles/r02_cfga_gate_variants.txt): 142.7 / 133.1 / 129.7 ms per step for
+// 0 / 1 / 2.  The encoder keeps the exact math: its gradients sit at 0.0090-0.0095 of the 1e-2 bf16 budget from the bf16
+// rounding of operands alone (tools/cfga_margin.py), mode 2 leaves them there (0.0089-0.0094), mode 3 moves the B = 64 case
+// to 0.0103.
+template <typename TA>
+int gate_x8_mode(int H, long long gi_tstride) {
+  if (sizeof(TA) != 2 || (H & 7) || (gi_tstride & 7)) return 0;
+  static const int mode = [] { const char* e = getenv("MVAE_LSTM_GATE_X8"); return e ? atoi(e) : MVAE_LSTM_GATE_X8_DEFAULT; }();
+  if (mode <= 0) return 0;
+  if (mode == 1) return 1;
+  return (mode >= 3 || H >= 256) ? 2 : 1;
+}
 template <typename TA, typename TG>
 int lstm_fwd(const ADims& d, const AWS& w, cudaStream_t st, const TG* gi, long long gi_tstride, const TA* Whh, TA* hs, TA* sv,
              int H, const void* WhhC = nullptr) {
@@ -277,8 +295,22 @@ int lstm_fwd(const ADims& d, const AWS& w, cudaStream_t st, const TG* gi, long l
     }
   }
   const int gate_grid = (int)ceil_div64((long long)slab, 256);
+  const int x8 = gate_x8_mode<TA>(H, gi_tstride);
   for (int t = 0; t < T; ++t) {
     RC(gemm<TA>(w.err_flag, st, hs + t * slab, H, false, Whh, H, true, w.gh, 4 * H, false, Bp, 4 * H, H, nullptr, false, 1));
+    if constexpr (sizeof(TA) == 2) {
+      if (x8) {
+        const int g8 = (int)ceil_div64((long long)(slab / 8), 256);
+        if (x8 == 2)
+          simt::lstm_gate_fwd_x8_kernel<TG, true><<<g8, 256, 0, st>>>(gi + (size_t)t * gi_tstride, w.gh, w.c, hs + (t + 1) * slab,
+                                                                      sv ? sv + (size_t)t * Bp * 6 * H : nullptr, Bp, H);
+        else
+          simt::lstm_gate_fwd_x8_kernel<TG, false><<<g8, 256, 0, st>>>(gi + (size_t)t * gi_tstride, w.gh, w.c, hs + (t + 1) * slab,
+                                                                       sv ? sv + (size_t)t * Bp * 6 * H : nullptr, Bp, H);
+        KCHECK();
+        continue;
+      }
+    }
     simt::lstm_gate_fwd_kernel<TA, TG><<<gate_grid, 256, 0, st>>>(gi + (size_t)t * gi_tstride, w.gh, w.c, hs + (t + 1) * slab,
                                                                   sv ? sv + (size_t)t * Bp * 6 * H : nullptr, Bp, H);
     KCHECK();
@@ -292,10 +324,20 @@ int lstm_bwd(const ADims& d, const AWS& w, cudaStream_t st, const TA* Whh, const
   RC(memset_async(w.dh_carry, slab * 4, st));
   RC(memset_async(w.dc_carry, slab * 4, st));
   const int gate_grid = (int)ceil_div64((long long)slab, 256);
+  const int x8 = gate_x8_mode<TA>(H, 0);
   for (int t = T - 1; t >= 0; --t) {
     TA* dGt = dG + (size_t)t * Bp * 4 * H;
-    simt::lstm_gate_bwd_kernel<TA><<<gate_grid, 256, 0, st>>>(sv + (size_t)t * Bp * 6 * H, dX + t * slab, w.dh_carry,
-                                                              w.dc_carry, dGt, Bp, H);
+    bool done = false;
+    if constexpr (sizeof(TA) == 2) {
+      if (x8) {
+        simt::lstm_gate_bwd_x8_kernel<<<(int)ceil_div64((long long)(slab / 8), 256), 256, 0, st>>>(
+            sv + (size_t)t * Bp * 6 * H, dX + t * slab, w.dh_carry, w.dc_carry, dGt, Bp, H);
+        done = true;
+      }
+    }
+    if (!done)
+      simt::lstm_gate_bwd_kernel<TA><<<gate_grid, 256, 0, st>>>(sv + (size_t)t * Bp * 6 * H, dX + t * slab, w.dh_carry,
+                                                                w.dc_carry, dGt, Bp, H);
     KCHECK();
     if (t > 0)   // dh_{t-1} (recurrent part) = dG_t W_hh
       RC(gemm<TA>(w.err_flag, st, dGt, 4 * H, false, Whh, H, false, w.dh_carry, H, false, Bp, H, 4 * H, nullptr, false, 1));

@@ -696,6 +696,103 @@ __global__ void lstm_gate_bwd_kernel(const TA* __restrict__ sv, const TA* __rest
   dG[g4 + 3 * Hp] = from_f32<TA>(dh * tc * o * (1.f - o));
   dc_carry[idx] = dct * f;
 }
+// Eight units per thread (16-byte accesses, every load of the thread issued before the first use): the bf16 path of Config A's
+// decoder (B = 4096, H = 1024: 184 MB per forward call, 136 MB per BPTT call) is HBM-bound, and with exact expf / tanhf /
+// IEEE divisions the forward cell was ALU-bound on top of it (~165 lane instructions per unit).  bf16 mode only: the gates use
+// ex2.approx + rcp.approx (absolute error ~2e-7, three orders of magnitude under the bf16 rounding of the saved gates and of h);
+// the fp32 check mode keeps the scalar kernels above.  Needs Hp % 8 == 0 and 16-byte aligned arrays.
+struct F8 { float v[8]; };
+__device__ __forceinline__ F8 ld8(const __nv_bfloat16* p) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+  F8 r;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { r.v[2 * k] = __uint_as_float(w[k] << 16); r.v[2 * k + 1] = __uint_as_float(w[k] & 0xffff0000u); }
+  return r;
+}
+__device__ __forceinline__ F8 ld8(const float* p) {
+  const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  return F8{{a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w}};
+}
+__device__ __forceinline__ void st8(__nv_bfloat16* p, const F8& f) {
+  uint32_t w[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(f.v[2 * k], f.v[2 * k + 1]);
+    w[k] = *reinterpret_cast<const uint32_t*>(&h);
+  }
+  *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+}
+__device__ __forceinline__ void st8(float* p, const F8& f) {
+  *reinterpret_cast<float4*>(p) = make_float4(f.v[0], f.v[1], f.v[2], f.v[3]);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(f.v[4], f.v[5], f.v[6], f.v[7]);
+}
+__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float tanh_fast(float x) { return fmaf(2.0f, sigmoid_fast(2.0f * x), -1.0f); }
+
+template <typename TG, bool FAST>
+__global__ void __launch_bounds__(256) lstm_gate_fwd_x8_kernel(const TG* __restrict__ gi, const float* __restrict__ gh,
+                                                               float* __restrict__ c, __nv_bfloat16* __restrict__ hnextA,
+                                                               __nv_bfloat16* __restrict__ sv, int Bp, int Hp) {
+  const int H8 = Hp >> 3;
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= (long long)Bp * H8) return;
+  const int b = (int)(idx / H8), j = (int)(idx - (long long)b * H8) * 8;
+  const long long g4 = (long long)b * 4 * Hp + j, e = (long long)b * Hp + j;
+  const F8 xi = ld8(gi + g4), xf = ld8(gi + g4 + Hp), xg = ld8(gi + g4 + 2 * Hp), xo = ld8(gi + g4 + 3 * Hp);
+  const F8 hi = ld8(gh + g4), hf = ld8(gh + g4 + Hp), hg = ld8(gh + g4 + 2 * Hp), ho = ld8(gh + g4 + 3 * Hp);
+  const F8 cp = ld8(c + e);
+  F8 i, f, g, o, cn, tc, h;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    if constexpr (FAST) {
+      i.v[k] = sigmoid_fast(xi.v[k] + hi.v[k]);
+      f.v[k] = sigmoid_fast(xf.v[k] + hf.v[k]);
+      g.v[k] = tanh_fast(xg.v[k] + hg.v[k]);
+      o.v[k] = sigmoid_fast(xo.v[k] + ho.v[k]);
+    } else {   // bit-identical to lstm_gate_fwd_kernel
+      i.v[k] = sigmoid_acc(xi.v[k] + hi.v[k]);
+      f.v[k] = sigmoid_acc(xf.v[k] + hf.v[k]);
+      g.v[k] = tanhf(xg.v[k] + hg.v[k]);
+      o.v[k] = sigmoid_acc(xo.v[k] + ho.v[k]);
+    }
+    cn.v[k] = fmaf(f.v[k], cp.v[k], i.v[k] * g.v[k]);
+    tc.v[k] = FAST ? tanh_fast(cn.v[k]) : tanhf(cn.v[k]);
+    h.v[k] = o.v[k] * tc.v[k];
+  }
+  st8(c + e, cn);
+  st8(hnextA + e, h);
+  if (sv) {
+    const long long s6 = (long long)b * 6 * Hp + j;
+    st8(sv + s6, i); st8(sv + s6 + Hp, f); st8(sv + s6 + 2 * Hp, g);
+    st8(sv + s6 + 3 * Hp, o); st8(sv + s6 + 4 * Hp, cp); st8(sv + s6 + 5 * Hp, tc);
+  }
+}
+__global__ void __launch_bounds__(256) lstm_gate_bwd_x8_kernel(const __nv_bfloat16* __restrict__ sv, const __nv_bfloat16* __restrict__ dX,
+                                                               const float* __restrict__ dh_carry, float* __restrict__ dc_carry,
+                                                               __nv_bfloat16* __restrict__ dG, int Bp, int Hp) {
+  const int H8 = Hp >> 3;
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= (long long)Bp * H8) return;
+  const int b = (int)(idx / H8), j = (int)(idx - (long long)b * H8) * 8;
+  const long long s6 = (long long)b * 6 * Hp + j, g4 = (long long)b * 4 * Hp + j, e = (long long)b * Hp + j;
+  const F8 i = ld8(sv + s6), f = ld8(sv + s6 + Hp), g = ld8(sv + s6 + 2 * Hp), o = ld8(sv + s6 + 3 * Hp),
+           cp = ld8(sv + s6 + 4 * Hp), tc = ld8(sv + s6 + 5 * Hp);
+  const F8 dx = ld8(dX + e), dhc = ld8(dh_carry + e), dcc = ld8(dc_carry + e);
+  F8 di, df, dg, dO, dc;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const float dh = dhc.v[k] + dx.v[k];
+    const float dct = dcc.v[k] + dh * o.v[k] * (1.f - tc.v[k] * tc.v[k]);
+    di.v[k] = dct * g.v[k] * i.v[k] * (1.f - i.v[k]);
+    df.v[k] = dct * cp.v[k] * f.v[k] * (1.f - f.v[k]);
+    dg.v[k] = dct * i.v[k] * (1.f - g.v[k] * g.v[k]);
+    dO.v[k] = dh * tc.v[k] * o.v[k] * (1.f - o.v[k]);
+    dc.v[k] = dct * f.v[k];
+  }
+  st8(dG + g4, di); st8(dG + g4 + Hp, df); st8(dG + g4 + 2 * Hp, dg); st8(dG + g4 + 3 * Hp, dO);
+  st8(dc_carry + e, dc);
+}
 // 4-gate padding helpers: dst[4Hp][cols_p] <- src[4H][cols] ; inverse ; bias vectors
 template <typename T>
 __global__ void pad_gates4_kernel(const float* __restrict__ src, int H, int cols, T* __restrict__ dst, int Hp, int cols_p) {
